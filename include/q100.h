@@ -1,0 +1,149 @@
+/*
+ * q100.h -- C ABI of libq100.so: sm_100a kernels for the group-wise quantized-linear
+ * hot path of SilviaUvA/LLaMA3-Quantization.
+ *
+ * The reference has no FFI / plugin interface for this path: it is pure PyTorch and the
+ * module boundary (quant/quantizer.py, quant/int_linear.py, quant/int_matmul.py) *is*
+ * the interface.  Each entry point below names the reference code it replaces; the
+ * Python drop-in modules in llama3-quantization_b200/quant/ bind them with ctypes
+ * (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (torch tensors); the
+ *     library allocates nothing that outlives a call except an internal cache of TMA
+ *     descriptors;
+ *   - `stream` is a cudaStream_t / CUstream passed as void*; kernels are enqueued on
+ *     it with no host synchronisation;
+ *   - return value 0 == success, otherwise a Q100_E* code; q100_last_error() returns
+ *     a thread-local human readable message.  No exceptions cross the ABI;
+ *   - dtype codes: 0 = fp16, 1 = bf16, 2 = fp32.  Scales / zero-points / LWC
+ *     multipliers are stored in the same dtype as the tensor they belong to, exactly
+ *     like the reference's `scale` / `round_zero_point` (quant/quantizer.py:149-159).
+ *   - there is no CPU path: every compute entry point fails with Q100_ENODEVICE when
+ *     no sm_100 device is present.
+ */
+#ifndef Q100_H_
+#define Q100_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library itself is built with -fvisibility=hidden */
+#endif
+
+#define Q100_ABI_VERSION 1
+
+enum q100_dtype { Q100_F16 = 0, Q100_BF16 = 1, Q100_F32 = 2 };
+
+enum q100_status {
+  Q100_OK = 0,
+  Q100_EINVAL = 1,      /* bad shape / dtype / flag combination                   */
+  Q100_EUNSUPPORTED = 2,/* valid for the reference, not implemented by a kernel   */
+  Q100_ECUDA = 3,       /* a CUDA runtime / driver call failed (see last_error)   */
+  Q100_ENODEVICE = 4,   /* no CUDA device, or device is not sm_100                */
+  Q100_EWORKSPACE = 5   /* workspace too small (see q100_gemm_workspace_bytes)    */
+};
+
+/* flags for the quantize entry points */
+#define Q100_FLAG_IEEE_DIV    0x1  /* f16/bf16: use div.rn.f32 for x/scale instead of the
+                                      rcp + 2-FMA exact-for-16-bit sequence (same bits, slower) */
+#define Q100_FLAG_SCALAR_MATH 0x2  /* f16/bf16: per-element fp32 math instead of packed half2 ops */
+/* flags for the GEMM entry points */
+#define Q100_GEMM_FORCE_SKINNY 0x1 /* always use the mma.sync weight-streaming kernel  */
+#define Q100_GEMM_FORCE_TC     0x2 /* always use the tcgen05 kernel                    */
+
+const char* q100_last_error(void);
+int q100_abi_version(void);
+/* 0 if device `dev` exists and is compute capability 10.x, else Q100_ENODEVICE. */
+int q100_device_ok(int dev);
+
+/*
+ * K1/K2 -- UniformAffineQuantizer.forward for a 2-D view [rows, cols] (contiguous).
+ * Replaces per_token_dynamic_calibration + fake_quant, quant/quantizer.py:94-159
+ * (17 eager elementwise/reduction launches) with one pass.
+ *
+ *   group       quantisation group along cols (quantizer.py:135 reshape(-1, g));
+ *               0 = one group per row (group_size=None: per-channel weights,
+ *               per-token activations).  cols % group must be 0 (the reference's
+ *               LWC zero-padding for K % g != 0, quantizer.py:136-139, is done by
+ *               the caller).
+ *   n_bits      2..8 (packed output) or 2..15 (dequant output only)
+ *   symmetric / disable_zp   quantizer.py:146-159
+ *   lwc_up/lwc_low   nullable; POST-sigmoid multipliers [rows*cols/group] in `dtype`
+ *               (quantizer.py:143-145; torch computes the sigmoid)
+ *   dequant_out nullable; [rows, cols] in `dtype`      == forward()'s return value
+ *   packed_out  nullable; uint32 [rows, q100_packed_words_per_row(cols, n_bits)]
+ *   scales_out  nullable; [rows*cols/group] in `dtype` == self.scale
+ *   zeros_out   nullable; [rows*cols/group] in `dtype` == self.round_zero_point
+ *               (ignored when disable_zp)
+ *   meta_out    nullable; packed-weight side band for the GEMM kernels: interleaved
+ *               (scale, zero) pairs in `dtype`, TRANSPOSED to [cols/group, rows, 2]
+ *               so one K-group of consecutive rows is contiguous.  fp16/bf16 only.
+ */
+int q100_quantize_groupwise(const void* x, int dtype, int64_t rows, int64_t cols, int group,
+                            int n_bits, int symmetric, int disable_zp,
+                            const void* lwc_up, const void* lwc_low,
+                            void* dequant_out, void* packed_out,
+                            void* scales_out, void* zeros_out, void* meta_out,
+                            int flags, void* stream);
+
+/*
+ * K2 -- per-token activation fake-quant (asymmetric, one group per row), the
+ * act_quantizer / x1_quantizer / x2_quantizer call of quant/int_linear.py:59-60 and
+ * quant/int_matmul.py:31-39.  Thin alias of q100_quantize_groupwise(group = 0).
+ */
+int q100_fakequant_rows(const void* x, int dtype, int64_t rows, int64_t cols, int n_bits,
+                        void* out, void* scales_out, void* zeros_out, int flags, void* stream);
+
+/* uint32 words per packed row (q100 v1 layout, see DESIGN.md "Packed layout"). */
+int64_t q100_packed_words_per_row(int64_t cols, int n_bits);
+
+/*
+ * Expand packed codes back to a dense tensor in `dtype`:
+ *   out[r, c] = ((code - zero) * scale) with the reference's per-op rounding
+ *   (quant/quantizer.py:107-110), or the raw integer code when scales == NULL.
+ * scales/zeros use the reference layout [rows*cols/group].
+ */
+int q100_dequantize(const void* packed, const void* scales, const void* zeros, int dtype,
+                    int64_t rows, int64_t cols, int group, int n_bits, int disable_zp,
+                    void* out, void* stream);
+
+/*
+ * K3 -- fused dequant-GEMM  y[M, N] = x[M, K] . dequant(W)[N, K]^T (+ bias[N]).
+ * Replaces F.linear on the fp16 fake-quantised weight, quant/int_linear.py:62, reading
+ * n_bits/8 bytes per weight instead of 2.
+ *
+ *   x, y, bias  `dtype` (fp16 or bf16), row-major, bias nullable
+ *   packed      uint32 [N, words_per_row(K, n_bits)]   (from q100_quantize_groupwise)
+ *   meta        [K/group, N, 2] (scale, zero) pairs in `dtype` (meta_out above)
+ *   group       quantisation group along K (multiple of 64; 0 = K)
+ *   workspace   device scratch of at least q100_gemm_workspace_bytes(...) bytes, zero
+ *               filled once by the caller before first use (the kernels leave it
+ *               zeroed); may be NULL when that function returns 0
+ */
+int q100_gemm_wna16(const void* x, const void* packed, const void* meta, const void* bias,
+                    void* y, int64_t M, int64_t N, int64_t K, int group, int n_bits,
+                    int disable_zp, int dtype, void* workspace, size_t workspace_bytes,
+                    int flags, void* stream);
+
+size_t q100_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int n_bits, int flags);
+
+/*
+ * Development / verification hooks (used by tests only).
+ * q100_selftest_div: exhaustively compares the fast 16-bit division sequence with
+ * div.rn.f32 + round over all (x, scale) pairs of `dtype` with scale in [1e-5, 1e4];
+ * writes the mismatch count to *mismatches_out (device uint64).
+ */
+int q100_selftest_div(int dtype, void* mismatches_out, void* stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* Q100_H_ */

@@ -1,0 +1,103 @@
+// q100_gemm.cu -- C-ABI front of the fused dequant-GEMM (K3): argument checks, path choice
+// (weight-streaming mma.sync kernel for decode shapes, tcgen05 kernel for prefill shapes),
+// and the host-side TMA descriptor encoder.
+#include <mutex>
+
+#include <cudaTypedefs.h>
+
+#include "q100_common.cuh"
+#include "q100_ptx.cuh"
+
+namespace q100 {
+
+int gemm_skinny(const void* x, const void* packed, const void* meta, const void* bias, void* y,
+                int64_t M, int64_t N, int64_t K, int group, int n_bits, int disable_zp, int dtype,
+                void* workspace, size_t workspace_bytes, cudaStream_t st);
+size_t skinny_workspace_bytes(int64_t M, int64_t N, int64_t K);
+
+int gemm_tc(const void* x, const void* packed, const void* meta, const void* bias, void* y,
+            int64_t M, int64_t N, int64_t K, int group, int n_bits, int disable_zp, int dtype,
+            cudaStream_t st);
+bool gemm_tc_supported(int64_t M, int64_t N, int64_t K, int group, int n_bits);
+
+// ---------------------------------------------------------------- tensor maps
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+static std::once_flag g_encode_once;
+
+int make_tmap_2d(CUtensorMap* out, const void* base, int elem_bytes, uint64_t inner, uint64_t outer,
+                 uint64_t row_pitch_bytes, uint32_t box_inner, uint32_t box_outer, int swizzle_bytes) {
+  std::call_once(g_encode_once, []() {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPointByVersion("cuTensorMapEncodeTiled", &fn, 12000, cudaEnableDefault, &qres) ==
+            cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    else
+      cudaGetLastError();
+  });
+  Q100_REQUIRE(g_encode != nullptr, Q100_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
+  CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32
+                          : elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16
+                                            : CU_TENSOR_MAP_DATA_TYPE_UINT8;
+  CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                        : swizzle_bytes == 64  ? CU_TENSOR_MAP_SWIZZLE_64B
+                        : swizzle_bytes == 32  ? CU_TENSOR_MAP_SWIZZLE_32B
+                                               : CU_TENSOR_MAP_SWIZZLE_NONE;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_pitch_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(out, dt, 2, const_cast<void*>(base), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  Q100_REQUIRE(r == CUDA_SUCCESS, Q100_ECUDA,
+               "cuTensorMapEncodeTiled failed (%d): inner=%llu outer=%llu pitch=%llu box=%ux%u", (int)r,
+               (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)row_pitch_bytes,
+               box_inner, box_outer);
+  return Q100_OK;
+}
+
+}  // namespace q100
+
+using namespace q100;
+
+extern "C" size_t q100_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int n_bits, int flags) {
+  (void)n_bits; (void)flags;
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  const int64_t mm = M < 32 ? M : 32;
+  return skinny_workspace_bytes(mm, N, K);
+}
+
+extern "C" int q100_gemm_wna16(const void* x, const void* packed, const void* meta, const void* bias,
+                               void* y, int64_t M, int64_t N, int64_t K, int group, int n_bits,
+                               int disable_zp, int dtype, void* workspace, size_t workspace_bytes,
+                               int flags, void* stream) {
+  Q100_REQUIRE(x && packed && meta && y, Q100_EINVAL, "NULL pointer argument");
+  Q100_REQUIRE(dtype == Q100_F16 || dtype == Q100_BF16, Q100_EUNSUPPORTED,
+               "fused dequant-GEMM computes in fp16 or bf16 (got dtype %d)", dtype);
+  Q100_REQUIRE(n_bits == 2 || n_bits == 3 || n_bits == 4 || n_bits == 8, Q100_EUNSUPPORTED,
+               "n_bits in {2,3,4,8} (got %d)", n_bits);
+  Q100_REQUIRE(M >= 0 && N > 0 && K > 0, Q100_EINVAL, "bad shape M=%lld N=%lld K=%lld", (long long)M,
+               (long long)N, (long long)K);
+  if (M == 0) return Q100_OK;
+  int rc = ensure_device();
+  if (rc != Q100_OK) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool want_tc = (flags & Q100_GEMM_FORCE_TC) ||
+                       (!(flags & Q100_GEMM_FORCE_SKINNY) && M > 32 && gemm_tc_supported(M, N, K, group, n_bits));
+  if (want_tc) {
+    Q100_REQUIRE(gemm_tc_supported(M, N, K, group, n_bits), Q100_EUNSUPPORTED,
+                 "tcgen05 path does not support this shape/bit-width");
+    return gemm_tc(x, packed, meta, bias, y, M, N, K, group, n_bits, disable_zp, dtype, st);
+  }
+  // weight-streaming kernel, 32 rows of x per pass
+  const size_t esz = 2;
+  for (int64_t m0 = 0; m0 < M; m0 += 32) {
+    const int64_t mc = (M - m0) < 32 ? (M - m0) : 32;
+    rc = gemm_skinny(reinterpret_cast<const uint8_t*>(x) + m0 * K * esz, packed, meta, bias,
+                     reinterpret_cast<uint8_t*>(y) + m0 * N * esz, mc, N, K, group, n_bits, disable_zp,
+                     dtype, workspace, workspace_bytes, st);
+    if (rc != Q100_OK) return rc;
+  }
+  return Q100_OK;
+}

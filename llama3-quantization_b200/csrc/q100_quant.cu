@@ -1,0 +1,679 @@
+// q100_quant.cu -- K1 (group-wise) and K2 (row-wise) fake-quantize / pack kernels.
+//
+// One pass over the tensor replaces the reference's per_token_dynamic_calibration +
+// fake_quant (quant/quantizer.py:94-159): per-group min/max -> scale / zero-point ->
+// round / clamp -> dequant, emitting any of {dequantised tensor, packed codes, scales,
+// zeros, transposed (scale, zero) side band}.  HBM-bound: every input byte is read once
+// with 128-bit streaming loads, every output byte written once.
+//
+// Bit-exactness contract: the reference executes each elementwise op in
+// the storage dtype; torch computes in fp32 and rounds to the storage dtype after every
+// op.  Two equivalent implementations live here:
+//   MATH_SCALAR : literal restatement, fp32 op + round-trip through T after each op.
+//   MATH_PACKED : (fp16/bf16 only) native packed half2/bfloat162 add/sub/mul, which are
+//                 correctly rounded and therefore equal to "fp32 op then round" (double
+//                 rounding is innocuous because 24 >= 2*11 + 2); division uses
+//                 q = x*rcp(s); q += fma(-q, s, x)*rcp(s), which rounds to the same
+//                 16-bit value as div.rn.f32 (checked exhaustively by q100_selftest_div).
+// Compile this file with -fmad=false: no implicit contraction may merge the per-op steps.
+#include "q100_common.cuh"
+
+namespace q100 {
+
+enum { MATH_PACKED = 0, MATH_SCALAR = 1, MATH_SCALAR_IEEE = 2 };
+
+struct QuantArgs {
+  const void* x;
+  void* deq;
+  uint32_t* packed;
+  void* scales;
+  void* zeros;
+  void* meta;
+  const void* lwc_up;
+  const void* lwc_low;
+  int64_t rows, cols, n_groups;
+  int group;            // elements per group
+  int groups_per_row;
+  int n_bits;
+  int symmetric;
+  int has_zp;
+  float qmin, qmax;     // reference code range (quantizer.py:46-51)
+  float denom;          // 2^n - 1 (asymmetric) or 2^(n-1) - 1 (symmetric)
+  int words_per_row;
+  int plane1_off;       // W3: word offset of the 1-bit plane inside a packed row
+};
+
+// ------------------------------------------------------------------ per-group parameters
+template <typename T>
+struct GroupQ {
+  float scale, zp, rcp;
+};
+
+// quantizer.py:143-159.  xmin/xmax are exact values of T.
+template <typename T>
+__device__ __forceinline__ GroupQ<T> group_params(float xmin, float xmax, const QuantArgs& a,
+                                                  int64_t g) {
+  using D = DT<T>;
+  if (a.lwc_up != nullptr) {
+    const float up = D::to_f(reinterpret_cast<const T*>(a.lwc_up)[g]);
+    const float low = D::to_f(reinterpret_cast<const T*>(a.lwc_low)[g]);
+    xmax = D::rd(up * xmax);
+    xmin = D::rd(low * xmin);
+  }
+  GroupQ<T> q;
+  if (a.symmetric) {
+    const float am = max_nan(fabsf(xmax), fabsf(xmin));
+    float s = D::rd(__fdiv_rn(am, a.denom));
+    q.scale = D::rd(clamp_nan(s, 1e-5f, 1e4f));
+    q.zp = D::rd(a.denom);
+  } else {
+    const float rng = D::rd(xmax - xmin);
+    float s = D::rd(__fdiv_rn(rng, a.denom));
+    q.scale = D::rd(clamp_nan(s, 1e-5f, 1e4f));
+    q.zp = D::rd(__fdiv_rn(D::rd(-xmin), q.scale));
+  }
+  q.zp = a.has_zp ? rintf(D::rd(clamp_nan(q.zp, -1e4f, 1e4f))) : 0.0f;
+  q.rcp = __frcp_rn(q.scale);
+  return q;
+}
+
+// x / s rounded like div.rn.f32 as far as a 16-bit result can tell (see file header).
+template <int MATH>
+__device__ __forceinline__ float div_x_s(float x, float s, float rcp) {
+  if (MATH == MATH_SCALAR_IEEE) return __fdiv_rn(x, s);
+  float q = x * rcp;
+  const float r = fmaf(-q, s, x);
+  return fmaf(r, rcp, q);
+}
+
+// ------------------------------------------------------------------ one 16-byte vector
+// Returns the dequantised vector; pairs[j] = code[2j] | code[2j+1] << 16 (unsigned codes,
+// i.e. x_int - qmin) for the packers.
+template <typename T, int MATH>
+struct VecQuant;
+
+// literal fp32 restatement, any T
+template <typename T, int MATH>
+__device__ __forceinline__ float quant_scalar(float x, const GroupQ<T>& q, const QuantArgs& a,
+                                              uint32_t& code) {
+  using D = DT<T>;
+  const float v = D::rd(div_x_s<(DT<T>::kCode == Q100_F32) ? MATH_SCALAR_IEEE : MATH>(x, q.scale, q.rcp));
+  float xi = D::rd(D::rd(rintf(v) - v) + v);            // round_ste forward value, quantizer.py:19
+  if (a.has_zp) xi = D::rd(xi + q.zp);
+  const float c = clamp_nan(xi, a.qmin, a.qmax);
+  code = static_cast<uint32_t>(__float2int_rn(c - a.qmin));   // NaN -> 0
+  const float d = a.has_zp ? D::rd(c - q.zp) : c;
+  return D::rd(d * q.scale);
+}
+
+template <int MATH>
+struct VecQuant<float, MATH> {
+  static constexpr int E = 4;
+  __device__ static __forceinline__ uint4 run(const uint4& in, const GroupQ<float>& q,
+                                              const QuantArgs& a, uint32_t (&pairs)[2]) {
+    uint32_t c0, c1, c2, c3;
+    uint4 o;
+    o.x = __float_as_uint(quant_scalar<float, MATH>(__uint_as_float(in.x), q, a, c0));
+    o.y = __float_as_uint(quant_scalar<float, MATH>(__uint_as_float(in.y), q, a, c1));
+    o.z = __float_as_uint(quant_scalar<float, MATH>(__uint_as_float(in.z), q, a, c2));
+    o.w = __float_as_uint(quant_scalar<float, MATH>(__uint_as_float(in.w), q, a, c3));
+    pairs[0] = c0 | (c1 << 16);
+    pairs[1] = c2 | (c3 << 16);
+    return o;
+  }
+};
+
+template <typename T>
+struct Packed16;
+template <>
+struct Packed16<__half> {
+  using T2 = __half2;
+  __device__ static __forceinline__ T2 bcast(float v) { return __float2half2_rn(v); }
+  __device__ static __forceinline__ T2 rint2(T2 v) { return h2rint(v); }
+};
+template <>
+struct Packed16<__nv_bfloat16> {
+  using T2 = __nv_bfloat162;
+  __device__ static __forceinline__ T2 bcast(float v) { return __float2bfloat162_rn(v); }
+  __device__ static __forceinline__ T2 rint2(T2 v) { return h2rint(v); }
+};
+
+template <typename T, int MATH>
+__device__ __forceinline__ uint32_t quant_pair(uint32_t in, const GroupQ<T>& q, const QuantArgs& a,
+                                               uint32_t& pair) {
+  using D = DT<T>;
+  if (MATH != MATH_PACKED) {
+    const float2 xf = D::to_f2(in);
+    uint32_t c0, c1;
+    const float d0 = quant_scalar<T, MATH>(xf.x, q, a, c0);
+    const float d1 = quant_scalar<T, MATH>(xf.y, q, a, c1);
+    pair = c0 | (c1 << 16);
+    return D::pack2(d0, d1);
+  } else {
+    using P = Packed16<T>;
+    using T2 = typename P::T2;
+    const float2 xf = D::to_f2(in);
+    const float q0 = div_x_s<MATH_PACKED>(xf.x, q.scale, q.rcp);
+    const float q1 = div_x_s<MATH_PACKED>(xf.y, q.scale, q.rcp);
+    uint32_t vb = D::pack2(q0, q1);                         // rd(x / scale), both lanes
+    const T2 v = *reinterpret_cast<T2*>(&vb);
+    // round_ste: rint(v) + (v - v): +0 for finite v (so -0 becomes +0), NaN for inf/NaN
+    T2 xi = __hadd2(P::rint2(v), __hsub2(v, v));
+    const T2 zp2 = P::bcast(q.zp);
+    if (a.has_zp) xi = __hadd2(xi, zp2);
+    const T2 c = __hmin2_nan(__hmax2_nan(xi, P::bcast(a.qmin)), P::bcast(a.qmax));
+    // unsigned codes through fp32 (exact: |c| <= 2^15)
+    uint32_t cb = *reinterpret_cast<const uint32_t*>(&c);
+    const float2 cf = D::to_f2(cb);
+    pair = static_cast<uint32_t>(__float2int_rn(cf.x - a.qmin)) |
+           (static_cast<uint32_t>(__float2int_rn(cf.y - a.qmin)) << 16);
+    T2 d = a.has_zp ? __hsub2(c, zp2) : c;
+    d = __hmul2(d, P::bcast(q.scale));
+    return *reinterpret_cast<uint32_t*>(&d);
+  }
+}
+
+template <typename T, int MATH>
+struct VecQuant {
+  static constexpr int E = 8;
+  __device__ static __forceinline__ uint4 run(const uint4& in, const GroupQ<T>& q,
+                                              const QuantArgs& a, uint32_t (&pairs)[4]) {
+    uint4 o;
+    o.x = quant_pair<T, MATH>(in.x, q, a, pairs[0]);
+    o.y = quant_pair<T, MATH>(in.y, q, a, pairs[1]);
+    o.z = quant_pair<T, MATH>(in.z, q, a, pairs[2]);
+    o.w = quant_pair<T, MATH>(in.w, q, a, pairs[3]);
+    return o;
+  }
+};
+
+// ------------------------------------------------------------------ min / max of a vector
+template <typename T>
+__device__ __forceinline__ void vec_minmax(const uint4& v, float& mn, float& mx);
+
+template <>
+__device__ __forceinline__ void vec_minmax<float>(const uint4& v, float& mn, float& mx) {
+  const float a = __uint_as_float(v.x), b = __uint_as_float(v.y), c = __uint_as_float(v.z),
+              d = __uint_as_float(v.w);
+  mn = fminf(fminf(a, b), fminf(c, d));
+  mx = fmaxf(fmaxf(a, b), fmaxf(c, d));
+  if (a != a || b != b || c != c || d != d) mn = mx = nan_f();
+}
+template <>
+__device__ __forceinline__ void vec_minmax<__half>(const uint4& v, float& mn, float& mx) {
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+  const __half2 lo = __hmin2_nan(__hmin2_nan(h[0], h[1]), __hmin2_nan(h[2], h[3]));
+  const __half2 hi = __hmax2_nan(__hmax2_nan(h[0], h[1]), __hmax2_nan(h[2], h[3]));
+  mn = min_nan(__low2float(lo), __high2float(lo));
+  mx = max_nan(__low2float(hi), __high2float(hi));
+}
+template <>
+__device__ __forceinline__ void vec_minmax<__nv_bfloat16>(const uint4& v, float& mn, float& mx) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+  const __nv_bfloat162 lo = __hmin2_nan(__hmin2_nan(h[0], h[1]), __hmin2_nan(h[2], h[3]));
+  const __nv_bfloat162 hi = __hmax2_nan(__hmax2_nan(h[0], h[1]), __hmax2_nan(h[2], h[3]));
+  mn = min_nan(__low2float(lo), __high2float(lo));
+  mx = max_nan(__low2float(hi), __high2float(hi));
+}
+
+// ------------------------------------------------------------------ packers (q100 v1 layout)
+// A uint32 word of a b-bit plane covers F = 32/b consecutive K elements; element e of the
+// word sits in field (e >> 1) + (e & 1) * F/2, i.e. bit b*(e>>1) + 16*(e&1).  With
+// pairs[j] = code[2j] | code[2j+1] << 16 a vector starting at (even) word-relative element
+// o contributes  sum_j pairs[j] << (b * (o/2 + j)).
+template <int NP>
+__device__ __forceinline__ uint32_t plane_word(const uint32_t (&pairs)[NP], int b, int shift0,
+                                               uint32_t pair_mask, int pre_shift) {
+  uint32_t w = 0;
+#pragma unroll
+  for (int j = 0; j < NP; ++j) w |= ((pairs[j] >> pre_shift) & pair_mask) << (shift0 + b * j);
+  return w;
+}
+
+// Emits the packed words of one vector.  `vec_in_row` = index of this 16-byte vector inside
+// its row, `lane_sub` = position of the thread among consecutive-vector lanes (all lanes
+// of the warp call this together: shuffles inside).
+template <int E>
+__device__ __forceinline__ void emit_packed(const uint32_t (&pairs)[E / 2], const QuantArgs& a,
+                                            int64_t row, int64_t vec_in_row, bool valid) {
+  uint32_t* prow = a.packed + row * a.words_per_row;
+  const int64_t e0 = vec_in_row * E;                 // first element (column) of the vector
+  const int nb = a.n_bits;
+  if (nb == 8) {
+    if (E == 8) {
+      if (valid) {
+        uint2 w;
+        w.x = (pairs[0] & 0x00ff00ffu) | ((pairs[1] & 0x00ff00ffu) << 8);
+        w.y = (pairs[E / 2 - 2] & 0x00ff00ffu) | ((pairs[E / 2 - 1] & 0x00ff00ffu) << 8);
+        *reinterpret_cast<uint2*>(prow + (e0 >> 2)) = w;
+      }
+    } else {
+      if (valid) prow[e0 >> 2] = (pairs[0] & 0x00ff00ffu) | ((pairs[1] & 0x00ff00ffu) << 8);
+    }
+    return;
+  }
+  // planes: (bits, mask, pre_shift, word offset)
+  const int n_planes = (nb == 3) ? 2 : 1;
+#pragma unroll
+  for (int pl = 0; pl < 2; ++pl) {
+    if (pl >= n_planes) break;
+    const int b = (nb == 3) ? (pl == 0 ? 2 : 1) : nb;
+    const int pre = (nb == 3 && pl == 1) ? 2 : 0;
+    const uint32_t m1 = (1u << b) - 1u;
+    const uint32_t pmask = m1 | (m1 << 16);
+    const int F = 32 / b;                      // elements per word
+    const int lpw = F / E;                     // lanes per word (>= 1 here)
+    const int o = static_cast<int>(e0 % F);    // word-relative first element (multiple of E)
+    uint32_t w = plane_word<E / 2>(pairs, b, b * (o >> 1), pmask, pre);
+    if (!valid) w = 0;
+    for (int d = 1; d < lpw; d <<= 1) w |= __shfl_xor_sync(0xffffffffu, w, d);
+    if (valid && o == 0) prow[(pl == 1 ? a.plane1_off : 0) + e0 / F] = w;
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ void store_group_meta(const QuantArgs& a, int64_t g, const GroupQ<T>& q) {
+  using D = DT<T>;
+  if (a.scales) reinterpret_cast<T*>(a.scales)[g] = D::from_f(q.scale);
+  if (a.zeros && a.has_zp) reinterpret_cast<T*>(a.zeros)[g] = D::from_f(q.zp);
+  if (a.meta) {
+    const int64_t row = g / a.groups_per_row, kg = g % a.groups_per_row;
+    T* m = reinterpret_cast<T*>(a.meta) + (kg * a.rows + row) * 2;
+    m[0] = D::from_f(q.scale);
+    m[1] = D::from_f(q.zp);
+  }
+}
+
+// ------------------------------------------------------------------ K1: L lanes x V vectors per group
+template <typename T, int L, int V, int MATH, bool PACK>
+__global__ void __launch_bounds__(256) k1_groups(const QuantArgs a) {
+  constexpr int E = DT<T>::kVec;
+  constexpr int GPW = 32 / L;                       // groups per warp step
+  const int lane = threadIdx.x & 31;
+  const int l = lane % L, sub = lane / L;
+  const int64_t warp = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t n_warps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  const uint4* __restrict__ xin = reinterpret_cast<const uint4*>(a.x);
+  uint4* __restrict__ dq = reinterpret_cast<uint4*>(a.deq);
+
+  int64_t g = warp * GPW + sub;
+  const int64_t gstep = n_warps * GPW;
+  const int64_t g_end = ((a.n_groups + GPW - 1) / GPW) * GPW;   // warp-uniform trip count
+
+  uint4 cur[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k)
+    cur[k] = (g < a.n_groups) ? ldg_stream(xin + g * (L * V) + k * L + l) : make_uint4(0, 0, 0, 0);
+
+  for (; g - sub < g_end; g += gstep) {
+    const bool valid = g < a.n_groups;
+    // software prefetch of the next step (keeps >= 2V 128-bit loads in flight per lane)
+    uint4 nxt[V];
+    const int64_t gn = g + gstep;
+#pragma unroll
+    for (int k = 0; k < V; ++k)
+      nxt[k] = (gn < a.n_groups) ? ldg_stream(xin + gn * (L * V) + k * L + l) : make_uint4(0, 0, 0, 0);
+
+    float mn, mx;
+    vec_minmax<T>(cur[0], mn, mx);
+#pragma unroll
+    for (int k = 1; k < V; ++k) {
+      float m0, m1;
+      vec_minmax<T>(cur[k], m0, m1);
+      mn = min_nan(mn, m0);
+      mx = max_nan(mx, m1);
+    }
+#pragma unroll
+    for (int d = 1; d < L; d <<= 1) {
+      mn = min_nan(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+      mx = max_nan(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    }
+    const GroupQ<T> q = group_params<T>(mn, mx, a, valid ? g : 0);
+
+    int64_t row = 0, vec0 = 0;
+    if (PACK) {
+      row = g / a.groups_per_row;
+      vec0 = (g % a.groups_per_row) * (L * V);
+    }
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      uint32_t pairs[E / 2];
+      const uint4 o = VecQuant<T, MATH>::run(cur[k], q, a, pairs);
+      if (dq != nullptr && valid) stg_stream(dq + g * (L * V) + k * L + l, o);
+      if (PACK) emit_packed<E>(pairs, a, row, vec0 + k * L + l, valid && row < a.rows);
+    }
+    if (l == 0 && valid) store_group_meta<T>(a, g, q);
+#pragma unroll
+    for (int k = 0; k < V; ++k) cur[k] = nxt[k];
+  }
+}
+
+// ------------------------------------------------------------------ K2: one CTA per row
+template <typename T, int VMAX, int MATH, bool PACK>
+__global__ void __launch_bounds__(1024) k2_rows(const QuantArgs a) {
+  constexpr int E = DT<T>::kVec;
+  __shared__ float s_mn[32], s_mx[32];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+  const int nvec = static_cast<int>(a.cols / E);
+  const int vper = (nvec + nt - 1) / nt;            // uniform trip count <= VMAX
+  const uint4* __restrict__ xin = reinterpret_cast<const uint4*>(a.x);
+  uint4* __restrict__ dq = reinterpret_cast<uint4*>(a.deq);
+
+  for (int64_t row = blockIdx.x; row < a.rows; row += gridDim.x) {
+    uint4 v[VMAX];
+    float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);   // +inf / -inf
+#pragma unroll
+    for (int k = 0; k < VMAX; ++k) {
+      const int idx = k * nt + tid;
+      if (k < vper && idx < nvec) {
+        v[k] = ldg_stream(xin + row * nvec + idx);
+        float m0, m1;
+        vec_minmax<T>(v[k], m0, m1);
+        mn = min_nan(mn, m0);
+        mx = max_nan(mx, m1);
+      }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      mn = min_nan(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+      mx = max_nan(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    }
+    if (lane == 0) { s_mn[wid] = mn; s_mx[wid] = mx; }
+    __syncthreads();
+    mn = (lane < nw) ? s_mn[lane] : __int_as_float(0x7f800000);
+    mx = (lane < nw) ? s_mx[lane] : __int_as_float(0xff800000);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      mn = min_nan(mn, __shfl_xor_sync(0xffffffffu, mn, d));
+      mx = max_nan(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    }
+    __syncthreads();                                   // s_mn/s_mx reusable next row
+    const GroupQ<T> q = group_params<T>(mn, mx, a, row);
+#pragma unroll
+    for (int k = 0; k < VMAX; ++k) {
+      if (k < vper) {
+        const int idx = k * nt + tid;
+        const bool valid = idx < nvec;
+        uint32_t pairs[E / 2];
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if (valid) o = VecQuant<T, MATH>::run(v[k], q, a, pairs);
+        else {
+#pragma unroll
+          for (int j = 0; j < E / 2; ++j) pairs[j] = 0;
+        }
+        if (dq != nullptr && valid) stg_stream(dq + row * nvec + idx, o);
+        if (PACK) emit_packed<E>(pairs, a, row, idx, valid);
+      }
+    }
+    if (tid == 0) store_group_meta<T>(a, row, q);
+  }
+}
+
+// ------------------------------------------------------------------ dequantize (utility, not hot)
+template <typename T>
+__global__ void k_dequantize(const uint32_t* __restrict__ packed, const T* __restrict__ scales,
+                             const T* __restrict__ zeros, T* __restrict__ out, int64_t rows,
+                             int64_t cols, int group, int n_bits, float qmin, int words_per_row,
+                             int plane1_off) {
+  using D = DT<T>;
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const int64_t r = i / cols, c = i % cols;
+  const uint32_t* prow = packed + r * words_per_row;
+  auto field = [&](int b, int off) -> uint32_t {
+    const int F = 32 / b;
+    const int e = static_cast<int>(c % F);
+    const uint32_t w = prow[off + c / F];
+    return (w >> (b * (e >> 1) + 16 * (e & 1))) & ((1u << b) - 1u);
+  };
+  uint32_t u;
+  if (n_bits == 3) u = field(2, 0) | (field(1, plane1_off) << 2);
+  else u = field(n_bits, 0);
+  float code = static_cast<float>(u) + qmin;
+  if (scales == nullptr) { out[i] = D::from_f(code); return; }
+  const int64_t g = i / group;
+  const float s = D::to_f(scales[g]);
+  float d = code;
+  if (zeros != nullptr) d = D::rd(code - D::to_f(zeros[g]));
+  out[i] = D::from_f(D::rd(d * s));
+}
+
+// ------------------------------------------------------------------ division self-test
+template <typename T>
+__global__ void k_selftest_div(unsigned long long* mismatches) {
+  using D = DT<T>;
+  // blockIdx.x enumerates scale bit patterns, threads sweep x bit patterns
+  const uint32_t sbits = blockIdx.x;
+  uint16_t sb = static_cast<uint16_t>(sbits);
+  const T st = *reinterpret_cast<T*>(&sb);
+  const float s = D::to_f(st);
+  if (!(s >= 1e-5f && s <= 1e4f)) return;
+  const float rcp = __frcp_rn(s);
+  unsigned long long bad = 0;
+  for (uint32_t xb = threadIdx.x; xb < 65536u; xb += blockDim.x) {
+    uint16_t xs = static_cast<uint16_t>(xb);
+    const float x = D::to_f(*reinterpret_cast<T*>(&xs));
+    const float ref = D::rd(__fdiv_rn(x, s));
+    const float got = D::rd(div_x_s<MATH_PACKED>(x, s, rcp));
+    // the quantizer only consumes round_ste(v): compare what it can observe
+    const float r0 = D::rd(D::rd(rintf(ref) - ref) + ref);
+    const float r1 = D::rd(D::rd(rintf(got) - got) + got);
+    const bool same = (r0 == r1) || (r0 != r0 && r1 != r1);
+    bad += same ? 0ull : 1ull;
+  }
+  if (bad) atomicAdd(mismatches, bad);
+}
+
+// ------------------------------------------------------------------ host dispatch
+static int64_t words_per_row_host(int64_t cols, int n_bits) {
+  if (n_bits == 3) return cols / 16 + cols / 32;
+  return cols * n_bits / 32;
+}
+
+template <typename T, int L, int V, int MATH>
+static int launch_k1_lv(const QuantArgs& a, bool pack, cudaStream_t st) {
+  constexpr int GPW = 32 / L;
+  const int64_t warps_needed = (a.n_groups + GPW - 1) / GPW;
+  const int sms = sm_count();
+  int64_t blocks = (warps_needed + 7) / 8;
+  const int64_t cap = static_cast<int64_t>(sms) * 8;          // persistent: <= 8 CTAs / SM
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  if (pack) k1_groups<T, L, V, MATH, true><<<static_cast<unsigned>(blocks), 256, 0, st>>>(a);
+  else k1_groups<T, L, V, MATH, false><<<static_cast<unsigned>(blocks), 256, 0, st>>>(a);
+  return check_cuda(cudaGetLastError(), "k1_groups launch");
+}
+
+template <typename T, int MATH>
+static int launch_k1(const QuantArgs& a, bool pack, cudaStream_t st, bool& handled) {
+  constexpr int E = DT<T>::kVec;
+  const int vecs = a.group / E;               // vectors per group
+  handled = true;
+  if (E == 8) {
+    switch (vecs) {
+      case 4:  return launch_k1_lv<T, 4, 1, MATH>(a, pack, st);    // g = 32
+      case 8:  return launch_k1_lv<T, 8, 1, MATH>(a, pack, st);    // g = 64
+      case 16: return launch_k1_lv<T, 8, 2, MATH>(a, pack, st);    // g = 128
+      case 32: return launch_k1_lv<T, 8, 4, MATH>(a, pack, st);    // g = 256
+      default: break;
+    }
+  } else {
+    switch (vecs) {
+      case 8:  return launch_k1_lv<T, 8, 1, MATH>(a, pack, st);    // g = 32
+      case 16: return launch_k1_lv<T, 8, 2, MATH>(a, pack, st);    // g = 64
+      case 32: return launch_k1_lv<T, 8, 4, MATH>(a, pack, st);    // g = 128
+      case 64: return launch_k1_lv<T, 16, 4, MATH>(a, pack, st);   // g = 256
+      default: break;
+    }
+  }
+  handled = false;
+  return Q100_OK;
+}
+
+template <typename T, int MATH>
+static int launch_k2(const QuantArgs& a_in, bool pack, cudaStream_t st) {
+  constexpr int E = DT<T>::kVec;
+  constexpr int VMAX = 8;
+  // rows kernel treats every group as a row of `group` elements
+  QuantArgs a = a_in;
+  const int64_t nvec = a.group / E;
+  Q100_REQUIRE(nvec <= VMAX * 1024, Q100_EUNSUPPORTED,
+               "row/group length %d exceeds the register-resident limit of %d elements",
+               a.group, VMAX * 1024 * E);
+  if (pack)
+    Q100_REQUIRE(a.groups_per_row == 1, Q100_EUNSUPPORTED,
+                 "packed output needs group in {32,64,128,256} or one group per row (got %d)", a.group);
+  int nt = 64;
+  while (nt < 1024 && static_cast<int64_t>(nt) * 4 < nvec) nt <<= 1;
+  while (static_cast<int64_t>(nt) * VMAX < nvec) nt <<= 1;
+  // present the flat [n_groups, group] view to the kernel: every group is a "row"
+  a.rows = a.n_groups;
+  a.cols = a.group;
+  a.groups_per_row = 1;
+  const QuantArgs& k = a;
+  const int sms = sm_count();
+  int64_t blocks = a.n_groups;
+  const int64_t cap = static_cast<int64_t>(sms) * (2048 / nt);
+  if (blocks > cap) blocks = cap;
+  if (pack) k2_rows<T, VMAX, MATH, true><<<static_cast<unsigned>(blocks), nt, 0, st>>>(k);
+  else k2_rows<T, VMAX, MATH, false><<<static_cast<unsigned>(blocks), nt, 0, st>>>(k);
+  return check_cuda(cudaGetLastError(), "k2_rows launch");
+}
+
+template <typename T>
+static int quantize_dispatch(const QuantArgs& a, bool pack, int flags, cudaStream_t st) {
+  constexpr bool k16 = (DT<T>::kCode != Q100_F32);
+  const int math = !k16 ? MATH_SCALAR_IEEE
+                        : (flags & Q100_FLAG_IEEE_DIV)    ? MATH_SCALAR_IEEE
+                        : (flags & Q100_FLAG_SCALAR_MATH) ? MATH_SCALAR
+                                                          : MATH_PACKED;
+  bool handled = false;
+  int rc = Q100_OK;
+  if (math == MATH_SCALAR_IEEE) rc = launch_k1<T, MATH_SCALAR_IEEE>(a, pack, st, handled);
+  else if (math == MATH_SCALAR) rc = launch_k1<T, k16 ? MATH_SCALAR : MATH_SCALAR_IEEE>(a, pack, st, handled);
+  else rc = launch_k1<T, k16 ? MATH_PACKED : MATH_SCALAR_IEEE>(a, pack, st, handled);
+  if (handled) return rc;
+  // everything else goes through the one-CTA-per-group row kernel, which cannot address
+  // the transposed side band (or packed rows) of a multi-group row
+  Q100_REQUIRE(a.meta == nullptr || a.groups_per_row == 1, Q100_EUNSUPPORTED,
+               "meta side band needs group in {32,64,128,256} or one group per row (got %d)", a.group);
+  if (math == MATH_SCALAR_IEEE) return launch_k2<T, MATH_SCALAR_IEEE>(a, pack, st);
+  if (math == MATH_SCALAR) return launch_k2<T, k16 ? MATH_SCALAR : MATH_SCALAR_IEEE>(a, pack, st);
+  return launch_k2<T, k16 ? MATH_PACKED : MATH_SCALAR_IEEE>(a, pack, st);
+}
+
+}  // namespace q100
+
+using namespace q100;
+
+extern "C" int64_t q100_packed_words_per_row(int64_t cols, int n_bits) {
+  if (n_bits != 2 && n_bits != 3 && n_bits != 4 && n_bits != 8) return -1;
+  if (cols % 32 != 0) return -1;
+  return words_per_row_host(cols, n_bits);
+}
+
+extern "C" int q100_quantize_groupwise(const void* x, int dtype, int64_t rows, int64_t cols, int group,
+                                       int n_bits, int symmetric, int disable_zp,
+                                       const void* lwc_up, const void* lwc_low,
+                                       void* dequant_out, void* packed_out,
+                                       void* scales_out, void* zeros_out, void* meta_out,
+                                       int flags, void* stream) {
+  Q100_REQUIRE(x != nullptr, Q100_EINVAL, "x is NULL");
+  Q100_REQUIRE(dtype >= 0 && dtype <= 2, Q100_EINVAL, "bad dtype %d", dtype);
+  Q100_REQUIRE(rows >= 0 && cols >= 0, Q100_EINVAL, "negative shape");
+  Q100_REQUIRE(n_bits >= 2 && n_bits <= 15, Q100_EINVAL,
+               "n_bits=%d: the quantizer handles 2..15 (>= 16 is the identity, quantizer.py:119)", n_bits);
+  // 9..15 bits: qmax is not representable in bf16 and the reference's clamp then depends on
+  // how torch casts the bound; no shipped configuration uses it (wbits 2/3/4/8, abits 4/8).
+  Q100_REQUIRE(n_bits <= 8, Q100_EUNSUPPORTED, "n_bits=%d > 8 is not implemented", n_bits);
+  Q100_REQUIRE((lwc_up == nullptr) == (lwc_low == nullptr), Q100_EINVAL,
+               "lwc_up and lwc_low must be given together");
+  if (rows == 0 || cols == 0) return Q100_OK;            // empty tensor: nothing to do
+  const int g = (group == 0) ? static_cast<int>(cols) : group;
+  Q100_REQUIRE(group >= 0 && cols % g == 0, Q100_EINVAL,
+               "cols=%lld not divisible by group=%d (pad first, quantizer.py:136-139)",
+               static_cast<long long>(cols), g);
+  const int esz = (dtype == Q100_F32) ? 4 : 2;
+  Q100_REQUIRE((static_cast<int64_t>(g) * esz) % 16 == 0, Q100_EUNSUPPORTED,
+               "group/row of %d elements is not a multiple of 16 bytes", g);
+  Q100_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+               (reinterpret_cast<uintptr_t>(dequant_out) & 15) == 0, Q100_EINVAL,
+               "x / dequant_out must be 16-byte aligned");
+  const bool pack = packed_out != nullptr;
+  if (pack) {
+    Q100_REQUIRE(n_bits == 2 || n_bits == 3 || n_bits == 4 || n_bits == 8, Q100_EUNSUPPORTED,
+                 "packed output supports n_bits in {2,3,4,8}, got %d", n_bits);
+    Q100_REQUIRE(cols % 32 == 0, Q100_EUNSUPPORTED, "packed output needs cols %% 32 == 0");
+  }
+  Q100_REQUIRE(meta_out == nullptr || dtype != Q100_F32, Q100_EUNSUPPORTED,
+               "meta side band is fp16/bf16 only");
+  int rc = ensure_device();
+  if (rc != Q100_OK) return rc;
+
+  QuantArgs a{};
+  a.x = x; a.deq = dequant_out; a.packed = reinterpret_cast<uint32_t*>(packed_out);
+  a.scales = scales_out; a.zeros = zeros_out; a.meta = meta_out;
+  a.lwc_up = lwc_up; a.lwc_low = lwc_low;
+  a.rows = rows; a.cols = cols; a.group = g;
+  a.groups_per_row = static_cast<int>(cols / g);
+  a.n_groups = rows * a.groups_per_row;
+  Q100_REQUIRE(a.n_groups < (1ll << 31), Q100_EUNSUPPORTED, "too many groups");
+  a.n_bits = n_bits; a.symmetric = symmetric ? 1 : 0; a.has_zp = disable_zp ? 0 : 1;
+  if (disable_zp) { a.qmin = -static_cast<float>(1 << (n_bits - 1)); a.qmax = static_cast<float>((1 << (n_bits - 1)) - 1); }
+  else { a.qmin = 0.0f; a.qmax = static_cast<float>((1 << n_bits) - 1); }
+  a.denom = symmetric ? static_cast<float>((1 << (n_bits - 1)) - 1) : static_cast<float>((1 << n_bits) - 1);
+  a.words_per_row = pack ? static_cast<int>(words_per_row_host(cols, n_bits)) : 0;
+  a.plane1_off = static_cast<int>(cols / 16);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (dtype) {
+    case Q100_F16:  return quantize_dispatch<__half>(a, pack, flags, st);
+    case Q100_BF16: return quantize_dispatch<__nv_bfloat16>(a, pack, flags, st);
+    default:        return quantize_dispatch<float>(a, pack, flags, st);
+  }
+}
+
+extern "C" int q100_fakequant_rows(const void* x, int dtype, int64_t rows, int64_t cols, int n_bits,
+                                   void* out, void* scales_out, void* zeros_out, int flags,
+                                   void* stream) {
+  return q100_quantize_groupwise(x, dtype, rows, cols, 0, n_bits, 0, 0, nullptr, nullptr, out,
+                                 nullptr, scales_out, zeros_out, nullptr, flags, stream);
+}
+
+extern "C" int q100_dequantize(const void* packed, const void* scales, const void* zeros, int dtype,
+                               int64_t rows, int64_t cols, int group, int n_bits, int disable_zp,
+                               void* out, void* stream) {
+  Q100_REQUIRE(packed && out, Q100_EINVAL, "NULL pointer");
+  Q100_REQUIRE(dtype >= 0 && dtype <= 2, Q100_EINVAL, "bad dtype %d", dtype);
+  Q100_REQUIRE(n_bits == 2 || n_bits == 3 || n_bits == 4 || n_bits == 8, Q100_EUNSUPPORTED,
+               "n_bits in {2,3,4,8}");
+  Q100_REQUIRE(cols % 32 == 0, Q100_EUNSUPPORTED, "cols %% 32 != 0");
+  if (rows == 0 || cols == 0) return Q100_OK;
+  const int g = group == 0 ? static_cast<int>(cols) : group;
+  int rc = ensure_device();
+  if (rc != Q100_OK) return rc;
+  const float qmin = disable_zp ? -static_cast<float>(1 << (n_bits - 1)) : 0.0f;
+  const int wpr = static_cast<int>(words_per_row_host(cols, n_bits));
+  const int64_t n = rows * cols;
+  const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const uint32_t* p = reinterpret_cast<const uint32_t*>(packed);
+  if (dtype == Q100_F16)
+    k_dequantize<__half><<<blocks, 256, 0, st>>>(p, (const __half*)scales, (const __half*)zeros, (__half*)out, rows, cols, g, n_bits, qmin, wpr, (int)(cols / 16));
+  else if (dtype == Q100_BF16)
+    k_dequantize<__nv_bfloat16><<<blocks, 256, 0, st>>>(p, (const __nv_bfloat16*)scales, (const __nv_bfloat16*)zeros, (__nv_bfloat16*)out, rows, cols, g, n_bits, qmin, wpr, (int)(cols / 16));
+  else
+    k_dequantize<float><<<blocks, 256, 0, st>>>(p, (const float*)scales, (const float*)zeros, (float*)out, rows, cols, g, n_bits, qmin, wpr, (int)(cols / 16));
+  return check_cuda(cudaGetLastError(), "k_dequantize launch");
+}
+
+extern "C" int q100_selftest_div(int dtype, void* mismatches_out, void* stream) {
+  Q100_REQUIRE(dtype == Q100_F16 || dtype == Q100_BF16, Q100_EINVAL, "fp16/bf16 only");
+  Q100_REQUIRE(mismatches_out != nullptr, Q100_EINVAL, "NULL output");
+  int rc = ensure_device();
+  if (rc != Q100_OK) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == Q100_F16) k_selftest_div<__half><<<65536, 256, 0, st>>>((unsigned long long*)mismatches_out);
+  else k_selftest_div<__nv_bfloat16><<<65536, 256, 0, st>>>((unsigned long long*)mismatches_out);
+  return check_cuda(cudaGetLastError(), "k_selftest_div launch");
+}

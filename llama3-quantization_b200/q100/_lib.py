@@ -1,0 +1,69 @@
+"""ctypes binding of libq100.so (C ABI declared in include/q100.h).
+
+Loading is eager and loud: if the shared library has not been built
+(``python tools/build_ext.py`` / ``__graft_entry__.build()``) importing this module
+raises ``ImportError``.  There is no Python or CPU fallback for any kernel.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libq100.so")
+
+OK, EINVAL, EUNSUPPORTED, ECUDA, ENODEVICE, EWORKSPACE = range(6)
+F16, BF16, F32 = 0, 1, 2
+FLAG_IEEE_DIV = 0x1
+FLAG_SCALAR_MATH = 0x2
+GEMM_FORCE_SKINNY = 0x1
+GEMM_FORCE_TC = 0x2
+
+_vp, _i, _i64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
+
+# name -> (restype, argtypes); must list every symbol include/q100.h declares
+SIGNATURES = {
+    "q100_last_error": (C.c_char_p, []),
+    "q100_abi_version": (_i, []),
+    "q100_device_ok": (_i, [_i]),
+    "q100_quantize_groupwise": (_i, [_vp, _i, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "q100_fakequant_rows": (_i, [_vp, _i, _i64, _i64, _i, _vp, _vp, _vp, _i, _vp]),
+    "q100_packed_words_per_row": (_i64, [_i64, _i]),
+    "q100_dequantize": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _i, _i, _i, _vp, _vp]),
+    "q100_gemm_wna16": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _sz, _i, _vp]),
+    "q100_gemm_workspace_bytes": (_sz, [_i64, _i64, _i64, _i, _i]),
+    "q100_selftest_div": (_i, [_i, _vp, _vp]),
+}
+
+
+class Q100Error(RuntimeError):
+    """A libq100 entry point returned a non-zero status."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libq100 error {code}: {msg}")
+        self.code = code
+
+
+def _load() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build the CUDA extension first "
+            "(python tools/build_ext.py or __graft_entry__.build()). q100 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError == ABI mismatch, let it propagate
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = _load()
+
+
+def last_error() -> str:
+    return lib.q100_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int) -> None:
+    if rc != OK:
+        raise Q100Error(rc, last_error())

@@ -1,0 +1,208 @@
+"""Torch-facing wrappers of the libq100 kernels.
+
+PyTorch is plumbing only here: it owns device memory and the stream; every
+computation below is one call through the C ABI (include/q100.h).  All functions
+require CUDA tensors and raise otherwise -- there is no CPU path.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import lib, check
+
+_DT = {torch.float16: _lib.F16, torch.bfloat16: _lib.BF16, torch.float32: _lib.F32}
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"q100: unsupported dtype {t.dtype} (fp16, bf16, fp32 only)") from None
+
+
+def _require_cuda(*ts: Optional[torch.Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("q100: CUDA tensor required -- the quantized hot path has no CPU fallback")
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def packed_words_per_row(cols: int, n_bits: int) -> int:
+    w = lib.q100_packed_words_per_row(cols, n_bits)
+    if w < 0:
+        raise ValueError(f"q100: cannot pack cols={cols} at {n_bits} bits (cols % 32 == 0, bits in 2/3/4/8)")
+    return int(w)
+
+
+@dataclass
+class QuantResult:
+    """Outputs of one quantize pass (any subset)."""
+    dequant: Optional[torch.Tensor] = None     # forward() value, same shape/dtype as the input
+    packed: Optional[torch.Tensor] = None      # int32 [rows, words_per_row]
+    scales: Optional[torch.Tensor] = None      # [n_groups, 1]  == quantizer.scale
+    zeros: Optional[torch.Tensor] = None       # [n_groups, 1]  == quantizer.round_zero_point (None if disabled)
+    meta: Optional[torch.Tensor] = None        # [cols/group, rows, 2] (scale, zero) side band for the GEMMs
+
+
+def quantize_groupwise(x: torch.Tensor, group: int, n_bits: int, symmetric: bool = False,
+                       disable_zero_point: bool = False, lwc_up: Optional[torch.Tensor] = None,
+                       lwc_low: Optional[torch.Tensor] = None, want_dequant: bool = True,
+                       want_packed: bool = False, want_meta: bool = False, flags: int = 0) -> QuantResult:
+    """One fused pass of UniformAffineQuantizer.forward over a 2-D tensor [rows, cols].
+
+    ``group == 0`` quantises one group per row.  ``lwc_up`` / ``lwc_low`` are the
+    post-sigmoid LWC multipliers (quant/quantizer.py:143-145), shape [n_groups, 1].
+    """
+    _require_cuda(x, lwc_up, lwc_low)
+    if x.dim() != 2:
+        raise ValueError("q100.quantize_groupwise expects a 2-D tensor")
+    x = x.contiguous()
+    rows, cols = x.shape
+    g = cols if group in (0, None) else int(group)
+    if cols % g != 0:
+        raise ValueError(f"cols={cols} not divisible by group={g}")
+    n_groups = rows * (cols // g)
+    dev, dt = x.device, x.dtype
+    res = QuantResult()
+    if want_dequant:
+        res.dequant = torch.empty_like(x)
+    if want_packed:
+        res.packed = torch.empty((rows, packed_words_per_row(cols, n_bits)), dtype=torch.int32, device=dev)
+    res.scales = torch.empty((n_groups, 1), dtype=dt, device=dev)
+    if not disable_zero_point:
+        res.zeros = torch.empty((n_groups, 1), dtype=dt, device=dev)
+    if want_meta:
+        res.meta = torch.zeros((cols // g, rows, 2), dtype=dt, device=dev)
+    if lwc_up is not None:
+        lwc_up = lwc_up.to(dt).contiguous()
+        lwc_low = lwc_low.to(dt).contiguous()
+        if lwc_up.numel() != n_groups or lwc_low.numel() != n_groups:
+            raise ValueError("LWC multipliers must have one entry per group")
+    with torch.cuda.device(dev):
+        check(lib.q100_quantize_groupwise(
+            x.data_ptr(), _dtype_code(x), rows, cols, 0 if group in (0, None) else g, n_bits,
+            int(bool(symmetric)), int(bool(disable_zero_point)), _ptr(lwc_up), _ptr(lwc_low),
+            _ptr(res.dequant), _ptr(res.packed), _ptr(res.scales), _ptr(res.zeros), _ptr(res.meta),
+            flags, _stream(x)))
+    return res
+
+
+def fakequant_rows(x: torch.Tensor, n_bits: int, flags: int = 0) -> QuantResult:
+    """Per-token activation fake-quant over the last dim (any leading shape)."""
+    _require_cuda(x)
+    shp = x.shape
+    x2 = x.contiguous().view(-1, shp[-1])
+    rows, cols = x2.shape
+    res = QuantResult(dequant=torch.empty_like(x2),
+                      scales=torch.empty((rows, 1), dtype=x.dtype, device=x.device),
+                      zeros=torch.empty((rows, 1), dtype=x.dtype, device=x.device))
+    with torch.cuda.device(x.device):
+        check(lib.q100_fakequant_rows(x2.data_ptr(), _dtype_code(x2), rows, cols, n_bits,
+                                      res.dequant.data_ptr(), res.scales.data_ptr(), res.zeros.data_ptr(),
+                                      flags, _stream(x2)))
+    res.dequant = res.dequant.view(shp)
+    res.scales = res.scales.view(*shp[:-1], 1)
+    res.zeros = res.zeros.view(*shp[:-1], 1)
+    return res
+
+
+def dequantize(packed: torch.Tensor, scales: Optional[torch.Tensor], zeros: Optional[torch.Tensor],
+               cols: int, group: int, n_bits: int, dtype: torch.dtype,
+               disable_zero_point: bool = False) -> torch.Tensor:
+    """Packed codes -> dense tensor (raw integer codes when ``scales`` is None)."""
+    _require_cuda(packed, scales, zeros)
+    rows = packed.shape[0]
+    out = torch.empty((rows, cols), dtype=dtype, device=packed.device)
+    with torch.cuda.device(packed.device):
+        check(lib.q100_dequantize(packed.data_ptr(), _ptr(scales), _ptr(zeros), _DT[dtype], rows, cols,
+                                  0 if group in (0, None) else group, n_bits, int(bool(disable_zero_point)),
+                                  out.data_ptr(), _stream(packed)))
+    return out
+
+
+@dataclass
+class PackedWeight:
+    """A quantised nn.Linear weight [N, K] in the q100 v1 layout."""
+    packed: torch.Tensor       # int32 [N, words_per_row(K, n_bits)]
+    meta: torch.Tensor         # [K/group, N, 2] (scale, zero) in the compute dtype
+    scales: torch.Tensor       # [N*K/group, 1] reference layout
+    zeros: Optional[torch.Tensor]
+    n_bits: int
+    group: int                 # elements per group (== K for per-channel)
+    N: int
+    K: int
+    disable_zero_point: bool = False
+
+    @property
+    def dtype(self) -> torch.dtype:
+        return self.meta.dtype
+
+    def nbytes(self) -> int:
+        return self.packed.numel() * 4 + self.meta.numel() * self.meta.element_size()
+
+
+def pack_weight(w: torch.Tensor, n_bits: int, group: Optional[int], symmetric: bool = False,
+                disable_zero_point: bool = False, lwc_up=None, lwc_low=None,
+                want_dequant: bool = False):
+    """Quantise + pack an [N, K] weight.  Returns (PackedWeight, QuantResult)."""
+    g = w.shape[1] if group in (0, None) else int(group)
+    r = quantize_groupwise(w, g, n_bits, symmetric, disable_zero_point, lwc_up, lwc_low,
+                           want_dequant=want_dequant, want_packed=True, want_meta=True)
+    pw = PackedWeight(r.packed, r.meta, r.scales, r.zeros, n_bits, g, w.shape[0], w.shape[1],
+                      bool(disable_zero_point))
+    return pw, r
+
+
+_WORKSPACES: dict = {}
+
+
+def _workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
+    """Per-(device, stream) zero-initialised scratch; kernels leave it zeroed."""
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    ws = _WORKSPACES.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(nbytes, 1 << 22), dtype=torch.uint8, device=dev)
+        _WORKSPACES[key] = ws
+    return ws
+
+
+def gemm_wna16(x: torch.Tensor, w: PackedWeight, bias: Optional[torch.Tensor] = None,
+               flags: int = 0) -> torch.Tensor:
+    """y = x @ dequant(w)^T (+ bias) straight from packed codes (K3)."""
+    _require_cuda(x, w.packed, bias)
+    if x.dtype != w.dtype:
+        raise TypeError(f"q100.gemm_wna16: x is {x.dtype} but the packed weight was built for {w.dtype}")
+    shp = x.shape
+    if shp[-1] != w.K:
+        raise ValueError(f"q100.gemm_wna16: x has K={shp[-1]}, weight has K={w.K}")
+    x2 = x.contiguous().view(-1, w.K)
+    M = x2.shape[0]
+    y = torch.empty((M, w.N), dtype=x.dtype, device=x.device)
+    if bias is not None:
+        bias = bias.to(x.dtype).contiguous()
+    need = lib.q100_gemm_workspace_bytes(M, w.N, w.K, w.n_bits, flags)
+    ws = _workspace(x.device, need)
+    with torch.cuda.device(x.device):
+        check(lib.q100_gemm_wna16(x2.data_ptr(), w.packed.data_ptr(), w.meta.data_ptr(), _ptr(bias),
+                                  y.data_ptr(), M, w.N, w.K, w.group, w.n_bits, int(w.disable_zero_point),
+                                  _DT[x.dtype], ws.data_ptr(), ws.numel(), flags, _stream(x2)))
+    return y.view(*shp[:-1], w.N)
+
+
+def selftest_div(dtype: torch.dtype, device="cuda") -> int:
+    """Exhaustive check of the fast 16-bit division; returns the mismatch count."""
+    out = torch.zeros(1, dtype=torch.int64, device=device)
+    with torch.cuda.device(out.device):
+        check(lib.q100_selftest_div(_DT[dtype], out.data_ptr(), _stream(out)))
+    return int(out.item())

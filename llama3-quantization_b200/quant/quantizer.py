@@ -1,0 +1,285 @@
+"""Drop-in for the reference's ``quant/quantizer.py`` backed by the libq100 sm_100a kernels.
+
+Same class name, constructor keywords, attributes and method names as
+``/root/reference/quant/quantizer.py:23-165`` so that the reference's
+``models/int_llama_layer.py``, ``quant/omniquant.py``, ``quant/utils.py``,
+``models/transformation.py`` and ``main.py`` run unmodified on top of it.
+
+What changes underneath: ``forward`` no longer issues ~17 eager elementwise /
+reduction kernels (per_token_dynamic_calibration + fake_quant); it makes ONE call
+into ``q100_quantize_groupwise`` (K1/K2), which reproduces the reference's results
+bit-for-bit (tests/test_parity_quant.py).  There is no CPU path: a CPU tensor
+raises ``RuntimeError``.
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+import q100
+from q100 import ops as _ops
+
+CLIPMIN = 1e-5   # reference quantizer.py:10
+
+
+def round_ste(x: torch.Tensor):
+    """Straight-through rounding, reference quantizer.py:15-19 (kept for API parity)."""
+    return (x.round() - x).detach() + x
+
+
+# --------------------------------------------------------------------------------------
+# Backward of forward() expressed on the tensors the kernel returns.  It follows torch
+# autograd through the reference's op sequence (quantizer.py:94-159): STE for round_ste,
+# pass-through mask for clamp, zero gradient through zero_point.round(), amin/amax
+# gradients split evenly over ties, torch.max ties split in half.
+# --------------------------------------------------------------------------------------
+def fake_quant_backward(xg: torch.Tensor, gout: torch.Tensor, scale: torch.Tensor,
+                        zp: Optional[torch.Tensor], su: Optional[torch.Tensor], sl: Optional[torch.Tensor],
+                        n_bits: int, symmetric: bool, qmin: int, qmax: int,
+                        need_x: bool = True, need_lwc: bool = False):
+    """xg, gout: [groups, g]; scale/zp/su/sl: [groups, 1].  Returns (grad_x, grad_su, grad_sl)."""
+    v = xg / scale
+    t = v.round()
+    if zp is not None:
+        t = t + zp
+    inside = (t >= qmin) & (t <= qmax)
+    c = t.clamp(qmin, qmax)
+    cz = c - zp if zp is not None else c
+    m = inside.to(xg.dtype)
+    # d(deq)/dx through x/scale (STE) ; d(deq)/dscale = (c - zp) - mask * v
+    grad_x = gout * m if need_x else None
+    g_scale = (gout * (cz - m * v)).sum(dim=-1, keepdim=True)
+
+    xmin = xg.amin(dim=-1, keepdim=True)
+    xmax = xg.amax(dim=-1, keepdim=True)
+    xmax_c = xmax * su if su is not None else xmax
+    xmin_c = xmin * sl if sl is not None else xmin
+    if symmetric:
+        denom = 2 ** (n_bits - 1) - 1
+        a_hi, a_lo = xmax_c.abs(), xmin_c.abs()
+        s_raw = torch.max(a_hi, a_lo) / denom
+        live = ((s_raw >= CLIPMIN) & (s_raw <= 1e4)).to(xg.dtype)
+        g_abs = g_scale * live / denom
+        w_hi = (a_hi > a_lo).to(xg.dtype) + 0.5 * (a_hi == a_lo).to(xg.dtype)
+        g_xmax_c = g_abs * w_hi * torch.sign(xmax_c)
+        g_xmin_c = g_abs * (1.0 - w_hi) * torch.sign(xmin_c)
+    else:
+        denom = 2 ** n_bits - 1
+        s_raw = (xmax_c - xmin_c) / denom
+        live = ((s_raw >= CLIPMIN) & (s_raw <= 1e4)).to(xg.dtype)
+        g_xmax_c = g_scale * live / denom
+        g_xmin_c = -g_xmax_c
+    grad_su = grad_sl = None
+    if su is not None:
+        if need_lwc:
+            grad_su = g_xmax_c * xmax
+            grad_sl = g_xmin_c * xmin
+        g_xmax, g_xmin = g_xmax_c * su, g_xmin_c * sl
+    else:
+        g_xmax, g_xmin = g_xmax_c, g_xmin_c
+    if need_x:
+        is_max = (xg == xmax).to(xg.dtype)
+        is_min = (xg == xmin).to(xg.dtype)
+        grad_x = grad_x + is_max * (g_xmax / is_max.sum(dim=-1, keepdim=True)) \
+                        + is_min * (g_xmin / is_min.sum(dim=-1, keepdim=True))
+    return grad_x, grad_su, grad_sl
+
+
+class _FakeQuantFn(torch.autograd.Function):
+    """Forward = one libq100 pass; backward = :func:`fake_quant_backward`."""
+
+    @staticmethod
+    def forward(ctx, x2d, su, sl, group, n_bits, symmetric, disable_zp, qmin, qmax):
+        res = _ops.quantize_groupwise(x2d, group, n_bits, symmetric, disable_zp, su, sl)
+        ctx.save_for_backward(x2d, res.scales, res.zeros, su, sl)
+        ctx.cfg = (group, n_bits, symmetric, qmin, qmax)
+        ctx.mark_non_differentiable(res.scales)
+        if res.zeros is not None:
+            ctx.mark_non_differentiable(res.zeros)
+            return res.dequant, res.scales, res.zeros
+        return res.dequant, res.scales, None
+
+    @staticmethod
+    def backward(ctx, gout, _gs, _gz):
+        x2d, scale, zp, su, sl = ctx.saved_tensors
+        group, n_bits, symmetric, qmin, qmax = ctx.cfg
+        g = x2d.shape[1] if group in (0, None) else group
+        need_x = ctx.needs_input_grad[0]
+        need_lwc = su is not None and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
+        gx, gsu, gsl = fake_quant_backward(
+            x2d.reshape(-1, g), gout.reshape(-1, g), scale, zp, su, sl,
+            n_bits, symmetric, qmin, qmax, need_x, need_lwc)
+        if gx is not None:
+            gx = gx.reshape(x2d.shape)
+        return gx, gsu, gsl, None, None, None, None, None, None
+
+
+class UniformAffineQuantizer(nn.Module):
+    def __init__(
+        self,
+        n_bits: int = 8,
+        symmetric: bool = False,
+        per_channel_axes=[],
+        metric="minmax",
+        dynamic=False,
+        dynamic_method="per_cluster",
+        group_size=None,
+        shape=None,
+        lwc=False,
+        disable_zero_point=False,
+    ):
+        """Same signature and attributes as reference quantizer.py:24-83."""
+        super().__init__()
+        self.symmetric = symmetric
+        self.disable_zero_point = disable_zero_point
+        assert 2 <= n_bits <= 16, "bitwidth not supported"
+        self.n_bits = n_bits
+        self.change_n_bits(n_bits)
+        self.per_channel_axes = per_channel_axes
+        self.metric = metric
+        self.cluster_counts = None
+        self.cluster_dim = None
+
+        self.scale = None
+        self.zero_point = None
+        self.round_zero_point = None
+
+        self.cached_xmin = None
+        self.cached_xmax = None
+        self.dynamic = dynamic
+        self.dynamic_method = dynamic_method
+        self.deficiency = 0
+        self.lwc = lwc
+
+        init_value = 4.0             # init value of learnable weight clipping
+        if lwc:
+            if group_size:
+                dim1 = int(shape[0] * math.ceil(shape[1] / group_size))
+                self.deficiency = shape[-1] % group_size
+                if self.deficiency > 0:
+                    self.deficiency = group_size - self.deficiency
+                    assert self.symmetric   # support for mlc-llm symmetric quantization
+            else:
+                dim1 = shape[0]
+            self.upbound_factor = nn.Parameter(torch.ones((dim1, 1)) * init_value)
+            self.lowbound_factor = nn.Parameter(torch.ones((dim1, 1)) * init_value)
+        self.sigmoid = nn.Sigmoid()
+
+        self.enable = True
+        self.group_size = group_size
+        # packed twin of the last no-grad 2-D quantisation (consumed by QuantLinear's fused GEMM)
+        self.keep_packed = False
+        self._packed = None
+        self._packed_of = None
+
+    def change_n_bits(self, n_bits):
+        self.n_bits = n_bits
+        if self.disable_zero_point:
+            self.qmin = -(2 ** (n_bits - 1))
+            self.qmax = 2 ** (n_bits - 1) - 1
+        else:
+            self.qmin = 0
+            self.qmax = 2 ** (n_bits) - 1
+
+    # -- kept for API parity: the reference exposes these two as separate steps ------------
+    def per_token_dynamic_calibration(self, x):
+        """Sets ``self.scale`` / ``self.round_zero_point`` (reference quantizer.py:132-159)."""
+        self._run(x, want_dequant=False)
+
+    def fake_quant(self, x, scale, round_zero_point):
+        """Reference quantizer.py:94-115.  ``scale`` / ``round_zero_point`` are recomputed by the
+        fused kernel from ``x`` itself; they equal the arguments whenever those came from
+        ``per_token_dynamic_calibration(x)``, which is the only way the reference calls it."""
+        return self._run(x, want_dequant=True)
+
+    def forward(self, x: torch.Tensor):
+        if self.n_bits >= 16 or not self.enable:
+            return x
+        if self.metric == "fix0to1":
+            # reference quantizer.py:121-122; unreachable with shipped configs (n_bits == 16 there)
+            return x.mul_(2 ** self.n_bits - 1).round_().div_(2 ** self.n_bits - 1)
+        if self.dynamic_method == "per_token" or self.dynamic_method == "per_channel":
+            return self._run(x, want_dequant=True)
+        raise NotImplementedError()
+
+    # ---------------------------------------------------------------------------------------
+    def _lwc_multipliers(self, x):
+        """sigmoid(bound factors) in the dtype torch's type promotion gives ``sigmoid(f) * xmax``
+        (reference quantizer.py:143-145).  Returns (x in that dtype, up, low)."""
+        if not self.lwc:
+            return x, None, None
+        up = self.sigmoid(self.upbound_factor)
+        low = self.sigmoid(self.lowbound_factor)
+        cdt = torch.promote_types(x.dtype, up.dtype)
+        return x.to(cdt), up.to(cdt), low.to(cdt)
+
+    def _run(self, x: torch.Tensor, want_dequant: bool):
+        if not x.is_cuda:
+            raise RuntimeError("q100 UniformAffineQuantizer: CUDA tensor required -- there is no CPU fallback")
+        if self.n_bits > 8:
+            raise NotImplementedError(f"q100: n_bits={self.n_bits} (9..15) is not implemented")
+        orig_shape = x.shape
+        x, up, low = self._lwc_multipliers(x)
+        if self.group_size:
+            if x.dim() != 2:
+                # the reference reshapes for calibration and then asserts in fake_quant (quantizer.py:100)
+                raise AssertionError("only support linear layer now")
+            if self.deficiency > 0:
+                pad = torch.zeros((x.shape[0], self.deficiency), dtype=x.dtype, device=x.device)
+                x = torch.cat((x, pad), dim=1)
+            x2d, group = x, self.group_size
+            stat_shape = (-1, 1)
+        else:
+            x2d, group = x.reshape(-1, x.shape[-1]), 0
+            stat_shape = (*x.shape[:-1], 1)
+
+        need_grad = torch.is_grad_enabled() and (
+            x2d.requires_grad or (up is not None and (up.requires_grad or low.requires_grad)))
+        if need_grad:
+            deq, scale, zp = _FakeQuantFn.apply(x2d.contiguous(), up, low, group, self.n_bits,
+                                                bool(self.symmetric), bool(self.disable_zero_point),
+                                                self.qmin, self.qmax)
+            self._packed = self._packed_of = None
+        else:
+            keep = self.keep_packed and x2d.dim() == 2 and want_dequant and self.deficiency == 0 \
+                and self.n_bits in (2, 3, 4, 8) and x2d.dtype in (torch.float16, torch.bfloat16) \
+                and x2d.shape[1] % 128 == 0
+            res = _ops.quantize_groupwise(
+                x2d, group, self.n_bits, bool(self.symmetric), bool(self.disable_zero_point),
+                None if up is None else up.detach(), None if low is None else low.detach(),
+                want_dequant=want_dequant, want_packed=keep, want_meta=keep)
+            deq, scale, zp = res.dequant, res.scales, res.zeros
+            if keep:
+                g = x2d.shape[1] if group == 0 else group
+                self._packed = _ops.PackedWeight(res.packed, res.meta, res.scales, res.zeros, self.n_bits, g,
+                                                 x2d.shape[0], x2d.shape[1], bool(self.disable_zero_point))
+                self._packed_of = None    # filled below once the output tensor exists
+            else:
+                self._packed = self._packed_of = None
+        self.scale = scale.reshape(stat_shape)
+        self.round_zero_point = None if zp is None else zp.reshape(stat_shape)
+        if not want_dequant:
+            return None
+        if self.group_size and self.deficiency > 0:
+            deq = deq[:, :-self.deficiency]
+        out = deq.reshape(orig_shape)
+        if self._packed is not None:
+            self._packed_of = (out.data_ptr(), out._version, tuple(out.shape), out.dtype)
+        return out
+
+    def packed_for(self, w: torch.Tensor):
+        """PackedWeight twin of ``w`` if ``w`` is exactly the tensor the last forward returned."""
+        if self._packed is None or self._packed_of is None:
+            return None
+        if self._packed_of == (w.data_ptr(), w._version, tuple(w.shape), w.dtype):
+            return self._packed
+        return None
+
+    def register_scales_and_zeros(self):
+        self.register_buffer('scales', self.scale)
+        self.register_buffer('zeros', self.round_zero_point)
+        del self.scale
+        del self.round_zero_point
