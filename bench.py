@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the q100 hot path (driver contract).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): the seven QuantLinear GEMMs of ONE LLaMA3-8B decoder
+block, W4A16 g128, random-init weights, synthetic activations.  One "step" = one prefill
+pass (M = 2048 tokens) over q/k/v/o/gate/up/down.  Metric: dequant-GEMM TFLOP/s
+(2*M*N*K summed over the seven linears / step time).  The same JSON line also carries the
+decode-shape numbers (GB/s of packed-weight stream, M = 1 and 16) and the quantize kernel's
+GB/s, each with its roofline fraction.
+
+N > 1 (torchrun): tensor parallel -- q/k/v/gate/up column-sharded, o/down row-sharded, one
+NCCL all-reduce after each row-parallel GEMM; the block is fixed, so scaling is "strong".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (os.path.join(ROOT, "llama3-quantization_b200"), os.path.join(ROOT, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+HIDDEN, INTER, KV = 4096, 14336, 1024
+# name -> (N, K, input buffer)
+LINEARS = [("q_proj", HIDDEN, HIDDEN, "h"), ("k_proj", KV, HIDDEN, "h"), ("v_proj", KV, HIDDEN, "h"),
+           ("o_proj", HIDDEN, HIDDEN, "a"), ("gate_proj", INTER, HIDDEN, "h"), ("up_proj", INTER, HIDDEN, "h"),
+           ("down_proj", HIDDEN, INTER, "m")]
+PREFILL_M = 2048
+GROUP, WBITS = 128, 4
+METRIC = "w4a16_g128_dequant_gemm_tflops"
+UNIT = "TFLOP/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm": d["hbm_gbs"], "tc_burst": d["bf16_tflops"], "tc_sustained": d["bf16_tflops_sustained"],
+                "src": "measured"}
+    return {"hbm": 6650.0, "tc_burst": 1590.0, "tc_sustained": 1400.0, "src": "fallback"}
+
+
+def step_flops(M=PREFILL_M):
+    return sum(2.0 * M * n * k for _, n, k, _ in LINEARS)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+            except Exception:
+                continue
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """The reference's own CPU implementation of the path, on the host cores.
+
+    /root/reference does not exist on the GPU box and the reference is pure PyTorch (nothing to
+    compile into oracle/_ref), so this leg runs oracle/torch_port.py: the same eager torch op
+    sequence as quant/quantizer.py + quant/int_linear.py (pinned against the unmodified
+    reference by the golden fixtures), in the reference's post-calibration inference mode --
+    weights already fake-quantised, QuantLinear.forward == F.linear on the dense weight
+    (int_linear.py:56-62).  fp32 on CPU (the reference keeps fp16 for the GPU only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch_port as TP
+    torch.set_num_threads(os.cpu_count() or 1)
+    gen = torch.Generator().manual_seed(0)
+    M = PREFILL_M
+    weights = {}
+    with torch.no_grad():
+        for j, (name, n, k, _) in enumerate(LINEARS):
+            w = torch.randn(n, k, generator=gen) * 0.02
+            weights[name] = TP.fake_quant(w, WBITS, GROUP)[0]          # post-omniquant state
+        xs = {"h": torch.randn(M, HIDDEN, generator=gen), "a": torch.randn(M, HIDDEN, generator=gen),
+              "m": torch.randn(M, INTER, generator=gen)}
+
+        def step():
+            for name, n, k, src in LINEARS:
+                TP.quant_linear(xs[src], weights[name], None, WBITS, GROUP, requantize=False)
+
+        for _ in range(args.warmup):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        dt = (time.perf_counter() - t0) / args.steps
+    val = step_flops() / dt / 1e12
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "llama3-8b decoder block, 7 QuantLinear GEMMs, W4 g128 fake-quantised weights, "
+                                   "prefill M=2048", "where": "host CPU, torch eager"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                             "sample": "full step (7 linears, M=2048), fp32, torch CPU"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ our arm
+def timed(fn, iters, stream=None):
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    e.synchronize()
+    return s.elapsed_time(e) / iters          # ms
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import q100
+    from q100 import tp, _lib
+    from quant.int_linear import QuantLinear
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the q100 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    P = peaks()
+    dt_t = torch.bfloat16
+    flags = _lib.GEMM_FORCE_SKINNY if os.environ.get("Q100_BENCH_FORCE_SKINNY") else 0
+
+    # ---- weights: NB independent blocks so that successive decode steps stream from HBM, not L2
+    NB = 3
+    gen = torch.Generator(device=dev).manual_seed(0)
+    blocks = []
+    for b in range(NB):
+        blk = {}
+        for j, (name, n, k, _) in enumerate(LINEARS):
+            mode = tp.LLAMA_PLAN[name]
+            sh = tp.shard_bounds(n, k, mode, rank, world, GROUP)
+            gen.manual_seed(b * 7 + j)                              # same full weight on every rank
+            w = (torch.randn(n, k, generator=gen, device=dev) * 0.02).to(dt_t)
+            wl = w[sh.n0:sh.n1, sh.k0:sh.k1].contiguous()
+            pw, _ = q100.pack_weight(wl, WBITS, GROUP)
+            blk[name] = (pw, mode)
+            del w, wl
+        blocks.append(blk)
+    torch.cuda.synchronize()
+
+    def make_inputs(M):
+        g2 = torch.Generator(device=dev).manual_seed(1)
+        full = {"h": torch.randn(M, HIDDEN, generator=g2, device=dev).to(dt_t),
+                "a": torch.randn(M, HIDDEN, generator=g2, device=dev).to(dt_t),
+                "m": torch.randn(M, INTER, generator=g2, device=dev).to(dt_t)}
+        return {k: v for k, v in full.items()}
+
+    launches = [0]
+
+    def block_step(blk, xs):
+        outs = []
+        for name, n, k, src in LINEARS:
+            pw, mode = blk[name]
+            x = tp.shard_input(xs[src], mode, rank, world) if world > 1 else xs[src]
+            y = q100.gemm_wna16(x, pw, None, flags)
+            launches[0] += 1
+            tp.reduce_output(y, mode)
+            outs.append(y)
+        return outs
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # =============== headline: prefill M = 2048 ===============
+    xs = make_inputs(PREFILL_M)
+    it = [0]
+
+    def prefill_step():
+        block_step(blocks[it[0] % NB], xs)
+        it[0] += 1
+
+    for _ in range(max(args.warmup, 3)):
+        prefill_step()
+    sync_all()
+    sampler = ClockSampler(local) if rank == 0 else None
+    launches[0] = 0
+    ms = timed(prefill_step, args.steps)
+    sync_all()
+    clocks = sampler.stop() if sampler else None
+    n_launch = launches[0]
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    value = step_flops() / (ms * 1e-3) / 1e12
+
+    # per-launch duration of the dominant kernel (tcgen05 dequant-GEMM on up_proj), events on the launch stream
+    pw_up, mode_up = blocks[0]["up_proj"]
+    x_up = tp.shard_input(xs["h"], mode_up, rank, world) if world > 1 else xs["h"]
+    ms_up = min(timed(lambda: q100.gemm_wna16(x_up, pw_up, None, flags), 10) for _ in range(3))
+    fl_up = 2.0 * PREFILL_M * pw_up.N * pw_up.K
+    ach = fl_up / (ms_up * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": "k3_tc (W4A16 g128 dequant-GEMM, up_proj 14336x4096, M=2048)",
+                "achieved": ach, "peak": P["tc_burst"], "unit": "TFLOP/s", "frac": ach / P["tc_burst"],
+                "peak_src": P["src"] + " cuBLAS bf16 burst", "traffic": None,
+                "frac_of_sustained": ach / P["tc_sustained"]}
+
+    # =============== decode shapes: packed-weight stream GB/s ===============
+    decode = {}
+    for M in (1, 16):
+        xd = make_inputs(M)
+        jt = [0]
+
+        def dstep():
+            block_step(blocks[jt[0] % NB], xd)
+            jt[0] += 1
+
+        for _ in range(6):
+            dstep()
+        sync_all()
+        msd = timed(dstep, 30)
+        esz = 2
+        byts = sum(blocks[0][nm][0].nbytes() + M * blocks[0][nm][0].K * esz + M * blocks[0][nm][0].N * esz
+                   for nm, *_ in LINEARS)
+        gbs = byts / (msd * 1e-3) / 1e9
+        decode[f"M{M}"] = {"ms_per_block": msd, "algorithmic_MB": byts / 1e6, "GBps": gbs, "frac_hbm": gbs / P["hbm"],
+                           "launches_per_block": 7}
+
+    # =============== quantize kernel (K1): fake-quant and pack modes on up_proj ===============
+    quant = {}
+    if rank == 0:
+        wq = [(torch.randn(INTER, HIDDEN, device=dev) * 0.02).to(torch.float16) for _ in range(3)]
+        qi = [0]
+
+        def q_fake():
+            q100.quantize_groupwise(wq[qi[0] % 3], GROUP, WBITS, want_dequant=True)
+            qi[0] += 1
+
+        def q_pack():
+            q100.quantize_groupwise(wq[qi[0] % 3], GROUP, WBITS, want_dequant=False, want_packed=True)
+            qi[0] += 1
+
+        n_el = INTER * HIDDEN
+        for nm, fn, bpe in (("fake_quant_f16", q_fake, 4.03125), ("pack_f16", q_pack, 2.53125)):
+            for _ in range(5):
+                fn()
+            torch.cuda.synchronize()
+            msq = timed(fn, 30)
+            gbs = n_el * bpe / (msq * 1e-3) / 1e9
+            quant[nm] = {"ms": msq, "GBps": gbs, "frac_hbm": gbs / P["hbm"], "bytes_per_element": bpe}
+        del wq
+
+    # =============== e2e: module API, host buffers, H2D + D2H inside the timed region ===============
+    e2e = None
+    cpu_base = None
+    if rank == 0 and world == 1:
+        class _Lin:      # minimal nn.Linear stand-in holding the (full) fake-quantised weight
+            pass
+        mods = []
+        g3 = torch.Generator(device=dev)
+        for j, (name, n, k, src) in enumerate(LINEARS):
+            g3.manual_seed(j)
+            lin = torch.nn.Linear(k, n, bias=False, device=dev, dtype=dt_t)
+            with torch.no_grad():
+                lin.weight.copy_((torch.randn(n, k, generator=g3, device=dev) * 0.02).to(dt_t))
+            ql = QuantLinear(lin, {"n_bits": WBITS, "per_channel_axes": [0], "symmetric": False,
+                                   "dynamic_method": "per_channel", "group_size": GROUP, "lwc": False,
+                                   "disable_zero_point": False},
+                             {"n_bits": 16, "per_channel_axes": [], "symmetric": False, "dynamic_method": "per_token"})
+            ql.set_quant_state(True, False)
+            mods.append((ql, src))
+        hin = {k: v.cpu().pin_memory() for k, v in xs.items()}
+        hout = [torch.empty(PREFILL_M, n, dtype=dt_t).pin_memory() for _, n, _, _ in LINEARS]
+        din = {k: torch.empty_like(v) for k, v in xs.items()}
+
+        def e2e_step():
+            with torch.no_grad():
+                for k in din:
+                    din[k].copy_(hin[k], non_blocking=True)
+                for (ql, src), ho in zip(mods, hout):
+                    ho.copy_(ql(din[src]), non_blocking=True)
+            torch.cuda.synchronize()
+
+        for _ in range(3):
+            e2e_step()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            e2e_step()
+        dte = (time.perf_counter() - t0) / args.steps
+        e2e = {"value": step_flops() / dte / 1e12, "unit": UNIT, "ms_per_step": dte * 1e3,
+               "h2d_bytes_per_step": sum(v.numel() * 2 for v in hin.values()),
+               "d2h_bytes_per_step": sum(h.numel() * 2 for h in hout),
+               "api": "quant.int_linear.QuantLinear.forward (use_weight_quant=True), pinned host buffers"}
+        del mods
+
+        # ---- CPU baseline on the host cores: bounded sample of the same workload (torch port)
+        import torch_port as TP
+        torch.set_num_threads(os.cpu_count() or 1)
+        with torch.no_grad():
+            gc = torch.Generator().manual_seed(0)
+            ws = {}
+            for name, n, k, _ in LINEARS:
+                ws[name] = TP.fake_quant(torch.randn(n, k, generator=gc) * 0.02, WBITS, GROUP)[0]
+            Ms = 512
+            xc = {"h": torch.randn(Ms, HIDDEN), "a": torch.randn(Ms, HIDDEN), "m": torch.randn(Ms, INTER)}
+
+            def cstep():
+                for name, n, k, src in LINEARS:
+                    TP.quant_linear(xc[src], ws[name], None, WBITS, GROUP, requantize=False)
+            cstep()
+            t0 = time.perf_counter()
+            reps = 0
+            while reps < 3 or (time.perf_counter() - t0 < 8 and reps < 50):
+                cstep()
+                reps += 1
+            dtc = (time.perf_counter() - t0) / reps
+            wq_cpu = torch.randn(INTER, HIDDEN) * 0.02
+            t1 = time.perf_counter()
+            TP.fake_quant(wq_cpu, WBITS, GROUP)
+            tq = time.perf_counter() - t1
+        cpu_base = {"value": step_flops(Ms) / dtc / 1e12, "unit": UNIT, "cores": torch.get_num_threads(),
+                    "kind": "port",
+                    "sample": f"7 linears of the block at M={Ms} (of 2048), fp32, {reps} reps, torch eager on host cores",
+                    "fake_quant_up_proj_ms": tq * 1e3}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "llama3-8b decoder block: 7 QuantLinear GEMMs (q,k,v,o,gate,up,down), "
+                                       "W4A16 g128, prefill M=2048",
+                           "parallelism": f"tp{world}" if world > 1 else "single",
+                           "l2": "3 weight sets rotated; per-step working set (109 MB packed weights + 270 MB "
+                                 "activations/outputs) exceeds the 126 MB L2",
+                           "force_skinny": bool(flags)},
+                "roofline": roofline, "decode": decode, "quantize": quant, "cpu_baseline": cpu_base, "e2e": e2e,
+                "gpu_launches": n_launch, "clocks": clocks, "peaks": P}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -139,6 +139,13 @@ size_t q100_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int n_bits, in
  * writes the mismatch count to *mismatches_out (device uint64).
  */
 int q100_selftest_div(int dtype, void* mismatches_out, void* stream);
+/*
+ * q100_debug_gemm_dense_tc: y[M, N] = x[M, K] . w[N, K]^T for DENSE fp16/bf16 w through the
+ * tcgen05 kernel's TMA / UMMA-descriptor / TMEM plumbing (B tile loaded by TMA instead of
+ * being dequantised).  Regression hook for the tensor-core path; not a product entry point.
+ */
+int q100_debug_gemm_dense_tc(const void* x, const void* w, void* y, int64_t M, int64_t N, int64_t K,
+                             int dtype, void* stream);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

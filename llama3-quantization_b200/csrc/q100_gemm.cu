@@ -19,6 +19,8 @@ int gemm_tc(const void* x, const void* packed, const void* meta, const void* bia
             int64_t M, int64_t N, int64_t K, int group, int n_bits, int disable_zp, int dtype,
             cudaStream_t st);
 bool gemm_tc_supported(int64_t M, int64_t N, int64_t K, int group, int n_bits);
+int gemm_tc_dense(const void* x, const void* w, void* y, int64_t M, int64_t N, int64_t K, int dtype,
+                  cudaStream_t st);
 
 // ---------------------------------------------------------------- tensor maps
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
@@ -100,4 +102,13 @@ extern "C" int q100_gemm_wna16(const void* x, const void* packed, const void* me
     if (rc != Q100_OK) return rc;
   }
   return Q100_OK;
+}
+
+extern "C" int q100_debug_gemm_dense_tc(const void* x, const void* w, void* y, int64_t M, int64_t N, int64_t K,
+                                        int dtype, void* stream) {
+  Q100_REQUIRE(x && w && y, Q100_EINVAL, "NULL pointer argument");
+  Q100_REQUIRE(dtype == Q100_F16 || dtype == Q100_BF16, Q100_EUNSUPPORTED, "fp16 / bf16 only");
+  int rc = ensure_device();
+  if (rc != Q100_OK) return rc;
+  return gemm_tc_dense(x, w, y, M, N, K, dtype, reinterpret_cast<cudaStream_t>(stream));
 }

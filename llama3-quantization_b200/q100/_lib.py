@@ -33,6 +33,7 @@ SIGNATURES = {
     "q100_gemm_wna16": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _sz, _i, _vp]),
     "q100_gemm_workspace_bytes": (_sz, [_i64, _i64, _i64, _i, _i]),
     "q100_selftest_div": (_i, [_i, _vp, _vp]),
+    "q100_debug_gemm_dense_tc": (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _i, _vp]),
 }
 
 

@@ -206,3 +206,15 @@ def selftest_div(dtype: torch.dtype, device="cuda") -> int:
     with torch.cuda.device(out.device):
         check(lib.q100_selftest_div(_DT[dtype], out.data_ptr(), _stream(out)))
     return int(out.item())
+
+
+def debug_gemm_dense_tc(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
+    """x[M,K] @ w[N,K]^T through the tcgen05 plumbing with a dense 16-bit weight (regression hook)."""
+    _require_cuda(x, w)
+    x = x.contiguous()
+    w = w.contiguous()
+    y = torch.empty((x.shape[0], w.shape[0]), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.q100_debug_gemm_dense_tc(x.data_ptr(), w.data_ptr(), y.data_ptr(), x.shape[0], w.shape[0],
+                                           x.shape[1], _DT[x.dtype], _stream(x)))
+    return y

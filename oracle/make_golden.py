@@ -92,7 +92,7 @@ def run_weight_case(name, w_t, dtype, n_bits, group, symmetric=False, disable_zp
         "dtype": dtype, "n_bits": n_bits, "group": group or 0, "symmetric": int(symmetric),
         "disable_zp": int(disable_zp), "lwc": int(lwc), "deficiency": int(q.deficiency),
         "w": t2bits(w_t), "dequant": t2bits(deq), "scales": t2bits(q.scale),
-        "codes": codes.float().numpy().astype(np.int16),
+        "codes": np.nan_to_num(codes.float().numpy(), nan=-32768).astype(np.int16),   # NaN code -> -32768
     }
     if q.round_zero_point is not None:
         rec["zeros"] = t2bits(q.round_zero_point)

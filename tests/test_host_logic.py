@@ -1,0 +1,120 @@
+"""CPU: the drop-in module surface (names, attributes, error behaviour of the reference)
+and the custom backward against torch autograd through the torch port."""
+import pytest
+import torch
+import torch.nn as nn
+
+import torch_port as TP
+from quant.quantizer import UniformAffineQuantizer, fake_quant_backward, round_ste, CLIPMIN
+from quant.int_linear import QuantLinear
+from quant.int_matmul import QuantMatMul
+
+WQ = {"n_bits": 4, "per_channel_axes": [0], "symmetric": False, "dynamic_method": "per_channel",
+      "group_size": 128, "lwc": True, "disable_zero_point": False}
+AQ = {"n_bits": 16, "per_channel_axes": [], "symmetric": False, "dynamic_method": "per_token"}
+
+
+def test_quantizer_surface():
+    q = UniformAffineQuantizer(**WQ, shape=(64, 512))
+    for attr in ("n_bits", "qmin", "qmax", "scale", "round_zero_point", "zero_point", "group_size", "deficiency",
+                 "enable", "lwc", "symmetric", "disable_zero_point", "upbound_factor", "lowbound_factor",
+                 "sigmoid", "metric", "dynamic_method", "per_channel_axes", "cached_xmin", "cached_xmax"):
+        assert hasattr(q, attr), attr
+    assert (q.qmin, q.qmax) == (0, 15)
+    assert q.upbound_factor.shape == (64 * 4, 1) and float(q.upbound_factor[0]) == 4.0
+    assert {n for n, _ in q.named_parameters()} == {"upbound_factor", "lowbound_factor"}
+    q.change_n_bits(3)
+    assert (q.n_bits, q.qmin, q.qmax) == (3, 0, 7)
+    qs = UniformAffineQuantizer(n_bits=4, disable_zero_point=True)
+    assert (qs.qmin, qs.qmax) == (-8, 7)
+    with pytest.raises(AssertionError):
+        UniformAffineQuantizer(n_bits=1)
+    # deficiency only with lwc + symmetric (reference quantizer.py:70-75)
+    qd = UniformAffineQuantizer(n_bits=4, symmetric=True, group_size=128, shape=(8, 200), lwc=True)
+    assert qd.deficiency == 56 and qd.upbound_factor.shape == (16, 1)
+    with pytest.raises(AssertionError):
+        UniformAffineQuantizer(n_bits=4, symmetric=False, group_size=128, shape=(8, 200), lwc=True)
+
+
+def test_quantizer_identity_and_errors():
+    x = torch.randn(4, 128)
+    q16 = UniformAffineQuantizer(n_bits=16, metric="fix0to1")
+    assert q16(x) is x                                   # reference quantizer.py:119-120
+    q = UniformAffineQuantizer(n_bits=4, dynamic_method="per_token")
+    q.enable = False
+    assert q(x) is x
+    q.enable = True
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        q(x)
+    with pytest.raises(NotImplementedError):
+        UniformAffineQuantizer(n_bits=4, dynamic_method="per_cluster")(x)
+    assert torch.equal(round_ste(torch.tensor([0.5, 1.5, 2.4])), torch.tensor([0.0, 2.0, 2.0]))
+    assert CLIPMIN == 1e-5
+
+
+def test_register_scales_and_zeros():
+    q = UniformAffineQuantizer(n_bits=4, dynamic_method="per_channel", group_size=128)
+    q.scale = torch.ones(4, 1)
+    q.round_zero_point = torch.zeros(4, 1)
+    q.register_scales_and_zeros()
+    assert set(q.state_dict()) == {"scales", "zeros"} and not hasattr(q, "scale")
+
+
+def test_quantlinear_surface_and_passthrough():
+    lin = nn.Linear(256, 64)
+    ql = QuantLinear(lin, WQ, AQ)
+    assert set(dict(ql.named_buffers())) == {"weight", "bias"}
+    assert ql.in_features == 256 and ql.out_features == 64
+    assert not ql.use_weight_quant and not ql.use_act_quant and not ql.use_temporary_parameter
+    assert isinstance(ql.weight_quantizer, UniformAffineQuantizer) and ql.weight_quantizer.group_size == 128
+    x = torch.randn(3, 256)
+    assert torch.equal(ql(x), torch.nn.functional.linear(x, lin.weight, lin.bias))
+    # temporary parameters take precedence (reference int_linear.py:49-51)
+    ql.temp_weight = torch.zeros_like(lin.weight)
+    ql.temp_bias = None
+    ql.use_temporary_parameter = True
+    assert float(ql(x).abs().max()) == 0.0
+    ql.use_temporary_parameter = False
+    ql.set_quant_state(True, True)
+    assert ql.use_weight_quant and ql.use_act_quant
+    nb = QuantLinear(nn.Linear(8, 8, bias=False), {"n_bits": 4, "group_size": None, "dynamic_method": "per_channel"}, AQ,
+                     disable_input_quant=True)
+    assert nb.bias is None and nb.act_quantizer is None
+    # parameter selection by substring, as quant/utils.py:16-21 does
+    assert sorted(n for n, _ in ql.named_parameters() if "bound_factor" in n) == [
+        "weight_quantizer.lowbound_factor", "weight_quantizer.upbound_factor"]
+
+
+def test_quantmatmul_surface():
+    mm = QuantMatMul(AQ, AQ, matmul_func=torch.matmul)
+    a, b = torch.randn(2, 3, 4), torch.randn(2, 4, 5)
+    assert torch.equal(mm(a, b), torch.matmul(a, b))
+    assert mm.quant_x1(a) is a                       # use_act_quant False
+    mm.set_quant_state(False, True)
+    assert mm.quant_x1(a) is a                       # 16 bit => identity
+    assert mm.use_act_quant and mm.x1_quantizer.n_bits == 16
+
+
+@pytest.mark.parametrize("bits,sym,lwc,group", [(4, False, True, 128), (3, False, False, 128), (2, True, True, 128),
+                                                (4, True, False, None), (8, False, False, None), (4, False, True, None)])
+def test_backward_matches_autograd(bits, sym, lwc, group):
+    torch.manual_seed(bits * 7 + int(sym))
+    w = (torch.randn(16, 512) * 0.02).requires_grad_(True)
+    ng = 16 * (512 // group) if group else 16
+    up = (4 + torch.randn(ng, 1)).requires_grad_(True) if lwc else None
+    low = (4 + torch.randn(ng, 1)).requires_grad_(True) if lwc else None
+    out, scale, zp = TP.fake_quant(w, bits, group, sym, False, up, low)
+    go = torch.randn_like(out)
+    out.backward(go)
+    g = group or 512
+    su = torch.sigmoid(up.detach()) if lwc else None
+    sl = torch.sigmoid(low.detach()) if lwc else None
+    gx, gsu, gsl = fake_quant_backward(w.detach().reshape(-1, g), go.reshape(-1, g), scale.detach(),
+                                       zp.detach(), su, sl, bits, sym, 0, 2 ** bits - 1, True, lwc)
+    ref = w.grad
+    assert float((gx.reshape(ref.shape) - ref).abs().max()) <= 1e-5 * float(ref.abs().max())
+    if lwc:
+        gu = gsu * su * (1 - su)
+        gl = gsl * sl * (1 - sl)
+        assert float((gu - up.grad).abs().max()) <= 1e-4 * float(up.grad.abs().max() + 1e-12)
+        assert float((gl - low.grad).abs().max()) <= 1e-4 * float(low.grad.abs().max() + 1e-12)

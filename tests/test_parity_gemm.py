@@ -1,0 +1,144 @@
+"""GPU: fused dequant-GEMM (K3) through the C ABI against the oracle.
+
+The dequantised weight the kernel rebuilds in registers is bit-identical to the oracle's
+fake-quantised weight, so the only difference to ``F.linear`` on that weight is the fp32
+accumulation order.  Tolerance (stated here, used everywhere): with
+``ref = float64 matmul of the same fp16/bf16 operands``,
+    |y - ref| <= 2 * eps_out * |ref| + 8 * eps_acc * sum_k |x_k * w_k|  (+ tiny absolute term)
+where eps_out = 2^-11 (fp16) / 2^-8 (bf16) is the output rounding and eps_acc = 2^-24 the
+fp32 accumulator rounding.
+"""
+import numpy as np
+import pytest
+import torch
+
+import q100
+import q100_oracle as O
+from q100 import _lib
+from conftest import TDT, bits_to_torch, load_golden, torch_to_bits
+
+pytestmark = pytest.mark.gpu
+EPS_OUT = {"f16": 2.0 ** -11, "bf16": 2.0 ** -8}
+
+
+def _check(y, x, wdeq, bias, dtype):
+    x64 = x.double().cpu().numpy().reshape(-1, x.shape[-1])
+    w64 = wdeq.double().cpu().numpy()
+    ref = x64 @ w64.T
+    mag = np.abs(x64) @ np.abs(w64).T
+    if bias is not None:
+        ref = ref + bias.double().cpu().numpy()
+        mag = mag + np.abs(bias.double().cpu().numpy())
+    got = y.double().cpu().numpy().reshape(ref.shape)
+    tol = 2 * EPS_OUT[dtype] * np.abs(ref) + 8 * 2.0 ** -24 * mag + 1e-7
+    bad = np.abs(got - ref) > tol
+    assert not bad.any(), f"{int(bad.sum())}/{bad.size} outside tolerance, max abs err {np.abs(got - ref).max():.3e}"
+    return float(np.abs(got - ref).max()), float(np.abs(ref).max())
+
+
+def _make(N, K, M, dtype, n_bits, group, seed, nozp=False, sym=False):
+    gen = torch.Generator().manual_seed(seed)
+    w = (torch.randn(N, K, generator=gen) * 0.02).to(TDT[dtype]).cuda()
+    x = torch.randn(M, K, generator=gen).to(TDT[dtype]).cuda()
+    pw, r = q100.pack_weight(w, n_bits, group, sym, nozp, want_dequant=True)
+    return x, w, pw, r
+
+
+@pytest.mark.parametrize("dtype", ["f16", "bf16"])
+@pytest.mark.parametrize("n_bits", [4, 2, 3, 8])
+@pytest.mark.parametrize("M", [1, 2, 5, 8, 9, 16, 17, 32])
+def test_skinny_vs_oracle(dtype, n_bits, M):
+    N, K = 384, 1024
+    x, w, pw, r = _make(N, K, M, dtype, n_bits, 128, 1000 + M + n_bits)
+    # the packed twin is consistent with the oracle (bit-exact)
+    o = O.quantize_groupwise(O.from_bits(torch_to_bits(w), dtype).reshape(N, K), dtype, 128, n_bits)
+    assert np.array_equal(pw.packed.cpu().numpy().view(np.uint32), O.pack_codes(o["codes"], n_bits))
+    y = q100.gemm_wna16(x, pw, None, flags=_lib.GEMM_FORCE_SKINNY)
+    torch.cuda.synchronize()
+    wdeq = torch.from_numpy(o["dequant"])
+    _check(y, x, wdeq, None, dtype)
+
+
+@pytest.mark.parametrize("dtype", ["f16", "bf16"])
+@pytest.mark.parametrize("N,K,group", [(128, 128, 128), (136, 384, 128), (1024, 4096, 128), (4096, 4096, 128),
+                                       (512, 14336, 128), (256, 512, 64), (256, 512, 32), (256, 1024, 256),
+                                       (256, 1024, 0), (6144, 4096, 128)])
+def test_skinny_shapes(dtype, N, K, group):
+    for M, bias in ((1, False), (16, True)):
+        x, w, pw, r = _make(N, K, M, dtype, 4, group or None, N + K + M)
+        b = (torch.randn(N) * 0.1).to(TDT[dtype]).cuda() if bias else None
+        y = q100.gemm_wna16(x, pw, b, flags=_lib.GEMM_FORCE_SKINNY)
+        torch.cuda.synchronize()
+        _check(y, x, r.dequant, b, dtype)
+
+
+@pytest.mark.parametrize("dtype", ["f16", "bf16"])
+def test_skinny_symmetric_and_nozp(dtype):
+    for n_bits in (2, 3, 4, 8):
+        for sym, nozp in ((True, False), (True, True)):
+            x, w, pw, r = _make(256, 512, 4, dtype, n_bits, 128, 77 + n_bits, nozp=nozp, sym=sym)
+            y = q100.gemm_wna16(x, pw, None, flags=_lib.GEMM_FORCE_SKINNY)
+            _check(y, x, r.dequant, None, dtype)
+
+
+def test_skinny_deterministic_and_workspace_clean():
+    x, w, pw, r = _make(4096, 4096, 16, "bf16", 4, 128, 5)
+    y1 = q100.gemm_wna16(x, pw, None, flags=_lib.GEMM_FORCE_SKINNY)
+    y2 = q100.gemm_wna16(x, pw, None, flags=_lib.GEMM_FORCE_SKINNY)
+    torch.cuda.synchronize()
+    assert torch.equal(y1.view(torch.int16), y2.view(torch.int16))
+    from q100 import ops
+    for ws in ops._WORKSPACES.values():
+        n_tiles_bytes = 4096 // 128 * 4
+        assert int(ws[:n_tiles_bytes].abs().sum()) == 0, "tile counters must return to zero"
+
+
+def test_weird_zero_points():
+    """Zero-points outside [0, 2^n-1] (all-positive / all-negative / constant groups)."""
+    torch.manual_seed(3)
+    w = torch.randn(128, 256) * 0.02
+    w[0:8] = w[0:8].abs() + 0.5
+    w[8:16] = -(w[8:16].abs() + 0.5)
+    w[16:24] = 0.3
+    w[24:32] = 0.0
+    w = w.half().cuda()
+    x = torch.randn(3, 256).half().cuda()
+    pw, r = q100.pack_weight(w, 4, 128, want_dequant=True)
+    y = q100.gemm_wna16(x, pw, None, flags=_lib.GEMM_FORCE_SKINNY)
+    _check(y, x, r.dequant, None, "f16")
+
+
+L = load_golden("linear")
+
+
+@pytest.mark.parametrize("case", sorted(c for c in L if "f32" not in c and "a16" in c))
+def test_golden_linear_through_module(case):
+    """QuantLinear drop-in (weight re-quantised each call, int_linear.py:52-53) vs the
+    reference's own output stored in the fixture."""
+    import torch.nn as nn
+    from quant.int_linear import QuantLinear
+    rec = L[case]
+    dtype = str(rec["dtype"])
+    w = bits_to_torch(rec["w"], dtype)
+    lin = nn.Linear(w.shape[1], w.shape[0], bias=True).to(TDT[dtype])
+    with torch.no_grad():
+        lin.weight.copy_(w)
+        lin.bias.copy_(bits_to_torch(rec["bias"], dtype))
+    lin = lin.cuda()
+    ql = QuantLinear(lin, {"n_bits": int(rec["w_bits"]), "per_channel_axes": [0], "symmetric": False,
+                           "dynamic_method": "per_channel", "group_size": int(rec["group"]) or None,
+                           "lwc": False, "disable_zero_point": False},
+                     {"n_bits": int(rec["a_bits"]), "per_channel_axes": [], "symmetric": False,
+                      "dynamic_method": "per_token"})
+    ql.set_quant_state(True, False)
+    x = bits_to_torch(rec["x"], dtype, "cuda")
+    with torch.no_grad():
+        y = ql(x)
+    yr = bits_to_torch(rec["y"], dtype).float()
+    # N = 48 is a multiple of 8 and K = 512 of 128 => the fused kernel ran
+    assert ql._requant_cache is not None
+    err = float((y.float().cpu() - yr).abs().max())
+    tol = 4 * EPS_OUT[dtype] * max(float(yr.abs().max()), 1.0)
+    assert err <= tol, (err, tol)
+    # reference side effects: scale / round_zero_point live on the quantizer
+    assert ql.weight_quantizer.scale.shape == (w.shape[0] * (w.shape[1] // (int(rec["group"]) or w.shape[1])), 1)

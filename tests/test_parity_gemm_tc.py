@@ -1,0 +1,54 @@
+"""GPU: the tcgen05 path (K3b).  First the TMA / UMMA / TMEM plumbing alone on a dense
+16-bit weight, then the fused dequant-GEMM against the oracle, same tolerance as the
+skinny kernel (tests/test_parity_gemm.py)."""
+import numpy as np
+import pytest
+import torch
+
+import q100
+import q100_oracle as O
+from q100 import _lib, ops
+from conftest import TDT, torch_to_bits
+from test_parity_gemm import _check, _make
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f16"])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (128, 256, 64), (128, 256, 256), (256, 512, 1024),
+                                   (200, 384, 512), (2048, 1024, 4096)])
+def test_dense_plumbing(dtype, M, N, K):
+    gen = torch.Generator().manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=gen).to(TDT[dtype]).cuda()
+    w = (torch.randn(N, K, generator=gen) * 0.05).to(TDT[dtype]).cuda()
+    y = ops.debug_gemm_dense_tc(x, w)
+    torch.cuda.synchronize()
+    _check(y, x, w, None, dtype)
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f16"])
+@pytest.mark.parametrize("M,N,K,group", [(128, 128, 128, 128), (128, 256, 128, 128), (64, 256, 512, 128),
+                                         (200, 384, 1024, 128), (2048, 1024, 4096, 128), (256, 512, 512, 64),
+                                         (256, 512, 1024, 256), (256, 512, 1024, 0), (2048, 4096, 4096, 128)])
+def test_tc_vs_oracle(dtype, M, N, K, group):
+    x, w, pw, r = _make(N, K, M, dtype, 4, group or None, M + N + K)
+    b = (torch.randn(N) * 0.1).to(TDT[dtype]).cuda()
+    y = q100.gemm_wna16(x, pw, b, flags=_lib.GEMM_FORCE_TC)
+    torch.cuda.synchronize()
+    _check(y, x, r.dequant, b, dtype)
+    if N * K <= 1 << 20:       # oracle-side check that the fake-quantised weight itself is right
+        o = O.quantize_groupwise(O.from_bits(torch_to_bits(w), dtype).reshape(N, K), dtype, group, 4)
+        assert np.array_equal(torch_to_bits(r.dequant), O.to_bits(o["dequant"], dtype))
+
+
+def test_tc_matches_skinny_bits_of_weight():
+    """Both GEMM paths rebuild the same weight: on an identity-like x they must agree exactly."""
+    N, K = 256, 256
+    gen = torch.Generator().manual_seed(9)
+    w = (torch.randn(N, K, generator=gen) * 0.02).to(torch.bfloat16).cuda()
+    pw, r = q100.pack_weight(w, 4, 128, want_dequant=True)
+    x = torch.eye(K, dtype=torch.bfloat16, device="cuda")          # y = dequant(W)^T exactly
+    y_tc = q100.gemm_wna16(x, pw, None, flags=_lib.GEMM_FORCE_TC)
+    assert torch.equal(y_tc.t().contiguous().view(torch.int16), r.dequant.view(torch.int16))
+    y_sk = q100.gemm_wna16(x[:32].contiguous(), pw, None, flags=_lib.GEMM_FORCE_SKINNY)
+    assert torch.equal(y_sk.view(torch.int16), y_tc[:32].contiguous().view(torch.int16))
