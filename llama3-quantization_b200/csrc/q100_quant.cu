@@ -579,9 +579,9 @@ extern "C" int q100_quantize_groupwise(const void* x, int dtype, int64_t rows, i
                                        void* dequant_out, void* packed_out,
                                        void* scales_out, void* zeros_out, void* meta_out,
                                        int flags, void* stream) {
-  Q100_REQUIRE(x != nullptr, Q100_EINVAL, "x is NULL");
   Q100_REQUIRE(dtype >= 0 && dtype <= 2, Q100_EINVAL, "bad dtype %d", dtype);
   Q100_REQUIRE(rows >= 0 && cols >= 0, Q100_EINVAL, "negative shape");
+  Q100_REQUIRE(x != nullptr || rows == 0 || cols == 0, Q100_EINVAL, "x is NULL");
   Q100_REQUIRE(n_bits >= 2 && n_bits <= 15, Q100_EINVAL,
                "n_bits=%d: the quantizer handles 2..15 (>= 16 is the identity, quantizer.py:119)", n_bits);
   // 9..15 bits: qmax is not representable in bf16 and the reference's clamp then depends on

@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--which", default="k1,k1pack,k2,skinny1,skinny16,tc")
     ap.add_argument("--iters", type=int, default=3)
     ap.add_argument("--dtype", default="bf16")
+    ap.add_argument("--graph", action="store_true", help="time each kernel inside a CUDA graph (no launch gaps)")
     a = ap.parse_args()
     which = a.which.split(",")
     dt = {"bf16": torch.bfloat16, "f16": torch.float16}[a.dtype]
@@ -45,6 +46,26 @@ def main():
         e.record()
         e.synchronize()
         ms = s.elapsed_time(e) / a.iters
+        if a.graph:
+            g = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for i in range(3):
+                    fn(i)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                for i in range(a.iters):
+                    fn(i)
+            g.replay()
+            torch.cuda.synchronize()
+            s.record()
+            for _ in range(3):
+                g.replay()
+            e.record()
+            e.synchronize()
+            ms = s.elapsed_time(e) / (3 * a.iters)
         msg = f"{name:10s} {ms * 1e3:9.1f} us"
         if algo_bytes:
             msg += f"  {algo_bytes / ms / 1e6:8.1f} GB/s"
