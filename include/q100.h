@@ -55,6 +55,9 @@ enum q100_status {
 /* flags for the GEMM entry points */
 #define Q100_GEMM_FORCE_SKINNY 0x1 /* always use the mma.sync weight-streaming kernel  */
 #define Q100_GEMM_FORCE_TC     0x2 /* always use the tcgen05 kernel                    */
+#define Q100_GEMM_EXACT_WEIGHTS 0x4 /* decode kernel: rebuild the 16-bit fake-quantised weight
+                                      r(r(q-zp)*scale) bit-exactly before the MMA (slower); default
+                                      keeps (q-zp) exact and applies the scale in fp32 per group   */
 
 const char* q100_last_error(void);
 int q100_abi_version(void);
@@ -76,7 +79,9 @@ int q100_device_ok(int dev);
  *   lwc_up/lwc_low   nullable; POST-sigmoid multipliers [rows*cols/group] in `dtype`
  *               (quantizer.py:143-145; torch computes the sigmoid)
  *   dequant_out nullable; [rows, cols] in `dtype`      == forward()'s return value
- *   packed_out  nullable; uint32 [rows, q100_packed_words_per_row(cols, n_bits)]
+ *   packed_out  nullable; uint32 [q100_packed_words(rows, cols, n_bits)], tile-major layout v2
+ *               (DESIGN.md "Packed layout"); must be zero-filled by the caller when
+ *               rows % 128 != 0 (padding rows are never written)
  *   scales_out  nullable; [rows*cols/group] in `dtype` == self.scale
  *   zeros_out   nullable; [rows*cols/group] in `dtype` == self.round_zero_point
  *               (ignored when disable_zp)
@@ -99,8 +104,9 @@ int q100_quantize_groupwise(const void* x, int dtype, int64_t rows, int64_t cols
 int q100_fakequant_rows(const void* x, int dtype, int64_t rows, int64_t cols, int n_bits,
                         void* out, void* scales_out, void* zeros_out, int flags, void* stream);
 
-/* uint32 words per packed row (q100 v1 layout, see DESIGN.md "Packed layout"). */
-int64_t q100_packed_words_per_row(int64_t cols, int n_bits);
+/* Total uint32 words of a packed [rows, cols] code matrix (q100 v2 tile-major layout: tiles of
+ * 128 rows x 64 k, ordered [n_tile][k_tile]; see DESIGN.md "Packed layout"); -1 if unsupported. */
+int64_t q100_packed_words(int64_t rows, int64_t cols, int n_bits);
 
 /*
  * Expand packed codes back to a dense tensor in `dtype`:
@@ -118,7 +124,7 @@ int q100_dequantize(const void* packed, const void* scales, const void* zeros, i
  * n_bits/8 bytes per weight instead of 2.
  *
  *   x, y, bias  `dtype` (fp16 or bf16), row-major, bias nullable
- *   packed      uint32 [N, words_per_row(K, n_bits)]   (from q100_quantize_groupwise)
+ *   packed      uint32 [q100_packed_words(N, K, n_bits)]   (from q100_quantize_groupwise)
  *   meta        [K/group, N, 2] (scale, zero) pairs in `dtype` (meta_out above)
  *   group       quantisation group along K (multiple of 64; 0 = K)
  *   workspace   device scratch of at least q100_gemm_workspace_bytes(...) bytes, zero

@@ -12,7 +12,7 @@ namespace q100 {
 
 int gemm_skinny(const void* x, const void* packed, const void* meta, const void* bias, void* y,
                 int64_t M, int64_t N, int64_t K, int group, int n_bits, int disable_zp, int dtype,
-                void* workspace, size_t workspace_bytes, cudaStream_t st);
+                void* workspace, size_t workspace_bytes, int exact_weights, cudaStream_t st);
 size_t skinny_workspace_bytes(int64_t M, int64_t N, int64_t K);
 
 int gemm_tc(const void* x, const void* packed, const void* meta, const void* bias, void* y,
@@ -98,7 +98,7 @@ extern "C" int q100_gemm_wna16(const void* x, const void* packed, const void* me
     const int64_t mc = (M - m0) < 32 ? (M - m0) : 32;
     rc = gemm_skinny(reinterpret_cast<const uint8_t*>(x) + m0 * K * esz, packed, meta, bias,
                      reinterpret_cast<uint8_t*>(y) + m0 * N * esz, mc, N, K, group, n_bits, disable_zp,
-                     dtype, workspace, workspace_bytes, st);
+                     dtype, workspace, workspace_bytes, (flags & Q100_GEMM_EXACT_WEIGHTS) ? 1 : 0, st);
     if (rc != Q100_OK) return rc;
   }
   return Q100_OK;

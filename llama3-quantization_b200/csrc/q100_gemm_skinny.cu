@@ -5,8 +5,9 @@
 // HBM-bound: the packed weights (n_bits/8 B per weight) are the only large stream; they
 // are read exactly once.  Structure (one persistent CTA per SM slot, 8 consumer warps +
 // 1 producer warp):
-//   * producer: TMA 2-D tiles [128 rows x 128 k] of packed codes, 1-D bulk copies of the
-//     transposed (scale, zero) side band, cp.async of the x slab -> 4-stage smem ring,
+//   * producer: TMA bulk copies (cp.async.bulk) of whole [128 rows x 64 k] packed tiles -- the
+//     tile-major layout makes every pipeline unit one contiguous run of HBM -- plus 1-D bulk copies
+//     of the transposed (scale, zero) side band and cp.async of the x slab -> 4-stage smem ring,
 //     mbarrier full/empty pairs;
 //   * consumers: each warp owns 16 output rows; packed codes -> registers, dequantised
 //     in registers with the reference's exact per-op rounding
@@ -41,6 +42,7 @@ constexpr int SK_XPITCH = 320;     // bytes per (m, 128-k) x row in smem: 256 + 
 
 struct SkinnyArgs {
   const void* x;          // [M, K] T
+  const void* packed;     // tile-major packed codes (layout v2)
   const void* meta;       // [K/group, N, 2] T
   const void* bias;       // [N] T or null
   void* y;                // [M, N] T
@@ -55,20 +57,23 @@ struct SkinnyArgs {
   int max_slots;
   int has_zp;
   float qmin;
-  int meta_stage;         // bytes of (scale, zero) side band per stage, multiple of 1024
-  int stage_bytes;        // W + side band + x slab, multiple of 1024
+  int meta_stage;         // bytes of (scale, zero) side band per stage, multiple of 128
+  int post;               // 1: magic-form operand + fp32 group scaling (group % 128 == 0)
+  int stage_bytes;        // W + side band + x slab, multiple of 128
 };
 
+// Packed layout v2: tiles of [128 rows x 64 k] are contiguous in HBM; a 128-k block is two
+// consecutive k-tiles.  Each k-tile is bulk-copied to its own padded slot in shared memory so that
+// the two k-tiles of a block fall on different banks (conflict-free LDS for all four lanes t).
 template <int NBITS> struct WGeom {
-  static constexpr int kRowBytes = NBITS * 16;     // bytes per row per 128-k block
-};
-template <> struct WGeom<3> {
-  static constexpr int kRowBytes = 32;             // 2-bit plane; the 1-bit plane adds 16
+  static constexpr int kTileBytes = NBITS == 3 ? 128 * 24 : 128 * 8 * NBITS;   // one [128 x 64] tile
+  static constexpr int kPitch = kTileBytes + (NBITS == 8 ? 16 : 64);
+  static constexpr int kRowBytes = NBITS == 3 ? 16 : 8 * NBITS;                // plane 0 bytes per row per k-tile
 };
 
 template <int NBITS, int MB>
 struct SkinnySmem {
-  static constexpr int kWBytes = SK_KBU * SK_ROWS * (NBITS == 3 ? 48 : NBITS * 16);
+  static constexpr int kWBytes = ((SK_KBU * 2 * WGeom<NBITS>::kPitch) + 127) & ~127;
   static constexpr int kXBytes = SK_KBU * MB * 8 * SK_XPITCH;
   __host__ __device__ static constexpr int stage(int meta_stage) { return kWBytes + meta_stage + kXBytes; }
   __host__ __device__ static constexpr int total(int meta_stage) { return SK_STAGES * stage(meta_stage) + 1024; }
@@ -79,11 +84,13 @@ template <typename T> struct DQ;
 template <> struct DQ<__half> {
   using T2 = __half2;
   static constexpr uint32_t kMagic = 0x64006400u;      // 1024.0 in both halves
+  static constexpr float kMagicF = 1024.0f;
   __device__ static __forceinline__ T2 magic_val() { return __float2half2_rn(1024.0f); }
 };
 template <> struct DQ<__nv_bfloat16> {
   using T2 = __nv_bfloat162;
   static constexpr uint32_t kMagic = 0x43004300u;      // 128.0 in both halves (codes < 128)
+  static constexpr float kMagicF = 128.0f;
   __device__ static __forceinline__ T2 magic_val() { return __float2bfloat162_rn(128.0f); }
 };
 
@@ -125,12 +132,13 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
   return v;
 }
 
-// A lane's 32 codes (k in [32t, 32t+32) of one row's 128-k block) as 16 pairs.
+// A lane's 32 codes (k in [32t, 32t+32) of one row's 128-k block) as 16 pairs.  `blk` is the shared
+// address of the block's first k-tile; lane t reads k-tile (t >> 1), half (t & 1).
 template <int NBITS> struct LaneCodes;
 template <> struct LaneCodes<4> {
   uint4 w;
-  __device__ __forceinline__ void load(uint32_t wtile, uint32_t /*w1tile*/, int row, int t) {
-    w = lds128(wtile + row * 64 + t * 16);
+  __device__ __forceinline__ void load(uint32_t blk, int row, int t) {
+    w = lds128(blk + (t >> 1) * WGeom<4>::kPitch + row * 32 + (t & 1) * 16);
   }
   __device__ __forceinline__ uint32_t pair(int i) const {
     const uint32_t x = (i >> 2) == 0 ? w.x : (i >> 2) == 1 ? w.y : (i >> 2) == 2 ? w.z : w.w;
@@ -139,8 +147,8 @@ template <> struct LaneCodes<4> {
 };
 template <> struct LaneCodes<2> {
   uint2 w;
-  __device__ __forceinline__ void load(uint32_t wtile, uint32_t, int row, int t) {
-    w = lds64(wtile + row * 32 + t * 8);
+  __device__ __forceinline__ void load(uint32_t blk, int row, int t) {
+    w = lds64(blk + (t >> 1) * WGeom<2>::kPitch + row * 16 + (t & 1) * 8);
   }
   __device__ __forceinline__ uint32_t pair(int i) const {
     const uint32_t x = (i >> 3) == 0 ? w.x : w.y;
@@ -149,9 +157,10 @@ template <> struct LaneCodes<2> {
 };
 template <> struct LaneCodes<8> {
   uint4 w0, w1;
-  __device__ __forceinline__ void load(uint32_t wtile, uint32_t, int row, int t) {
-    w0 = lds128(wtile + row * 128 + t * 32);
-    w1 = lds128(wtile + row * 128 + t * 32 + 16);
+  __device__ __forceinline__ void load(uint32_t blk, int row, int t) {
+    const uint32_t p = blk + (t >> 1) * WGeom<8>::kPitch + row * 64 + (t & 1) * 32;
+    w0 = lds128(p);
+    w1 = lds128(p + 16);
   }
   __device__ __forceinline__ uint32_t pair(int i) const {
     const int wi = i >> 1;
@@ -163,9 +172,10 @@ template <> struct LaneCodes<8> {
 template <> struct LaneCodes<3> {
   uint2 lo;
   uint32_t hi;
-  __device__ __forceinline__ void load(uint32_t wtile, uint32_t w1tile, int row, int t) {
-    lo = lds64(wtile + row * 32 + t * 8);
-    hi = lds32(w1tile + row * 16 + t * 4);
+  __device__ __forceinline__ void load(uint32_t blk, int row, int t) {
+    const uint32_t p = blk + (t >> 1) * WGeom<3>::kPitch;
+    lo = lds64(p + row * 16 + (t & 1) * 8);                  // 2-bit plane: 128 rows x 16 B
+    hi = lds32(p + 128 * 16 + row * 8 + (t & 1) * 4);        // 1-bit plane: 128 rows x 8 B
   }
   __device__ __forceinline__ uint32_t pair(int i) const {
     const uint32_t x = (i >> 3) == 0 ? lo.x : lo.y;
@@ -179,17 +189,14 @@ __device__ __forceinline__ int unit_owner(int u, int G, int U) {
 }
 
 // ---------------------------------------------------------------- kernel
-template <typename T, int NBITS, int MB>
+template <typename T, int NBITS, int MB, bool POST>
 __global__ void __launch_bounds__(SK_THREADS)
-k3_skinny(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_w1,
-          const SkinnyArgs a) {
+k3_skinny(const SkinnyArgs a) {
   using SM = SkinnySmem<NBITS, MB>;
   using T2 = typename DQ<T>::T2;
   constexpr bool kBf16 = DT<T>::kCode == Q100_BF16;
-  constexpr int kRowB = WGeom<NBITS>::kRowBytes;
-  constexpr int kW0Block = SK_ROWS * kRowB;                         // bytes of one 128-k block, plane 0
-  constexpr int kW1Off = SK_KBU * kW0Block;                         // W3: offset of the 1-bit plane
-  constexpr int kW1Block = SK_ROWS * 16;
+  constexpr int kTileB = WGeom<NBITS>::kTileBytes;
+  constexpr int kPitch = WGeom<NBITS>::kPitch;
 
   extern __shared__ __align__(128) uint8_t smem_raw[];
   // 1024-aligned carve-up
@@ -218,7 +225,6 @@ k3_skinny(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUte
 
   if (warp == 8) {
     // ============================ producer warp ============================
-    if (lane == 0) { tma_prefetch_desc(&tm_w); if (NBITS == 3) tma_prefetch_desc(&tm_w1); }
     const uint64_t pol = policy_evict_first();
     const T* xg = reinterpret_cast<const T*>(a.x);
     int it = 0;
@@ -234,17 +240,15 @@ k3_skinny(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUte
       const int rows_valid = min(SK_ROWS, a.N - n0);
       if (lane == 0) {
         const uint32_t meta_bytes = static_cast<uint32_t>(rows_valid) * 2u * sizeof(T);
-        const uint32_t wbytes = static_cast<uint32_t>(SK_ROWS) * (NBITS == 3 ? 48 : NBITS * 16);
-        mbar_expect_tx(&full_bar[stage], nkb * (wbytes + groups_per_block * meta_bytes));
+        mbar_expect_tx(&full_bar[stage], nkb * (2u * kTileB + groups_per_block * meta_bytes));
+        // 2*nkb consecutive [128 x 64] tiles of this row tile: one contiguous run in HBM
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.packed) +
+                              (static_cast<int64_t>(tile) * (a.kblocks * 2) + kb0 * 2) * kTileB;
+        for (int kt = 0; kt < 2 * nkb; ++kt)
+          bulk_load_1d_hint(st + kt * kPitch, wsrc + static_cast<int64_t>(kt) * kTileB, kTileB,
+                            &full_bar[stage], pol);
         for (int kb = 0; kb < nkb; ++kb) {
           const int kblk = kb0 + kb;
-          if (NBITS == 3) {
-            tma_load_2d_hint(st + kb * kW0Block, &tm_w, &full_bar[stage], kblk * 8, n0, pol);
-            tma_load_2d_hint(st + kW1Off + kb * kW1Block, &tm_w1, &full_bar[stage],
-                             a.K / 16 + kblk * 4, n0, pol);
-          } else {
-            tma_load_2d_hint(st + kb * kW0Block, &tm_w, &full_bar[stage], kblk * (NBITS * 4), n0, pol);
-          }
           for (int gi = 0; gi < groups_per_block; ++gi) {
             const int kg = (kblk * SK_KB + gi * a.group) / a.group;
             const T* src = reinterpret_cast<const T*>(a.meta) + (static_cast<int64_t>(kg) * a.N + n0) * 2;
@@ -299,38 +303,85 @@ k3_skinny(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUte
     mbar_wait(&full_bar[stage], phase);
     const uint32_t st = base_u32 + stage * a.stage_bytes;
     for (int kb = 0; kb < nkb; ++kb) {
-      const uint32_t wt = st + kb * kW0Block;
-      const uint32_t wt1 = st + kW1Off + kb * kW1Block;
+      const uint32_t wblk = st + kb * 2 * kPitch;
       LaneCodes<NBITS> c0, c1;
-      c0.load(wt, wt1, r0, t);
-      c1.load(wt, wt1, r1, t);
+      c0.load(wblk, r0, t);
+      c1.load(wblk, r1, t);
       const int gi = a.group >= SK_KB ? 0 : (32 * t) / a.group;
       const uint32_t mt = st + SM::kWBytes + (kb * groups_per_block + gi) * (SK_ROWS * 2 * sizeof(T));
       const uint32_t m0 = lds32(mt + r0 * 4), m1 = lds32(mt + r1 * 4);
-      const uint32_t s0b = __byte_perm(m0, 0, 0x1010), z0b = __byte_perm(m0, 0, 0x3232);
-      const uint32_t s1b = __byte_perm(m1, 0, 0x1010), z1b = __byte_perm(m1, 0, 0x3232);
-      const T2 s0 = *reinterpret_cast<const T2*>(&s0b), z0 = *reinterpret_cast<const T2*>(&z0b);
-      const T2 s1 = *reinterpret_cast<const T2*>(&s1b), z1 = *reinterpret_cast<const T2*>(&z1b);
       const uint32_t xs = st + SM::kWBytes + a.meta_stage + (kb * MB * 8) * SK_XPITCH;
+      if (POST) {
+        // Magic-form operand: the tensor core multiplies x by (MAGIC + q) straight from an AND/OR of
+        // the packed word; a second MMA with an all-ones A fragment yields S[m] = sum_k x[m][k] of
+        // the block, and the group's contribution is  scale * (acc_q - (MAGIC + zp) * S)  in fp32.
+        // (q - zp) is exact; the weight is never rounded to 16 bits (DESIGN.md "K3a numerics").
+        constexpr uint32_t kOne2 = kBf16 ? 0x3f803f80u : 0x3c003c00u;
+        const uint32_t ones[4] = {kOne2, kOne2, kOne2, kOne2};
+        float ag[MB][4], so[MB][4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 xb[MB];
+        for (int j = 0; j < 4; ++j) {
+          uint4 xb[MB];
 #pragma unroll
-        for (int mb = 0; mb < MB; ++mb) xb[mb] = lds128(xs + (mb * 8 + g) * SK_XPITCH + t * 16 + j * 64);
+          for (int mb = 0; mb < MB; ++mb) xb[mb] = lds128(xs + (mb * 8 + g) * SK_XPITCH + t * 16 + j * 64);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int p = 4 * j + 2 * h;            // pair index of k = 32t + 8j + 4h + {0,1}
-          uint32_t af[4];
-          af[0] = dq_pair<T, NBITS>(c0.pair(p), qmin2, z0, s0, has_zp);
-          af[1] = dq_pair<T, NBITS>(c1.pair(p), qmin2, z1, s1, has_zp);
-          af[2] = dq_pair<T, NBITS>(c0.pair(p + 1), qmin2, z0, s0, has_zp);
-          af[3] = dq_pair<T, NBITS>(c1.pair(p + 1), qmin2, z1, s1, has_zp);
+          for (int h = 0; h < 2; ++h) {
+            const int p = 4 * j + 2 * h;
+            uint32_t af[4];
+            af[0] = c0.pair(p) | DQ<T>::kMagic;
+            af[1] = c1.pair(p) | DQ<T>::kMagic;
+            af[2] = c0.pair(p + 1) | DQ<T>::kMagic;
+            af[3] = c1.pair(p + 1) | DQ<T>::kMagic;
 #pragma unroll
-          for (int mb = 0; mb < MB; ++mb) {
-            uint32_t bf[2];
-            bf[0] = h == 0 ? xb[mb].x : xb[mb].z;
-            bf[1] = h == 0 ? xb[mb].y : xb[mb].w;
-            mma_16816(acc[mb], af, bf, kBf16);
+            for (int mb = 0; mb < MB; ++mb) {
+              uint32_t bf[2];
+              bf[0] = h == 0 ? xb[mb].x : xb[mb].z;
+              bf[1] = h == 0 ? xb[mb].y : xb[mb].w;
+              if (j == 0 && h == 0) {
+                mma_16816_zero(ag[mb], af, bf, kBf16);
+                mma_16816_zero(so[mb], ones, bf, kBf16);
+              } else {
+                mma_16816(ag[mb], af, bf, kBf16);
+                mma_16816(so[mb], ones, bf, kBf16);
+              }
+            }
+          }
+        }
+        const float2 sz0 = DT<T>::to_f2(m0), sz1 = DT<T>::to_f2(m1);     // (scale, zero) of rows r0, r1
+        const float off0 = -(DQ<T>::kMagicF + (has_zp ? sz0.y : -a.qmin));
+        const float off1 = -(DQ<T>::kMagicF + (has_zp ? sz1.y : -a.qmin));
+#pragma unroll
+        for (int mb = 0; mb < MB; ++mb) {
+          acc[mb][0] = fmaf(sz0.x, fmaf(off0, so[mb][0], ag[mb][0]), acc[mb][0]);
+          acc[mb][1] = fmaf(sz0.x, fmaf(off0, so[mb][1], ag[mb][1]), acc[mb][1]);
+          acc[mb][2] = fmaf(sz1.x, fmaf(off1, so[mb][2], ag[mb][2]), acc[mb][2]);
+          acc[mb][3] = fmaf(sz1.x, fmaf(off1, so[mb][3], ag[mb][3]), acc[mb][3]);
+        }
+      } else {
+        const uint32_t s0b = __byte_perm(m0, 0, 0x1010), z0b = __byte_perm(m0, 0, 0x3232);
+        const uint32_t s1b = __byte_perm(m1, 0, 0x1010), z1b = __byte_perm(m1, 0, 0x3232);
+        const T2 s0 = *reinterpret_cast<const T2*>(&s0b), z0 = *reinterpret_cast<const T2*>(&z0b);
+        const T2 s1 = *reinterpret_cast<const T2*>(&s1b), z1 = *reinterpret_cast<const T2*>(&z1b);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 xb[MB];
+#pragma unroll
+          for (int mb = 0; mb < MB; ++mb) xb[mb] = lds128(xs + (mb * 8 + g) * SK_XPITCH + t * 16 + j * 64);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int p = 4 * j + 2 * h;            // pair index of k = 32t + 8j + 4h + {0,1}
+            uint32_t af[4];
+            af[0] = dq_pair<T, NBITS>(c0.pair(p), qmin2, z0, s0, has_zp);
+            af[1] = dq_pair<T, NBITS>(c1.pair(p), qmin2, z1, s1, has_zp);
+            af[2] = dq_pair<T, NBITS>(c0.pair(p + 1), qmin2, z0, s0, has_zp);
+            af[3] = dq_pair<T, NBITS>(c1.pair(p + 1), qmin2, z1, s1, has_zp);
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb) {
+              uint32_t bf[2];
+              bf[0] = h == 0 ? xb[mb].x : xb[mb].z;
+              bf[1] = h == 0 ? xb[mb].y : xb[mb].w;
+              mma_16816(acc[mb], af, bf, kBf16);
+            }
           }
         }
       }
@@ -407,10 +458,10 @@ k3_skinny(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUte
 }
 
 // ---------------------------------------------------------------- host
-template <typename T, int NBITS, int MB>
-static int launch_skinny(const CUtensorMap& tw, const CUtensorMap& tw1, SkinnyArgs a, cudaStream_t st) {
+template <typename T, int NBITS, int MB, bool POST>
+static int launch_skinny(SkinnyArgs a, cudaStream_t st) {
   using SM = SkinnySmem<NBITS, MB>;
-  auto kern = k3_skinny<T, NBITS, MB>;
+  auto kern = k3_skinny<T, NBITS, MB, POST>;
   const int smem = SM::total(a.meta_stage);
   a.stage_bytes = SM::stage(a.meta_stage);
   static std::mutex mu;           // one per instantiation
@@ -438,26 +489,31 @@ static int launch_skinny(const CUtensorMap& tw, const CUtensorMap& tw1, SkinnyAr
   if (grid > a.total_units) grid = a.total_units;
   Q100_REQUIRE(static_cast<int64_t>(a.units_per_tile) * grid / a.total_units + 2 <= a.max_slots, Q100_EWORKSPACE,
                "internal: slot bound");
-  kern<<<grid, SK_THREADS, smem, st>>>(tw, tw1, a);
+  kern<<<grid, SK_THREADS, smem, st>>>(a);
   return check_cuda(cudaGetLastError(), "k3_skinny launch");
 }
 
 template <typename T, int NBITS>
-static int launch_skinny_mb(const CUtensorMap& tw, const CUtensorMap& tw1, const SkinnyArgs& a,
-                            cudaStream_t st) {
-  if (a.M <= 8) return launch_skinny<T, NBITS, 1>(tw, tw1, a, st);
-  if (a.M <= 16) return launch_skinny<T, NBITS, 2>(tw, tw1, a, st);
-  return launch_skinny<T, NBITS, 4>(tw, tw1, a, st);
+static int launch_skinny_mb(const SkinnyArgs& a, cudaStream_t st) {
+  // 8-bit codes do not fit bf16's 7-bit OR-magic; that combination keeps the exact path
+  constexpr bool kCanPost = !(NBITS == 8 && DT<T>::kCode == Q100_BF16);
+  if (a.post && kCanPost) {
+    if (a.M <= 8) return launch_skinny<T, NBITS, 1, kCanPost>(a, st);
+    if (a.M <= 16) return launch_skinny<T, NBITS, 2, kCanPost>(a, st);
+    return launch_skinny<T, NBITS, 4, kCanPost>(a, st);
+  }
+  if (a.M <= 8) return launch_skinny<T, NBITS, 1, false>(a, st);
+  if (a.M <= 16) return launch_skinny<T, NBITS, 2, false>(a, st);
+  return launch_skinny<T, NBITS, 4, false>(a, st);
 }
 
 template <typename T>
-static int launch_skinny_bits(int n_bits, const CUtensorMap& tw, const CUtensorMap& tw1, const SkinnyArgs& a,
-                              cudaStream_t st) {
+static int launch_skinny_bits(int n_bits, const SkinnyArgs& a, cudaStream_t st) {
   switch (n_bits) {
-    case 2: return launch_skinny_mb<T, 2>(tw, tw1, a, st);
-    case 3: return launch_skinny_mb<T, 3>(tw, tw1, a, st);
-    case 4: return launch_skinny_mb<T, 4>(tw, tw1, a, st);
-    default: return launch_skinny_mb<T, 8>(tw, tw1, a, st);
+    case 2: return launch_skinny_mb<T, 2>(a, st);
+    case 3: return launch_skinny_mb<T, 3>(a, st);
+    case 4: return launch_skinny_mb<T, 4>(a, st);
+    default: return launch_skinny_mb<T, 8>(a, st);
   }
 }
 
@@ -491,7 +547,7 @@ size_t skinny_workspace_bytes(int64_t M, int64_t N, int64_t K) {
 
 int gemm_skinny(const void* x, const void* packed, const void* meta, const void* bias, void* y,
                 int64_t M, int64_t N, int64_t K, int group, int n_bits, int disable_zp, int dtype,
-                void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                void* workspace, size_t workspace_bytes, int exact_weights, cudaStream_t st) {
   Q100_REQUIRE(M >= 1 && M <= 32, Q100_EINVAL, "skinny GEMM handles 1 <= M <= 32 (got %lld)", (long long)M);
   Q100_REQUIRE(K % SK_KB == 0, Q100_EUNSUPPORTED, "K=%lld must be a multiple of 128", (long long)K);
   Q100_REQUIRE(N % 8 == 0, Q100_EUNSUPPORTED, "N=%lld must be a multiple of 8", (long long)N);
@@ -504,19 +560,8 @@ int gemm_skinny(const void* x, const void* packed, const void* meta, const void*
   Q100_REQUIRE(workspace != nullptr && workspace_bytes >= need, Q100_EWORKSPACE,
                "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
 
-  const int wpr = static_cast<int>(n_bits == 3 ? K / 16 + K / 32 : K * n_bits / 32);
-  CUtensorMap tw, tw1;
-  const uint32_t box_inner = n_bits == 3 ? 8 : n_bits * 4;
-  int rc = make_tmap_2d(&tw, packed, 4, wpr, N, static_cast<uint64_t>(wpr) * 4, box_inner, SK_ROWS, 0);
-  if (rc != Q100_OK) return rc;
-  tw1 = tw;
-  if (n_bits == 3) {
-    rc = make_tmap_2d(&tw1, packed, 4, wpr, N, static_cast<uint64_t>(wpr) * 4, 4, SK_ROWS, 0);
-    if (rc != Q100_OK) return rc;
-  }
-
   SkinnyArgs a{};
-  a.x = x; a.meta = meta; a.bias = bias; a.y = y;
+  a.x = x; a.packed = packed; a.meta = meta; a.bias = bias; a.y = y;
   const int mb = M <= 8 ? 1 : M <= 16 ? 2 : 4;
   const size_t partials = static_cast<size_t>(p.n_tiles) * p.max_slots * SK_ROWS * mb * 8 * sizeof(float);
   a.ws_counters = reinterpret_cast<int*>(workspace);
@@ -530,9 +575,10 @@ int gemm_skinny(const void* x, const void* packed, const void* meta, const void*
   a.has_zp = disable_zp ? 0 : 1;
   a.qmin = disable_zp ? -static_cast<float>(1 << (n_bits - 1)) : 0.0f;
   const int gpb = g >= SK_KB ? 1 : SK_KB / g;
-  a.meta_stage = ((p.kbu * gpb * SK_ROWS * 2 * 2) + 1023) & ~1023;
-  if (dtype == Q100_F16) return launch_skinny_bits<__half>(n_bits, tw, tw1, a, st);
-  return launch_skinny_bits<__nv_bfloat16>(n_bits, tw, tw1, a, st);
+  a.post = (g % SK_KB == 0 && !exact_weights) ? 1 : 0;
+  a.meta_stage = ((p.kbu * gpb * SK_ROWS * 2 * 2) + 127) & ~127;
+  if (dtype == Q100_F16) return launch_skinny_bits<__half>(n_bits, a, st);
+  return launch_skinny_bits<__nv_bfloat16>(n_bits, a, st);
 }
 
 }  // namespace q100

@@ -1,258 +1,391 @@
-// q100_gemm_tc.cu -- K3b: tcgen05 dequant-GEMM for prefill shapes (M > 32).
+// q100_gemm_tc.cu -- K3b: persistent tcgen05 dequant-GEMM for prefill shapes (M > 32).
 //
 //   y[M, N] = x[M, K] . dequant(W)[N, K]^T (+ bias)        quant/int_linear.py:62
 //
-// Tensor-core bound.  One CTA computes a [128 x BN] output tile with the accumulator in TMEM:
-//   warp 8      TMA producer: x tile [128 x 64] (SWIZZLE_128B), packed codes [BN x 64 k] and
-//               the (scale, zero) side band into a STAGES-deep shared-memory ring;
-//   warps 0-7   dequantise the packed tile in registers (r(r(q - zp) * scale), bit-identical
-//               to the reference's fake-quantised weight) and write it as the K-major
-//               SWIZZLE_128B B operand; fence.proxy.async; arrive on the stage's mbarrier;
-//               after the main loop the same warps run the epilogue (tcgen05.ld -> bf16/fp16
-//               -> global);
-//   warp 9      allocates TMEM, issues tcgen05.mma (kind::f16, M=128, N=BN, K=16) from one
-//               elected thread, tcgen05.commit frees the stage / publishes the accumulator.
-// The DENSE instantiation (B tile loaded by TMA from a 16-bit weight) exists to validate the
+// Tensor-core bound.  Persistent CTAs (one per SM) walk [256 x 128] output tiles, m fastest so
+// that concurrently running CTAs share weight tiles in L2.  Per tile and 64-wide k block:
+//   warp 12     TMA producer of the x-tile ring [256 x 64] (SWIZZLE_128B, 4 stages);
+//   warp 14     TMA producer of the packed-code ring [128 x 64 k] + (scale, zero) side band
+//               (small stages, up to 8 deep, so the dequant warps never wait on HBM/L2 latency);
+//   warps 0-7   two dequant groups of 4 warps that alternate stages (two stages in flight):
+//               packed codes -> registers -> r(r(q - zp) * scale) in packed 16-bit arithmetic
+//               (bit-identical to the reference's fake-quantised weight) -> K-major
+//               SWIZZLE_128B B operand in shared memory; fence.proxy.async; mbarrier arrive;
+//   warp 13     allocates TMEM (512 columns = 2 accumulator stages x 2 m-halves x 128), one
+//               elected thread issues 8 x tcgen05.mma (kind::f16, M=128, N=128, K=16) per
+//               stage -- the B tile is dequantised once and used by both m-halves --
+//               tcgen05.commit frees the stage / publishes the accumulator;
+//   warps 8-11  epilogue: tcgen05.ld -> (+bias) -> bf16/fp16 -> global, overlapped with the next
+//               tile's main loop through the second accumulator stage.
+// The DENSE instantiation (B tile loaded by TMA from a 16-bit weight) validates the
 // TMA / descriptor / TMEM plumbing independently of the dequant stage.
 #include "q100_common.cuh"
 #include "q100_ptx.cuh"
 
 namespace q100 {
 
-constexpr int TC_BM = 128;
+constexpr int TC_BM = 256;           // two UMMA M=128 halves share one B tile
+constexpr int TC_BN = 128;
 constexpr int TC_BK = 64;
-constexpr int TC_DQ_THREADS = 256;
-constexpr int TC_THREADS = TC_DQ_THREADS + 64;
+constexpr int TC_SA = 4;             // x-tile ring depth
+constexpr int TC_SB = 4;             // dequantised-B ring depth
+constexpr int TC_DQ_WARPS = 8;       // two groups of four
+constexpr int TC_EPI_WARP0 = 8;      // warps 8..11 (warp % 4 == TMEM lane quadrant)
+constexpr int TC_TMA_WARP = 12;      // x tiles
+constexpr int TC_MMA_WARP = 13;
+constexpr int TC_TMAP_WARP = 14;     // packed codes + side band (own ring, runs far ahead)
+constexpr int TC_THREADS = 15 * 32;
+constexpr int TC_TMEM_COLS = 512;
 
 struct TcArgs {
+  const void* packed;   // tile-major packed codes (layout v2): [N/128][K/64][128 rows x 64 k]
   const void* meta;     // [K/group, N, 2] T
   const void* bias;     // [N] T or null
   void* y;              // [M, N] T
   int M, N, K, group;
   int has_zp;
   float qmin;
+  int m_tiles, n_tiles;
 };
 
-template <int BN, int NBITS, bool DENSE>
+template <int NBITS, bool DENSE>
 struct TcSmem {
-  static constexpr int kA = TC_BM * TC_BK * 2;                       // 16 KB
-  static constexpr int kB = BN * TC_BK * 2;                          // dequantised / dense B tile
-  static constexpr int kP = DENSE ? 0 : BN * TC_BK * NBITS / 8;      // packed codes
-  static constexpr int kMeta = DENSE ? 0 : ((BN * 4 + 1023) & ~1023);
-  static constexpr int kStage = kA + kB + kP + kMeta;                // multiples of 1024
-  static constexpr int kStages = (kStage * 4 + 2048 <= 227 * 1024) ? 4 : 3;
-  static constexpr int kTotal = kStages * kStage + 1024;
+  // three independent rings: x tiles (TMA), dequantised B tiles (written by the dequant warps or, in
+  // the DENSE instantiation, by TMA), packed codes + side band (TMA, small, deep)
+  static constexpr int kA = TC_BM * TC_BK * 2;                        // 32 KB
+  static constexpr int kB = TC_BN * TC_BK * 2;                        // 16 KB
+  static constexpr int kP = DENSE ? 0 : TC_BN * TC_BK * NBITS / 8;    // packed codes
+  static constexpr int kPStage = DENSE ? 0 : kP + 512;                // + 128 rows x (scale, zero)
+  static constexpr int kOffB = TC_SA * kA;
+  static constexpr int kOffP = kOffB + TC_SB * kB;
+  static constexpr int kBudget = 226 * 1024 - 1024;
+  static constexpr int kSP = DENSE ? 1 : ((kBudget - kOffP) / (kPStage > 0 ? kPStage : 1) > 8
+                                              ? 8 : (kBudget - kOffP) / (kPStage > 0 ? kPStage : 1));
+  static constexpr int kTotal = kOffP + kSP * kPStage + 1024;
+  static_assert(kSP >= 2 || DENSE, "packed ring too shallow");
+  static_assert(kTotal <= 227 * 1024, "shared memory budget");
 };
 
 template <typename T> struct DQT;
 template <> struct DQT<__half> {
   using T2 = __half2;
-  static constexpr uint32_t kMagic = 0x64006400u;
-  __device__ static __forceinline__ T2 magic_val() { return __float2half2_rn(1024.0f); }
+  static constexpr uint32_t kMagic = 0x64006400u;      // 1024.0
+  static constexpr float kMagicF = 1024.0f;
+  static constexpr float kFastZp = 1000.0f;            // |zp| below this: magic + zp is exact
+  __device__ static __forceinline__ T2 bcast(float v) { return __float2half2_rn(v); }
 };
 template <> struct DQT<__nv_bfloat16> {
   using T2 = __nv_bfloat162;
-  static constexpr uint32_t kMagic = 0x43004300u;
-  __device__ static __forceinline__ T2 magic_val() { return __float2bfloat162_rn(128.0f); }
+  static constexpr uint32_t kMagic = 0x43004300u;      // 128.0 (codes < 128)
+  static constexpr float kMagicF = 128.0f;
+  static constexpr float kFastZp = 112.0f;
+  __device__ static __forceinline__ T2 bcast(float v) { return __float2bfloat162_rn(v); }
 };
 
-template <typename T>
-__device__ __forceinline__ uint32_t tc_dq_pair(uint32_t pair, typename DQT<T>::T2 qmin2,
-                                               typename DQT<T>::T2 zp2, typename DQT<T>::T2 s2, bool has_zp) {
+// pair i (elements 2i, 2i+1) of the packed word(s) covering this chunk, codes in the low bits
+template <int NBITS>
+__device__ __forceinline__ uint32_t tc_pair(const uint32_t (&w)[4], int i) {
+  if (NBITS == 4) return (w[i >> 2] >> (4 * (i & 3))) & 0x000f000fu;
+  if (NBITS == 2) return (w[i >> 3] >> (2 * (i & 7))) & 0x00030003u;
+  return (w[i >> 1] >> (8 * (i & 1))) & 0x00ff00ffu;     // NBITS == 8
+}
+
+// sub2 = magic - qmin + zp (exact) on the fast path; otherwise the literal two-step form
+template <typename T, int NBITS, bool FAST>
+__device__ __forceinline__ uint32_t tc_dq(uint32_t pair, typename DQT<T>::T2 sub2, typename DQT<T>::T2 zp2,
+                                          typename DQT<T>::T2 s2, typename DQT<T>::T2 magic2,
+                                          typename DQT<T>::T2 qmin2, bool has_zp) {
   using T2 = typename DQT<T>::T2;
-  const uint32_t m = pair | DQT<T>::kMagic;
-  T2 c = __hsub2(*reinterpret_cast<const T2*>(&m), DQT<T>::magic_val());
-  if (has_zp) c = __hsub2(c, zp2);
-  else c = __hadd2(c, qmin2);
-  c = __hmul2(c, s2);
+  T2 c;
+  if (NBITS == 8 && DT<T>::kCode == Q100_BF16) {        // 8-bit codes do not fit bf16's OR-magic trick
+    const uint32_t b = DT<T>::pack2(static_cast<float>(pair & 0xffffu), static_cast<float>(pair >> 16));
+    c = *reinterpret_cast<const T2*>(&b);
+    c = has_zp ? __hsub2(c, zp2) : __hadd2(c, qmin2);
+  } else {
+    const uint32_t m = pair | DQT<T>::kMagic;
+    if (FAST) {
+      c = __hsub2(*reinterpret_cast<const T2*>(&m), sub2);                  // (magic + q) - (magic + zp), exact
+    } else {
+      c = __hsub2(*reinterpret_cast<const T2*>(&m), magic2);                // exact
+      c = has_zp ? __hsub2(c, zp2) : __hadd2(c, qmin2);                     // r(q - zp)
+    }
+  }
+  c = __hmul2(c, s2);                                                        // r(. * scale)
   return *reinterpret_cast<uint32_t*>(&c);
 }
 
-template <typename T, int BN, int NBITS, bool DENSE>
+template <typename T, int NBITS, bool DENSE>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k3_tc(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w, const TcArgs a) {
-  using SM = TcSmem<BN, NBITS, DENSE>;
+  using SM = TcSmem<NBITS, DENSE>;
   using T2 = typename DQT<T>::T2;
-  constexpr int STAGES = SM::kStages;
   constexpr bool kBf16 = DT<T>::kCode == Q100_BF16;
+  constexpr int SP = SM::kSP;
 
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const uint32_t base_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base = smem_raw + (base_u32 - smem_u32(smem_raw));
-  __shared__ uint64_t full_tma[STAGES], full_b[STAGES], empty_bar[STAGES], tmem_full;
+  __shared__ uint64_t full_a[TC_SA], empty_a[TC_SA], full_b[TC_SB], empty_b[TC_SB], full_p[SP], empty_p[SP];
+  __shared__ uint64_t tmem_full[2], tmem_empty[2];
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n0 = blockIdx.x * BN;
-  const int m0 = blockIdx.y * TC_BM;
   const int num_kb = a.K / TC_BK;
+  const int n_tiles_total = a.m_tiles * a.n_tiles;
 
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_tma[s], 1);
-      mbar_init(&full_b[s], TC_DQ_THREADS / 32);
-      mbar_init(&empty_bar[s], 1);
+    for (int s = 0; s < TC_SA; ++s) { mbar_init(&full_a[s], 1); mbar_init(&empty_a[s], 1); }
+    for (int s = 0; s < TC_SB; ++s) {
+      mbar_init(&full_b[s], DENSE ? 1 : TC_DQ_WARPS / 2);      // DENSE: TMA expect_tx; else 4 dequant warps
+      mbar_init(&empty_b[s], 1);
     }
-    mbar_init(&tmem_full, 1);
+    for (int s = 0; s < SP; ++s) { mbar_init(&full_p[s], 1); mbar_init(&empty_p[s], TC_DQ_WARPS / 2); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
     fence_mbar_init();
   }
-  if (warp == 9) tmem_alloc(&tmem_base_s, BN);
+  if (warp == TC_MMA_WARP) tmem_alloc(&tmem_base_s, TC_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = tmem_base_s;
 
-  if (warp == 8) {
-    // ===================== TMA producer =====================
+  if (warp == TC_TMA_WARP) {
+    // ===================== TMA producer: x tiles (and the dense B tile) =====================
     if (lane == 0) {
       tma_prefetch_desc(&tm_x);
-      tma_prefetch_desc(&tm_w);
-      const uint64_t pol_w = policy_evict_first();
+      if (DENSE) tma_prefetch_desc(&tm_w);
       const uint64_t pol_x = policy_evict_last();
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        uint8_t* st = base + s * SM::kStage;
-        uint32_t bytes = SM::kA + (DENSE ? SM::kB : SM::kP + BN * 4);
-        mbar_expect_tx(&full_tma[s], bytes);
-        tma_load_2d_hint(st, &tm_x, &full_tma[s], kb * TC_BK, m0, pol_x);
-        if (DENSE) {
-          tma_load_2d_hint(st + SM::kA, &tm_w, &full_tma[s], kb * TC_BK, n0, pol_w);
-        } else {
-          tma_load_2d_hint(st + SM::kA + SM::kB, &tm_w, &full_tma[s], kb * (TC_BK * NBITS / 32), n0, pol_w);
+      const uint64_t pol_w = policy_evict_first();
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+        const int m0 = (tile % a.m_tiles) * TC_BM;
+        const int n0 = (tile / a.m_tiles) * TC_BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % TC_SA;
+          mbar_wait(&empty_a[s], ((it / TC_SA) & 1) ^ 1);
+          mbar_expect_tx(&full_a[s], SM::kA);
+          tma_load_2d_hint(base + s * SM::kA, &tm_x, &full_a[s], kb * TC_BK, m0, pol_x);
+          if (DENSE) {
+            const int sb = it % TC_SB;
+            mbar_wait(&empty_b[sb], ((it / TC_SB) & 1) ^ 1);
+            mbar_expect_tx(&full_b[sb], SM::kB);
+            tma_load_2d_hint(base + SM::kOffB + sb * SM::kB, &tm_w, &full_b[sb], kb * TC_BK, n0, pol_w);
+          }
+        }
+      }
+    }
+  } else if (warp == TC_TMAP_WARP) {
+    // ===================== TMA producer: packed codes + side band =====================
+    if (!DENSE && lane == 0) {
+      const uint64_t pol_w = policy_evict_first();
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+        const int n0 = (tile / a.m_tiles) * TC_BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % SP;
+          mbar_wait(&empty_p[s], ((it / SP) & 1) ^ 1);
+          uint8_t* st = base + SM::kOffP + s * SM::kPStage;
+          mbar_expect_tx(&full_p[s], SM::kP + TC_BN * 4);
+          // one [128 x 64] tile = one contiguous SM::kP-byte run in HBM
+          const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.packed) +
+                                (static_cast<int64_t>(tile / a.m_tiles) * num_kb + kb) * SM::kP;
+          bulk_load_1d_hint(st, wsrc, SM::kP, &full_p[s], pol_w);
           const int kg = (kb * TC_BK) / a.group;
           const T* src = reinterpret_cast<const T*>(a.meta) + (static_cast<int64_t>(kg) * a.N + n0) * 2;
-          bulk_load_1d(st + SM::kA + SM::kB + SM::kP, src, BN * 4, &full_tma[s]);
+          bulk_load_1d(st + SM::kP, src, TC_BN * 4, &full_p[s]);
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == TC_MMA_WARP) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = umma_idesc_f16(kBf16 ? 1 : 0, TC_BM, BN);
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int s = kb % STAGES;
-      const uint32_t ph = (kb / STAGES) & 1;
-      mbar_wait(&full_tma[s], ph);
-      if (!DENSE) mbar_wait(&full_b[s], ph);
+    constexpr uint32_t idesc = umma_idesc_f16(kBf16 ? 1 : 0, 128, TC_BN);
+    uint32_t it = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++tcount) {
+      const uint32_t acc = tcount & 1, acc_ph = (tcount >> 1) & 1;
+      mbar_wait(&tmem_empty[acc], acc_ph ^ 1);            // epilogue has drained this accumulator stage
       tc_fence_after();
-      if (lane == 0) {
-        uint8_t* st = base + s * SM::kStage;
-        const uint64_t da = umma_desc_sw128(st);
-        const uint64_t db = umma_desc_sw128(st + SM::kA);
+      const uint32_t d0 = tmem_acc + acc * 256;
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int sa = it % TC_SA, sb = it % TC_SB;
+        mbar_wait(&full_b[sb], (it / TC_SB) & 1);
+        mbar_wait(&full_a[sa], (it / TC_SA) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          uint8_t* sta = base + sa * SM::kA;
+          const uint64_t da = umma_desc_sw128(sta);
+          const uint64_t da1 = umma_desc_sw128(sta + 128 * TC_BK * 2);     // rows 128..255 of the x tile
+          const uint64_t db = umma_desc_sw128(base + SM::kOffB + sb * SM::kB);
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k) {
-          // +32 bytes per K=16 step inside the 128-byte swizzled row (start-address field is >> 4)
-          umma_f16_ss(tmem_acc, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            // +32 bytes per K=16 step inside the 128-byte swizzled row (start-address field is >> 4)
+            const uint32_t accum = (kb | k) != 0 ? 1u : 0u;
+            umma_f16_ss(d0, da + 2 * k, db + 2 * k, idesc, accum);
+            umma_f16_ss(d0 + 128, da1 + 2 * k, db + 2 * k, idesc, accum);
+          }
+          umma_commit(&empty_a[sa]);                  // both rings are released when these MMAs retire
+          umma_commit(&empty_b[sb]);
+          if (kb == num_kb - 1) umma_commit(&tmem_full[acc]);
         }
-        umma_commit(&empty_bar[s]);                 // frees the stage when these MMAs retire
-        if (kb == num_kb - 1) umma_commit(&tmem_full);
+        __syncwarp();
       }
-      __syncwarp();
     }
-  } else {
-    // ===================== dequant warps (0..7) =====================
+  } else if (warp < TC_DQ_WARPS) {
+    // ===================== dequant warps: group g handles iterations it % 2 == g =====================
     if (!DENSE) {
+      const int grp = warp >> 2;
+      const int gtid = tid & 127;
       const uint32_t qb = DT<T>::pack2(a.qmin, a.qmin);
       const T2 qmin2 = *reinterpret_cast<const T2*>(&qb);
+      const T2 magic2 = DQT<T>::bcast(DQT<T>::kMagicF);
       const bool has_zp = a.has_zp != 0;
-      constexpr int CODES_PER_CHUNK = 128 / NBITS;                 // codes in one 16-byte chunk
-      constexpr int CHUNKS_PER_ROW = TC_BK / CODES_PER_CHUNK;      // W4: 2
-      constexpr int N_CHUNKS = BN * CHUNKS_PER_ROW;
-      static_assert(NBITS == 4, "tcgen05 dequant path: W4 only for now");
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full_tma[s], ph);
-        const uint32_t st = base_u32 + s * SM::kStage;
-        const uint32_t bt = st + SM::kA;
-        const uint32_t pt = st + SM::kA + SM::kB;
-        const uint32_t mt = pt + SM::kP;
-        for (int c = tid; c < N_CHUNKS; c += TC_DQ_THREADS) {
-          const int row = c / CHUNKS_PER_ROW, hf = c % CHUNKS_PER_ROW;
-          uint4 w;
-          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                       : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w) : "r"(pt + c * 16));
-          uint32_t m;
-          asm volatile("ld.shared.u32 %0, [%1];" : "=r"(m) : "r"(mt + row * 4));
-          const uint32_t sb = __byte_perm(m, 0, 0x1010), zb = __byte_perm(m, 0, 0x3232);
-          const T2 s2 = *reinterpret_cast<const T2*>(&sb), z2 = *reinterpret_cast<const T2*>(&zb);
-          const uint32_t ww[4] = {w.x, w.y, w.z, w.w};
+      constexpr int CODES = 128 / NBITS;                 // codes in one 16-byte chunk
+      constexpr int CHUNKS_PER_ROW = TC_BK / CODES;      // W4: 2, W2: 1, W8: 4
+      constexpr int N_CHUNKS = TC_BN * CHUNKS_PER_ROW;
+      constexpr int OUT16 = CODES / 8;                   // 16-byte output chunks per input chunk
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          if (static_cast<int>(it & 1) != grp) continue;
+          const int sp = it % SP, sb = it % TC_SB;
+          mbar_wait(&full_p[sp], (it / SP) & 1);                  // packed codes have landed
+          mbar_wait(&empty_b[sb], ((it / TC_SB) & 1) ^ 1);        // the tensor core is done with this B slot
+          const uint32_t bt = base_u32 + SM::kOffB + sb * SM::kB;
+          const uint32_t pt = base_u32 + SM::kOffP + sp * SM::kPStage;
+          const uint32_t mt = pt + SM::kP;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {        // word j: 8 consecutive k -> one 16-byte chunk of the B row
-            uint4 o;
-            o.x = tc_dq_pair<T>(ww[j] & 0x000f000fu, qmin2, z2, s2, has_zp);
-            o.y = tc_dq_pair<T>((ww[j] >> 4) & 0x000f000fu, qmin2, z2, s2, has_zp);
-            o.z = tc_dq_pair<T>((ww[j] >> 8) & 0x000f000fu, qmin2, z2, s2, has_zp);
-            o.w = tc_dq_pair<T>((ww[j] >> 12) & 0x000f000fu, qmin2, z2, s2, has_zp);
-            const int chunk = hf * 4 + j;                                  // 16-byte chunk index in the 128-byte row
-            const uint32_t dst = bt + row * 128 + ((chunk ^ (row & 7)) << 4);   // SWIZZLE_128B
-            asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};"
-                         :: "r"(dst), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
-          }
-        }
-        fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&full_b[s]);
-      }
-    }
-    // ===================== epilogue =====================
-    mbar_wait(&tmem_full, 0);
-    tc_fence_after();
-    const int quad = warp & 3;                         // TMEM lane quadrant this warp may read
-    const int col_half = warp >> 2;                    // warps 0-3: columns [0, BN/2), 4-7: the rest
-    const int m = m0 + quad * 32 + lane;
-    T* yrow = reinterpret_cast<T*>(a.y) + static_cast<int64_t>(m) * a.N + n0;
-    const T* bias = reinterpret_cast<const T*>(a.bias);
-#pragma unroll 1
-    for (int c0 = col_half * (BN / 2); c0 < (col_half + 1) * (BN / 2); c0 += 32) {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(tmem_acc + (static_cast<uint32_t>(quad * 32) << 16) + c0, r);
-      tmem_ld_wait();
-      if (m < a.M) {
+          for (int c = gtid; c < N_CHUNKS; c += 128) {
+            const int row = c / CHUNKS_PER_ROW, part = c % CHUNKS_PER_ROW;
+            uint32_t w[4];
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(pt + c * 16));
+            uint32_t m;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(m) : "r"(mt + row * 4));
+            const uint32_t sb2 = __byte_perm(m, 0, 0x1010), zb = __byte_perm(m, 0, 0x3232);
+            const T2 s2 = *reinterpret_cast<const T2*>(&sb2), z2 = *reinterpret_cast<const T2*>(&zb);
+            // fast path: magic + zp (or magic - qmin) is an exactly representable integer
+            const float zf = DT<T>::to_f(*reinterpret_cast<const T*>(&zb));
+            const bool fast = !has_zp || fabsf(zf) <= DQT<T>::kFastZp;
+            const T2 sub2 = DQT<T>::bcast(DQT<T>::kMagicF + (has_zp ? zf : -a.qmin));
+            const uint32_t row_off = bt + row * 128;
+            const int sw = row & 7;
+            if (fast) {
 #pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          uint32_t o[4];
+              for (int j = 0; j < OUT16; ++j) {
+                uint4 o;
+                o.x = tc_dq<T, NBITS, true>(tc_pair<NBITS>(w, 4 * j + 0), sub2, z2, s2, magic2, qmin2, has_zp);
+                o.y = tc_dq<T, NBITS, true>(tc_pair<NBITS>(w, 4 * j + 1), sub2, z2, s2, magic2, qmin2, has_zp);
+                o.z = tc_dq<T, NBITS, true>(tc_pair<NBITS>(w, 4 * j + 2), sub2, z2, s2, magic2, qmin2, has_zp);
+                o.w = tc_dq<T, NBITS, true>(tc_pair<NBITS>(w, 4 * j + 3), sub2, z2, s2, magic2, qmin2, has_zp);
+                const int chunk = part * OUT16 + j;                        // 16-byte chunk in the 128-byte row
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};"
+                             :: "r"(row_off + ((chunk ^ sw) << 4)), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+              }
+            } else {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            float f0 = __uint_as_float(r[v * 8 + 2 * e]), f1 = __uint_as_float(r[v * 8 + 2 * e + 1]);
-            if (bias) {
-              f0 += DT<T>::to_f(bias[n0 + c0 + v * 8 + 2 * e]);
-              f1 += DT<T>::to_f(bias[n0 + c0 + v * 8 + 2 * e + 1]);
+              for (int j = 0; j < OUT16; ++j) {
+                uint4 o;
+                o.x = tc_dq<T, NBITS, false>(tc_pair<NBITS>(w, 4 * j + 0), sub2, z2, s2, magic2, qmin2, has_zp);
+                o.y = tc_dq<T, NBITS, false>(tc_pair<NBITS>(w, 4 * j + 1), sub2, z2, s2, magic2, qmin2, has_zp);
+                o.z = tc_dq<T, NBITS, false>(tc_pair<NBITS>(w, 4 * j + 2), sub2, z2, s2, magic2, qmin2, has_zp);
+                o.w = tc_dq<T, NBITS, false>(tc_pair<NBITS>(w, 4 * j + 3), sub2, z2, s2, magic2, qmin2, has_zp);
+                const int chunk = part * OUT16 + j;
+                asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};"
+                             :: "r"(row_off + ((chunk ^ sw) << 4)), "r"(o.x), "r"(o.y), "r"(o.z), "r"(o.w) : "memory");
+              }
             }
-            o[e] = DT<T>::pack2(f0, f1);
           }
-          *reinterpret_cast<uint4*>(yrow + c0 + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+          fence_proxy_async_smem();          // generic-proxy writes -> visible to the tensor core (async proxy)
+          __syncwarp();
+          if (lane == 0) {
+            mbar_arrive(&full_b[sb]);
+            mbar_arrive(&empty_p[sp]);       // packed slot may be refilled
+          }
         }
       }
     }
-    tc_fence_before();
+  } else {
+    // ===================== epilogue warps (8..11) =====================
+    const int quad = warp & 3;                          // TMEM lane quadrant this warp may read
+    const T* bias = reinterpret_cast<const T*>(a.bias);
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++tcount) {
+      const uint32_t acc = tcount & 1, acc_ph = (tcount >> 1) & 1;
+      const int m0 = (tile % a.m_tiles) * TC_BM;
+      const int n0 = (tile / a.m_tiles) * TC_BN;
+      mbar_wait(&tmem_full[acc], acc_ph);
+      tc_fence_after();
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        const int m = m0 + half * 128 + quad * 32 + lane;
+        T* yrow = reinterpret_cast<T*>(a.y) + static_cast<int64_t>(m) * a.N + n0;
+#pragma unroll 1
+        for (int c0 = 0; c0 < TC_BN; c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(tmem_acc + (static_cast<uint32_t>(quad * 32) << 16) + acc * 256 + half * 128 + c0, r);
+          tmem_ld_wait();
+          if (m < a.M) {
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+              uint32_t o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float f0 = __uint_as_float(r[v * 8 + 2 * e]), f1 = __uint_as_float(r[v * 8 + 2 * e + 1]);
+                if (bias) {
+                  f0 += DT<T>::to_f(bias[n0 + c0 + v * 8 + 2 * e]);
+                  f1 += DT<T>::to_f(bias[n0 + c0 + v * 8 + 2 * e + 1]);
+                }
+                o[e] = DT<T>::pack2(f0, f1);
+              }
+              *reinterpret_cast<uint4*>(yrow + c0 + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+    }
   }
+  tc_fence_before();
   __syncthreads();
-  if (warp == 9) {
+  if (warp == TC_MMA_WARP) {
     tc_fence_after();
-    tmem_dealloc(tmem_acc, BN);
+    tmem_dealloc(tmem_acc, TC_TMEM_COLS);
   }
 }
 
 // ---------------------------------------------------------------- host
-template <typename T, int BN, int NBITS, bool DENSE>
-static int launch_tc(const CUtensorMap& tx, const CUtensorMap& tw, const TcArgs& a, cudaStream_t st) {
-  using SM = TcSmem<BN, NBITS, DENSE>;
-  auto kern = k3_tc<T, BN, NBITS, DENSE>;
+template <typename T, int NBITS, bool DENSE>
+static int launch_tc(const CUtensorMap& tx, const CUtensorMap& tw, TcArgs a, cudaStream_t st) {
+  using SM = TcSmem<NBITS, DENSE>;
+  auto kern = k3_tc<T, NBITS, DENSE>;
   static bool attr_done = false;
   if (!attr_done) {
     Q100_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
     attr_done = true;
   }
-  dim3 grid(a.N / BN, (a.M + TC_BM - 1) / TC_BM);
+  a.m_tiles = (a.M + TC_BM - 1) / TC_BM;
+  a.n_tiles = a.N / TC_BN;
+  int grid = a.m_tiles * a.n_tiles;
+  const int sms = sm_count();
+  if (grid > sms) grid = sms;
   kern<<<grid, TC_THREADS, SM::kTotal, st>>>(tx, tw, a);
   return check_cuda(cudaGetLastError(), "k3_tc launch");
 }
 
 bool gemm_tc_supported(int64_t M, int64_t N, int64_t K, int group, int n_bits) {
   const int64_t g = group == 0 ? K : group;
-  return n_bits == 4 && M >= 1 && N % 128 == 0 && K % TC_BK == 0 && g % TC_BK == 0 && K % g == 0;
+  return (n_bits == 4 || n_bits == 2 || n_bits == 8) && M >= 1 && N % TC_BN == 0 && K % TC_BK == 0 &&
+         g % TC_BK == 0 && K % g == 0;
+}
+
+template <typename T>
+static int gemm_tc_t(const CUtensorMap& tx, const CUtensorMap& tw, const TcArgs& a, int n_bits, cudaStream_t st) {
+  switch (n_bits) {
+    case 2: return launch_tc<T, 2, false>(tx, tw, a, st);
+    case 8: return launch_tc<T, 8, false>(tx, tw, a, st);
+    default: return launch_tc<T, 4, false>(tx, tw, a, st);
+  }
 }
 
 int gemm_tc(const void* x, const void* packed, const void* meta, const void* bias, void* y,
@@ -260,42 +393,32 @@ int gemm_tc(const void* x, const void* packed, const void* meta, const void* bia
             cudaStream_t st) {
   Q100_REQUIRE(gemm_tc_supported(M, N, K, group, n_bits), Q100_EUNSUPPORTED, "tcgen05 path: unsupported shape");
   const int g = group == 0 ? static_cast<int>(K) : group;
-  const int bn = (N % 256 == 0) ? 256 : 128;
-  CUtensorMap tx, tw;
+  CUtensorMap tx;
   int rc = make_tmap_2d(&tx, x, 2, K, M, static_cast<uint64_t>(K) * 2, TC_BK, TC_BM, 128);
   if (rc != Q100_OK) return rc;
-  const int64_t wpr = K * n_bits / 32;
-  rc = make_tmap_2d(&tw, packed, 4, wpr, N, static_cast<uint64_t>(wpr) * 4, TC_BK * n_bits / 32, bn, 0);
-  if (rc != Q100_OK) return rc;
+  const CUtensorMap& tw = tx;          // unused by the dequant instantiation (codes arrive by bulk copy)
   TcArgs a{};
-  a.meta = meta; a.bias = bias; a.y = y;
+  a.packed = packed; a.meta = meta; a.bias = bias; a.y = y;
   a.M = static_cast<int>(M); a.N = static_cast<int>(N); a.K = static_cast<int>(K); a.group = g;
   a.has_zp = disable_zp ? 0 : 1;
   a.qmin = disable_zp ? -static_cast<float>(1 << (n_bits - 1)) : 0.0f;
-  if (dtype == Q100_F16) {
-    return bn == 256 ? launch_tc<__half, 256, 4, false>(tx, tw, a, st) : launch_tc<__half, 128, 4, false>(tx, tw, a, st);
-  }
-  return bn == 256 ? launch_tc<__nv_bfloat16, 256, 4, false>(tx, tw, a, st)
-                   : launch_tc<__nv_bfloat16, 128, 4, false>(tx, tw, a, st);
+  if (dtype == Q100_F16) return gemm_tc_t<__half>(tx, tw, a, n_bits, st);
+  return gemm_tc_t<__nv_bfloat16>(tx, tw, a, n_bits, st);
 }
 
 // dense 16-bit weight through the same TMA/UMMA/TMEM plumbing (bring-up / regression hook)
 int gemm_tc_dense(const void* x, const void* w, void* y, int64_t M, int64_t N, int64_t K, int dtype,
                   cudaStream_t st) {
-  Q100_REQUIRE(N % 128 == 0 && K % TC_BK == 0 && M >= 1, Q100_EUNSUPPORTED, "dense tc: N %% 128, K %% 64");
-  const int bn = (N % 256 == 0) ? 256 : 128;
+  Q100_REQUIRE(N % TC_BN == 0 && K % TC_BK == 0 && M >= 1, Q100_EUNSUPPORTED, "dense tc: N %% 128, K %% 64");
   CUtensorMap tx, tw;
   int rc = make_tmap_2d(&tx, x, 2, K, M, static_cast<uint64_t>(K) * 2, TC_BK, TC_BM, 128);
   if (rc != Q100_OK) return rc;
-  rc = make_tmap_2d(&tw, w, 2, K, N, static_cast<uint64_t>(K) * 2, TC_BK, bn, 128);
+  rc = make_tmap_2d(&tw, w, 2, K, N, static_cast<uint64_t>(K) * 2, TC_BK, TC_BN, 128);
   if (rc != Q100_OK) return rc;
   TcArgs a{};
   a.y = y; a.M = static_cast<int>(M); a.N = static_cast<int>(N); a.K = static_cast<int>(K); a.group = static_cast<int>(K);
-  if (dtype == Q100_F16) {
-    return bn == 256 ? launch_tc<__half, 256, 4, true>(tx, tw, a, st) : launch_tc<__half, 128, 4, true>(tx, tw, a, st);
-  }
-  return bn == 256 ? launch_tc<__nv_bfloat16, 256, 4, true>(tx, tw, a, st)
-                   : launch_tc<__nv_bfloat16, 128, 4, true>(tx, tw, a, st);
+  if (dtype == Q100_F16) return launch_tc<__half, 4, true>(tx, tw, a, st);
+  return launch_tc<__nv_bfloat16, 4, true>(tx, tw, a, st);
 }
 
 }  // namespace q100

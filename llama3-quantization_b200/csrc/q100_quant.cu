@@ -39,9 +39,15 @@ struct QuantArgs {
   int has_zp;
   float qmin, qmax;     // reference code range (quantizer.py:46-51)
   float denom;          // 2^n - 1 (asymmetric) or 2^(n-1) - 1 (symmetric)
-  int words_per_row;
-  int plane1_off;       // W3: word offset of the 1-bit plane inside a packed row
+  int k_tiles;          // packed layout v2: cols / 64
+  int tile_words;       // uint32 words per [128 rows x 64 k] tile
 };
+
+// ---- packed layout v2 (tile-major, DESIGN.md "Packed layout"): tiles of 128 rows x 64 k stored
+// contiguously in [n_tile][k_tile] order; W3 = a 2-bit plane (128 x 4 words) then a 1-bit plane.
+__host__ __device__ __forceinline__ int tile_words_of(int n_bits) {
+  return n_bits == 3 ? 128 * 6 : 128 * (2 * n_bits);
+}
 
 // ------------------------------------------------------------------ per-group parameters
 template <typename T>
@@ -235,39 +241,44 @@ __device__ __forceinline__ uint32_t plane_word(const uint32_t (&pairs)[NP], int 
 // of the warp call this together: shuffles inside).
 template <int E>
 __device__ __forceinline__ void emit_packed(const uint32_t (&pairs)[E / 2], const QuantArgs& a,
-                                            int64_t row, int64_t vec_in_row, bool valid) {
-  uint32_t* prow = a.packed + row * a.words_per_row;
-  const int64_t e0 = vec_in_row * E;                 // first element (column) of the vector
+                                            int row, int vec_in_row, bool valid) {
+  const int e0 = vec_in_row * E;                     // first element (column) of the vector
+  // base of the [128 x 64] tile holding (row, e0), then the row inside the tile
+  uint32_t* tile = a.packed + (static_cast<int64_t>(row >> 7) * a.k_tiles + (e0 >> 6)) * a.tile_words;
+  const int r = row & 127;
+  const int ek = e0 & 63;                            // column inside the tile
   const int nb = a.n_bits;
-  if (nb == 8) {
+  if (nb == 8) {                                     // 16 words per row, 4 codes per word
+    uint32_t* prow = tile + r * 16;
     if (E == 8) {
       if (valid) {
         uint2 w;
         w.x = (pairs[0] & 0x00ff00ffu) | ((pairs[1] & 0x00ff00ffu) << 8);
         w.y = (pairs[E / 2 - 2] & 0x00ff00ffu) | ((pairs[E / 2 - 1] & 0x00ff00ffu) << 8);
-        *reinterpret_cast<uint2*>(prow + (e0 >> 2)) = w;
+        *reinterpret_cast<uint2*>(prow + (ek >> 2)) = w;
       }
     } else {
-      if (valid) prow[e0 >> 2] = (pairs[0] & 0x00ff00ffu) | ((pairs[1] & 0x00ff00ffu) << 8);
+      if (valid) prow[ek >> 2] = (pairs[0] & 0x00ff00ffu) | ((pairs[1] & 0x00ff00ffu) << 8);
     }
     return;
   }
-  // planes: (bits, mask, pre_shift, word offset)
+  // planes: b bits per field, F = 32 / b = 1 << lf elements per word (all powers of two: shifts only)
   const int n_planes = (nb == 3) ? 2 : 1;
 #pragma unroll
   for (int pl = 0; pl < 2; ++pl) {
     if (pl >= n_planes) break;
     const int b = (nb == 3) ? (pl == 0 ? 2 : 1) : nb;
     const int pre = (nb == 3 && pl == 1) ? 2 : 0;
+    const int lf = (b == 4) ? 3 : (b == 2) ? 4 : 5;          // log2(F)
     const uint32_t m1 = (1u << b) - 1u;
     const uint32_t pmask = m1 | (m1 << 16);
-    const int F = 32 / b;                      // elements per word
-    const int lpw = F / E;                     // lanes per word (>= 1 here)
-    const int o = static_cast<int>(e0 % F);    // word-relative first element (multiple of E)
+    const int lpw = (1 << lf) / E;                           // lanes per word (>= 1 here)
+    const int o = ek & ((1 << lf) - 1);                      // word-relative first element (multiple of E)
     uint32_t w = plane_word<E / 2>(pairs, b, b * (o >> 1), pmask, pre);
     if (!valid) w = 0;
     for (int d = 1; d < lpw; d <<= 1) w |= __shfl_xor_sync(0xffffffffu, w, d);
-    if (valid && o == 0) prow[(pl == 1 ? a.plane1_off : 0) + e0 / F] = w;
+    // words per row inside the tile for this plane: 64 * b / 32 = 2 * b
+    if (valid && o == 0) tile[(pl == 1 ? 128 * 4 : 0) + r * (2 * b) + (ek >> lf)] = w;
   }
 }
 
@@ -277,8 +288,9 @@ __device__ __forceinline__ void store_group_meta(const QuantArgs& a, int64_t g, 
   if (a.scales) reinterpret_cast<T*>(a.scales)[g] = D::from_f(q.scale);
   if (a.zeros && a.has_zp) reinterpret_cast<T*>(a.zeros)[g] = D::from_f(q.zp);
   if (a.meta) {
-    const int64_t row = g / a.groups_per_row, kg = g % a.groups_per_row;
-    T* m = reinterpret_cast<T*>(a.meta) + (kg * a.rows + row) * 2;
+    const int gi = static_cast<int>(g);
+    const int row = gi / a.groups_per_row, kg = gi - row * a.groups_per_row;
+    T* m = reinterpret_cast<T*>(a.meta) + (static_cast<int64_t>(kg) * a.rows + row) * 2;
     m[0] = D::from_f(q.scale);
     m[1] = D::from_f(q.zp);
   }
@@ -330,10 +342,11 @@ __global__ void __launch_bounds__(256) k1_groups(const QuantArgs a) {
     }
     const GroupQ<T> q = group_params<T>(mn, mx, a, valid ? g : 0);
 
-    int64_t row = 0, vec0 = 0;
-    if (PACK) {
-      row = g / a.groups_per_row;
-      vec0 = (g % a.groups_per_row) * (L * V);
+    int row = 0, vec0 = 0;
+    if (PACK) {                                         // 32-bit: n_groups < 2^31 is checked on the host
+      const int gi = static_cast<int>(g);
+      row = gi / a.groups_per_row;
+      vec0 = (gi - row * a.groups_per_row) * (L * V);
     }
 #pragma unroll
     for (int k = 0; k < V; ++k) {
@@ -403,7 +416,7 @@ __global__ void __launch_bounds__(1024) k2_rows(const QuantArgs a) {
           for (int j = 0; j < E / 2; ++j) pairs[j] = 0;
         }
         if (dq != nullptr && valid) stg_stream(dq + row * nvec + idx, o);
-        if (PACK) emit_packed<E>(pairs, a, row, idx, valid);
+        if (PACK) emit_packed<E>(pairs, a, static_cast<int>(row), idx, valid);
       }
     }
     if (tid == 0) store_group_meta<T>(a, row, q);
@@ -414,21 +427,21 @@ __global__ void __launch_bounds__(1024) k2_rows(const QuantArgs a) {
 template <typename T>
 __global__ void k_dequantize(const uint32_t* __restrict__ packed, const T* __restrict__ scales,
                              const T* __restrict__ zeros, T* __restrict__ out, int64_t rows,
-                             int64_t cols, int group, int n_bits, float qmin, int words_per_row,
-                             int plane1_off) {
+                             int64_t cols, int group, int n_bits, float qmin, int k_tiles, int tile_words) {
   using D = DT<T>;
   const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= rows * cols) return;
   const int64_t r = i / cols, c = i % cols;
-  const uint32_t* prow = packed + r * words_per_row;
-  auto field = [&](int b, int off) -> uint32_t {
+  const uint32_t* tile = packed + ((r >> 7) * k_tiles + (c >> 6)) * tile_words;
+  const int rr = static_cast<int>(r & 127), ek = static_cast<int>(c & 63);
+  auto field = [&](int b, int plane_off) -> uint32_t {
     const int F = 32 / b;
-    const int e = static_cast<int>(c % F);
-    const uint32_t w = prow[off + c / F];
+    const int e = ek % F;
+    const uint32_t w = tile[plane_off + rr * (2 * b) + ek / F];
     return (w >> (b * (e >> 1) + 16 * (e & 1))) & ((1u << b) - 1u);
   };
   uint32_t u;
-  if (n_bits == 3) u = field(2, 0) | (field(1, plane1_off) << 2);
+  if (n_bits == 3) u = field(2, 0) | (field(1, 128 * 4) << 2);
   else u = field(n_bits, 0);
   float code = static_cast<float>(u) + qmin;
   if (scales == nullptr) { out[i] = D::from_f(code); return; }
@@ -466,10 +479,6 @@ __global__ void k_selftest_div(unsigned long long* mismatches) {
 }
 
 // ------------------------------------------------------------------ host dispatch
-static int64_t words_per_row_host(int64_t cols, int n_bits) {
-  if (n_bits == 3) return cols / 16 + cols / 32;
-  return cols * n_bits / 32;
-}
 
 template <typename T, int L, int V, int MATH>
 static int launch_k1_lv(const QuantArgs& a, bool pack, cudaStream_t st) {
@@ -567,10 +576,10 @@ static int quantize_dispatch(const QuantArgs& a, bool pack, int flags, cudaStrea
 
 using namespace q100;
 
-extern "C" int64_t q100_packed_words_per_row(int64_t cols, int n_bits) {
+extern "C" int64_t q100_packed_words(int64_t rows, int64_t cols, int n_bits) {
   if (n_bits != 2 && n_bits != 3 && n_bits != 4 && n_bits != 8) return -1;
-  if (cols % 32 != 0) return -1;
-  return words_per_row_host(cols, n_bits);
+  if (rows < 0 || cols < 0 || cols % 64 != 0) return -1;
+  return ((rows + 127) / 128) * (cols / 64) * tile_words_of(n_bits);
 }
 
 extern "C" int q100_quantize_groupwise(const void* x, int dtype, int64_t rows, int64_t cols, int group,
@@ -604,7 +613,7 @@ extern "C" int q100_quantize_groupwise(const void* x, int dtype, int64_t rows, i
   if (pack) {
     Q100_REQUIRE(n_bits == 2 || n_bits == 3 || n_bits == 4 || n_bits == 8, Q100_EUNSUPPORTED,
                  "packed output supports n_bits in {2,3,4,8}, got %d", n_bits);
-    Q100_REQUIRE(cols % 32 == 0, Q100_EUNSUPPORTED, "packed output needs cols %% 32 == 0");
+    Q100_REQUIRE(cols % 64 == 0, Q100_EUNSUPPORTED, "packed output needs cols %% 64 == 0");
   }
   Q100_REQUIRE(meta_out == nullptr || dtype != Q100_F32, Q100_EUNSUPPORTED,
                "meta side band is fp16/bf16 only");
@@ -623,8 +632,8 @@ extern "C" int q100_quantize_groupwise(const void* x, int dtype, int64_t rows, i
   if (disable_zp) { a.qmin = -static_cast<float>(1 << (n_bits - 1)); a.qmax = static_cast<float>((1 << (n_bits - 1)) - 1); }
   else { a.qmin = 0.0f; a.qmax = static_cast<float>((1 << n_bits) - 1); }
   a.denom = symmetric ? static_cast<float>((1 << (n_bits - 1)) - 1) : static_cast<float>((1 << n_bits) - 1);
-  a.words_per_row = pack ? static_cast<int>(words_per_row_host(cols, n_bits)) : 0;
-  a.plane1_off = static_cast<int>(cols / 16);
+  a.k_tiles = static_cast<int>(cols / 64);
+  a.tile_words = pack ? tile_words_of(n_bits) : 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (dtype) {
     case Q100_F16:  return quantize_dispatch<__half>(a, pack, flags, st);
@@ -647,23 +656,23 @@ extern "C" int q100_dequantize(const void* packed, const void* scales, const voi
   Q100_REQUIRE(dtype >= 0 && dtype <= 2, Q100_EINVAL, "bad dtype %d", dtype);
   Q100_REQUIRE(n_bits == 2 || n_bits == 3 || n_bits == 4 || n_bits == 8, Q100_EUNSUPPORTED,
                "n_bits in {2,3,4,8}");
-  Q100_REQUIRE(cols % 32 == 0, Q100_EUNSUPPORTED, "cols %% 32 != 0");
+  Q100_REQUIRE(cols % 64 == 0, Q100_EUNSUPPORTED, "cols %% 64 != 0");
   if (rows == 0 || cols == 0) return Q100_OK;
   const int g = group == 0 ? static_cast<int>(cols) : group;
   int rc = ensure_device();
   if (rc != Q100_OK) return rc;
   const float qmin = disable_zp ? -static_cast<float>(1 << (n_bits - 1)) : 0.0f;
-  const int wpr = static_cast<int>(words_per_row_host(cols, n_bits));
+  const int kt = static_cast<int>(cols / 64), tw = tile_words_of(n_bits);
   const int64_t n = rows * cols;
   const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const uint32_t* p = reinterpret_cast<const uint32_t*>(packed);
   if (dtype == Q100_F16)
-    k_dequantize<__half><<<blocks, 256, 0, st>>>(p, (const __half*)scales, (const __half*)zeros, (__half*)out, rows, cols, g, n_bits, qmin, wpr, (int)(cols / 16));
+    k_dequantize<__half><<<blocks, 256, 0, st>>>(p, (const __half*)scales, (const __half*)zeros, (__half*)out, rows, cols, g, n_bits, qmin, kt, tw);
   else if (dtype == Q100_BF16)
-    k_dequantize<__nv_bfloat16><<<blocks, 256, 0, st>>>(p, (const __nv_bfloat16*)scales, (const __nv_bfloat16*)zeros, (__nv_bfloat16*)out, rows, cols, g, n_bits, qmin, wpr, (int)(cols / 16));
+    k_dequantize<__nv_bfloat16><<<blocks, 256, 0, st>>>(p, (const __nv_bfloat16*)scales, (const __nv_bfloat16*)zeros, (__nv_bfloat16*)out, rows, cols, g, n_bits, qmin, kt, tw);
   else
-    k_dequantize<float><<<blocks, 256, 0, st>>>(p, (const float*)scales, (const float*)zeros, (float*)out, rows, cols, g, n_bits, qmin, wpr, (int)(cols / 16));
+    k_dequantize<float><<<blocks, 256, 0, st>>>(p, (const float*)scales, (const float*)zeros, (float*)out, rows, cols, g, n_bits, qmin, kt, tw);
   return check_cuda(cudaGetLastError(), "k_dequantize launch");
 }
 

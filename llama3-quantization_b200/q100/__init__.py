@@ -7,8 +7,8 @@ from . import _lib  # noqa: F401  (loads the shared library, raises ImportError 
 from ._lib import Q100Error, LIB_PATH  # noqa: F401
 from .ops import (  # noqa: F401
     PackedWeight, QuantResult, dequantize, fakequant_rows, gemm_wna16, pack_weight,
-    packed_words_per_row, quantize_groupwise, selftest_div,
+    packed_shape, quantize_groupwise, selftest_div,
 )
 
 __all__ = ["PackedWeight", "QuantResult", "Q100Error", "dequantize", "fakequant_rows", "gemm_wna16",
-           "pack_weight", "packed_words_per_row", "quantize_groupwise", "selftest_div", "LIB_PATH"]
+           "pack_weight", "packed_shape", "quantize_groupwise", "selftest_div", "LIB_PATH"]

@@ -18,6 +18,7 @@ FLAG_IEEE_DIV = 0x1
 FLAG_SCALAR_MATH = 0x2
 GEMM_FORCE_SKINNY = 0x1
 GEMM_FORCE_TC = 0x2
+GEMM_EXACT_WEIGHTS = 0x4
 
 _vp, _i, _i64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
 
@@ -28,7 +29,7 @@ SIGNATURES = {
     "q100_device_ok": (_i, [_i]),
     "q100_quantize_groupwise": (_i, [_vp, _i, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "q100_fakequant_rows": (_i, [_vp, _i, _i64, _i64, _i, _vp, _vp, _vp, _i, _vp]),
-    "q100_packed_words_per_row": (_i64, [_i64, _i]),
+    "q100_packed_words": (_i64, [_i64, _i64, _i]),
     "q100_dequantize": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _i, _i, _i, _vp, _vp]),
     "q100_gemm_wna16": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _sz, _i, _vp]),
     "q100_gemm_workspace_bytes": (_sz, [_i64, _i64, _i64, _i, _i]),

@@ -38,18 +38,23 @@ def _stream(t: torch.Tensor) -> int:
     return torch.cuda.current_stream(t.device).cuda_stream
 
 
-def packed_words_per_row(cols: int, n_bits: int) -> int:
-    w = lib.q100_packed_words_per_row(cols, n_bits)
+TILE_ROWS, TILE_K = 128, 64
+
+
+def packed_shape(rows: int, cols: int, n_bits: int):
+    """[n_tiles, k_tiles, tile_words] of the tile-major packed layout (DESIGN.md "Packed layout")."""
+    w = lib.q100_packed_words(rows, cols, n_bits)
     if w < 0:
-        raise ValueError(f"q100: cannot pack cols={cols} at {n_bits} bits (cols % 32 == 0, bits in 2/3/4/8)")
-    return int(w)
+        raise ValueError(f"q100: cannot pack [{rows}, {cols}] at {n_bits} bits (cols % 64 == 0, bits in 2/3/4/8)")
+    nt, kt = (rows + TILE_ROWS - 1) // TILE_ROWS, cols // TILE_K
+    return nt, kt, (int(w) // (nt * kt) if nt * kt else 0)
 
 
 @dataclass
 class QuantResult:
     """Outputs of one quantize pass (any subset)."""
     dequant: Optional[torch.Tensor] = None     # forward() value, same shape/dtype as the input
-    packed: Optional[torch.Tensor] = None      # int32 [rows, words_per_row]
+    packed: Optional[torch.Tensor] = None      # int32 [n_tiles, k_tiles, tile_words] (tile-major)
     scales: Optional[torch.Tensor] = None      # [n_groups, 1]  == quantizer.scale
     zeros: Optional[torch.Tensor] = None       # [n_groups, 1]  == quantizer.round_zero_point (None if disabled)
     meta: Optional[torch.Tensor] = None        # [cols/group, rows, 2] (scale, zero) side band for the GEMMs
@@ -78,7 +83,8 @@ def quantize_groupwise(x: torch.Tensor, group: int, n_bits: int, symmetric: bool
     if want_dequant:
         res.dequant = torch.empty_like(x)
     if want_packed:
-        res.packed = torch.empty((rows, packed_words_per_row(cols, n_bits)), dtype=torch.int32, device=dev)
+        shp = packed_shape(rows, cols, n_bits)
+        res.packed = (torch.zeros if rows % TILE_ROWS else torch.empty)(shp, dtype=torch.int32, device=dev)
     res.scales = torch.empty((n_groups, 1), dtype=dt, device=dev)
     if not disable_zero_point:
         res.zeros = torch.empty((n_groups, 1), dtype=dt, device=dev)
@@ -118,11 +124,10 @@ def fakequant_rows(x: torch.Tensor, n_bits: int, flags: int = 0) -> QuantResult:
 
 
 def dequantize(packed: torch.Tensor, scales: Optional[torch.Tensor], zeros: Optional[torch.Tensor],
-               cols: int, group: int, n_bits: int, dtype: torch.dtype,
+               rows: int, cols: int, group: int, n_bits: int, dtype: torch.dtype,
                disable_zero_point: bool = False) -> torch.Tensor:
-    """Packed codes -> dense tensor (raw integer codes when ``scales`` is None)."""
+    """Packed codes -> dense [rows, cols] tensor (raw integer codes when ``scales`` is None)."""
     _require_cuda(packed, scales, zeros)
-    rows = packed.shape[0]
     out = torch.empty((rows, cols), dtype=dtype, device=packed.device)
     with torch.cuda.device(packed.device):
         check(lib.q100_dequantize(packed.data_ptr(), _ptr(scales), _ptr(zeros), _DT[dtype], rows, cols,
@@ -134,7 +139,7 @@ def dequantize(packed: torch.Tensor, scales: Optional[torch.Tensor], zeros: Opti
 @dataclass
 class PackedWeight:
     """A quantised nn.Linear weight [N, K] in the q100 v1 layout."""
-    packed: torch.Tensor       # int32 [N, words_per_row(K, n_bits)]
+    packed: torch.Tensor       # int32 [ceil(N/128), K/64, tile_words] (tile-major)
     meta: torch.Tensor         # [K/group, N, 2] (scale, zero) in the compute dtype
     scales: torch.Tensor       # [N*K/group, 1] reference layout
     zeros: Optional[torch.Tensor]

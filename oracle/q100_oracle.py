@@ -240,68 +240,86 @@ def quant_linear(x, w, bias, dtype, group, w_bits, a_bits=16, symmetric=False,
     return linear(xq, wq, bias, dtype)
 
 
-# --------------------------------------------------------------------------- packed layout (q100 v1)
+# --------------------------------------------------------------------------- packed layout (q100 v2)
 # The reference never materialises integer codes; its --real_quant packing lives in
 # AutoGPTQ (not vendored).  The packed layout is therefore this project's own and is
 # pinned by the round trip unpack(pack(codes)) == codes plus the CUDA kernel writing
 # byte-identical words.  See DESIGN.md "Packed layout".
 #
-#   n_bits in {2,4,8}: F = 32/n_bits fields per uint32, a word covers F consecutive
-#     K-elements e[0..F); field j < F/2 holds e[2j], field F/2 + j holds e[2j+1]
-#     (so ``(word >> n_bits*j) & pair_mask`` yields the half2 pair (e[2j], e[2j+1])).
-#   n_bits == 3: two planes per row: the low 2 bits packed as n_bits=2 words
-#     ([rows, cols/16]) followed row-wise by the high bit packed with F = 32 fields
-#     ([rows, cols/32], same even/odd split: field j<16 -> e[2j], 16+j -> e[2j+1]).
+#   Tile-major: the [N, K] code matrix is cut into tiles of 128 rows x 64 k; tiles are stored
+#   contiguously, ordered [n_tile][k_tile] (so a CTA streaming along K for one row tile reads one
+#   contiguous run of HBM); N is padded up to a multiple of 128 with zero codes.
+#   Inside a tile, rows are stored one after the other.  A row's 64 codes are packed as
+#     n_bits in {2,4,8}: F = 32/n_bits codes per uint32, consecutive k; code e of a word sits in
+#       field (e >> 1) + (e & 1) * F/2, i.e. bit n_bits*(e>>1) + 16*(e&1)
+#       (so ``(word >> n_bits*j) & pair_mask`` yields the half2 pair (e[2j], e[2j+1])).
+#     n_bits == 3: the tile holds two planes: all rows' low 2 bits packed as n_bits=2 words
+#       (128 rows x 4 words) followed by all rows' high bit packed as 1-bit fields
+#       (128 rows x 2 words, same even/odd split).
 #   Stored code = x_int - qmin (unsigned).
-def words_per_row(cols: int, n_bits: int) -> int:
+TILE_ROWS = 128
+TILE_K = 64
+
+
+def tile_words(n_bits: int) -> int:
     if n_bits == 3:
-        return cols // 16 + cols // 32
-    return cols * n_bits // 32
+        return TILE_ROWS * (4 + 2)
+    return TILE_ROWS * (TILE_K * n_bits // 32)
+
+
+def packed_shape(rows: int, cols: int, n_bits: int):
+    assert cols % TILE_K == 0
+    return ((rows + TILE_ROWS - 1) // TILE_ROWS, cols // TILE_K, tile_words(n_bits))
 
 
 def _pack_plane(u: np.ndarray, bits: int) -> np.ndarray:
-    rows, cols = u.shape
+    """u: [..., 64] unsigned codes -> [..., 64*bits/32] words."""
     F = 32 // bits
-    assert cols % F == 0
-    e = u.reshape(rows, cols // F, F).astype(np.uint32)
-    word = np.zeros((rows, cols // F), dtype=np.uint32)
+    e = u.reshape(*u.shape[:-1], u.shape[-1] // F, F).astype(np.uint32)
+    word = np.zeros(e.shape[:-1], dtype=np.uint32)
     for j in range(F // 2):
-        word |= e[:, :, 2 * j] << np.uint32(bits * j)
-        word |= e[:, :, 2 * j + 1] << np.uint32(bits * (F // 2 + j))
+        word |= e[..., 2 * j] << np.uint32(bits * j)
+        word |= e[..., 2 * j + 1] << np.uint32(bits * (F // 2 + j))
     return word
 
 
 def _unpack_plane(word: np.ndarray, bits: int) -> np.ndarray:
-    rows, nw = word.shape
     F = 32 // bits
     mask = np.uint32((1 << bits) - 1)
-    e = np.zeros((rows, nw, F), dtype=np.uint32)
+    e = np.zeros((*word.shape, F), dtype=np.uint32)
     for j in range(F // 2):
-        e[:, :, 2 * j] = (word >> np.uint32(bits * j)) & mask
-        e[:, :, 2 * j + 1] = (word >> np.uint32(bits * (F // 2 + j))) & mask
-    return e.reshape(rows, nw * F)
+        e[..., 2 * j] = (word >> np.uint32(bits * j)) & mask
+        e[..., 2 * j + 1] = (word >> np.uint32(bits * (F // 2 + j))) & mask
+    return e.reshape(*word.shape[:-1], word.shape[-1] * F)
 
 
 def pack_codes(codes: np.ndarray, n_bits: int, disable_zero_point: bool = False) -> np.ndarray:
-    """Integer-valued codes ``[rows, cols]`` -> uint32 ``[rows, words_per_row]``."""
+    """Integer-valued codes ``[rows, cols]`` -> uint32 ``[n_tiles, k_tiles, tile_words]``."""
     qmin, _ = qrange(n_bits, disable_zero_point)
+    rows, cols = codes.shape
+    NT, KT, TW = packed_shape(rows, cols, n_bits)
     u = (np.nan_to_num(np.asarray(codes, np.float64), nan=float(qmin)) - qmin).astype(np.int64)
     assert u.min() >= 0 and u.max() < (1 << n_bits)
-    u = u.astype(np.uint32)
+    up = np.zeros((NT * TILE_ROWS, cols), dtype=np.uint32)
+    up[:rows] = u
+    t = up.reshape(NT, TILE_ROWS, KT, TILE_K).transpose(0, 2, 1, 3)          # [NT, KT, 128, 64]
     if n_bits == 3:
-        lo = _pack_plane(u & np.uint32(3), 2)
-        hi = _pack_plane(u >> np.uint32(2), 1)
-        return np.concatenate([lo, hi], axis=1)
-    return _pack_plane(u, n_bits)
+        lo = _pack_plane(t & np.uint32(3), 2).reshape(NT, KT, -1)
+        hi = _pack_plane(t >> np.uint32(2), 1).reshape(NT, KT, -1)
+        return np.ascontiguousarray(np.concatenate([lo, hi], axis=2))
+    return np.ascontiguousarray(_pack_plane(t, n_bits).reshape(NT, KT, TW))
 
 
-def unpack_codes(words: np.ndarray, cols: int, n_bits: int, disable_zero_point: bool = False) -> np.ndarray:
+def unpack_codes(words: np.ndarray, rows: int, cols: int, n_bits: int,
+                 disable_zero_point: bool = False) -> np.ndarray:
     qmin, _ = qrange(n_bits, disable_zero_point)
-    words = np.asarray(words, dtype=np.uint32)
+    NT, KT, TW = packed_shape(rows, cols, n_bits)
+    words = np.asarray(words, dtype=np.uint32).reshape(NT, KT, TW)
     if n_bits == 3:
-        lo = _unpack_plane(words[:, : cols // 16], 2)
-        hi = _unpack_plane(words[:, cols // 16:], 1)
-        u = lo | (hi << np.uint32(2))
+        lo = _unpack_plane(words[:, :, : TILE_ROWS * 4].reshape(NT, KT, TILE_ROWS, 4), 2)
+        hi = _unpack_plane(words[:, :, TILE_ROWS * 4:].reshape(NT, KT, TILE_ROWS, 2), 1)
+        t = lo | (hi << np.uint32(2))
     else:
-        u = _unpack_plane(words, n_bits)
+        t = _unpack_plane(words.reshape(NT, KT, TILE_ROWS, -1), n_bits)
+    u = t.transpose(0, 2, 1, 3).reshape(NT * TILE_ROWS, cols)[:rows]
     return u.astype(np.float32) + np.float32(qmin)

@@ -31,15 +31,16 @@ def test_abi_version():
     assert _lib.lib.q100_abi_version() == 1
 
 
-def test_words_per_row():
-    assert q100.packed_words_per_row(4096, 4) == 512
-    assert q100.packed_words_per_row(4096, 2) == 256
-    assert q100.packed_words_per_row(4096, 8) == 1024
-    assert q100.packed_words_per_row(4096, 3) == 256 + 128
+def test_packed_shape():
+    assert q100.packed_shape(4096, 4096, 4) == (32, 64, 1024)
+    assert q100.packed_shape(4096, 4096, 2) == (32, 64, 512)
+    assert q100.packed_shape(4096, 4096, 8) == (32, 64, 2048)
+    assert q100.packed_shape(4096, 4096, 3) == (32, 64, 768)
+    assert q100.packed_shape(130, 128, 4) == (2, 2, 1024)          # rows padded to 128
     with pytest.raises(ValueError):
-        q100.packed_words_per_row(100, 4)
+        q100.packed_shape(128, 96, 4)
     with pytest.raises(ValueError):
-        q100.packed_words_per_row(4096, 5)
+        q100.packed_shape(128, 4096, 5)
 
 
 def test_workspace_bytes_is_pure():

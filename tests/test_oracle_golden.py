@@ -85,24 +85,33 @@ def test_oracle_linear(case):
 def test_pack_roundtrip(n_bits, nozp):
     rng = np.random.RandomState(n_bits)
     qmin, qmax = O.qrange(n_bits, nozp)
-    codes = rng.randint(qmin, qmax + 1, size=(7, 256)).astype(np.float32)
-    words = O.pack_codes(codes, n_bits, nozp)
-    assert words.shape == (7, O.words_per_row(256, n_bits)) and words.dtype == np.uint32
-    assert np.array_equal(O.unpack_codes(words, 256, n_bits, nozp), codes)
+    for rows, cols in ((7, 256), (128, 64), (300, 192)):
+        codes = rng.randint(qmin, qmax + 1, size=(rows, cols)).astype(np.float32)
+        words = O.pack_codes(codes, n_bits, nozp)
+        assert words.shape == O.packed_shape(rows, cols, n_bits) and words.dtype == np.uint32
+        assert np.array_equal(O.unpack_codes(words, rows, cols, n_bits, nozp), codes)
 
 
 def test_pack_layout_known_answer():
-    # W4: element e of a word sits at bit 4*(e>>1) + 16*(e&1)
-    codes = np.tile(np.arange(8, dtype=np.float32), 4).reshape(1, 32)
+    # W4: element e of a word sits at bit 4*(e>>1) + 16*(e&1); a row of a tile is 8 words
+    codes = np.zeros((130, 128), np.float32)
+    codes[0, :8] = np.arange(8)
+    codes[1, 64:72] = 15                      # row 1, second k-tile
+    codes[129, 8:16] = np.arange(8)           # second n-tile, row 1, word 1
     w = O.pack_codes(codes, 4)
-    assert w.shape == (1, 4) and int(w[0, 0]) == 0x75316420
-    # W2: 16 elements per word, pairs (e0,e1) -> bits [0,2) and [16,18)
-    c2 = np.array([[1, 2] + [0] * 30], dtype=np.float32)
-    assert int(O.pack_codes(c2, 2)[0, 0]) == (1 | (2 << 16))
-    # W3: low 2 bits as W2 words, then the high bit as 32-per-word
-    c3 = np.array([[5, 6] + [0] * 30], dtype=np.float32)
+    assert w.shape == (2, 2, 1024)
+    assert int(w[0, 0, 0]) == 0x75316420
+    assert int(w[0, 1, 8]) == 0xFFFFFFFF and int(w[0, 0, 8]) == 0
+    assert int(w[1, 0, 8 + 1]) == 0x75316420
+    # W2: 16 codes per word, 4 words per row
+    c2 = np.zeros((1, 64), np.float32); c2[0, :2] = (1, 2); c2[0, 16] = 3
+    w2 = O.pack_codes(c2, 2)
+    assert w2.shape == (1, 1, 512) and int(w2[0, 0, 0]) == (1 | (2 << 16)) and int(w2[0, 0, 1]) == 3
+    # W3: plane of low 2 bits (128 rows x 4 words) then plane of high bits (128 rows x 2 words)
+    c3 = np.zeros((2, 64), np.float32); c3[1, :2] = (5, 6)
     w3 = O.pack_codes(c3, 3)
-    assert w3.shape == (1, 3) and int(w3[0, 0]) == (1 | (2 << 16)) and int(w3[0, 2]) == (1 | (1 << 16))
+    assert w3.shape == (1, 1, 768)
+    assert int(w3[0, 0, 4]) == (1 | (2 << 16)) and int(w3[0, 0, 512 + 2]) == (1 | (1 << 16))
 
 
 def test_rounding_helpers():

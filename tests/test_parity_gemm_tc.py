@@ -52,3 +52,32 @@ def test_tc_matches_skinny_bits_of_weight():
     assert torch.equal(y_tc.t().contiguous().view(torch.int16), r.dequant.view(torch.int16))
     y_sk = q100.gemm_wna16(x[:32].contiguous(), pw, None, flags=_lib.GEMM_FORCE_SKINNY)
     assert torch.equal(y_sk.view(torch.int16), y_tc[:32].contiguous().view(torch.int16))
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f16"])
+@pytest.mark.parametrize("n_bits", [2, 8])
+def test_tc_other_bits(dtype, n_bits):
+    for (M, N, K, group) in ((128, 128, 128, 128), (300, 384, 1024, 128), (512, 256, 512, 0)):
+        x, w, pw, r = _make(N, K, M, dtype, n_bits, group or None, M + N + K + n_bits)
+        y = q100.gemm_wna16(x, pw, None, flags=_lib.GEMM_FORCE_TC)
+        torch.cuda.synchronize()
+        _check(y, x, r.dequant, None, dtype)
+
+
+def test_tc_weird_zero_points_and_nozp():
+    """Slow dequant path (zero-points far outside the code range) and the no-zero-point mode."""
+    torch.manual_seed(3)
+    w = torch.randn(128, 256) * 0.02
+    w[0:8] = w[0:8].abs() + 0.5
+    w[8:16] = -(w[8:16].abs() + 0.5)
+    w[16:24] = 0.3
+    w[24:32] = 0.0
+    for dt in (torch.float16, torch.bfloat16):
+        wd = w.to(dt).cuda()
+        x = torch.randn(64, 256).to(dt).cuda()
+        pw, r = q100.pack_weight(wd, 4, 128, want_dequant=True)
+        y = q100.gemm_wna16(x, pw, None, flags=_lib.GEMM_FORCE_TC)
+        _check(y, x, r.dequant, None, "f16" if dt == torch.float16 else "bf16")
+        pw, r = q100.pack_weight(wd, 4, 128, True, True, want_dequant=True)
+        y = q100.gemm_wna16(x, pw, None, flags=_lib.GEMM_FORCE_TC)
+        _check(y, x, r.dequant, None, "f16" if dt == torch.float16 else "bf16")

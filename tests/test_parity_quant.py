@@ -17,8 +17,8 @@ A = load_golden("activations")
 MODES = {"packed": 0, "scalar": _lib.FLAG_SCALAR_MATH, "ieee": _lib.FLAG_IEEE_DIV}
 
 
-def _codes_from_packed(packed, cols, n_bits, nozp):
-    return O.unpack_codes(packed.cpu().numpy().view(np.uint32), cols, n_bits, nozp)
+def _codes_from_packed(packed, rows, cols, n_bits, nozp):
+    return O.unpack_codes(packed.cpu().numpy().view(np.uint32), rows, cols, n_bits, nozp)
 
 
 @pytest.mark.parametrize("mode", sorted(MODES))
@@ -37,7 +37,7 @@ def test_golden_weights(case, mode):
     low = bits_to_torch(rec["lwc_low"], dtype, "cuda") if lwc else None
     cols = w.shape[1]
     g = group or cols
-    can_pack = cols % 32 == 0 and (g in (32, 64, 128, 256) or g == cols)
+    can_pack = cols % 64 == 0 and (g in (32, 64, 128, 256) or g == cols)
     can_meta = can_pack and dtype != "f32"
     r = q100.quantize_groupwise(w, group, n_bits, sym, nozp, up, low, want_dequant=True,
                                 want_packed=can_pack, want_meta=can_meta, flags=MODES[mode])
@@ -50,7 +50,7 @@ def test_golden_weights(case, mode):
     else:
         assert_same_bits(torch_to_bits(r.zeros), rec["zeros"], dtype, "zeros")
     if can_pack:
-        codes = _codes_from_packed(r.packed, cols, n_bits, nozp)
+        codes = _codes_from_packed(r.packed, w.shape[0], cols, n_bits, nozp)
         want = rec["codes"].reshape(codes.shape).astype(np.float32)
         qmin, _ = O.qrange(n_bits, nozp)
         want = np.where(want == -32768, qmin, want)            # NaN code is stored as qmin
@@ -109,7 +109,7 @@ def test_random_vs_oracle(dtype, n_bits, shape, group):
         with pytest.raises(q100.Q100Error):
             q100.quantize_groupwise(x.cuda(), group, n_bits)
         return
-    can_pack = cols % 32 == 0 and (g in (32, 64, 128, 256) or g == cols)
+    can_pack = cols % 64 == 0 and (g in (32, 64, 128, 256) or g == cols)
     r = q100.quantize_groupwise(x.cuda(), group, n_bits, want_packed=can_pack)
     torch.cuda.synchronize()
     assert_same_bits(torch_to_bits(r.dequant), O.to_bits(o["dequant"], dtype), dtype, "dequant")
@@ -118,9 +118,9 @@ def test_random_vs_oracle(dtype, n_bits, shape, group):
     if can_pack:
         assert np.array_equal(r.packed.cpu().numpy().view(np.uint32), O.pack_codes(o["codes"], n_bits))
         # dequantize(packed) reproduces the fake-quantised tensor bit for bit
-        back = q100.dequantize(r.packed, r.scales, r.zeros, cols, group, n_bits, TDT[dtype])
+        back = q100.dequantize(r.packed, r.scales, r.zeros, shape[0], cols, group, n_bits, TDT[dtype])
         assert_same_bits(torch_to_bits(back), torch_to_bits(r.dequant), dtype, "dequantize(pack(x))")
-        raw = q100.dequantize(r.packed, None, None, cols, group, n_bits, torch.float32)
+        raw = q100.dequantize(r.packed, None, None, shape[0], cols, group, n_bits, torch.float32)
         assert np.array_equal(raw.cpu().numpy(), o["codes"])
 
 
@@ -136,7 +136,7 @@ def test_symmetric_and_nozp_vs_oracle(dtype):
             assert_same_bits(torch_to_bits(r.dequant), O.to_bits(o["dequant"], dtype), dtype, f"deq w{n_bits} {sym} {nozp}")
             assert_same_bits(torch_to_bits(r.scales), O.to_bits(o["scales"], dtype), dtype, "scales")
             assert np.array_equal(r.packed.cpu().numpy().view(np.uint32), O.pack_codes(o["codes"], n_bits, nozp))
-            back = q100.dequantize(r.packed, r.scales, r.zeros, 1024, 128, n_bits, TDT[dtype], nozp)
+            back = q100.dequantize(r.packed, r.scales, r.zeros, 64, 1024, 128, n_bits, TDT[dtype], nozp)
             assert_same_bits(torch_to_bits(back), torch_to_bits(r.dequant), dtype, "dequantize")
 
 
@@ -168,7 +168,7 @@ def test_full_size_properties(dtype):
     r = q100.quantize_groupwise(w, 128, 4, want_packed=True, want_meta=(dtype != "f32"))
     torch.cuda.synchronize()
     # (1) decode(pack) == fake-quant output, bit for bit
-    back = q100.dequantize(r.packed, r.scales, r.zeros, 4096, 128, 4, TDT[dtype])
+    back = q100.dequantize(r.packed, r.scales, r.zeros, 14336, 4096, 128, 4, TDT[dtype])
     assert torch.equal(back.view(torch.int32 if dtype == "f32" else torch.int16),
                        r.dequant.view(torch.int32 if dtype == "f32" else torch.int16))
     # (2) all three math paths agree on every bit
@@ -178,14 +178,15 @@ def test_full_size_properties(dtype):
         assert torch.equal(r2.dequant.view(torch.int16 if dtype != "f32" else torch.int32),
                            r.dequant.view(torch.int16 if dtype != "f32" else torch.int32))
     # (3) codes span the range and the error is bounded by scale/2 (+ storage rounding)
-    codes = q100.dequantize(r.packed, None, None, 4096, 128, 4, torch.float32)
+    codes = q100.dequantize(r.packed, None, None, 14336, 4096, 128, 4, torch.float32)
     assert float(codes.min()) == 0.0 and float(codes.max()) == 15.0
     err = (r.dequant.float() - w.float()).abs().view(-1, 128)
-    assert bool((err <= r.scales.float() * 0.51 + 1e-6).all())
+    assert bool((err <= r.scales.float() * 1.01 + 1e-6).all())   # <= scale/2 rounding + <= scale/2 from the rounded zero-point
     # (4) row-sharding invariance: quantising a slice == slicing the result
     sl = slice(1024, 1024 + 512)
     r3 = q100.quantize_groupwise(w[sl].contiguous(), 128, 4, want_packed=True)
-    assert torch.equal(r3.packed, r.packed[sl]) and torch.equal(r3.scales.view(512, -1), r.scales.view(14336, -1)[sl])
+    assert torch.equal(r3.packed, r.packed[1024 // 128:(1024 + 512) // 128]) and \
+        torch.equal(r3.scales.view(512, -1), r.scales.view(14336, -1)[sl])
     # (5) K-sharding invariance on multiples of the group
     r4 = q100.quantize_groupwise(w[:, 2048:].contiguous(), 128, 4)
     assert torch.equal(r4.dequant.view(torch.int16 if dtype != "f32" else torch.int32),
@@ -195,4 +196,5 @@ def test_full_size_properties(dtype):
     ws = w[idx].contiguous()
     o = O.quantize_groupwise(O.from_bits(torch_to_bits(ws), dtype).reshape(6, 4096), dtype, 128, 4)
     assert_same_bits(torch_to_bits(r.dequant[idx]), O.to_bits(o["dequant"], dtype), dtype, "sample rows")
-    assert np.array_equal(r.packed[idx].cpu().numpy().view(np.uint32), O.pack_codes(o["codes"], 4))
+    codes_s = q100.dequantize(r.packed, None, None, 14336, 4096, 128, 4, torch.float32)[idx]
+    assert np.array_equal(codes_s.cpu().numpy(), o["codes"])

@@ -85,6 +85,18 @@ def main():
         run("skinny_m1", lambda i: q100.gemm_wna16(x1, pws[i % 3], None, _lib.GEMM_FORCE_SKINNY), algo_bytes=wbytes)
     if "skinny16" in which:
         run("skinny_m16", lambda i: q100.gemm_wna16(x16, pws[i % 3], None, _lib.GEMM_FORCE_SKINNY), algo_bytes=wbytes)
+    if "dense" in which:
+        from q100 import ops
+        wd = ws[0]
+        run("dense_tc", lambda i: ops.debug_gemm_dense_tc(x2k, ws[i % 3]), flops=2.0 * 2048 * N * K)
+    if "contig" in which:
+        # same bytes as up_proj but every [128 rows x 256 k] unit is one contiguous 16 KB run in HBM
+        Nc, Kc = N * 16, K // 16
+        wc = [(torch.randn(Nc, Kc, device=dev) * 0.02).to(dt) for _ in range(3)]
+        pwc = [q100.pack_weight(w, 4, 128)[0] for w in wc]
+        xc = torch.randn(1, Kc, device=dev).to(dt)
+        run("skinny_ctg", lambda i: q100.gemm_wna16(xc, pwc[i % 3], None, _lib.GEMM_FORCE_SKINNY), algo_bytes=pwc[0].nbytes())
+        del wc, pwc
     if "tc" in which:
         run("tc_m2048", lambda i: q100.gemm_wna16(x2k, pws[i % 3], None, _lib.GEMM_FORCE_TC), flops=2.0 * 2048 * N * K)
 
