@@ -85,11 +85,12 @@ extern "C" int q100_gemm_wna16(const void* x, const void* packed, const void* me
   int rc = ensure_device();
   if (rc != Q100_OK) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool skinny_ok = (K % 256 == 0) && (N % 8 == 0);
+  const bool tc_ok = gemm_tc_supported(M, N, K, group, n_bits);
   const bool want_tc = (flags & Q100_GEMM_FORCE_TC) ||
-                       (!(flags & Q100_GEMM_FORCE_SKINNY) && M > 32 && gemm_tc_supported(M, N, K, group, n_bits));
+                       (!(flags & Q100_GEMM_FORCE_SKINNY) && tc_ok && (M > 32 || !skinny_ok));
   if (want_tc) {
-    Q100_REQUIRE(gemm_tc_supported(M, N, K, group, n_bits), Q100_EUNSUPPORTED,
-                 "tcgen05 path does not support this shape/bit-width");
+    Q100_REQUIRE(tc_ok, Q100_EUNSUPPORTED, "tcgen05 path does not support this shape/bit-width");
     return gemm_tc(x, packed, meta, bias, y, M, N, K, group, n_bits, disable_zp, dtype, st);
   }
   // weight-streaming kernel, 32 rows of x per pass

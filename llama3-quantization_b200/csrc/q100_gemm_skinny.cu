@@ -2,23 +2,30 @@
 //
 //   y[M, N] = x[M, K] . dequant(W)[N, K]^T (+ bias)        quant/int_linear.py:62
 //
-// HBM-bound: the packed weights (n_bits/8 B per weight) are the only large stream; they
-// are read exactly once.  Structure (one persistent CTA per SM slot, 8 consumer warps +
-// 1 producer warp):
-//   * producer: TMA bulk copies (cp.async.bulk) of whole [128 rows x 64 k] packed tiles -- the
-//     tile-major layout makes every pipeline unit one contiguous run of HBM -- plus 1-D bulk copies
-//     of the transposed (scale, zero) side band and cp.async of the x slab -> 4-stage smem ring,
-//     mbarrier full/empty pairs;
-//   * consumers: each warp owns 16 output rows; packed codes -> registers, dequantised
-//     in registers with the reference's exact per-op rounding
-//     (w = r(r(q - zp) * scale), bit-identical to the fake-quantised weight) and fed to
-//     mma.sync.m16n8k16 as the A operand, x^T as B, fp32 accumulators.
-//     tcgen05 is deliberately not used here: at M <= 32 the operand would have to be
-//     written back to shared memory (2 B/weight) and that traffic alone exceeds the time
-//     budget of the 0.5 B/weight HBM stream (DESIGN.md "K3a").
-//   * work is split stream-K style over 148*k CTAs in units of [128 rows x 256 k]; a tile
-//     finished by several CTAs is reduced by the last arriver from fp32 partials in a
-//     caller-provided workspace, in fixed slot order (deterministic).
+// HBM-bound: the packed weights (n_bits/8 B per weight) are the only large stream and are read
+// exactly once.  Structure (persistent CTAs of 8 warps):
+//   * every consumer warp owns 16 output rows of the CTA's 128-row tile and streams ITS OWN
+//     slice of the packed codes straight from global memory into registers with 128-bit
+//     ld.global.nc loads, four 128-k blocks ahead (software-pipelined register ring).  The
+//     tile-major packed layout makes each warp-wide load two fully used 256-byte segments and
+//     the CTA's whole stream one linear run of HBM.  (A TMA/shared-memory ring for the codes was
+//     measured first: it topped out at 3.9 TB/s with no compute at all -- profiles/ r01 notes --
+//     because the per-SM bulk-copy path cannot keep enough bytes in flight against HBM latency;
+//     registers can.)
+//   * x is tiny: the CTA stages the slab of x it needs (up to 16 k-blocks at a time) into shared
+//     memory itself, in a bank-conflict-free permuted order, together with the per-block sums
+//     S[m] = sum_k x[m][k]; no producer warp, no mbarrier ring, one __syncthreads per 2048 k;
+//   * codes are used in "magic form": (MAGIC + q) is built with one AND/OR per pair and fed to
+//     mma.sync.m16n8k16 as the A operand (x^T is B); the block's contribution is
+//     scale * (acc_q - (MAGIC + zp) * S) in fp32.  With Q100_GEMM_EXACT_WEIGHTS (or group < 128)
+//     the 16-bit fake-quantised weight r(r(q-zp)*scale) is rebuilt bit-exactly instead.
+//     tcgen05 is deliberately not used here: at M <= 32 the operand would have to be written
+//     back to shared memory (2 B/weight) and that traffic alone exceeds the time budget of the
+//     0.5 B/weight HBM stream (DESIGN.md "K3a").
+//   * work is split stream-K style over 148*k CTAs in units of [128 rows x 256 k]; a tile shared
+//     by several CTAs is finished warp-asynchronously: each warp stores its fp32 fragment to its
+//     CTA's slot, fences, bumps the counter of ITS 16-row fragment, and the last arriver sums that
+//     fragment's slots in slot order (deterministic) and writes y.  No CTA-wide barrier there.
 //
 // Lane <-> k mapping: inside a 128-k block lane t (= lane & 3) owns k in [32t, 32t+32) for
 // both operands, i.e. the mma "slot" (s, 2t+{0,1,8,9}) of k16-step s carries
@@ -33,11 +40,14 @@
 namespace q100 {
 
 constexpr int SK_ROWS = 128;       // output rows per tile (8 warps x 16)
-constexpr int SK_KB = 128;         // k per block (one TMA box)
-constexpr int SK_KBU = 2;          // k blocks per pipeline unit
-constexpr int SK_STAGES = 4;
-constexpr int SK_CONSUMERS = 256;
-constexpr int SK_THREADS = SK_CONSUMERS + 32;
+constexpr int SK_KB = 128;         // k per block
+constexpr int SK_KBU = 2;          // k blocks per stream-K unit
+constexpr int SK_DEPTH = 2;        // k blocks of packed codes in flight per lane (register ring); occupancy,
+                                   // not per-warp depth, is what fills HBM (profiles/r01 stream microbenchmarks)
+constexpr int SK_MAX_CTAS = 4;     // resident CTAs per SM the launch bounds aim for (MB = 1)
+constexpr int SK_CHUNK = 16;       // k blocks of x staged in shared memory at a time (multiple of SK_DEPTH)
+constexpr int SK_THREADS = 256;
+constexpr size_t SK_COUNTER_BYTES = 1 << 18;   // workspace prefix: per-fragment arrival counters (N <= 1 M rows)
 constexpr int SK_XPITCH = 320;     // bytes per (m, 128-k) x row in smem: 256 + 64 pad (conflict-free LDS.128)
 
 struct SkinnyArgs {
@@ -47,37 +57,27 @@ struct SkinnyArgs {
   const void* bias;       // [N] T or null
   void* y;                // [M, N] T
   float* ws_partials;     // workspace: fp32 partial tiles
-  int* ws_counters;       // workspace: one arrival counter per tile (zero between launches)
+  int* ws_counters;       // workspace: one arrival counter per 16-row fragment (zero between launches)
   int M, N, K, group;
   int kblocks;            // K / 128
-  int kbu;                // k blocks per unit (1 or 2)
-  int units_per_tile;
+  int units_per_tile;     // kblocks / 2
   int n_tiles;
   int total_units;
   int max_slots;
   int has_zp;
   float qmin;
-  int meta_stage;         // bytes of (scale, zero) side band per stage, multiple of 128
   int post;               // 1: magic-form operand + fp32 group scaling (group % 128 == 0)
-  int stage_bytes;        // W + side band + x slab, multiple of 128
+  int m_rows;             // rows of x kept in shared memory (= M)
 };
 
-// Packed layout v2: tiles of [128 rows x 64 k] are contiguous in HBM; a 128-k block is two
-// consecutive k-tiles.  Each k-tile is bulk-copied to its own padded slot in shared memory so that
-// the two k-tiles of a block fall on different banks (conflict-free LDS for all four lanes t).
 template <int NBITS> struct WGeom {
   static constexpr int kTileBytes = NBITS == 3 ? 128 * 24 : 128 * 8 * NBITS;   // one [128 x 64] tile
-  static constexpr int kPitch = kTileBytes + (NBITS == 8 ? 16 : 64);
-  static constexpr int kRowBytes = NBITS == 3 ? 16 : 8 * NBITS;                // plane 0 bytes per row per k-tile
 };
 
-template <int NBITS, int MB>
-struct SkinnySmem {
-  static constexpr int kWBytes = ((SK_KBU * 2 * WGeom<NBITS>::kPitch) + 127) & ~127;
-  static constexpr int kXBytes = SK_KBU * MB * 8 * SK_XPITCH;
-  __host__ __device__ static constexpr int stage(int meta_stage) { return kWBytes + meta_stage + kXBytes; }
-  __host__ __device__ static constexpr int total(int meta_stage) { return SK_STAGES * stage(meta_stage) + 1024; }
-};
+// shared memory: x slab [SK_CHUNK blocks][m_rows][SK_XPITCH] + block sums [SK_CHUNK][MB*8] fp32
+__host__ __device__ constexpr int skinny_smem_bytes(int m_rows, int mb) {
+  return SK_CHUNK * m_rows * SK_XPITCH + SK_CHUNK * mb * 8 * 4 + 128;
+}
 
 // ---------------------------------------------------------------- dequant helpers
 template <typename T> struct DQ;
@@ -121,24 +121,24 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
   return v;
 }
-__device__ __forceinline__ uint2 lds64(uint32_t addr) {
-  uint2 v;
-  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
-  return v;
+__device__ __forceinline__ uint2 ldg64_stream(const void* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+  return r;
 }
-__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
-  uint32_t v;
-  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
-  return v;
+__device__ __forceinline__ uint32_t ldg32_stream(const void* p) {
+  uint32_t r;
+  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+  return r;
 }
 
-// A lane's 32 codes (k in [32t, 32t+32) of one row's 128-k block) as 16 pairs.  `blk` is the shared
-// address of the block's first k-tile; lane t reads k-tile (t >> 1), half (t & 1).
+// A lane's 32 codes (k in [32t, 32t+32) of one row's 128-k block) as 16 pairs, loaded from the
+// two consecutive [128 x 64] tiles of the block: lane t reads k-tile (t >> 1), half (t & 1).
 template <int NBITS> struct LaneCodes;
 template <> struct LaneCodes<4> {
   uint4 w;
-  __device__ __forceinline__ void load(uint32_t blk, int row, int t) {
-    w = lds128(blk + (t >> 1) * WGeom<4>::kPitch + row * 32 + (t & 1) * 16);
+  __device__ __forceinline__ void load(const uint8_t* blk, int row, int t) {
+    w = ldg_stream(blk + (t >> 1) * WGeom<4>::kTileBytes + row * 32 + (t & 1) * 16);
   }
   __device__ __forceinline__ uint32_t pair(int i) const {
     const uint32_t x = (i >> 2) == 0 ? w.x : (i >> 2) == 1 ? w.y : (i >> 2) == 2 ? w.z : w.w;
@@ -147,8 +147,8 @@ template <> struct LaneCodes<4> {
 };
 template <> struct LaneCodes<2> {
   uint2 w;
-  __device__ __forceinline__ void load(uint32_t blk, int row, int t) {
-    w = lds64(blk + (t >> 1) * WGeom<2>::kPitch + row * 16 + (t & 1) * 8);
+  __device__ __forceinline__ void load(const uint8_t* blk, int row, int t) {
+    w = ldg64_stream(blk + (t >> 1) * WGeom<2>::kTileBytes + row * 16 + (t & 1) * 8);
   }
   __device__ __forceinline__ uint32_t pair(int i) const {
     const uint32_t x = (i >> 3) == 0 ? w.x : w.y;
@@ -157,10 +157,10 @@ template <> struct LaneCodes<2> {
 };
 template <> struct LaneCodes<8> {
   uint4 w0, w1;
-  __device__ __forceinline__ void load(uint32_t blk, int row, int t) {
-    const uint32_t p = blk + (t >> 1) * WGeom<8>::kPitch + row * 64 + (t & 1) * 32;
-    w0 = lds128(p);
-    w1 = lds128(p + 16);
+  __device__ __forceinline__ void load(const uint8_t* blk, int row, int t) {
+    const uint8_t* p = blk + (t >> 1) * WGeom<8>::kTileBytes + row * 64 + (t & 1) * 32;
+    w0 = ldg_stream(p);
+    w1 = ldg_stream(p + 16);
   }
   __device__ __forceinline__ uint32_t pair(int i) const {
     const int wi = i >> 1;
@@ -172,15 +172,22 @@ template <> struct LaneCodes<8> {
 template <> struct LaneCodes<3> {
   uint2 lo;
   uint32_t hi;
-  __device__ __forceinline__ void load(uint32_t blk, int row, int t) {
-    const uint32_t p = blk + (t >> 1) * WGeom<3>::kPitch;
-    lo = lds64(p + row * 16 + (t & 1) * 8);                  // 2-bit plane: 128 rows x 16 B
-    hi = lds32(p + 128 * 16 + row * 8 + (t & 1) * 4);        // 1-bit plane: 128 rows x 8 B
+  __device__ __forceinline__ void load(const uint8_t* blk, int row, int t) {
+    const uint8_t* p = blk + (t >> 1) * WGeom<3>::kTileBytes;
+    lo = ldg64_stream(p + row * 16 + (t & 1) * 8);                  // 2-bit plane: 128 rows x 16 B
+    hi = ldg32_stream(p + 128 * 16 + row * 8 + (t & 1) * 4);        // 1-bit plane: 128 rows x 8 B
   }
   __device__ __forceinline__ uint32_t pair(int i) const {
     const uint32_t x = (i >> 3) == 0 ? lo.x : lo.y;
     return ((x >> (2 * (i & 7))) & 0x00030003u) | (((hi >> i) & 0x00010001u) << 2);
   }
+};
+
+// everything a lane needs for one 128-k block: codes of its two rows + their (scale, zero) pairs
+template <int NBITS>
+struct BlockRegs {
+  LaneCodes<NBITS> c0, c1;
+  uint32_t m0, m1;
 };
 
 // owner CTA of stream-K unit u when G CTAs split U units as [floor(c*U/G), floor((c+1)*U/G))
@@ -190,20 +197,18 @@ __device__ __forceinline__ int unit_owner(int u, int G, int U) {
 
 // ---------------------------------------------------------------- kernel
 template <typename T, int NBITS, int MB, bool POST>
-__global__ void __launch_bounds__(SK_THREADS)
+__global__ void __launch_bounds__(SK_THREADS, MB == 1 ? 4 : MB == 2 ? 3 : 2)
 k3_skinny(const SkinnyArgs a) {
-  using SM = SkinnySmem<NBITS, MB>;
   using T2 = typename DQ<T>::T2;
   constexpr bool kBf16 = DT<T>::kCode == Q100_BF16;
   constexpr int kTileB = WGeom<NBITS>::kTileBytes;
-  constexpr int kPitch = WGeom<NBITS>::kPitch;
+  constexpr int FRAG = SK_ROWS * MB * 8;              // floats per partial tile
 
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  // 1024-aligned carve-up
-  const uint32_t base_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* base = smem_raw + (base_u32 - smem_u32(smem_raw));
-  __shared__ uint64_t full_bar[SK_STAGES], empty_bar[SK_STAGES];
-  __shared__ int s_flag;
+  const uint32_t xs_u32 = (smem_u32(smem_raw) + 127u) & ~127u;
+  uint8_t* xs_ptr = smem_raw + (xs_u32 - smem_u32(smem_raw));
+  const int mrows = a.m_rows;
+  float* xsum_s = reinterpret_cast<float*>(xs_ptr + SK_CHUNK * mrows * SK_XPITCH);     // [SK_CHUNK][MB*8]
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -212,247 +217,227 @@ k3_skinny(const SkinnyArgs a) {
   const int u_begin = static_cast<int>(static_cast<int64_t>(cta) * U / G);
   const int u_end = static_cast<int>(static_cast<int64_t>(cta + 1) * U / G);
 
-  if (tid == 0) {
-    for (int s = 0; s < SK_STAGES; ++s) {
-      mbar_init(&full_bar[s], 1 + 32);        // expect_tx arrive + 32 cp.async noinc arrives
-      mbar_init(&empty_bar[s], 8);            // one arrive per consumer warp
-    }
-    fence_mbar_init();
-  }
-  __syncthreads();
-
-  const int groups_per_block = a.group >= SK_KB ? 1 : SK_KB / a.group;   // side-band rows per 128-k block
-
-  if (warp == 8) {
-    // ============================ producer warp ============================
-    const uint64_t pol = policy_evict_first();
-    const T* xg = reinterpret_cast<const T*>(a.x);
-    int it = 0;
-    for (int u = u_begin; u < u_end; ++u, ++it) {
-      const int stage = it % SK_STAGES;
-      const uint32_t phase = (it / SK_STAGES) & 1;
-      mbar_wait(&empty_bar[stage], phase ^ 1);
-      uint8_t* st = base + stage * a.stage_bytes;
-      const int tile = u / a.units_per_tile, ku = u % a.units_per_tile;
-      const int n0 = tile * SK_ROWS;
-      const int kb0 = ku * a.kbu;
-      const int nkb = min(a.kbu, a.kblocks - kb0);
-      const int rows_valid = min(SK_ROWS, a.N - n0);
-      if (lane == 0) {
-        const uint32_t meta_bytes = static_cast<uint32_t>(rows_valid) * 2u * sizeof(T);
-        mbar_expect_tx(&full_bar[stage], nkb * (2u * kTileB + groups_per_block * meta_bytes));
-        // 2*nkb consecutive [128 x 64] tiles of this row tile: one contiguous run in HBM
-        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.packed) +
-                              (static_cast<int64_t>(tile) * (a.kblocks * 2) + kb0 * 2) * kTileB;
-        for (int kt = 0; kt < 2 * nkb; ++kt)
-          bulk_load_1d_hint(st + kt * kPitch, wsrc + static_cast<int64_t>(kt) * kTileB, kTileB,
-                            &full_bar[stage], pol);
-        for (int kb = 0; kb < nkb; ++kb) {
-          const int kblk = kb0 + kb;
-          for (int gi = 0; gi < groups_per_block; ++gi) {
-            const int kg = (kblk * SK_KB + gi * a.group) / a.group;
-            const T* src = reinterpret_cast<const T*>(a.meta) + (static_cast<int64_t>(kg) * a.N + n0) * 2;
-            bulk_load_1d(st + SM::kWBytes + (kb * groups_per_block + gi) * (SK_ROWS * 2 * sizeof(T)),
-                         src, meta_bytes, &full_bar[stage]);
-          }
-        }
-      }
-      // x slab: rows m < MB*8, 16 chunks of 16 B per (m, k block); chunk c = 4t + j is stored at
-      // offset 16t + 64j so that consumer LDS.128 is bank-conflict free.
-      {
-        const uint32_t xs = smem_u32(st + SM::kWBytes + a.meta_stage);
-        const int n_chunks = nkb * MB * 8 * 16;
-        for (int c = lane; c < n_chunks; c += 32) {
-          const int kb = c / (MB * 8 * 16);
-          const int rem = c % (MB * 8 * 16);
-          const int m = rem >> 4, ch = rem & 15;
-          const uint32_t dst = xs + (kb * MB * 8 + m) * SK_XPITCH + (ch >> 2) * 16 + (ch & 3) * 64;
-          const bool ok = m < a.M;
-          const T* src = xg + static_cast<int64_t>(ok ? m : 0) * a.K + (kb0 + kb) * SK_KB + ch * 8;
-          const uint32_t src_bytes = ok ? 16u : 0u;      // src-size 0 => zero fill
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
-                       :: "r"(dst), "l"(src), "r"(src_bytes) : "memory");
-        }
-        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];"
-                     :: "r"(smem_u32(&full_bar[stage])) : "memory");
-      }
-    }
-    // drain: do not exit while copies are in flight
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    return;
-  }
-
-  // ============================ consumer warps ============================
   const int g = lane >> 2, t = lane & 3;
   const int r0 = warp * 16 + g, r1 = r0 + 8;
-  float acc[MB][4];
-#pragma unroll
-  for (int mb = 0; mb < MB; ++mb) { acc[mb][0] = acc[mb][1] = acc[mb][2] = acc[mb][3] = 0.f; }
   const uint32_t qb = DT<T>::pack2(a.qmin, a.qmin);
   const T2 qmin2 = *reinterpret_cast<const T2*>(&qb);
   const bool has_zp = a.has_zp != 0;
+  const uint8_t* wbase = reinterpret_cast<const uint8_t*>(a.packed);
+  const uint8_t* mbase = reinterpret_cast<const uint8_t*>(a.meta);
 
-  int it = 0;
-  int seg_begin = u_begin;                      // first unit of the current tile segment
-  for (int u = u_begin; u < u_end; ++u, ++it) {
-    const int stage = it % SK_STAGES;
-    const uint32_t phase = (it / SK_STAGES) & 1;
-    const int tile = u / a.units_per_tile, ku = u % a.units_per_tile;
-    const int kb0 = ku * a.kbu;
-    const int nkb = min(a.kbu, a.kblocks - kb0);
-    mbar_wait(&full_bar[stage], phase);
-    const uint32_t st = base_u32 + stage * a.stage_bytes;
-    for (int kb = 0; kb < nkb; ++kb) {
-      const uint32_t wblk = st + kb * 2 * kPitch;
-      LaneCodes<NBITS> c0, c1;
-      c0.load(wblk, r0, t);
-      c1.load(wblk, r1, t);
-      const int gi = a.group >= SK_KB ? 0 : (32 * t) / a.group;
-      const uint32_t mt = st + SM::kWBytes + (kb * groups_per_block + gi) * (SK_ROWS * 2 * sizeof(T));
-      const uint32_t m0 = lds32(mt + r0 * 4), m1 = lds32(mt + r1 * 4);
-      const uint32_t xs = st + SM::kWBytes + a.meta_stage + (kb * MB * 8) * SK_XPITCH;
+  // linear k-block index q = tile * kblocks + kblk; block q starts at tile-major tile 2q.  The load
+  // cursor (tile, kblk) advances with q, so there is no integer division per block.
+  int ld_tile = (u_begin * SK_KBU) / a.kblocks, ld_kblk = (u_begin * SK_KBU) - ld_tile * a.kblocks;
+  const int gdiv = a.group / SK_KB;                       // groups >= 128: k blocks per group
+  auto load_block = [&](BlockRegs<NBITS>& b, int q) {
+    const uint8_t* blk = wbase + static_cast<int64_t>(q) * (2 * kTileB);
+    b.c0.load(blk, r0, t);
+    b.c1.load(blk, r1, t);
+    int kg;
+    if (a.group >= SK_KB) kg = gdiv == 1 ? ld_kblk : (gdiv >= a.kblocks ? 0 : ld_kblk / gdiv);
+    else kg = ld_kblk * (SK_KB / a.group) + (a.group == 32 ? t : (t >> 1));
+    const int n0 = ld_tile * SK_ROWS;
+    const int64_t row_base = static_cast<int64_t>(kg) * a.N;
+    b.m0 = ldg32_stream(mbase + (row_base + min(n0 + r0, a.N - 1)) * (2 * sizeof(T)));
+    b.m1 = ldg32_stream(mbase + (row_base + min(n0 + r1, a.N - 1)) * (2 * sizeof(T)));
+    if (++ld_kblk == a.kblocks) { ld_kblk = 0; ++ld_tile; }
+  };
+
+  // x slab of local blocks [c0, c0 + n): rows m < M only; 16-byte chunk c = 4t + j of a block is stored
+  // at offset 16t + 64j (conflict-free LDS.128 for the mma B fragments); S[m] = sum of the block.
+  auto stage_x = [&](int q0, int n) {
+    const T* xg = reinterpret_cast<const T*>(a.x);
+    const int total = n * mrows * 16;                      // 16-byte chunks
+    for (int c = tid; c < total; c += SK_THREADS) {
+      const int bl = c / (mrows * 16);
+      const int rem = c - bl * (mrows * 16);
+      const int m = rem >> 4, ch = rem & 15;
+      const int kblk = (q0 + bl) % a.kblocks;
+      const uint4 v = *reinterpret_cast<const uint4*>(xg + static_cast<int64_t>(m) * a.K + kblk * SK_KB + ch * 8);
+      *reinterpret_cast<uint4*>(xs_ptr + (bl * mrows + m) * SK_XPITCH + (ch >> 2) * 16 + (ch & 3) * 64) = v;
       if (POST) {
-        // Magic-form operand: the tensor core multiplies x by (MAGIC + q) straight from an AND/OR of
-        // the packed word; a second MMA with an all-ones A fragment yields S[m] = sum_k x[m][k] of
-        // the block, and the group's contribution is  scale * (acc_q - (MAGIC + zp) * S)  in fp32.
-        // (q - zp) is exact; the weight is never rounded to 16 bits (DESIGN.md "K3a numerics").
-        constexpr uint32_t kOne2 = kBf16 ? 0x3f803f80u : 0x3c003c00u;
-        const uint32_t ones[4] = {kOne2, kOne2, kOne2, kOne2};
-        float ag[MB][4], so[MB][4];
+        const float2 f0 = DT<T>::to_f2(v.x), f1 = DT<T>::to_f2(v.y), f2 = DT<T>::to_f2(v.z), f3 = DT<T>::to_f2(v.w);
+        float sm = ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
+        // the 16 chunks of one (block, m) sit in 16 consecutive threads
+        const uint32_t half_mask = (lane < 16) ? 0x0000ffffu : 0xffff0000u;   // total is a multiple of 16
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 xb[MB];
+        for (int d = 1; d < 16; d <<= 1) sm += __shfl_xor_sync(half_mask, sm, d);
+        if (ch == 0) xsum_s[bl * (MB * 8) + m] = sm;
+      }
+    }
+  };
+
+  float acc[MB][4];
 #pragma unroll
-          for (int mb = 0; mb < MB; ++mb) xb[mb] = lds128(xs + (mb * 8 + g) * SK_XPITCH + t * 16 + j * 64);
+  for (int mb = 0; mb < MB; ++mb) { acc[mb][0] = acc[mb][1] = acc[mb][2] = acc[mb][3] = 0.f; }
+
+  auto compute_block = [&](const BlockRegs<NBITS>& b, int bl) {
+    const uint32_t xs = xs_u32 + (bl * mrows) * SK_XPITCH;
+    if (POST) {
+      float ag[MB][4];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int p = 4 * j + 2 * h;
-            uint32_t af[4];
-            af[0] = c0.pair(p) | DQ<T>::kMagic;
-            af[1] = c1.pair(p) | DQ<T>::kMagic;
-            af[2] = c0.pair(p + 1) | DQ<T>::kMagic;
-            af[3] = c1.pair(p + 1) | DQ<T>::kMagic;
+      for (int j = 0; j < 4; ++j) {
+        uint4 xb[MB];
 #pragma unroll
-            for (int mb = 0; mb < MB; ++mb) {
-              uint32_t bf[2];
-              bf[0] = h == 0 ? xb[mb].x : xb[mb].z;
-              bf[1] = h == 0 ? xb[mb].y : xb[mb].w;
-              if (j == 0 && h == 0) {
-                mma_16816_zero(ag[mb], af, bf, kBf16);
-                mma_16816_zero(so[mb], ones, bf, kBf16);
-              } else {
-                mma_16816(ag[mb], af, bf, kBf16);
-                mma_16816(so[mb], ones, bf, kBf16);
-              }
-            }
+        for (int mb = 0; mb < MB; ++mb)
+          xb[mb] = (mb * 8 + g < mrows) ? lds128(xs + (mb * 8 + g) * SK_XPITCH + t * 16 + j * 64) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int p = 4 * j + 2 * h;            // pair index of k = 32t + 8j + 4h + {0,1}
+          uint32_t af[4];
+          af[0] = b.c0.pair(p) | DQ<T>::kMagic;
+          af[1] = b.c1.pair(p) | DQ<T>::kMagic;
+          af[2] = b.c0.pair(p + 1) | DQ<T>::kMagic;
+          af[3] = b.c1.pair(p + 1) | DQ<T>::kMagic;
+#pragma unroll
+          for (int mb = 0; mb < MB; ++mb) {
+            uint32_t bf[2];
+            bf[0] = h == 0 ? xb[mb].x : xb[mb].z;
+            bf[1] = h == 0 ? xb[mb].y : xb[mb].w;
+            if (j == 0 && h == 0) mma_16816_zero(ag[mb], af, bf, kBf16);
+            else mma_16816(ag[mb], af, bf, kBf16);
           }
         }
-        const float2 sz0 = DT<T>::to_f2(m0), sz1 = DT<T>::to_f2(m1);     // (scale, zero) of rows r0, r1
-        const float off0 = -(DQ<T>::kMagicF + (has_zp ? sz0.y : -a.qmin));
-        const float off1 = -(DQ<T>::kMagicF + (has_zp ? sz1.y : -a.qmin));
+      }
+      const float2 sz0 = DT<T>::to_f2(b.m0), sz1 = DT<T>::to_f2(b.m1);     // (scale, zero) of rows r0, r1
+      const float off0 = -(DQ<T>::kMagicF + (has_zp ? sz0.y : -a.qmin));
+      const float off1 = -(DQ<T>::kMagicF + (has_zp ? sz1.y : -a.qmin));
 #pragma unroll
-        for (int mb = 0; mb < MB; ++mb) {
-          acc[mb][0] = fmaf(sz0.x, fmaf(off0, so[mb][0], ag[mb][0]), acc[mb][0]);
-          acc[mb][1] = fmaf(sz0.x, fmaf(off0, so[mb][1], ag[mb][1]), acc[mb][1]);
-          acc[mb][2] = fmaf(sz1.x, fmaf(off1, so[mb][2], ag[mb][2]), acc[mb][2]);
-          acc[mb][3] = fmaf(sz1.x, fmaf(off1, so[mb][3], ag[mb][3]), acc[mb][3]);
-        }
-      } else {
-        const uint32_t s0b = __byte_perm(m0, 0, 0x1010), z0b = __byte_perm(m0, 0, 0x3232);
-        const uint32_t s1b = __byte_perm(m1, 0, 0x1010), z1b = __byte_perm(m1, 0, 0x3232);
-        const T2 s0 = *reinterpret_cast<const T2*>(&s0b), z0 = *reinterpret_cast<const T2*>(&z0b);
-        const T2 s1 = *reinterpret_cast<const T2*>(&s1b), z1 = *reinterpret_cast<const T2*>(&z1b);
+      for (int mb = 0; mb < MB; ++mb) {
+        const int m = mb * 8 + 2 * t;
+        const float s_a = (m < mrows) ? xsum_s[bl * (MB * 8) + m] : 0.f;
+        const float s_b = (m + 1 < mrows) ? xsum_s[bl * (MB * 8) + m + 1] : 0.f;
+        acc[mb][0] = fmaf(sz0.x, fmaf(off0, s_a, ag[mb][0]), acc[mb][0]);
+        acc[mb][1] = fmaf(sz0.x, fmaf(off0, s_b, ag[mb][1]), acc[mb][1]);
+        acc[mb][2] = fmaf(sz1.x, fmaf(off1, s_a, ag[mb][2]), acc[mb][2]);
+        acc[mb][3] = fmaf(sz1.x, fmaf(off1, s_b, ag[mb][3]), acc[mb][3]);
+      }
+    } else {
+      const uint32_t s0b = __byte_perm(b.m0, 0, 0x1010), z0b = __byte_perm(b.m0, 0, 0x3232);
+      const uint32_t s1b = __byte_perm(b.m1, 0, 0x1010), z1b = __byte_perm(b.m1, 0, 0x3232);
+      const T2 s0 = *reinterpret_cast<const T2*>(&s0b), z0 = *reinterpret_cast<const T2*>(&z0b);
+      const T2 s1 = *reinterpret_cast<const T2*>(&s1b), z1 = *reinterpret_cast<const T2*>(&z1b);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint4 xb[MB];
+      for (int j = 0; j < 4; ++j) {
+        uint4 xb[MB];
 #pragma unroll
-          for (int mb = 0; mb < MB; ++mb) xb[mb] = lds128(xs + (mb * 8 + g) * SK_XPITCH + t * 16 + j * 64);
+        for (int mb = 0; mb < MB; ++mb)
+          xb[mb] = (mb * 8 + g < mrows) ? lds128(xs + (mb * 8 + g) * SK_XPITCH + t * 16 + j * 64) : make_uint4(0, 0, 0, 0);
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const int p = 4 * j + 2 * h;            // pair index of k = 32t + 8j + 4h + {0,1}
-            uint32_t af[4];
-            af[0] = dq_pair<T, NBITS>(c0.pair(p), qmin2, z0, s0, has_zp);
-            af[1] = dq_pair<T, NBITS>(c1.pair(p), qmin2, z1, s1, has_zp);
-            af[2] = dq_pair<T, NBITS>(c0.pair(p + 1), qmin2, z0, s0, has_zp);
-            af[3] = dq_pair<T, NBITS>(c1.pair(p + 1), qmin2, z1, s1, has_zp);
+        for (int h = 0; h < 2; ++h) {
+          const int p = 4 * j + 2 * h;
+          uint32_t af[4];
+          af[0] = dq_pair<T, NBITS>(b.c0.pair(p), qmin2, z0, s0, has_zp);
+          af[1] = dq_pair<T, NBITS>(b.c1.pair(p), qmin2, z1, s1, has_zp);
+          af[2] = dq_pair<T, NBITS>(b.c0.pair(p + 1), qmin2, z0, s0, has_zp);
+          af[3] = dq_pair<T, NBITS>(b.c1.pair(p + 1), qmin2, z1, s1, has_zp);
 #pragma unroll
-            for (int mb = 0; mb < MB; ++mb) {
-              uint32_t bf[2];
-              bf[0] = h == 0 ? xb[mb].x : xb[mb].z;
-              bf[1] = h == 0 ? xb[mb].y : xb[mb].w;
-              mma_16816(acc[mb], af, bf, kBf16);
-            }
+          for (int mb = 0; mb < MB; ++mb) {
+            uint32_t bf[2];
+            bf[0] = h == 0 ? xb[mb].x : xb[mb].z;
+            bf[1] = h == 0 ? xb[mb].y : xb[mb].w;
+            mma_16816(acc[mb], af, bf, kBf16);
           }
         }
       }
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty_bar[stage]);
+  };
 
-    // ---- end of a tile segment?
-    const bool last_of_tile = (ku == a.units_per_tile - 1);
-    if (last_of_tile || u == u_end - 1) {
-      const int tile_u0 = tile * a.units_per_tile;
-      const int tile_u1 = tile_u0 + a.units_per_tile;           // exclusive
-      const int n0 = tile * SK_ROWS;
-      const bool whole = (seg_begin == tile_u0) && (u + 1 == tile_u1);
-      bool write_out = whole;
-      if (!whole) {
-        const int c_first = unit_owner(tile_u0, G, U);
-        const int c_last = unit_owner(tile_u1 - 1, G, U);
-        const int n_contrib = c_last - c_first + 1;
-        const int slot = cta - c_first;
-        float* wsp = a.ws_partials +
-                     (static_cast<int64_t>(tile) * a.max_slots + slot) * (SK_ROWS * MB * 8);
-        // fragment-order layout: [warp][mb][reg][lane]
+  // y <- fragment `v` of this warp's 16 rows of tile n0 (mma D layout), + bias, converted to T
+  auto write_fragment = [&](const float (&v)[MB][4], int n0) {
+    T* y = reinterpret_cast<T*>(a.y);
+    const T* bias = reinterpret_cast<const T*>(a.bias);
+#pragma unroll
+    for (int mb = 0; mb < MB; ++mb)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int n = n0 + ((r & 2) ? r1 : r0);
+        const int m = mb * 8 + 2 * t + (r & 1);
+        if (m < a.M && n < a.N) {
+          float o = v[mb][r];
+          if (bias) o += DT<T>::to_f(bias[n]);
+          y[static_cast<int64_t>(m) * a.N + n] = DT<T>::from_f(o);
+        }
+      }
+  };
+
+  // end of a tile segment [seg_begin, u]: write y or hand the fragment to the stream-K fix-up
+  auto finish_segment = [&](int u, int seg_begin) {
+    const int tile = u / a.units_per_tile;
+    const int tile_u0 = tile * a.units_per_tile;
+    const int tile_u1 = tile_u0 + a.units_per_tile;           // exclusive
+    const int n0 = tile * SK_ROWS;
+    if (seg_begin == tile_u0 && u + 1 == tile_u1) {
+      write_fragment(acc, n0);                                // this CTA owns the whole tile
+    } else {
+      const int c_first = unit_owner(tile_u0, G, U);
+      const int c_last = unit_owner(tile_u1 - 1, G, U);
+      const int n_contrib = c_last - c_first + 1;
+      // slot layout: [slot][warp][mb][reg][lane]; this warp only ever touches its own [warp] part
+      float* wst = a.ws_partials + static_cast<int64_t>(tile) * a.max_slots * FRAG + warp * (MB * 4 * 32);
+      float* wsp = wst + static_cast<int64_t>(cta - c_first) * FRAG;
+#pragma unroll
+      for (int mb = 0; mb < MB; ++mb)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) wsp[(mb * 4 + r) * 32 + lane] = acc[mb][r];
+      __threadfence();
+      __syncwarp();
+      int old = 0;
+      int* cnt = a.ws_counters + tile * 8 + warp;
+      if (lane == 0) old = atomicAdd(cnt, 1);
+      old = __shfl_sync(0xffffffffu, old, 0);
+      if (old == n_contrib - 1) {
+        // last contributor of this 16-row fragment: all slots are visible
+        __threadfence();
+        float v[MB][4];
 #pragma unroll
         for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
-          for (int r = 0; r < 4; ++r) wsp[((warp * MB + mb) * 4 + r) * 32 + lane] = acc[mb][r];
-        __threadfence();
-        asm volatile("bar.sync 1, %0;" :: "n"(SK_CONSUMERS) : "memory");
-        if (tid == 0) {
-          const int old = atomicAdd(&a.ws_counters[tile], 1);
-          s_flag = (old == n_contrib - 1) ? 1 : 0;
-          if (old == n_contrib - 1) a.ws_counters[tile] = 0;       // leave the workspace clean
-        }
-        asm volatile("bar.sync 1, %0;" :: "n"(SK_CONSUMERS) : "memory");
-        if (s_flag) {
-          __threadfence();
-          const float* wst = a.ws_partials + static_cast<int64_t>(tile) * a.max_slots * (SK_ROWS * MB * 8);
+          for (int r = 0; r < 4; ++r) v[mb][r] = 0.f;
+        for (int sl = 0; sl < n_contrib; ++sl) {
 #pragma unroll
           for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-              float s = 0.f;
-              for (int sl = 0; sl < n_contrib; ++sl)
-                s += __ldcg(wst + static_cast<int64_t>(sl) * (SK_ROWS * MB * 8) +
-                            ((warp * MB + mb) * 4 + r) * 32 + lane);
-              acc[mb][r] = s;
-            }
-          write_out = true;
+            for (int r = 0; r < 4; ++r)
+              v[mb][r] += __ldcg(wst + static_cast<int64_t>(sl) * FRAG + (mb * 4 + r) * 32 + lane);
         }
-        asm volatile("bar.sync 1, %0;" :: "n"(SK_CONSUMERS) : "memory");   // s_flag reusable
+        write_fragment(v, n0);
+        if (lane == 0) *cnt = 0;                              // leave the workspace clean
       }
-      if (write_out) {
-        T* y = reinterpret_cast<T*>(a.y);
-        const T* bias = reinterpret_cast<const T*>(a.bias);
+    }
 #pragma unroll
-        for (int mb = 0; mb < MB; ++mb)
+    for (int mb = 0; mb < MB; ++mb) { acc[mb][0] = acc[mb][1] = acc[mb][2] = acc[mb][3] = 0.f; }
+  };
+
+  const int q_begin = u_begin * SK_KBU, q_end = u_end * SK_KBU;
+  BlockRegs<NBITS> ring[SK_DEPTH];
 #pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            const int n = n0 + ((r & 2) ? r1 : r0);
-            const int m = mb * 8 + 2 * t + (r & 1);
-            if (m < a.M && n < a.N) {
-              float v = acc[mb][r];
-              if (bias) v += DT<T>::to_f(bias[n]);
-              y[static_cast<int64_t>(m) * a.N + n] = DT<T>::from_f(v);
+  for (int d = 0; d < SK_DEPTH; ++d)
+    if (q_begin + d < q_end) load_block(ring[d], q_begin + d);
+
+  int seg_begin = u_begin;                      // first unit of the current tile segment
+  for (int qc = q_begin; qc < q_end; qc += SK_CHUNK) {
+    const int nblk = min(SK_CHUNK, q_end - qc);
+    __syncthreads();                            // everyone is done with the previous slab
+    stage_x(qc, nblk);
+    __syncthreads();
+    for (int b0 = 0; b0 < nblk; b0 += SK_DEPTH) {
+#pragma unroll
+      for (int d = 0; d < SK_DEPTH; ++d) {
+        const int q = qc + b0 + d;
+        if (q < q_end) {
+          compute_block(ring[d], b0 + d);
+          if (q + SK_DEPTH < q_end) load_block(ring[d], q + SK_DEPTH);
+          if (d & 1) {                          // a unit = 2 k blocks: unit boundary after the odd block
+            const int u = q / SK_KBU;
+            const int ku = u % a.units_per_tile;
+            if (ku == a.units_per_tile - 1 || u == u_end - 1) {
+              finish_segment(u, seg_begin);
+              seg_begin = u + 1;
             }
           }
+        }
       }
-#pragma unroll
-      for (int mb = 0; mb < MB; ++mb) { acc[mb][0] = acc[mb][1] = acc[mb][2] = acc[mb][3] = 0.f; }
-      seg_begin = u + 1;
     }
   }
 }
@@ -460,10 +445,8 @@ k3_skinny(const SkinnyArgs a) {
 // ---------------------------------------------------------------- host
 template <typename T, int NBITS, int MB, bool POST>
 static int launch_skinny(SkinnyArgs a, cudaStream_t st) {
-  using SM = SkinnySmem<NBITS, MB>;
   auto kern = k3_skinny<T, NBITS, MB, POST>;
-  const int smem = SM::total(a.meta_stage);
-  a.stage_bytes = SM::stage(a.meta_stage);
+  const int smem = skinny_smem_bytes(a.m_rows, MB);
   static std::mutex mu;           // one per instantiation
   static int max_set = 0;
   static std::unordered_map<int, int> occ_cache;
@@ -483,9 +466,8 @@ static int launch_skinny(SkinnyArgs a, cudaStream_t st) {
     }
   }
   Q100_REQUIRE(occ >= 1, Q100_ECUDA, "k3_skinny does not fit on an SM (%d bytes smem)", smem);
-  if (occ > 2) occ = 2;
   // persistent grid: every CTA resident at once, units split evenly (stream-K)
-  int grid = sm_count() * occ;
+  int grid = sm_count() * (occ > SK_MAX_CTAS ? SK_MAX_CTAS : occ);
   if (grid > a.total_units) grid = a.total_units;
   Q100_REQUIRE(static_cast<int64_t>(a.units_per_tile) * grid / a.total_units + 2 <= a.max_slots, Q100_EWORKSPACE,
                "internal: slot bound");
@@ -518,20 +500,18 @@ static int launch_skinny_bits(int n_bits, const SkinnyArgs& a, cudaStream_t st) 
 }
 
 struct SkinnyPlan {
-  int kbu, units_per_tile, n_tiles, total_units, grid, max_slots;
+  int units_per_tile, n_tiles, total_units, max_slots;
 };
 
 static SkinnyPlan plan_skinny(int64_t N, int64_t K) {
   SkinnyPlan p;
   const int kblocks = static_cast<int>(K / SK_KB);
-  p.kbu = (kblocks % SK_KBU == 0) ? SK_KBU : 1;
-  p.units_per_tile = kblocks / p.kbu;
+  p.units_per_tile = kblocks / SK_KBU;
   p.n_tiles = static_cast<int>((N + SK_ROWS - 1) / SK_ROWS);
   p.total_units = p.n_tiles * p.units_per_tile;
-  int grid = sm_count() * 2;                  // two CTAs per SM fit in shared memory for MB <= 2
+  int grid = sm_count() * SK_MAX_CTAS;        // upper bound of the persistent grid
   if (grid > p.total_units) grid = p.total_units;
   if (grid < 1) grid = 1;
-  p.grid = grid;
   // a tile of `units_per_tile` units can be touched by at most this many CTAs
   p.max_slots = static_cast<int>((static_cast<int64_t>(p.units_per_tile) * grid + p.total_units - 1) /
                                  p.total_units) + 2;
@@ -542,14 +522,14 @@ size_t skinny_workspace_bytes(int64_t M, int64_t N, int64_t K) {
   const SkinnyPlan p = plan_skinny(N, K);
   const int mb = M <= 8 ? 1 : M <= 16 ? 2 : 4;
   const size_t partials = static_cast<size_t>(p.n_tiles) * p.max_slots * SK_ROWS * mb * 8 * sizeof(float);
-  return partials + static_cast<size_t>(p.n_tiles) * sizeof(int) + 256;
+  return partials + SK_COUNTER_BYTES;
 }
 
 int gemm_skinny(const void* x, const void* packed, const void* meta, const void* bias, void* y,
                 int64_t M, int64_t N, int64_t K, int group, int n_bits, int disable_zp, int dtype,
                 void* workspace, size_t workspace_bytes, int exact_weights, cudaStream_t st) {
   Q100_REQUIRE(M >= 1 && M <= 32, Q100_EINVAL, "skinny GEMM handles 1 <= M <= 32 (got %lld)", (long long)M);
-  Q100_REQUIRE(K % SK_KB == 0, Q100_EUNSUPPORTED, "K=%lld must be a multiple of 128", (long long)K);
+  Q100_REQUIRE(K % (SK_KB * SK_KBU) == 0, Q100_EUNSUPPORTED, "K=%lld must be a multiple of 256", (long long)K);
   Q100_REQUIRE(N % 8 == 0, Q100_EUNSUPPORTED, "N=%lld must be a multiple of 8", (long long)N);
   const int g = group == 0 ? static_cast<int>(K) : group;
   Q100_REQUIRE(g == 32 || g == 64 || g % 128 == 0, Q100_EUNSUPPORTED,
@@ -562,21 +542,20 @@ int gemm_skinny(const void* x, const void* packed, const void* meta, const void*
 
   SkinnyArgs a{};
   a.x = x; a.packed = packed; a.meta = meta; a.bias = bias; a.y = y;
-  const int mb = M <= 8 ? 1 : M <= 16 ? 2 : 4;
-  const size_t partials = static_cast<size_t>(p.n_tiles) * p.max_slots * SK_ROWS * mb * 8 * sizeof(float);
   a.ws_counters = reinterpret_cast<int*>(workspace);
-  a.ws_partials = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) +
-                                           ((static_cast<size_t>(p.n_tiles) * sizeof(int) + 255) & ~size_t(255)));
-  (void)partials;
+  // counters live in a fixed-size prefix so that partials of one launch can never land on what a
+  // later launch (different N) uses as counters: the prefix is the only part that must stay zero
+  Q100_REQUIRE(static_cast<size_t>(p.n_tiles) * 8 * sizeof(int) <= SK_COUNTER_BYTES, Q100_EUNSUPPORTED,
+               "N=%lld too large for the stream-K counter area", (long long)N);
+  a.ws_partials = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + SK_COUNTER_BYTES);
   a.M = static_cast<int>(M); a.N = static_cast<int>(N); a.K = static_cast<int>(K); a.group = g;
   a.kblocks = static_cast<int>(K / SK_KB);
-  a.kbu = p.kbu; a.units_per_tile = p.units_per_tile; a.n_tiles = p.n_tiles;
+  a.units_per_tile = p.units_per_tile; a.n_tiles = p.n_tiles;
   a.total_units = p.total_units; a.max_slots = p.max_slots;
   a.has_zp = disable_zp ? 0 : 1;
   a.qmin = disable_zp ? -static_cast<float>(1 << (n_bits - 1)) : 0.0f;
-  const int gpb = g >= SK_KB ? 1 : SK_KB / g;
   a.post = (g % SK_KB == 0 && !exact_weights) ? 1 : 0;
-  a.meta_stage = ((p.kbu * gpb * SK_ROWS * 2 * 2) + 127) & ~127;
+  a.m_rows = static_cast<int>(M);
   if (dtype == Q100_F16) return launch_skinny_bits<__half>(n_bits, a, st);
   return launch_skinny_bits<__nv_bfloat16>(n_bits, a, st);
 }

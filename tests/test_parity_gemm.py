@@ -71,7 +71,7 @@ def test_skinny_vs_oracle(dtype, n_bits, M):
 
 
 @pytest.mark.parametrize("dtype", ["f16", "bf16"])
-@pytest.mark.parametrize("N,K,group", [(128, 128, 128), (136, 384, 128), (1024, 4096, 128), (4096, 4096, 128),
+@pytest.mark.parametrize("N,K,group", [(128, 256, 128), (136, 512, 128), (1024, 4096, 128), (4096, 4096, 128),
                                        (512, 14336, 128), (256, 512, 64), (256, 512, 32), (256, 1024, 256),
                                        (256, 1024, 0), (6144, 4096, 128)])
 def test_skinny_shapes(dtype, N, K, group):

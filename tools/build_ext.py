@@ -26,7 +26,7 @@ OUT = os.path.join(PKG, "q100", "libq100.so")
 OBJ = os.path.join(ROOT, "build", "obj")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
+COMMON = os.environ.get("Q100_NVCC_FLAGS", "").split() + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
           "--expt-relaxed-constexpr", "-I", os.path.join(ROOT, "include")]
 # per-file extras: the quantize kernels must not contract mul+add (bit-exact per-op rounding)
 EXTRA = {"q100_quant.cu": ["-fmad=false"]}
