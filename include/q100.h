@@ -58,6 +58,11 @@ enum q100_status {
 #define Q100_GEMM_EXACT_WEIGHTS 0x4 /* decode kernel: rebuild the 16-bit fake-quantised weight
                                       r(r(q-zp)*scale) bit-exactly before the MMA (slower); default
                                       keeps (q-zp) exact and applies the scale in fp32 per group   */
+#define Q100_GEMM_PDL          0x8 /* launch with programmatic stream serialization: the kernel starts
+                                      streaming its (static) weights while the previous kernel of the
+                                      stream drains, and waits (griddepcontrol.wait) before it touches
+                                      x, y or the workspace.  Only valid when `packed`/`meta` were not
+                                      written by the immediately preceding q100 GEMM launch.        */
 
 const char* q100_last_error(void);
 int q100_abi_version(void);

@@ -12,7 +12,7 @@ namespace q100 {
 
 int gemm_skinny(const void* x, const void* packed, const void* meta, const void* bias, void* y,
                 int64_t M, int64_t N, int64_t K, int group, int n_bits, int disable_zp, int dtype,
-                void* workspace, size_t workspace_bytes, int exact_weights, cudaStream_t st);
+                void* workspace, size_t workspace_bytes, int exact_weights, int pdl, cudaStream_t st);
 size_t skinny_workspace_bytes(int64_t M, int64_t N, int64_t K);
 
 int gemm_tc(const void* x, const void* packed, const void* meta, const void* bias, void* y,
@@ -85,7 +85,7 @@ extern "C" int q100_gemm_wna16(const void* x, const void* packed, const void* me
   int rc = ensure_device();
   if (rc != Q100_OK) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const bool skinny_ok = (K % 256 == 0) && (N % 8 == 0);
+  const bool skinny_ok = (K % 128 == 0) && (N % 8 == 0);
   const bool tc_ok = gemm_tc_supported(M, N, K, group, n_bits);
   const bool want_tc = (flags & Q100_GEMM_FORCE_TC) ||
                        (!(flags & Q100_GEMM_FORCE_SKINNY) && tc_ok && (M > 32 || !skinny_ok));
@@ -99,11 +99,19 @@ extern "C" int q100_gemm_wna16(const void* x, const void* packed, const void* me
     const int64_t mc = (M - m0) < 32 ? (M - m0) : 32;
     rc = gemm_skinny(reinterpret_cast<const uint8_t*>(x) + m0 * K * esz, packed, meta, bias,
                      reinterpret_cast<uint8_t*>(y) + m0 * N * esz, mc, N, K, group, n_bits, disable_zp,
-                     dtype, workspace, workspace_bytes, (flags & Q100_GEMM_EXACT_WEIGHTS) ? 1 : 0, st);
+                     dtype, workspace, workspace_bytes, (flags & Q100_GEMM_EXACT_WEIGHTS) ? 1 : 0,
+                     (flags & Q100_GEMM_PDL) ? 1 : 0, st);
     if (rc != Q100_OK) return rc;
   }
   return Q100_OK;
 }
+
+#ifdef SK_TIMING
+namespace q100 { int skinny_timing(long long* out, int n); }
+extern "C" __attribute__((visibility("default"))) int q100_debug_skinny_timing(long long* out, int n) {
+  return q100::skinny_timing(out, n);
+}
+#endif
 
 extern "C" int q100_debug_gemm_dense_tc(const void* x, const void* w, void* y, int64_t M, int64_t N, int64_t K,
                                         int dtype, void* stream) {

@@ -3,29 +3,32 @@
 //   y[M, N] = x[M, K] . dequant(W)[N, K]^T (+ bias)        quant/int_linear.py:62
 //
 // HBM-bound: the packed weights (n_bits/8 B per weight) are the only large stream and are read
-// exactly once.  Structure (persistent CTAs of 8 warps):
-//   * every consumer warp owns 16 output rows of the CTA's 128-row tile and streams ITS OWN
-//     slice of the packed codes straight from global memory into registers with 128-bit
-//     ld.global.nc loads, four 128-k blocks ahead (software-pipelined register ring).  The
-//     tile-major packed layout makes each warp-wide load two fully used 256-byte segments and
-//     the CTA's whole stream one linear run of HBM.  (A TMA/shared-memory ring for the codes was
-//     measured first: it topped out at 3.9 TB/s with no compute at all -- profiles/ r01 notes --
-//     because the per-SM bulk-copy path cannot keep enough bytes in flight against HBM latency;
-//     registers can.)
-//   * x is tiny: the CTA stages the slab of x it needs (up to 16 k-blocks at a time) into shared
-//     memory itself, in a bank-conflict-free permuted order, together with the per-block sums
-//     S[m] = sum_k x[m][k]; no producer warp, no mbarrier ring, one __syncthreads per 2048 k;
-//   * codes are used in "magic form": (MAGIC + q) is built with one AND/OR per pair and fed to
-//     mma.sync.m16n8k16 as the A operand (x^T is B); the block's contribution is
-//     scale * (acc_q - (MAGIC + zp) * S) in fp32.  With Q100_GEMM_EXACT_WEIGHTS (or group < 128)
-//     the 16-bit fake-quantised weight r(r(q-zp)*scale) is rebuilt bit-exactly instead.
+// exactly once.  Structure (persistent CTAs, 3 per SM, 8 consumer warps + 1 producer warp):
+//   * the producer warp streams the CTA's contiguous run of [128 rows x 128 k] code blocks (8 KB
+//     at W4; the tile-major packed layout makes the run linear in HBM) plus the blocks'
+//     (scale, zero) side band into a deep shared-memory ring with cp.async.bulk (TMA) and mbarrier
+//     full/empty pairs: ~170 KB are in flight per SM from the first cycle, independent of how fast
+//     the math runs (tools/micro/stream_bench3.cu: this ring alone sustains 6.37 TB/s = 97 % of the
+//     measured copy bandwidth; a register ring tops out near 5.2 TB/s).  The stream does not
+//     depend on the previous kernel, so with programmatic dependent launch (Q100_GEMM_PDL) the
+//     ring fills while the previous kernel drains;
+//   * consumer warp w owns 16 output rows of the tile: it pulls its slice of a landed block into
+//     registers (conflict-free LDS.128: the two 64-k halves are 64 bytes apart modulo 128), frees
+//     the slot, and feeds the codes in "magic form" -- (MAGIC + q) built with one LOP3 per pair --
+//     to mma.sync.m16n8k16 as the A operand (x^T is B); the block's contribution is
+//     scale * (acc_q - (MAGIC + zp) * S) in fp32, S = sum of x over the block.  fp16/W4 uses the
+//     word's nibbles in place ((w & 0x00f000f0) | MAGIC = 1024 + 16 q goes to a second accumulator
+//     that is scaled by 1/16), five ALU ops per eight codes.  With Q100_GEMM_EXACT_WEIGHTS (or
+//     group < 128) the 16-bit fake-quantised weight r(r(q-zp)*scale) is rebuilt bit-exactly.
 //     tcgen05 is deliberately not used here: at M <= 32 the operand would have to be written
 //     back to shared memory (2 B/weight) and that traffic alone exceeds the time budget of the
-//     0.5 B/weight HBM stream (DESIGN.md "K3a").
-//   * work is split stream-K style over 148*k CTAs in units of [128 rows x 256 k]; a tile shared
-//     by several CTAs is finished warp-asynchronously: each warp stores its fp32 fragment to its
-//     CTA's slot, fences, bumps the counter of ITS 16-row fragment, and the last arriver sums that
-//     fragment's slots in slot order (deterministic) and writes y.  No CTA-wide barrier there.
+//     0.5 B/weight HBM stream (DESIGN.md "K3a");
+//   * x is tiny: the consumers stage the slab of x they need into shared memory themselves, in a
+//     bank-conflict-free permuted order, together with the per-block sums S[m];
+//   * work is split stream-K style over 148*3 CTAs in units of one block; a tile shared by several
+//     CTAs is finished warp-asynchronously: each warp stores its fp32 fragment to its CTA's slot,
+//     fences, bumps the counter of ITS 16-row fragment, and the last arriver sums that fragment's
+//     slots in slot order (deterministic) and writes y.  No CTA-wide barrier there.
 //
 // Lane <-> k mapping: inside a 128-k block lane t (= lane & 3) owns k in [32t, 32t+32) for
 // both operands, i.e. the mma "slot" (s, 2t+{0,1,8,9}) of k16-step s carries
@@ -41,12 +44,14 @@ namespace q100 {
 
 constexpr int SK_ROWS = 128;       // output rows per tile (8 warps x 16)
 constexpr int SK_KB = 128;         // k per block
-constexpr int SK_KBU = 2;          // k blocks per stream-K unit
-constexpr int SK_DEPTH = 2;        // k blocks of packed codes in flight per lane (register ring); occupancy,
-                                   // not per-warp depth, is what fills HBM (profiles/r01 stream microbenchmarks)
-constexpr int SK_MAX_CTAS = 4;     // resident CTAs per SM the launch bounds aim for (MB = 1)
-constexpr int SK_CHUNK = 16;       // k blocks of x staged in shared memory at a time (multiple of SK_DEPTH)
-constexpr int SK_THREADS = 256;
+constexpr int SK_CWARPS = 8;       // consumer warps
+constexpr int SK_THREADS = (SK_CWARPS + 1) * 32;
+constexpr int SK_CTHREADS = SK_CWARPS * 32;
+constexpr int SK_MAX_STAGES = 16;
+constexpr int SK_CHUNK_MAX = 128;   // k blocks of x staged in shared memory at a time
+#ifndef SK_OCC
+#define SK_OCC 3                   // resident CTAs per SM the kernel is sized for (2 for M > 16)
+#endif
 constexpr size_t SK_COUNTER_BYTES = 1 << 18;   // workspace prefix: per-fragment arrival counters (N <= 1 M rows)
 constexpr int SK_XPITCH = 320;     // bytes per (m, 128-k) x row in smem: 256 + 64 pad (conflict-free LDS.128)
 
@@ -59,25 +64,33 @@ struct SkinnyArgs {
   float* ws_partials;     // workspace: fp32 partial tiles
   int* ws_counters;       // workspace: one arrival counter per 16-row fragment (zero between launches)
   int M, N, K, group;
-  int kblocks;            // K / 128
-  int units_per_tile;     // kblocks / 2
+  int kblocks;            // K / 128 = stream-K units per tile
   int n_tiles;
-  int total_units;
+  int total_units;        // n_tiles * kblocks
   int max_slots;
   int has_zp;
   float qmin;
   int post;               // 1: magic-form operand + fp32 group scaling (group % 128 == 0)
   int m_rows;             // rows of x kept in shared memory (= M)
+  int chunk;              // k blocks of x staged per round
+  int stages;             // ring depth
+  int nsub;               // (scale, zero) rows per block: 128 / group for group < 128, else 1
+  int pdl;                // launch with programmatic stream serialization
 };
 
+// One [128 rows x 64 k] tile of codes; a block = two tiles.  In shared memory the second tile is placed
+// kPad bytes past a multiple of 128 so that the eight lanes of an LDS phase (two rows x four k-quarters)
+// hit eight different 16-byte bank groups.
 template <int NBITS> struct WGeom {
-  static constexpr int kTileBytes = NBITS == 3 ? 128 * 24 : 128 * 8 * NBITS;   // one [128 x 64] tile
+  static constexpr int kTileBytes = NBITS == 3 ? 128 * 24 : 128 * 8 * NBITS;
+  static constexpr int kPad = NBITS == 8 ? 16 : 64;
+  static constexpr int kTileStride = kTileBytes + kPad;
+  static constexpr int kCodeBytes = 2 * kTileStride;       // smem footprint of a block's codes (16-B multiple)
 };
-
-// shared memory: x slab [SK_CHUNK blocks][m_rows][SK_XPITCH] + block sums [SK_CHUNK][MB*8] fp32
-__host__ __device__ constexpr int skinny_smem_bytes(int m_rows, int mb) {
-  return SK_CHUNK * m_rows * SK_XPITCH + SK_CHUNK * mb * 8 * 4 + 128;
+template <int NBITS> __host__ __device__ constexpr int stage_bytes(int nsub) {
+  return WGeom<NBITS>::kCodeBytes + nsub * 512;
 }
+__host__ __device__ constexpr int slab_bytes(int m_rows, int chunk) { return (chunk * m_rows + 1) * SK_XPITCH; }
 
 // ---------------------------------------------------------------- dequant helpers
 template <typename T> struct DQ;
@@ -121,66 +134,113 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
   return v;
 }
-__device__ __forceinline__ uint2 ldg64_stream(const void* p) {
-  uint2 r;
-  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
-  return r;
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
 }
-__device__ __forceinline__ uint32_t ldg32_stream(const void* p) {
-  uint32_t r;
-  asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
-  return r;
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float2 lds64f(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
 }
 
-// A lane's 32 codes (k in [32t, 32t+32) of one row's 128-k block) as 16 pairs, loaded from the
-// two consecutive [128 x 64] tiles of the block: lane t reads k-tile (t >> 1), half (t & 1).
+// (w & MASK) | orv as ONE LOP3: the mask is the immediate, the magic constant stays in a register
+// (left to itself the compiler emits two immediate-form LOP3s)
+template <uint32_t MASK>
+__device__ __forceinline__ uint32_t lop_and_or(uint32_t w, uint32_t orv) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(w), "n"(MASK), "r"(orv));
+  return d;
+}
+// opaque register copy of a constant (keeps ptxas from folding it back into an immediate)
+__device__ __forceinline__ uint32_t reg_const(uint32_t v) {
+  uint32_t d;
+  asm volatile("mov.b32 %0, %1;" : "=r"(d) : "r"(v));
+  return d;
+}
+
+// A lane's 32 codes (k in [32t, 32t+32) of one row's 128-k block) as 16 pairs, read from the two
+// [128 x 64] tiles of a landed block: lane t reads k-tile (t >> 1), half (t & 1).
+//   lane_off(row, t): byte offset of the lane's codes of `row` inside the block's smem image
+//   kRow8:            byte distance to the lane's second row (row + 8)
 template <int NBITS> struct LaneCodes;
 template <> struct LaneCodes<4> {
   uint4 w;
-  __device__ __forceinline__ void load(const uint8_t* blk, int row, int t) {
-    w = ldg_stream(blk + (t >> 1) * WGeom<4>::kTileBytes + row * 32 + (t & 1) * 16);
+  __device__ __forceinline__ uint32_t word(int i) const { return i == 0 ? w.x : i == 1 ? w.y : i == 2 ? w.z : w.w; }
+  __device__ static __forceinline__ int lane_off(int row, int t) {
+    return (t >> 1) * WGeom<4>::kTileStride + row * 32 + (t & 1) * 16;
   }
+  static constexpr int kRow8 = 8 * 32;
+  __device__ __forceinline__ void load(uint32_t p, uint32_t) { w = lds128(p); }
   __device__ __forceinline__ uint32_t pair(int i) const {
-    const uint32_t x = (i >> 2) == 0 ? w.x : (i >> 2) == 1 ? w.y : (i >> 2) == 2 ? w.z : w.w;
-    return (x >> (4 * (i & 3))) & 0x000f000fu;
+    return (word(i >> 2) >> (4 * (i & 3))) & 0x000f000fu;
+  }
+  __device__ __forceinline__ uint32_t mpair(int i, uint32_t magic) const {     // pair(i) | magic
+    return lop_and_or<0x000f000fu>(word(i >> 2) >> (4 * (i & 3)), magic);
   }
 };
 template <> struct LaneCodes<2> {
   uint2 w;
-  __device__ __forceinline__ void load(const uint8_t* blk, int row, int t) {
-    w = ldg64_stream(blk + (t >> 1) * WGeom<2>::kTileBytes + row * 16 + (t & 1) * 8);
+  __device__ static __forceinline__ int lane_off(int row, int t) {
+    return (t >> 1) * WGeom<2>::kTileStride + row * 16 + (t & 1) * 8;
   }
+  static constexpr int kRow8 = 8 * 16;
+  __device__ __forceinline__ void load(uint32_t p, uint32_t) { w = lds64(p); }
   __device__ __forceinline__ uint32_t pair(int i) const {
     const uint32_t x = (i >> 3) == 0 ? w.x : w.y;
     return (x >> (2 * (i & 7))) & 0x00030003u;
   }
+  __device__ __forceinline__ uint32_t mpair(int i, uint32_t magic) const {
+    const uint32_t x = (i >> 3) == 0 ? w.x : w.y;
+    return lop_and_or<0x00030003u>(x >> (2 * (i & 7)), magic);
+  }
 };
 template <> struct LaneCodes<8> {
   uint4 w0, w1;
-  __device__ __forceinline__ void load(const uint8_t* blk, int row, int t) {
-    const uint8_t* p = blk + (t >> 1) * WGeom<8>::kTileBytes + row * 64 + (t & 1) * 32;
-    w0 = ldg_stream(p);
-    w1 = ldg_stream(p + 16);
+  __device__ static __forceinline__ int lane_off(int row, int t) {
+    return (t >> 1) * WGeom<8>::kTileStride + row * 64 + (t & 1) * 32;
   }
-  __device__ __forceinline__ uint32_t pair(int i) const {
-    const int wi = i >> 1;
-    const uint32_t x = wi == 0 ? w0.x : wi == 1 ? w0.y : wi == 2 ? w0.z : wi == 3 ? w0.w
-                     : wi == 4 ? w1.x : wi == 5 ? w1.y : wi == 6 ? w1.z : w1.w;
-    return (x >> (8 * (i & 1))) & 0x00ff00ffu;
+  static constexpr int kRow8 = 8 * 64;
+  __device__ __forceinline__ void load(uint32_t p, uint32_t) {
+    w0 = lds128(p);
+    w1 = lds128(p + 16);
+  }
+  __device__ __forceinline__ uint32_t wsel(int wi) const {
+    return wi == 0 ? w0.x : wi == 1 ? w0.y : wi == 2 ? w0.z : wi == 3 ? w0.w
+         : wi == 4 ? w1.x : wi == 5 ? w1.y : wi == 6 ? w1.z : w1.w;
+  }
+  __device__ __forceinline__ uint32_t pair(int i) const { return (wsel(i >> 1) >> (8 * (i & 1))) & 0x00ff00ffu; }
+  __device__ __forceinline__ uint32_t mpair(int i, uint32_t magic) const {
+    return __byte_perm(wsel(i >> 1), magic, (i & 1) ? 0x7371 : 0x7270);      // [b, magic_hi, b', magic_hi]: one PRMT
   }
 };
 template <> struct LaneCodes<3> {
   uint2 lo;
   uint32_t hi;
-  __device__ __forceinline__ void load(const uint8_t* blk, int row, int t) {
-    const uint8_t* p = blk + (t >> 1) * WGeom<3>::kTileBytes;
-    lo = ldg64_stream(p + row * 16 + (t & 1) * 8);                  // 2-bit plane: 128 rows x 16 B
-    hi = ldg32_stream(p + 128 * 16 + row * 8 + (t & 1) * 4);        // 1-bit plane: 128 rows x 8 B
+  // 2-bit plane: 128 rows x 16 B at the tile start; 1-bit plane: 128 rows x 8 B right after it
+  __device__ static __forceinline__ int lane_off(int row, int t) {
+    return (t >> 1) * WGeom<3>::kTileStride + row * 16 + (t & 1) * 8;
+  }
+  __device__ static __forceinline__ int lane_off_hi(int row, int t) {
+    return (t >> 1) * WGeom<3>::kTileStride + 128 * 16 + row * 8 + (t & 1) * 4;
+  }
+  static constexpr int kRow8 = 8 * 16;
+  static constexpr int kRow8Hi = 8 * 8;
+  __device__ __forceinline__ void load(uint32_t p_lo, uint32_t p_hi) {
+    lo = lds64(p_lo);
+    hi = lds32(p_hi);
   }
   __device__ __forceinline__ uint32_t pair(int i) const {
     const uint32_t x = (i >> 3) == 0 ? lo.x : lo.y;
     return ((x >> (2 * (i & 7))) & 0x00030003u) | (((hi >> i) & 0x00010001u) << 2);
   }
+  __device__ __forceinline__ uint32_t mpair(int i, uint32_t magic) const { return pair(i) | magic; }
 };
 
 // everything a lane needs for one 128-k block: codes of its two rows + their (scale, zero) pairs
@@ -195,122 +255,340 @@ __device__ __forceinline__ int unit_owner(int u, int G, int U) {
   return static_cast<int>((static_cast<int64_t>(u + 1) * G + U - 1) / U) - 1;
 }
 
+__device__ __forceinline__ void bar_sync_consumers() {
+  asm volatile("bar.sync 1, %0;" :: "n"(SK_CTHREADS) : "memory");
+}
+
+// POST kernels always contract in fp16 (bf16 activations are converted exactly, see stage_x), so the
+// W4 nibbles can be used in place for both dtypes, see file header
+template <int NBITS> struct UseLoHi {
+  static constexpr bool value = (NBITS == 4);
+};
+// w >> 8 on the FMA pipe (IMAD.HI): the ALU pipe (LOP3/SHF, 64 lanes/clk/SM) is the scarce unit here
+__device__ __forceinline__ uint32_t shr8_fma(uint32_t w) {
+  uint32_t d;
+  asm("mul.hi.u32 %0, %1, 16777216;" : "=r"(d) : "r"(w));
+  return d;
+}
+// mbarrier wait without bookkeeping instructions in the retry path (try_wait suspends in hardware)
+__device__ __forceinline__ void mbar_arrive_u32(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_u32(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d_hint_u32(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar,
+                                                      uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+      :: "r"(dst), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar), "l"(policy)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait_tight_u32(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t}\n"
+      :: "r"(bar), "r"(parity) : "memory");
+}
+
+#ifdef SK_TIMING
+// debug build: per-CTA cycle breakdown (consumer warp 0 / producer), read back by q100_debug_skinny_timing
+__device__ long long g_sk_t[2048][8];
+#define SK_T(var) const long long var = clock64()
+#else
+#define SK_T(var)
+#endif
+
 // ---------------------------------------------------------------- kernel
 template <typename T, int NBITS, int MB, bool POST>
-__global__ void __launch_bounds__(SK_THREADS, MB == 1 ? 4 : MB == 2 ? 3 : 2)
+__global__ void __launch_bounds__(SK_THREADS, MB <= 2 ? SK_OCC : 2)
 k3_skinny(const SkinnyArgs a) {
   using T2 = typename DQ<T>::T2;
-  constexpr bool kBf16 = DT<T>::kCode == Q100_BF16;
+  constexpr bool kBf16 = !POST && DT<T>::kCode == Q100_BF16;    // MMA operand type (POST: always fp16)
+  constexpr bool kConvX = POST && DT<T>::kCode == Q100_BF16;    // bf16 activations -> scaled fp16 at staging
+  constexpr bool LOHI = POST && UseLoHi<NBITS>::value;
+  using DQM = DQ<__half>;                                        // magic constants of the POST path
   constexpr int kTileB = WGeom<NBITS>::kTileBytes;
+  constexpr int kBlkB = 2 * kTileB;                   // one [128 rows x 128 k] block of codes in HBM
   constexpr int FRAG = SK_ROWS * MB * 8;              // floats per partial tile
 
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  const uint32_t xs_u32 = (smem_u32(smem_raw) + 127u) & ~127u;
-  uint8_t* xs_ptr = smem_raw + (xs_u32 - smem_u32(smem_raw));
-  const int mrows = a.m_rows;
-  float* xsum_s = reinterpret_cast<float*>(xs_ptr + SK_CHUNK * mrows * SK_XPITCH);     // [SK_CHUNK][MB*8]
+  __shared__ uint64_t full_bar[SK_MAX_STAGES], empty_bar[SK_MAX_STAGES];
+  const uint32_t ring_u32 = (smem_u32(smem_raw) + 127u) & ~127u;
+  uint8_t* ring_ptr = smem_raw + (ring_u32 - smem_u32(smem_raw));
+  const int stage_pitch = (stage_bytes<NBITS>(a.nsub) + 127) & ~127;
+  const int stages = a.stages;
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int G = gridDim.x, U = a.total_units;
   const int cta = blockIdx.x;
-  const int u_begin = static_cast<int>(static_cast<int64_t>(cta) * U / G);
-  const int u_end = static_cast<int>(static_cast<int64_t>(cta + 1) * U / G);
+  const int q_begin = static_cast<int>(static_cast<int64_t>(cta) * U / G);
+  const int q_end = static_cast<int>(static_cast<int64_t>(cta + 1) * U / G);
+  const int kblocks = a.kblocks;
 
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], SK_CWARPS); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  pdl_launch_dependents();
+
+  if (warp == SK_CWARPS) {
+    // ===================== producer: codes + side band of blocks [q_begin, q_end) =====================
+    // (static data: no griddepcontrol.wait on this path).  One lane per bulk copy of a stage -- lane 0/1
+    // the two code tiles, lanes 2.. the (scale, zero) rows -- each with its own incrementally updated
+    // source pointer, so that issuing a stage costs the warp a couple of dozen instructions.
+    if (lane < 2 + a.nsub) {
+      const uint64_t pol = policy_evict_first();
+      const bool is_code = lane < 2;
+      const int sub = lane - 2;
+      const int esz2 = 2 * static_cast<int>(sizeof(T));
+      const int64_t mrow_pitch = static_cast<int64_t>(a.N) * esz2;
+      const int gdiv = a.group >= SK_KB ? min(a.group / SK_KB, kblocks) : 1;     // k blocks per side-band row
+      const int64_t mstep = a.group >= SK_KB ? mrow_pitch : a.nsub * mrow_pitch;    // advance every gdiv blocks
+      int tile = q_begin / kblocks, kblk = q_begin - tile * kblocks;
+      const uint8_t* mtile = reinterpret_cast<const uint8_t*>(a.meta) + static_cast<int64_t>(tile) * SK_ROWS * esz2;
+      const uint8_t* src;
+      uint32_t dst_off, bytes;
+      int gleft = gdiv - kblk % gdiv;                 // blocks until the side-band row changes
+      int mbytes = min(SK_ROWS, a.N - tile * SK_ROWS) * esz2;
+      if (is_code) {
+        src = reinterpret_cast<const uint8_t*>(a.packed) + static_cast<int64_t>(q_begin) * kBlkB + lane * kTileB;
+        dst_off = lane * WGeom<NBITS>::kTileStride;
+        bytes = kTileB;
+      } else {
+        const int kg = a.group >= SK_KB ? kblk / gdiv : kblk * a.nsub + sub;
+        src = mtile + kg * mrow_pitch;
+        dst_off = WGeom<NBITS>::kCodeBytes + sub * 512;
+        bytes = mbytes;
+      }
+      uint32_t tx = kBlkB + a.nsub * mbytes;
+      int kleft = kblocks - kblk;                     // blocks until the tile changes
+      uint32_t soff = 0, boff = 0;
+      int sleft = stages;
+      uint32_t ph = 1;                                // parity the producer waits on (slots start free)
+      const uint32_t ring_base = ring_u32 + dst_off;
+      const uint32_t full_u32 = smem_u32(&full_bar[0]), empty_u32 = smem_u32(&empty_bar[0]);
+#ifdef SK_TIMING
+      long long p_wait = 0; const long long p_t0 = clock64();
+#endif
+#pragma unroll 1
+      for (int q = q_begin; q < q_end; ++q) {
+        SK_T(pw0);
+        mbar_wait_tight_u32(empty_u32 + boff, ph);
+#ifdef SK_TIMING
+        p_wait += clock64() - pw0;
+#endif
+        if (lane == 0) mbar_expect_tx_u32(full_u32 + boff, tx);
+        bulk_load_1d_hint_u32(ring_base + soff, src, bytes, full_u32 + boff, pol);
+        soff += stage_pitch; boff += 8;
+        if (--sleft == 0) { sleft = stages; soff = 0; boff = 0; ph ^= 1; }
+        if (is_code) src += kBlkB;
+        else if (--gleft == 0) { gleft = gdiv; src += mstep; }
+        if (--kleft == 0) {                           // next tile
+          kleft = kblocks; ++tile;
+          mtile += SK_ROWS * esz2;
+          mbytes = min(SK_ROWS, a.N - tile * SK_ROWS) * esz2;
+          tx = kBlkB + a.nsub * mbytes;
+          if (!is_code) { src = mtile + (a.group >= SK_KB ? 0 : sub) * mrow_pitch; bytes = mbytes; gleft = gdiv; }
+        }
+      }
+#ifdef SK_TIMING
+      if (lane == 0) { g_sk_t[cta][6] = p_wait; g_sk_t[cta][7] = clock64() - p_t0; }
+#endif
+    }
+    return;
+  }
+
+  // ===================== consumers =====================
+  const uint32_t xs_u32 = ring_u32 + stages * stage_pitch;
+  uint8_t* xs_ptr = ring_ptr + stages * stage_pitch;
+  const int mrows = a.m_rows;
+  const int blk_pitch = mrows * SK_XPITCH;            // bytes of x per staged k block
   const int g = lane >> 2, t = lane & 3;
   const int r0 = warp * 16 + g, r1 = r0 + 8;
-  const uint32_t qb = DT<T>::pack2(a.qmin, a.qmin);
-  const T2 qmin2 = *reinterpret_cast<const T2*>(&qb);
   const bool has_zp = a.has_zp != 0;
-  const uint8_t* wbase = reinterpret_cast<const uint8_t*>(a.packed);
-  const uint8_t* mbase = reinterpret_cast<const uint8_t*>(a.meta);
 
-  // linear k-block index q = tile * kblocks + kblk; block q starts at tile-major tile 2q.  The load
-  // cursor (tile, kblk) advances with q, so there is no integer division per block.
-  int ld_tile = (u_begin * SK_KBU) / a.kblocks, ld_kblk = (u_begin * SK_KBU) - ld_tile * a.kblocks;
-  const int gdiv = a.group / SK_KB;                       // groups >= 128: k blocks per group
-  auto load_block = [&](BlockRegs<NBITS>& b, int q) {
-    const uint8_t* blk = wbase + static_cast<int64_t>(q) * (2 * kTileB);
-    b.c0.load(blk, r0, t);
-    b.c1.load(blk, r1, t);
-    int kg;
-    if (a.group >= SK_KB) kg = gdiv == 1 ? ld_kblk : (gdiv >= a.kblocks ? 0 : ld_kblk / gdiv);
-    else kg = ld_kblk * (SK_KB / a.group) + (a.group == 32 ? t : (t >> 1));
-    const int n0 = ld_tile * SK_ROWS;
-    const int64_t row_base = static_cast<int64_t>(kg) * a.N;
-    b.m0 = ldg32_stream(mbase + (row_base + min(n0 + r0, a.N - 1)) * (2 * sizeof(T)));
-    b.m1 = ldg32_stream(mbase + (row_base + min(n0 + r1, a.N - 1)) * (2 * sizeof(T)));
-    if (++ld_kblk == a.kblocks) { ld_kblk = 0; ++ld_tile; }
-  };
+  // per-lane offsets inside a stage
+  const int coff = LaneCodes<NBITS>::lane_off(r0, t);
+  int coff_hi = 0;                                    // W3 only: 1-bit plane
+  if constexpr (NBITS == 3) coff_hi = LaneCodes<3>::lane_off_hi(r0, t);
+  const int msub = a.group >= SK_KB ? 0 : (a.group == 32 ? t : (t >> 1));
+  const int moff = WGeom<NBITS>::kCodeBytes + msub * 512 + r0 * 4;
+  // opaque copies: keeps these per-lane addresses in registers (ptxas otherwise recomputes them from
+  // %tid in every iteration, on the ALU pipe that the extraction needs)
+  const uint32_t cbase = reg_const(ring_u32 + coff), chbase = reg_const(ring_u32 + coff_hi);
+  const uint32_t mbase_l = reg_const(ring_u32 + moff);
+  const uint32_t full_u32 = reg_const(smem_u32(&full_bar[0])), empty_u32 = reg_const(smem_u32(&empty_bar[0]));
 
-  // x slab of local blocks [c0, c0 + n): rows m < M only; 16-byte chunk c = 4t + j of a block is stored
-  // at offset 16t + 64j (conflict-free LDS.128 for the mma B fragments); S[m] = sum of the block.
+  // x slab of local blocks [q0, q0 + n): rows m < M only.  The 16-byte chunk c = 4t + j of a block is
+  // stored at offset 16t + 64j (conflict-free LDS.128 for the mma B fragments); LOHI additionally swaps
+  // the two middle words so that one LDS.128 yields (k0,k1 | k4,k5 | k2,k3 | k6,k7).  The block sums
+  // (sum of the "plain" pairs, sum of the "x16" pairs) of row (bl, m) go to the row's padding.
   auto stage_x = [&](int q0, int n) {
     const T* xg = reinterpret_cast<const T*>(a.x);
-    const int total = n * mrows * 16;                      // 16-byte chunks
-    for (int c = tid; c < total; c += SK_THREADS) {
-      const int bl = c / (mrows * 16);
-      const int rem = c - bl * (mrows * 16);
+    const int per_blk = mrows * 16;
+    const int total = n * per_blk;                         // 16-byte chunks
+    const int kblk0 = q0 % kblocks;
+    for (int c = tid; c < total; c += SK_CTHREADS) {
+      const int bl = c / per_blk;
+      const int rem = c - bl * per_blk;
       const int m = rem >> 4, ch = rem & 15;
-      const int kblk = (q0 + bl) % a.kblocks;
-      const uint4 v = *reinterpret_cast<const uint4*>(xg + static_cast<int64_t>(m) * a.K + kblk * SK_KB + ch * 8);
-      *reinterpret_cast<uint4*>(xs_ptr + (bl * mrows + m) * SK_XPITCH + (ch >> 2) * 16 + (ch & 3) * 64) = v;
-      if (POST) {
-        const float2 f0 = DT<T>::to_f2(v.x), f1 = DT<T>::to_f2(v.y), f2 = DT<T>::to_f2(v.z), f3 = DT<T>::to_f2(v.w);
-        float sm = ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y));
+      const int kblk = (kblk0 + bl) % kblocks;
+      uint4 v = *reinterpret_cast<const uint4*>(xg + static_cast<int64_t>(m) * a.K + kblk * SK_KB + ch * 8);
+      if constexpr (POST) {
+        float2 f0 = DT<T>::to_f2(v.x), f1 = DT<T>::to_f2(v.y), f2 = DT<T>::to_f2(v.z), f3 = DT<T>::to_f2(v.w);
         // the 16 chunks of one (block, m) sit in 16 consecutive threads
         const uint32_t half_mask = (lane < 16) ? 0x0000ffffu : 0xffff0000u;   // total is a multiple of 16
+        float inv = 1.0f;
+        if constexpr (kConvX) {
+          // bf16 -> fp16 without loss: scale the (token, block) slice by a power of two that puts its
+          // largest magnitude in [2^14, 2^15); every element down to 2^-31 of that maximum is then an
+          // exact fp16 number (8 significant bits), smaller ones round at 2^-40 of it -- far below what
+          // the fp32 accumulation resolves.  The inverse power goes into the fp32 post step.
+          float am = fmaxf(fmaxf(fmaxf(fabsf(f0.x), fabsf(f0.y)), fmaxf(fabsf(f1.x), fabsf(f1.y))),
+                           fmaxf(fmaxf(fabsf(f2.x), fabsf(f2.y)), fmaxf(fabsf(f3.x), fabsf(f3.y))));
 #pragma unroll
-        for (int d = 1; d < 16; d <<= 1) sm += __shfl_xor_sync(half_mask, sm, d);
-        if (ch == 0) xsum_s[bl * (MB * 8) + m] = sm;
+          for (int d = 1; d < 16; d <<= 1) am = fmaxf(am, __shfl_xor_sync(half_mask, am, d));
+          const int e = static_cast<int>((__float_as_uint(am) >> 23) & 0xffu);       // biased exponent
+          int fe = 268 - e;                                                          // 2^(14 - (e - 127))
+          fe = (e == 0 || e == 255) ? 127 : min(max(fe, 1), 253);                    // zero / inf / nan: 1.0
+          const float f = __uint_as_float(static_cast<uint32_t>(fe) << 23);
+          inv = __uint_as_float(static_cast<uint32_t>(254 - fe) << 23);
+          f0.x *= f; f0.y *= f; f1.x *= f; f1.y *= f; f2.x *= f; f2.y *= f; f3.x *= f; f3.y *= f;
+          v.x = DT<__half>::pack2(f0.x, f0.y); v.y = DT<__half>::pack2(f1.x, f1.y);
+          v.z = DT<__half>::pack2(f2.x, f2.y); v.w = DT<__half>::pack2(f3.x, f3.y);
+          if (e != 0 && e != 255) {      // sums of what the tensor core will see (exact conversions)
+            f0 = DT<__half>::to_f2(v.x); f1 = DT<__half>::to_f2(v.y); f2 = DT<__half>::to_f2(v.z); f3 = DT<__half>::to_f2(v.w);
+          }
+        }
+        float s_a, s_b;
+        if (LOHI) { s_a = (f0.x + f0.y) + (f2.x + f2.y); s_b = (f1.x + f1.y) + (f3.x + f3.y); }
+        else { s_a = ((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y)); s_b = 0.f; }
+#pragma unroll
+        for (int d = 1; d < 16; d <<= 1) {
+          s_a += __shfl_xor_sync(half_mask, s_a, d);
+          if (LOHI) s_b += __shfl_xor_sync(half_mask, s_b, d);
+        }
+        if (ch == 0)
+          *reinterpret_cast<float4*>(xs_ptr + bl * blk_pitch + m * SK_XPITCH + 256) = make_float4(s_a, s_b, inv, 0.f);
       }
+      if (LOHI) { const uint32_t y = v.y; v.y = v.z; v.z = y; }
+      *reinterpret_cast<uint4*>(xs_ptr + bl * blk_pitch + m * SK_XPITCH + (ch >> 2) * 16 + (ch & 3) * 64) = v;
     }
   };
+
+  // per-lane x addresses: column n = mb*8+g of the mma B operand is token m; columns >= M read the last
+  // valid row instead (their results are never stored), so no zero fill and no branch is needed
+  uint32_t xrow[MB], srow[MB];
+#pragma unroll
+  for (int mb = 0; mb < MB; ++mb) {
+    xrow[mb] = xs_u32 + min(mb * 8 + g, mrows - 1) * SK_XPITCH + t * 16;
+    // this lane's two output columns need the block sums of tokens m = mb*8 + 2t, 2t+1 (clamped like x)
+    srow[mb] = xs_u32 + min(mb * 8 + 2 * t, mrows - 1) * SK_XPITCH + 256;
+  }
 
   float acc[MB][4];
 #pragma unroll
   for (int mb = 0; mb < MB; ++mb) { acc[mb][0] = acc[mb][1] = acc[mb][2] = acc[mb][3] = 0.f; }
 
-  auto compute_block = [&](const BlockRegs<NBITS>& b, int bl) {
-    const uint32_t xs = xs_u32 + (bl * mrows) * SK_XPITCH;
-    if (POST) {
-      float ag[MB][4];
+  const uint32_t qb = DT<T>::pack2(a.qmin, a.qmin);
+  const T2 qmin2 = *reinterpret_cast<const T2*>(&qb);
+  const float zp_fix = -a.qmin;                       // effective zero-point when the quantizer has none
+  const uint32_t magic = reg_const(DQM::kMagic);
+
+  auto compute_block = [&](const BlockRegs<NBITS>& b, uint32_t xoff) {
+    if constexpr (POST) {
+      float ag[MB][4], agh[LOHI ? MB : 1][4];
+      if constexpr (LOHI) {
+        // fp16 W4: words in place, pairs {0,2} (value 1024+q) and {1,3} (value 1024+16q) of each word
+        const uint32_t w0[4] = {b.c0.word(0), b.c0.word(1), b.c0.word(2), b.c0.word(3)};
+        const uint32_t w1[4] = {b.c1.word(0), b.c1.word(1), b.c1.word(2), b.c1.word(3)};
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint4 xb[MB];
+        for (int i = 0; i < 4; ++i) {
+          uint4 xb[MB];
 #pragma unroll
-        for (int mb = 0; mb < MB; ++mb)
-          xb[mb] = (mb * 8 + g < mrows) ? lds128(xs + (mb * 8 + g) * SK_XPITCH + t * 16 + j * 64) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int p = 4 * j + 2 * h;            // pair index of k = 32t + 8j + 4h + {0,1}
-          uint32_t af[4];
-          af[0] = b.c0.pair(p) | DQ<T>::kMagic;
-          af[1] = b.c1.pair(p) | DQ<T>::kMagic;
-          af[2] = b.c0.pair(p + 1) | DQ<T>::kMagic;
-          af[3] = b.c1.pair(p + 1) | DQ<T>::kMagic;
+          for (int mb = 0; mb < MB; ++mb) xb[mb] = lds128(xrow[mb] + xoff + i * 64);
+          const uint32_t s0 = shr8_fma(w0[i]), s1 = shr8_fma(w1[i]);
+          uint32_t al[4], ah[4];
+#ifdef SK_EXP_NOEXTRACT
+          al[0] = w0[i]; al[1] = w1[i]; al[2] = s0; al[3] = s1; ah[0] = w0[i] ^ magic; ah[1] = w1[i] ^ magic; ah[2] = s0 ^ magic; ah[3] = s1 ^ magic;
+#else
+          al[0] = lop_and_or<0x000f000fu>(w0[i], magic);
+          al[1] = lop_and_or<0x000f000fu>(w1[i], magic);
+          al[2] = lop_and_or<0x000f000fu>(s0, magic);
+          al[3] = lop_and_or<0x000f000fu>(s1, magic);
+          ah[0] = lop_and_or<0x00f000f0u>(w0[i], magic);
+          ah[1] = lop_and_or<0x00f000f0u>(w1[i], magic);
+          ah[2] = lop_and_or<0x00f000f0u>(s0, magic);
+          ah[3] = lop_and_or<0x00f000f0u>(s1, magic);
+#endif
 #pragma unroll
           for (int mb = 0; mb < MB; ++mb) {
-            uint32_t bf[2];
-            bf[0] = h == 0 ? xb[mb].x : xb[mb].z;
-            bf[1] = h == 0 ? xb[mb].y : xb[mb].w;
-            if (j == 0 && h == 0) mma_16816_zero(ag[mb], af, bf, kBf16);
-            else mma_16816(ag[mb], af, bf, kBf16);
+            const uint32_t bl2[2] = {xb[mb].x, xb[mb].y}, bh2[2] = {xb[mb].z, xb[mb].w};
+#ifdef SK_EXP_NOMMA
+            if (i == 0) { for (int r = 0; r < 4; ++r) { ag[mb][r] = __uint_as_float(al[r] ^ bl2[r & 1]); agh[mb][r] = __uint_as_float(ah[r] ^ bh2[r & 1]); } }
+            else { for (int r = 0; r < 4; ++r) { ag[mb][r] = __uint_as_float(__float_as_uint(ag[mb][r]) ^ al[r] ^ bl2[r & 1]); agh[mb][r] = __uint_as_float(__float_as_uint(agh[mb][r]) ^ ah[r] ^ bh2[r & 1]); } }
+#else
+            if (i == 0) { mma_16816_zero(ag[mb], al, bl2, kBf16); mma_16816_zero(agh[mb], ah, bh2, kBf16); }
+            else { mma_16816(ag[mb], al, bl2, kBf16); mma_16816(agh[mb], ah, bh2, kBf16); }
+#endif
+          }
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 xb[MB];
+#pragma unroll
+          for (int mb = 0; mb < MB; ++mb) xb[mb] = lds128(xrow[mb] + xoff + j * 64);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int p = 4 * j + 2 * h;            // pair index of k = 32t + 8j + 4h + {0,1}
+            uint32_t af[4];
+            af[0] = b.c0.mpair(p, magic);
+            af[1] = b.c1.mpair(p, magic);
+            af[2] = b.c0.mpair(p + 1, magic);
+            af[3] = b.c1.mpair(p + 1, magic);
+#pragma unroll
+            for (int mb = 0; mb < MB; ++mb) {
+              const uint32_t bf[2] = {h == 0 ? xb[mb].x : xb[mb].z, h == 0 ? xb[mb].y : xb[mb].w};
+              if (j == 0 && h == 0) mma_16816_zero(ag[mb], af, bf, kBf16);
+              else mma_16816(ag[mb], af, bf, kBf16);
+            }
           }
         }
       }
       const float2 sz0 = DT<T>::to_f2(b.m0), sz1 = DT<T>::to_f2(b.m1);     // (scale, zero) of rows r0, r1
-      const float off0 = -(DQ<T>::kMagicF + (has_zp ? sz0.y : -a.qmin));
-      const float off1 = -(DQ<T>::kMagicF + (has_zp ? sz1.y : -a.qmin));
+      const float z0 = has_zp ? sz0.y : zp_fix, z1 = has_zp ? sz1.y : zp_fix;
+      const float off0 = -(DQM::kMagicF + z0), off1 = -(DQM::kMagicF + z1);
+      const float offh0 = -(DQM::kMagicF * 0.0625f + z0), offh1 = -(DQM::kMagicF * 0.0625f + z1);
 #pragma unroll
       for (int mb = 0; mb < MB; ++mb) {
-        const int m = mb * 8 + 2 * t;
-        const float s_a = (m < mrows) ? xsum_s[bl * (MB * 8) + m] : 0.f;
-        const float s_b = (m + 1 < mrows) ? xsum_s[bl * (MB * 8) + m + 1] : 0.f;
-        acc[mb][0] = fmaf(sz0.x, fmaf(off0, s_a, ag[mb][0]), acc[mb][0]);
-        acc[mb][1] = fmaf(sz0.x, fmaf(off0, s_b, ag[mb][1]), acc[mb][1]);
-        acc[mb][2] = fmaf(sz1.x, fmaf(off1, s_a, ag[mb][2]), acc[mb][2]);
-        acc[mb][3] = fmaf(sz1.x, fmaf(off1, s_b, ag[mb][3]), acc[mb][3]);
+        // (S_plain, S_x16, 2^-e, -) of tokens m = mb*8 + 2t and 2t + 1
+        const uint4 u0 = lds128(srow[mb] + xoff), u1 = lds128(srow[mb] + xoff + SK_XPITCH);
+        const float sa0 = __uint_as_float(u0.x), sb0 = __uint_as_float(u0.y);
+        const float sa1 = __uint_as_float(u1.x), sb1 = __uint_as_float(u1.y);
+        float v0 = ag[mb][0], v1 = ag[mb][1], v2 = ag[mb][2], v3 = ag[mb][3];
+        if constexpr (LOHI) {
+          v0 = fmaf(agh[mb][0], 0.0625f, v0); v1 = fmaf(agh[mb][1], 0.0625f, v1);
+          v2 = fmaf(agh[mb][2], 0.0625f, v2); v3 = fmaf(agh[mb][3], 0.0625f, v3);
+          v0 = fmaf(offh0, sb0, v0); v1 = fmaf(offh0, sb1, v1);
+          v2 = fmaf(offh1, sb0, v2); v3 = fmaf(offh1, sb1, v3);
+        }
+        float w00 = sz0.x, w01 = sz0.x, w10 = sz1.x, w11 = sz1.x;
+        if constexpr (kConvX) {
+          const float i0 = __uint_as_float(u0.z), i1 = __uint_as_float(u1.z);
+          w00 *= i0; w01 *= i1; w10 *= i0; w11 *= i1;
+        }
+        acc[mb][0] = fmaf(w00, fmaf(off0, sa0, v0), acc[mb][0]);
+        acc[mb][1] = fmaf(w01, fmaf(off0, sa1, v1), acc[mb][1]);
+        acc[mb][2] = fmaf(w10, fmaf(off1, sa0, v2), acc[mb][2]);
+        acc[mb][3] = fmaf(w11, fmaf(off1, sa1, v3), acc[mb][3]);
       }
     } else {
       const uint32_t s0b = __byte_perm(b.m0, 0, 0x1010), z0b = __byte_perm(b.m0, 0, 0x3232);
@@ -321,8 +599,7 @@ k3_skinny(const SkinnyArgs a) {
       for (int j = 0; j < 4; ++j) {
         uint4 xb[MB];
 #pragma unroll
-        for (int mb = 0; mb < MB; ++mb)
-          xb[mb] = (mb * 8 + g < mrows) ? lds128(xs + (mb * 8 + g) * SK_XPITCH + t * 16 + j * 64) : make_uint4(0, 0, 0, 0);
+        for (int mb = 0; mb < MB; ++mb) xb[mb] = lds128(xrow[mb] + xoff + j * 64);
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int p = 4 * j + 2 * h;
@@ -333,9 +610,7 @@ k3_skinny(const SkinnyArgs a) {
           af[3] = dq_pair<T, NBITS>(b.c1.pair(p + 1), qmin2, z1, s1, has_zp);
 #pragma unroll
           for (int mb = 0; mb < MB; ++mb) {
-            uint32_t bf[2];
-            bf[0] = h == 0 ? xb[mb].x : xb[mb].z;
-            bf[1] = h == 0 ? xb[mb].y : xb[mb].w;
+            const uint32_t bf[2] = {h == 0 ? xb[mb].x : xb[mb].z, h == 0 ? xb[mb].y : xb[mb].w};
             mma_16816(acc[mb], af, bf, kBf16);
           }
         }
@@ -361,92 +636,172 @@ k3_skinny(const SkinnyArgs a) {
       }
   };
 
-  // end of a tile segment [seg_begin, u]: write y or hand the fragment to the stream-K fix-up
-  auto finish_segment = [&](int u, int seg_begin) {
-    const int tile = u / a.units_per_tile;
-    const int tile_u0 = tile * a.units_per_tile;
-    const int tile_u1 = tile_u0 + a.units_per_tile;           // exclusive
-    const int n0 = tile * SK_ROWS;
-    if (seg_begin == tile_u0 && u + 1 == tile_u1) {
-      write_fragment(acc, n0);                                // this CTA owns the whole tile
+  // end of a tile segment [seg_begin, q]: write y or hand the fragment to the stream-K fix-up.  The fix-up
+  // is split in two so that the round trip of the arrival counter overlaps the next block's math:
+  // finish_segment() stores the partial fragment and ISSUES the counter RMW; resolve_pending(), one block
+  // later (or at the end of the CTA's run), looks at its result and -- if this warp was the last
+  // contributor of the fragment -- sums the slots in slot order (deterministic) and writes y.
+  int pend_tile = -1, pend_old = 0, pend_n = 0;
+  auto slot_base = [&](int tile) {
+    // slot layout: [slot][warp][mb][reg][lane]; this warp only ever touches its own [warp] part
+    return a.ws_partials + static_cast<int64_t>(tile) * a.max_slots * FRAG + warp * (MB * 4 * 32);
+  };
+  auto resolve_pending = [&]() {
+    const int old = __shfl_sync(0xffffffffu, pend_old, 0);
+    __syncwarp();
+    if (old == pend_n - 1) {
+      // last contributor of this 16-row fragment: all slots are visible
+      const float* wst = slot_base(pend_tile);
+      float v[MB][4];
+#pragma unroll
+      for (int mb = 0; mb < MB; ++mb)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) v[mb][r] = 0.f;
+      for (int sl = 0; sl < pend_n; ++sl) {
+#pragma unroll
+        for (int mb = 0; mb < MB; ++mb)
+#pragma unroll
+          for (int r = 0; r < 4; ++r)
+            v[mb][r] += __ldcg(wst + static_cast<int64_t>(sl) * FRAG + (mb * 4 + r) * 32 + lane);
+      }
+      write_fragment(v, pend_tile * SK_ROWS);
+      if (lane == 0) a.ws_counters[pend_tile * 8 + warp] = 0;     // leave the workspace clean
+    }
+    pend_tile = -1;
+  };
+  auto finish_segment = [&](int q, int seg_begin) {
+    const int tile = q / kblocks;
+    const int tile_q0 = tile * kblocks;
+    const int tile_q1 = tile_q0 + kblocks;                    // exclusive
+    if (seg_begin == tile_q0 && q + 1 == tile_q1) {
+      write_fragment(acc, tile * SK_ROWS);                    // this CTA owns the whole tile
     } else {
-      const int c_first = unit_owner(tile_u0, G, U);
-      const int c_last = unit_owner(tile_u1 - 1, G, U);
-      const int n_contrib = c_last - c_first + 1;
-      // slot layout: [slot][warp][mb][reg][lane]; this warp only ever touches its own [warp] part
-      float* wst = a.ws_partials + static_cast<int64_t>(tile) * a.max_slots * FRAG + warp * (MB * 4 * 32);
-      float* wsp = wst + static_cast<int64_t>(cta - c_first) * FRAG;
+      const int c_first = unit_owner(tile_q0, G, U);
+      const int c_last = unit_owner(tile_q1 - 1, G, U);
+      float* wsp = slot_base(tile) + static_cast<int64_t>(cta - c_first) * FRAG;
 #pragma unroll
       for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
         for (int r = 0; r < 4; ++r) wsp[(mb * 4 + r) * 32 + lane] = acc[mb][r];
-      __threadfence();
+      // publish: the warp barrier orders the lanes' stores before lane 0's acq_rel RMW (release for our
+      // slot, acquire for the slots of the CTAs that arrived earlier); the shuffle + barrier in
+      // resolve_pending() order the other lanes' reads behind that acquire.  No MEMBAR.SC needed.
       __syncwarp();
-      int old = 0;
       int* cnt = a.ws_counters + tile * 8 + warp;
-      if (lane == 0) old = atomicAdd(cnt, 1);
-      old = __shfl_sync(0xffffffffu, old, 0);
-      if (old == n_contrib - 1) {
-        // last contributor of this 16-row fragment: all slots are visible
-        __threadfence();
-        float v[MB][4];
-#pragma unroll
-        for (int mb = 0; mb < MB; ++mb)
-#pragma unroll
-          for (int r = 0; r < 4; ++r) v[mb][r] = 0.f;
-        for (int sl = 0; sl < n_contrib; ++sl) {
-#pragma unroll
-          for (int mb = 0; mb < MB; ++mb)
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-              v[mb][r] += __ldcg(wst + static_cast<int64_t>(sl) * FRAG + (mb * 4 + r) * 32 + lane);
-        }
-        write_fragment(v, n0);
-        if (lane == 0) *cnt = 0;                              // leave the workspace clean
-      }
+      if (lane == 0) asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(pend_old) : "l"(cnt) : "memory");
+      pend_tile = tile;
+      pend_n = c_last - c_first + 1;
     }
 #pragma unroll
     for (int mb = 0; mb < MB; ++mb) { acc[mb][0] = acc[mb][1] = acc[mb][2] = acc[mb][3] = 0.f; }
   };
 
-  const int q_begin = u_begin * SK_KBU, q_end = u_end * SK_KBU;
-  BlockRegs<NBITS> ring[SK_DEPTH];
-#pragma unroll
-  for (int d = 0; d < SK_DEPTH; ++d)
-    if (q_begin + d < q_end) load_block(ring[d], q_begin + d);
+  pdl_wait();                                   // x, y and the workspace belong to the stream order
+#ifdef SK_TIMING
+  const long long c_t0 = clock64(); long long c_stage = 0, c_wait = 0, c_fin = 0, c_comp = 0;
+#endif
 
-  int seg_begin = u_begin;                      // first unit of the current tile segment
-  for (int qc = q_begin; qc < q_end; qc += SK_CHUNK) {
-    const int nblk = min(SK_CHUNK, q_end - qc);
-    __syncthreads();                            // everyone is done with the previous slab
+  int seg_begin = q_begin;                      // first block of the current tile segment
+  int kb = q_begin % kblocks;                   // block index inside its tile
+  uint32_t soff = 0, boff = 0;                  // byte offsets of the current stage / its barriers
+  int sleft = stages;                           // stages until the ring wraps
+  uint32_t ph = 0;
+  for (int qc = q_begin; qc < q_end; qc += a.chunk) {
+    const int nblk = min(a.chunk, q_end - qc);
+    SK_T(ts0);
+    bar_sync_consumers();                       // everyone is done with the previous slab
     stage_x(qc, nblk);
-    __syncthreads();
-    for (int b0 = 0; b0 < nblk; b0 += SK_DEPTH) {
-#pragma unroll
-      for (int d = 0; d < SK_DEPTH; ++d) {
-        const int q = qc + b0 + d;
-        if (q < q_end) {
-          compute_block(ring[d], b0 + d);
-          if (q + SK_DEPTH < q_end) load_block(ring[d], q + SK_DEPTH);
-          if (d & 1) {                          // a unit = 2 k blocks: unit boundary after the odd block
-            const int u = q / SK_KBU;
-            const int ku = u % a.units_per_tile;
-            if (ku == a.units_per_tile - 1 || u == u_end - 1) {
-              finish_segment(u, seg_begin);
-              seg_begin = u + 1;
-            }
-          }
-        }
+    bar_sync_consumers();
+#ifdef SK_TIMING
+    c_stage += clock64() - ts0;
+#endif
+    uint32_t xoff = 0;
+#pragma unroll 1
+    for (int bl = 0; bl < nblk; ++bl) {
+      SK_T(tw0);
+      mbar_wait_tight_u32(full_u32 + boff, ph);
+#ifdef SK_TIMING
+      const long long tw1 = clock64(); c_wait += tw1 - tw0;
+#endif
+      BlockRegs<NBITS> b;
+      b.c0.load(cbase + soff, chbase + soff);
+      b.c1.load(cbase + soff + LaneCodes<NBITS>::kRow8, chbase + soff + 64);
+      b.m0 = lds32(mbase_l + soff);
+      b.m1 = lds32(mbase_l + soff + 32);
+      __syncwarp();
+      if (lane == 0) mbar_arrive_u32(empty_u32 + boff);     // slot may be refilled: the block is in registers
+      soff += stage_pitch; boff += 8;
+      if (--sleft == 0) { sleft = stages; soff = 0; boff = 0; ph ^= 1; }
+      compute_block(b, xoff);
+      xoff += blk_pitch;
+#ifdef SK_TIMING
+      const long long tc1 = clock64(); c_comp += tc1 - tw1;
+#endif
+      const int q = qc + bl;
+      if (pend_tile >= 0) resolve_pending();
+      if (++kb == kblocks || q == q_end - 1) {
+        finish_segment(q, seg_begin);
+        seg_begin = q + 1;
+        kb = 0;
+#ifdef SK_TIMING
+        c_fin += clock64() - tc1;
+#endif
       }
     }
   }
+  if (pend_tile >= 0) resolve_pending();
+#ifdef SK_TIMING
+  if (tid == 0) {
+    g_sk_t[cta][0] = clock64() - c_t0; g_sk_t[cta][1] = c_stage; g_sk_t[cta][2] = c_wait; g_sk_t[cta][3] = c_comp;
+    g_sk_t[cta][4] = c_fin; g_sk_t[cta][5] = q_end - q_begin;
+  }
+#endif
 }
 
 // ---------------------------------------------------------------- host
+struct SkinnyPlan {
+  int n_tiles, total_units, max_slots, grid_cap;
+};
+
+static SkinnyPlan plan_skinny(int64_t N, int64_t K) {
+  SkinnyPlan p;
+  const int kblocks = static_cast<int>(K / SK_KB);
+  p.n_tiles = static_cast<int>((N + SK_ROWS - 1) / SK_ROWS);
+  p.total_units = p.n_tiles * kblocks;
+  int grid = sm_count() * SK_OCC;             // upper bound of the persistent grid
+  if (grid > p.total_units) grid = p.total_units;
+  if (grid < 1) grid = 1;
+  p.grid_cap = grid;
+  // a tile of `kblocks` units can be touched by at most this many CTAs
+  p.max_slots = static_cast<int>((static_cast<int64_t>(kblocks) * grid + p.total_units - 1) / p.total_units) + 2;
+  return p;
+}
+
 template <typename T, int NBITS, int MB, bool POST>
 static int launch_skinny(SkinnyArgs a, cudaStream_t st) {
   auto kern = k3_skinny<T, NBITS, MB, POST>;
-  const int smem = skinny_smem_bytes(a.m_rows, MB);
+  constexpr int occ_target = MB <= 2 ? SK_OCC : 2;
+  // per-CTA shared memory: ring + x slab within the budget that keeps occ_target CTAs resident
+  const int budget = (228 * 1024) / occ_target - 1024 /* driver reserve */ - 512 /* static */ - 128 /* align */;
+  const int stage_pitch = (stage_bytes<NBITS>(a.nsub) + 127) & ~127;
+  const int row_b = a.m_rows * SK_XPITCH;
+  // reserve ~2/3 of the budget (at most 6 stages) for the ring; then as much x as fits up to SK_CHUNK_MAX
+  // blocks; what is left goes back to the ring
+  int min_stages = (2 * budget / 3) / stage_pitch;
+  if (min_stages > 6) min_stages = 6;
+  if (min_stages < 2) min_stages = 2;
+  int chunk = (budget - min_stages * stage_pitch - SK_XPITCH) / row_b;
+  if (chunk > SK_CHUNK_MAX) chunk = SK_CHUNK_MAX;
+  Q100_REQUIRE(chunk >= 1, Q100_EUNSUPPORTED, "k3_skinny: M=%d rows of x do not fit in shared memory", a.m_rows);
+  // a CTA never needs more x than its share of the blocks: keep the slab small so that the ring is deep
+  const int grid_est = plan_skinny(a.N, a.K).grid_cap;
+  const int share = (a.total_units + grid_est - 1) / grid_est + 1;
+  if (chunk > share) chunk = share;
+  int stages = (budget - slab_bytes(a.m_rows, chunk)) / stage_pitch;
+  if (stages > SK_MAX_STAGES) stages = SK_MAX_STAGES;
+  a.chunk = chunk;
+  a.stages = stages;
+  const int smem = stages * stage_pitch + slab_bytes(a.m_rows, chunk) + 128;
   static std::mutex mu;           // one per instantiation
   static int max_set = 0;
   static std::unordered_map<int, int> occ_cache;
@@ -467,26 +822,34 @@ static int launch_skinny(SkinnyArgs a, cudaStream_t st) {
   }
   Q100_REQUIRE(occ >= 1, Q100_ECUDA, "k3_skinny does not fit on an SM (%d bytes smem)", smem);
   // persistent grid: every CTA resident at once, units split evenly (stream-K)
-  int grid = sm_count() * (occ > SK_MAX_CTAS ? SK_MAX_CTAS : occ);
+  int grid = sm_count() * (occ > SK_OCC ? SK_OCC : occ);
   if (grid > a.total_units) grid = a.total_units;
-  Q100_REQUIRE(static_cast<int64_t>(a.units_per_tile) * grid / a.total_units + 2 <= a.max_slots, Q100_EWORKSPACE,
+  Q100_REQUIRE(static_cast<int64_t>(a.kblocks) * grid / a.total_units + 2 <= a.max_slots, Q100_EWORKSPACE,
                "internal: slot bound");
-  kern<<<grid, SK_THREADS, smem, st>>>(a);
-  return check_cuda(cudaGetLastError(), "k3_skinny launch");
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(SK_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = a.pdl ? 1 : 0;
+  return check_cuda(cudaLaunchKernelEx(&cfg, kern, a), "k3_skinny launch");
+}
+
+template <typename T, int NBITS, int MB>
+static int launch_skinny_post(const SkinnyArgs& a, cudaStream_t st) {
+  if (a.post) return launch_skinny<T, NBITS, MB, true>(a, st);
+  return launch_skinny<T, NBITS, MB, false>(a, st);
 }
 
 template <typename T, int NBITS>
 static int launch_skinny_mb(const SkinnyArgs& a, cudaStream_t st) {
-  // 8-bit codes do not fit bf16's 7-bit OR-magic; that combination keeps the exact path
-  constexpr bool kCanPost = !(NBITS == 8 && DT<T>::kCode == Q100_BF16);
-  if (a.post && kCanPost) {
-    if (a.M <= 8) return launch_skinny<T, NBITS, 1, kCanPost>(a, st);
-    if (a.M <= 16) return launch_skinny<T, NBITS, 2, kCanPost>(a, st);
-    return launch_skinny<T, NBITS, 4, kCanPost>(a, st);
-  }
-  if (a.M <= 8) return launch_skinny<T, NBITS, 1, false>(a, st);
-  if (a.M <= 16) return launch_skinny<T, NBITS, 2, false>(a, st);
-  return launch_skinny<T, NBITS, 4, false>(a, st);
+  if (a.M <= 8) return launch_skinny_post<T, NBITS, 1>(a, st);
+  if (a.M <= 16) return launch_skinny_post<T, NBITS, 2>(a, st);
+  return launch_skinny_post<T, NBITS, 4>(a, st);
 }
 
 template <typename T>
@@ -499,24 +862,11 @@ static int launch_skinny_bits(int n_bits, const SkinnyArgs& a, cudaStream_t st) 
   }
 }
 
-struct SkinnyPlan {
-  int units_per_tile, n_tiles, total_units, max_slots;
-};
-
-static SkinnyPlan plan_skinny(int64_t N, int64_t K) {
-  SkinnyPlan p;
-  const int kblocks = static_cast<int>(K / SK_KB);
-  p.units_per_tile = kblocks / SK_KBU;
-  p.n_tiles = static_cast<int>((N + SK_ROWS - 1) / SK_ROWS);
-  p.total_units = p.n_tiles * p.units_per_tile;
-  int grid = sm_count() * SK_MAX_CTAS;        // upper bound of the persistent grid
-  if (grid > p.total_units) grid = p.total_units;
-  if (grid < 1) grid = 1;
-  // a tile of `units_per_tile` units can be touched by at most this many CTAs
-  p.max_slots = static_cast<int>((static_cast<int64_t>(p.units_per_tile) * grid + p.total_units - 1) /
-                                 p.total_units) + 2;
-  return p;
+#ifdef SK_TIMING
+int skinny_timing(long long* out, int n) {
+  return check_cuda(cudaMemcpyFromSymbol(out, g_sk_t, sizeof(long long) * 8 * n), "timing readback");
 }
+#endif
 
 size_t skinny_workspace_bytes(int64_t M, int64_t N, int64_t K) {
   const SkinnyPlan p = plan_skinny(N, K);
@@ -527,9 +877,9 @@ size_t skinny_workspace_bytes(int64_t M, int64_t N, int64_t K) {
 
 int gemm_skinny(const void* x, const void* packed, const void* meta, const void* bias, void* y,
                 int64_t M, int64_t N, int64_t K, int group, int n_bits, int disable_zp, int dtype,
-                void* workspace, size_t workspace_bytes, int exact_weights, cudaStream_t st) {
+                void* workspace, size_t workspace_bytes, int exact_weights, int pdl, cudaStream_t st) {
   Q100_REQUIRE(M >= 1 && M <= 32, Q100_EINVAL, "skinny GEMM handles 1 <= M <= 32 (got %lld)", (long long)M);
-  Q100_REQUIRE(K % (SK_KB * SK_KBU) == 0, Q100_EUNSUPPORTED, "K=%lld must be a multiple of 256", (long long)K);
+  Q100_REQUIRE(K % SK_KB == 0, Q100_EUNSUPPORTED, "K=%lld must be a multiple of 128", (long long)K);
   Q100_REQUIRE(N % 8 == 0, Q100_EUNSUPPORTED, "N=%lld must be a multiple of 8", (long long)N);
   const int g = group == 0 ? static_cast<int>(K) : group;
   Q100_REQUIRE(g == 32 || g == 64 || g % 128 == 0, Q100_EUNSUPPORTED,
@@ -550,12 +900,14 @@ int gemm_skinny(const void* x, const void* packed, const void* meta, const void*
   a.ws_partials = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + SK_COUNTER_BYTES);
   a.M = static_cast<int>(M); a.N = static_cast<int>(N); a.K = static_cast<int>(K); a.group = g;
   a.kblocks = static_cast<int>(K / SK_KB);
-  a.units_per_tile = p.units_per_tile; a.n_tiles = p.n_tiles;
+  a.n_tiles = p.n_tiles;
   a.total_units = p.total_units; a.max_slots = p.max_slots;
   a.has_zp = disable_zp ? 0 : 1;
   a.qmin = disable_zp ? -static_cast<float>(1 << (n_bits - 1)) : 0.0f;
   a.post = (g % SK_KB == 0 && !exact_weights) ? 1 : 0;
   a.m_rows = static_cast<int>(M);
+  a.nsub = g >= SK_KB ? 1 : SK_KB / g;
+  a.pdl = pdl;
   if (dtype == Q100_F16) return launch_skinny_bits<__half>(n_bits, a, st);
   return launch_skinny_bits<__nv_bfloat16>(n_bits, a, st);
 }

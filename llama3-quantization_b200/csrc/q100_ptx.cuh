@@ -31,6 +31,11 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// No-ops unless the kernel was launched with cudaLaunchAttributeProgrammaticStreamSerialization.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");

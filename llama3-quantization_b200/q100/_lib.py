@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libq100.so")
+# Q100_LIB selects an experiment build (tools/build_ext.py, Q100_VARIANT); the default is the in-tree library
+LIB_PATH = os.environ.get("Q100_LIB") or os.path.join(_HERE, "libq100.so")
 
 OK, EINVAL, EUNSUPPORTED, ECUDA, ENODEVICE, EWORKSPACE = range(6)
 F16, BF16, F32 = 0, 1, 2
@@ -19,6 +20,7 @@ FLAG_SCALAR_MATH = 0x2
 GEMM_FORCE_SKINNY = 0x1
 GEMM_FORCE_TC = 0x2
 GEMM_EXACT_WEIGHTS = 0x4
+GEMM_PDL = 0x8
 
 _vp, _i, _i64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
 

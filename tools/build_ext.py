@@ -22,8 +22,11 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PKG = os.path.join(ROOT, "llama3-quantization_b200")
 CSRC = os.path.join(PKG, "csrc")
-OUT = os.path.join(PKG, "q100", "libq100.so")
-OBJ = os.path.join(ROOT, "build", "obj")
+# experiment builds: Q100_VARIANT=<tag> (+ Q100_NVCC_FLAGS) writes libq100_<tag>.so from its own object dir;
+# select it at run time with Q100_LIB=<path> (q100/_lib.py)
+_VAR = os.environ.get("Q100_VARIANT", "")
+OUT = os.path.join(PKG, "q100", f"libq100_{_VAR}.so" if _VAR else "libq100.so")
+OBJ = os.path.join(ROOT, "build", f"obj_{_VAR}" if _VAR else "obj")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = os.environ.get("Q100_NVCC_FLAGS", "").split() + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
