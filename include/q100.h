@@ -58,6 +58,10 @@ enum q100_status {
 #define Q100_GEMM_EXACT_WEIGHTS 0x4 /* decode kernel: rebuild the 16-bit fake-quantised weight
                                       r(r(q-zp)*scale) bit-exactly before the MMA (slower); default
                                       keeps (q-zp) exact and applies the scale in fp32 per group   */
+#define Q100_GEMM_FORCE_MMA_SYNC 0x10 /* decode shapes: always the mma.sync streaming kernel                 */
+#define Q100_GEMM_FORCE_STREAM_TC 0x20 /* decode shapes: the tcgen05 streaming kernel (weights as the TMEM A
+                                      operand) wherever it applies (M <= 16, W2/W4, group % 128 == 0);
+                                      default: 8 < M <= 16                                           */
 #define Q100_GEMM_PDL          0x8 /* launch with programmatic stream serialization: the kernel starts
                                       streaming its (static) weights while the previous kernel of the
                                       stream drains, and waits (griddepcontrol.wait) before it touches

@@ -14,6 +14,11 @@ int gemm_skinny(const void* x, const void* packed, const void* meta, const void*
                 int64_t M, int64_t N, int64_t K, int group, int n_bits, int disable_zp, int dtype,
                 void* workspace, size_t workspace_bytes, int exact_weights, int pdl, cudaStream_t st);
 size_t skinny_workspace_bytes(int64_t M, int64_t N, int64_t K);
+int gemm_stream(const void* x, const void* packed, const void* meta, const void* bias, void* y,
+                int64_t M, int64_t N, int64_t K, int group, int n_bits, int disable_zp, int dtype,
+                void* workspace, size_t workspace_bytes, int pdl, cudaStream_t st);
+size_t stream_workspace_bytes(int64_t M, int64_t N, int64_t K);
+bool gemm_stream_supported(int64_t M, int64_t N, int64_t K, int group, int n_bits);
 
 int gemm_tc(const void* x, const void* packed, const void* meta, const void* bias, void* y,
             int64_t M, int64_t N, int64_t K, int group, int n_bits, int disable_zp, int dtype,
@@ -67,7 +72,9 @@ extern "C" size_t q100_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int
   (void)n_bits; (void)flags;
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   const int64_t mm = M < 32 ? M : 32;
-  return skinny_workspace_bytes(mm, N, K);
+  const size_t a = skinny_workspace_bytes(mm, N, K);
+  const size_t b = stream_workspace_bytes(mm < 16 ? mm : 16, N, K);
+  return a > b ? a : b;
 }
 
 extern "C" int q100_gemm_wna16(const void* x, const void* packed, const void* meta, const void* bias,
@@ -93,7 +100,15 @@ extern "C" int q100_gemm_wna16(const void* x, const void* packed, const void* me
     Q100_REQUIRE(tc_ok, Q100_EUNSUPPORTED, "tcgen05 path does not support this shape/bit-width");
     return gemm_tc(x, packed, meta, bias, y, M, N, K, group, n_bits, disable_zp, dtype, st);
   }
-  // weight-streaming kernel, 32 rows of x per pass
+  // decode shapes: tcgen05 weight-streaming kernel (weights as the TMEM A operand)
+  // (measured, profiles/r01: it is M-independent -- 107 us at M = 16 vs 161 us for the mma.sync kernel on
+  // 57344 x 8192 -- but its small-N MMAs and its per-block latency chain lose to mma.sync up to M = 8)
+  const bool want_stream = (flags & Q100_GEMM_FORCE_STREAM_TC) || M > 8;
+  if (want_stream && !(flags & (Q100_GEMM_FORCE_MMA_SYNC | Q100_GEMM_EXACT_WEIGHTS)) &&
+      gemm_stream_supported(M, N, K, group, n_bits))
+    return gemm_stream(x, packed, meta, bias, y, M, N, K, group, n_bits, disable_zp, dtype, workspace,
+                       workspace_bytes, (flags & Q100_GEMM_PDL) ? 1 : 0, st);
+  // mma.sync weight-streaming kernel, 32 rows of x per pass
   const size_t esz = 2;
   for (int64_t m0 = 0; m0 < M; m0 += 32) {
     const int64_t mc = (M - m0) < 32 ? (M - m0) : 32;

@@ -25,6 +25,9 @@ from conftest import TDT, bits_to_torch, load_golden, torch_to_bits
 pytestmark = pytest.mark.gpu
 EPS_OUT = {"f16": 2.0 ** -11, "bf16": 2.0 ** -8}
 EPS_W = {"f16": 2.0 ** -12, "bf16": 2.0 ** -9}
+# decode shapes have two kernels: the tcgen05 streaming kernel (M <= 16, W2/W4, group % 128 == 0; default
+# for 8 < M <= 16) and the mma.sync streaming kernel (everything else); both are forced here in turn
+PATHS = {"stream_tc": _lib.GEMM_FORCE_STREAM_TC, "mma_sync": _lib.GEMM_FORCE_MMA_SYNC}
 
 
 def _check(y, x, wdeq, bias, dtype, exact_weights=True):
@@ -52,17 +55,20 @@ def _make(N, K, M, dtype, n_bits, group, seed, nozp=False, sym=False):
     return x, w, pw, r
 
 
+@pytest.mark.parametrize("path", sorted(PATHS))
 @pytest.mark.parametrize("dtype", ["f16", "bf16"])
 @pytest.mark.parametrize("n_bits", [4, 2, 3, 8])
 @pytest.mark.parametrize("M", [1, 2, 5, 8, 9, 16, 17, 32])
-def test_skinny_vs_oracle(dtype, n_bits, M):
+def test_skinny_vs_oracle(dtype, n_bits, M, path):
+    if path == "stream_tc" and (n_bits in (3, 8) or M > 16):
+        pytest.skip("same kernel as mma_sync for this case")
     N, K = 384, 1024
     x, w, pw, r = _make(N, K, M, dtype, n_bits, 128, 1000 + M + n_bits)
     # the packed twin is consistent with the oracle (bit-exact)
     o = O.quantize_groupwise(O.from_bits(torch_to_bits(w), dtype).reshape(N, K), dtype, 128, n_bits)
     assert np.array_equal(pw.packed.cpu().numpy().view(np.uint32), O.pack_codes(o["codes"], n_bits))
     wdeq = torch.from_numpy(o["dequant"])
-    y = q100.gemm_wna16(x, pw, None, flags=_lib.GEMM_FORCE_SKINNY)
+    y = q100.gemm_wna16(x, pw, None, flags=_lib.GEMM_FORCE_SKINNY | PATHS[path])
     torch.cuda.synchronize()
     _check(y, x, wdeq, None, dtype, exact_weights=False)
     y = q100.gemm_wna16(x, pw, None, flags=_lib.GEMM_FORCE_SKINNY | _lib.GEMM_EXACT_WEIGHTS)
@@ -70,34 +76,39 @@ def test_skinny_vs_oracle(dtype, n_bits, M):
     _check(y, x, wdeq, None, dtype, exact_weights=True)
 
 
+@pytest.mark.parametrize("path", sorted(PATHS))
 @pytest.mark.parametrize("dtype", ["f16", "bf16"])
 @pytest.mark.parametrize("N,K,group", [(128, 256, 128), (136, 512, 128), (1024, 4096, 128), (4096, 4096, 128),
                                        (512, 14336, 128), (256, 512, 64), (256, 512, 32), (256, 1024, 256),
                                        (256, 1024, 0), (6144, 4096, 128)])
-def test_skinny_shapes(dtype, N, K, group):
-    for M, bias in ((1, False), (16, True)):
+def test_skinny_shapes(dtype, N, K, group, path):
+    if path == "stream_tc" and group in (32, 64):
+        pytest.skip("same kernel as mma_sync for this case")
+    for M, bias in ((1, False), (3, True), (16, True)):
         x, w, pw, r = _make(N, K, M, dtype, 4, group or None, N + K + M)
         b = (torch.randn(N) * 0.1).to(TDT[dtype]).cuda() if bias else None
-        y = q100.gemm_wna16(x, pw, b, flags=_lib.GEMM_FORCE_SKINNY)
+        y = q100.gemm_wna16(x, pw, b, flags=_lib.GEMM_FORCE_SKINNY | PATHS[path])
         torch.cuda.synchronize()
         _check(y, x, r.dequant, b, dtype, exact_weights=(group in (32, 64)))
 
 
+@pytest.mark.parametrize("path", sorted(PATHS))
 @pytest.mark.parametrize("dtype", ["f16", "bf16"])
-def test_skinny_symmetric_and_nozp(dtype):
+def test_skinny_symmetric_and_nozp(dtype, path):
     for n_bits in (2, 3, 4, 8):
         for sym, nozp in ((True, False), (True, True)):
             x, w, pw, r = _make(256, 512, 4, dtype, n_bits, 128, 77 + n_bits, nozp=nozp, sym=sym)
-            y = q100.gemm_wna16(x, pw, None, flags=_lib.GEMM_FORCE_SKINNY)
+            y = q100.gemm_wna16(x, pw, None, flags=_lib.GEMM_FORCE_SKINNY | PATHS[path])
             _check(y, x, r.dequant, None, dtype, exact_weights=False)
             y = q100.gemm_wna16(x, pw, None, flags=_lib.GEMM_FORCE_SKINNY | _lib.GEMM_EXACT_WEIGHTS)
             _check(y, x, r.dequant, None, dtype, exact_weights=True)
 
 
-def test_skinny_deterministic_and_workspace_clean():
+@pytest.mark.parametrize("path", sorted(PATHS))
+def test_skinny_deterministic_and_workspace_clean(path):
     x, w, pw, r = _make(4096, 4096, 16, "bf16", 4, 128, 5)
-    y1 = q100.gemm_wna16(x, pw, None, flags=_lib.GEMM_FORCE_SKINNY)
-    y2 = q100.gemm_wna16(x, pw, None, flags=_lib.GEMM_FORCE_SKINNY)
+    y1 = q100.gemm_wna16(x, pw, None, flags=_lib.GEMM_FORCE_SKINNY | PATHS[path])
+    y2 = q100.gemm_wna16(x, pw, None, flags=_lib.GEMM_FORCE_SKINNY | PATHS[path])
     torch.cuda.synchronize()
     assert torch.equal(y1.view(torch.int16), y2.view(torch.int16))
     from q100 import ops
@@ -117,8 +128,9 @@ def test_weird_zero_points():
     w = w.half().cuda()
     x = torch.randn(3, 256).half().cuda()
     pw, r = q100.pack_weight(w, 4, 128, want_dequant=True)
-    y = q100.gemm_wna16(x, pw, None, flags=_lib.GEMM_FORCE_SKINNY)
-    _check(y, x, r.dequant, None, "f16", exact_weights=False)
+    for path in sorted(PATHS):
+        y = q100.gemm_wna16(x, pw, None, flags=_lib.GEMM_FORCE_SKINNY | PATHS[path])
+        _check(y, x, r.dequant, None, "f16", exact_weights=False)
     y = q100.gemm_wna16(x, pw, None, flags=_lib.GEMM_FORCE_SKINNY | _lib.GEMM_EXACT_WEIGHTS)
     _check(y, x, r.dequant, None, "f16", exact_weights=True)
 

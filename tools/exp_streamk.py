@@ -20,12 +20,14 @@ def main():
     ap.add_argument("--dtype", default="bf16")
     ap.add_argument("--m", default="1")
     ap.add_argument("--pdl", action="store_true")
+    ap.add_argument("--mma-sync", action="store_true", help="force the mma.sync streaming kernel")
+    ap.add_argument("--stream-tc", action="store_true", help="force the tcgen05 streaming kernel")
     ap.add_argument("--bits", type=int, default=4)
     ap.add_argument("--shapes", default="up,gateup,down,o,qkv,gateup70")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     dt = {"bf16": torch.bfloat16, "f16": torch.float16}[a.dtype]
-    flags = _lib.GEMM_FORCE_SKINNY | (_lib.GEMM_PDL if a.pdl else 0)
+    flags = _lib.GEMM_FORCE_SKINNY | (_lib.GEMM_PDL if a.pdl else 0) | (_lib.GEMM_FORCE_MMA_SYNC if a.mma_sync else 0) | (_lib.GEMM_FORCE_STREAM_TC if a.stream_tc else 0)
     for name in a.shapes.split(","):
         N, K = SHAPES[name]
         nset = max(2, -(-340_000_000 // (N * K * a.bits // 8)))   # rotate through > 2.5x the 126 MB L2
