@@ -174,12 +174,16 @@ def run_ours(args):
     dt_t = torch.bfloat16
     flags = _lib.GEMM_FORCE_SKINNY if os.environ.get("Q100_BENCH_FORCE_SKINNY") else 0
 
-    # ---- weights: NB independent blocks so that successive decode steps stream from HBM, not L2
+    # ---- weights: NB independent blocks so that successive decode steps stream from HBM, not L2.
+    # Besides the seven per-linear packs (prefill / module API) each block carries the decode-time fusion
+    # q|k|v and gate|up (concatenation along N is exact: groups run along K), SURVEY.md section 8.
     NB = 3
+    FUSED = [("qkv", ("q_proj", "k_proj", "v_proj"), "h"), ("o", ("o_proj",), "a"),
+             ("gateup", ("gate_proj", "up_proj"), "h"), ("down", ("down_proj",), "m")]
     gen = torch.Generator(device=dev).manual_seed(0)
-    blocks = []
+    blocks, fblocks = [], []
     for b in range(NB):
-        blk = {}
+        blk, shards = {}, {}
         for j, (name, n, k, _) in enumerate(LINEARS):
             mode = tp.LLAMA_PLAN[name]
             sh = tp.shard_bounds(n, k, mode, rank, world, GROUP)
@@ -188,8 +192,15 @@ def run_ours(args):
             wl = w[sh.n0:sh.n1, sh.k0:sh.k1].contiguous()
             pw, _ = q100.pack_weight(wl, WBITS, GROUP)
             blk[name] = (pw, mode)
-            del w, wl
+            shards[name] = wl
+            del w
         blocks.append(blk)
+        fblk = {}
+        for fname, parts, _ in FUSED:
+            wl = torch.cat([shards[p_] for p_ in parts], dim=0) if len(parts) > 1 else shards[parts[0]]
+            fblk[fname] = (q100.pack_weight(wl, WBITS, GROUP)[0], tp.LLAMA_PLAN[parts[0]])
+        fblocks.append(fblk)
+        del shards
     torch.cuda.synchronize()
 
     def make_inputs(M):
@@ -253,25 +264,86 @@ def run_ours(args):
                 "frac_of_sustained": ach / P["tc_sustained"]}
 
     # =============== decode shapes: packed-weight stream GB/s ===============
+    # One decode step of the block's linears = 4 launches (q|k|v, o, gate|up, down), captured for all NB
+    # weight sets in one CUDA graph with programmatic dependent launch, so that each kernel's weight
+    # stream starts while its predecessor drains.  "api" = the same step as 7 separate un-graphed calls.
     decode = {}
-    for M in (1, 16):
+    dflags = flags | _lib.GEMM_PDL
+    for M in (1, 4, 16):
         xd = make_inputs(M)
+
+        def fused_step(fb):
+            for fname, parts, src in FUSED:
+                pw, mode = fb[fname]
+                x = tp.shard_input(xd[src], mode, rank, world) if world > 1 else xd[src]
+                y = q100.gemm_wna16(x, pw, None, dflags)
+                tp.reduce_output(y, mode)
+
+        for fb in fblocks:
+            fused_step(fb)
+        sync_all()
+        graph = None
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                fused_step(fblocks[0])
+            torch.cuda.current_stream().wait_stream(side)
+            sync_all()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                for fb in fblocks:
+                    fused_step(fb)
+            graph.replay()
+            sync_all()
+            msd = timed(graph.replay, 20) / NB
+        except Exception as ex:                                   # e.g. a collective that cannot be captured
+            graph = None
+            jt = [0]
+
+            def dstep():
+                fused_step(fblocks[jt[0] % NB])
+                jt[0] += 1
+            msd = timed(dstep, 30)
+        t = torch.tensor([msd], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        msd = float(t.item())
+        esz = 2
+        byts = sum(fblocks[0][fn][0].nbytes() + M * fblocks[0][fn][0].K * esz + M * fblocks[0][fn][0].N * esz
+                   for fn, *_ in FUSED)
+        gbs = byts * world / (msd * 1e-3) / 1e9
+        # per-launch times of the fused kernels (events around single launches, weight sets rotated)
+        per = {}
+        if rank == 0:
+            for fname, parts, src in FUSED:
+                x = tp.shard_input(xd[src], fblocks[0][fname][1], rank, world) if world > 1 else xd[src]
+                kt = [0]
+
+                def one():
+                    q100.gemm_wna16(x, fblocks[kt[0] % NB][fname][0], None, flags)
+                    kt[0] += 1
+                for _ in range(3):
+                    one()
+                torch.cuda.synchronize()
+                m1 = timed(one, 12)
+                nb_ = fblocks[0][fname][0].nbytes()
+                per[fname] = {"us": m1 * 1e3, "GBps": nb_ / (m1 * 1e-3) / 1e9, "frac_hbm": nb_ / (m1 * 1e-3) / 1e9 / P["hbm"]}
         jt = [0]
 
-        def dstep():
+        def api_step():
             block_step(blocks[jt[0] % NB], xd)
             jt[0] += 1
-
-        for _ in range(6):
-            dstep()
+        for _ in range(3):
+            api_step()
         sync_all()
-        msd = timed(dstep, 30)
-        esz = 2
-        byts = sum(blocks[0][nm][0].nbytes() + M * blocks[0][nm][0].K * esz + M * blocks[0][nm][0].N * esz
-                   for nm, *_ in LINEARS)
-        gbs = byts / (msd * 1e-3) / 1e9
-        decode[f"M{M}"] = {"ms_per_block": msd, "algorithmic_MB": byts / 1e6, "GBps": gbs, "frac_hbm": gbs / P["hbm"],
-                           "launches_per_block": 7}
+        ms_api = timed(api_step, 20)
+        decode[f"M{M}"] = {"ms_per_block": msd, "algorithmic_MB_per_gpu": byts / 1e6, "GBps": gbs,
+                           "frac_hbm": gbs / (P["hbm"] * world), "launches_per_block": len(FUSED),
+                           "cuda_graph": graph is not None, "pdl": True,
+                           "linear_tokens_per_s_32_blocks": M / (32 * msd * 1e-3),
+                           "per_launch": per, "api_7_launches_ms_per_block": ms_api}
+        del graph
 
     # =============== quantize kernel (K1): fake-quant and pack modes on up_proj ===============
     quant = {}

@@ -62,6 +62,8 @@ enum q100_status {
 #define Q100_GEMM_FORCE_STREAM_TC 0x20 /* decode shapes: the tcgen05 streaming kernel (weights as the TMEM A
                                       operand) wherever it applies (M <= 16, W2/W4, group % 128 == 0);
                                       default: 8 < M <= 16                                           */
+#define Q100_GEMM_FORCE_TC_SMEM 0x40 /* prefill: the first tcgen05 kernel (dequantised weights staged in
+                                      shared memory as the B operand) instead of the TMEM-A kernel      */
 #define Q100_GEMM_PDL          0x8 /* launch with programmatic stream serialization: the kernel starts
                                       streaming its (static) weights while the previous kernel of the
                                       stream drains, and waits (griddepcontrol.wait) before it touches

@@ -26,6 +26,10 @@ int gemm_tc(const void* x, const void* packed, const void* meta, const void* bia
 bool gemm_tc_supported(int64_t M, int64_t N, int64_t K, int group, int n_bits);
 int gemm_tc_dense(const void* x, const void* w, void* y, int64_t M, int64_t N, int64_t K, int dtype,
                   cudaStream_t st);
+int gemm_tca(const void* x, const void* packed, const void* meta, const void* bias, void* y,
+             int64_t M, int64_t N, int64_t K, int group, int n_bits, int disable_zp, int dtype,
+             cudaStream_t st);
+bool gemm_tca_supported(int64_t M, int64_t N, int64_t K, int group, int n_bits);
 
 // ---------------------------------------------------------------- tensor maps
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
@@ -93,11 +97,14 @@ extern "C" int q100_gemm_wna16(const void* x, const void* packed, const void* me
   if (rc != Q100_OK) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool skinny_ok = (K % 128 == 0) && (N % 8 == 0);
-  const bool tc_ok = gemm_tc_supported(M, N, K, group, n_bits);
+  // prefill: K3b' (weights as the TMEM A operand); K3b (dequantised weights through shared memory) on request
+  const bool tca_ok = gemm_tca_supported(M, N, K, group, n_bits) && !(flags & Q100_GEMM_FORCE_TC_SMEM);
+  const bool tc_ok = tca_ok || gemm_tc_supported(M, N, K, group, n_bits);
   const bool want_tc = (flags & Q100_GEMM_FORCE_TC) ||
                        (!(flags & Q100_GEMM_FORCE_SKINNY) && tc_ok && (M > 32 || !skinny_ok));
   if (want_tc) {
     Q100_REQUIRE(tc_ok, Q100_EUNSUPPORTED, "tcgen05 path does not support this shape/bit-width");
+    if (tca_ok) return gemm_tca(x, packed, meta, bias, y, M, N, K, group, n_bits, disable_zp, dtype, st);
     return gemm_tc(x, packed, meta, bias, y, M, N, K, group, n_bits, disable_zp, dtype, st);
   }
   // decode shapes: tcgen05 weight-streaming kernel (weights as the TMEM A operand)

@@ -1,0 +1,408 @@
+// q100_gemm_tca.cu -- K3b': persistent tcgen05 dequant-GEMM for prefill shapes, weights as the A operand
+// in TENSOR MEMORY.
+//
+//   y[M, N] = x[M, K] . dequant(W)[N, K]^T (+ bias)        quant/int_linear.py:62
+//
+// Why a second prefill kernel: ncu on K3b (q100_gemm_tc.cu; profiles/r01f) shows the tensor pipe 45 % busy
+// with the shared-memory pipe as the limiter -- per 64-wide k block it moves 32 KB of x in, 32 KB of x out
+// to the tensor core, 16 KB of dequantised weights in and 32 KB of them out again (two M halves), 236 bytes
+// per tensor-core cycle against 128 B/clk of shared-memory bandwidth.  Here the dequantised weights never
+// touch shared memory: the dequant warps write them straight into tensor memory (tcgen05.st) and the MMA
+// reads its A operand from there, so shared memory only carries the x tile (TMA in, tensor core out) and
+// the packed codes: 143 bytes per tensor-core cycle at a [128 rows x 256 tokens] tile.
+//
+// Per CTA (one per SM, persistent over [128 weight rows x NT tokens] output tiles, token tiles fastest so
+// that CTAs running at the same time share weight tiles in L2), BK = 64:
+//   warp 12     TMA producer of the x ring: [NT tokens x 64 k] boxes, SWIZZLE_128B = the K-major B operand;
+//   warp 14     bulk-copy producer of the packed ring: the tile's [128 x 64] code tile (one contiguous run in
+//               the tile-major layout) + its (scale, zero) row;
+//   warps 0-7   two dequant groups of four warps alternating k blocks; thread = weight row: 32 bytes of
+//               codes -> registers -> r(r(q - zp) * scale) in packed 16-bit arithmetic (bit-identical to the
+//               reference's fake-quantised weight) -> tcgen05.st into one of four A stages (32 columns);
+//   warp 13     allocates TMEM (512 columns: D = NT fp32 columns, A ring = 4 x 32); one elected thread issues
+//               4 x tcgen05.mma (M = 128, N = NT, K = 16, A from TMEM, B from shared memory) per k block,
+//               tcgen05.commit frees the A stage and the x stage / publishes the accumulator;
+//   warps 8-11  epilogue: tcgen05.ld (lane = weight row, column = token) -> (+bias) -> bf16/fp16 -> global.
+#include "q100_common.cuh"
+#include "q100_ptx.cuh"
+
+namespace q100 {
+
+constexpr int TA_ROWS = 128;          // weight rows per tile (UMMA M)
+constexpr int TA_BK = 64;
+constexpr int TA_SA = 4;              // A stages in tensor memory
+constexpr int TA_SP = 8;              // packed-code stages
+constexpr int TA_DQ_WARPS = 8;
+constexpr int TA_EPI_WARP0 = 8;
+constexpr int TA_TMAX_WARP = 12, TA_MMA_WARP = 13, TA_TMAP_WARP = 14;
+constexpr int TA_THREADS = 15 * 32;
+constexpr uint32_t TA_TMEM_COLS = 512;
+constexpr uint32_t TA_COL_A = 256;    // A ring starts after the (up to) 256 accumulator columns
+
+struct TcaArgs {
+  const void* packed;
+  const void* meta;
+  const void* bias;
+  void* y;
+  int M, N, K, group;
+  int has_zp;
+  float qmin;
+  int m_tiles, n_tiles;
+};
+
+template <int NBITS, int NT>
+struct TcaSmem {
+  static constexpr int kX = NT * TA_BK * 2;                           // x stage
+  static constexpr int kP = TA_ROWS * TA_BK * NBITS / 8;              // packed codes of a stage
+  static constexpr int kPStage = kP + 512;
+  static constexpr int kBudget = 225 * 1024;
+  static constexpr int kSX = (kBudget - TA_SP * kPStage) / kX > 6 ? 6 : (kBudget - TA_SP * kPStage) / kX;
+  static constexpr int kOffP = kSX * kX;
+  static constexpr int kTotal = kOffP + TA_SP * kPStage + 1024;
+  static_assert(kSX >= 3, "x ring too shallow");
+  static_assert(kTotal <= 227 * 1024, "shared memory budget");
+};
+
+template <typename T> struct TaDQ;
+template <> struct TaDQ<__half> {
+  using T2 = __half2;
+  static constexpr uint32_t kMagic = 0x64006400u;
+  static constexpr float kMagicF = 1024.0f;
+  static constexpr float kFastZp = 1000.0f;            // |zp| below this: magic + zp is exact
+  __device__ static __forceinline__ T2 bcast(float v) { return __float2half2_rn(v); }
+};
+template <> struct TaDQ<__nv_bfloat16> {
+  using T2 = __nv_bfloat162;
+  static constexpr uint32_t kMagic = 0x43004300u;
+  static constexpr float kMagicF = 128.0f;
+  static constexpr float kFastZp = 112.0f;
+  __device__ static __forceinline__ T2 bcast(float v) { return __float2bfloat162_rn(v); }
+};
+
+__device__ __forceinline__ uint32_t ta_reg(uint32_t v) {
+  uint32_t d;
+  asm volatile("mov.b32 %0, %1;" : "=r"(d) : "r"(v));
+  return d;
+}
+template <int SH>
+__device__ __forceinline__ uint32_t ta_shr(uint32_t w) {              // w >> SH on the FMA pipe
+  if (SH == 0) return w;
+  uint32_t d;
+  asm("mul.hi.u32 %0, %1, %2;" : "=r"(d) : "r"(w), "n"(SH == 0 ? 1u : (1u << (32 - SH))));
+  return d;
+}
+template <uint32_t MASK>
+__device__ __forceinline__ uint32_t ta_and_or(uint32_t w, uint32_t orv) {
+  uint32_t d;
+  asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(w), "n"(MASK), "r"(orv));
+  return d;
+}
+__device__ __forceinline__ void ta_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t}\n"
+      :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void ta_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+
+// column c (pair of k = 2c, 2c+1 inside the 64-k block) of a row's codes, as (MAGIC | q) or raw pair
+template <int NBITS>
+__device__ __forceinline__ uint32_t ta_pair_magic(const uint32_t* w, int c, uint32_t magic) {
+  if (NBITS == 4) {
+    const int i = c >> 2, j = c & 3;
+    return j == 0 ? ta_and_or<0x000f000fu>(w[i], magic)
+         : j == 1 ? ta_and_or<0x000f000fu>(ta_shr<4>(w[i]), magic)
+         : j == 2 ? ta_and_or<0x000f000fu>(ta_shr<8>(w[i]), magic)
+                  : ta_and_or<0x000f000fu>(ta_shr<12>(w[i]), magic);
+  } else if (NBITS == 2) {
+    const int i = c >> 3, j = c & 7;
+    const uint32_t x = j == 0 ? w[i] : j == 1 ? ta_shr<2>(w[i]) : j == 2 ? ta_shr<4>(w[i]) : j == 3 ? ta_shr<6>(w[i])
+                     : j == 4 ? ta_shr<8>(w[i]) : j == 5 ? ta_shr<10>(w[i]) : j == 6 ? ta_shr<12>(w[i]) : ta_shr<14>(w[i]);
+    return ta_and_or<0x00030003u>(x, magic);
+  } else {   // 8 bits: pair = (w >> 8j) & 0x00ff00ff
+    const int i = c >> 1, j = c & 1;
+    return __byte_perm(w[i], magic, j ? 0x7371 : 0x7270);
+  }
+}
+
+template <typename T, int NBITS, int NT>
+__global__ void __launch_bounds__(TA_THREADS, 1)
+k3_tca(const __grid_constant__ CUtensorMap tm_x, const TcaArgs a) {
+  using SM = TcaSmem<NBITS, NT>;
+  using DQ = TaDQ<T>;
+  using T2 = typename DQ::T2;
+  constexpr bool kBf16 = DT<T>::kCode == Q100_BF16;
+  constexpr int SX = SM::kSX;
+  constexpr int NW = SM::kP / TA_ROWS / 4;             // code words per row per k block (W4: 8)
+
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const uint32_t base_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  __shared__ uint64_t bars[SX + SX + TA_SP + TA_SP + TA_SA + TA_SA + 2];
+  __shared__ uint32_t tmem_base_s;
+  const uint32_t b0 = smem_u32(&bars[0]);
+  const uint32_t full_x = b0, empty_x = full_x + 8 * SX, full_p = empty_x + 8 * SX, empty_p = full_p + 8 * TA_SP;
+  const uint32_t a_full = empty_p + 8 * TA_SP, a_empty = a_full + 8 * TA_SA, d_full = a_empty + 8 * TA_SA, d_empty = d_full + 8;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int num_kb = a.K / TA_BK;
+  const int n_tiles_total = a.m_tiles * a.n_tiles;
+
+  if (tid == 0) {
+    for (int s = 0; s < SX; ++s) { mbar_init(&bars[s], 1); mbar_init(&bars[SX + s], 1); }
+    for (int s = 0; s < TA_SP; ++s) { mbar_init(&bars[2 * SX + s], 1); mbar_init(&bars[2 * SX + TA_SP + s], 4); }
+    for (int s = 0; s < TA_SA; ++s) { mbar_init(&bars[2 * SX + 2 * TA_SP + s], 4); mbar_init(&bars[2 * SX + 2 * TA_SP + TA_SA + s], 1); }
+    mbar_init(&bars[2 * SX + 2 * TA_SP + 2 * TA_SA], 1);        // d_full
+    mbar_init(&bars[2 * SX + 2 * TA_SP + 2 * TA_SA + 1], 4);    // d_empty
+    fence_mbar_init();
+  }
+  if (warp == TA_MMA_WARP) tmem_alloc(&tmem_base_s, TA_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+
+  if (warp == TA_TMAX_WARP) {
+    // ===================== TMA producer: x tiles =====================
+    if (lane == 0) {
+      tma_prefetch_desc(&tm_x);
+      const uint64_t pol_x = policy_evict_last();
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+        const int m0 = (tile % a.m_tiles) * NT;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % SX;
+          ta_wait(empty_x + 8 * s, ((it / SX) & 1) ^ 1);
+          mbar_expect_tx(&bars[s], SM::kX);
+          tma_load_2d_hint(reinterpret_cast<void*>(smem_raw + (base_u32 - smem_u32(smem_raw)) + s * SM::kX), &tm_x, &bars[s],
+                           kb * TA_BK, m0, pol_x);
+        }
+      }
+    }
+  } else if (warp == TA_TMAP_WARP) {
+    // ===================== producer: packed codes + side band =====================
+    if (lane == 0) {
+      const uint64_t pol_w = policy_evict_first();
+      uint8_t* pbase = smem_raw + (base_u32 - smem_u32(smem_raw)) + SM::kOffP;
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+        const int nt = tile / a.m_tiles;
+        const int n0 = nt * TA_ROWS;
+        const int mbytes = min(TA_ROWS, a.N - n0) * 4;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % TA_SP;
+          ta_wait(empty_p + 8 * s, ((it / TA_SP) & 1) ^ 1);
+          uint8_t* st = pbase + s * SM::kPStage;
+          mbar_expect_tx(&bars[2 * SX + s], SM::kP + mbytes);
+          const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(a.packed) + (static_cast<int64_t>(nt) * num_kb + kb) * SM::kP;
+          bulk_load_1d_hint(st, wsrc, SM::kP, &bars[2 * SX + s], pol_w);
+          const int kg = (kb * TA_BK) / a.group;
+          const T* src = reinterpret_cast<const T*>(a.meta) + (static_cast<int64_t>(kg) * a.N + n0) * 2;
+          bulk_load_1d(st + SM::kP, src, mbytes, &bars[2 * SX + s]);
+        }
+      }
+    }
+  } else if (warp == TA_MMA_WARP) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc_f16(kBf16 ? 1 : 0, TA_ROWS, NT);
+    uint32_t it = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++tcount) {
+      ta_wait(d_empty, (tcount & 1) ^ 1);            // the epilogue has drained the accumulator
+      tc_fence_after();
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const uint32_t sx = it % SX, sa = it % TA_SA;
+        ta_wait(a_full + 8 * sa, (it / TA_SA) & 1);
+        ta_wait(full_x + 8 * sx, (it / SX) & 1);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint64_t bd = umma_desc_sw128_u32(base_u32 + sx * SM::kX);
+          const uint32_t at = tmem + TA_COL_A + sa * 32;
+#pragma unroll
+          for (int k = 0; k < TA_BK / 16; ++k)
+            umma_f16_ts(tmem, at + 8 * k, bd + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_commit_u32(a_empty + 8 * sa);
+          umma_commit_u32(empty_x + 8 * sx);
+          if (kb == num_kb - 1) umma_commit_u32(d_full);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < TA_DQ_WARPS) {
+    // ===================== dequant warps: group g handles iterations it % 2 == g; thread = weight row =====================
+    const int grp = warp >> 2;
+    const int row = tid & 127;
+    const uint32_t lane_t = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16) + TA_COL_A;
+    const uint32_t qb = DT<T>::pack2(a.qmin, a.qmin);
+    const T2 qmin2 = *reinterpret_cast<const T2*>(&qb);
+    const T2 magic2 = DQ::bcast(DQ::kMagicF);
+    const uint32_t magic = ta_reg(DQ::kMagic);
+    const bool has_zp = a.has_zp != 0;
+    const uint32_t code_off = ta_reg(base_u32 + SM::kOffP + row * (NW * 4));
+    const uint32_t meta_off = ta_reg(base_u32 + SM::kOffP + SM::kP + row * 4);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        if (static_cast<int>(it & 1) != grp) continue;
+        const uint32_t sp = it % TA_SP, sa = it % TA_SA;
+        ta_wait(full_p + 8 * sp, (it / TA_SP) & 1);
+        uint32_t w[NW];
+#pragma unroll
+        for (int i = 0; i < NW / 4; ++i) {
+          uint4 v;
+          asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(code_off + sp * SM::kPStage + i * 16));
+          w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+        }
+        uint32_t m;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(m) : "r"(meta_off + sp * SM::kPStage));
+        __syncwarp();
+        if (lane == 0) ta_arrive(empty_p + 8 * sp);          // the codes are in registers
+        const uint32_t sb2 = __byte_perm(m, 0, 0x1010), zb = __byte_perm(m, 0, 0x3232);
+        const T2 s2 = *reinterpret_cast<const T2*>(&sb2), z2 = *reinterpret_cast<const T2*>(&zb);
+        const float zf = DT<T>::to_f(*reinterpret_cast<const T*>(&zb));
+        // fast path: magic + zp (or magic - qmin) is an exactly representable integer; warp-uniform choice
+        const bool fast = __all_sync(0xffffffffu, !has_zp || fabsf(zf) <= DQ::kFastZp);
+        const T2 sub2 = DQ::bcast(DQ::kMagicF + (has_zp ? zf : -a.qmin));
+        uint32_t av[32];
+        if constexpr (NBITS == 8 && kBf16) {
+          // 8-bit codes do not fit bf16's OR-magic trick (128 + q needs 9 significant bits): go through fp32
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const uint32_t pr = (w[c >> 1] >> (8 * (c & 1))) & 0x00ff00ffu;
+            const uint32_t cb = DT<T>::pack2(static_cast<float>(pr & 0xffffu), static_cast<float>(pr >> 16));
+            T2 v = *reinterpret_cast<const T2*>(&cb);
+            v = has_zp ? __hsub2(v, z2) : __hadd2(v, qmin2);
+            v = __hmul2(v, s2);
+            av[c] = *reinterpret_cast<uint32_t*>(&v);
+          }
+        } else if (fast) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const uint32_t pm = ta_pair_magic<NBITS>(w, c, magic);
+            T2 v = __hsub2(*reinterpret_cast<const T2*>(&pm), sub2);       // (magic + q) - (magic + zp): exact
+            v = __hmul2(v, s2);                                            // r(. * scale)
+            av[c] = *reinterpret_cast<uint32_t*>(&v);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const uint32_t pm = ta_pair_magic<NBITS>(w, c, magic);
+            T2 v = __hsub2(*reinterpret_cast<const T2*>(&pm), magic2);     // exact
+            v = has_zp ? __hsub2(v, z2) : __hadd2(v, qmin2);               // r(q - zp)
+            v = __hmul2(v, s2);
+            av[c] = *reinterpret_cast<uint32_t*>(&v);
+          }
+        }
+        ta_wait(a_empty + 8 * sa, ((it / TA_SA) & 1) ^ 1);   // the tensor core is done with this A stage
+        tc_fence_after();
+        tmem_st_32x32b_x32(lane_t + sa * 32, av);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ta_arrive(a_full + 8 * sa);
+      }
+    }
+  } else {
+    // ===================== epilogue warps (8..11): lane = weight row, columns = tokens =====================
+    const int quad = warp & 3;
+    const T* bias = reinterpret_cast<const T*>(a.bias);
+    const uint32_t lane_t = tmem + (static_cast<uint32_t>(quad * 32) << 16);
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++tcount) {
+      const int m0 = (tile % a.m_tiles) * NT;
+      const int n = (tile / a.m_tiles) * TA_ROWS + quad * 32 + lane;
+      ta_wait(d_full, tcount & 1);
+      tc_fence_after();
+      const float bv = (bias != nullptr && n < a.N) ? DT<T>::to_f(bias[n]) : 0.f;
+      T* ycol = reinterpret_cast<T*>(a.y) + n;
+#pragma unroll 1
+      for (int c0 = 0; c0 < NT; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(lane_t + c0, r);
+        tmem_ld_wait();
+        if (c0 + 32 >= NT) {                         // last chunk read: the accumulator may be overwritten
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ta_arrive(d_empty);
+        }
+        if (n < a.N) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int m = m0 + c0 + j;
+            if (m < a.M) ycol[static_cast<int64_t>(m) * a.N] = DT<T>::from_f(__uint_as_float(r[j]) + bv);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == TA_MMA_WARP) {
+    tc_fence_after();
+    tmem_dealloc(tmem, TA_TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------- host
+bool gemm_tca_supported(int64_t M, int64_t N, int64_t K, int group, int n_bits) {
+  const int64_t g = group == 0 ? K : group;
+  return (n_bits == 4 || n_bits == 2 || n_bits == 8) && M >= 1 && N % 8 == 0 && K % TA_BK == 0 &&
+         g % TA_BK == 0 && K % g == 0;
+}
+
+template <typename T, int NBITS, int NT>
+static int launch_tca(const void* x, TcaArgs a, cudaStream_t st) {
+  using SM = TcaSmem<NBITS, NT>;
+  auto kern = k3_tca<T, NBITS, NT>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    Q100_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
+    attr_done = true;
+  }
+  CUtensorMap tx;
+  int rc = make_tmap_2d(&tx, x, 2, a.K, a.M, static_cast<uint64_t>(a.K) * 2, TA_BK, NT, 128);
+  if (rc != Q100_OK) return rc;
+  a.m_tiles = (a.M + NT - 1) / NT;
+  a.n_tiles = (a.N + TA_ROWS - 1) / TA_ROWS;
+  int grid = a.m_tiles * a.n_tiles;
+  const int sms = sm_count();
+  if (grid > sms) grid = sms;
+  kern<<<grid, TA_THREADS, SM::kTotal, st>>>(tx, a);
+  return check_cuda(cudaGetLastError(), "k3_tca launch");
+}
+
+template <typename T, int NBITS>
+static int gemm_tca_nt(const void* x, const TcaArgs& a, cudaStream_t st) {
+  if (a.M <= 128) return launch_tca<T, NBITS, 128>(x, a, st);
+  return launch_tca<T, NBITS, 256>(x, a, st);
+}
+
+template <typename T>
+static int gemm_tca_t(const void* x, const TcaArgs& a, int n_bits, cudaStream_t st) {
+  switch (n_bits) {
+    case 2: return gemm_tca_nt<T, 2>(x, a, st);
+    case 8: return gemm_tca_nt<T, 8>(x, a, st);
+    default: return gemm_tca_nt<T, 4>(x, a, st);
+  }
+}
+
+int gemm_tca(const void* x, const void* packed, const void* meta, const void* bias, void* y,
+             int64_t M, int64_t N, int64_t K, int group, int n_bits, int disable_zp, int dtype,
+             cudaStream_t st) {
+  Q100_REQUIRE(gemm_tca_supported(M, N, K, group, n_bits), Q100_EUNSUPPORTED, "tcgen05 (TMEM-A) path: unsupported shape");
+  TcaArgs a{};
+  a.packed = packed; a.meta = meta; a.bias = bias; a.y = y;
+  a.M = static_cast<int>(M); a.N = static_cast<int>(N); a.K = static_cast<int>(K);
+  a.group = group == 0 ? static_cast<int>(K) : group;
+  a.has_zp = disable_zp ? 0 : 1;
+  a.qmin = disable_zp ? -static_cast<float>(1 << (n_bits - 1)) : 0.0f;
+  if (dtype == Q100_F16) return gemm_tca_t<__half>(x, a, n_bits, st);
+  return gemm_tca_t<__nv_bfloat16>(x, a, n_bits, st);
+}
+
+}  // namespace q100

@@ -16,6 +16,8 @@
 //                 q = x*rcp(s); q += fma(-q, s, x)*rcp(s), which rounds to the same
 //                 16-bit value as div.rn.f32 (checked exhaustively by q100_selftest_div).
 // Compile this file with -fmad=false: no implicit contraction may merge the per-op steps.
+#include <type_traits>
+
 #include "q100_common.cuh"
 
 namespace q100 {
@@ -115,6 +117,7 @@ __device__ __forceinline__ float quant_scalar(float x, const GroupQ<T>& q, const
 template <int MATH>
 struct VecQuant<float, MATH> {
   static constexpr int E = 4;
+  template <bool WANT_DEQ, bool WANT_CODES, bool FAST = false>
   __device__ static __forceinline__ uint4 run(const uint4& in, const GroupQ<float>& q,
                                               const QuantArgs& a, uint32_t (&pairs)[2]) {
     uint32_t c0, c1, c2, c3;
@@ -136,15 +139,29 @@ struct Packed16<__half> {
   using T2 = __half2;
   __device__ static __forceinline__ T2 bcast(float v) { return __float2half2_rn(v); }
   __device__ static __forceinline__ T2 rint2(T2 v) { return h2rint(v); }
+  // (v + C) - C == rint(v) (ties to even, -0 -> +0) for |v| <= kFastLimit: C = 1.5 * 2^10
+  static constexpr float kRintMagic = 1536.0f, kFastLimit = 500.0f;
 };
 template <>
 struct Packed16<__nv_bfloat16> {
   using T2 = __nv_bfloat162;
   __device__ static __forceinline__ T2 bcast(float v) { return __float2bfloat162_rn(v); }
   __device__ static __forceinline__ T2 rint2(T2 v) { return h2rint(v); }
+  static constexpr float kRintMagic = 192.0f, kFastLimit = 60.0f;       // C = 1.5 * 2^7
 };
 
-template <typename T, int MATH>
+template <typename T> struct FastLimit { static constexpr float value = 0.0f; };
+template <> struct FastLimit<__half> { static constexpr float value = 500.0f; };
+template <> struct FastLimit<__nv_bfloat16> { static constexpr float value = 60.0f; };
+template <typename T> struct CodeMagic;
+template <> struct CodeMagic<__half> { static constexpr float kMagic = 1024.0f; static constexpr uint32_t kMask = 0x03ff03ffu; };
+template <> struct CodeMagic<__nv_bfloat16> { static constexpr float kMagic = 128.0f; static constexpr uint32_t kMask = 0x007f007fu; };
+
+// One pair of elements.  Returns the dequantised pair (only computed when WANT_DEQ) and, when
+// WANT_CODES, pair = code[0] | code[1] << 16 with code = x_int - qmin (NaN -> 0).
+// FAST (warp-uniform, decided per step): every |x / scale| of the step is small enough for the magic-add
+// rint below, which yields exactly round_ste's forward value for finite inputs of that size.
+template <typename T, int MATH, bool WANT_DEQ, bool WANT_CODES, bool FAST = false>
 __device__ __forceinline__ uint32_t quant_pair(uint32_t in, const GroupQ<T>& q, const QuantArgs& a,
                                                uint32_t& pair) {
   using D = DT<T>;
@@ -164,15 +181,28 @@ __device__ __forceinline__ uint32_t quant_pair(uint32_t in, const GroupQ<T>& q, 
     uint32_t vb = D::pack2(q0, q1);                         // rd(x / scale), both lanes
     const T2 v = *reinterpret_cast<T2*>(&vb);
     // round_ste: rint(v) + (v - v): +0 for finite v (so -0 becomes +0), NaN for inf/NaN
-    T2 xi = __hadd2(P::rint2(v), __hsub2(v, v));
+    T2 xi;
+    if (FAST) xi = __hsub2(__hadd2(v, P::bcast(P::kRintMagic)), P::bcast(P::kRintMagic));
+    else xi = __hadd2(P::rint2(v), __hsub2(v, v));
     const T2 zp2 = P::bcast(q.zp);
     if (a.has_zp) xi = __hadd2(xi, zp2);
     const T2 c = __hmin2_nan(__hmax2_nan(xi, P::bcast(a.qmin)), P::bcast(a.qmax));
-    // unsigned codes through fp32 (exact: |c| <= 2^15)
-    uint32_t cb = *reinterpret_cast<const uint32_t*>(&c);
-    const float2 cf = D::to_f2(cb);
-    pair = static_cast<uint32_t>(__float2int_rn(cf.x - a.qmin)) |
-           (static_cast<uint32_t>(__float2int_rn(cf.y - a.qmin)) << 16);
+    if (WANT_CODES) {
+      if (a.n_bits < 8 || D::kCode == Q100_F16) {
+        // integer-valued c in [qmin, qmax]: c - qmin + MAGIC is exact and carries the code in its low
+        // mantissa bits; the non-propagating max turns NaN into qmin, i.e. code 0
+        const T2 cc = __hmax2(c, P::bcast(a.qmin));
+        const T2 m = __hadd2(cc, P::bcast(CodeMagic<T>::kMagic - a.qmin));
+        pair = *reinterpret_cast<const uint32_t*>(&m) & CodeMagic<T>::kMask;
+      } else {
+        // bf16, 8-bit codes: 128 + code is not representable; go through fp32 (exact: |c| <= 2^15)
+        uint32_t cb = *reinterpret_cast<const uint32_t*>(&c);
+        const float2 cf = D::to_f2(cb);
+        pair = static_cast<uint32_t>(__float2int_rn(cf.x - a.qmin)) |
+               (static_cast<uint32_t>(__float2int_rn(cf.y - a.qmin)) << 16);
+      }
+    }
+    if (!WANT_DEQ) return 0u;
     T2 d = a.has_zp ? __hsub2(c, zp2) : c;
     d = __hmul2(d, P::bcast(q.scale));
     return *reinterpret_cast<uint32_t*>(&d);
@@ -182,13 +212,14 @@ __device__ __forceinline__ uint32_t quant_pair(uint32_t in, const GroupQ<T>& q, 
 template <typename T, int MATH>
 struct VecQuant {
   static constexpr int E = 8;
+  template <bool WANT_DEQ, bool WANT_CODES, bool FAST = false>
   __device__ static __forceinline__ uint4 run(const uint4& in, const GroupQ<T>& q,
                                               const QuantArgs& a, uint32_t (&pairs)[4]) {
     uint4 o;
-    o.x = quant_pair<T, MATH>(in.x, q, a, pairs[0]);
-    o.y = quant_pair<T, MATH>(in.y, q, a, pairs[1]);
-    o.z = quant_pair<T, MATH>(in.z, q, a, pairs[2]);
-    o.w = quant_pair<T, MATH>(in.w, q, a, pairs[3]);
+    o.x = quant_pair<T, MATH, WANT_DEQ, WANT_CODES, FAST>(in.x, q, a, pairs[0]);
+    o.y = quant_pair<T, MATH, WANT_DEQ, WANT_CODES, FAST>(in.y, q, a, pairs[1]);
+    o.z = quant_pair<T, MATH, WANT_DEQ, WANT_CODES, FAST>(in.z, q, a, pairs[2]);
+    o.w = quant_pair<T, MATH, WANT_DEQ, WANT_CODES, FAST>(in.w, q, a, pairs[3]);
     return o;
   }
 };
@@ -282,6 +313,16 @@ __device__ __forceinline__ void emit_packed(const uint32_t (&pairs)[E / 2], cons
   }
 }
 
+// W4, 16-bit input: a vector of 8 elements is exactly one packed word (4 pairs, 4 bits apart); the
+// shifts-and-adds run as IMADs on the FMA pipe.  Same word, same address as emit_packed<8>.
+__device__ __forceinline__ void emit_packed_w4(const uint32_t (&pairs)[4], const QuantArgs& a,
+                                               int row, int vec_in_row) {
+  const int e0 = vec_in_row * 8;
+  uint32_t* tile = a.packed + (static_cast<int64_t>(row >> 7) * a.k_tiles + (e0 >> 6)) * (128 * 8);
+  const uint32_t w = pairs[0] + pairs[1] * 16u + pairs[2] * 256u + pairs[3] * 4096u;
+  tile[(row & 127) * 8 + ((e0 & 63) >> 3)] = w;
+}
+
 template <typename T>
 __device__ __forceinline__ void store_group_meta(const QuantArgs& a, int64_t g, const GroupQ<T>& q) {
   using D = DT<T>;
@@ -297,8 +338,10 @@ __device__ __forceinline__ void store_group_meta(const QuantArgs& a, int64_t g, 
 }
 
 // ------------------------------------------------------------------ K1: L lanes x V vectors per group
-template <typename T, int L, int V, int MATH, bool PACK>
+// PB: 0 = no packed output, 1 = packed, any bit width (runtime), 4 = packed W4 from a 16-bit dtype
+template <typename T, int L, int V, int MATH, int PB>
 __global__ void __launch_bounds__(256) k1_groups(const QuantArgs a) {
+  constexpr bool PACK = PB != 0;
   constexpr int E = DT<T>::kVec;
   constexpr int GPW = 32 / L;                       // groups per warp step
   const int lane = threadIdx.x & 31;
@@ -348,13 +391,26 @@ __global__ void __launch_bounds__(256) k1_groups(const QuantArgs a) {
       row = gi / a.groups_per_row;
       vec0 = (gi - row * a.groups_per_row) * (L * V);
     }
-#pragma unroll
-    for (int k = 0; k < V; ++k) {
-      uint32_t pairs[E / 2];
-      const uint4 o = VecQuant<T, MATH>::run(cur[k], q, a, pairs);
-      if (dq != nullptr && valid) stg_stream(dq + g * (L * V) + k * L + l, o);
-      if (PACK) emit_packed<E>(pairs, a, row, vec0 + k * L + l, valid && row < a.rows);
+    // magic-add rint is valid when every |x / scale| of the warp's groups is small (and finite)
+    bool fast = false;
+    if (MATH == MATH_PACKED && DT<T>::kCode != Q100_F32) {
+      const float lim = fmaxf(fabsf(mn), fabsf(mx)) * q.rcp;
+      fast = __all_sync(0xffffffffu, lim < FastLimit<T>::value);        // false for NaN
     }
+    auto body = [&](auto deq_tag, auto fast_tag) {
+      constexpr bool kDeq = decltype(deq_tag)::value, kFast = decltype(fast_tag)::value;
+#pragma unroll
+      for (int k = 0; k < V; ++k) {
+        uint32_t pairs[E / 2];
+        const uint4 o = VecQuant<T, MATH>::template run<kDeq, PACK, kFast>(cur[k], q, a, pairs);
+        if (kDeq && valid) stg_stream(dq + g * (L * V) + k * L + l, o);
+        if (PB == 4) { if (valid && row < a.rows) emit_packed_w4(*reinterpret_cast<uint32_t(*)[4]>(&pairs), a, row, vec0 + k * L + l); }
+        else if (PACK) emit_packed<E>(pairs, a, row, vec0 + k * L + l, valid && row < a.rows);
+      }
+    };
+    using TT = std::true_type; using FF = std::false_type;
+    if (dq != nullptr) { if (fast) body(TT{}, TT{}); else body(TT{}, FF{}); }
+    else { if (fast) body(FF{}, TT{}); else body(FF{}, FF{}); }
     if (l == 0 && valid) store_group_meta<T>(a, g, q);
 #pragma unroll
     for (int k = 0; k < V; ++k) cur[k] = nxt[k];
@@ -410,7 +466,7 @@ __global__ void __launch_bounds__(1024) k2_rows(const QuantArgs a) {
         const bool valid = idx < nvec;
         uint32_t pairs[E / 2];
         uint4 o = make_uint4(0, 0, 0, 0);
-        if (valid) o = VecQuant<T, MATH>::run(v[k], q, a, pairs);
+        if (valid) o = VecQuant<T, MATH>::template run<true, PACK>(v[k], q, a, pairs);
         else {
 #pragma unroll
           for (int j = 0; j < E / 2; ++j) pairs[j] = 0;
@@ -489,8 +545,10 @@ static int launch_k1_lv(const QuantArgs& a, bool pack, cudaStream_t st) {
   const int64_t cap = static_cast<int64_t>(sms) * 8;          // persistent: <= 8 CTAs / SM
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
-  if (pack) k1_groups<T, L, V, MATH, true><<<static_cast<unsigned>(blocks), 256, 0, st>>>(a);
-  else k1_groups<T, L, V, MATH, false><<<static_cast<unsigned>(blocks), 256, 0, st>>>(a);
+  constexpr bool k16 = DT<T>::kCode != Q100_F32;
+  if (!pack) k1_groups<T, L, V, MATH, 0><<<static_cast<unsigned>(blocks), 256, 0, st>>>(a);
+  else if (k16 && MATH == MATH_PACKED && a.n_bits == 4) k1_groups<T, L, V, MATH, (k16 && MATH == MATH_PACKED) ? 4 : 1><<<static_cast<unsigned>(blocks), 256, 0, st>>>(a);
+  else k1_groups<T, L, V, MATH, 1><<<static_cast<unsigned>(blocks), 256, 0, st>>>(a);
   return check_cuda(cudaGetLastError(), "k1_groups launch");
 }
 

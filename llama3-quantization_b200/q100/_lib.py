@@ -23,6 +23,7 @@ GEMM_EXACT_WEIGHTS = 0x4
 GEMM_PDL = 0x8
 GEMM_FORCE_MMA_SYNC = 0x10
 GEMM_FORCE_STREAM_TC = 0x20
+GEMM_FORCE_TC_SMEM = 0x40
 
 _vp, _i, _i64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
 

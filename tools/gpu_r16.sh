@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 300 python tools/profile_kernels.py --iters 3 --which tc > gpurun_out/plain_tc.log 2>&1 && \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:'k3_tc' -s 3 -c 1 -o gpurun_out/prof_r1f_tc python tools/profile_kernels.py --iters 3 --which tc > gpurun_out/ncu_tc.log 2>&1
+echo "rc=$?"; tail -2 gpurun_out/ncu_tc.log; cat gpurun_out/plain_tc.log
