@@ -1,6 +1,7 @@
 // q100_gemm.cu -- C-ABI front of the fused dequant-GEMM (K3): argument checks, path choice
 // (weight-streaming mma.sync kernel for decode shapes, tcgen05 kernel for prefill shapes),
 // and the host-side TMA descriptor encoder.
+#include <cstdlib>
 #include <mutex>
 
 #include <cudaTypedefs.h>
@@ -28,7 +29,7 @@ int gemm_tc_dense(const void* x, const void* w, void* y, int64_t M, int64_t N, i
                   cudaStream_t st);
 int gemm_tca(const void* x, const void* packed, const void* meta, const void* bias, void* y,
              int64_t M, int64_t N, int64_t K, int group, int n_bits, int disable_zp, int dtype,
-             cudaStream_t st);
+             int cluster, cudaStream_t st);
 bool gemm_tca_supported(int64_t M, int64_t N, int64_t K, int group, int n_bits);
 
 // ---------------------------------------------------------------- tensor maps
@@ -104,7 +105,14 @@ extern "C" int q100_gemm_wna16(const void* x, const void* packed, const void* me
                        (!(flags & Q100_GEMM_FORCE_SKINNY) && tc_ok && (M > 32 || !skinny_ok));
   if (want_tc) {
     Q100_REQUIRE(tc_ok, Q100_EUNSUPPORTED, "tcgen05 path does not support this shape/bit-width");
-    if (tca_ok) return gemm_tca(x, packed, meta, bias, y, M, N, K, group, n_bits, disable_zp, dtype, st);
+    if (tca_ok) {
+      // cluster size for the x multicast: Q100_TCA_CLUSTER in the environment (1, 2 or 4) overrides the default
+      static const int env_cluster = []() { const char* e = getenv("Q100_TCA_CLUSTER"); return e ? atoi(e) : 0; }();
+      // measured on up_proj, M = 2048 (profiles/r01): 1193 / 1221 / 1236 TFLOP/s for clusters of 1 / 2 / 4
+      const int64_t row_tiles = (N + 127) / 128;
+      const int cluster = env_cluster > 0 ? env_cluster : (row_tiles % 4 == 0 ? 4 : row_tiles % 2 == 0 ? 2 : 1);
+      return gemm_tca(x, packed, meta, bias, y, M, N, K, group, n_bits, disable_zp, dtype, cluster, st);
+    }
     return gemm_tc(x, packed, meta, bias, y, M, N, K, group, n_bits, disable_zp, dtype, st);
   }
   // decode shapes: tcgen05 weight-streaming kernel (weights as the TMEM A operand)

@@ -55,10 +55,12 @@ struct TcaSmem {
   static constexpr int kX = NT * TA_BK * 2;                           // x stage
   static constexpr int kP = TA_ROWS * TA_BK * NBITS / 8;              // packed codes of a stage
   static constexpr int kPStage = kP + 512;
-  static constexpr int kBudget = 225 * 1024;
+  static constexpr int kEpi = 4 * 2 * 32 * 64;                       // 4 warps x 2 buffers x [32 tokens x 32 rows] 16-bit
+  static constexpr int kBudget = 225 * 1024 - kEpi;
   static constexpr int kSX = (kBudget - TA_SP * kPStage) / kX > 6 ? 6 : (kBudget - TA_SP * kPStage) / kX;
   static constexpr int kOffP = kSX * kX;
-  static constexpr int kTotal = kOffP + TA_SP * kPStage + 1024;
+  static constexpr int kOffE = kOffP + TA_SP * kPStage;
+  static constexpr int kTotal = kOffE + kEpi + 1024;
   static_assert(kSX >= 3, "x ring too shallow");
   static_assert(kTotal <= 227 * 1024, "shared memory budget");
 };
@@ -131,7 +133,10 @@ __device__ __forceinline__ uint32_t ta_pair_magic(const uint32_t* w, int c, uint
   }
 }
 
-template <typename T, int NBITS, int NT>
+// CL = cluster size along N: the CL CTAs of a cluster work on CL consecutive weight-row tiles of the SAME token
+// tile; each loads 1/CL of the x box and multicasts it to all of them, which divides the L2 -> SM traffic of
+// the x re-reads (the limiter of the single-CTA version: 1.9 GB per up_proj GEMM, 8.8 TB/s) by CL.
+template <typename T, int NBITS, int NT, int CL>
 __global__ void __launch_bounds__(TA_THREADS, 1)
 k3_tca(const __grid_constant__ CUtensorMap tm_x, const TcaArgs a) {
   using SM = TcaSmem<NBITS, NT>;
@@ -151,10 +156,15 @@ k3_tca(const __grid_constant__ CUtensorMap tm_x, const TcaArgs a) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int num_kb = a.K / TA_BK;
-  const int n_tiles_total = a.m_tiles * a.n_tiles;
+  // cluster tiles: (token tile, group of CL consecutive weight-row tiles); this CTA takes row tile `rank`
+  const int rank = CL > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int n_groups = (a.n_tiles + CL - 1) / CL;
+  const int n_ct = a.m_tiles * n_groups;
+  const int ct0 = blockIdx.x / CL, ct_step = gridDim.x / CL;
+  constexpr uint16_t kMask = static_cast<uint16_t>((1u << CL) - 1u);
 
   if (tid == 0) {
-    for (int s = 0; s < SX; ++s) { mbar_init(&bars[s], 1); mbar_init(&bars[SX + s], 1); }
+    for (int s = 0; s < SX; ++s) { mbar_init(&bars[s], 1); mbar_init(&bars[SX + s], CL); }
     for (int s = 0; s < TA_SP; ++s) { mbar_init(&bars[2 * SX + s], 1); mbar_init(&bars[2 * SX + TA_SP + s], 4); }
     for (int s = 0; s < TA_SA; ++s) { mbar_init(&bars[2 * SX + 2 * TA_SP + s], 4); mbar_init(&bars[2 * SX + 2 * TA_SP + TA_SA + s], 1); }
     mbar_init(&bars[2 * SX + 2 * TA_SP + 2 * TA_SA], 1);        // d_full
@@ -164,6 +174,7 @@ k3_tca(const __grid_constant__ CUtensorMap tm_x, const TcaArgs a) {
   if (warp == TA_MMA_WARP) tmem_alloc(&tmem_base_s, TA_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();                    // every CTA's barriers exist before any remote arrive
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
 
@@ -173,14 +184,22 @@ k3_tca(const __grid_constant__ CUtensorMap tm_x, const TcaArgs a) {
       tma_prefetch_desc(&tm_x);
       const uint64_t pol_x = policy_evict_last();
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
-        const int m0 = (tile % a.m_tiles) * NT;
+      for (int ct = ct0; ct < n_ct; ct += ct_step) {
+        const int m0 = (ct % a.m_tiles) * NT;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const uint32_t s = it % SX;
-          ta_wait(empty_x + 8 * s, ((it / SX) & 1) ^ 1);
-          mbar_expect_tx(&bars[s], SM::kX);
-          tma_load_2d_hint(reinterpret_cast<void*>(smem_raw + (base_u32 - smem_u32(smem_raw)) + s * SM::kX), &tm_x, &bars[s],
-                           kb * TA_BK, m0, pol_x);
+          ta_wait(empty_x + 8 * s, ((it / SX) & 1) ^ 1);     // all CL CTAs have retired their MMAs on this stage
+#ifdef TA_EXP_NOX
+          if (it >= SX) { mbar_arrive(&bars[s]); continue; }
+#endif
+          mbar_expect_tx(&bars[s], SM::kX);                  // the whole box: own slice + the peers' slices
+          if (CL == 1) {
+            tma_load_2d_hint(reinterpret_cast<void*>(smem_raw + (base_u32 - smem_u32(smem_raw)) + s * SM::kX), &tm_x,
+                             &bars[s], kb * TA_BK, m0, pol_x);
+          } else {
+            tma_load_2d_mc(base_u32 + s * SM::kX + rank * (NT / CL) * 128, &tm_x, full_x + 8 * s, kb * TA_BK,
+                           m0 + rank * (NT / CL), kMask, pol_x);
+          }
         }
       }
     }
@@ -190,8 +209,8 @@ k3_tca(const __grid_constant__ CUtensorMap tm_x, const TcaArgs a) {
       const uint64_t pol_w = policy_evict_first();
       uint8_t* pbase = smem_raw + (base_u32 - smem_u32(smem_raw)) + SM::kOffP;
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
-        const int nt = tile / a.m_tiles;
+      for (int ct = ct0; ct < n_ct; ct += ct_step) {
+        const int nt = min((ct / a.m_tiles) * CL + rank, a.n_tiles - 1);   // ragged last group: redo the last tile
         const int n0 = nt * TA_ROWS;
         const int mbytes = min(TA_ROWS, a.N - n0) * 4;
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
@@ -211,7 +230,7 @@ k3_tca(const __grid_constant__ CUtensorMap tm_x, const TcaArgs a) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = umma_idesc_f16(kBf16 ? 1 : 0, TA_ROWS, NT);
     uint32_t it = 0, tcount = 0;
-    for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++tcount) {
+    for (int ct = ct0; ct < n_ct; ct += ct_step, ++tcount) {
       ta_wait(d_empty, (tcount & 1) ^ 1);            // the epilogue has drained the accumulator
       tc_fence_after();
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
@@ -226,7 +245,8 @@ k3_tca(const __grid_constant__ CUtensorMap tm_x, const TcaArgs a) {
           for (int k = 0; k < TA_BK / 16; ++k)
             umma_f16_ts(tmem, at + 8 * k, bd + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
           umma_commit_u32(a_empty + 8 * sa);
-          umma_commit_u32(empty_x + 8 * sx);
+          if (CL == 1) umma_commit_u32(empty_x + 8 * sx);
+          else umma_commit_mc(empty_x + 8 * sx, kMask);      // frees the stage in every CTA of the cluster
           if (kb == num_kb - 1) umma_commit_u32(d_full);
         }
         __syncwarp();
@@ -245,7 +265,7 @@ k3_tca(const __grid_constant__ CUtensorMap tm_x, const TcaArgs a) {
     const uint32_t code_off = ta_reg(base_u32 + SM::kOffP + row * (NW * 4));
     const uint32_t meta_off = ta_reg(base_u32 + SM::kOffP + SM::kP + row * 4);
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+    for (int ct = ct0; ct < n_ct; ct += ct_step) {
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         if (static_cast<int>(it & 1) != grp) continue;
         const uint32_t sp = it % TA_SP, sa = it % TA_SA;
@@ -300,8 +320,12 @@ k3_tca(const __grid_constant__ CUtensorMap tm_x, const TcaArgs a) {
         }
         ta_wait(a_empty + 8 * sa, ((it / TA_SA) & 1) ^ 1);   // the tensor core is done with this A stage
         tc_fence_after();
+#ifndef TA_EXP_NOST
         tmem_st_32x32b_x32(lane_t + sa * 32, av);
         tmem_st_wait();
+#else
+        if (av[0] == 0x12345678u && av[31] == 0x9abcdef0u) tmem_st_32x32b_x32(lane_t + sa * 32, av);
+#endif
         tc_fence_before();
         __syncwarp();
         if (lane == 0) ta_arrive(a_full + 8 * sa);
@@ -313,13 +337,19 @@ k3_tca(const __grid_constant__ CUtensorMap tm_x, const TcaArgs a) {
     const T* bias = reinterpret_cast<const T*>(a.bias);
     const uint32_t lane_t = tmem + (static_cast<uint32_t>(quad * 32) << 16);
     uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++tcount) {
-      const int m0 = (tile % a.m_tiles) * NT;
-      const int n = (tile / a.m_tiles) * TA_ROWS + quad * 32 + lane;
+    for (int ct = ct0; ct < n_ct; ct += ct_step, ++tcount) {
+      const int m0 = (ct % a.m_tiles) * NT;
+      const int nt = (ct / a.m_tiles) * CL + rank;      // >= n_tiles in a ragged last group: nothing to store
+      const int n = nt < a.n_tiles ? nt * TA_ROWS + quad * 32 + lane : a.N;
       ta_wait(d_full, tcount & 1);
       tc_fence_after();
       const float bv = (bias != nullptr && n < a.N) ? DT<T>::to_f(bias[n]) : 0.f;
-      T* ycol = reinterpret_cast<T*>(a.y) + n;
+      // y is [tokens, rows]: the accumulator has a row per lane, so a chunk of [32 tokens x 32 rows] is
+      // transposed through shared memory and leaves as 16-byte stores (8 rows of one token each) -- the
+      // direct form, one 2-byte store per value, kept the tensor core idle for ~6 us per tile
+      const int n_warp = nt * TA_ROWS + quad * 32;                      // first row of this warp
+      const uint32_t ebase = base_u32 + SM::kOffE + quad * (2 * 2048);
+      const int tj = lane >> 2, rq = (lane & 3) * 8;                    // read side: token tj (+8i), rows rq..rq+7
 #pragma unroll 1
       for (int c0 = 0; c0 < NT; c0 += 32) {
         uint32_t r[32];
@@ -330,18 +360,32 @@ k3_tca(const __grid_constant__ CUtensorMap tm_x, const TcaArgs a) {
           __syncwarp();
           if (lane == 0) ta_arrive(d_empty);
         }
-        if (n < a.N) {
+        const uint32_t eb = ebase + ((c0 >> 5) & 1) * 2048;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int m = m0 + c0 + j;
-            if (m < a.M) ycol[static_cast<int64_t>(m) * a.N] = DT<T>::from_f(__uint_as_float(r[j]) + bv);
+        for (int j = 0; j < 32; ++j) {
+          const T v = DT<T>::from_f(__uint_as_float(r[j]) + bv);
+          asm volatile("st.shared.u16 [%0], %1;" :: "r"(eb + j * 64 + lane * 2), "h"(*reinterpret_cast<const uint16_t*>(&v)) : "memory");
+        }
+        __syncwarp();
+        if (nt < a.n_tiles) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int m = m0 + c0 + tj + 8 * i;
+            uint4 v;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(eb + (tj + 8 * i) * 64 + rq * 2));
+            if (m < a.M && n_warp + rq < a.N)
+              *reinterpret_cast<uint4*>(reinterpret_cast<T*>(a.y) + static_cast<int64_t>(m) * a.N + n_warp + rq) = v;
           }
         }
+        // the buffer is reused two chunks later: the __syncwarp of the next chunk orders these reads before
+        // the writes after it
       }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();                    // nobody leaves while a peer may still multicast into it
   if (warp == TA_MMA_WARP) {
     tc_fence_after();
     tmem_dealloc(tmem, TA_TMEM_COLS);
@@ -355,45 +399,72 @@ bool gemm_tca_supported(int64_t M, int64_t N, int64_t K, int group, int n_bits) 
          g % TA_BK == 0 && K % g == 0;
 }
 
-template <typename T, int NBITS, int NT>
+template <typename T, int NBITS, int NT, int CL>
 static int launch_tca(const void* x, TcaArgs a, cudaStream_t st) {
   using SM = TcaSmem<NBITS, NT>;
-  auto kern = k3_tca<T, NBITS, NT>;
+  auto kern = k3_tca<T, NBITS, NT, CL>;
   static bool attr_done = false;
   if (!attr_done) {
     Q100_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
     attr_done = true;
   }
   CUtensorMap tx;
-  int rc = make_tmap_2d(&tx, x, 2, a.K, a.M, static_cast<uint64_t>(a.K) * 2, TA_BK, NT, 128);
+  int rc = make_tmap_2d(&tx, x, 2, a.K, a.M, static_cast<uint64_t>(a.K) * 2, TA_BK, NT / CL, 128);
   if (rc != Q100_OK) return rc;
   a.m_tiles = (a.M + NT - 1) / NT;
   a.n_tiles = (a.N + TA_ROWS - 1) / TA_ROWS;
-  int grid = a.m_tiles * a.n_tiles;
-  const int sms = sm_count();
-  if (grid > sms) grid = sms;
-  kern<<<grid, TA_THREADS, SM::kTotal, st>>>(tx, a);
-  return check_cuda(cudaGetLastError(), "k3_tca launch");
+  const int n_ct = a.m_tiles * ((a.n_tiles + CL - 1) / CL);
+  int clusters = sm_count() / CL;
+  if (clusters > n_ct) clusters = n_ct;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(clusters * CL);
+  cfg.blockDim = dim3(TA_THREADS);
+  cfg.dynamicSmemBytes = SM::kTotal;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CL > 1 ? 1 : 0;
+  if (CL > 1) {
+    // persistent kernel: never launch more clusters than can be resident at once (GPC packing: clusters of
+    // four do not tile all 148 SMs)
+    static int max_clusters = 0;
+    if (max_clusters == 0) {
+      cfg.gridDim = dim3(sm_count() / CL * CL);
+      Q100_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
+      if (max_clusters < 1) max_clusters = 1;
+    }
+    if (clusters > max_clusters) clusters = max_clusters;
+    cfg.gridDim = dim3(clusters * CL);
+  }
+  return check_cuda(cudaLaunchKernelEx(&cfg, kern, tx, a), "k3_tca launch");
 }
 
 template <typename T, int NBITS>
-static int gemm_tca_nt(const void* x, const TcaArgs& a, cudaStream_t st) {
-  if (a.M <= 128) return launch_tca<T, NBITS, 128>(x, a, st);
-  return launch_tca<T, NBITS, 256>(x, a, st);
+static int gemm_tca_nt(const void* x, const TcaArgs& a, int cluster, cudaStream_t st) {
+  const int n_tiles = (a.N + TA_ROWS - 1) / TA_ROWS;
+  if (a.M <= 128) {
+    if (cluster >= 2 && n_tiles >= 2) return launch_tca<T, NBITS, 128, 2>(x, a, st);
+    return launch_tca<T, NBITS, 128, 1>(x, a, st);
+  }
+  if (cluster >= 4 && n_tiles >= 4) return launch_tca<T, NBITS, 256, 4>(x, a, st);
+  if (cluster >= 2 && n_tiles >= 2) return launch_tca<T, NBITS, 256, 2>(x, a, st);
+  return launch_tca<T, NBITS, 256, 1>(x, a, st);
 }
 
 template <typename T>
-static int gemm_tca_t(const void* x, const TcaArgs& a, int n_bits, cudaStream_t st) {
+static int gemm_tca_t(const void* x, const TcaArgs& a, int n_bits, int cluster, cudaStream_t st) {
   switch (n_bits) {
-    case 2: return gemm_tca_nt<T, 2>(x, a, st);
-    case 8: return gemm_tca_nt<T, 8>(x, a, st);
-    default: return gemm_tca_nt<T, 4>(x, a, st);
+    case 2: return gemm_tca_nt<T, 2>(x, a, cluster, st);
+    case 8: return gemm_tca_nt<T, 8>(x, a, cluster, st);
+    default: return gemm_tca_nt<T, 4>(x, a, cluster, st);
   }
 }
 
 int gemm_tca(const void* x, const void* packed, const void* meta, const void* bias, void* y,
              int64_t M, int64_t N, int64_t K, int group, int n_bits, int disable_zp, int dtype,
-             cudaStream_t st) {
+             int cluster, cudaStream_t st) {
   Q100_REQUIRE(gemm_tca_supported(M, N, K, group, n_bits), Q100_EUNSUPPORTED, "tcgen05 (TMEM-A) path: unsupported shape");
   TcaArgs a{};
   a.packed = packed; a.meta = meta; a.bias = bias; a.y = y;
@@ -401,8 +472,8 @@ int gemm_tca(const void* x, const void* packed, const void* meta, const void* bi
   a.group = group == 0 ? static_cast<int>(K) : group;
   a.has_zp = disable_zp ? 0 : 1;
   a.qmin = disable_zp ? -static_cast<float>(1 << (n_bits - 1)) : 0.0f;
-  if (dtype == Q100_F16) return gemm_tca_t<__half>(x, a, n_bits, st);
-  return gemm_tca_t<__nv_bfloat16>(x, a, n_bits, st);
+  if (dtype == Q100_F16) return gemm_tca_t<__half>(x, a, n_bits, cluster, st);
+  return gemm_tca_t<__nv_bfloat16>(x, a, n_bits, cluster, st);
 }
 
 }  // namespace q100
