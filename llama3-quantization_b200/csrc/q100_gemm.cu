@@ -136,6 +136,13 @@ extern "C" int q100_gemm_wna16(const void* x, const void* packed, const void* me
   return Q100_OK;
 }
 
+#ifdef TA_TIMING
+namespace q100 { int tca_timing(long long* out, int n); }
+extern "C" __attribute__((visibility("default"))) int q100_debug_tca_timing(long long* out, int n) {
+  return q100::tca_timing(out, n);
+}
+#endif
+
 #ifdef SK_TIMING
 namespace q100 { int skinny_timing(long long* out, int n); }
 extern "C" __attribute__((visibility("default"))) int q100_debug_skinny_timing(long long* out, int n) {

@@ -23,6 +23,8 @@
 //               4 x tcgen05.mma (M = 128, N = NT, K = 16, A from TMEM, B from shared memory) per k block,
 //               tcgen05.commit frees the A stage and the x stage / publishes the accumulator;
 //   warps 8-11  epilogue: tcgen05.ld (lane = weight row, column = token) -> (+bias) -> bf16/fp16 -> global.
+#include <cstdlib>
+
 #include "q100_common.cuh"
 #include "q100_ptx.cuh"
 
@@ -136,6 +138,13 @@ __device__ __forceinline__ uint32_t ta_pair_magic(const uint32_t* w, int c, uint
 // CL = cluster size along N: the CL CTAs of a cluster work on CL consecutive weight-row tiles of the SAME token
 // tile; each loads 1/CL of the x box and multicasts it to all of them, which divides the L2 -> SM traffic of
 // the x re-reads (the limiter of the single-CTA version: 1.9 GB per up_proj GEMM, 8.8 TB/s) by CL.
+#ifdef TA_TIMING
+__device__ long long g_ta_t[256][8];
+#define TA_T(v) const long long v = clock64()
+#else
+#define TA_T(v)
+#endif
+
 template <typename T, int NBITS, int NT, int CL>
 __global__ void __launch_bounds__(TA_THREADS, 1)
 k3_tca(const __grid_constant__ CUtensorMap tm_x, const TcaArgs a) {
@@ -230,13 +239,26 @@ k3_tca(const __grid_constant__ CUtensorMap tm_x, const TcaArgs a) {
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = umma_idesc_f16(kBf16 ? 1 : 0, TA_ROWS, NT);
     uint32_t it = 0, tcount = 0;
+#ifdef TA_TIMING
+    long long t_de = 0, t_af = 0, t_fx = 0, t_is = 0; const long long t_begin = clock64();
+#endif
     for (int ct = ct0; ct < n_ct; ct += ct_step, ++tcount) {
+      TA_T(q0);
       ta_wait(d_empty, (tcount & 1) ^ 1);            // the epilogue has drained the accumulator
       tc_fence_after();
+#ifdef TA_TIMING
+      t_de += clock64() - q0;
+#endif
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const uint32_t sx = it % SX, sa = it % TA_SA;
+        TA_T(q1);
         ta_wait(a_full + 8 * sa, (it / TA_SA) & 1);
+        TA_T(q2);
         ta_wait(full_x + 8 * sx, (it / SX) & 1);
+        TA_T(q3);
+#ifdef TA_TIMING
+        t_af += q2 - q1; t_fx += q3 - q2;
+#endif
         tc_fence_after();
         if (lane == 0) {
           const uint64_t bd = umma_desc_sw128_u32(base_u32 + sx * SM::kX);
@@ -250,8 +272,14 @@ k3_tca(const __grid_constant__ CUtensorMap tm_x, const TcaArgs a) {
           if (kb == num_kb - 1) umma_commit_u32(d_full);
         }
         __syncwarp();
+#ifdef TA_TIMING
+        t_is += clock64() - q3;
+#endif
       }
     }
+#ifdef TA_TIMING
+    if (lane == 0 && blockIdx.x < 256) { g_ta_t[blockIdx.x][0] = clock64() - t_begin; g_ta_t[blockIdx.x][1] = t_de; g_ta_t[blockIdx.x][2] = t_af; g_ta_t[blockIdx.x][3] = t_fx; g_ta_t[blockIdx.x][4] = t_is; g_ta_t[blockIdx.x][5] = it; }
+#endif
   } else if (warp < TA_DQ_WARPS) {
     // ===================== dequant warps: group g handles iterations it % 2 == g; thread = weight row =====================
     const int grp = warp >> 2;
@@ -269,7 +297,9 @@ k3_tca(const __grid_constant__ CUtensorMap tm_x, const TcaArgs a) {
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         if (static_cast<int>(it & 1) != grp) continue;
         const uint32_t sp = it % TA_SP, sa = it % TA_SA;
+        TA_T(d0);
         ta_wait(full_p + 8 * sp, (it / TA_SP) & 1);
+        TA_T(d1);
         uint32_t w[NW];
 #pragma unroll
         for (int i = 0; i < NW / 4; ++i) {
@@ -318,7 +348,9 @@ k3_tca(const __grid_constant__ CUtensorMap tm_x, const TcaArgs a) {
             av[c] = *reinterpret_cast<uint32_t*>(&v);
           }
         }
+        TA_T(d2);
         ta_wait(a_empty + 8 * sa, ((it / TA_SA) & 1) ^ 1);   // the tensor core is done with this A stage
+        TA_T(d3);
         tc_fence_after();
 #ifndef TA_EXP_NOST
         tmem_st_32x32b_x32(lane_t + sa * 32, av);
@@ -329,6 +361,12 @@ k3_tca(const __grid_constant__ CUtensorMap tm_x, const TcaArgs a) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) ta_arrive(a_full + 8 * sa);
+#ifdef TA_TIMING
+        if (tid == 0 && blockIdx.x < 256) {
+          g_ta_t[blockIdx.x][6] += (d1 - d0) + (d3 - d2);       // waiting (full_p + a_empty)
+          g_ta_t[blockIdx.x][7] += (d2 - d1) + (clock64() - d3); // working (loads + math, store + publish)
+        }
+#endif
       }
     }
   } else {
@@ -393,6 +431,15 @@ k3_tca(const __grid_constant__ CUtensorMap tm_x, const TcaArgs a) {
 }
 
 // ---------------------------------------------------------------- host
+#ifdef TA_TIMING
+int tca_timing(long long* out, int n) {
+  int rc = check_cuda(cudaMemcpyFromSymbol(out, g_ta_t, sizeof(long long) * 8 * n), "timing readback");
+  static long long zeros[256][8] = {};
+  cudaMemcpyToSymbol(g_ta_t, zeros, sizeof(zeros));
+  return rc;
+}
+#endif
+
 bool gemm_tca_supported(int64_t M, int64_t N, int64_t K, int group, int n_bits) {
   const int64_t g = group == 0 ? K : group;
   return (n_bits == 4 || n_bits == 2 || n_bits == 8) && M >= 1 && N % 8 == 0 && K % TA_BK == 0 &&
@@ -444,7 +491,10 @@ static int launch_tca(const void* x, TcaArgs a, cudaStream_t st) {
 template <typename T, int NBITS>
 static int gemm_tca_nt(const void* x, const TcaArgs& a, int cluster, cudaStream_t st) {
   const int n_tiles = (a.N + TA_ROWS - 1) / TA_ROWS;
-  if (a.M <= 128) {
+  // 128-token tiles only when there are no more tokens: measured (profiles/r01 notes) a 128-token tile takes
+  // as long as a 256-token one (the per-k-block pipeline, not the MMA, sets the pace), so it never pays
+  static const int env_nt = []() { const char* e = getenv("Q100_TCA_NT"); return e ? atoi(e) : 0; }();   // experiments
+  if (a.M <= 128 || env_nt == 128) {
     if (cluster >= 2 && n_tiles >= 2) return launch_tca<T, NBITS, 128, 2>(x, a, st);
     return launch_tca<T, NBITS, 128, 1>(x, a, st);
   }
