@@ -1,0 +1,455 @@
+"""Drop-in for the reference's ``models/int_llama_layer.py``: QuantLlamaMLP (lines 20-45),
+QuantLlamaAttention (48-188) and QuantLlamaDecoderLayer (190-344), the callers of the quantised-linear
+hot path.
+
+Same classes, constructor signatures, attribute names and methods (``set_quant_state``,
+``smooth_and_quant_inplace`` / ``smooth_and_quant_temporary`` / ``clear_temp_variable``,
+``register_scales_and_zeros``, ``lwc_parameters`` / ``let_parameters`` / ``omni_parameters`` /
+``omni_state_dict``), so ``quant/omniquant.py`` and ``main.py`` can build blocks from here.  What is
+B200-specific sits underneath:
+
+* the three projections that read the same normalised activation (q, k, v) and the two of the MLP
+  (gate, up) run as ONE fused dequant-GEMM launch each on the concatenation of their packed weights
+  (concatenating along N is exact: quantisation groups run along K), so a decoder block is four GEMM
+  launches instead of seven -- the k/v shapes are sub-2-microsecond at the HBM roofline and cannot be
+  efficient as launches of their own ("fuse q|k|v and gate|up");
+* the per-token activation fake-quant of a shared input runs once (K2), not once per consumer;
+* under tensor parallelism (``tp_world > 1``) q/k/v/gate/up hold column shards, o/down row shards, and
+  the one collective is the all-reduce after o_proj and down_proj (q100/tp.py).
+
+The attention core between the two ``QuantMatMul``s is the reference's eager formulation (fp32 softmax);
+with ``fast_attention = True`` and no activation quantisation it is ``scaled_dot_product_attention``
+(a library kernel; the attention core is SURVEY section 8 row f3, not part of this path).
+
+The rotary embedding follows transformers 4.37 (the version the reference pins): ``rotary_emb(x, seq_len)``
+returns the ``[seq_len, head_dim]`` cos/sin cache which ``apply_rotary_pos_emb`` indexes by position.  If
+``org_module.rotary_emb`` exists it is deep-copied like the reference does (int_llama_layer.py:70); otherwise
+one is built from ``config.rope_theta``.
+
+LET (``self.let = True``: learnable equivalent transformation) needs ``models/transformation.py``, a
+calibration-side caller that is out of scope here; those branches import it from the reference checkout
+(``Q100_REF_PATH`` / ``sys.path``) and raise if it is absent.
+"""
+from __future__ import annotations
+
+import copy
+import math
+from collections import OrderedDict
+from typing import Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from q100 import ops as _ops
+from q100 import tp as _tp
+from quant.int_linear import QuantLinear
+from quant.int_matmul import QuantMatMul
+from quant.omni_norm import OmniLlamaRMSNorm
+
+
+def _act_fn(name: str):
+    if name in ("silu", "swish"):
+        return F.silu
+    if name == "gelu":
+        return F.gelu
+    if name == "relu":
+        return F.relu
+    from transformers.activations import ACT2FN
+    return ACT2FN[name]
+
+
+# ------------------------------------------------------------------------------------ rotary (4.37 form)
+class LlamaRotaryEmbedding(nn.Module):
+    """cos/sin cache ``[seq_len, dim]``; ``forward(x, seq_len)`` like transformers 4.37."""
+
+    def __init__(self, dim, max_position_embeddings=8192, base=500000.0, device=None):
+        super().__init__()
+        self.dim, self.base = dim, base
+        self.max_seq_len_cached = 0
+        self._device = device
+        self.register_buffer("cos_cached", torch.empty(0), persistent=False)
+        self.register_buffer("sin_cached", torch.empty(0), persistent=False)
+
+    def _build(self, seq_len, device):
+        inv_freq = 1.0 / (self.base ** (torch.arange(0, self.dim, 2, dtype=torch.int64).float().to(device) / self.dim))
+        t = torch.arange(seq_len, device=device, dtype=torch.int64).type_as(inv_freq)
+        freqs = torch.outer(t, inv_freq)
+        emb = torch.cat((freqs, freqs), dim=-1)
+        self.cos_cached, self.sin_cached = emb.cos(), emb.sin()
+        self.max_seq_len_cached = seq_len
+
+    def forward(self, x, seq_len=None):
+        if seq_len > self.max_seq_len_cached or self.cos_cached.device != x.device:
+            self._build(max(seq_len, 2048), x.device)
+        return self.cos_cached[:seq_len].to(dtype=x.dtype), self.sin_cached[:seq_len].to(dtype=x.dtype)
+
+
+def rotate_half(x):
+    x1 = x[..., : x.shape[-1] // 2]
+    x2 = x[..., x.shape[-1] // 2:]
+    return torch.cat((-x2, x1), dim=-1)
+
+
+def apply_rotary_pos_emb(q, k, cos, sin, position_ids):
+    cos = cos[position_ids].unsqueeze(1)
+    sin = sin[position_ids].unsqueeze(1)
+    return (q * cos) + (rotate_half(q) * sin), (k * cos) + (rotate_half(k) * sin)
+
+
+def repeat_kv(hidden_states: torch.Tensor, n_rep: int) -> torch.Tensor:
+    batch, num_key_value_heads, slen, head_dim = hidden_states.shape
+    if n_rep == 1:
+        return hidden_states
+    hidden_states = hidden_states[:, :, None, :, :].expand(batch, num_key_value_heads, n_rep, slen, head_dim)
+    return hidden_states.reshape(batch, num_key_value_heads * n_rep, slen, head_dim)
+
+
+# ------------------------------------------------------------------------------------ fused launches
+class _FusedLinears:
+    """Several QuantLinears that consume the same input, run as one dequant-GEMM on the concatenation
+    (along N) of their packed weights.  The concatenation is cached on the identity of the parts."""
+
+    def __init__(self):
+        self._key = None
+        self._pw = None
+
+    def _concat(self, parts):
+        p0 = parts[0]
+        zeros = None if p0.zeros is None else torch.cat([p.zeros for p in parts], dim=0)
+        return _ops.PackedWeight(torch.cat([p.packed for p in parts], dim=0),
+                                 torch.cat([p.meta for p in parts], dim=1).contiguous(),
+                                 torch.cat([p.scales for p in parts], dim=0), zeros,
+                                 p0.n_bits, p0.group, sum(p.N for p in parts), p0.K, p0.disable_zero_point)
+
+    def __call__(self, mods, x: torch.Tensor):
+        """Returns the outputs of ``mods`` on ``x`` (a tuple), or None when the modules cannot be fused
+        (then the caller runs them one by one exactly like the reference)."""
+        if not x.is_cuda or x.dtype not in (torch.float16, torch.bfloat16):
+            return None
+        parts = []
+        m0 = mods[0]
+        for m in mods:
+            if m.bias is not None or m.use_act_quant != m0.use_act_quant \
+                    or m.disable_input_quant != m0.disable_input_quant:
+                return None
+            p = m.packed_operand(x)
+            if p is None or p.dtype != x.dtype or p.N % _ops.TILE_ROWS != 0:
+                return None
+            parts.append(p)
+        p0 = parts[0]
+        for p in parts[1:]:
+            if (p.K, p.n_bits, p.group, p.disable_zero_point) != (p0.K, p0.n_bits, p0.group, p0.disable_zero_point):
+                return None
+        key = tuple((p.packed.data_ptr(), p.packed._version, p.meta.data_ptr()) for p in parts)
+        if key != self._key:
+            self._pw = self._concat(parts)
+            self._key = key
+        if m0.use_act_quant and not m0.disable_input_quant:
+            xq = m0.act_quantizer(x)                  # same input, same per-token statistics for every consumer
+            for m in mods[1:]:
+                aq, a0 = m.act_quantizer, m0.act_quantizer
+                if aq.n_bits != a0.n_bits or aq.enable != a0.enable:
+                    return None
+                if aq.n_bits < 16 and aq.enable:
+                    aq.scale, aq.round_zero_point = a0.scale, a0.round_zero_point
+            x = xq
+        y = _ops.gemm_wna16(x, self._pw)
+        return y.split([p.N for p in parts], dim=-1)
+
+
+class QuantLlamaMLP(nn.Module):
+    def __init__(self, org_module: nn.Module, hidden_size: int, intermediate_size: int, hidden_act: str,
+                 args=None):
+        super().__init__()
+        self.gate_proj = QuantLinear(org_module.gate_proj, args.weight_quant_params, args.act_quant_params)
+        self.down_proj = QuantLinear(org_module.down_proj, args.weight_quant_params, args.act_quant_params)
+        self.up_proj = QuantLinear(org_module.up_proj, args.weight_quant_params, args.act_quant_params)
+        self.act_fn = _act_fn(hidden_act)
+        self._gate_up = _FusedLinears()
+        self.tp_group = None
+
+    def forward(self, x):
+        fused = self._gate_up((self.gate_proj, self.up_proj), x)
+        if fused is not None:
+            gate, up = fused
+        else:
+            gate, up = self.gate_proj(x), self.up_proj(x)
+        out = self.down_proj(self.act_fn(gate) * up)
+        return _tp.reduce_output(out, _tp.ROW, self.tp_group) if getattr(self, "tp_world", 1) > 1 else out
+
+
+class QuantLlamaAttention(nn.Module):
+    """Multi-headed attention with quantised projections (reference int_llama_layer.py:48-188)."""
+
+    def __init__(self, org_module: nn.Module, config, args=None):
+        super().__init__()
+        self.config = config
+        self.hidden_size = config.hidden_size
+        self.num_heads = config.num_attention_heads
+        self.head_dim = self.hidden_size // self.num_heads
+        self.num_key_value_heads = config.num_key_value_heads
+        self.num_key_value_groups = self.num_heads // self.num_key_value_heads
+        self.max_position_embeddings = config.max_position_embeddings
+        if (self.head_dim * self.num_heads) != self.hidden_size:
+            raise ValueError(
+                f"hidden_size must be divisible by num_heads (got `hidden_size`: {self.hidden_size}"
+                f" and `num_heads`: {self.num_heads})."
+            )
+        rot = getattr(org_module, "rotary_emb", None)
+        if rot is not None:
+            self.rotary_emb = copy.deepcopy(rot)
+        else:
+            self.rotary_emb = LlamaRotaryEmbedding(self.head_dim, self.max_position_embeddings,
+                                                   float(getattr(config, "rope_theta", 500000.0)))
+        self.k_proj = QuantLinear(org_module.k_proj, args.weight_quant_params, args.act_quant_params)
+        self.v_proj = QuantLinear(org_module.v_proj, args.weight_quant_params, args.act_quant_params)
+        self.q_proj = QuantLinear(org_module.q_proj, args.weight_quant_params, args.act_quant_params)
+        self.o_proj = QuantLinear(org_module.o_proj, args.weight_quant_params, args.act_quant_params)
+        self.qkt_matmul = QuantMatMul(args.q_quant_params, args.k_quant_params, matmul_func=torch.matmul)
+        self.pv_matmul = QuantMatMul(args.p_quant_params, args.v_quant_params, matmul_func=torch.matmul)
+        self.use_weight_quant = False
+        self.use_act_quant = False
+        self.fast_attention = False
+        self._qkv = _FusedLinears()
+        # tensor parallel: this rank's share of the heads (set by q100.llama when tp_world > 1)
+        self.tp_world = 1
+        self.tp_group = None
+
+    def _shape(self, tensor: torch.Tensor, seq_len: int, bsz: int):
+        return tensor.view(bsz, seq_len, self.num_heads, self.head_dim).transpose(1, 2).contiguous()
+
+    def forward(
+        self,
+        hidden_states: torch.Tensor,
+        attention_mask: Optional[torch.Tensor] = None,
+        position_ids: Optional[torch.LongTensor] = None,
+        past_key_value: Optional[Tuple[torch.Tensor]] = None,
+        output_attentions: bool = False,
+        use_cache: bool = False,
+    ) -> Tuple[torch.Tensor, Optional[torch.Tensor], Optional[Tuple[torch.Tensor]]]:
+        bsz, q_len, _ = hidden_states.size()
+        nh = self.num_heads // self.tp_world
+        nkv = max(self.num_key_value_heads // self.tp_world, 1)
+
+        fused = self._qkv((self.q_proj, self.k_proj, self.v_proj), hidden_states)
+        if fused is not None:
+            q, k, v = fused
+        else:
+            q, k, v = self.q_proj(hidden_states), self.k_proj(hidden_states), self.v_proj(hidden_states)
+        query_states = q.view(bsz, q_len, nh, self.head_dim).transpose(1, 2).type(torch.float32)
+        key_states = k.view(bsz, q_len, nkv, self.head_dim).transpose(1, 2)
+        value_states = v.view(bsz, q_len, nkv, self.head_dim).transpose(1, 2)
+
+        kv_seq_len = key_states.shape[-2]
+        if past_key_value is not None:
+            kv_seq_len += past_key_value[0].shape[-2]
+        cos, sin = self.rotary_emb(value_states, seq_len=kv_seq_len)
+        if position_ids is None:
+            position_ids = torch.arange(kv_seq_len - q_len, kv_seq_len, device=hidden_states.device).unsqueeze(0)
+        query_states, key_states = apply_rotary_pos_emb(query_states, key_states, cos, sin, position_ids)
+
+        if past_key_value is not None:
+            key_states = torch.cat([past_key_value[0], key_states], dim=2)
+            value_states = torch.cat([past_key_value[1], value_states], dim=2)
+        past_key_value = (key_states, value_states) if use_cache else None
+
+        if not torch.is_autocast_enabled():
+            # the reference leaves Q in fp32 (int_llama_layer.py:117) and relies on autocast to bring both
+            # matmul operands to the model dtype; outside autocast do that cast here
+            query_states = query_states.to(key_states.dtype)
+        n_rep = nh // nkv
+
+        if self.fast_attention and not self.use_act_quant and not output_attentions:
+            attn_output = F.scaled_dot_product_attention(
+                query_states, key_states, value_states, attn_mask=attention_mask,
+                is_causal=attention_mask is None and q_len > 1, enable_gqa=n_rep > 1)
+            attn_weights = None
+        else:
+            key_states = repeat_kv(key_states, n_rep)
+            value_states = repeat_kv(value_states, n_rep)
+            query_states = self.qkt_matmul.quant_x1(query_states)
+            key_states = self.qkt_matmul.quant_x2(key_states)
+            attn_weights = self.qkt_matmul(query_states, key_states.transpose(2, 3)) / math.sqrt(self.head_dim)
+            if attn_weights.size() != (bsz, nh, q_len, kv_seq_len):
+                raise ValueError(
+                    f"Attention weights should be of size {(bsz, nh, q_len, kv_seq_len)}, but is"
+                    f" {attn_weights.size()}"
+                )
+            if attention_mask is not None:
+                if attention_mask.size() != (bsz, 1, q_len, kv_seq_len):
+                    raise ValueError(
+                        f"Attention mask should be of size {(bsz, 1, q_len, kv_seq_len)}, but is {attention_mask.size()}"
+                    )
+                attn_weights = attn_weights + attention_mask
+                attn_weights = torch.max(attn_weights, torch.tensor(torch.finfo(attn_weights.dtype).min))
+            # upcast attention to fp32
+            attn_weights = nn.functional.softmax(attn_weights, dim=-1, dtype=torch.float32).to(query_states.dtype)
+            attn_weights = self.pv_matmul.quant_x1(attn_weights)
+            value_states = self.pv_matmul.quant_x2(value_states)
+            attn_output = self.pv_matmul(attn_weights, value_states)
+
+        if attn_output.size() != (bsz, nh, q_len, self.head_dim):
+            raise ValueError(
+                f"`attn_output` should be of size {(bsz, nh, q_len, self.head_dim)}, but is"
+                f" {attn_output.size()}"
+            )
+        attn_output = attn_output.transpose(1, 2)
+        attn_output = attn_output.reshape(bsz, q_len, nh * self.head_dim)
+        attn_output = self.o_proj(attn_output)
+        if self.tp_world > 1:
+            attn_output = _tp.reduce_output(attn_output, _tp.ROW, self.tp_group)
+        if not output_attentions:
+            attn_weights = None
+        return attn_output, attn_weights, past_key_value
+
+    def set_quant_state(self, weight_quant: bool = False, act_quant: bool = False):
+        # setting weight quantization here does not affect actual forward pass
+        self.use_weight_quant = weight_quant
+        self.use_act_quant = act_quant
+        for m in self.modules():
+            if isinstance(m, (QuantLinear, QuantMatMul)):
+                m.set_quant_state(weight_quant, act_quant)
+
+
+def _transformation():
+    """models/transformation.py of the reference (LET smoothing; a calibration-side caller, out of scope)."""
+    try:
+        import importlib
+        return importlib.import_module("models.transformation")
+    except Exception as ex:  # pragma: no cover - depends on the reference checkout being importable
+        raise NotImplementedError(
+            "LET (let=True) needs the reference's models/transformation.py on sys.path / Q100_REF_PATH") from ex
+
+
+class QuantLlamaDecoderLayer(nn.Module):
+    def __init__(self, config, ori_layer, args):
+        super().__init__()
+        self.hidden_size = config.hidden_size
+        self.self_attn = QuantLlamaAttention(org_module=ori_layer.self_attn, config=config, args=args)
+        self.mlp = QuantLlamaMLP(
+            org_module=ori_layer.mlp,
+            hidden_size=self.hidden_size,
+            intermediate_size=config.intermediate_size,
+            hidden_act=config.hidden_act,
+            args=args,
+        )
+        self.input_layernorm = OmniLlamaRMSNorm(ori_layer.input_layernorm,
+                                                eps=ori_layer.input_layernorm.variance_epsilon)
+        self.post_attention_layernorm = OmniLlamaRMSNorm(ori_layer.post_attention_layernorm,
+                                                         eps=ori_layer.post_attention_layernorm.variance_epsilon)
+        self.let = False
+
+    def forward(
+        self,
+        hidden_states: torch.Tensor,
+        attention_mask: Optional[torch.Tensor] = None,
+        position_ids: Optional[torch.LongTensor] = None,
+        past_key_value: Optional[Tuple[torch.Tensor]] = None,
+        output_attentions: Optional[bool] = False,
+        use_cache: Optional[bool] = False,
+    ):
+        residual = hidden_states
+        hidden_states = self.input_layernorm(hidden_states)
+        hidden_states, self_attn_weights, present_key_value = self.self_attn(
+            hidden_states=hidden_states,
+            attention_mask=attention_mask,
+            position_ids=position_ids,
+            past_key_value=past_key_value,
+            output_attentions=output_attentions,
+            use_cache=use_cache,
+        )
+        hidden_states = residual + hidden_states
+
+        residual = hidden_states
+        hidden_states = self.post_attention_layernorm(hidden_states)
+        hidden_states = self.mlp(hidden_states)
+        hidden_states = residual + hidden_states
+
+        outputs = (hidden_states,)
+        if output_attentions:
+            outputs += (self_attn_weights,)
+        if use_cache:
+            outputs += (present_key_value,)
+        return outputs
+
+    # ------------------------------------------------------------------ quantisation state
+    def _quant_linears(self):
+        return [m for _, m in self.named_modules() if isinstance(m, QuantLinear)]
+
+    def set_quant_state(self, weight_quant: bool = False, act_quant: bool = False):
+        # setting weight quantization here does not affect actual forward pass
+        self.use_weight_quant = weight_quant
+        self.use_act_quant = act_quant
+        for name, m in self.named_modules():
+            if isinstance(m, (QuantLinear, QuantMatMul)):
+                m.set_quant_state(weight_quant, act_quant)
+
+    def _let_smooth(self, suffix: str):
+        t = _transformation()
+        with torch.no_grad():
+            for name, module in self.named_parameters():
+                if "smooth_scale" in name:
+                    module.data = t.truncate_number(module)
+        ln_fcs = getattr(t, "smooth_ln_fcs_" + suffix)
+        fc_fc = getattr(t, "smooth_fc_fc_" + suffix)
+        q_k = getattr(t, "smooth_q_k_" + suffix)
+        ln_fcs(self.input_layernorm, [self.self_attn.q_proj, self.self_attn.k_proj, self.self_attn.v_proj],
+               self.qkv_smooth_scale, self.qkv_smooth_shift)
+        ln_fcs(self.post_attention_layernorm, [self.mlp.up_proj, self.mlp.gate_proj],
+               self.fc1_smooth_scale, self.fc1_smooth_shift)
+        fc_fc(self.self_attn.v_proj, self.self_attn.o_proj, self.out_smooth_scale, self.out_smooth_shift)
+        q_k(self.self_attn.q_proj, self.self_attn.k_proj, self.qkt_smooth_scale)
+
+    def smooth_and_quant_temporary(self):
+        if self.let:
+            self._let_smooth("temporary")
+            self.mlp.down_proj.temp_weight = self.mlp.down_proj.weight
+        else:
+            for module in self._quant_linears():
+                module.temp_weight = module.weight
+        for module in self._quant_linears():
+            if hasattr(module, "temp_weight"):
+                module.temp_weight = module.weight_quantizer(module.temp_weight)
+            else:
+                module.temp_weight = module.weight_quantizer(module.weight)
+            if not hasattr(module, "temp_bias"):
+                module.temp_bias = module.bias
+            module.use_temporary_parameter = True
+
+    def clear_temp_variable(self):
+        for module in self._quant_linears():
+            del module.temp_weight
+            del module.temp_bias
+
+    @torch.no_grad()
+    def smooth_and_quant_inplace(self):
+        if self.let:
+            self._let_smooth("inplace")
+        for module in self._quant_linears():
+            module.weight = module.weight_quantizer(module.weight)
+            module.use_temporary_parameter = False
+
+    def let_parameters(self, use_shift=True):
+        template = "smooth" if use_shift else "smooth_scale"
+        return iter([m for n, m in self.named_parameters() if n.find(template) > -1])
+
+    def lwc_parameters(self):
+        return iter([m for n, m in self.named_parameters() if n.find('bound_factor') > -1])
+
+    def omni_parameters(self, use_shift=True):
+        template = "smooth" if use_shift else "smooth_scale"
+        return iter([m for n, m in self.named_parameters()
+                     if n.find('bound_factor') > -1 or n.find(template) > -1])
+
+    def omni_state_dict(self, destination=None, prefix='', keep_vars=False):
+        if destination is None:
+            destination = OrderedDict()
+        for name, param in self.named_parameters():
+            if name.find('smooth') > -1 or name.find('bound_factor') > -1:
+                destination[prefix + name] = param if keep_vars else param.detach()
+        return destination
+
+    def register_scales_and_zeros(self):
+        for module in self._quant_linears():
+            module.weight_quantizer.register_scales_and_zeros()

@@ -1,0 +1,204 @@
+"""A LLaMA stack of q100 decoder blocks with seeded random weights, for the whole-model rows of the
+benchmark contract: synthetic-token perplexity exactly as
+``main.py:122-151`` computes it, prefill tokens/s and per-token decode latency with a KV cache
+(methodology of the reference's ``llama.py:409-465``: median per-token latency).
+
+There is no checkpoint and no dataset on the box, so weights are N(0, 0.02) from a per-tensor seed
+(``seed * 1000 + layer * 7 + j``; identical on every tensor-parallel rank, each rank keeps its shard) and
+tokens are ``randint``.  Blocks are built one at a time, quantised in place (``smooth_and_quant_inplace``,
+LET off -- what ``main.py`` leaves behind after calibration) and only the packed codes + side band are
+kept: an 8B model is 4.3 GB of W4 codes, a 70B shard at TP=8 is 4.5 GB per GPU.
+
+Tensor parallel layout per block (q100/tp.py): q/k/v/gate/up column shards (heads split across ranks),
+o/down row shards, one all-reduce after o_proj and after down_proj.  Embedding, norms and lm_head are
+replicated (lm_head is unquantised fp16/bf16 in the reference as well).
+"""
+from __future__ import annotations
+
+import math
+import types
+from dataclasses import dataclass
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import tp as _tp
+from models.int_llama_layer import QuantLlamaDecoderLayer
+
+
+@dataclass
+class LlamaCfg:
+    hidden_size: int
+    intermediate_size: int
+    num_attention_heads: int
+    num_key_value_heads: int
+    num_hidden_layers: int
+    vocab_size: int
+    rms_norm_eps: float = 1e-5
+    rope_theta: float = 500000.0
+    max_position_embeddings: int = 8192
+    hidden_act: str = "silu"
+
+
+LLAMA3_8B = LlamaCfg(4096, 14336, 32, 8, 32, 128256)
+LLAMA3_70B = LlamaCfg(8192, 28672, 64, 8, 80, 128256)
+
+_LINEARS = ("q_proj", "k_proj", "v_proj", "o_proj", "gate_proj", "up_proj", "down_proj")
+
+
+def quant_args(wbits=4, group_size=128, abits=16, symmetric=False, lwc=False, disable_zero_point=False):
+    """The parameter dicts main.py:317-353 builds from the command line."""
+    act = {"n_bits": abits, "per_channel_axes": [], "symmetric": False, "dynamic_method": "per_token"}
+    return types.SimpleNamespace(
+        weight_quant_params={"n_bits": wbits, "per_channel_axes": [0], "symmetric": symmetric,
+                             "dynamic_method": "per_channel", "group_size": group_size, "lwc": lwc,
+                             "disable_zero_point": disable_zero_point},
+        act_quant_params=dict(act), q_quant_params=dict(act), k_quant_params=dict(act), v_quant_params=dict(act),
+        p_quant_params={"n_bits": 16, "metric": "fix0to1"}, wbits=wbits, abits=abits, group_size=group_size)
+
+
+class _Norm(nn.Module):
+    def __init__(self, w, eps):
+        super().__init__()
+        self.weight = nn.Parameter(w, requires_grad=False)
+        self.variance_epsilon = eps
+
+
+def _linear(w: torch.Tensor) -> nn.Linear:
+    m = nn.Linear(w.shape[1], w.shape[0], bias=False, device="meta")
+    m.weight = nn.Parameter(w, requires_grad=False)
+    return m
+
+
+def linear_shapes(cfg: LlamaCfg):
+    kv = cfg.num_key_value_heads * (cfg.hidden_size // cfg.num_attention_heads)
+    return {"q_proj": (cfg.hidden_size, cfg.hidden_size), "k_proj": (kv, cfg.hidden_size),
+            "v_proj": (kv, cfg.hidden_size), "o_proj": (cfg.hidden_size, cfg.hidden_size),
+            "gate_proj": (cfg.intermediate_size, cfg.hidden_size),
+            "up_proj": (cfg.intermediate_size, cfg.hidden_size),
+            "down_proj": (cfg.hidden_size, cfg.intermediate_size)}
+
+
+def random_block_weights(cfg: LlamaCfg, layer: int, seed: int, device, dtype, rank=0, world=1, group=128,
+                         std=0.02):
+    """This rank's shard of every linear of block ``layer`` plus the two norm weights."""
+    gen = torch.Generator(device=device)
+    out = {}
+    for j, (name, (n, k)) in enumerate(linear_shapes(cfg).items()):
+        gen.manual_seed(seed * 1000 + layer * 7 + j)
+        w = (torch.randn(n, k, generator=gen, device=device) * std).to(dtype)
+        if world > 1:
+            w = _tp.shard_weight(w, _tp.LLAMA_PLAN[name], rank, world, group or k)
+        out[name] = w
+    gen.manual_seed(seed * 1000 + layer * 7 + 900_000)
+    for name in ("input_layernorm", "post_attention_layernorm"):
+        out[name] = (1.0 + 0.1 * torch.randn(cfg.hidden_size, generator=gen, device=device)).to(dtype)
+    return out
+
+
+def build_block(cfg: LlamaCfg, weights: dict, args, rank=0, world=1, tp_group=None, quantize=True,
+                drop_dense=True) -> QuantLlamaDecoderLayer:
+    """QuantLlamaDecoderLayer from dense weights; quantised in place like main.py leaves it."""
+    attn = types.SimpleNamespace(**{n: _linear(weights[n]) for n in ("q_proj", "k_proj", "v_proj", "o_proj")})
+    mlp = types.SimpleNamespace(**{n: _linear(weights[n]) for n in ("gate_proj", "up_proj", "down_proj")})
+    ori = types.SimpleNamespace(self_attn=attn, mlp=mlp,
+                                input_layernorm=_Norm(weights["input_layernorm"], cfg.rms_norm_eps),
+                                post_attention_layernorm=_Norm(weights["post_attention_layernorm"],
+                                                               cfg.rms_norm_eps))
+    layer = QuantLlamaDecoderLayer(cfg, ori, args)
+    layer.self_attn.tp_world, layer.self_attn.tp_group = world, tp_group
+    layer.mlp.tp_world, layer.mlp.tp_group = world, tp_group
+    if quantize and args.weight_quant_params["n_bits"] < 16:
+        layer.smooth_and_quant_inplace()
+        if drop_dense:
+            for m in layer._quant_linears():
+                m.release_dense_weight()          # inference only needs the packed twin
+    layer.set_quant_state(weight_quant=False, act_quant=args.act_quant_params["n_bits"] < 16)
+    return layer
+
+
+class QuantLlamaModel(nn.Module):
+    def __init__(self, cfg: LlamaCfg, layers: List[QuantLlamaDecoderLayer], embed: torch.Tensor,
+                 norm_w: torch.Tensor, lm_head: Optional[torch.Tensor]):
+        super().__init__()
+        self.cfg = cfg
+        self.layers = nn.ModuleList(layers)
+        self.register_buffer("embed_tokens", embed)
+        self.register_buffer("norm_weight", norm_w)
+        self.register_buffer("lm_head", lm_head)
+
+    # ------------------------------------------------------------------ construction
+    @classmethod
+    def random_init(cls, cfg: LlamaCfg, args, device, dtype=torch.float16, seed=0, rank=0, world=1,
+                    tp_group=None, n_layers: Optional[int] = None, with_head=True, fast_attention=False,
+                    quantize=True, drop_dense=True):
+        gen = torch.Generator(device=device).manual_seed(seed * 1000 + 999_001)
+        embed = (torch.randn(cfg.vocab_size, cfg.hidden_size, generator=gen, device=device) * 0.02).to(dtype)
+        head = (torch.randn(cfg.vocab_size, cfg.hidden_size, generator=gen, device=device) * 0.02).to(dtype) \
+            if with_head else None
+        norm_w = (1.0 + 0.1 * torch.randn(cfg.hidden_size, generator=gen, device=device)).to(dtype)
+        layers = []
+        grp = args.weight_quant_params["group_size"]
+        for li in range(n_layers if n_layers is not None else cfg.num_hidden_layers):
+            w = random_block_weights(cfg, li, seed, device, dtype, rank, world, grp)
+            blk = build_block(cfg, w, args, rank, world, tp_group, quantize, drop_dense)
+            blk.self_attn.fast_attention = fast_attention
+            layers.append(blk)
+            del w
+        return cls(cfg, layers, embed, norm_w, head)
+
+    # ------------------------------------------------------------------ forward
+    def _norm(self, x):
+        dt = x.dtype
+        var = x.to(torch.float32).pow(2).mean(-1, keepdim=True)
+        return (self.norm_weight * (x * torch.rsqrt(var + self.cfg.rms_norm_eps))).to(dt)
+
+    @staticmethod
+    def causal_mask(bsz, q_len, kv_len, dtype, device):
+        m = torch.full((q_len, kv_len), torch.finfo(dtype).min, dtype=dtype, device=device)
+        i = torch.arange(q_len, device=device).unsqueeze(1)
+        j = torch.arange(kv_len, device=device).unsqueeze(0)
+        m = m.masked_fill(j <= i + (kv_len - q_len), 0.0)
+        return m[None, None].expand(bsz, 1, q_len, kv_len)
+
+    @torch.no_grad()
+    def forward(self, tokens: torch.Tensor, past=None, use_cache=False):
+        """LlamaModel.forward: hidden states after the final norm (+ the new cache)."""
+        bsz, q_len = tokens.shape
+        past_len = 0 if past is None else past[0][0].shape[-2]
+        x = F.embedding(tokens, self.embed_tokens)
+        fast = all(l.self_attn.fast_attention and not l.self_attn.use_act_quant for l in self.layers)
+        mask = None
+        if not (fast and (q_len == 1 or past_len == 0)):
+            mask = self.causal_mask(bsz, q_len, past_len + q_len, x.dtype, x.device)
+        pos = torch.arange(past_len, past_len + q_len, device=x.device).unsqueeze(0)
+        new_past = []
+        for i, layer in enumerate(self.layers):
+            out = layer(x, attention_mask=mask, position_ids=pos,
+                        past_key_value=None if past is None else past[i], use_cache=use_cache)
+            x = out[0]
+            if use_cache:
+                new_past.append(out[-1])
+        x = self._norm(x)
+        return (x, new_past) if use_cache else x
+
+    @torch.no_grad()
+    def logits(self, tokens):
+        return F.linear(self.forward(tokens), self.lm_head)
+
+    @torch.no_grad()
+    def perplexity(self, testenc: torch.Tensor, seqlen: int):
+        """main.py:122-151 on a [1, n] token tensor; returns (ppl, mean nll per token)."""
+        nsamples = testenc.numel() // seqlen
+        nlls = []
+        for i in range(nsamples):
+            batch = testenc[:, (i * seqlen): ((i + 1) * seqlen)].to(self.embed_tokens.device)
+            lg = self.logits(batch)
+            shift_logits = lg[:, :-1, :]
+            shift_labels = batch[:, 1:]
+            loss = F.cross_entropy(shift_logits.reshape(-1, shift_logits.size(-1)).float(), shift_labels.reshape(-1))
+            nlls.append(loss.float() * seqlen)
+        mean_nll = torch.stack(nlls).sum() / (nsamples * seqlen)
+        return math.exp(mean_nll.item()), mean_nll.item()

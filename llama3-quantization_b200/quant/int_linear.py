@@ -94,6 +94,44 @@ class QuantLinear(nn.Module):
         self._requant_cache = (key, (pw, wq.scale, wq.round_zero_point))
         return pw
 
+    def packed_operand(self, input: torch.Tensor):
+        """The PackedWeight ``forward(input)`` would hand to the fused dequant-GEMM, or None when
+        forward would take the dense ``F.linear`` route (temporary parameters, autograd, custom
+        ``fwd_func``, unsupported shape).  Lets a caller that owns several linears on the same
+        input (q|k|v, gate|up) run them as one launch (models/int_llama_layer.py)."""
+        if self.use_temporary_parameter or not self.use_fused_gemm or self.fwd_func is not F.linear \
+                or self.fwd_kwargs:
+            return None
+        if self.use_weight_quant:
+            if torch.is_grad_enabled() and (
+                    input.requires_grad or self.weight.requires_grad
+                    or any(p.requires_grad for p in self.weight_quantizer.parameters())):
+                return None
+            packed = self._packed_requant()
+        else:
+            if torch.is_grad_enabled() and (input.requires_grad or self.weight.requires_grad):
+                return None
+            packed = self.weight_quantizer.packed_for(self.weight)
+        if packed is None or not input.is_cuda:
+            return None
+        if not (packed.K % 128 == 0 and packed.N % 8 == 0
+                and (packed.group in (32, 64) or packed.group % 128 == 0)):
+            return None
+        return packed
+
+    def release_dense_weight(self) -> bool:
+        """Inference-only extension: free the dense fake-quantised ``weight`` buffer and keep only its
+        packed twin (0.5 B/weight at W4 instead of 2.5).  ``weight`` becomes an empty tensor of the same
+        dtype/device; forward() keeps working through the fused dequant-GEMM.  Returns False (and changes
+        nothing) when there is no packed twin."""
+        pw = self.weight_quantizer.packed_for(self.weight)
+        if pw is None:
+            return False
+        self.weight = torch.empty(0, dtype=self.weight.dtype, device=self.weight.device)
+        self.weight_quantizer._packed_of = (self.weight.data_ptr(), self.weight._version,
+                                            tuple(self.weight.shape), self.weight.dtype)
+        return True
+
     def forward(self, input: torch.Tensor):
         packed = None
         weight = None
