@@ -61,8 +61,7 @@ struct SkinnyArgs {
   const void* meta;       // [K/group, N, 2] T
   const void* bias;       // [N] T or null
   void* y;                // [M, N] T
-  float* ws_partials;     // workspace: fp32 partial tiles
-  int* ws_counters;       // workspace: one arrival counter per 16-row fragment (zero between launches)
+  uint2* ws_partials;     // workspace: fp32 partial fragments as {value, flag} pairs (all zero between launches)
   int M, N, K, group;
   int kblocks;            // K / 128 = stream-K units per tile
   int n_tiles;
@@ -76,6 +75,7 @@ struct SkinnyArgs {
   int stages;             // ring depth
   int nsub;               // (scale, zero) rows per block: 128 / group for group < 128, else 1
   int pdl;                // launch with programmatic stream serialization
+  int seq;                // launch sequence number (timing builds)
 };
 
 // One [128 rows x 64 k] tile of codes; a block = two tiles.  In shared memory the second tile is placed
@@ -295,9 +295,23 @@ __device__ __forceinline__ void mbar_wait_tight_u32(uint32_t bar, uint32_t parit
       :: "r"(bar), "r"(parity) : "memory");
 }
 
+// 8-byte accesses of the stream-K fix-up slots: .volatile keeps them out of L1 and un-merged; an aligned
+// 8-byte access is single-copy atomic, so {value, flag} is observed whole or not at all
+__device__ __forceinline__ uint2 ld_volatile_u2(const uint2* p) {
+  uint2 v;
+  asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u2(uint2* p, uint2 v) {
+  asm volatile("st.volatile.global.v2.u32 [%0], {%1,%2};" :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+
 #ifdef SK_TIMING
 // debug build: per-CTA cycle breakdown (consumer warp 0 / producer), read back by q100_debug_skinny_timing
 __device__ long long g_sk_t[2048][8];
+// per-launch wall-clock stamps (globaltimer, ns): [launch % 16][cta][entry, after pdl_wait, before resolve, end]
+__device__ long long g_sk_w[16][512][4];
+__device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 #define SK_T(var) const long long var = clock64()
 #else
 #define SK_T(var)
@@ -327,6 +341,9 @@ k3_skinny(const SkinnyArgs a) {
   const int warp = tid >> 5, lane = tid & 31;
   const int G = gridDim.x, U = a.total_units;
   const int cta = blockIdx.x;
+#ifdef SK_TIMING
+  if (tid == 0 && cta < 512) g_sk_w[a.seq & 15][cta][0] = gtime();
+#endif
   const int q_begin = static_cast<int>(static_cast<int64_t>(cta) * U / G);
   const int q_end = static_cast<int>(static_cast<int64_t>(cta + 1) * U / G);
   const int kblocks = a.kblocks;
@@ -636,37 +653,58 @@ k3_skinny(const SkinnyArgs a) {
       }
   };
 
-  // end of a tile segment [seg_begin, q]: write y or hand the fragment to the stream-K fix-up.  The fix-up
-  // is split in two so that the round trip of the arrival counter overlaps the next block's math:
-  // finish_segment() stores the partial fragment and ISSUES the counter RMW; resolve_pending(), one block
-  // later (or at the end of the CTA's run), looks at its result and -- if this warp was the last
-  // contributor of the fragment -- sums the slots in slot order (deterministic) and writes y.
-  int pend_tile = -1, pend_old = 0, pend_n = 0;
+  // end of a tile segment [seg_begin, q]: write y or hand the fragment to the stream-K fix-up.
+  // Fix-up protocol ("LL": data and flag travel in one 8-byte store, which is single-copy atomic, so no
+  // fence, no atomic and no counter is needed): every contributor of a shared tile stores its fp32
+  // fragment as {value, 1} pairs into its slot and moves on.  The CTA that owns the tile's LAST unit is the
+  // reducer.  Units are processed in increasing order, so that CTA meets the shared tile at the START of
+  // its run: it stores its own fragment like everybody else and defers the reduction to the END of its run,
+  // when the other contributors (lower-numbered CTAs, which reach the tile at the end of THEIR runs) are
+  // finishing too.  It then polls the slots in slot order (deterministic sum), writes y and resets the
+  // flags, leaving the workspace zeroed for the next launch.  The reducer only ever waits for
+  // lower-numbered CTAs, which the hardware dispatches first, so the wait cannot deadlock a partially
+  // resident grid.
+  int pend_tile = -1, pend_n = 0;
   auto slot_base = [&](int tile) {
-    // slot layout: [slot][warp][mb][reg][lane]; this warp only ever touches its own [warp] part
+    // slot layout: [slot][warp][mb][reg][lane] of {value, flag}; this warp only ever touches its own [warp] part
     return a.ws_partials + static_cast<int64_t>(tile) * a.max_slots * FRAG + warp * (MB * 4 * 32);
   };
   auto resolve_pending = [&]() {
-    const int old = __shfl_sync(0xffffffffu, pend_old, 0);
-    __syncwarp();
-    if (old == pend_n - 1) {
-      // last contributor of this 16-row fragment: all slots are visible
-      const float* wst = slot_base(pend_tile);
-      float v[MB][4];
+    uint2* wst = slot_base(pend_tile);
+    float v[MB][4];
 #pragma unroll
-      for (int mb = 0; mb < MB; ++mb)
+    for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
-        for (int r = 0; r < 4; ++r) v[mb][r] = 0.f;
-      for (int sl = 0; sl < pend_n; ++sl) {
+      for (int r = 0; r < 4; ++r) v[mb][r] = 0.f;
+    uint2 cur[MB * 4];
+    auto fetch = [&](uint2 (&dst)[MB * 4], int sl) {
 #pragma unroll
-        for (int mb = 0; mb < MB; ++mb)
+      for (int i = 0; i < MB * 4; ++i) dst[i] = ld_volatile_u2(wst + static_cast<int64_t>(sl) * FRAG + i * 32 + lane);
+    };
+    fetch(cur, 0);
+    for (int sl = 0; sl < pend_n; ++sl) {
+      uint2 nxt[MB * 4];
+      if (MB <= 2 && sl + 1 < pend_n) fetch(nxt, sl + 1);        // next slot's round trip overlaps this one's poll
+      for (;;) {
+        uint32_t ok = 1;
 #pragma unroll
-          for (int r = 0; r < 4; ++r)
-            v[mb][r] += __ldcg(wst + static_cast<int64_t>(sl) * FRAG + (mb * 4 + r) * 32 + lane);
+        for (int i = 0; i < MB * 4; ++i) ok &= cur[i].y;
+        if (__all_sync(0xffffffffu, ok != 0)) break;
+        fetch(cur, sl);
       }
-      write_fragment(v, pend_tile * SK_ROWS);
-      if (lane == 0) a.ws_counters[pend_tile * 8 + warp] = 0;     // leave the workspace clean
+#pragma unroll
+      for (int i = 0; i < MB * 4; ++i) {
+        v[i >> 2][i & 3] += __uint_as_float(cur[i].x);
+        wst[static_cast<int64_t>(sl) * FRAG + i * 32 + lane] = make_uint2(0u, 0u);     // leave the workspace clean
+      }
+      if (MB <= 2) {
+#pragma unroll
+        for (int i = 0; i < MB * 4; ++i) cur[i] = nxt[i];
+      } else if (sl + 1 < pend_n) {
+        fetch(cur, sl + 1);
+      }
     }
+    write_fragment(v, pend_tile * SK_ROWS);
     pend_tile = -1;
   };
   auto finish_segment = [&](int q, int seg_begin) {
@@ -678,19 +716,16 @@ k3_skinny(const SkinnyArgs a) {
     } else {
       const int c_first = unit_owner(tile_q0, G, U);
       const int c_last = unit_owner(tile_q1 - 1, G, U);
-      float* wsp = slot_base(tile) + static_cast<int64_t>(cta - c_first) * FRAG;
+      uint2* wsp = slot_base(tile) + static_cast<int64_t>(cta - c_first) * FRAG;
 #pragma unroll
       for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
-        for (int r = 0; r < 4; ++r) wsp[(mb * 4 + r) * 32 + lane] = acc[mb][r];
-      // publish: the warp barrier orders the lanes' stores before lane 0's acq_rel RMW (release for our
-      // slot, acquire for the slots of the CTAs that arrived earlier); the shuffle + barrier in
-      // resolve_pending() order the other lanes' reads behind that acquire.  No MEMBAR.SC needed.
-      __syncwarp();
-      int* cnt = a.ws_counters + tile * 8 + warp;
-      if (lane == 0) asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], 1;" : "=r"(pend_old) : "l"(cnt) : "memory");
-      pend_tile = tile;
-      pend_n = c_last - c_first + 1;
+        for (int r = 0; r < 4; ++r)
+          st_volatile_u2(wsp + (mb * 4 + r) * 32 + lane, make_uint2(__float_as_uint(acc[mb][r]), 1u));
+      if (cta == c_last) {                                    // reduce at the end of this CTA's run
+        pend_tile = tile;
+        pend_n = c_last - c_first + 1;
+      }
     }
 #pragma unroll
     for (int mb = 0; mb < MB; ++mb) { acc[mb][0] = acc[mb][1] = acc[mb][2] = acc[mb][3] = 0.f; }
@@ -699,6 +734,7 @@ k3_skinny(const SkinnyArgs a) {
   pdl_wait();                                   // x, y and the workspace belong to the stream order
 #ifdef SK_TIMING
   const long long c_t0 = clock64(); long long c_stage = 0, c_wait = 0, c_fin = 0, c_comp = 0;
+  if (tid == 0 && cta < 512) g_sk_w[a.seq & 15][cta][1] = gtime();
 #endif
 
   int seg_begin = q_begin;                      // first block of the current tile segment
@@ -738,7 +774,6 @@ k3_skinny(const SkinnyArgs a) {
       const long long tc1 = clock64(); c_comp += tc1 - tw1;
 #endif
       const int q = qc + bl;
-      if (pend_tile >= 0) resolve_pending();
       if (++kb == kblocks || q == q_end - 1) {
         finish_segment(q, seg_begin);
         seg_begin = q + 1;
@@ -749,8 +784,12 @@ k3_skinny(const SkinnyArgs a) {
       }
     }
   }
+#ifdef SK_TIMING
+  if (tid == 0 && cta < 512) g_sk_w[a.seq & 15][cta][2] = pend_tile >= 0 ? gtime() : -gtime();
+#endif
   if (pend_tile >= 0) resolve_pending();
 #ifdef SK_TIMING
+  if (tid == 0 && cta < 512) g_sk_w[a.seq & 15][cta][3] = gtime();
   if (tid == 0) {
     g_sk_t[cta][0] = clock64() - c_t0; g_sk_t[cta][1] = c_stage; g_sk_t[cta][2] = c_wait; g_sk_t[cta][3] = c_comp;
     g_sk_t[cta][4] = c_fin; g_sk_t[cta][5] = q_end - q_begin;
@@ -864,6 +903,7 @@ static int launch_skinny_bits(int n_bits, const SkinnyArgs& a, cudaStream_t st) 
 
 #ifdef SK_TIMING
 int skinny_timing(long long* out, int n) {
+  if (n < 0) return check_cuda(cudaMemcpyFromSymbol(out, g_sk_w, sizeof(g_sk_w)), "wall timing readback");
   return check_cuda(cudaMemcpyFromSymbol(out, g_sk_t, sizeof(long long) * 8 * n), "timing readback");
 }
 #endif
@@ -871,7 +911,7 @@ int skinny_timing(long long* out, int n) {
 size_t skinny_workspace_bytes(int64_t M, int64_t N, int64_t K) {
   const SkinnyPlan p = plan_skinny(N, K);
   const int mb = M <= 8 ? 1 : M <= 16 ? 2 : 4;
-  const size_t partials = static_cast<size_t>(p.n_tiles) * p.max_slots * SK_ROWS * mb * 8 * sizeof(float);
+  const size_t partials = static_cast<size_t>(p.n_tiles) * p.max_slots * SK_ROWS * mb * 8 * sizeof(uint2);
   return partials + SK_COUNTER_BYTES;
 }
 
@@ -892,12 +932,9 @@ int gemm_skinny(const void* x, const void* packed, const void* meta, const void*
 
   SkinnyArgs a{};
   a.x = x; a.packed = packed; a.meta = meta; a.bias = bias; a.y = y;
-  a.ws_counters = reinterpret_cast<int*>(workspace);
-  // counters live in a fixed-size prefix so that partials of one launch can never land on what a
-  // later launch (different N) uses as counters: the prefix is the only part that must stay zero
-  Q100_REQUIRE(static_cast<size_t>(p.n_tiles) * 8 * sizeof(int) <= SK_COUNTER_BYTES, Q100_EUNSUPPORTED,
-               "N=%lld too large for the stream-K counter area", (long long)N);
-  a.ws_partials = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(workspace) + SK_COUNTER_BYTES);
+  // the first SK_COUNTER_BYTES of the workspace belong to the arrival counters of the tcgen05 streaming
+  // kernel (q100_gemm_stream.cu); this kernel's {value, flag} slots start behind them and are left zeroed
+  a.ws_partials = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(workspace) + SK_COUNTER_BYTES);
   a.M = static_cast<int>(M); a.N = static_cast<int>(N); a.K = static_cast<int>(K); a.group = g;
   a.kblocks = static_cast<int>(K / SK_KB);
   a.n_tiles = p.n_tiles;
@@ -908,6 +945,8 @@ int gemm_skinny(const void* x, const void* packed, const void* meta, const void*
   a.m_rows = static_cast<int>(M);
   a.nsub = g >= SK_KB ? 1 : SK_KB / g;
   a.pdl = pdl;
+  static int launch_seq = 0;
+  a.seq = launch_seq++;
   if (dtype == Q100_F16) return launch_skinny_bits<__half>(n_bits, a, st);
   return launch_skinny_bits<__nv_bfloat16>(n_bits, a, st);
 }

@@ -352,7 +352,11 @@ k3_stream(const __grid_constant__ CUtensorMap tm_x, const StreamArgs a) {
         for (int m = 0; m < MB; ++m) v[m] = 0.f;
         for (int sl = 0; sl < pend_n; ++sl) {
 #pragma unroll
-          for (int m = 0; m < MB; ++m) v[m] += __ldcg(wst + static_cast<int64_t>(sl) * FRAG + m * ST_ROWS + row);
+          for (int m = 0; m < MB; ++m) {
+            float* pp = const_cast<float*>(wst) + static_cast<int64_t>(sl) * FRAG + m * ST_ROWS + row;
+            v[m] += __ldcg(pp);
+            *pp = 0.f;           // the workspace is shared with K3a, whose {value, flag} slots must find zeros
+          }
         }
         write_rows(v, pend_tile);
         if (lane == 0) a.ws_counters[pend_tile * 8 + warp] = 0;

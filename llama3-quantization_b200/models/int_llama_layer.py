@@ -105,6 +105,23 @@ def repeat_kv(hidden_states: torch.Tensor, n_rep: int) -> torch.Tensor:
     return hidden_states.reshape(batch, num_key_value_heads * n_rep, slen, head_dim)
 
 
+class StaticKV:
+    """Extension for CUDA-graph decode: a preallocated ``[bsz, kv_heads, max_len, head_dim]`` K/V pair written
+    in place at ``position_ids`` (a device tensor), so a decode step has fixed shapes and can be captured.
+    Passing one as ``past_key_value`` replaces the reference's ``torch.cat`` cache (int_llama_layer.py:130-133);
+    the caller supplies an attention mask over ``max_len`` that hides the slots not written yet."""
+
+    def __init__(self, bsz, kv_heads, max_len, head_dim, dtype, device):
+        self.k = torch.zeros(bsz, kv_heads, max_len, head_dim, dtype=dtype, device=device)
+        self.v = torch.zeros_like(self.k)
+
+    def update(self, k_new, v_new, position_ids):
+        idx = position_ids.reshape(-1)[-k_new.shape[2]:]
+        self.k.index_copy_(2, idx, k_new.to(self.k.dtype))
+        self.v.index_copy_(2, idx, v_new.to(self.v.dtype))
+        return self.k, self.v
+
+
 # ------------------------------------------------------------------------------------ fused launches
 class _FusedLinears:
     """Several QuantLinears that consume the same input, run as one dequant-GEMM on the concatenation
@@ -241,18 +258,24 @@ class QuantLlamaAttention(nn.Module):
         key_states = k.view(bsz, q_len, nkv, self.head_dim).transpose(1, 2)
         value_states = v.view(bsz, q_len, nkv, self.head_dim).transpose(1, 2)
 
+        static_kv = past_key_value if isinstance(past_key_value, StaticKV) else None
         kv_seq_len = key_states.shape[-2]
-        if past_key_value is not None:
+        if static_kv is not None:
+            kv_seq_len = static_kv.k.shape[-2]
+        elif past_key_value is not None:
             kv_seq_len += past_key_value[0].shape[-2]
         cos, sin = self.rotary_emb(value_states, seq_len=kv_seq_len)
         if position_ids is None:
             position_ids = torch.arange(kv_seq_len - q_len, kv_seq_len, device=hidden_states.device).unsqueeze(0)
         query_states, key_states = apply_rotary_pos_emb(query_states, key_states, cos, sin, position_ids)
 
-        if past_key_value is not None:
+        if static_kv is not None:
+            key_states, value_states = static_kv.update(key_states, value_states, position_ids)
+        elif past_key_value is not None:
             key_states = torch.cat([past_key_value[0], key_states], dim=2)
             value_states = torch.cat([past_key_value[1], value_states], dim=2)
-        past_key_value = (key_states, value_states) if use_cache else None
+        if static_kv is None:
+            past_key_value = (key_states, value_states) if use_cache else None
 
         if not torch.is_autocast_enabled():
             # the reference leaves Q in fp32 (int_llama_layer.py:117) and relies on autocast to bring both

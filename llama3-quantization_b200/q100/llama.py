@@ -202,3 +202,67 @@ class QuantLlamaModel(nn.Module):
             nlls.append(loss.float() * seqlen)
         mean_nll = torch.stack(nlls).sum() / (nsamples * seqlen)
         return math.exp(mean_nll.item()), mean_nll.item()
+
+
+class GraphDecoder:
+    """One-token decode step of a QuantLlamaModel with fixed shapes (static KV cache, device-side position
+    counter), captured in a CUDA graph: embedding -> blocks -> norm -> lm_head -> argmax.  The reference
+    measures per-token latency with a growing ``torch.cat`` cache and one Python dispatch per op
+    (llama.py:409-465); the arithmetic per token is the same, the launch overhead is not."""
+
+    def __init__(self, model: QuantLlamaModel, bsz: int, max_len: int, use_graph: bool = True):
+        from models.int_llama_layer import StaticKV
+        self.model, self.bsz, self.max_len = model, bsz, max_len
+        cfg = model.cfg
+        dev, dt = model.embed_tokens.device, model.embed_tokens.dtype
+        hd = cfg.hidden_size // cfg.num_attention_heads
+        self.caches = []
+        for layer in model.layers:
+            nkv = max(cfg.num_key_value_heads // layer.self_attn.tp_world, 1)
+            self.caches.append(StaticKV(bsz, nkv, max_len, hd, dt, dev))
+        self.tok = torch.zeros(bsz, 1, dtype=torch.long, device=dev)
+        self.pos = torch.zeros(1, 1, dtype=torch.long, device=dev)
+        self.next_tok = torch.zeros(bsz, 1, dtype=torch.long, device=dev)
+        self._slots = torch.arange(max_len, device=dev).view(1, 1, 1, max_len)
+        self._neg = torch.finfo(dt).min
+        self.graph = None
+        self.use_graph = use_graph
+
+    def _step(self):
+        m = self.model
+        x = F.embedding(self.tok, m.embed_tokens)
+        mask = torch.where(self._slots <= self.pos.view(1, 1, 1, 1), 0.0, self._neg).to(x.dtype)
+        mask = mask.expand(self.bsz, 1, 1, self.max_len)
+        for layer, kv in zip(m.layers, self.caches):
+            x = layer(x, attention_mask=mask, position_ids=self.pos, past_key_value=kv, use_cache=False)[0]
+        x = m._norm(x)
+        logits = F.linear(x, m.lm_head)
+        self.next_tok.copy_(logits.argmax(-1))
+        self.pos.add_(1)
+
+    @torch.no_grad()
+    def prime(self, start_pos: int = 0):
+        """Warm up (builds rotary caches, fused packs, workspaces) and capture."""
+        self.pos.fill_(start_pos)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self._step()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        if self.use_graph:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self._step()
+        self.pos.fill_(start_pos)
+
+    @torch.no_grad()
+    def step(self, tokens: Optional[torch.Tensor] = None):
+        if tokens is not None:
+            self.tok.copy_(tokens)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._step()
+        return self.next_tok

@@ -1,0 +1,122 @@
+#!/usr/bin/env python
+"""Whole-model rows of the benchmark contract: random-init LLaMA3-8B,
+W{2,3,4}A16 g128, synthetic tokens -- perplexity against the torch port on the same weights, prefill tokens/s at
+seq 2048, per-token decode latency (median) at batch 1-16 with a static KV cache in a CUDA graph.
+
+    python tools/bench_model.py [--layers 32] [--wbits 4] [--ppl-samples 2] [--batches 1,4,16]
+
+Prints one JSON line.  Under torchrun the blocks are tensor parallel (q100/tp.py)."""
+import argparse, json, os, statistics, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (os.path.join(ROOT, "llama3-quantization_b200"), os.path.join(ROOT, "oracle")):
+    sys.path.insert(0, p)
+import torch
+import torch.distributed as dist
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--layers", type=int, default=32)
+    ap.add_argument("--wbits", type=int, default=4)
+    ap.add_argument("--abits", type=int, default=16)
+    ap.add_argument("--group", type=int, default=128)
+    ap.add_argument("--dtype", default="f16")
+    ap.add_argument("--seqlen", type=int, default=2048)
+    ap.add_argument("--ppl-samples", type=int, default=2)
+    ap.add_argument("--ppl-ref", action="store_true", help="also run the torch port (F.linear on fake-quantised weights)")
+    ap.add_argument("--batches", default="1,4,16")
+    ap.add_argument("--decode-steps", type=int, default=64)
+    ap.add_argument("--ctx", type=int, default=256, help="KV positions already filled when decode is timed")
+    ap.add_argument("--no-graph", action="store_true")
+    a = ap.parse_args()
+    from q100 import llama as QL
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    dt = {"f16": torch.float16, "bf16": torch.bfloat16}[a.dtype]
+    cfg = QL.LLAMA3_8B
+    args = QL.quant_args(a.wbits, a.group, a.abits)
+    t0 = time.time()
+    model = QL.QuantLlamaModel.random_init(cfg, args, dev, dt, seed=0, rank=rank, world=world, n_layers=a.layers,
+                                           fast_attention=True)
+    torch.cuda.synchronize()
+    out = {"model": f"llama3-8b random-init, {a.layers} blocks, W{a.wbits}A{a.abits} g{a.group}, {a.dtype}",
+           "tp": world, "build_s": round(time.time() - t0, 2),
+           "hbm_GB_after_build": round(torch.cuda.memory_allocated() / 1e9, 2)}
+    g = torch.Generator().manual_seed(1)
+    testenc = torch.randint(0, cfg.vocab_size, (1, a.ppl_samples * a.seqlen), generator=g)
+    # ---- perplexity (main.py:122-151) ----
+    if a.ppl_samples > 0:
+        for l in model.layers:
+            l.self_attn.fast_attention = False        # reference attention formulation for the parity number
+        ppl, nll = model.perplexity(testenc, a.seqlen)
+        out["ppl"] = {"ppl": ppl, "mean_nll": nll, "tokens": a.ppl_samples * a.seqlen}
+        if a.ppl_ref and world == 1:
+            import llama_port as LP
+            bc = LP.BlockCfg(cfg.hidden_size, cfg.intermediate_size, cfg.num_attention_heads,
+                             cfg.num_key_value_heads, cfg.rms_norm_eps, cfg.rope_theta, a.wbits, a.group, a.abits)
+            blocks = []
+            for li in range(a.layers):
+                w = QL.random_block_weights(cfg, li, 0, dev, dt)
+                blocks.append(LP.fake_quant_weights(w, bc))
+                del w
+
+            def logits_fn(batch):
+                with torch.no_grad():
+                    h = LP.model_forward(batch.to(dev), model.embed_tokens, blocks, model.norm_weight, bc,
+                                         act_quant=a.abits < 16)
+                    return torch.nn.functional.linear(h, model.lm_head).float()
+            ppl_r, nll_r = LP.perplexity(testenc, a.seqlen, logits_fn)
+            out["ppl"].update({"ref_ppl": ppl_r, "ref_mean_nll": nll_r, "delta_mean_nll": nll - nll_r,
+                               "delta_ppl_rel": (ppl - ppl_r) / ppl_r,
+                               "delta_ppl_at_wikitext2_scale(6.1)": 6.1 * (ppl - ppl_r) / ppl_r})
+            del blocks
+            torch.cuda.empty_cache()
+        for l in model.layers:
+            l.self_attn.fast_attention = True
+    # ---- prefill tokens/s ----
+    batch = testenc[:, :a.seqlen].to(dev)
+    for _ in range(2):
+        model.forward(batch)
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    iters = 5
+    for _ in range(iters):
+        model.forward(batch)
+    e.record(); e.synchronize()
+    ms = s.elapsed_time(e) / iters
+    out["prefill"] = {"seq": a.seqlen, "ms": ms, "tokens_per_s": a.seqlen / ms * 1e3}
+    # ---- decode ----
+    out["decode"] = {}
+    for B in [int(b) for b in a.batches.split(",")]:
+        dec = QL.GraphDecoder(model, B, a.ctx + a.decode_steps + 8, use_graph=not a.no_graph)
+        dec.prime(a.ctx)
+        tok = torch.randint(0, cfg.vocab_size, (B, 1), generator=g).to(dev)
+        dec.step(tok)
+        torch.cuda.synchronize()
+        lat = []
+        for i in range(a.decode_steps):
+            s.record()
+            dec.step()
+            e.record(); e.synchronize()
+            lat.append(s.elapsed_time(e))
+        med = statistics.median(lat)
+        w4_bytes = sum(m.weight_quantizer._packed.nbytes() for l in model.layers for m in l._quant_linears()
+                       if m.weight_quantizer._packed is not None)
+        head_bytes = model.lm_head.numel() * model.lm_head.element_size()
+        out["decode"][f"B{B}"] = {"median_ms_per_token": med, "tokens_per_s": B / med * 1e3,
+                                  "weight_stream_GBps": (w4_bytes + head_bytes) / med / 1e6,
+                                  "cuda_graph": dec.graph is not None}
+        del dec
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
