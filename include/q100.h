@@ -150,6 +150,38 @@ int q100_gemm_wna16(const void* x, const void* packed, const void* meta, const v
 size_t q100_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int n_bits, int flags);
 
 /*
+ * K4-K6 -- the memory-bound steps between the quantised linears of a decoder block at decode shapes
+ * (QuantLlamaDecoderLayer.forward, models/int_llama_layer.py:213-262): ~35 eager launches per block and
+ * token in the reference, four here.  fp16 / bf16 only; each reproduces the reference's op order and
+ * per-op rounding (fp32 where torch promotes, one rounding where torch stores).
+ *
+ * q100_add_rmsnorm: h = residual + x (rounded to dtype; skipped when residual == NULL, then h = x),
+ *   norm_out = weight * (h * rsqrt(mean(h^2) + eps))        quant/omni_norm.py:52-63 (OmniLlamaRMSNorm),
+ *   residual adds of int_llama_layer.py:246, 251.  sum_out (nullable) receives h.  [rows, cols],
+ *   cols % 8 == 0, cols <= 8192.
+ */
+int q100_add_rmsnorm(const void* x, const void* residual, const void* weight, float eps,
+                     void* sum_out, void* norm_out, int64_t rows, int64_t cols, int dtype, void* stream);
+/*
+ * q100_rope_kv_decode: one new token per sequence.  qkv [batch, (heads + 2*kv_heads) * head_dim] is the
+ *   fused q|k|v projection; cos_cache / sin_cache [>= position+1, head_dim] in dtype (transformers 4.37
+ *   LlamaRotaryEmbedding); position: DEVICE pointer to one int64 (so a captured graph can advance it).
+ *   q_out [batch, heads, head_dim] = rotary(q) computed in fp32 on the fp32-cast query
+ *   (int_llama_layer.py:117, 125) and rounded once; rotary(k) with every op rounded to dtype and v are
+ *   written to k_cache / v_cache [batch, kv_heads, max_len, head_dim] at `position`
+ *   (the static-cache form of int_llama_layer.py:130-133).
+ */
+int q100_rope_kv_decode(const void* qkv, const void* cos_cache, const void* sin_cache,
+                        const void* position, void* q_out, void* k_cache, void* v_cache,
+                        int batch, int heads, int kv_heads, int head_dim, int64_t max_len,
+                        int dtype, void* stream);
+/*
+ * q100_silu_mul: out[rows, inter] = silu(gate) * up for gate_up [rows, 2*inter] (gate columns first), the
+ *   epilogue of the fused gate|up GEMM: act_fn(gate_proj(x)) * up_proj(x), int_llama_layer.py:45.
+ */
+int q100_silu_mul(const void* gate_up, void* out, int64_t rows, int64_t inter, int dtype, void* stream);
+
+/*
  * Development / verification hooks (used by tests only).
  * q100_selftest_div: exhaustively compares the fast 16-bit division sequence with
  * div.rn.f32 + round over all (x, scale) pairs of `dtype` with scale in [1e-5, 1e4];

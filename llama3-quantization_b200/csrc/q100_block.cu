@@ -1,0 +1,229 @@
+// q100_block.cu -- the small memory-bound steps that sit between the quantised linears of a decoder block
+// at decode shapes (QuantLlamaDecoderLayer.forward, models/int_llama_layer.py:213-262 of the reference):
+//
+//   K4 add_rmsnorm   h = x + residual;  n = OmniLlamaRMSNorm(h)            quant/omni_norm.py:52-63, int_llama_layer.py:246-251
+//   K5 rope_kv       rotary embedding of q and k for the new token(s), K/V written into a static cache
+//                                                                          int_llama_layer.py:114-133
+//   K6 silu_mul      act_fn(gate) * up on the fused gate|up GEMM output    int_llama_layer.py:45
+//
+// In eager torch these are ~35 launches per block and token (the reference's decode loop is launch-bound on
+// them); here they are four, so that a decode step of a block is 4 GEMMs + 4 small kernels + the attention
+// core.  Each kernel reproduces the reference's op sequence and per-op rounding (fp32 where torch promotes,
+// one rounding to the 16-bit storage type where torch stores); only the order of the fp32 sum inside the
+// variance differs from torch's reduction.  All are HBM/L2-latency bound and tiny: one CTA per row / head.
+#include "q100_common.cuh"
+
+namespace q100 {
+
+// ---------------------------------------------------------------- K4: (residual add +) RMSNorm
+// rows x cols, one CTA of 256 threads per row, the row lives in registers (cols <= 8192).
+template <typename T, int VMAX>
+__global__ void __launch_bounds__(256) k4_add_rmsnorm(const T* __restrict__ x, const T* __restrict__ res,
+                                                      const T* __restrict__ w, float eps, T* __restrict__ sum_out,
+                                                      T* __restrict__ norm_out, int cols) {
+  using D = DT<T>;
+  const int64_t row = blockIdx.x;
+  const int nvec = cols >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + row * cols);
+  const uint4* rr = res ? reinterpret_cast<const uint4*>(res + row * cols) : nullptr;
+  uint4 h[VMAX];
+  float ss = 0.f;
+#pragma unroll
+  for (int k = 0; k < VMAX; ++k) {
+    const int v = threadIdx.x + k * 256;
+    if (v < nvec) {
+      uint4 a = xr[v];
+      if (rr) {
+        const uint4 b = rr[v];
+        uint32_t* aw = reinterpret_cast<uint32_t*>(&a);
+        const uint32_t* bw = reinterpret_cast<const uint32_t*>(&b);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {                       // residual + hidden_states, rounded to T
+          const float2 fa = D::to_f2(aw[j]), fb = D::to_f2(bw[j]);
+          aw[j] = D::pack2(__fadd_rn(fb.x, fa.x), __fadd_rn(fb.y, fa.y));
+        }
+        if (sum_out) reinterpret_cast<uint4*>(sum_out + row * cols)[v] = a;
+      }
+      h[k] = a;
+      const uint32_t* aw = reinterpret_cast<const uint32_t*>(&a);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = D::to_f2(aw[j]);
+        ss = fmaf(f.x, f.x, ss);
+        ss = fmaf(f.y, f.y, ss);
+      }
+    }
+  }
+  __shared__ float red[8];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, d);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += red[i];
+  const float inv = rsqrtf(__fadd_rn(__fdiv_rn(tot, static_cast<float>(cols)), eps));
+  const uint4* wr = reinterpret_cast<const uint4*>(w);
+#pragma unroll
+  for (int k = 0; k < VMAX; ++k) {
+    const int v = threadIdx.x + k * 256;
+    if (v < nvec) {
+      const uint4 wv = wr[v];
+      const uint32_t* hw = reinterpret_cast<const uint32_t*>(&h[k]);
+      const uint32_t* ww = reinterpret_cast<const uint32_t*>(&wv);
+      uint4 o;
+      uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {                         // weight * (h * rsqrt(var + eps)), both products in fp32
+        const float2 f = D::to_f2(hw[j]), g = D::to_f2(ww[j]);
+        ow[j] = D::pack2(__fmul_rn(g.x, __fmul_rn(f.x, inv)), __fmul_rn(g.y, __fmul_rn(f.y, inv)));
+      }
+      reinterpret_cast<uint4*>(norm_out + row * cols)[v] = o;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- K5: rotary + KV-cache append (decode)
+// grid (heads_total, B), D/2 threads: thread i owns the pair (i, i + D/2) of one head of one token.
+// q: fp32 math on the fp32-cast query (int_llama_layer.py:117, 125), one rounding to T at the end;
+// k: every op rounded to T (fp16/bf16 tensor math); v: copied.
+template <typename T>
+__global__ void k5_rope_kv(const T* __restrict__ qkv, const T* __restrict__ cosb, const T* __restrict__ sinb,
+                           const int64_t* __restrict__ pos_p, T* __restrict__ q_out, T* __restrict__ k_cache,
+                           T* __restrict__ v_cache, int H, int KVH, int D, int64_t max_len) {
+  using Dt = DT<T>;
+  const int head = blockIdx.x, b = blockIdx.y, i = threadIdx.x, half = D >> 1;
+  const int64_t pos = *pos_p;
+  const T* src = qkv + static_cast<int64_t>(b) * (H + 2 * KVH) * D + static_cast<int64_t>(head) * D;
+  const float x1 = Dt::to_f(src[i]), x2 = Dt::to_f(src[i + half]);
+  if (head >= H + KVH) {                                   // value head: plain copy into the cache
+    T* dst = v_cache + ((static_cast<int64_t>(b) * KVH + (head - H - KVH)) * max_len + pos) * D;
+    dst[i] = src[i];
+    dst[i + half] = src[i + half];
+    return;
+  }
+  const float c1 = Dt::to_f(cosb[pos * D + i]), c2 = Dt::to_f(cosb[pos * D + i + half]);
+  const float s1 = Dt::to_f(sinb[pos * D + i]), s2 = Dt::to_f(sinb[pos * D + i + half]);
+  if (head < H) {
+    T* dst = q_out + (static_cast<int64_t>(b) * H + head) * D;
+    dst[i] = Dt::from_f(__fadd_rn(__fmul_rn(x1, c1), __fmul_rn(-x2, s1)));
+    dst[i + half] = Dt::from_f(__fadd_rn(__fmul_rn(x2, c2), __fmul_rn(x1, s2)));
+  } else {
+    T* dst = k_cache + ((static_cast<int64_t>(b) * KVH + (head - H)) * max_len + pos) * D;
+    dst[i] = Dt::from_f(__fadd_rn(Dt::rd(__fmul_rn(x1, c1)), Dt::rd(__fmul_rn(-x2, s1))));
+    dst[i + half] = Dt::from_f(__fadd_rn(Dt::rd(__fmul_rn(x2, c2)), Dt::rd(__fmul_rn(x1, s2))));
+  }
+}
+
+// ---------------------------------------------------------------- K6: silu(gate) * up
+// gate_up [M, 2I] (gate columns first), out [M, I]; 8 elements per thread.
+template <typename T>
+__global__ void __launch_bounds__(256) k6_silu_mul(const T* __restrict__ gu, T* __restrict__ out, int64_t M, int I) {
+  using D = DT<T>;
+  const int vec_per_row = I >> 3;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= M * vec_per_row) return;
+  const int64_t m = idx / vec_per_row;
+  const int v = static_cast<int>(idx - m * vec_per_row);
+  const uint4 g = reinterpret_cast<const uint4*>(gu + m * 2 * I)[v];
+  const uint4 u = reinterpret_cast<const uint4*>(gu + m * 2 * I + I)[v];
+  const uint32_t* gw = reinterpret_cast<const uint32_t*>(&g);
+  const uint32_t* uw = reinterpret_cast<const uint32_t*>(&u);
+  uint4 o;
+  uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 a = D::to_f2(gw[j]), b = D::to_f2(uw[j]);
+    const float sx = D::rd(__fdiv_rn(a.x, __fadd_rn(1.0f, expf(-a.x))));     // F.silu: fp32 math, stored as T
+    const float sy = D::rd(__fdiv_rn(a.y, __fadd_rn(1.0f, expf(-a.y))));
+    ow[j] = D::pack2(__fmul_rn(sx, b.x), __fmul_rn(sy, b.y));
+  }
+  reinterpret_cast<uint4*>(out + m * I)[v] = o;
+}
+
+template <typename T>
+static int launch_add_rmsnorm(const void* x, const void* res, const void* w, float eps, void* sum_out,
+                              void* norm_out, int64_t rows, int cols, cudaStream_t st) {
+  const int nvec = cols / 8;
+  const T* xp = reinterpret_cast<const T*>(x);
+  const T* rp = reinterpret_cast<const T*>(res);
+  const T* wp = reinterpret_cast<const T*>(w);
+  T* sp = reinterpret_cast<T*>(sum_out);
+  T* np_ = reinterpret_cast<T*>(norm_out);
+  const unsigned grid = static_cast<unsigned>(rows);
+  if (nvec <= 256) k4_add_rmsnorm<T, 1><<<grid, 256, 0, st>>>(xp, rp, wp, eps, sp, np_, cols);
+  else if (nvec <= 512) k4_add_rmsnorm<T, 2><<<grid, 256, 0, st>>>(xp, rp, wp, eps, sp, np_, cols);
+  else k4_add_rmsnorm<T, 4><<<grid, 256, 0, st>>>(xp, rp, wp, eps, sp, np_, cols);
+  return check_cuda(cudaGetLastError(), "k4_add_rmsnorm launch");
+}
+
+}  // namespace q100
+
+using namespace q100;
+
+extern "C" int q100_add_rmsnorm(const void* x, const void* residual, const void* weight, float eps,
+                                void* sum_out, void* norm_out, int64_t rows, int64_t cols, int dtype,
+                                void* stream) {
+  Q100_REQUIRE(x && weight && norm_out, Q100_EINVAL, "NULL pointer argument");
+  Q100_REQUIRE(dtype == Q100_F16 || dtype == Q100_BF16, Q100_EUNSUPPORTED, "fp16 / bf16 only (got dtype %d)", dtype);
+  Q100_REQUIRE(rows >= 0 && cols > 0 && cols % 8 == 0 && cols <= 8192, Q100_EUNSUPPORTED,
+               "cols=%lld: multiple of 8, at most 8192", (long long)cols);
+  Q100_REQUIRE(rows < (1ll << 31), Q100_EINVAL, "too many rows");
+  if (rows == 0) return Q100_OK;
+  int rc = ensure_device();
+  if (rc != Q100_OK) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == Q100_F16)
+    return launch_add_rmsnorm<__half>(x, residual, weight, eps, sum_out, norm_out, rows, static_cast<int>(cols), st);
+  return launch_add_rmsnorm<__nv_bfloat16>(x, residual, weight, eps, sum_out, norm_out, rows, static_cast<int>(cols), st);
+}
+
+extern "C" int q100_rope_kv_decode(const void* qkv, const void* cos_cache, const void* sin_cache,
+                                   const void* position, void* q_out, void* k_cache, void* v_cache,
+                                   int batch, int heads, int kv_heads, int head_dim, int64_t max_len,
+                                   int dtype, void* stream) {
+  Q100_REQUIRE(qkv && cos_cache && sin_cache && position && q_out && k_cache && v_cache, Q100_EINVAL,
+               "NULL pointer argument");
+  Q100_REQUIRE(dtype == Q100_F16 || dtype == Q100_BF16, Q100_EUNSUPPORTED, "fp16 / bf16 only (got dtype %d)", dtype);
+  Q100_REQUIRE(batch >= 0 && heads > 0 && kv_heads > 0 && head_dim >= 2 && head_dim % 2 == 0 && head_dim <= 2048 &&
+               max_len > 0, Q100_EINVAL, "bad shape");
+  if (batch == 0) return Q100_OK;
+  int rc = ensure_device();
+  if (rc != Q100_OK) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const dim3 grid(heads + 2 * kv_heads, batch);
+  const int64_t* pos = reinterpret_cast<const int64_t*>(position);
+  if (dtype == Q100_F16)
+    k5_rope_kv<__half><<<grid, head_dim / 2, 0, st>>>(
+        reinterpret_cast<const __half*>(qkv), reinterpret_cast<const __half*>(cos_cache),
+        reinterpret_cast<const __half*>(sin_cache), pos, reinterpret_cast<__half*>(q_out),
+        reinterpret_cast<__half*>(k_cache), reinterpret_cast<__half*>(v_cache), heads, kv_heads, head_dim, max_len);
+  else
+    k5_rope_kv<__nv_bfloat16><<<grid, head_dim / 2, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(cos_cache),
+        reinterpret_cast<const __nv_bfloat16*>(sin_cache), pos, reinterpret_cast<__nv_bfloat16*>(q_out),
+        reinterpret_cast<__nv_bfloat16*>(k_cache), reinterpret_cast<__nv_bfloat16*>(v_cache), heads, kv_heads,
+        head_dim, max_len);
+  return check_cuda(cudaGetLastError(), "k5_rope_kv launch");
+}
+
+extern "C" int q100_silu_mul(const void* gate_up, void* out, int64_t rows, int64_t inter, int dtype, void* stream) {
+  Q100_REQUIRE(gate_up && out, Q100_EINVAL, "NULL pointer argument");
+  Q100_REQUIRE(dtype == Q100_F16 || dtype == Q100_BF16, Q100_EUNSUPPORTED, "fp16 / bf16 only (got dtype %d)", dtype);
+  Q100_REQUIRE(rows >= 0 && inter > 0 && inter % 8 == 0 && inter < (1ll << 31), Q100_EUNSUPPORTED,
+               "inter=%lld must be a positive multiple of 8", (long long)inter);
+  if (rows == 0) return Q100_OK;
+  int rc = ensure_device();
+  if (rc != Q100_OK) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t total = rows * (inter / 8);
+  const unsigned grid = static_cast<unsigned>((total + 255) / 256);
+  if (dtype == Q100_F16)
+    k6_silu_mul<__half><<<grid, 256, 0, st>>>(reinterpret_cast<const __half*>(gate_up), reinterpret_cast<__half*>(out),
+                                              rows, static_cast<int>(inter));
+  else
+    k6_silu_mul<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(gate_up),
+                                                     reinterpret_cast<__nv_bfloat16*>(out), rows,
+                                                     static_cast<int>(inter));
+  return check_cuda(cudaGetLastError(), "k6_silu_mul launch");
+}

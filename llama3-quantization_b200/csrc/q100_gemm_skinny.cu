@@ -53,6 +53,8 @@ constexpr int SK_CHUNK_MAX = 128;   // k blocks of x staged in shared memory at 
 #define SK_OCC 3                   // resident CTAs per SM the kernel is sized for (2 for M > 16)
 #endif
 constexpr size_t SK_COUNTER_BYTES = 1 << 18;   // workspace prefix: per-fragment arrival counters (N <= 1 M rows)
+constexpr int SK_MAX_SPLIT = 4;    // contributors per tile the stream-K split aims for on small problems
+constexpr int SK_SPLIT_UNITS = 8;  // ... as long as that keeps a CTA at or below this many blocks
 constexpr int SK_XPITCH = 320;     // bytes per (m, 128-k) x row in smem: 256 + 64 pad (conflict-free LDS.128)
 
 struct SkinnyArgs {
@@ -809,6 +811,14 @@ static SkinnyPlan plan_skinny(int64_t N, int64_t K) {
   p.total_units = p.n_tiles * kblocks;
   int grid = sm_count() * SK_OCC;             // upper bound of the persistent grid
   if (grid > p.total_units) grid = p.total_units;
+  // small problems: do not cut a tile more than SK_MAX_SPLIT ways unless a CTA would get more than
+  // SK_SPLIT_UNITS blocks.  Measured with globaltimer stamps (profiles/r02_decode_timeline.txt): o_proj
+  // (32 tiles x 32 blocks) cut 14 ways over 444 CTAs spends 4.6 us in the reducer's wait; 128 CTAs of 8
+  // blocks finish in 8.5 us instead of 10.9 us.
+  int min_units = (kblocks + SK_MAX_SPLIT - 1) / SK_MAX_SPLIT;
+  if (min_units > SK_SPLIT_UNITS) min_units = SK_SPLIT_UNITS;
+  const int cap = (p.total_units + min_units - 1) / min_units;
+  if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
   p.grid_cap = grid;
   // a tile of `kblocks` units can be touched by at most this many CTAs
@@ -863,6 +873,7 @@ static int launch_skinny(SkinnyArgs a, cudaStream_t st) {
   // persistent grid: every CTA resident at once, units split evenly (stream-K)
   int grid = sm_count() * (occ > SK_OCC ? SK_OCC : occ);
   if (grid > a.total_units) grid = a.total_units;
+  if (grid > grid_est) grid = grid_est;         // split cap, see plan_skinny
   Q100_REQUIRE(static_cast<int64_t>(a.kblocks) * grid / a.total_units + 2 <= a.max_slots, Q100_EWORKSPACE,
                "internal: slot bound");
   cudaLaunchConfig_t cfg{};

@@ -139,9 +139,10 @@ class _FusedLinears:
                                  torch.cat([p.scales for p in parts], dim=0), zeros,
                                  p0.n_bits, p0.group, sum(p.N for p in parts), p0.K, p0.disable_zero_point)
 
-    def __call__(self, mods, x: torch.Tensor):
-        """Returns the outputs of ``mods`` on ``x`` (a tuple), or None when the modules cannot be fused
-        (then the caller runs them one by one exactly like the reference)."""
+    def __call__(self, mods, x: torch.Tensor, split: bool = True):
+        """Returns the outputs of ``mods`` on ``x`` (a tuple; the unsplit ``[..., sum N]`` tensor with
+        ``split=False``), or None when the modules cannot be fused (then the caller runs them one by one
+        exactly like the reference)."""
         if not x.is_cuda or x.dtype not in (torch.float16, torch.bfloat16):
             return None
         parts = []
@@ -172,7 +173,7 @@ class _FusedLinears:
                     aq.scale, aq.round_zero_point = a0.scale, a0.round_zero_point
             x = xq
         y = _ops.gemm_wna16(x, self._pw)
-        return y.split([p.N for p in parts], dim=-1)
+        return y.split([p.N for p in parts], dim=-1) if split else y
 
 
 class QuantLlamaMLP(nn.Module):
@@ -395,6 +396,46 @@ class QuantLlamaDecoderLayer(nn.Module):
         if use_cache:
             outputs += (present_key_value,)
         return outputs
+
+    # ------------------------------------------------------------------ fused decode step (extension)
+    @torch.no_grad()
+    def decode_step_fused(self, x, residual, kv: "StaticKV", position, attention_mask):
+        """One new token per sequence through this block in 4 GEMM launches + 4 small kernels + the
+        attention core, on a static KV cache (CUDA-graph friendly).  Same arithmetic as ``forward`` with
+        ``past_key_value=kv`` (tests/test_block.py compares the two); what moves is where the residual add
+        happens: this block receives the previous block's MLP output ``x`` and residual stream ``residual``
+        separately, adds them inside its first norm kernel (K4), and returns its own (mlp_out, residual)
+        pair.  Returns None when the block cannot take this route (activation quantisation on, dense
+        weights, non-SiLU activation, fp32): the caller then uses ``forward``."""
+        attn, mlp = self.self_attn, self.mlp
+        if x.dtype not in (torch.float16, torch.bfloat16) or attn.use_act_quant or mlp.act_fn is not F.silu \
+                or self.input_layernorm.use_temporary_parameter or self.post_attention_layernorm.use_temporary_parameter:
+            return None
+        bsz = x.shape[0]
+        nh = attn.num_heads // attn.tp_world
+        nkv = max(attn.num_key_value_heads // attn.tp_world, 1)
+        h0, n1 = _ops.add_rmsnorm(x, self.input_layernorm.weight, self.input_layernorm.variance_epsilon, residual)
+        qkv = attn._qkv((attn.q_proj, attn.k_proj, attn.v_proj), n1, split=False)
+        if qkv is None:
+            return None
+        rc = getattr(attn, "_rope16", None)
+        if rc is None or rc[0].dtype != x.dtype or rc[0].shape[0] < kv.k.shape[-2] or rc[0].device != x.device:
+            cos, sin = attn.rotary_emb(kv.v, seq_len=kv.k.shape[-2])
+            rc = attn._rope16 = (cos.to(x.dtype).contiguous(), sin.to(x.dtype).contiguous())
+        q = _ops.rope_kv_decode(qkv, rc[0], rc[1], position, kv.k, kv.v, nh, nkv)
+        att = F.scaled_dot_product_attention(q, kv.k, kv.v, attn_mask=attention_mask, enable_gqa=nh != nkv)
+        o = attn.o_proj(att.reshape(bsz, 1, nh * attn.head_dim))
+        if attn.tp_world > 1:
+            o = _tp.reduce_output(o, _tp.ROW, attn.tp_group)
+        h1, n2 = _ops.add_rmsnorm(o, self.post_attention_layernorm.weight,
+                                  self.post_attention_layernorm.variance_epsilon, h0)
+        gu = mlp._gate_up((mlp.gate_proj, mlp.up_proj), n2, split=False)
+        if gu is None:
+            return None
+        d = mlp.down_proj(_ops.silu_mul(gu))
+        if getattr(mlp, "tp_world", 1) > 1:
+            d = _tp.reduce_output(d, _tp.ROW, mlp.tp_group)
+        return d, h1
 
     # ------------------------------------------------------------------ quantisation state
     def _quant_linears(self):

@@ -210,8 +210,11 @@ class GraphDecoder:
     measures per-token latency with a growing ``torch.cat`` cache and one Python dispatch per op
     (llama.py:409-465); the arithmetic per token is the same, the launch overhead is not."""
 
-    def __init__(self, model: QuantLlamaModel, bsz: int, max_len: int, use_graph: bool = True):
+    def __init__(self, model: QuantLlamaModel, bsz: int, max_len: int, use_graph: bool = True,
+                 fused: bool = True):
         from models.int_llama_layer import StaticKV
+        self.fused = fused
+        self.pdl = True
         self.model, self.bsz, self.max_len = model, bsz, max_len
         cfg = model.cfg
         dev, dt = model.embed_tokens.device, model.embed_tokens.dtype
@@ -233,9 +236,20 @@ class GraphDecoder:
         x = F.embedding(self.tok, m.embed_tokens)
         mask = torch.where(self._slots <= self.pos.view(1, 1, 1, 1), 0.0, self._neg).to(x.dtype)
         mask = mask.expand(self.bsz, 1, 1, self.max_len)
+        res = None                  # residual stream, kept apart from the last MLP output on the fused route
         for layer, kv in zip(m.layers, self.caches):
-            x = layer(x, attention_mask=mask, position_ids=self.pos, past_key_value=kv, use_cache=False)[0]
-        x = m._norm(x)
+            out = layer.decode_step_fused(x, res, kv, self.pos, mask) if self.fused else None
+            if out is not None:
+                x, res = out
+            else:
+                if res is not None:
+                    x, res = x + res, None
+                x = layer(x, attention_mask=mask, position_ids=self.pos, past_key_value=kv, use_cache=False)[0]
+        if res is not None:
+            from . import ops as _ops
+            x = _ops.add_rmsnorm(x, m.norm_weight, m.cfg.rms_norm_eps, res)[1]
+        else:
+            x = m._norm(x)
         logits = F.linear(x, m.lm_head)
         self.next_tok.copy_(logits.argmax(-1))
         self.pos.add_(1)
@@ -248,13 +262,13 @@ class GraphDecoder:
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(2):
-                self._step()
+                self._step_pdl()
         torch.cuda.current_stream().wait_stream(s)
         torch.cuda.synchronize()
         if self.use_graph:
             self.graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph):
-                self._step()
+                self._step_pdl()
         self.pos.fill_(start_pos)
 
     @torch.no_grad()
@@ -264,5 +278,15 @@ class GraphDecoder:
         if self.graph is not None:
             self.graph.replay()
         else:
-            self._step()
+            self._step_pdl()
         return self.next_tok
+
+    def _step_pdl(self):
+        # the weights are static during decode, so every GEMM may start streaming them while its
+        # predecessor drains (programmatic dependent launch, include/q100.h Q100_GEMM_PDL)
+        from . import ops as _ops, _lib
+        old = _ops.set_default_gemm_flags(_lib.GEMM_PDL if self.pdl else 0)
+        try:
+            self._step()
+        finally:
+            _ops.set_default_gemm_flags(old)

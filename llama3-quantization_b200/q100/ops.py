@@ -170,6 +170,16 @@ def pack_weight(w: torch.Tensor, n_bits: int, group: Optional[int], symmetric: b
 
 
 _WORKSPACES: dict = {}
+_DEFAULT_GEMM_FLAGS = 0
+
+
+def set_default_gemm_flags(flags: int) -> int:
+    """Flags OR-ed into every gemm_wna16 call that does not pass its own (e.g. ``_lib.GEMM_PDL`` while a
+    decode step is captured: weights are static there, which is what the flag requires).  Returns the
+    previous value."""
+    global _DEFAULT_GEMM_FLAGS
+    old, _DEFAULT_GEMM_FLAGS = _DEFAULT_GEMM_FLAGS, int(flags)
+    return old
 
 
 def _workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
@@ -193,7 +203,10 @@ def gemm_wna16(x: torch.Tensor, w: PackedWeight, bias: Optional[torch.Tensor] = 
         raise ValueError(f"q100.gemm_wna16: x has K={shp[-1]}, weight has K={w.K}")
     x2 = x.contiguous().view(-1, w.K)
     M = x2.shape[0]
+    flags |= _DEFAULT_GEMM_FLAGS
     y = torch.empty((M, w.N), dtype=x.dtype, device=x.device)
+    if M == 0:
+        return y.view(*shp[:-1], w.N)
     if bias is not None:
         bias = bias.to(x.dtype).contiguous()
     need = lib.q100_gemm_workspace_bytes(M, w.N, w.K, w.n_bits, flags)
@@ -203,6 +216,57 @@ def gemm_wna16(x: torch.Tensor, w: PackedWeight, bias: Optional[torch.Tensor] = 
                                   y.data_ptr(), M, w.N, w.K, w.group, w.n_bits, int(w.disable_zero_point),
                                   _DT[x.dtype], ws.data_ptr(), ws.numel(), flags, _stream(x2)))
     return y.view(*shp[:-1], w.N)
+
+
+def add_rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float, residual: Optional[torch.Tensor] = None):
+    """(h, n) with h = residual + x (or x) and n = OmniLlamaRMSNorm(h); one launch (K4)."""
+    _require_cuda(x, weight, residual)
+    x = x.contiguous()
+    cols = x.shape[-1]
+    rows = x.numel() // cols
+    norm = torch.empty_like(x)
+    h = x
+    if residual is not None:
+        residual = residual.contiguous()
+        h = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(lib.q100_add_rmsnorm(x.data_ptr(), _ptr(residual), weight.data_ptr(), float(eps),
+                                   h.data_ptr() if residual is not None else None, norm.data_ptr(), rows, cols,
+                                   _DT[x.dtype], _stream(x)))
+    return h, norm
+
+
+def rope_kv_decode(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, position: torch.Tensor,
+                   k_cache: torch.Tensor, v_cache: torch.Tensor, heads: int, kv_heads: int) -> torch.Tensor:
+    """Rotary on q/k of one new token per sequence + append of k, v to the static cache (K5).
+    Returns q [batch, heads, 1, head_dim]."""
+    _require_cuda(qkv, cos, sin, position, k_cache, v_cache)
+    bsz = k_cache.shape[0]
+    hd, max_len = k_cache.shape[-1], k_cache.shape[-2]
+    qkv = qkv.contiguous()
+    if qkv.numel() != bsz * (heads + 2 * kv_heads) * hd or position.dtype != torch.int64:
+        raise ValueError("q100.rope_kv_decode: qkv must be [batch, (heads + 2 kv_heads) * head_dim], position int64")
+    if cos.dtype != qkv.dtype or cos.shape[-1] != hd or not cos.is_contiguous():
+        raise ValueError("q100.rope_kv_decode: cos/sin cache must be contiguous [pos, head_dim] in the model dtype")
+    q = torch.empty((bsz, heads, 1, hd), dtype=qkv.dtype, device=qkv.device)
+    with torch.cuda.device(qkv.device):
+        check(lib.q100_rope_kv_decode(qkv.data_ptr(), cos.data_ptr(), sin.data_ptr(), position.data_ptr(),
+                                      q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), bsz, heads, kv_heads,
+                                      hd, max_len, _DT[qkv.dtype], _stream(qkv)))
+    return q
+
+
+def silu_mul(gate_up: torch.Tensor) -> torch.Tensor:
+    """silu(gate) * up on the fused gate|up GEMM output [..., 2I] -> [..., I] (K6)."""
+    _require_cuda(gate_up)
+    gate_up = gate_up.contiguous()
+    inter = gate_up.shape[-1] // 2
+    rows = gate_up.numel() // (2 * inter)
+    out = torch.empty((*gate_up.shape[:-1], inter), dtype=gate_up.dtype, device=gate_up.device)
+    with torch.cuda.device(gate_up.device):
+        check(lib.q100_silu_mul(gate_up.data_ptr(), out.data_ptr(), rows, inter, _DT[gate_up.dtype],
+                                _stream(gate_up)))
+    return out
 
 
 def selftest_div(dtype: torch.dtype, device="cuda") -> int:

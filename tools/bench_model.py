@@ -47,7 +47,7 @@ def main():
            "tp": world, "build_s": round(time.time() - t0, 2),
            "hbm_GB_after_build": round(torch.cuda.memory_allocated() / 1e9, 2)}
     g = torch.Generator().manual_seed(1)
-    testenc = torch.randint(0, cfg.vocab_size, (1, a.ppl_samples * a.seqlen), generator=g)
+    testenc = torch.randint(0, cfg.vocab_size, (1, max(a.ppl_samples, 1) * a.seqlen), generator=g)
     # ---- perplexity (main.py:122-151) ----
     if a.ppl_samples > 0:
         for l in model.layers:

@@ -28,7 +28,7 @@ def run(N, K, M, tag, pdl=True):
     print(f"--- {tag} N={N} K={K} M={M} pdl={pdl}: per launch (us): entry spread | first entry -> first wait-done | wait-done spread | "
           f"consumer span (median / max) | resolve (max) | launch period")
     prev_end = None
-    for li in order[4:12]:
+    for li in order[6:10]:
         v = valid[li]
         e, w, r, d = t[li, v, 0], t[li, v, 1], t[li, v, 2], t[li, v, 3]
         period = "" if prev_end is None else f"{(e.min() - prev_start) / 1e3:6.2f}"
@@ -36,7 +36,9 @@ def run(N, K, M, tag, pdl=True):
               f"consumer med {np.median(d-w)/1e3:5.2f} max {(d-w).max()/1e3:5.2f} | resolve max {(d-r).max()/1e3:5.2f} | kernel span {(d.max()-e.min())/1e3:6.2f} | "
               f"prev_end->this first waitdone {'' if prev_end is None else f'{(w.min()-prev_end)/1e3:5.2f}'} | period {period}")
         prev_end = d.max(); prev_start = e.min()
-run(4096, 4096, 1, "o")
-run(14336, 4096, 1, "up")
-run(28672, 4096, 1, "gateup")
-run(4096, 4096, 1, "o", pdl=False)
+import sys as _s
+for pdl in (True, False):
+    run(4096, 4096, 1, "o", pdl)
+    run(14336, 4096, 1, "up", pdl)
+    run(28672, 4096, 1, "gateup", pdl)
+    run(4096, 14336, 1, "down", pdl)
