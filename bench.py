@@ -25,7 +25,7 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-for _p in (os.path.join(ROOT, "llama3-quantization_b200"), os.path.join(ROOT, "oracle")):
+for _p in (os.path.join(ROOT, "llama3-quantization_b200"), os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tools")):
     if _p not in sys.path:
         sys.path.insert(0, _p)
 
@@ -379,46 +379,59 @@ def run_ours(args):
     # =============== e2e: module API, host buffers, H2D + D2H inside the timed region ===============
     e2e = None
     cpu_base = None
-    if rank == 0 and world == 1:
-        class _Lin:      # minimal nn.Linear stand-in holding the (full) fake-quantised weight
-            pass
+    if True:
+        # every rank drives its shard of the block through QuantLinear.forward: H2D of the (sharded)
+        # activations from pinned host memory, the GEMMs, the row-parallel all-reduce, D2H of the outputs
         mods = []
         g3 = torch.Generator(device=dev)
         for j, (name, n, k, src) in enumerate(LINEARS):
+            mode = tp.LLAMA_PLAN[name]
+            sh = tp.shard_bounds(n, k, mode, rank, world, GROUP)
             g3.manual_seed(j)
-            lin = torch.nn.Linear(k, n, bias=False, device=dev, dtype=dt_t)
+            wfull = (torch.randn(n, k, generator=g3, device=dev) * 0.02).to(dt_t)
+            lin = torch.nn.Linear(sh.k1 - sh.k0, sh.n1 - sh.n0, bias=False, device=dev, dtype=dt_t)
             with torch.no_grad():
-                lin.weight.copy_((torch.randn(n, k, generator=g3, device=dev) * 0.02).to(dt_t))
+                lin.weight.copy_(wfull[sh.n0:sh.n1, sh.k0:sh.k1])
+            del wfull
             ql = QuantLinear(lin, {"n_bits": WBITS, "per_channel_axes": [0], "symmetric": False,
                                    "dynamic_method": "per_channel", "group_size": GROUP, "lwc": False,
                                    "disable_zero_point": False},
                              {"n_bits": 16, "per_channel_axes": [], "symmetric": False, "dynamic_method": "per_token"})
             ql.set_quant_state(True, False)
-            mods.append((ql, src))
-        hin = {k: v.cpu().pin_memory() for k, v in xs.items()}
-        hout = [torch.empty(M_PRE, n, dtype=dt_t).pin_memory() for _, n, _, _ in LINEARS]
-        din = {k: torch.empty_like(v) for k, v in xs.items()}
+            mods.append((ql, src, mode))
+        hin = {k: (tp.shard_input(v, tp.ROW, rank, world) if (world > 1 and k != "h") else v).cpu().pin_memory()
+               for k, v in xs.items()}
+        hout = [torch.empty(M_PRE, ql.out_features, dtype=dt_t).pin_memory() for ql, _, _ in mods]
+        din = {k: torch.empty(v.shape, dtype=dt_t, device=dev) for k, v in hin.items()}
 
         def e2e_step():
             with torch.no_grad():
                 for k in din:
                     din[k].copy_(hin[k], non_blocking=True)
-                for (ql, src), ho in zip(mods, hout):
-                    ho.copy_(ql(din[src]), non_blocking=True)
+                for (ql, src, mode), ho in zip(mods, hout):
+                    ho.copy_(tp.reduce_output(ql(din[src]), mode), non_blocking=True)
             torch.cuda.synchronize()
 
         for _ in range(3):
             e2e_step()
+        sync_all()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             e2e_step()
+        sync_all()
         dte = (time.perf_counter() - t0) / args.steps
-        e2e = {"value": step_flops() / dte / 1e12, "unit": UNIT, "ms_per_step": dte * 1e3,
-               "h2d_bytes_per_step": sum(v.numel() * 2 for v in hin.values()),
-               "d2h_bytes_per_step": sum(h.numel() * 2 for h in hout),
-               "api": "quant.int_linear.QuantLinear.forward (use_weight_quant=True), pinned host buffers"}
-        del mods
+        te = torch.tensor([dte], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dte = float(te.item())
+        e2e = {"value": step_flops(M_PRE) / dte / 1e12, "unit": UNIT, "ms_per_step": dte * 1e3,
+               "h2d_bytes_per_step": sum(v.numel() * 2 for v in hin.values()) * world,
+               "d2h_bytes_per_step": sum(h.numel() * 2 for h in hout) * world,
+               "api": "quant.int_linear.QuantLinear.forward (use_weight_quant=True), pinned host buffers, "
+                      "all ranks; bytes summed over ranks"}
+        del mods, hin, hout, din
 
+    if rank == 0 and world == 1:
         # ---- CPU baseline on the host cores: bounded sample of the same workload (torch port)
         import torch_port as TP
         torch.set_num_threads(os.cpu_count() or 1)
@@ -449,6 +462,16 @@ def run_ours(args):
                     "sample": f"7 linears of the block at M={Ms} (of 2048), fp32, {reps} reps, torch eager on host cores",
                     "fake_quant_up_proj_ms": tq * 1e3}
 
+    # =============== whole model: random-init LLaMA3-8B W4A16 g128, tensor parallel ===========
+    model_res = None
+    if not os.environ.get("Q100_BENCH_SKIP_MODEL"):
+        blocks.clear()
+        fblocks.clear()
+        torch.cuda.empty_cache()
+        import bench_model
+        model_res = bench_model.run(bench_model.default_args(ppl_samples=1 if world == 1 else 0,
+                                                             ppl_ref=world == 1), dev, rank, world)
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
@@ -459,7 +482,8 @@ def run_ours(args):
                            "l2": "3 weight sets rotated; per-step working set (109 MB packed weights + 270 MB "
                                  "activations/outputs) exceeds the 126 MB L2",
                            "force_skinny": bool(flags)},
-                "roofline": roofline, "decode": decode, "quantize": quant, "cpu_baseline": cpu_base, "e2e": e2e,
+                "roofline": roofline, "decode": decode, "quantize": quant, "llama3_8b": model_res,
+                "cpu_baseline": cpu_base, "e2e": e2e,
                 "gpu_launches": n_launch, "clocks": clocks, "peaks": P}
         print(json.dumps(line), flush=True)
     if world > 1:

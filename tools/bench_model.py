@@ -14,6 +14,14 @@ import torch
 import torch.distributed as dist
 
 
+def default_args(**kw):
+    a = argparse.Namespace(layers=32, wbits=4, abits=16, group=128, dtype="f16", seqlen=2048, ppl_samples=1,
+                           ppl_ref=True, batches="1,4,16", decode_steps=48, ctx=256, no_graph=False)
+    for k, v in kw.items():
+        setattr(a, k, v)
+    return a
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--layers", type=int, default=32)
@@ -29,13 +37,21 @@ def main():
     ap.add_argument("--ctx", type=int, default=256, help="KV positions already filled when decode is timed")
     ap.add_argument("--no-graph", action="store_true")
     a = ap.parse_args()
-    from q100 import llama as QL
     world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    out = run(a, dev, rank, world)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run(a, dev, rank=0, world=1):
+    from q100 import llama as QL
     dt = {"f16": torch.float16, "bf16": torch.bfloat16}[a.dtype]
     cfg = QL.LLAMA3_8B
     args = QL.quant_args(a.wbits, a.group, a.abits)
@@ -112,10 +128,9 @@ def main():
                                   "weight_stream_GBps": (w4_bytes + head_bytes) / med / 1e6,
                                   "cuda_graph": dec.graph is not None}
         del dec
-    if rank == 0:
-        print(json.dumps(out), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    del model
+    torch.cuda.empty_cache()
+    return out
 
 
 if __name__ == "__main__":
