@@ -52,6 +52,8 @@ enum q100_status {
 #define Q100_FLAG_IEEE_DIV    0x1  /* f16/bf16: use div.rn.f32 for x/scale instead of the
                                       rcp + 2-FMA exact-for-16-bit sequence (same bits, slower) */
 #define Q100_FLAG_SCALAR_MATH 0x2  /* f16/bf16: per-element fp32 math instead of packed half2 ops */
+#define Q100_FLAG_K1_GENERIC  0x4  /* f16/bf16, group 64/128/256: the first group kernel (k1_groups) instead of
+                                      k1_fast (same bits; kept for A/B parity tests and profiling)          */
 /* flags for the GEMM entry points */
 #define Q100_GEMM_FORCE_SKINNY 0x1 /* always use the mma.sync weight-streaming kernel  */
 #define Q100_GEMM_FORCE_TC     0x2 /* always use the tcgen05 kernel                    */

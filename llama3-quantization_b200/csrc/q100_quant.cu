@@ -41,6 +41,7 @@ struct QuantArgs {
   int has_zp;
   float qmin, qmax;     // reference code range (quantizer.py:46-51)
   float denom;          // 2^n - 1 (asymmetric) or 2^(n-1) - 1 (symmetric)
+  float rcp_denom;      // RN(1 / denom), for k1_fast
   int k_tiles;          // packed layout v2: cols / 64
   int tile_words;       // uint32 words per [128 rows x 64 k] tile
 };
@@ -417,6 +418,236 @@ __global__ void __launch_bounds__(256) k1_groups(const QuantArgs a) {
   }
 }
 
+// ------------------------------------------------------------------ K1 fast: 8 lanes x V vectors per group, 16-bit T
+// Same results as k1_groups<T, 8, V, MATH_PACKED, PB>, about a third of its instructions (profiles/r01h:
+// k1_groups is ALU-pipe bound at 28 thread instructions per element, most of them the NaN-aware fp32 min/max
+// chains, three div.rn.f32 sequences per group and the per-step index divisions).  Differences:
+//   * min/max stay packed: one T2 holds (min, -max) so a single HMNMX2.NAN per butterfly step reduces both;
+//   * group parameters use the Markstein division q = x*rcp(d); q += fma(-q, d, x)*rcp(d).  For the scale
+//     (x = range, d = 2^n - 1 or 2^(n-1) - 1) the 16-bit result equals rd(div.rn.f32) for every finite
+//     16-bit x >= 0 (checked exhaustively, tools/check_markstein.py); for the zero-point only
+//     rint(clamp(.)) is consumed, which q100_selftest_div covers;
+//   * the element pass works in the shifted integer domain t = rd(v + C) = C + rint(v):
+//     c' = clamp(t, C + qmin - zp, C + qmax - zp) = C + (x_int - zp), dequant = (c' - C) * scale,
+//     code = c' - C + zp - qmin.  Every step is exact integer arithmetic when |v| and |zp| are small;
+//   * x / scale for two elements at a time with {mul,fma}.rn.f32x2.
+// A warp step whose groups do not qualify (NaN/inf, |x/scale| or |zp| too large for the magic-add rint)
+// runs the generic group_params + VecQuant path instead (warp-uniform branch), so coverage is unchanged.
+__device__ __forceinline__ unsigned long long pack_f2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f2(unsigned long long v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long mul_f2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ unsigned long long fma_f2(unsigned long long a, unsigned long long b,
+                                                     unsigned long long c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
+template <typename T>
+struct FastQ {
+  typename Packed16<T>::T2 magic, lo, hi, scale, code_add;
+  unsigned long long rcp2, nscale2;
+};
+
+template <typename T2>
+__device__ __forceinline__ uint32_t bits_of(const T2& v) { return *reinterpret_cast<const uint32_t*>(&v); }
+template <typename T2>
+__device__ __forceinline__ T2 from_bits(uint32_t v) { return *reinterpret_cast<const T2*>(&v); }
+
+// quantizer.py:143-159 for finite, well-scaled groups.  Returns false when the step must take the generic path.
+template <typename T>
+__device__ __forceinline__ bool fast_params(float mn, float mx, const QuantArgs& a, int64_t g, GroupQ<T>& q) {
+  using D = DT<T>;
+  float xmin = mn, xmax = mx;
+  if (a.lwc_up != nullptr) {
+    xmax = D::rd(D::to_f(reinterpret_cast<const T*>(a.lwc_up)[g]) * xmax);
+    xmin = D::rd(D::to_f(reinterpret_cast<const T*>(a.lwc_low)[g]) * xmin);
+  }
+  const float num = a.symmetric ? fmaxf(fabsf(xmax), fabsf(xmin)) : D::rd(xmax - xmin);
+  float s = num * a.rcp_denom;
+  s = fmaf(fmaf(-s, a.denom, num), a.rcp_denom, s);
+  s = D::rd(s);
+  q.scale = D::rd(fminf(fmaxf(s, 1e-5f), 1e4f));
+  q.rcp = __frcp_rn(q.scale);
+  float zp = 0.0f;
+  if (a.has_zp) {
+    if (a.symmetric) zp = a.denom;
+    else {
+      const float nx = -xmin;
+      float z = nx * q.rcp;
+      z = fmaf(fmaf(-z, q.scale, nx), q.rcp, z);
+      z = D::rd(copysignf(z, nx));                       // the correction step turns -0 into +0
+      zp = rintf(D::rd(fminf(fmaxf(z, -1e4f), 1e4f)));
+    }
+  }
+  q.zp = zp;
+  const float lim = fmaxf(fabsf(mn), fabsf(mx)) * q.rcp;
+  // all comparisons are false for NaN; num < inf rejects an overflowed range
+  return (lim < FastLimit<T>::value) && (fabsf(zp) < FastLimit<T>::value) &&
+         (num < __int_as_float(0x7f800000)) && (fabsf(xmin) < __int_as_float(0x7f800000));
+}
+
+template <typename T>
+__device__ __forceinline__ FastQ<T> fast_consts(const GroupQ<T>& q, const QuantArgs& a) {
+  using P = Packed16<T>;
+  constexpr float C = P::kRintMagic;
+  // exact-integer window of the storage type around C: [C/1.5, 2C/1.5]; t = C + rint(v) lies strictly inside,
+  // so saturating the clamp bounds to the window never changes the result
+  constexpr float W0 = C / 1.5f, W1 = 2.0f * C / 1.5f;
+  FastQ<T> f;
+  f.magic = P::bcast(C);
+  f.lo = P::bcast(fmaxf(C + a.qmin - q.zp, W0));
+  f.hi = P::bcast(fminf(C + a.qmax - q.zp, W1));
+  f.scale = P::bcast(q.scale);
+  f.code_add = P::bcast(CodeMagic<T>::kMagic - C + q.zp - a.qmin);
+  f.rcp2 = pack_f2(q.rcp, q.rcp);
+  f.nscale2 = pack_f2(-q.scale, -q.scale);
+  return f;
+}
+
+template <typename T, bool WANT_DEQ, bool WANT_CODES>
+__device__ __forceinline__ uint32_t fast_pair(uint32_t in, const FastQ<T>& f, uint32_t& pair) {
+  using D = DT<T>;
+  using T2 = typename Packed16<T>::T2;
+  const float2 xf = D::to_f2(in);
+  const unsigned long long x2 = pack_f2(xf.x, xf.y);
+  unsigned long long q2 = mul_f2(x2, f.rcp2);
+  const unsigned long long r2 = fma_f2(q2, f.nscale2, x2);
+  q2 = fma_f2(r2, f.rcp2, q2);
+  float q0, q1;
+  unpack_f2(q2, q0, q1);
+  const T2 v = from_bits<T2>(D::pack2(q0, q1));                  // rd(x / scale)
+  const T2 t = __hadd2(v, f.magic);                              // C + rint(v)
+  const T2 c = __hmin2(__hmax2(t, f.lo), f.hi);                  // C + x_int - zp
+  if (WANT_CODES) {
+    const T2 m = __hadd2(c, f.code_add);                         // kMagic + code
+    pair = bits_of(m) & CodeMagic<T>::kMask;
+  }
+  if (!WANT_DEQ) return 0u;
+  const T2 d = __hmul2(__hsub2(c, f.magic), f.scale);
+  return bits_of(d);
+}
+
+template <typename T, int V, int PB>
+__global__ void __launch_bounds__(256) k1_fast(const QuantArgs a) {
+  using D = DT<T>;
+  using T2 = typename Packed16<T>::T2;
+  constexpr bool PACK = PB != 0;
+  constexpr int L = 8, E = 8, GPW = 32 / L;
+  const int lane = threadIdx.x & 31;
+  const int l = lane % L, sub = lane / L;
+  const int64_t warp = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t n_warps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  const uint4* __restrict__ xin = reinterpret_cast<const uint4*>(a.x);
+  uint4* __restrict__ dq = reinterpret_cast<uint4*>(a.deq);
+  const bool want_deq = dq != nullptr;
+
+  int64_t g = warp * GPW + sub;
+  const int64_t gstep = n_warps * GPW;
+  const int64_t g_end = ((a.n_groups + GPW - 1) / GPW) * GPW;   // warp-uniform trip count
+
+  // (row, k-group) of g, advanced incrementally (n_groups < 2^31 is checked on the host)
+  int row = static_cast<int>(g / a.groups_per_row);
+  int kg = static_cast<int>(g - static_cast<int64_t>(row) * a.groups_per_row);
+  const int step_row = static_cast<int>(gstep / a.groups_per_row);
+  const int step_kg = static_cast<int>(gstep - static_cast<int64_t>(step_row) * a.groups_per_row);
+
+  uint4 cur[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k)
+    cur[k] = (g < a.n_groups) ? ldg_stream(xin + g * (L * V) + k * L + l) : make_uint4(0, 0, 0, 0);
+
+  for (; g - sub < g_end; g += gstep) {
+    const bool valid = g < a.n_groups;
+    uint4 nxt[V];
+    const int64_t gn = g + gstep;
+#pragma unroll
+    for (int k = 0; k < V; ++k)
+      nxt[k] = (gn < a.n_groups) ? ldg_stream(xin + gn * (L * V) + k * L + l) : make_uint4(0, 0, 0, 0);
+
+    // ---- min / max of the lane's V vectors, kept packed
+    T2 lo, hi;
+    {
+      const T2* h = reinterpret_cast<const T2*>(&cur[0]);
+      lo = __hmin2_nan(__hmin2_nan(h[0], h[1]), __hmin2_nan(h[2], h[3]));
+      hi = __hmax2_nan(__hmax2_nan(h[0], h[1]), __hmax2_nan(h[2], h[3]));
+#pragma unroll
+      for (int k = 1; k < V; ++k) {
+        const T2* hk = reinterpret_cast<const T2*>(&cur[k]);
+        lo = __hmin2_nan(lo, __hmin2_nan(__hmin2_nan(hk[0], hk[1]), __hmin2_nan(hk[2], hk[3])));
+        hi = __hmax2_nan(hi, __hmax2_nan(__hmax2_nan(hk[0], hk[1]), __hmax2_nan(hk[2], hk[3])));
+      }
+    }
+    const uint32_t lob = bits_of(lo), nhib = bits_of(__hneg2(hi));
+    T2 m = __hmin2_nan(from_bits<T2>(__byte_perm(lob, nhib, 0x5410)),
+                       from_bits<T2>(__byte_perm(lob, nhib, 0x7632)));       // (min, -max)
+#pragma unroll
+    for (int d = 1; d < L; d <<= 1)
+      m = __hmin2_nan(m, from_bits<T2>(__shfl_xor_sync(0xffffffffu, bits_of(m), d)));
+    const float mn = __low2float(m), mx = -__high2float(m);
+
+    GroupQ<T> q;
+    const bool ok = fast_params<T>(mn, mx, a, valid ? g : 0, q);
+    const int vec0 = kg * (L * V) + l;
+    if (__all_sync(0xffffffffu, ok)) {
+      const FastQ<T> f = fast_consts<T>(q, a);
+      auto body = [&](auto deq_tag) {
+        constexpr bool kDeq = decltype(deq_tag)::value;
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          uint32_t pairs[4];
+          uint4 o;
+          o.x = fast_pair<T, kDeq, PACK>(cur[k].x, f, pairs[0]);
+          o.y = fast_pair<T, kDeq, PACK>(cur[k].y, f, pairs[1]);
+          o.z = fast_pair<T, kDeq, PACK>(cur[k].z, f, pairs[2]);
+          o.w = fast_pair<T, kDeq, PACK>(cur[k].w, f, pairs[3]);
+          if (kDeq && valid) stg_stream(dq + g * (L * V) + k * L + l, o);
+          if (PB == 4) { if (valid) emit_packed_w4(pairs, a, row, vec0 + k * L); }
+          else if (PACK) emit_packed<E>(pairs, a, row, vec0 + k * L, valid);
+        }
+      };
+      if (want_deq) body(std::true_type{}); else body(std::false_type{});
+    } else {
+      q = group_params<T>(mn, mx, a, valid ? g : 0);
+      auto body = [&](auto deq_tag) {
+        constexpr bool kDeq = decltype(deq_tag)::value;
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+          uint32_t pairs[4];
+          const uint4 o = VecQuant<T, MATH_PACKED>::template run<kDeq, PACK, false>(cur[k], q, a, pairs);
+          if (kDeq && valid) stg_stream(dq + g * (L * V) + k * L + l, o);
+          if (PB == 4) { if (valid) emit_packed_w4(pairs, a, row, vec0 + k * L); }
+          else if (PACK) emit_packed<E>(pairs, a, row, vec0 + k * L, valid);
+        }
+      };
+      if (want_deq) body(std::true_type{}); else body(std::false_type{});
+    }
+    if (l == 0 && valid) {
+      if (a.scales) reinterpret_cast<T*>(a.scales)[g] = D::from_f(q.scale);
+      if (a.zeros && a.has_zp) reinterpret_cast<T*>(a.zeros)[g] = D::from_f(q.zp);
+      if (a.meta) {
+        T* mp = reinterpret_cast<T*>(a.meta) + (static_cast<int64_t>(kg) * a.rows + row) * 2;
+        *reinterpret_cast<uint32_t*>(mp) = D::pack2(q.scale, q.zp);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < V; ++k) cur[k] = nxt[k];
+    row += step_row;
+    kg += step_kg;
+    if (kg >= a.groups_per_row) { kg -= a.groups_per_row; ++row; }
+  }
+}
+
 // ------------------------------------------------------------------ K2: one CTA per row
 template <typename T, int VMAX, int MATH, bool PACK>
 __global__ void __launch_bounds__(1024) k2_rows(const QuantArgs a) {
@@ -552,11 +783,38 @@ static int launch_k1_lv(const QuantArgs& a, bool pack, cudaStream_t st) {
   return check_cuda(cudaGetLastError(), "k1_groups launch");
 }
 
+template <typename T, int V>
+static int launch_k1_fast(const QuantArgs& a, bool pack, cudaStream_t st) {
+  const int64_t warps_needed = (a.n_groups + 3) / 4;
+  int64_t blocks = (warps_needed + 7) / 8;
+  const int64_t cap = static_cast<int64_t>(sm_count()) * 8;   // persistent: <= 8 CTAs / SM
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  if constexpr (DT<T>::kCode != Q100_F32) {
+    if (!pack) k1_fast<T, V, 0><<<static_cast<unsigned>(blocks), 256, 0, st>>>(a);
+    else if (a.n_bits == 4) k1_fast<T, V, 4><<<static_cast<unsigned>(blocks), 256, 0, st>>>(a);
+    else k1_fast<T, V, 1><<<static_cast<unsigned>(blocks), 256, 0, st>>>(a);
+  }
+  return check_cuda(cudaGetLastError(), "k1_fast launch");
+}
+
 template <typename T, int MATH>
-static int launch_k1(const QuantArgs& a, bool pack, cudaStream_t st, bool& handled) {
+static int launch_k1(const QuantArgs& a, bool pack, cudaStream_t st, bool& handled, bool generic) {
   constexpr int E = DT<T>::kVec;
   const int vecs = a.group / E;               // vectors per group
   handled = true;
+  if constexpr (E == 8 && MATH == MATH_PACKED) {
+    // bf16 cannot carry an 8-bit code in the mantissa of 128 + code: those packs stay on k1_groups
+    const bool bf16_w8_pack = pack && a.n_bits > 4 && DT<T>::kCode == Q100_BF16;
+    if (!generic && !bf16_w8_pack) {
+      switch (vecs) {
+        case 8:  return launch_k1_fast<T, 1>(a, pack, st);          // g = 64
+        case 16: return launch_k1_fast<T, 2>(a, pack, st);          // g = 128
+        case 32: return launch_k1_fast<T, 4>(a, pack, st);          // g = 256
+        default: break;
+      }
+    }
+  }
   if (E == 8) {
     switch (vecs) {
       case 4:  return launch_k1_lv<T, 4, 1, MATH>(a, pack, st);    // g = 32
@@ -617,9 +875,10 @@ static int quantize_dispatch(const QuantArgs& a, bool pack, int flags, cudaStrea
                                                           : MATH_PACKED;
   bool handled = false;
   int rc = Q100_OK;
-  if (math == MATH_SCALAR_IEEE) rc = launch_k1<T, MATH_SCALAR_IEEE>(a, pack, st, handled);
-  else if (math == MATH_SCALAR) rc = launch_k1<T, k16 ? MATH_SCALAR : MATH_SCALAR_IEEE>(a, pack, st, handled);
-  else rc = launch_k1<T, k16 ? MATH_PACKED : MATH_SCALAR_IEEE>(a, pack, st, handled);
+  const bool generic = (flags & Q100_FLAG_K1_GENERIC) != 0;
+  if (math == MATH_SCALAR_IEEE) rc = launch_k1<T, MATH_SCALAR_IEEE>(a, pack, st, handled, generic);
+  else if (math == MATH_SCALAR) rc = launch_k1<T, k16 ? MATH_SCALAR : MATH_SCALAR_IEEE>(a, pack, st, handled, generic);
+  else rc = launch_k1<T, k16 ? MATH_PACKED : MATH_SCALAR_IEEE>(a, pack, st, handled, generic);
   if (handled) return rc;
   // everything else goes through the one-CTA-per-group row kernel, which cannot address
   // the transposed side band (or packed rows) of a multi-group row
@@ -690,6 +949,7 @@ extern "C" int q100_quantize_groupwise(const void* x, int dtype, int64_t rows, i
   if (disable_zp) { a.qmin = -static_cast<float>(1 << (n_bits - 1)); a.qmax = static_cast<float>((1 << (n_bits - 1)) - 1); }
   else { a.qmin = 0.0f; a.qmax = static_cast<float>((1 << n_bits) - 1); }
   a.denom = symmetric ? static_cast<float>((1 << (n_bits - 1)) - 1) : static_cast<float>((1 << n_bits) - 1);
+  a.rcp_denom = 1.0f / a.denom;
   a.k_tiles = static_cast<int>(cols / 64);
   a.tile_words = pack ? tile_words_of(n_bits) : 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

@@ -17,6 +17,7 @@ OK, EINVAL, EUNSUPPORTED, ECUDA, ENODEVICE, EWORKSPACE = range(6)
 F16, BF16, F32 = 0, 1, 2
 FLAG_IEEE_DIV = 0x1
 FLAG_SCALAR_MATH = 0x2
+FLAG_K1_GENERIC = 0x4
 GEMM_FORCE_SKINNY = 0x1
 GEMM_FORCE_TC = 0x2
 GEMM_EXACT_WEIGHTS = 0x4

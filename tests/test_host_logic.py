@@ -118,3 +118,12 @@ def test_backward_matches_autograd(bits, sym, lwc, group):
         gl = gsl * sl * (1 - sl)
         assert float((gu - up.grad).abs().max()) <= 1e-4 * float(up.grad.abs().max() + 1e-12)
         assert float((gl - low.grad).abs().max()) <= 1e-4 * float(low.grad.abs().max() + 1e-12)
+
+
+def test_markstein_scale_division_exhaustive():
+    """tools/check_markstein.py: k1_fast's scale division equals div.rn.f32 in 16 bits for every input."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "check_markstein.py")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

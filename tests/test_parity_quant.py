@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 W = load_golden("weights")
 A = load_golden("activations")
-MODES = {"packed": 0, "scalar": _lib.FLAG_SCALAR_MATH, "ieee": _lib.FLAG_IEEE_DIV}
+MODES = {"packed": 0, "generic": _lib.FLAG_K1_GENERIC, "scalar": _lib.FLAG_SCALAR_MATH, "ieee": _lib.FLAG_IEEE_DIV}
 
 
 def _codes_from_packed(packed, rows, cols, n_bits, nozp):
@@ -198,3 +198,44 @@ def test_full_size_properties(dtype):
     assert_same_bits(torch_to_bits(r.dequant[idx]), O.to_bits(o["dequant"], dtype), dtype, "sample rows")
     codes_s = q100.dequantize(r.packed, None, None, 14336, 4096, 128, 4, torch.float32)[idx]
     assert np.array_equal(codes_s.cpu().numpy(), o["codes"])
+
+
+@pytest.mark.parametrize("dtype", ["f16", "bf16"])
+@pytest.mark.parametrize("n_bits", [2, 3, 4, 8])
+@pytest.mark.parametrize("group", [64, 128, 256])
+def test_k1_fast_vs_generic_stress(dtype, n_bits, group):
+    """k1_fast (default) against k1_groups (FLAG_K1_GENERIC) and the scalar IEEE path on rows built to flip
+    between the exact-integer fast step and the generic step: magnitudes from subnormal to overflow, one-sided
+    groups (large zero-points), constant groups, NaN / inf, and symmetric / no-zero-point / LWC variants."""
+    g = torch.Generator(device="cpu").manual_seed(1234 + n_bits + group)
+    rows, cols = 384, 1024
+    x = torch.randn(rows, cols, generator=g)
+    mag = torch.exp2(torch.randint(-26, 16, (rows, cols // group, 1), generator=g).float())
+    off = torch.randn(rows, cols // group, 1, generator=g) * torch.exp2(torch.randint(-4, 6, (rows, cols // group, 1), generator=g).float())
+    x = (x.view(rows, cols // group, group) * mag + off * mag * (torch.rand(rows, cols // group, 1, generator=g) < 0.4)).view(rows, cols)
+    x[5, :group] = 3.0                                   # constant group
+    x[6, :group] = 0.0
+    x[7, 3] = float("nan")
+    x[8, 70] = float("inf")
+    x[9, 130] = float("-inf")
+    x[10, :group] = -0.0
+    x = x.to(TDT[dtype]).cuda()
+    up = (torch.rand(rows * cols // group, 1, generator=g) * 0.5 + 0.5).to(TDT[dtype]).cuda()
+    low = (torch.rand(rows * cols // group, 1, generator=g) * 0.5 + 0.5).to(TDT[dtype]).cuda()
+    for sym, nozp, lwc in ((False, False, False), (True, False, False), (False, True, False), (True, True, False),
+                           (False, False, True)):
+        outs = []
+        for flags in (0, _lib.FLAG_K1_GENERIC, _lib.FLAG_IEEE_DIV):
+            r = q100.quantize_groupwise(x, group, n_bits, sym, nozp, up if lwc else None, low if lwc else None,
+                                        want_dequant=True, want_packed=True, want_meta=True, flags=flags)
+            torch.cuda.synchronize()
+            outs.append(r)
+        a = outs[0]
+        for b in outs[1:]:
+            tag = f"sym={sym} nozp={nozp} lwc={lwc}"
+            assert torch.equal(a.dequant.view(torch.int16), b.dequant.view(torch.int16)), "dequant " + tag
+            assert torch.equal(a.scales.view(torch.int16), b.scales.view(torch.int16)), "scales " + tag
+            if not nozp:
+                assert torch.equal(a.zeros.view(torch.int16), b.zeros.view(torch.int16)), "zeros " + tag
+            assert torch.equal(a.packed, b.packed), "packed " + tag
+            assert torch.equal(a.meta.view(torch.int16), b.meta.view(torch.int16)), "meta " + tag
