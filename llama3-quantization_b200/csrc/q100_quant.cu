@@ -418,7 +418,7 @@ __global__ void __launch_bounds__(256) k1_groups(const QuantArgs a) {
   }
 }
 
-// ------------------------------------------------------------------ K1 fast: 8 lanes x V vectors per group, 16-bit T
+// ------------------------------------------------------------------ K1 fast: L lanes x V vectors per group, 16-bit T
 // Same results as k1_groups<T, 8, V, MATH_PACKED, PB>, about a third of its instructions (profiles/r01h:
 // k1_groups is ALU-pipe bound at 28 thread instructions per element, most of them the NaN-aware fp32 min/max
 // chains, three div.rn.f32 sequences per group and the per-step index divisions).  Differences:
@@ -453,9 +453,14 @@ __device__ __forceinline__ unsigned long long fma_f2(unsigned long long a, unsig
   return r;
 }
 
+// loop-invariant constants of the element pass and of the half-precision parameter clamps
+template <typename T>
+struct FastK {
+  typename Packed16<T>::T2 magic, range, ktop, one, k_nlo, k_top, s_lo, s_hi, z_hi, sym_zp;
+};
 template <typename T>
 struct FastQ {
-  typename Packed16<T>::T2 magic, lo, hi, scale, code_add;
+  typename Packed16<T>::T2 magic, nlo, range, top, ktop, scale, one;
   unsigned long long rcp2, nscale2;
 };
 
@@ -464,57 +469,86 @@ __device__ __forceinline__ uint32_t bits_of(const T2& v) { return *reinterpret_c
 template <typename T2>
 __device__ __forceinline__ T2 from_bits(uint32_t v) { return *reinterpret_cast<const T2*>(&v); }
 
-// quantizer.py:143-159 for finite, well-scaled groups.  Returns false when the step must take the generic path.
 template <typename T>
-__device__ __forceinline__ bool fast_params(float mn, float mx, const QuantArgs& a, int64_t g, GroupQ<T>& q) {
+__device__ __forceinline__ FastK<T> fast_invariants(const QuantArgs& a) {
   using D = DT<T>;
-  float xmin = mn, xmax = mx;
+  using P = Packed16<T>;
+  constexpr float C = P::kRintMagic;
+  FastK<T> k;
+  // all of these are integers of magnitude < 2^(significand bits): exact in T
+  k.magic = P::bcast(C);
+  k.range = P::bcast(a.qmax - a.qmin);
+  k.ktop = P::bcast(CodeMagic<T>::kMagic + (a.qmax - a.qmin));
+  k.one = P::bcast(1.0f);
+  k.k_nlo = P::bcast(-(C + a.qmin));
+  k.k_top = P::bcast(a.qmax);
+  // rd(clamp(v, lo, hi)) == clamp(v, rd(lo), rd(hi)) for a value v of T (rounding is monotonic)
+  k.s_lo = P::bcast(1e-5f);
+  k.s_hi = P::bcast(1e4f);
+  k.z_hi = P::bcast(1e4f);
+  k.sym_zp = P::bcast(a.denom);
+  return k;
+}
+
+// quantizer.py:143-159 for finite, well-scaled groups; `m` = (min, -max) of the group in T.  The fp32 -> T
+// conversions run on the XU pipe at 16 results/clk/SM and were the kernel's limiter (profiles/r01i), so
+// everything that is exact in T stays in T: the range, the clamps (pre-rounded bounds), the zero-point's rint and
+// the per-group constants of the element pass.  Two conversions per group remain (scale, zero-point).
+// Returns false when the step must take the generic path; q / f are then unspecified.
+template <typename T>
+__device__ __forceinline__ bool fast_params(typename Packed16<T>::T2 m, const QuantArgs& a, const FastK<T>& k,
+                                            int64_t g, GroupQ<T>& q, FastQ<T>& f, uint32_t& sz_bits) {
+  using D = DT<T>;
+  using T2 = typename Packed16<T>::T2;
+  const float inf = __int_as_float(0x7f800000);
+  // packed T2 registers throughout (both halves carry the same value): no 16-bit scalar temporaries
+  const uint32_t mb = bits_of(m);
+  const float mn = __low2float(m), mx = -__high2float(m);
+  float xmin = mn, num;
   if (a.lwc_up != nullptr) {
-    xmax = D::rd(D::to_f(reinterpret_cast<const T*>(a.lwc_up)[g]) * xmax);
-    xmin = D::rd(D::to_f(reinterpret_cast<const T*>(a.lwc_low)[g]) * xmin);
+    const float xmax = D::rd(D::to_f(reinterpret_cast<const T*>(a.lwc_up)[g]) * mx);
+    xmin = D::rd(D::to_f(reinterpret_cast<const T*>(a.lwc_low)[g]) * mn);
+    num = a.symmetric ? fmaxf(fabsf(xmax), fabsf(xmin)) : D::rd(xmax - xmin);
+  } else if (a.symmetric) {
+    num = fmaxf(fabsf(mx), fabsf(mn));
+  } else {
+    const T2 d2 = __hadd2(m, from_bits<T2>(__byte_perm(mb, 0, 0x1032)));   // min + (-max) in both halves
+    num = -__low2float(d2);                                                // rd(max - min), one op in T
   }
-  const float num = a.symmetric ? fmaxf(fabsf(xmax), fabsf(xmin)) : D::rd(xmax - xmin);
   float s = num * a.rcp_denom;
   s = fmaf(fmaf(-s, a.denom, num), a.rcp_denom, s);
-  s = D::rd(s);
-  q.scale = D::rd(fminf(fmaxf(s, 1e-5f), 1e4f));
+  const T2 s2 = __hmin2(__hmax2(from_bits<T2>(D::pack2(s, s)), k.s_lo), k.s_hi);
+  q.scale = __low2float(s2);
   q.rcp = __frcp_rn(q.scale);
-  float zp = 0.0f;
+  T2 zp2 = from_bits<T2>(0u);
   if (a.has_zp) {
-    if (a.symmetric) zp = a.denom;
+    if (a.symmetric) zp2 = k.sym_zp;
     else {
       const float nx = -xmin;
       float z = nx * q.rcp;
       z = fmaf(fmaf(-z, q.scale, nx), q.rcp, z);
-      z = D::rd(copysignf(z, nx));                       // the correction step turns -0 into +0
-      zp = rintf(D::rd(fminf(fmaxf(z, -1e4f), 1e4f)));
+      z = copysignf(z, nx);                                // the correction step turns -0 into +0
+      zp2 = h2rint(__hmin2(__hmax2(from_bits<T2>(D::pack2(z, z)), __hneg2(k.z_hi)), k.z_hi));
     }
   }
-  q.zp = zp;
-  const float lim = fmaxf(fabsf(mn), fabsf(mx)) * q.rcp;
-  // all comparisons are false for NaN; num < inf rejects an overflowed range
-  return (lim < FastLimit<T>::value) && (fabsf(zp) < FastLimit<T>::value) &&
-         (num < __int_as_float(0x7f800000)) && (fabsf(xmin) < __int_as_float(0x7f800000));
-}
-
-template <typename T>
-__device__ __forceinline__ FastQ<T> fast_consts(const GroupQ<T>& q, const QuantArgs& a) {
-  using P = Packed16<T>;
-  constexpr float C = P::kRintMagic;
-  // exact-integer window of the storage type around C: [C/1.5, 2C/1.5]; t = C + rint(v) lies strictly inside,
-  // so saturating the clamp bounds to the window never changes the result
-  constexpr float W0 = C / 1.5f, W1 = 2.0f * C / 1.5f;
-  FastQ<T> f;
-  f.magic = P::bcast(C);
-  f.lo = P::bcast(fmaxf(C + a.qmin - q.zp, W0));
-  f.hi = P::bcast(fminf(C + a.qmax - q.zp, W1));
-  f.scale = P::bcast(q.scale);
-  f.code_add = P::bcast(CodeMagic<T>::kMagic - C + q.zp - a.qmin);
+  q.zp = __low2float(zp2);
+  sz_bits = __byte_perm(bits_of(s2), bits_of(zp2), 0x5410);              // scale | zero-point << 16
+  f.magic = k.magic; f.range = k.range; f.ktop = k.ktop; f.one = k.one;
+  f.nlo = __hadd2(zp2, k.k_nlo);                           // -(C + qmin - zp)
+  f.top = __hsub2(k.k_top, zp2);                           // qmax - zp
+  f.scale = s2;
   f.rcp2 = pack_f2(q.rcp, q.rcp);
   f.nscale2 = pack_f2(-q.scale, -q.scale);
-  return f;
+  const float lim = fmaxf(fabsf(mn), fabsf(mx)) * q.rcp;
+  // all comparisons are false for NaN; num < inf rejects an overflowed range
+  return (lim < FastLimit<T>::value) && (fabsf(q.zp) < FastLimit<T>::value) && (num < inf) && (fabsf(xmin) < inf);
 }
 
+// Clamp without the ALU pipe (HMNMX2 shares it with the integer work; profiles/r01i): with t = C + rint(v),
+//   u = relu(t - (C + qmin - zp)) = max(x_int, qmin) - qmin,   w = relu((qmax - qmin) - u),
+//   code = (qmax - qmin) - w,   x_int - zp = (qmax - zp) - w          (exact integer arithmetic throughout).
+// Returns the dequantised pair; `pair` (WANT_CODES) = bits of (kMagic + code) in both halves, NOT masked: the
+// W4 packer removes the constant part arithmetically, the generic packer masks.
 template <typename T, bool WANT_DEQ, bool WANT_CODES>
 __device__ __forceinline__ uint32_t fast_pair(uint32_t in, const FastQ<T>& f, uint32_t& pair) {
   using D = DT<T>;
@@ -528,22 +562,31 @@ __device__ __forceinline__ uint32_t fast_pair(uint32_t in, const FastQ<T>& f, ui
   unpack_f2(q2, q0, q1);
   const T2 v = from_bits<T2>(D::pack2(q0, q1));                  // rd(x / scale)
   const T2 t = __hadd2(v, f.magic);                              // C + rint(v)
-  const T2 c = __hmin2(__hmax2(t, f.lo), f.hi);                  // C + x_int - zp
-  if (WANT_CODES) {
-    const T2 m = __hadd2(c, f.code_add);                         // kMagic + code
-    pair = bits_of(m) & CodeMagic<T>::kMask;
-  }
+  const T2 u = __hfma2_relu(t, f.one, f.nlo);
+  const T2 w = __hfma2_relu(__hneg2(u), f.one, f.range);
+  if (WANT_CODES) pair = bits_of(__hsub2(f.ktop, w));            // kMagic + code
   if (!WANT_DEQ) return 0u;
-  const T2 d = __hmul2(__hsub2(c, f.magic), f.scale);
-  return bits_of(d);
+  return bits_of(__hmul2(__hsub2(f.top, w), f.scale));
 }
 
-template <typename T, int V, int PB>
+// W4 from fast_pair's unmasked pairs m_j = MAGICBITS + code pair j:  sum_j m_j << 4j  carries the constant
+// MAGICBITS * 0x1111 (mod 2^32) on top of the packed word; IMADs on the FMA pipe, no masks.
+template <typename T>
+__device__ __forceinline__ uint32_t w4_word_from_magic(const uint32_t (&m)[4]) {
+  constexpr uint32_t kBits = DT<T>::kCode == Q100_F16 ? 0x64006400u : 0x43004300u;
+  constexpr uint32_t kConst = kBits * 0x1111u;
+  uint32_t w = m[1] * 16u + m[0];
+  w = m[2] * 256u + w;
+  w = m[3] * 4096u + w;
+  return w - kConst;
+}
+
+template <typename T, int L, int V, int PB>
 __global__ void __launch_bounds__(256) k1_fast(const QuantArgs a) {
   using D = DT<T>;
   using T2 = typename Packed16<T>::T2;
   constexpr bool PACK = PB != 0;
-  constexpr int L = 8, E = 8, GPW = 32 / L;
+  constexpr int E = 8, GPW = 32 / L;
   const int lane = threadIdx.x & 31;
   const int l = lane % L, sub = lane / L;
   const int64_t warp = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -562,14 +605,11 @@ __global__ void __launch_bounds__(256) k1_fast(const QuantArgs a) {
   const int step_row = static_cast<int>(gstep / a.groups_per_row);
   const int step_kg = static_cast<int>(gstep - static_cast<int64_t>(step_row) * a.groups_per_row);
 
-  uint4 cur[V];
-#pragma unroll
-  for (int k = 0; k < V; ++k)
-    cur[k] = (g < a.n_groups) ? ldg_stream(xin + g * (L * V) + k * L + l) : make_uint4(0, 0, 0, 0);
+  const FastK<T> fk = fast_invariants<T>(a);
 
-  for (; g - sub < g_end; g += gstep) {
+  // one warp step: quantise the groups held in `cur` while the next step's vectors land in `nxt`
+  auto step = [&](uint4 (&cur)[V], uint4 (&nxt)[V]) {
     const bool valid = g < a.n_groups;
-    uint4 nxt[V];
     const int64_t gn = g + gstep;
 #pragma unroll
     for (int k = 0; k < V; ++k)
@@ -594,13 +634,17 @@ __global__ void __launch_bounds__(256) k1_fast(const QuantArgs a) {
 #pragma unroll
     for (int d = 1; d < L; d <<= 1)
       m = __hmin2_nan(m, from_bits<T2>(__shfl_xor_sync(0xffffffffu, bits_of(m), d)));
-    const float mn = __low2float(m), mx = -__high2float(m);
 
     GroupQ<T> q;
-    const bool ok = fast_params<T>(mn, mx, a, valid ? g : 0, q);
+    FastQ<T> f;
+    uint32_t sz_bits;                                            // (scale, zero-point) as two T values
+    const bool ok = fast_params<T>(m, a, fk, valid ? g : 0, q, f, sz_bits);
     const int vec0 = kg * (L * V) + l;
+    // W4: this lane's first word of the group inside the tile-major image (row's 32 bytes of k tile kg*V*L/8)
+    uint32_t* w4row = nullptr;
+    if (PB == 4)
+      w4row = a.packed + (static_cast<int64_t>(row >> 7) * a.k_tiles + kg * ((L * V) >> 3)) * (128 * 8) + (row & 127) * 8 + l;
     if (__all_sync(0xffffffffu, ok)) {
-      const FastQ<T> f = fast_consts<T>(q, a);
       auto body = [&](auto deq_tag) {
         constexpr bool kDeq = decltype(deq_tag)::value;
 #pragma unroll
@@ -612,13 +656,20 @@ __global__ void __launch_bounds__(256) k1_fast(const QuantArgs a) {
           o.z = fast_pair<T, kDeq, PACK>(cur[k].z, f, pairs[2]);
           o.w = fast_pair<T, kDeq, PACK>(cur[k].w, f, pairs[3]);
           if (kDeq && valid) stg_stream(dq + g * (L * V) + k * L + l, o);
-          if (PB == 4) { if (valid) emit_packed_w4(pairs, a, row, vec0 + k * L); }
-          else if (PACK) emit_packed<E>(pairs, a, row, vec0 + k * L, valid);
+          if (PB == 4) {
+            // vector k*L + l of the group: k tile (k*L) >> 3, word ((k*L) & 7) + l of the row's 8 -- constants
+            if (valid) w4row[((k * L) >> 3) * (128 * 8) + ((k * L) & 7)] = w4_word_from_magic<T>(pairs);
+          } else if (PACK) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pairs[j] &= CodeMagic<T>::kMask;
+            emit_packed<E>(pairs, a, row, vec0 + k * L, valid);
+          }
         }
       };
       if (want_deq) body(std::true_type{}); else body(std::false_type{});
     } else {
-      q = group_params<T>(mn, mx, a, valid ? g : 0);
+      q = group_params<T>(__low2float(m), -__high2float(m), a, valid ? g : 0);
+      sz_bits = D::pack2(q.scale, q.zp);
       auto body = [&](auto deq_tag) {
         constexpr bool kDeq = decltype(deq_tag)::value;
 #pragma unroll
@@ -633,18 +684,30 @@ __global__ void __launch_bounds__(256) k1_fast(const QuantArgs a) {
       if (want_deq) body(std::true_type{}); else body(std::false_type{});
     }
     if (l == 0 && valid) {
-      if (a.scales) reinterpret_cast<T*>(a.scales)[g] = D::from_f(q.scale);
-      if (a.zeros && a.has_zp) reinterpret_cast<T*>(a.zeros)[g] = D::from_f(q.zp);
+      if (a.scales) reinterpret_cast<uint16_t*>(a.scales)[g] = static_cast<uint16_t>(sz_bits);
+      if (a.zeros && a.has_zp) reinterpret_cast<uint16_t*>(a.zeros)[g] = static_cast<uint16_t>(sz_bits >> 16);
       if (a.meta) {
         T* mp = reinterpret_cast<T*>(a.meta) + (static_cast<int64_t>(kg) * a.rows + row) * 2;
-        *reinterpret_cast<uint32_t*>(mp) = D::pack2(q.scale, q.zp);
+        *reinterpret_cast<uint32_t*>(mp) = sz_bits;
       }
     }
-#pragma unroll
-    for (int k = 0; k < V; ++k) cur[k] = nxt[k];
+    g = gn;
     row += step_row;
     kg += step_kg;
     if (kg >= a.groups_per_row) { kg -= a.groups_per_row; ++row; }
+  };
+
+  // two register buffers used alternately (no copies between steps)
+  uint4 buf_a[V], buf_b[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k)
+    buf_a[k] = (g < a.n_groups) ? ldg_stream(xin + g * (L * V) + k * L + l) : make_uint4(0, 0, 0, 0);
+  if (!(g - sub < g_end)) return;
+  for (;;) {
+    step(buf_a, buf_b);
+    if (!(g - sub < g_end)) break;
+    step(buf_b, buf_a);
+    if (!(g - sub < g_end)) break;
   }
 }
 
@@ -783,19 +846,32 @@ static int launch_k1_lv(const QuantArgs& a, bool pack, cudaStream_t st) {
   return check_cuda(cudaGetLastError(), "k1_groups launch");
 }
 
-template <typename T, int V>
-static int launch_k1_fast(const QuantArgs& a, bool pack, cudaStream_t st) {
-  const int64_t warps_needed = (a.n_groups + 3) / 4;
-  int64_t blocks = (warps_needed + 7) / 8;
-  const int64_t cap = static_cast<int64_t>(sm_count()) * 8;   // persistent: <= 8 CTAs / SM
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) blocks = 1;
+template <typename K>
+static int resident_ctas(K kernel) {               // persistent grid = what the SMs can hold at once
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, 256, 0) != cudaSuccess || occ < 1) occ = 2;
+  return occ * sm_count();
+}
+
+template <typename T, int L, int V, int PB>
+static int launch_k1_fast_pb(const QuantArgs& a, cudaStream_t st) {
   if constexpr (DT<T>::kCode != Q100_F32) {
-    if (!pack) k1_fast<T, V, 0><<<static_cast<unsigned>(blocks), 256, 0, st>>>(a);
-    else if (a.n_bits == 4) k1_fast<T, V, 4><<<static_cast<unsigned>(blocks), 256, 0, st>>>(a);
-    else k1_fast<T, V, 1><<<static_cast<unsigned>(blocks), 256, 0, st>>>(a);
+    static const int cap = resident_ctas(k1_fast<T, L, V, PB>);
+    constexpr int GPW = 32 / L;
+    const int64_t warps_needed = (a.n_groups + GPW - 1) / GPW;
+    int64_t blocks = (warps_needed + 7) / 8;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    k1_fast<T, L, V, PB><<<static_cast<unsigned>(blocks), 256, 0, st>>>(a);
   }
   return check_cuda(cudaGetLastError(), "k1_fast launch");
+}
+
+template <typename T, int L, int V>
+static int launch_k1_fast(const QuantArgs& a, bool pack, cudaStream_t st) {
+  if (!pack) return launch_k1_fast_pb<T, L, V, 0>(a, st);
+  if (a.n_bits == 4) return launch_k1_fast_pb<T, L, V, 4>(a, st);
+  return launch_k1_fast_pb<T, L, V, 1>(a, st);
 }
 
 template <typename T, int MATH>
@@ -808,9 +884,11 @@ static int launch_k1(const QuantArgs& a, bool pack, cudaStream_t st, bool& handl
     const bool bf16_w8_pack = pack && a.n_bits > 4 && DT<T>::kCode == Q100_BF16;
     if (!generic && !bf16_w8_pack) {
       switch (vecs) {
-        case 8:  return launch_k1_fast<T, 1>(a, pack, st);          // g = 64
-        case 16: return launch_k1_fast<T, 2>(a, pack, st);          // g = 128
-        case 32: return launch_k1_fast<T, 4>(a, pack, st);          // g = 256
+        // 32 elements per lane and step: the per-group work (reduction, parameters, index bookkeeping) is
+        // amortised over twice as many elements as with 8 lanes x 2 vectors
+        case 8:  return launch_k1_fast<T, 4, 2>(a, pack, st);       // g = 64
+        case 16: return launch_k1_fast<T, 4, 4>(a, pack, st);       // g = 128
+        case 32: return launch_k1_fast<T, 8, 4>(a, pack, st);       // g = 256
         default: break;
       }
     }
