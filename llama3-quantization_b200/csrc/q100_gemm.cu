@@ -129,7 +129,8 @@ extern "C" int q100_gemm_wna16(const void* x, const void* packed, const void* me
     const int64_t mc = (M - m0) < 32 ? (M - m0) : 32;
     rc = gemm_skinny(reinterpret_cast<const uint8_t*>(x) + m0 * K * esz, packed, meta, bias,
                      reinterpret_cast<uint8_t*>(y) + m0 * N * esz, mc, N, K, group, n_bits, disable_zp,
-                     dtype, workspace, workspace_bytes, (flags & Q100_GEMM_EXACT_WEIGHTS) ? 1 : 0,
+                     dtype, workspace, workspace_bytes,
+                     (flags & Q100_GEMM_EXACT_WEIGHTS) ? 1 : (flags & Q100_GEMM_NO_IMMA) ? 2 : 0,
                      (flags & Q100_GEMM_PDL) ? 1 : 0, st);
     if (rc != Q100_OK) return rc;
   }

@@ -92,7 +92,9 @@ template <int NBITS> struct WGeom {
 template <int NBITS> __host__ __device__ constexpr int stage_bytes(int nsub) {
   return WGeom<NBITS>::kCodeBytes + nsub * 512;
 }
-__host__ __device__ constexpr int slab_bytes(int m_rows, int chunk) { return (chunk * m_rows + 1) * SK_XPITCH; }
+constexpr int SK_ICOL = 144;       // IMMA path: bytes per (block, column) of x limbs: 128 + 16 (S, coefficient; conflict-free LDS.128)
+constexpr int SK_IPITCH = 3 * SK_ICOL;   // ... per (block, token): three signed 8-bit limbs
+__host__ __device__ constexpr int slab_bytes(int m_rows, int chunk, int pitch) { return (chunk * m_rows + 1) * pitch; }
 
 // ---------------------------------------------------------------- dequant helpers
 template <typename T> struct DQ;
@@ -272,6 +274,17 @@ __device__ __forceinline__ uint32_t shr8_fma(uint32_t w) {
   asm("mul.hi.u32 %0, %1, 16777216;" : "=r"(d) : "r"(w));
   return d;
 }
+__device__ __forceinline__ uint32_t shr4_fma(uint32_t w) {
+  uint32_t d;
+  asm("mul.hi.u32 %0, %1, 268435456;" : "=r"(d) : "r"(w));
+  return d;
+}
+// D += A(16 x 32, unsigned bytes, row) * B(32 x 8, signed bytes, col), int32 accumulate
+__device__ __forceinline__ void imma_16832(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 // mbarrier wait without bookkeeping instructions in the retry path (try_wait suspends in hardware)
 __device__ __forceinline__ void mbar_arrive_u32(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
@@ -320,11 +333,18 @@ __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u6
 #endif
 
 // ---------------------------------------------------------------- kernel
-template <typename T, int NBITS, int MB, bool POST>
+// MODE 0: 16-bit fake-quantised weights rebuilt bit-exactly (any group size);  MODE 1 ("POST"): fp16 magic-form
+// operand + fp32 group step;  MODE 2 ("IMMA", W4, M <= 8): the codes go to the tensor core as unsigned bytes
+// (two LOP3 + one shift per eight codes instead of five ALU ops) against x in block fixed point -- three signed
+// 8-bit limbs per (token, 128-k block), one mma column each, MB = ceil(3 M / 8) column groups.  The integer
+// contraction is exact; x is rounded once to 2^-22 of its block maximum (below fp32 accumulation noise).
+template <typename T, int NBITS, int MB, int MODE>
 __global__ void __launch_bounds__(SK_THREADS, MB <= 2 ? SK_OCC : 2)
 k3_skinny(const SkinnyArgs a) {
   using T2 = typename DQ<T>::T2;
-  constexpr bool kBf16 = !POST && DT<T>::kCode == Q100_BF16;    // MMA operand type (POST: always fp16)
+  constexpr bool POST = MODE == 1;
+  constexpr bool IMMA = MODE == 2;
+  constexpr bool kBf16 = MODE == 0 && DT<T>::kCode == Q100_BF16;  // MMA operand type (POST: always fp16)
   constexpr bool kConvX = POST && DT<T>::kCode == Q100_BF16;    // bf16 activations -> scaled fp16 at staging
   constexpr bool LOHI = POST && UseLoHi<NBITS>::value;
   using DQM = DQ<__half>;                                        // magic constants of the POST path
@@ -428,7 +448,8 @@ k3_skinny(const SkinnyArgs a) {
   const uint32_t xs_u32 = ring_u32 + stages * stage_pitch;
   uint8_t* xs_ptr = ring_ptr + stages * stage_pitch;
   const int mrows = a.m_rows;
-  const int blk_pitch = mrows * SK_XPITCH;            // bytes of x per staged k block
+  constexpr int kXPitch = IMMA ? SK_IPITCH : SK_XPITCH;
+  const int blk_pitch = mrows * kXPitch;              // bytes of x per staged k block
   const int g = lane >> 2, t = lane & 3;
   const int r0 = warp * 16 + g, r1 = r0 + 8;
   const bool has_zp = a.has_zp != 0;
@@ -454,12 +475,85 @@ k3_skinny(const SkinnyArgs a) {
     const int per_blk = mrows * 16;
     const int total = n * per_blk;                         // 16-byte chunks
     const int kblk0 = q0 % kblocks;
-    for (int c = tid; c < total; c += SK_CTHREADS) {
+    // the global loads of up to XU rounds are issued before any of them is consumed: one L2 round trip per XU
+    // rounds instead of one per round (at M = 8 the slab of a 16-block run is 8 rounds; measured 26.5 us per
+    // gate|up launch against 19.6 us at M = 1 before this change, all of it in this loop)
+    constexpr int XU = 1;   // > 1 spills at the 72-register cap of 3 CTAs per SM and costs more than it saves (tried: 2, 4)
+    for (int c0 = tid; c0 < total; c0 += SK_CTHREADS * XU) {
+      uint4 vq[XU];
+#pragma unroll
+      for (int u = 0; u < XU; ++u) {
+        const int c = c0 + u * SK_CTHREADS;
+        if (c < total) {
+          const int bl = c / per_blk;
+          const int rem = c - bl * per_blk;
+          const int kblk = (kblk0 + bl) % kblocks;
+          vq[u] = *reinterpret_cast<const uint4*>(xg + static_cast<int64_t>(rem >> 4) * a.K + kblk * SK_KB + (rem & 15) * 8);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < XU; ++u) {
+      const int c = c0 + u * SK_CTHREADS;
+      if (c >= total) break;                                // uniform per half-warp: total is a multiple of 16
       const int bl = c / per_blk;
       const int rem = c - bl * per_blk;
       const int m = rem >> 4, ch = rem & 15;
-      const int kblk = (kblk0 + bl) % kblocks;
-      uint4 v = *reinterpret_cast<const uint4*>(xg + static_cast<int64_t>(m) * a.K + kblk * SK_KB + ch * 8);
+      uint4 v = vq[u];
+      if constexpr (IMMA) {
+        // block fixed point: xi = rint(x * 2^(21 - e)) with e the exponent of the (token, block) maximum, so
+        // |xi| < 2^22, split into balanced base-256 digits l0 + 256 l1 + 65536 l2 (each in [-128, 127]).
+        // Chunk ch holds k = 8 ch .. 8 ch + 7 = lane quarter t = ch >> 2, word j = ch & 3; its bytes are stored
+        // in the order (e0, e4, e1, e5 | e2, e6, e3, e7) in which the weight nibbles come out of a packed word.
+        const float2 p0 = DT<T>::to_f2(v.x), p1 = DT<T>::to_f2(v.y), p2 = DT<T>::to_f2(v.z), p3 = DT<T>::to_f2(v.w);
+        const float f[8] = {p0.x, p0.y, p1.x, p1.y, p2.x, p2.y, p3.x, p3.y};
+        const uint32_t half_mask = (lane < 16) ? 0x0000ffffu : 0xffff0000u;   // 16 chunks of one (block, m)
+        uint32_t ab = 0;                                   // max |x| as bits: finite < inf < NaN
+#pragma unroll
+        for (int i = 0; i < 8; ++i) ab = max(ab, __float_as_uint(f[i]) & 0x7fffffffu);
+#pragma unroll
+        for (int d = 1; d < 16; d <<= 1) ab = max(ab, __shfl_xor_sync(half_mask, ab, d));
+        const int e = static_cast<int>(ab >> 23);
+        const int fe = min(max(275 - e, 1), 250);          // scale = 2^(fe - 127) = 2^(21 - (e - 127))
+        const float scale = __uint_as_float(static_cast<uint32_t>(fe) << 23);
+        int l0[8], l1[8], l2[8];
+        int s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int xi = __float2int_rn(f[i] * scale);
+          l0[i] = (xi << 24) >> 24;
+          const int x1 = (xi - l0[i]) >> 8;
+          l1[i] = (x1 << 24) >> 24;
+          l2[i] = (x1 - l1[i]) >> 8;
+          s0 += l0[i]; s1 += l1[i]; s2 += l2[i];
+        }
+#pragma unroll
+        for (int d = 1; d < 16; d <<= 1) {
+          s0 += __shfl_xor_sync(half_mask, s0, d);
+          s1 += __shfl_xor_sync(half_mask, s1, d);
+          s2 += __shfl_xor_sync(half_mask, s2, d);
+        }
+        auto pk = [](int b0, int b1, int b2, int b3) {
+          return (static_cast<uint32_t>(b0) & 0xffu) | ((static_cast<uint32_t>(b1) & 0xffu) << 8) |
+                 ((static_cast<uint32_t>(b2) & 0xffu) << 16) | (static_cast<uint32_t>(b3) << 24);
+        };
+        uint8_t* colp = xs_ptr + bl * blk_pitch + (3 * m) * SK_ICOL;
+        const int boff = (ch >> 2) * 32 + (ch & 3) * 8;
+        *reinterpret_cast<uint2*>(colp + boff) = make_uint2(pk(l0[0], l0[4], l0[1], l0[5]), pk(l0[2], l0[6], l0[3], l0[7]));
+        *reinterpret_cast<uint2*>(colp + SK_ICOL + boff) = make_uint2(pk(l1[0], l1[4], l1[1], l1[5]), pk(l1[2], l1[6], l1[3], l1[7]));
+        *reinterpret_cast<uint2*>(colp + 2 * SK_ICOL + boff) = make_uint2(pk(l2[0], l2[4], l2[1], l2[5]), pk(l2[2], l2[6], l2[3], l2[7]));
+        if (ch == 0) {
+          // column coefficient 256^l / scale; inf / NaN anywhere in the block poisons the token's result
+          const uint32_t cexp = static_cast<uint32_t>(254 - fe);
+          const bool bad = e == 255;
+          const float c0 = bad ? nan_f() : __uint_as_float(cexp << 23);
+          const float c1 = bad ? nan_f() : __uint_as_float((cexp + 8) << 23);
+          const float c2 = bad ? nan_f() : __uint_as_float((cexp + 16) << 23);
+          *reinterpret_cast<float2*>(colp + 128) = make_float2(static_cast<float>(s0), c0);
+          *reinterpret_cast<float2*>(colp + SK_ICOL + 128) = make_float2(static_cast<float>(s1), c1);
+          *reinterpret_cast<float2*>(colp + 2 * SK_ICOL + 128) = make_float2(static_cast<float>(s2), c2);
+        }
+        continue;
+      }
       if constexpr (POST) {
         float2 f0 = DT<T>::to_f2(v.x), f1 = DT<T>::to_f2(v.y), f2 = DT<T>::to_f2(v.z), f3 = DT<T>::to_f2(v.w);
         // the 16 chunks of one (block, m) sit in 16 consecutive threads
@@ -499,17 +593,26 @@ k3_skinny(const SkinnyArgs a) {
       }
       if (LOHI) { const uint32_t y = v.y; v.y = v.z; v.z = y; }
       *reinterpret_cast<uint4*>(xs_ptr + bl * blk_pitch + m * SK_XPITCH + (ch >> 2) * 16 + (ch & 3) * 64) = v;
+      }
     }
   };
 
   // per-lane x addresses: column n = mb*8+g of the mma B operand is token m; columns >= M read the last
   // valid row instead (their results are never stored), so no zero fill and no branch is needed
-  uint32_t xrow[MB], srow[MB];
+  uint32_t xrow[MB], srow[MB], srow1[IMMA ? MB : 1];
 #pragma unroll
   for (int mb = 0; mb < MB; ++mb) {
-    xrow[mb] = xs_u32 + min(mb * 8 + g, mrows - 1) * SK_XPITCH + t * 16;
-    // this lane's two output columns need the block sums of tokens m = mb*8 + 2t, 2t+1 (clamped like x)
-    srow[mb] = xs_u32 + min(mb * 8 + 2 * t, mrows - 1) * SK_XPITCH + 256;
+    if constexpr (IMMA) {
+      // mma column n = mb*8 + g is (token, limb) = divmod(n, 3); this lane's output columns are n = mb*8 + 2t, +1
+      const int ncols = 3 * mrows;
+      xrow[mb] = xs_u32 + min(mb * 8 + g, ncols - 1) * SK_ICOL + t * 32;
+      srow[mb] = xs_u32 + min(mb * 8 + 2 * t, ncols - 1) * SK_ICOL + 128;
+      srow1[mb] = xs_u32 + min(mb * 8 + 2 * t + 1, ncols - 1) * SK_ICOL + 128;
+    } else {
+      xrow[mb] = xs_u32 + min(mb * 8 + g, mrows - 1) * SK_XPITCH + t * 16;
+      // this lane's two output columns need the block sums of tokens m = mb*8 + 2t, 2t+1 (clamped like x)
+      srow[mb] = xs_u32 + min(mb * 8 + 2 * t, mrows - 1) * SK_XPITCH + 256;
+    }
   }
 
   float acc[MB][4];
@@ -522,7 +625,42 @@ k3_skinny(const SkinnyArgs a) {
   const uint32_t magic = reg_const(DQM::kMagic);
 
   auto compute_block = [&](const BlockRegs<NBITS>& b, uint32_t xoff) {
-    if constexpr (POST) {
+    if constexpr (IMMA) {
+      int di[MB][4];
+#pragma unroll
+      for (int mb = 0; mb < MB; ++mb) { di[mb][0] = di[mb][1] = di[mb][2] = di[mb][3] = 0; }
+      uint4 xb[MB][2];
+#pragma unroll
+      for (int mb = 0; mb < MB; ++mb) { xb[mb][0] = lds128(xrow[mb] + xoff); xb[mb][1] = lds128(xrow[mb] + xoff + 16); }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t w0 = b.c0.word(j), w1 = b.c1.word(j);
+        uint32_t af[4];
+        af[0] = w0 & 0x0f0f0f0fu;                       // (e0, e4, e1, e5) of row r0
+        af[1] = w1 & 0x0f0f0f0fu;                       //                  of row r1
+        af[2] = shr4_fma(w0) & 0x0f0f0f0fu;             // (e2, e6, e3, e7)
+        af[3] = shr4_fma(w1) & 0x0f0f0f0fu;
+#pragma unroll
+        for (int mb = 0; mb < MB; ++mb) {
+          const uint4& q4 = xb[mb][j >> 1];
+          imma_16832(di[mb], af, (j & 1) ? q4.z : q4.x, (j & 1) ? q4.w : q4.y);
+        }
+      }
+      const float2 sz0 = DT<T>::to_f2(b.m0), sz1 = DT<T>::to_f2(b.m1);     // (scale, zero) of rows r0, r1
+      const float nz0 = has_zp ? -sz0.y : -zp_fix, nz1 = has_zp ? -sz1.y : -zp_fix;
+#pragma unroll
+      for (int mb = 0; mb < MB; ++mb) {
+        const float2 u0 = lds64f(srow[mb] + xoff), u1 = lds64f(srow1[mb] + xoff);   // (sum of limbs, coefficient)
+        const float v0 = fmaf(nz0, u0.x, static_cast<float>(di[mb][0]));
+        const float v1 = fmaf(nz0, u1.x, static_cast<float>(di[mb][1]));
+        const float v2 = fmaf(nz1, u0.x, static_cast<float>(di[mb][2]));
+        const float v3 = fmaf(nz1, u1.x, static_cast<float>(di[mb][3]));
+        acc[mb][0] = fmaf(sz0.x * u0.y, v0, acc[mb][0]);
+        acc[mb][1] = fmaf(sz0.x * u1.y, v1, acc[mb][1]);
+        acc[mb][2] = fmaf(sz1.x * u0.y, v2, acc[mb][2]);
+        acc[mb][3] = fmaf(sz1.x * u1.y, v3, acc[mb][3]);
+      }
+    } else if constexpr (POST) {
       float ag[MB][4], agh[LOHI ? MB : 1][4];
       if constexpr (LOHI) {
         // fp16 W4: words in place, pairs {0,2} (value 1024+q) and {1,3} (value 1024+16q) of each word
@@ -641,6 +779,34 @@ k3_skinny(const SkinnyArgs a) {
   auto write_fragment = [&](const float (&v)[MB][4], int n0) {
     T* y = reinterpret_cast<T*>(a.y);
     const T* bias = reinterpret_cast<const T*>(a.bias);
+    if constexpr (IMMA) {
+      // token m = sum of columns 3m, 3m+1, 3m+2 (the limb weights are already in the coefficients); column c
+      // lives in lane quarter (c & 7) >> 1, register (c & 1) (+2 for row r1) of column group c >> 3
+      float s0[(MB * 8 + 2) / 3], s1[(MB * 8 + 2) / 3];
+#pragma unroll
+      for (int i = 0; i < (MB * 8 + 2) / 3; ++i) s0[i] = s1[i] = 0.f;
+#pragma unroll
+      for (int c = 0; c < MB * 8; ++c) {
+        const int src = (lane & ~3) | ((c & 7) >> 1);
+        s0[c / 3] += __shfl_sync(0xffffffffu, v[c >> 3][c & 1], src);
+        s1[c / 3] += __shfl_sync(0xffffffffu, v[c >> 3][2 + (c & 1)], src);
+      }
+#pragma unroll
+      for (int m = 0; m < (MB * 8) / 3; ++m) {
+        if ((m & 3) == t && m < a.M) {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int n = n0 + (h ? r1 : r0);
+            if (n < a.N) {
+              float o = h ? s1[m] : s0[m];
+              if (bias) o += DT<T>::to_f(bias[n]);
+              y[static_cast<int64_t>(m) * a.N + n] = DT<T>::from_f(o);
+            }
+          }
+        }
+      }
+      return;
+    }
 #pragma unroll
     for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
@@ -678,32 +844,35 @@ k3_skinny(const SkinnyArgs a) {
     for (int mb = 0; mb < MB; ++mb)
 #pragma unroll
       for (int r = 0; r < 4; ++r) v[mb][r] = 0.f;
-    uint2 cur[MB * 4];
     auto fetch = [&](uint2 (&dst)[MB * 4], int sl) {
 #pragma unroll
       for (int i = 0; i < MB * 4; ++i) dst[i] = ld_volatile_u2(wst + static_cast<int64_t>(sl) * FRAG + i * 32 + lane);
     };
-    fetch(cur, 0);
-    for (int sl = 0; sl < pend_n; ++sl) {
-      uint2 nxt[MB * 4];
-      if (MB <= 2 && sl + 1 < pend_n) fetch(nxt, sl + 1);        // next slot's round trip overlaps this one's poll
-      for (;;) {
-        uint32_t ok = 1;
+    // the loads of up to RB slots are put in flight together: the reducer pays about one L2 round trip per
+    // batch instead of one per contributor (profiles/r01j: the serial version kept the reducers 3-4 us past
+    // the median CTA); the sum still runs in slot order, so the result stays deterministic
+    constexpr int RB = MB == 1 ? 6 : MB == 2 ? 3 : 2;
+    for (int base = 0; base < pend_n; base += RB) {
+      uint2 buf[RB][MB * 4];
 #pragma unroll
-        for (int i = 0; i < MB * 4; ++i) ok &= cur[i].y;
-        if (__all_sync(0xffffffffu, ok != 0)) break;
-        fetch(cur, sl);
-      }
+      for (int s = 0; s < RB; ++s)
+        if (base + s < pend_n) fetch(buf[s], base + s);
 #pragma unroll
-      for (int i = 0; i < MB * 4; ++i) {
-        v[i >> 2][i & 3] += __uint_as_float(cur[i].x);
-        wst[static_cast<int64_t>(sl) * FRAG + i * 32 + lane] = make_uint2(0u, 0u);     // leave the workspace clean
-      }
-      if (MB <= 2) {
+      for (int s = 0; s < RB; ++s) {
+        if (base + s < pend_n) {
+          for (;;) {
+            uint32_t ok = 1;
 #pragma unroll
-        for (int i = 0; i < MB * 4; ++i) cur[i] = nxt[i];
-      } else if (sl + 1 < pend_n) {
-        fetch(cur, sl + 1);
+            for (int i = 0; i < MB * 4; ++i) ok &= buf[s][i].y;
+            if (__all_sync(0xffffffffu, ok != 0)) break;
+            fetch(buf[s], base + s);
+          }
+#pragma unroll
+          for (int i = 0; i < MB * 4; ++i) {
+            v[i >> 2][i & 3] += __uint_as_float(buf[s][i].x);
+            wst[static_cast<int64_t>(base + s) * FRAG + i * 32 + lane] = make_uint2(0u, 0u);   // leave the workspace clean
+          }
+        }
       }
     }
     write_fragment(v, pend_tile * SK_ROWS);
@@ -826,31 +995,32 @@ static SkinnyPlan plan_skinny(int64_t N, int64_t K) {
   return p;
 }
 
-template <typename T, int NBITS, int MB, bool POST>
+template <typename T, int NBITS, int MB, int MODE>
 static int launch_skinny(SkinnyArgs a, cudaStream_t st) {
-  auto kern = k3_skinny<T, NBITS, MB, POST>;
+  auto kern = k3_skinny<T, NBITS, MB, MODE>;
+  constexpr int xpitch = MODE == 2 ? SK_IPITCH : SK_XPITCH;
   constexpr int occ_target = MB <= 2 ? SK_OCC : 2;
   // per-CTA shared memory: ring + x slab within the budget that keeps occ_target CTAs resident
   const int budget = (228 * 1024) / occ_target - 1024 /* driver reserve */ - 512 /* static */ - 128 /* align */;
   const int stage_pitch = (stage_bytes<NBITS>(a.nsub) + 127) & ~127;
-  const int row_b = a.m_rows * SK_XPITCH;
+  const int row_b = a.m_rows * xpitch;
   // reserve ~2/3 of the budget (at most 6 stages) for the ring; then as much x as fits up to SK_CHUNK_MAX
   // blocks; what is left goes back to the ring
   int min_stages = (2 * budget / 3) / stage_pitch;
   if (min_stages > 6) min_stages = 6;
   if (min_stages < 2) min_stages = 2;
-  int chunk = (budget - min_stages * stage_pitch - SK_XPITCH) / row_b;
+  int chunk = (budget - min_stages * stage_pitch - xpitch) / row_b;
   if (chunk > SK_CHUNK_MAX) chunk = SK_CHUNK_MAX;
   Q100_REQUIRE(chunk >= 1, Q100_EUNSUPPORTED, "k3_skinny: M=%d rows of x do not fit in shared memory", a.m_rows);
   // a CTA never needs more x than its share of the blocks: keep the slab small so that the ring is deep
   const int grid_est = plan_skinny(a.N, a.K).grid_cap;
   const int share = (a.total_units + grid_est - 1) / grid_est + 1;
   if (chunk > share) chunk = share;
-  int stages = (budget - slab_bytes(a.m_rows, chunk)) / stage_pitch;
+  int stages = (budget - slab_bytes(a.m_rows, chunk, xpitch)) / stage_pitch;
   if (stages > SK_MAX_STAGES) stages = SK_MAX_STAGES;
   a.chunk = chunk;
   a.stages = stages;
-  const int smem = stages * stage_pitch + slab_bytes(a.m_rows, chunk) + 128;
+  const int smem = stages * stage_pitch + slab_bytes(a.m_rows, chunk, xpitch) + 128;
   static std::mutex mu;           // one per instantiation
   static int max_set = 0;
   static std::unordered_map<int, int> occ_cache;
@@ -891,12 +1061,18 @@ static int launch_skinny(SkinnyArgs a, cudaStream_t st) {
 
 template <typename T, int NBITS, int MB>
 static int launch_skinny_post(const SkinnyArgs& a, cudaStream_t st) {
-  if (a.post) return launch_skinny<T, NBITS, MB, true>(a, st);
-  return launch_skinny<T, NBITS, MB, false>(a, st);
+  if (a.post) return launch_skinny<T, NBITS, MB, 1>(a, st);
+  return launch_skinny<T, NBITS, MB, 0>(a, st);
 }
 
 template <typename T, int NBITS>
 static int launch_skinny_mb(const SkinnyArgs& a, cudaStream_t st) {
+  if constexpr (NBITS == 4) {
+    // integer tensor-core path.  Measured (profiles/r01j): with one column group (M <= 2) it beats the fp16 form
+    // (gate|up 16.6 vs 19.3 us); with two groups (M = 4) the extra MMAs, int->float conversions and limb staging
+    // lose (25.3 vs 21.6 us), so larger M stay on the fp16 form.
+    if (a.post == 2) return launch_skinny<T, 4, 1, 2>(a, st);
+  }
   if (a.M <= 8) return launch_skinny_post<T, NBITS, 1>(a, st);
   if (a.M <= 16) return launch_skinny_post<T, NBITS, 2>(a, st);
   return launch_skinny_post<T, NBITS, 4>(a, st);
@@ -952,7 +1128,10 @@ int gemm_skinny(const void* x, const void* packed, const void* meta, const void*
   a.total_units = p.total_units; a.max_slots = p.max_slots;
   a.has_zp = disable_zp ? 0 : 1;
   a.qmin = disable_zp ? -static_cast<float>(1 << (n_bits - 1)) : 0.0f;
-  a.post = (g % SK_KB == 0 && !exact_weights) ? 1 : 0;
+  // exact_weights: 0 = default, 1 = bit-exact 16-bit weights (MODE 0), 2 = fp16 magic-form path even where
+  // the integer path applies
+  a.post = (g % SK_KB == 0 && exact_weights != 1) ? 1 : 0;
+  if (a.post && n_bits == 4 && M <= 2 && exact_weights == 0) a.post = 2;
   a.m_rows = static_cast<int>(M);
   a.nsub = g >= SK_KB ? 1 : SK_KB / g;
   a.pdl = pdl;

@@ -25,6 +25,7 @@ GEMM_PDL = 0x8
 GEMM_FORCE_MMA_SYNC = 0x10
 GEMM_FORCE_STREAM_TC = 0x20
 GEMM_FORCE_TC_SMEM = 0x40
+GEMM_NO_IMMA = 0x80
 
 _vp, _i, _i64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
 

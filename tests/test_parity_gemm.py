@@ -27,7 +27,10 @@ EPS_OUT = {"f16": 2.0 ** -11, "bf16": 2.0 ** -8}
 EPS_W = {"f16": 2.0 ** -12, "bf16": 2.0 ** -9}
 # decode shapes have two kernels: the tcgen05 streaming kernel (M <= 16, W2/W4, group % 128 == 0; default
 # for 8 < M <= 16) and the mma.sync streaming kernel (everything else); both are forced here in turn
-PATHS = {"stream_tc": _lib.GEMM_FORCE_STREAM_TC, "mma_sync": _lib.GEMM_FORCE_MMA_SYNC}
+# the mma.sync kernel itself has two operand forms for W4 at M <= 8: unsigned-byte codes x signed-byte limbs of x
+# on the integer tensor-core path (default) and the fp16 magic form (GEMM_NO_IMMA)
+PATHS = {"stream_tc": _lib.GEMM_FORCE_STREAM_TC, "mma_sync": _lib.GEMM_FORCE_MMA_SYNC,
+         "mma_sync_f16": _lib.GEMM_FORCE_MMA_SYNC | _lib.GEMM_NO_IMMA}
 
 
 def _check(y, x, wdeq, bias, dtype, exact_weights=True):
@@ -61,6 +64,8 @@ def _make(N, K, M, dtype, n_bits, group, seed, nozp=False, sym=False):
 @pytest.mark.parametrize("M", [1, 2, 5, 8, 9, 16, 17, 32])
 def test_skinny_vs_oracle(dtype, n_bits, M, path):
     if path == "stream_tc" and (n_bits in (3, 8) or M > 16):
+        pytest.skip("same kernel as mma_sync for this case")
+    if path == "mma_sync_f16" and (n_bits != 4 or M > 2):
         pytest.skip("same kernel as mma_sync for this case")
     N, K = 384, 1024
     x, w, pw, r = _make(N, K, M, dtype, n_bits, 128, 1000 + M + n_bits)
