@@ -339,7 +339,7 @@ __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u6
 // 8-bit limbs per (token, 128-k block), one mma column each, MB = ceil(3 M / 8) column groups.  The integer
 // contraction is exact; x is rounded once to 2^-22 of its block maximum (below fp32 accumulation noise).
 template <typename T, int NBITS, int MB, int MODE>
-__global__ void __launch_bounds__(SK_THREADS, MB <= 2 ? SK_OCC : 2)
+__global__ void __launch_bounds__(SK_THREADS, MB <= 1 ? SK_OCC : 2)
 k3_skinny(const SkinnyArgs a) {
   using T2 = typename DQ<T>::T2;
   constexpr bool POST = MODE == 1;
@@ -475,10 +475,10 @@ k3_skinny(const SkinnyArgs a) {
     const int per_blk = mrows * 16;
     const int total = n * per_blk;                         // 16-byte chunks
     const int kblk0 = q0 % kblocks;
-    // the global loads of up to XU rounds are issued before any of them is consumed: one L2 round trip per XU
-    // rounds instead of one per round (at M = 8 the slab of a 16-block run is 8 rounds; measured 26.5 us per
-    // gate|up launch against 19.6 us at M = 1 before this change, all of it in this loop)
-    constexpr int XU = 1;   // > 1 spills at the 72-register cap of 3 CTAs per SM and costs more than it saves (tried: 2, 4)
+    // XU > 1 (loads of several rounds in flight) and a cp.async variant (raw chunks global -> shared, transformed in
+    // place) were both measured: no gain -- the M dependence of this kernel (gate|up 16.7 us at M = 1, 26.5 us at
+    // M = 8) is shared-memory bandwidth of the x fragments (every warp re-reads the block's x), not this loop.
+    constexpr int XU = 1;
     for (int c0 = tid; c0 < total; c0 += SK_CTHREADS * XU) {
       uint4 vq[XU];
 #pragma unroll
@@ -999,7 +999,7 @@ template <typename T, int NBITS, int MB, int MODE>
 static int launch_skinny(SkinnyArgs a, cudaStream_t st) {
   auto kern = k3_skinny<T, NBITS, MB, MODE>;
   constexpr int xpitch = MODE == 2 ? SK_IPITCH : SK_XPITCH;
-  constexpr int occ_target = MB <= 2 ? SK_OCC : 2;
+  constexpr int occ_target = MB <= 1 ? SK_OCC : 2;
   // per-CTA shared memory: ring + x slab within the budget that keeps occ_target CTAs resident
   const int budget = (228 * 1024) / occ_target - 1024 /* driver reserve */ - 512 /* static */ - 128 /* align */;
   const int stage_pitch = (stage_bytes<NBITS>(a.nsub) + 127) & ~127;
