@@ -112,6 +112,23 @@ int q100_quantize_groupwise(const void* x, int dtype, int64_t rows, int64_t cols
                             int flags, void* stream);
 
 /*
+ * K1b -- backward of the group-wise fake-quantizer (what torch autograd computes through
+ * UniformAffineQuantizer.forward, quant/quantizer.py:94-159, in the calibration loop of
+ * quant/omniquant.py:261-293): straight-through estimator for round(), clamp mask, the scale's
+ * dependence on the group's min / max (shared equally by tied positions) and on the LWC
+ * multipliers; no gradient through the zero-point (quantizer.py:158 rounds it without STE).
+ *   x, grad_out  [rows, cols] in `dtype` (x = the forward's input, grad_out = d loss / d dequant)
+ *   group        32, 64, 128 or 256 elements (Q100_EUNSUPPORTED otherwise: the caller keeps its own path)
+ *   lwc_up/low   nullable, [rows*cols/group] post-sigmoid multipliers as given to the forward
+ *   grad_x       nullable; [rows, cols]
+ *   grad_up/low  nullable; [rows*cols/group] d loss / d multiplier (only written with LWC)
+ */
+int q100_quantize_backward(const void* x, const void* grad_out, int dtype, int64_t rows, int64_t cols,
+                           int group, int n_bits, int symmetric, int disable_zp,
+                           const void* lwc_up, const void* lwc_low,
+                           void* grad_x, void* grad_up, void* grad_low, void* stream);
+
+/*
  * K2 -- per-token activation fake-quant (asymmetric, one group per row), the
  * act_quantizer / x1_quantizer / x2_quantizer call of quant/int_linear.py:59-60 and
  * quant/int_matmul.py:31-39.  Thin alias of q100_quantize_groupwise(group = 0).

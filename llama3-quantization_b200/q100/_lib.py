@@ -35,6 +35,7 @@ SIGNATURES = {
     "q100_abi_version": (_i, []),
     "q100_device_ok": (_i, [_i]),
     "q100_quantize_groupwise": (_i, [_vp, _i, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+    "q100_quantize_backward": (_i, [_vp, _vp, _i, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "q100_fakequant_rows": (_i, [_vp, _i, _i64, _i64, _i, _vp, _vp, _vp, _i, _vp]),
     "q100_packed_words": (_i64, [_i64, _i64, _i]),
     "q100_dequantize": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _i, _i, _i, _vp, _vp]),

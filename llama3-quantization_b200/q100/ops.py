@@ -104,6 +104,37 @@ def quantize_groupwise(x: torch.Tensor, group: int, n_bits: int, symmetric: bool
     return res
 
 
+BACKWARD_GROUPS = (32, 64, 128, 256)
+
+
+def quantize_backward(x: torch.Tensor, grad_out: torch.Tensor, group: int, n_bits: int, symmetric: bool = False,
+                      disable_zero_point: bool = False, lwc_up: Optional[torch.Tensor] = None,
+                      lwc_low: Optional[torch.Tensor] = None, need_x: bool = True, need_lwc: bool = False):
+    """Fused backward of :func:`quantize_groupwise` (K1b).  Returns (grad_x, grad_up, grad_low); entries that were
+    not asked for (or have no meaning without LWC) are None.  ``group`` must be in BACKWARD_GROUPS."""
+    _require_cuda(x, grad_out, lwc_up, lwc_low)
+    if x.dim() != 2 or grad_out.shape != x.shape:
+        raise ValueError("q100.quantize_backward expects 2-D x and grad_out of the same shape")
+    x = x.contiguous()
+    grad_out = grad_out.to(x.dtype).contiguous()
+    rows, cols = x.shape
+    n_groups = rows * (cols // group)
+    gx = torch.empty_like(x) if need_x else None
+    gup = glow = None
+    if lwc_up is not None:
+        lwc_up = lwc_up.to(x.dtype).contiguous()
+        lwc_low = lwc_low.to(x.dtype).contiguous()
+        if need_lwc:
+            gup = torch.empty((n_groups, 1), dtype=x.dtype, device=x.device)
+            glow = torch.empty((n_groups, 1), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.q100_quantize_backward(
+            x.data_ptr(), grad_out.data_ptr(), _dtype_code(x), rows, cols, int(group), n_bits,
+            int(bool(symmetric)), int(bool(disable_zero_point)), _ptr(lwc_up), _ptr(lwc_low),
+            _ptr(gx), _ptr(gup), _ptr(glow), _stream(x)))
+    return gx, gup, glow
+
+
 def fakequant_rows(x: torch.Tensor, n_bits: int, flags: int = 0) -> QuantResult:
     """Per-token activation fake-quant over the last dim (any leading shape)."""
     _require_cuda(x)

@@ -109,6 +109,11 @@ class _FakeQuantFn(torch.autograd.Function):
         g = x2d.shape[1] if group in (0, None) else group
         need_x = ctx.needs_input_grad[0]
         need_lwc = su is not None and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2])
+        if g in _ops.BACKWARD_GROUPS and x2d.shape[1] % g == 0 and (need_x or need_lwc):
+            # K1b: one fused pass (libq100 q100_quantize_backward); other group sizes keep the op-by-op form below
+            gx, gsu, gsl = _ops.quantize_backward(x2d, gout, g, n_bits, symmetric, zp is None, su, sl,
+                                                  need_x, need_lwc)
+            return gx, gsu, gsl, None, None, None, None, None, None
         gx, gsu, gsl = fake_quant_backward(
             x2d.reshape(-1, g), gout.reshape(-1, g), scale, zp, su, sl,
             n_bits, symmetric, qmin, qmax, need_x, need_lwc)

@@ -122,6 +122,7 @@ def test_backward_matches_autograd(bits, sym, lwc, group):
 
 def test_markstein_scale_division_exhaustive():
     """tools/check_markstein.py: k1_fast's scale division equals div.rn.f32 in 16 bits for every input."""
+    import os
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

@@ -239,3 +239,71 @@ def test_k1_fast_vs_generic_stress(dtype, n_bits, group):
                 assert torch.equal(a.zeros.view(torch.int16), b.zeros.view(torch.int16)), "zeros " + tag
             assert torch.equal(a.packed, b.packed), "packed " + tag
             assert torch.equal(a.meta.view(torch.int16), b.meta.view(torch.int16)), "meta " + tag
+
+
+@pytest.mark.parametrize("dtype", ["f32", "f16", "bf16"])
+@pytest.mark.parametrize("n_bits", [2, 3, 4, 8])
+@pytest.mark.parametrize("group", [32, 64, 128, 256])
+def test_backward_kernel_vs_op_by_op(dtype, n_bits, group):
+    """K1b (q100_quantize_backward) against quant.quantizer.fake_quant_backward -- the op-by-op form that
+    tests/test_host_logic.py pins to torch autograd through the reference op sequence.  The STE mask comes from
+    the same per-op arithmetic as the forward (exact); the gradient arithmetic is fp32 in the kernel and
+    per-op-rounded in torch, hence the dtype-dependent tolerance."""
+    from quant.quantizer import fake_quant_backward
+    gen = torch.Generator(device="cpu").manual_seed(77 + n_bits + group)
+    rows, cols = 96, 1024
+    x = (torch.randn(rows, cols, generator=gen) * 0.05).to(TDT[dtype]).cuda()
+    x[3, :group] = 0.25                                     # constant group: every element is both min and max
+    x[4, 5] = x[4, 6] = x[4, :group].max()                  # tied maxima
+    go = torch.randn(rows, cols, generator=gen).to(TDT[dtype]).cuda()
+    ng = rows * cols // group
+    su = (torch.rand(ng, 1, generator=gen) * 0.4 + 0.6).to(TDT[dtype]).cuda()
+    sl = (torch.rand(ng, 1, generator=gen) * 0.4 + 0.6).to(TDT[dtype]).cuda()
+    tol = {"f32": 2e-5, "f16": 4e-3, "bf16": 3e-2}[dtype]
+    for sym, nozp, lwc in ((False, False, False), (False, False, True), (True, False, True), (False, True, False),
+                           (True, True, True)):
+        up, low = (su, sl) if lwc else (None, None)
+        r = q100.quantize_groupwise(x, group, n_bits, sym, nozp, up, low)
+        qmin, qmax = O.qrange(n_bits, nozp)
+        want = fake_quant_backward(x.reshape(-1, group), go.reshape(-1, group), r.scales, r.zeros, up, low,
+                                   n_bits, sym, qmin, qmax, True, lwc)
+        got = q100.ops.quantize_backward(x, go, group, n_bits, sym, nozp, up, low, True, lwc)
+        torch.cuda.synchronize()
+        tag = f"sym={sym} nozp={nozp} lwc={lwc}"
+        for name, g_, w_ in (("grad_x", got[0], want[0].reshape(rows, cols)), ("grad_up", got[1], want[1]),
+                             ("grad_low", got[2], want[2])):
+            if w_ is None:
+                assert g_ is None, name + " " + tag
+                continue
+            g64, w64 = g_.double(), w_.double()
+            err = (g64 - w64).abs()
+            # 16-bit: torch rounds every product of the group sum to the storage type before adding, the kernel keeps
+            # fp32 -- the reference's own noise scales with the largest term, not with the (cancelling) sum
+            ref_mag = w64.abs().mean() if dtype == "f32" else w64.abs().max()
+            bound = tol * (w64.abs() + ref_mag + 1e-6)
+            bad = err > bound
+            assert bad.sum().item() <= (0 if dtype == "f32" else bad.numel() // 1000), \
+                f"{name} {tag}: {int(bad.sum())}/{bad.numel()} outside tolerance, max err {err.max().item():.3e}"
+
+
+def test_backward_through_module_matches_autograd_of_port():
+    """End to end: UniformAffineQuantizer (LWC on) under autograd uses K1b; compare with torch autograd through
+    the torch restatement of the reference op sequence (oracle/torch_port.py)."""
+    import torch_port as TPORT
+    from quant.quantizer import UniformAffineQuantizer
+    torch.manual_seed(5)
+    w = (torch.randn(64, 512) * 0.03).cuda().requires_grad_(True)
+    q = UniformAffineQuantizer(n_bits=4, per_channel_axes=[0], symmetric=False, dynamic_method="per_channel",
+                               group_size=128, lwc=True, shape=w.shape).cuda()
+    go = torch.randn(64, 512, device="cuda")
+    out = q(w)
+    out.backward(go)
+    gw, gu, gl = w.grad.clone(), q.upbound_factor.grad.clone(), q.lowbound_factor.grad.clone()
+    w2 = w.detach().clone().requires_grad_(True)
+    up = q.upbound_factor.detach().clone().requires_grad_(True)
+    low = q.lowbound_factor.detach().clone().requires_grad_(True)
+    ref, _, _ = TPORT.fake_quant(w2, 4, 128, False, False, up, low)
+    ref.backward(go)
+    for a, b, nm in ((gw, w2.grad, "weight"), (gu, up.grad, "upbound"), (gl, low.grad, "lowbound")):
+        assert torch.allclose(a, b, rtol=2e-4, atol=1e-6 + 1e-4 * b.abs().mean().item()), \
+            f"{nm}: max err {(a - b).abs().max().item():.3e}"

@@ -32,7 +32,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = os.environ.get("Q100_NVCC_FLAGS", "").split() + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
           "--expt-relaxed-constexpr", "-I", os.path.join(ROOT, "include")]
 # per-file extras: the quantize kernels must not contract mul+add (bit-exact per-op rounding)
-EXTRA = {"q100_quant.cu": ["-fmad=false"]}
+EXTRA = {"q100_quant.cu": ["-fmad=false"], "q100_quant_bwd.cu": ["-fmad=false"]}
 
 
 def nvcc() -> str:
