@@ -380,6 +380,22 @@ def run_ours(args):
             gbs = n_el * bpe / (msq * 1e-3) / 1e9
             quant[nm] = {"ms": msq, "GBps": gbs, "frac_hbm": gbs / P["hbm"], "bytes_per_element": bpe}
         del wq
+        # K2: per-token activation fake-quant (the act_quantizer of the W8A8 / W4A4 configurations), prefill-size input
+        xa = [torch.randn(M_PRE, HIDDEN, device=dev).to(torch.float16) for _ in range(3)]
+
+        def q_act():
+            q100.fakequant_rows(xa[qi[0] % 3], 8)
+            qi[0] += 1
+
+        for _ in range(5):
+            q_act()
+        torch.cuda.synchronize()
+        msq = timed(q_act, 30)
+        bpe = 4.0 + 4.0 / HIDDEN
+        gbs = M_PRE * HIDDEN * bpe / (msq * 1e-3) / 1e9
+        quant["act_fake_quant_f16_a8"] = {"ms": msq, "GBps": gbs, "frac_hbm": gbs / P["hbm"], "bytes_per_element": bpe,
+                                          "shape": [M_PRE, HIDDEN]}
+        del xa
         # K1b: fused backward of the quantizer (calibration loop), fp32 like the reference's training dtype, LWC on
         from q100 import ops as _qops
         xb = torch.randn(INTER, HIDDEN, device=dev) * 0.02

@@ -443,6 +443,24 @@ __device__ __forceinline__ bool fast_params(typename Packed16<T>::T2 m, const Qu
   return (lim < FastLimit<T>::value) && (fabsf(q.zp) < FastLimit<T>::value) && (num < inf) && (fabsf(xmin) < inf);
 }
 
+// the same per-group constants from fp32 group parameters (K2: one set per row and thread)
+template <typename T>
+__device__ __forceinline__ FastQ<T> fast_from_group(const GroupQ<T>& q, const QuantArgs& a) {
+  using P = Packed16<T>;
+  constexpr float C = P::kRintMagic;
+  FastQ<T> f;
+  f.magic = P::bcast(C);
+  f.nlo = P::bcast(-(C + a.qmin - q.zp));
+  f.range = P::bcast(a.qmax - a.qmin);
+  f.top = P::bcast(a.qmax - q.zp);
+  f.ktop = P::bcast(CodeMagic<T>::kMagic + (a.qmax - a.qmin));
+  f.scale = P::bcast(q.scale);
+  f.one = P::bcast(1.0f);
+  f.rcp2 = pack_f2(q.rcp, q.rcp);
+  f.nscale2 = pack_f2(-q.scale, -q.scale);
+  return f;
+}
+
 // Clamp without the ALU pipe (HMNMX2 shares it with the integer work; profiles/r01i): with t = C + rint(v),
 //   u = relu(t - (C + qmin - zp)) = max(x_int, qmin) - qmin,   w = relu((qmax - qmin) - u),
 //   code = (qmax - qmin) - w,   x_int - zp = (qmax - zp) - w          (exact integer arithmetic throughout).
@@ -652,6 +670,37 @@ __global__ void __launch_bounds__(1024) k2_rows(const QuantArgs a) {
     }
     __syncthreads();                                   // s_mn/s_mx reusable next row
     const GroupQ<T> q = group_params<T>(mn, mx, a, row);
+    // rows whose |x / scale| and |zp| fit the exact-integer window take k1_fast's element pass (CTA-uniform)
+    if constexpr (MATH == MATH_PACKED && DT<T>::kCode != Q100_F32) {
+      const float lim = fmaxf(fabsf(mn), fabsf(mx)) * q.rcp;                 // NaN / inf: false
+      const bool code_ok = !PACK || DT<T>::kCode == Q100_F16 || a.n_bits <= 4;  // bf16 cannot carry 128 + an 8-bit code
+      if (lim < FastLimit<T>::value && fabsf(q.zp) < FastLimit<T>::value && code_ok) {
+        const FastQ<T> f = fast_from_group<T>(q, a);
+#pragma unroll
+        for (int k = 0; k < VMAX; ++k) {
+          if (k < vper) {
+            const int idx = k * nt + tid;
+            const bool valid = idx < nvec;
+            uint32_t pairs[4] = {0u, 0u, 0u, 0u};
+            uint4 o = make_uint4(0, 0, 0, 0);
+            if (valid) {
+              o.x = fast_pair<T, true, PACK>(v[k].x, f, pairs[0]);
+              o.y = fast_pair<T, true, PACK>(v[k].y, f, pairs[1]);
+              o.z = fast_pair<T, true, PACK>(v[k].z, f, pairs[2]);
+              o.w = fast_pair<T, true, PACK>(v[k].w, f, pairs[3]);
+            }
+            if (dq != nullptr && valid) stg_stream(dq + row * nvec + idx, o);
+            if (PACK) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) pairs[j] &= CodeMagic<T>::kMask;
+              emit_packed<8>(pairs, a, static_cast<int>(row), idx, valid);
+            }
+          }
+        }
+        if (tid == 0) store_group_meta<T>(a, row, q);
+        continue;
+      }
+    }
 #pragma unroll
     for (int k = 0; k < VMAX; ++k) {
       if (k < vper) {
