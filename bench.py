@@ -218,15 +218,9 @@ def run_ours(args):
         for name, n, k, src in LINEARS:
             pw, mode = blk[name]
             x = tp.shard_input(xs[src], mode, rank, world) if world > 1 else xs[src]
-            if world > 1 and mode == tp.ROW:
-                # row-parallel: all-reduce of token chunk i overlaps the GEMM of chunk i+1 (q100/tp.py)
-                def lin(xc, pw=pw):
-                    launches[0] += 1
-                    return q100.gemm_wna16(xc, pw, None, flags)
-                y = tp.row_parallel_overlapped(x, lin)
-            else:
-                y = q100.gemm_wna16(x, pw, None, flags)
-                launches[0] += 1
+            y = q100.gemm_wna16(x, pw, None, flags)
+            launches[0] += 1
+            tp.reduce_output(y, mode)
             outs.append(y)
         return outs
 
@@ -464,7 +458,7 @@ def run_ours(args):
                 keep = []
                 for (ql, src, mode), ho in zip(mods, hout):
                     cur.wait_event(ready[src])
-                    y = tp.row_parallel_overlapped(din[src], ql) if mode == tp.ROW else ql(din[src])
+                    y = tp.reduce_output(ql(din[src]), mode)
                     done = cur.record_event()
                     with torch.cuda.stream(s_out):
                         s_out.wait_event(done)

@@ -193,10 +193,8 @@ class QuantLlamaMLP(nn.Module):
             gate, up = fused
         else:
             gate, up = self.gate_proj(x), self.up_proj(x)
-        h = self.act_fn(gate) * up
-        if getattr(self, "tp_world", 1) > 1:
-            return _tp.row_parallel_overlapped(h, self.down_proj, self.tp_group)
-        return self.down_proj(h)
+        out = self.down_proj(self.act_fn(gate) * up)
+        return _tp.reduce_output(out, _tp.ROW, self.tp_group) if getattr(self, "tp_world", 1) > 1 else out
 
 
 class QuantLlamaAttention(nn.Module):
@@ -322,10 +320,9 @@ class QuantLlamaAttention(nn.Module):
             )
         attn_output = attn_output.transpose(1, 2)
         attn_output = attn_output.reshape(bsz, q_len, nh * self.head_dim)
+        attn_output = self.o_proj(attn_output)
         if self.tp_world > 1:
-            attn_output = _tp.row_parallel_overlapped(attn_output, self.o_proj, self.tp_group)
-        else:
-            attn_output = self.o_proj(attn_output)
+            attn_output = _tp.reduce_output(attn_output, _tp.ROW, self.tp_group)
         if not output_attentions:
             attn_weights = None
         return attn_output, attn_weights, past_key_value

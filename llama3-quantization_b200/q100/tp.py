@@ -84,32 +84,6 @@ def reduce_output(y: torch.Tensor, mode: str, group: Optional[dist.ProcessGroup]
     return y
 
 
-def row_parallel_overlapped(x: torch.Tensor, linear, group: Optional[dist.ProcessGroup] = None,
-                            n_chunks: int = 4, min_tokens: int = 1024) -> torch.Tensor:
-    """``all_reduce(linear(x))`` for a row-parallel linear with the collective of token chunk i running while the
-    GEMM of chunk i+1 computes (the all-reduce is element-wise over tokens, so chunking along the token dim changes
-    nothing but the schedule).  ``linear`` maps [m, K_local] -> [m, N].  Falls back to one GEMM + one all-reduce
-    when there is a single rank or too few tokens to split (decode)."""
-    if not dist.is_initialized() or dist.get_world_size(group) == 1:
-        return linear(x)
-    lead = x.shape[:-1]
-    x2 = x.reshape(-1, x.shape[-1])
-    m = x2.shape[0]
-    n = min(n_chunks, m // max(min_tokens, 1))
-    if n < 2:
-        return reduce_output(linear(x), ROW, group)
-    step = (m + n - 1) // n
-    outs, works = [], []
-    for m0 in range(0, m, step):
-        y = linear(x2[m0:m0 + step])
-        works.append(dist.all_reduce(y, op=dist.ReduceOp.SUM, group=group, async_op=True))
-        outs.append(y)
-    for w in works:
-        w.wait()
-    y = torch.cat(outs, dim=0)
-    return y.reshape(*lead, y.shape[-1])
-
-
 def gather_columns(y: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
     """all-gather of a column-parallel output along the feature dim (only needed when the
     consumer is not row-parallel, e.g. a vocab-sharded lm_head)."""

@@ -43,23 +43,6 @@ def _worker(rank, world, port, results):
         ref = x.astype(np.float64) @ full["dequant"].astype(np.float64).T
         assert np.allclose(y.numpy(), ref, rtol=1e-12, atol=1e-12)
 
-        # --- the same with the all-reduce pipelined over token chunks (prefill): identical result
-        xb = rng.randn(40, K).astype(np.float32)
-        xbl = tp.shard_input(torch.from_numpy(xb), tp.ROW, rank, world)
-        wt = torch.from_numpy(loc["dequant"].astype(np.float64).T)
-        calls = []
-
-        def lin(xc):
-            calls.append(xc.shape[0])
-            return xc.double() @ wt
-        yo = tp.row_parallel_overlapped(xbl.reshape(2, 20, -1), lin, None, n_chunks=4, min_tokens=8)
-        assert calls == [10, 10, 10, 10] and tuple(yo.shape) == (2, 20, N)
-        refb = xb.astype(np.float64) @ full["dequant"].astype(np.float64).T
-        assert np.allclose(yo.reshape(40, N).numpy(), refb, rtol=1e-12, atol=1e-12)
-        calls.clear()
-        y1 = tp.row_parallel_overlapped(xbl[:3], lin, None)                      # too few tokens: one GEMM
-        assert calls == [3] and np.allclose(y1.numpy(), refb[:3], rtol=1e-12, atol=1e-12)
-
         # --- column-parallel: N split, no collective; gather only for the check
         shc = tp.shard_bounds(N, K, tp.COLUMN, rank, world, 128)
         locc = O.quantize_groupwise(w[shc.n0:shc.n1], "f16", 128, 4)
