@@ -265,7 +265,7 @@ def run_ours(args):
                 "achieved": ach, "peak": P["tc_burst"], "unit": "TFLOP/s", "frac": ach / P["tc_burst"],
                 "peak_src": P["src"] + " cuBLAS bf16 burst",
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel (single GPU, up_proj,
-                # M = 2048) from the committed ncu --set full capture, profiles/r01j_full_tca.md: 48.6 + 11.9 MB
+                # M = 2048) from the committed ncu --set full capture, profiles/r01k_full_tca.md: 48.6 + 11.9 MB
                 # against 106.7 MB of algorithmic operand bytes (x 16.8, codes + side band 31.2, y 58.7 -- most of
                 # y is still in the 126 MB L2 when the kernel ends); null for shapes the capture does not cover
                 "traffic": 60.53e6 if (world == 1 and M_PRE == 2048) else None, "traffic_unit": "bytes per launch",

@@ -849,7 +849,7 @@ k3_skinny(const SkinnyArgs a) {
       for (int i = 0; i < MB * 4; ++i) dst[i] = ld_volatile_u2(wst + static_cast<int64_t>(sl) * FRAG + i * 32 + lane);
     };
     // the loads of up to RB slots are put in flight together: the reducer pays about one L2 round trip per
-    // batch instead of one per contributor (profiles/r01j: the serial version kept the reducers 3-4 us past
+    // batch instead of one per contributor (profiles/r01k: the serial version kept the reducers 3-4 us past
     // the median CTA); the sum still runs in slot order, so the result stays deterministic
     constexpr int RB = MB == 1 ? 6 : MB == 2 ? 3 : 2;
     for (int base = 0; base < pend_n; base += RB) {
@@ -1068,7 +1068,7 @@ static int launch_skinny_post(const SkinnyArgs& a, cudaStream_t st) {
 template <typename T, int NBITS>
 static int launch_skinny_mb(const SkinnyArgs& a, cudaStream_t st) {
   if constexpr (NBITS == 4) {
-    // integer tensor-core path.  Measured (profiles/r01j): with one column group (M <= 2) it beats the fp16 form
+    // integer tensor-core path.  Measured (profiles/r01k): with one column group (M <= 2) it beats the fp16 form
     // (gate|up 16.6 vs 19.3 us); with two groups (M = 4) the extra MMAs, int->float conversions and limb staging
     // lose (25.3 vs 21.6 us), so larger M stay on the fp16 form.
     if (a.post == 2) return launch_skinny<T, 4, 1, 2>(a, st);

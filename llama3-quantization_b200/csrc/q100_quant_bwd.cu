@@ -182,7 +182,12 @@ static int launch_bwd_lv(const BwdArgs& b, cudaStream_t st) {
   constexpr int GPW = 32 / L;
   const int64_t warps_needed = (b.q.n_groups + GPW - 1) / GPW;
   int64_t blocks = (warps_needed + 7) / 8;
-  const int64_t cap = static_cast<int64_t>(sm_count()) * 6;
+  // persistent grid = what the SMs hold at once (80 registers: 3 CTAs per SM; a fixed 6 per SM ran as two waves)
+  static const int64_t cap = []() {
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k1_backward<T, L, V>, 256, 0) != cudaSuccess || occ < 1) occ = 2;
+    return static_cast<int64_t>(occ) * sm_count();
+  }();
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   k1_backward<T, L, V><<<static_cast<unsigned>(blocks), 256, 0, st>>>(b);
