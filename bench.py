@@ -171,6 +171,10 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        if not os.environ.get("Q100_NO_PEER"):
+            # K7: the small all-reduces of the decode steps go over peer memory instead of NCCL (falls back by itself)
+            from q100 import peer
+            peer.enable(None, dev)
     P = peaks()
     dt_t = torch.bfloat16
     flags = _lib.GEMM_FORCE_SKINNY if os.environ.get("Q100_BENCH_FORCE_SKINNY") else 0
@@ -542,7 +546,26 @@ def run_ours(args):
                 "gpu_launches": n_launch, "clocks": clocks, "peaks": P}
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        _teardown_distributed()
+
+
+def _teardown_distributed():
+    """Peer buffers (symmetric memory) must go before the process group; a watchdog makes sure a stuck teardown can
+    never keep the job alive after the result line is out."""
+    import gc
+    import threading
+    import torch.distributed as dist
+    threading.Timer(45.0, lambda: os._exit(0)).start()
+    try:
+        from q100 import peer
+        peer.shutdown()
+    except Exception:                                               # noqa: BLE001
+        pass
+    gc.collect()
+    torch.cuda.synchronize()
+    dist.barrier()
+    dist.destroy_process_group()
+    os._exit(0)
 
 
 def main():

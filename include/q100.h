@@ -203,6 +203,24 @@ int q100_rope_kv_decode(const void* qkv, const void* cos_cache, const void* sin_
 int q100_silu_mul(const void* gate_up, void* out, int64_t rows, int64_t inter, int dtype, void* stream);
 
 /*
+ * K7 -- one-shot all-reduce(sum) of a small tensor over peer memory (NVLink): the collective after a
+ * row-parallel linear (o_proj, down_proj) at decode shapes, where NCCL's all-reduce is latency-bound
+ * (the reference has no counterpart -- it places layers, parallel_utils.py:89-163).
+ *   x, y        [n] in `dtype` (fp16 / bf16), n % 8 == 0; y may alias x
+ *   peer_bufs   DEVICE array [world] of pointers to every rank's staging buffer of 2 * world * slot_elems
+ *               elements, mapped into this process (e.g. torch symmetric memory: handle.buffer_ptrs_dev)
+ *   peer_flags  DEVICE array [world] of pointers to every rank's 2 * world * 32 uint32 flag words, zeroed
+ *               before the first call (all ranks, followed by a barrier)
+ *   epoch       this rank's 32 uint32 call counters, zeroed before the first call; advanced by the kernel
+ *   err_flag    one uint32, set to 1 if a peer did not answer within 30 s (the call then returns garbage
+ *               instead of hanging the GPU)
+ * Every rank must issue the same sequence of calls (same n).  Safe to capture in a CUDA graph.
+ */
+int q100_allreduce_oneshot(const void* x, void* y, int64_t n, int dtype, const void* peer_bufs,
+                           const void* peer_flags, void* epoch, int64_t slot_elems, int rank, int world,
+                           void* err_flag, void* stream);
+
+/*
  * Development / verification hooks (used by tests only).
  * q100_selftest_div: exhaustively compares the fast 16-bit division sequence with
  * div.rn.f32 + round over all (x, scale) pairs of `dtype` with scale in [1e-5, 1e4];

@@ -1,0 +1,123 @@
+// q100_peer.cu -- K7: one-shot all-reduce(sum) of a small tensor over peer memory (NVLink / NVSwitch).
+//
+// The only data-path collective of the tensor-parallel block is the all-reduce after the row-parallel linears
+// (o_proj, down_proj).  At decode shapes that is 8-128 KB per call: latency, not bandwidth.
+// NCCL spends ~10-15 us on it; this kernel needs one NVLink store round:
+//
+//   push   every rank stores its partial into slot [parity][rank] of EVERY rank's staging buffer (peer-mapped
+//          symmetric memory), fences, then stores the call's epoch into flag [parity][rank][cta] of every rank;
+//   wait   CTA c polls its own flags [parity][r][c] (acquire) until all `world` of them carry the epoch;
+//   sum    it adds the `world` local slots in rank order (fp32, one rounding): every rank computes the same bits.
+//
+// The protocol is chunk-local (CTA c of every rank owns elements [c*per, (c+1)*per)), so no grid-wide barrier is
+// needed.  Two parity sets make slot reuse safe: a rank can only start call e+2 after every peer has flagged e+1,
+// i.e. after every peer has finished summing call e.  The epoch lives in device memory (one counter per CTA,
+// advanced by the kernel), so the launch has no per-call host state and can be captured in a CUDA graph.
+#include "q100_common.cuh"
+
+namespace q100 {
+
+constexpr int K7_MAX_CTAS = 32;   // flag words per (parity, rank)
+constexpr int K7_CTAS = 16;       // CTAs per call
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k7_allreduce(const T* __restrict__ x, T* __restrict__ y, int64_t n,
+                                                    T* const* __restrict__ bufs, uint32_t* const* __restrict__ flags,
+                                                    uint32_t* __restrict__ epoch_p, int64_t slot_elems, int rank,
+                                                    int world, uint32_t* __restrict__ err) {
+  using D = DT<T>;
+  const int c = blockIdx.x, tid = threadIdx.x;
+  const uint32_t e = epoch_p[c] + 1;
+  const int par = static_cast<int>(e & 1u);
+  const int64_t nvec = n >> 3;                                   // 16-byte vectors (n % 8 == 0)
+  const int64_t per = (nvec + gridDim.x - 1) / gridDim.x;
+  const int64_t v0 = c * per, v1 = min(nvec, v0 + per);
+
+  // ---- push my chunk into slot [par][rank] of every rank (own buffer included), peers first
+  const uint4* xs = reinterpret_cast<const uint4*>(x);
+  for (int k = 1; k <= world; ++k) {
+    const int p = (rank + k) % world;
+    uint4* dst = reinterpret_cast<uint4*>(bufs[p] + (static_cast<int64_t>(par) * world + rank) * slot_elems);
+    for (int64_t v = v0 + tid; v < v1; v += blockDim.x) dst[v] = xs[v];
+  }
+  // bar.sync orders every thread's stores before the flag writers; st.release.sys (= fence.acq_rel.sys + store) is
+  // cumulative over them, so no per-thread MEMBAR.SYS is needed
+  __syncthreads();
+  if (tid < world)
+    st_release_sys(flags[tid] + (static_cast<int64_t>(par) * world + rank) * K7_MAX_CTAS + c, e);
+
+  // ---- wait for every rank's chunk c of this call
+  if (tid < world) {
+    const uint32_t* f = flags[rank] + (static_cast<int64_t>(par) * world + tid) * K7_MAX_CTAS + c;
+    const unsigned long long t0 = gtimer();
+    while (ld_acquire_sys(f) != e) {
+      if (gtimer() - t0 > 30000000000ull) { atomicExch(err, 1u); break; }     // 30 s: a peer is gone; do not hang
+    }
+  }
+  __syncthreads();
+
+  // ---- sum the world slots in rank order
+  const T* mine = bufs[rank] + static_cast<int64_t>(par) * world * slot_elems;
+  uint4* ys = reinterpret_cast<uint4*>(y);
+  for (int64_t v = v0 + tid; v < v1; v += blockDim.x) {
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int r = 0; r < world; ++r) {
+      const uint4 q = reinterpret_cast<const uint4*>(mine + r * slot_elems)[v];
+      const float2 a = D::to_f2(q.x), b = D::to_f2(q.y), cc = D::to_f2(q.z), d = D::to_f2(q.w);
+      acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+      acc[4] += cc.x; acc[5] += cc.y; acc[6] += d.x; acc[7] += d.y;
+    }
+    ys[v] = make_uint4(D::pack2(acc[0], acc[1]), D::pack2(acc[2], acc[3]), D::pack2(acc[4], acc[5]),
+                       D::pack2(acc[6], acc[7]));
+  }
+  __syncthreads();
+  if (tid == 0) epoch_p[c] = e;
+}
+
+}  // namespace q100
+
+using namespace q100;
+
+extern "C" int q100_allreduce_oneshot(const void* x, void* y, int64_t n, int dtype, const void* peer_bufs,
+                                      const void* peer_flags, void* epoch, int64_t slot_elems, int rank, int world,
+                                      void* err_flag, void* stream) {
+  Q100_REQUIRE(x && y && peer_bufs && peer_flags && epoch && err_flag, Q100_EINVAL, "NULL pointer argument");
+  Q100_REQUIRE(dtype == Q100_F16 || dtype == Q100_BF16, Q100_EUNSUPPORTED, "fp16 / bf16 only (got dtype %d)", dtype);
+  Q100_REQUIRE(world >= 2 && world <= 16 && rank >= 0 && rank < world, Q100_EINVAL, "bad rank %d / world %d", rank, world);
+  Q100_REQUIRE(n > 0 && n % 8 == 0 && n <= slot_elems, Q100_EUNSUPPORTED,
+               "n=%lld must be a positive multiple of 8 and fit a slot of %lld elements", (long long)n, (long long)slot_elems);
+  Q100_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0 && slot_elems % 8 == 0,
+               Q100_EINVAL, "x / y must be 16-byte aligned");
+  int rc = ensure_device();
+  if (rc != Q100_OK) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  // a FIXED number of CTAs, whatever n: all per-CTA epoch counters then advance in lockstep, so every CTA of a call
+  // uses the same parity set and the slot-reuse argument (file header) holds across calls of different sizes
+  const int ctas = K7_CTAS;
+  if (dtype == Q100_F16)
+    k7_allreduce<__half><<<ctas, 256, 0, st>>>(reinterpret_cast<const __half*>(x), reinterpret_cast<__half*>(y), n,
+        reinterpret_cast<__half* const*>(peer_bufs), reinterpret_cast<uint32_t* const*>(peer_flags),
+        reinterpret_cast<uint32_t*>(epoch), slot_elems, rank, world, reinterpret_cast<uint32_t*>(err_flag));
+  else
+    k7_allreduce<__nv_bfloat16><<<ctas, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(x),
+        reinterpret_cast<__nv_bfloat16*>(y), n, reinterpret_cast<__nv_bfloat16* const*>(peer_bufs),
+        reinterpret_cast<uint32_t* const*>(peer_flags), reinterpret_cast<uint32_t*>(epoch), slot_elems, rank, world,
+        reinterpret_cast<uint32_t*>(err_flag));
+  return check_cuda(cudaGetLastError(), "k7_allreduce launch");
+}

@@ -1,0 +1,83 @@
+"""One-shot all-reduce over peer memory (K7, csrc/q100_peer.cu) for the small row-parallel outputs of a
+tensor-parallel decode step.  Staging buffers and flags live in torch symmetric memory (peer-mapped over NVLink);
+if that cannot be set up (single rank, no peer access, older torch) `get()` returns None and the caller stays on
+NCCL.  Setup is collective: every rank of the group must call :func:`enable` at the same point, outside CUDA-graph
+capture."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+from ._lib import check, lib
+
+_DT = {torch.float16: _lib.F16, torch.bfloat16: _lib.BF16}
+_STATE: dict = {}
+FLAG_WORDS = 32                       # K7_MAX_CTAS
+
+
+class OneShotAllReduce:
+    def __init__(self, group, device: torch.device, slot_elems: int):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.device = device
+        self.slot_elems = int(slot_elems)
+        self.buf = symm.empty(2 * self.world * self.slot_elems, dtype=torch.float16, device=device)
+        self.flags = symm.empty(2 * self.world * FLAG_WORDS, dtype=torch.int32, device=device)
+        self.flags.zero_()
+        self.h_buf = symm.rendezvous(self.buf, self.group)
+        self.h_flags = symm.rendezvous(self.flags, self.group)
+        self.epoch = torch.zeros(FLAG_WORDS, dtype=torch.int32, device=device)
+        self.err = torch.zeros(1, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(self.group)                                  # every rank's flags are zero before the first call
+
+    def __call__(self, y: torch.Tensor) -> torch.Tensor:
+        """In-place all-reduce(sum) of a contiguous fp16 / bf16 tensor of at most slot_elems elements."""
+        n = y.numel()
+        with torch.cuda.device(self.device):
+            check(lib.q100_allreduce_oneshot(
+                y.data_ptr(), y.data_ptr(), n, _DT[y.dtype], self.h_buf.buffer_ptrs_dev, self.h_flags.buffer_ptrs_dev,
+                self.epoch.data_ptr(), self.slot_elems, self.rank, self.world, self.err.data_ptr(),
+                torch.cuda.current_stream(self.device).cuda_stream))
+        return y
+
+    def fits(self, y: torch.Tensor) -> bool:
+        return (y.is_cuda and y.dtype in _DT and y.is_contiguous() and y.numel() % 8 == 0
+                and 0 < y.numel() <= self.slot_elems and y.data_ptr() % 16 == 0)
+
+
+def enable(group=None, device: Optional[torch.device] = None, slot_elems: int = 16 * 8192) -> Optional[OneShotAllReduce]:
+    """Collective.  Sets up the peer buffers for ``group`` (default: world); returns None (and remembers it) when
+    symmetric memory is not available, in which case reduce_output keeps using NCCL."""
+    key = group
+    if key in _STATE:
+        return _STATE[key]
+    obj = None
+    if dist.is_initialized() and dist.get_world_size(group) > 1 and torch.cuda.is_available():
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        ok = torch.ones(1, device=dev)
+        try:
+            obj = OneShotAllReduce(group, dev, slot_elems)
+        except Exception as e:                                     # noqa: BLE001 -- any setup failure => NCCL
+            import warnings
+            warnings.warn(f"q100.peer: symmetric memory unavailable, small all-reduces stay on NCCL ({e!r})")
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)   # all ranks or none
+        if ok.item() == 0:
+            obj = None
+    _STATE[key] = obj
+    return obj
+
+
+def get(group=None) -> Optional[OneShotAllReduce]:
+    return _STATE.get(group)
+
+
+def shutdown() -> None:
+    """Drop the peer buffers of every group (call before dist.destroy_process_group)."""
+    _STATE.clear()

@@ -80,6 +80,11 @@ def reduce_output(y: torch.Tensor, mode: str, group: Optional[dist.ProcessGroup]
     """The one collective of the path: all-reduce(sum) after a row-parallel linear (NCCL over
     NVLink on GPU ranks; gloo in the CPU tests).  Column-parallel outputs stay sharded."""
     if mode == ROW and dist.is_initialized() and dist.get_world_size(group) > 1:
+        if y.is_cuda:
+            from . import peer                                   # K7: one-shot all-reduce over peer memory (decode sizes)
+            one = peer.get(group)
+            if one is not None and one.fits(y):
+                return one(y)
         dist.all_reduce(y, op=dist.ReduceOp.SUM, group=group)
     return y
 

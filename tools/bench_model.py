@@ -43,11 +43,22 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        if not os.environ.get("Q100_NO_PEER"):
+            from q100 import peer
+            peer.enable(None, dev)          # K7: decode-size all-reduces over peer memory (falls back to NCCL by itself)
     out = run(a, dev, rank, world)
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
+        import gc, threading
+        threading.Timer(45.0, lambda: os._exit(0)).start()           # a stuck teardown must not keep the job alive
+        from q100 import peer
+        peer.shutdown()
+        gc.collect()
+        torch.cuda.synchronize()
+        dist.barrier()
         dist.destroy_process_group()
+        os._exit(0)
 
 
 def run(a, dev, rank=0, world=1):
