@@ -521,6 +521,38 @@ def run_ours(args):
                     "sample": f"7 linears of the block at M={Ms} (of 2048), fp32, {reps} reps, torch eager on host cores",
                     "fake_quant_up_proj_ms": tq * 1e3}
 
+    # =============== the reference's deployment mode on this GPU: eager torch ops (SURVEY 8d "timing the reference") ====
+    gpu_eager = None
+    if rank == 0 and world == 1:
+        import torch_port as TP
+        with torch.no_grad():
+            wg = (torch.randn(INTER, HIDDEN, device=dev) * 0.02).half()
+
+            def eager_fq():
+                TP.fake_quant(wg, WBITS, GROUP)
+            for _ in range(2):
+                eager_fq()
+            ms_fq = timed(eager_fq, 5)
+            wd = TP.fake_quant(wg, WBITS, GROUP)[0]                      # dequantised fp16 weight, what F.linear reads
+            x2k = torch.randn(PREFILL_M, HIDDEN, device=dev).half()
+            x1 = torch.randn(1, HIDDEN, device=dev).half()
+            wds = [wd, wd.clone(), wd.clone()]
+            k_ = [0]
+
+            def eager_lin(x):
+                torch.nn.functional.linear(x, wds[k_[0] % 3])
+                k_[0] += 1
+            for _ in range(3):
+                eager_lin(x2k); eager_lin(x1)
+            ms_pre = timed(lambda: eager_lin(x2k), 10)
+            ms_dec = timed(lambda: eager_lin(x1), 30)
+        gpu_eager = {"what": "torch restatement of the reference op sequence, eager on this GPU, up_proj 14336x4096 fp16",
+                     "fake_quant_ms": ms_fq, "fake_quant_GBps_algorithmic": INTER * HIDDEN * 4.03125 / (ms_fq * 1e-3) / 1e9,
+                     "prefill_linear_ms": ms_pre, "prefill_linear_tflops": 2.0 * PREFILL_M * INTER * HIDDEN / (ms_pre * 1e-3) / 1e12,
+                     "decode_linear_us": ms_dec * 1e3,
+                     "decode_linear_fp16_weight_GBps": INTER * HIDDEN * 2 / (ms_dec * 1e-3) / 1e9}
+        del wg, wd, wds, x2k, x1
+
     # =============== whole model: random-init LLaMA3-8B W4A16 g128, tensor parallel ===========
     model_res = None
     if not os.environ.get("Q100_BENCH_SKIP_MODEL"):
@@ -542,7 +574,7 @@ def run_ours(args):
                                  "activations/outputs) exceeds the 126 MB L2",
                            "force_skinny": bool(flags)},
                 "roofline": roofline, "decode": decode, "quantize": quant, "llama3_8b": model_res,
-                "cpu_baseline": cpu_base, "e2e": e2e,
+                "cpu_baseline": cpu_base, "gpu_eager_reference_ops": gpu_eager, "e2e": e2e,
                 "gpu_launches": n_launch, "clocks": clocks, "peaks": P}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -589,7 +589,11 @@ k3_skinny(const SkinnyArgs a) {
           if (LOHI) s_b += __shfl_xor_sync(half_mask, s_b, d);
         }
         if (ch == 0)
-          *reinterpret_cast<float4*>(xs_ptr + bl * blk_pitch + m * SK_XPITCH + 256) = make_float4(s_a, s_b, inv, 0.f);
+          // slot (m >> 1) & 3 of the row's 64 bytes of padding: the four lane quarters of a warp read the sums of rows
+          // 2t / 2t + 1, which would otherwise sit 640 bytes apart = in the same 16-byte bank group (4-way conflict,
+          // measured: 10x the bank conflicts of M = 1 at M = 8)
+          *reinterpret_cast<float4*>(xs_ptr + bl * blk_pitch + m * SK_XPITCH + 256 + ((m >> 1) & 3) * 16) =
+              make_float4(s_a, s_b, inv, 0.f);
       }
       if (LOHI) { const uint32_t y = v.y; v.y = v.z; v.z = y; }
       *reinterpret_cast<uint4*>(xs_ptr + bl * blk_pitch + m * SK_XPITCH + (ch >> 2) * 16 + (ch & 3) * 64) = v;
@@ -611,7 +615,8 @@ k3_skinny(const SkinnyArgs a) {
     } else {
       xrow[mb] = xs_u32 + min(mb * 8 + g, mrows - 1) * SK_XPITCH + t * 16;
       // this lane's two output columns need the block sums of tokens m = mb*8 + 2t, 2t+1 (clamped like x)
-      srow[mb] = xs_u32 + min(mb * 8 + 2 * t, mrows - 1) * SK_XPITCH + 256;
+      const int srow_m = min(mb * 8 + 2 * t, mrows - 1);
+      srow[mb] = xs_u32 + srow_m * SK_XPITCH + 256 + ((srow_m >> 1) & 3) * 16;
     }
   }
 
