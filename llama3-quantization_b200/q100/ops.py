@@ -6,6 +6,7 @@ require CUDA tensors and raise otherwise -- there is no CPU path.
 """
 from __future__ import annotations
 
+import functools
 from dataclasses import dataclass
 from typing import Optional
 
@@ -36,6 +37,29 @@ def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
 
 def _stream(t: torch.Tensor) -> int:
     return torch.cuda.current_stream(t.device).cuda_stream
+
+
+class _on:
+    """Device guard that only switches when the tensor is not on the current device (torch.cuda.device() costs
+    several microseconds per call even when it has nothing to do; the eager decode path is host-bound)."""
+    __slots__ = ("ctx",)
+
+    def __init__(self, dev: torch.device):
+        self.ctx = None if dev.index == torch.cuda.current_device() else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *exc):
+        if self.ctx is not None:
+            return self.ctx.__exit__(*exc)
+        return False
+
+
+@functools.lru_cache(maxsize=4096)
+def _gemm_workspace_bytes(M: int, N: int, K: int, n_bits: int, flags: int) -> int:
+    return int(lib.q100_gemm_workspace_bytes(M, N, K, n_bits, flags))
 
 
 TILE_ROWS, TILE_K = 128, 64
@@ -95,7 +119,7 @@ def quantize_groupwise(x: torch.Tensor, group: int, n_bits: int, symmetric: bool
         lwc_low = lwc_low.to(dt).contiguous()
         if lwc_up.numel() != n_groups or lwc_low.numel() != n_groups:
             raise ValueError("LWC multipliers must have one entry per group")
-    with torch.cuda.device(dev):
+    with _on(dev):
         check(lib.q100_quantize_groupwise(
             x.data_ptr(), _dtype_code(x), rows, cols, 0 if group in (0, None) else g, n_bits,
             int(bool(symmetric)), int(bool(disable_zero_point)), _ptr(lwc_up), _ptr(lwc_low),
@@ -127,7 +151,7 @@ def quantize_backward(x: torch.Tensor, grad_out: torch.Tensor, group: int, n_bit
         if need_lwc:
             gup = torch.empty((n_groups, 1), dtype=x.dtype, device=x.device)
             glow = torch.empty((n_groups, 1), dtype=x.dtype, device=x.device)
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         check(lib.q100_quantize_backward(
             x.data_ptr(), grad_out.data_ptr(), _dtype_code(x), rows, cols, int(group), n_bits,
             int(bool(symmetric)), int(bool(disable_zero_point)), _ptr(lwc_up), _ptr(lwc_low),
@@ -144,7 +168,7 @@ def fakequant_rows(x: torch.Tensor, n_bits: int, flags: int = 0) -> QuantResult:
     res = QuantResult(dequant=torch.empty_like(x2),
                       scales=torch.empty((rows, 1), dtype=x.dtype, device=x.device),
                       zeros=torch.empty((rows, 1), dtype=x.dtype, device=x.device))
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         check(lib.q100_fakequant_rows(x2.data_ptr(), _dtype_code(x2), rows, cols, n_bits,
                                       res.dequant.data_ptr(), res.scales.data_ptr(), res.zeros.data_ptr(),
                                       flags, _stream(x2)))
@@ -160,7 +184,7 @@ def dequantize(packed: torch.Tensor, scales: Optional[torch.Tensor], zeros: Opti
     """Packed codes -> dense [rows, cols] tensor (raw integer codes when ``scales`` is None)."""
     _require_cuda(packed, scales, zeros)
     out = torch.empty((rows, cols), dtype=dtype, device=packed.device)
-    with torch.cuda.device(packed.device):
+    with _on(packed.device):
         check(lib.q100_dequantize(packed.data_ptr(), _ptr(scales), _ptr(zeros), _DT[dtype], rows, cols,
                                   0 if group in (0, None) else group, n_bits, int(bool(disable_zero_point)),
                                   out.data_ptr(), _stream(packed)))
@@ -240,9 +264,9 @@ def gemm_wna16(x: torch.Tensor, w: PackedWeight, bias: Optional[torch.Tensor] = 
         return y.view(*shp[:-1], w.N)
     if bias is not None:
         bias = bias.to(x.dtype).contiguous()
-    need = lib.q100_gemm_workspace_bytes(M, w.N, w.K, w.n_bits, flags)
+    need = _gemm_workspace_bytes(M, w.N, w.K, w.n_bits, flags)
     ws = _workspace(x.device, need)
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         check(lib.q100_gemm_wna16(x2.data_ptr(), w.packed.data_ptr(), w.meta.data_ptr(), _ptr(bias),
                                   y.data_ptr(), M, w.N, w.K, w.group, w.n_bits, int(w.disable_zero_point),
                                   _DT[x.dtype], ws.data_ptr(), ws.numel(), flags, _stream(x2)))
@@ -260,7 +284,7 @@ def add_rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float, residual: Opt
     if residual is not None:
         residual = residual.contiguous()
         h = torch.empty_like(x)
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         check(lib.q100_add_rmsnorm(x.data_ptr(), _ptr(residual), weight.data_ptr(), float(eps),
                                    h.data_ptr() if residual is not None else None, norm.data_ptr(), rows, cols,
                                    _DT[x.dtype], _stream(x)))
@@ -280,7 +304,7 @@ def rope_kv_decode(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, posi
     if cos.dtype != qkv.dtype or cos.shape[-1] != hd or not cos.is_contiguous():
         raise ValueError("q100.rope_kv_decode: cos/sin cache must be contiguous [pos, head_dim] in the model dtype")
     q = torch.empty((bsz, heads, 1, hd), dtype=qkv.dtype, device=qkv.device)
-    with torch.cuda.device(qkv.device):
+    with _on(qkv.device):
         check(lib.q100_rope_kv_decode(qkv.data_ptr(), cos.data_ptr(), sin.data_ptr(), position.data_ptr(),
                                       q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), bsz, heads, kv_heads,
                                       hd, max_len, _DT[qkv.dtype], _stream(qkv)))
@@ -294,7 +318,7 @@ def silu_mul(gate_up: torch.Tensor) -> torch.Tensor:
     inter = gate_up.shape[-1] // 2
     rows = gate_up.numel() // (2 * inter)
     out = torch.empty((*gate_up.shape[:-1], inter), dtype=gate_up.dtype, device=gate_up.device)
-    with torch.cuda.device(gate_up.device):
+    with _on(gate_up.device):
         check(lib.q100_silu_mul(gate_up.data_ptr(), out.data_ptr(), rows, inter, _DT[gate_up.dtype],
                                 _stream(gate_up)))
     return out
@@ -303,7 +327,7 @@ def silu_mul(gate_up: torch.Tensor) -> torch.Tensor:
 def selftest_div(dtype: torch.dtype, device="cuda") -> int:
     """Exhaustive check of the fast 16-bit division; returns the mismatch count."""
     out = torch.zeros(1, dtype=torch.int64, device=device)
-    with torch.cuda.device(out.device):
+    with _on(out.device):
         check(lib.q100_selftest_div(_DT[dtype], out.data_ptr(), _stream(out)))
     return int(out.item())
 
@@ -314,7 +338,7 @@ def debug_gemm_dense_tc(x: torch.Tensor, w: torch.Tensor) -> torch.Tensor:
     x = x.contiguous()
     w = w.contiguous()
     y = torch.empty((x.shape[0], w.shape[0]), dtype=x.dtype, device=x.device)
-    with torch.cuda.device(x.device):
+    with _on(x.device):
         check(lib.q100_debug_gemm_dense_tc(x.data_ptr(), w.data_ptr(), y.data_ptr(), x.shape[0], w.shape[0],
                                            x.shape[1], _DT[x.dtype], _stream(x)))
     return y

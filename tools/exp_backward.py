@@ -20,6 +20,9 @@ for dt in (torch.float32, torch.float16):
         for _ in range(n): fn()
         e.record(); e.synchronize()
         return s.elapsed_time(e) / n
+    ms_f = t(lambda: q100.quantize_groupwise(x, G, 4, False, False, su, sl))
+    fb = N * K * 2 * x.element_size() + ng * 4 * x.element_size()
+    print(f"{str(dt)[6:]:8s} K1 forward (LWC) {ms_f*1e3:8.1f} us  {fb/ms_f/1e6:7.1f} GB/s ({fb/ms_f/1e6/6550.7:.2%} of HBM)")
     ms_k = t(lambda: ops.quantize_backward(x, go, G, 4, False, False, su, sl, True, True))
     ms_t = t(lambda: fake_quant_backward(x.view(-1, G), go.view(-1, G), r.scales, r.zeros, su, sl, 4, False, 0, 15, True, True), 3)
     b = x.element_size()
