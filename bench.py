@@ -524,16 +524,26 @@ def run_ours(args):
     # =============== the reference's deployment mode on this GPU: eager torch ops (SURVEY 8d "timing the reference") ====
     gpu_eager = None
     if rank == 0 and world == 1:
-        import torch_port as TP
+        def ref_ops_fake_quant(w):
+            # the reference's op sequence written out with torch ops (quant/quantizer.py:132-159 then :94-115,
+            # asymmetric, group-wise): what its UniformAffineQuantizer launches, one kernel per line
+            xg = w.reshape(-1, GROUP)
+            xmin, xmax = xg.amin(-1, keepdim=True), xg.amax(-1, keepdim=True)
+            scale = ((xmax - xmin) / (2 ** WBITS - 1)).clamp(min=1e-5, max=1e4)
+            zp = (-xmin / scale).clamp(min=-1e4, max=1e4).round()
+            v = xg / scale
+            x_int = ((v.round() - v).detach() + v).add(zp).clamp(0, 2 ** WBITS - 1)
+            return x_int.sub(zp).mul(scale).reshape(w.shape)
+
         with torch.no_grad():
             wg = (torch.randn(INTER, HIDDEN, device=dev) * 0.02).half()
 
             def eager_fq():
-                TP.fake_quant(wg, WBITS, GROUP)
+                ref_ops_fake_quant(wg)
             for _ in range(2):
                 eager_fq()
             ms_fq = timed(eager_fq, 5)
-            wd = TP.fake_quant(wg, WBITS, GROUP)[0]                      # dequantised fp16 weight, what F.linear reads
+            wd = ref_ops_fake_quant(wg)                                  # dequantised fp16 weight, what F.linear reads
             x2k = torch.randn(PREFILL_M, HIDDEN, device=dev).half()
             x1 = torch.randn(1, HIDDEN, device=dev).half()
             wds = [wd, wd.clone(), wd.clone()]
@@ -546,7 +556,7 @@ def run_ours(args):
                 eager_lin(x2k); eager_lin(x1)
             ms_pre = timed(lambda: eager_lin(x2k), 10)
             ms_dec = timed(lambda: eager_lin(x1), 30)
-        gpu_eager = {"what": "torch restatement of the reference op sequence, eager on this GPU, up_proj 14336x4096 fp16",
+        gpu_eager = {"what": "the reference's op sequence as eager torch ops on this GPU, up_proj 14336x4096 fp16",
                      "fake_quant_ms": ms_fq, "fake_quant_GBps_algorithmic": INTER * HIDDEN * 4.03125 / (ms_fq * 1e-3) / 1e9,
                      "prefill_linear_ms": ms_pre, "prefill_linear_tflops": 2.0 * PREFILL_M * INTER * HIDDEN / (ms_pre * 1e-3) / 1e12,
                      "decode_linear_us": ms_dec * 1e3,
