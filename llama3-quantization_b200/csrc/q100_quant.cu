@@ -643,15 +643,33 @@ __global__ void __launch_bounds__(1024) k2_rows(const QuantArgs a) {
   for (int64_t row = blockIdx.x; row < a.rows; row += gridDim.x) {
     uint4 v[VMAX];
     float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);   // +inf / -inf
+    if constexpr (DT<T>::kCode != Q100_F32) {
+      // 16-bit: the thread's vectors are reduced in packed arithmetic (HMNMX2.NAN), one conversion at the end
+      using T2 = typename Packed16<T>::T2;
+      T2 lo = Packed16<T>::bcast(mn), hi = Packed16<T>::bcast(mx);
 #pragma unroll
-    for (int k = 0; k < VMAX; ++k) {
-      const int idx = k * nt + tid;
-      if (k < vper && idx < nvec) {
-        v[k] = ldg_stream(xin + row * nvec + idx);
-        float m0, m1;
-        vec_minmax<T>(v[k], m0, m1);
-        mn = min_nan(mn, m0);
-        mx = max_nan(mx, m1);
+      for (int k = 0; k < VMAX; ++k) {
+        const int idx = k * nt + tid;
+        if (k < vper && idx < nvec) {
+          v[k] = ldg_stream(xin + row * nvec + idx);
+          const T2* h = reinterpret_cast<const T2*>(&v[k]);
+          lo = __hmin2_nan(lo, __hmin2_nan(__hmin2_nan(h[0], h[1]), __hmin2_nan(h[2], h[3])));
+          hi = __hmax2_nan(hi, __hmax2_nan(__hmax2_nan(h[0], h[1]), __hmax2_nan(h[2], h[3])));
+        }
+      }
+      mn = min_nan(__low2float(lo), __high2float(lo));
+      mx = max_nan(__low2float(hi), __high2float(hi));
+    } else {
+#pragma unroll
+      for (int k = 0; k < VMAX; ++k) {
+        const int idx = k * nt + tid;
+        if (k < vper && idx < nvec) {
+          v[k] = ldg_stream(xin + row * nvec + idx);
+          float m0, m1;
+          vec_minmax<T>(v[k], m0, m1);
+          mn = min_nan(mn, m0);
+          mx = max_nan(mx, m1);
+        }
       }
     }
 #pragma unroll
