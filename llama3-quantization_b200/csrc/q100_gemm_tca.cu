@@ -129,6 +129,12 @@ __device__ __forceinline__ uint32_t ta_pair_magic(const uint32_t* w, int c, uint
     const uint32_t x = j == 0 ? w[i] : j == 1 ? ta_shr<2>(w[i]) : j == 2 ? ta_shr<4>(w[i]) : j == 3 ? ta_shr<6>(w[i])
                      : j == 4 ? ta_shr<8>(w[i]) : j == 5 ? ta_shr<10>(w[i]) : j == 6 ? ta_shr<12>(w[i]) : ta_shr<14>(w[i]);
     return ta_and_or<0x00030003u>(x, magic);
+  } else if (NBITS == 3) {
+    // w[0..3]: the row's 2-bit plane (8 pairs per word), w[4..5]: its 1-bit plane (16 pairs per word)
+    const int i = c >> 3, j = c & 7;
+    const uint32_t lo = (w[i] >> (2 * j)) & 0x00030003u;
+    const uint32_t hi = ((w[4 + (c >> 4)] >> (c & 15)) & 0x00010001u) << 2;
+    return lo | hi | magic;
   } else {   // 8 bits: pair = (w >> 8j) & 0x00ff00ff
     const int i = c >> 1, j = c & 1;
     return __byte_perm(w[i], magic, j ? 0x7371 : 0x7270);
@@ -290,7 +296,9 @@ k3_tca(const __grid_constant__ CUtensorMap tm_x, const TcaArgs a) {
     const T2 magic2 = DQ::bcast(DQ::kMagicF);
     const uint32_t magic = ta_reg(DQ::kMagic);
     const bool has_zp = a.has_zp != 0;
-    const uint32_t code_off = ta_reg(base_u32 + SM::kOffP + row * (NW * 4));
+    // W3: a tile is its 2-bit plane (128 rows x 16 bytes) followed by its 1-bit plane (128 rows x 8 bytes)
+    const uint32_t code_off = ta_reg(base_u32 + SM::kOffP + row * (NBITS == 3 ? 16 : NW * 4));
+    const uint32_t code_off_hi = ta_reg(base_u32 + SM::kOffP + 128 * 16 + row * 8);
     const uint32_t meta_off = ta_reg(base_u32 + SM::kOffP + SM::kP + row * 4);
     uint32_t it = 0;
     for (int ct = ct0; ct < n_ct; ct += ct_step) {
@@ -301,12 +309,20 @@ k3_tca(const __grid_constant__ CUtensorMap tm_x, const TcaArgs a) {
         ta_wait(full_p + 8 * sp, (it / TA_SP) & 1);
         TA_T(d1);
         uint32_t w[NW];
-#pragma unroll
-        for (int i = 0; i < NW / 4; ++i) {
+        if constexpr (NBITS == 3) {
           uint4 v;
           asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
-                       : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(code_off + sp * SM::kPStage + i * 16));
-          w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+                       : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(code_off + sp * SM::kPStage));
+          w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w;
+          asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(w[4]), "=r"(w[5]) : "r"(code_off_hi + sp * SM::kPStage));
+        } else {
+#pragma unroll
+          for (int i = 0; i < NW / 4; ++i) {
+            uint4 v;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(code_off + sp * SM::kPStage + i * 16));
+            w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+          }
         }
         uint32_t m;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(m) : "r"(meta_off + sp * SM::kPStage));
@@ -442,7 +458,7 @@ int tca_timing(long long* out, int n) {
 
 bool gemm_tca_supported(int64_t M, int64_t N, int64_t K, int group, int n_bits) {
   const int64_t g = group == 0 ? K : group;
-  return (n_bits == 4 || n_bits == 2 || n_bits == 8) && M >= 1 && N % 8 == 0 && K % TA_BK == 0 &&
+  return (n_bits == 4 || n_bits == 2 || n_bits == 3 || n_bits == 8) && M >= 1 && N % 8 == 0 && K % TA_BK == 0 &&
          g % TA_BK == 0 && K % g == 0;
 }
 
@@ -507,6 +523,7 @@ template <typename T>
 static int gemm_tca_t(const void* x, const TcaArgs& a, int n_bits, int cluster, cudaStream_t st) {
   switch (n_bits) {
     case 2: return gemm_tca_nt<T, 2>(x, a, cluster, st);
+    case 3: return gemm_tca_nt<T, 3>(x, a, cluster, st);
     case 8: return gemm_tca_nt<T, 8>(x, a, cluster, st);
     default: return gemm_tca_nt<T, 4>(x, a, cluster, st);
   }

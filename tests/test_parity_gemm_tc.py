@@ -59,9 +59,11 @@ def test_tc_matches_skinny_bits_of_weight():
 
 
 @pytest.mark.parametrize("dtype", ["bf16", "f16"])
-@pytest.mark.parametrize("n_bits", [2, 8])
+@pytest.mark.parametrize("n_bits", [2, 3, 8])
 @pytest.mark.parametrize("kern", sorted(KERN))
 def test_tc_other_bits(dtype, n_bits, kern):
+    if n_bits == 3 and kern != "tmem_a":
+        pytest.skip("W3 (2-bit + 1-bit planes) runs on the TMEM-A kernel only")
     for (M, N, K, group) in ((128, 128, 128, 128), (300, 384, 1024, 128), (512, 256, 512, 0)):
         x, w, pw, r = _make(N, K, M, dtype, n_bits, group or None, M + N + K + n_bits)
         y = q100.gemm_wna16(x, pw, None, flags=KERN[kern])
@@ -98,3 +100,15 @@ def test_tc_weird_zero_points_and_nozp():
             pw, r = q100.pack_weight(wd, 4, 128, True, True, want_dequant=True)
             y = q100.gemm_wna16(x, pw, None, flags=KERN[kern])
             _check(y, x, r.dequant, None, "f16" if dt == torch.float16 else "bf16")
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f16"])
+def test_tca_w3_bits_of_weight(dtype):
+    """W3 on the prefill kernel: with x = identity the output is the fake-quantised weight itself, bit for bit."""
+    N, K = 256, 256
+    gen = torch.Generator().manual_seed(11)
+    w = (torch.randn(N, K, generator=gen) * 0.02).to(TDT[dtype]).cuda()
+    pw, r = q100.pack_weight(w, 3, 128, want_dequant=True)
+    x = torch.eye(K, dtype=TDT[dtype], device="cuda")
+    y = q100.gemm_wna16(x, pw, None)
+    assert torch.equal(y.t().contiguous().view(torch.int16), r.dequant.view(torch.int16))
