@@ -66,7 +66,7 @@ enum q100_status {
                                       default: 8 < M <= 16                                           */
 #define Q100_GEMM_FORCE_TC_SMEM 0x40 /* prefill: the first tcgen05 kernel (dequantised weights staged in
                                       shared memory as the B operand) instead of the TMEM-A kernel      */
-#define Q100_GEMM_NO_IMMA      0x80 /* decode shapes, W4, M <= 8: the fp16 magic-form mma.sync path instead of the
+#define Q100_GEMM_NO_IMMA      0x80 /* decode shapes, W4 / W2, M <= 2: the fp16 magic-form mma.sync path instead of the
                                       integer (u8 x s8 limbs of x) mma.sync path                      */
 #define Q100_GEMM_PDL          0x8 /* launch with programmatic stream serialization: the kernel starts
                                       streaming its (static) weights while the previous kernel of the

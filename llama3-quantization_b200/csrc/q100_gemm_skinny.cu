@@ -537,10 +537,25 @@ k3_skinny(const SkinnyArgs a) {
                  ((static_cast<uint32_t>(b2) & 0xffu) << 16) | (static_cast<uint32_t>(b3) << 24);
         };
         uint8_t* colp = xs_ptr + bl * blk_pitch + (3 * m) * SK_ICOL;
-        const int boff = (ch >> 2) * 32 + (ch & 3) * 8;
-        *reinterpret_cast<uint2*>(colp + boff) = make_uint2(pk(l0[0], l0[4], l0[1], l0[5]), pk(l0[2], l0[6], l0[3], l0[7]));
-        *reinterpret_cast<uint2*>(colp + SK_ICOL + boff) = make_uint2(pk(l1[0], l1[4], l1[1], l1[5]), pk(l1[2], l1[6], l1[3], l1[7]));
-        *reinterpret_cast<uint2*>(colp + 2 * SK_ICOL + boff) = make_uint2(pk(l2[0], l2[4], l2[1], l2[5]), pk(l2[2], l2[6], l2[3], l2[7]));
+        if constexpr (NBITS == 4) {
+          const int boff = (ch >> 2) * 32 + (ch & 3) * 8;
+          *reinterpret_cast<uint2*>(colp + boff) = make_uint2(pk(l0[0], l0[4], l0[1], l0[5]), pk(l0[2], l0[6], l0[3], l0[7]));
+          *reinterpret_cast<uint2*>(colp + SK_ICOL + boff) = make_uint2(pk(l1[0], l1[4], l1[1], l1[5]), pk(l1[2], l1[6], l1[3], l1[7]));
+          *reinterpret_cast<uint2*>(colp + 2 * SK_ICOL + boff) = make_uint2(pk(l2[0], l2[4], l2[1], l2[5]), pk(l2[2], l2[6], l2[3], l2[7]));
+        } else {
+          // W2: a packed word holds 16 codes; (w >> 2 jr) & 0x03030303 yields elements (2jr, 2jr+8, 2jr+1, 2jr+9) of
+          // the word, registers jr = 0..3; mma m = 2 * word + (jr >> 1) takes register jr even as a0 and jr odd as a2.
+          // Element i of chunk ch is element e = 8 (ch & 1) + i of word (ch & 3) >> 1 of lane quarter t = ch >> 2.
+          const int t4 = (ch >> 2) * 32, wi = (ch & 3) >> 1;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int e = 8 * (ch & 1) + i, e7 = e & 7, jr = e7 >> 1;
+            const int off = t4 + (wi * 2 + (jr >> 1)) * 8 + (jr & 1) * 4 + (e >> 3) + (e7 & 1) * 2;
+            colp[off] = static_cast<uint8_t>(l0[i]);
+            colp[SK_ICOL + off] = static_cast<uint8_t>(l1[i]);
+            colp[2 * SK_ICOL + off] = static_cast<uint8_t>(l2[i]);
+          }
+        }
         if (ch == 0) {
           // column coefficient 256^l / scale; inf / NaN anywhere in the block poisons the token's result
           const uint32_t cexp = static_cast<uint32_t>(254 - fe);
@@ -639,12 +654,21 @@ k3_skinny(const SkinnyArgs a) {
       for (int mb = 0; mb < MB; ++mb) { xb[mb][0] = lds128(xrow[mb] + xoff); xb[mb][1] = lds128(xrow[mb] + xoff + 16); }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const uint32_t w0 = b.c0.word(j), w1 = b.c1.word(j);
         uint32_t af[4];
-        af[0] = w0 & 0x0f0f0f0fu;                       // (e0, e4, e1, e5) of row r0
-        af[1] = w1 & 0x0f0f0f0fu;                       //                  of row r1
-        af[2] = shr4_fma(w0) & 0x0f0f0f0fu;             // (e2, e6, e3, e7)
-        af[3] = shr4_fma(w1) & 0x0f0f0f0fu;
+        if constexpr (NBITS == 4) {
+          const uint32_t w0 = b.c0.word(j), w1 = b.c1.word(j);
+          af[0] = w0 & 0x0f0f0f0fu;                       // (e0, e4, e1, e5) of row r0
+          af[1] = w1 & 0x0f0f0f0fu;                       //                  of row r1
+          af[2] = shr4_fma(w0) & 0x0f0f0f0fu;             // (e2, e6, e3, e7)
+          af[3] = shr4_fma(w1) & 0x0f0f0f0fu;
+        } else {                                          // W2: word j >> 1, registers jr = 2 (j & 1), + 1
+          const uint32_t w0 = (j >> 1) ? b.c0.w.y : b.c0.w.x, w1 = (j >> 1) ? b.c1.w.y : b.c1.w.x;
+          constexpr uint32_t m2 = 0x03030303u;
+          af[0] = ((j & 1) ? (w0 >> 4) : w0) & m2;
+          af[1] = ((j & 1) ? (w1 >> 4) : w1) & m2;
+          af[2] = ((j & 1) ? (w0 >> 6) : (w0 >> 2)) & m2;
+          af[3] = ((j & 1) ? (w1 >> 6) : (w1 >> 2)) & m2;
+        }
 #pragma unroll
         for (int mb = 0; mb < MB; ++mb) {
           const uint4& q4 = xb[mb][j >> 1];
@@ -1072,11 +1096,11 @@ static int launch_skinny_post(const SkinnyArgs& a, cudaStream_t st) {
 
 template <typename T, int NBITS>
 static int launch_skinny_mb(const SkinnyArgs& a, cudaStream_t st) {
-  if constexpr (NBITS == 4) {
+  if constexpr (NBITS == 4 || NBITS == 2) {
     // integer tensor-core path.  Measured (profiles/r01k): with one column group (M <= 2) it beats the fp16 form
     // (gate|up 16.6 vs 19.3 us); with two groups (M = 4) the extra MMAs, int->float conversions and limb staging
     // lose (25.3 vs 21.6 us), so larger M stay on the fp16 form.
-    if (a.post == 2) return launch_skinny<T, 4, 1, 2>(a, st);
+    if (a.post == 2) return launch_skinny<T, NBITS, 1, 2>(a, st);
   }
   if (a.M <= 8) return launch_skinny_post<T, NBITS, 1>(a, st);
   if (a.M <= 16) return launch_skinny_post<T, NBITS, 2>(a, st);
@@ -1136,7 +1160,7 @@ int gemm_skinny(const void* x, const void* packed, const void* meta, const void*
   // exact_weights: 0 = default, 1 = bit-exact 16-bit weights (MODE 0), 2 = fp16 magic-form path even where
   // the integer path applies
   a.post = (g % SK_KB == 0 && exact_weights != 1) ? 1 : 0;
-  if (a.post && n_bits == 4 && M <= 2 && exact_weights == 0) a.post = 2;
+  if (a.post && (n_bits == 4 || n_bits == 2) && M <= 2 && exact_weights == 0) a.post = 2;
   a.m_rows = static_cast<int>(M);
   a.nsub = g >= SK_KB ? 1 : SK_KB / g;
   a.pdl = pdl;

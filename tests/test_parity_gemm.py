@@ -65,7 +65,7 @@ def _make(N, K, M, dtype, n_bits, group, seed, nozp=False, sym=False):
 def test_skinny_vs_oracle(dtype, n_bits, M, path):
     if path == "stream_tc" and (n_bits in (3, 8) or M > 16):
         pytest.skip("same kernel as mma_sync for this case")
-    if path == "mma_sync_f16" and (n_bits != 4 or M > 2):
+    if path == "mma_sync_f16" and (n_bits not in (2, 4) or M > 2):
         pytest.skip("same kernel as mma_sync for this case")
     N, K = 384, 1024
     x, w, pw, r = _make(N, K, M, dtype, n_bits, 128, 1000 + M + n_bits)
