@@ -68,6 +68,10 @@ enum q100_status {
                                       shared memory as the B operand) instead of the TMEM-A kernel      */
 #define Q100_GEMM_NO_IMMA      0x80 /* decode shapes, W4 / W2, M <= 2: the fp16 magic-form mma.sync path instead of the
                                       integer (u8 x s8 limbs of x) mma.sync path                      */
+#define Q100_GEMM_X_GATE_UP    0x100 /* decode shapes (M <= 32): x is [M, 2K] = gate | up of the MLP and the kernel
+                                      applies act_fn(gate) * up (SiLU, the arithmetic of q100_silu_mul, i.e. of
+                                      models/int_llama_layer.py:45) while it stages x: down_proj without the
+                                      separate element-wise launch.  Q100_EUNSUPPORTED for M > 32.      */
 #define Q100_GEMM_PDL          0x8 /* launch with programmatic stream serialization: the kernel starts
                                       streaming its (static) weights while the previous kernel of the
                                       stream drains, and waits (griddepcontrol.wait) before it touches

@@ -13,7 +13,7 @@ namespace q100 {
 
 int gemm_skinny(const void* x, const void* packed, const void* meta, const void* bias, void* y,
                 int64_t M, int64_t N, int64_t K, int group, int n_bits, int disable_zp, int dtype,
-                void* workspace, size_t workspace_bytes, int exact_weights, int pdl, cudaStream_t st);
+                void* workspace, size_t workspace_bytes, int exact_weights, int pdl, int x_gate_up, cudaStream_t st);
 size_t skinny_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int gemm_stream(const void* x, const void* packed, const void* meta, const void* bias, void* y,
                 int64_t M, int64_t N, int64_t K, int group, int n_bits, int disable_zp, int dtype,
@@ -98,11 +98,15 @@ extern "C" int q100_gemm_wna16(const void* x, const void* packed, const void* me
   if (rc != Q100_OK) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool skinny_ok = (K % 128 == 0) && (N % 8 == 0);
+  const bool gate_up = (flags & Q100_GEMM_X_GATE_UP) != 0;
+  if (gate_up)
+    Q100_REQUIRE(M <= 32 && skinny_ok && !(flags & Q100_GEMM_FORCE_TC), Q100_EUNSUPPORTED,
+                 "Q100_GEMM_X_GATE_UP is a decode-kernel option (M <= 32, K %% 128 == 0); got M=%lld", (long long)M);
   // prefill: K3b' (weights as the TMEM A operand); K3b (dequantised weights through shared memory) on request
   const bool tca_ok = gemm_tca_supported(M, N, K, group, n_bits) && !(flags & Q100_GEMM_FORCE_TC_SMEM);
   const bool tc_ok = tca_ok || gemm_tc_supported(M, N, K, group, n_bits);
-  const bool want_tc = (flags & Q100_GEMM_FORCE_TC) ||
-                       (!(flags & Q100_GEMM_FORCE_SKINNY) && tc_ok && (M > 32 || !skinny_ok));
+  const bool want_tc = !gate_up && ((flags & Q100_GEMM_FORCE_TC) ||
+                       (!(flags & Q100_GEMM_FORCE_SKINNY) && tc_ok && (M > 32 || !skinny_ok)));
   if (want_tc) {
     Q100_REQUIRE(tc_ok, Q100_EUNSUPPORTED, "tcgen05 path does not support this shape/bit-width");
     if (tca_ok) {
@@ -119,7 +123,7 @@ extern "C" int q100_gemm_wna16(const void* x, const void* packed, const void* me
   // (measured, profiles/r01: it is M-independent -- 107 us at M = 16 vs 161 us for the mma.sync kernel on
   // 57344 x 8192 -- but its small-N MMAs and its per-block latency chain lose to mma.sync up to M = 8)
   const bool want_stream = (flags & Q100_GEMM_FORCE_STREAM_TC) || M > 8;
-  if (want_stream && !(flags & (Q100_GEMM_FORCE_MMA_SYNC | Q100_GEMM_EXACT_WEIGHTS)) &&
+  if (want_stream && !gate_up && !(flags & (Q100_GEMM_FORCE_MMA_SYNC | Q100_GEMM_EXACT_WEIGHTS)) &&
       gemm_stream_supported(M, N, K, group, n_bits))
     return gemm_stream(x, packed, meta, bias, y, M, N, K, group, n_bits, disable_zp, dtype, workspace,
                        workspace_bytes, (flags & Q100_GEMM_PDL) ? 1 : 0, st);
@@ -127,11 +131,11 @@ extern "C" int q100_gemm_wna16(const void* x, const void* packed, const void* me
   const size_t esz = 2;
   for (int64_t m0 = 0; m0 < M; m0 += 32) {
     const int64_t mc = (M - m0) < 32 ? (M - m0) : 32;
-    rc = gemm_skinny(reinterpret_cast<const uint8_t*>(x) + m0 * K * esz, packed, meta, bias,
+    rc = gemm_skinny(reinterpret_cast<const uint8_t*>(x) + m0 * K * esz * (gate_up ? 2 : 1), packed, meta, bias,
                      reinterpret_cast<uint8_t*>(y) + m0 * N * esz, mc, N, K, group, n_bits, disable_zp,
                      dtype, workspace, workspace_bytes,
                      (flags & Q100_GEMM_EXACT_WEIGHTS) ? 1 : (flags & Q100_GEMM_NO_IMMA) ? 2 : 0,
-                     (flags & Q100_GEMM_PDL) ? 1 : 0, st);
+                     (flags & Q100_GEMM_PDL) ? 1 : 0, gate_up ? 1 : 0, st);
     if (rc != Q100_OK) return rc;
   }
   return Q100_OK;

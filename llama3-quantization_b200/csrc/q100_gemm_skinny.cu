@@ -78,6 +78,7 @@ struct SkinnyArgs {
   int nsub;               // (scale, zero) rows per block: 128 / group for group < 128, else 1
   int pdl;                // launch with programmatic stream serialization
   int seq;                // launch sequence number (timing builds)
+  int x_gate_up;          // x is [M, 2K] = gate | up: stage act_fn(gate) * up (K6's arithmetic)
 };
 
 // One [128 rows x 64 k] tile of codes; a block = two tiles.  In shared memory the second tile is placed
@@ -285,6 +286,22 @@ __device__ __forceinline__ void imma_16832(int (&d)[4], const uint32_t (&a)[4], 
                : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// act_fn(gate) * up for eight elements: F.silu in fp32 stored as T, then the product rounded to T -- the arithmetic
+// of k6_silu_mul (q100_block.cu), i.e. of models/int_llama_layer.py:45 on 16-bit tensors
+template <typename T>
+__device__ __noinline__ uint4 silu_mul8(const uint4& g, const uint4& u) {   // out of line: keeps its temporaries out of the kernel's 72-register budget
+  using D = DT<T>;
+  const uint32_t gw[4] = {g.x, g.y, g.z, g.w}, uw[4] = {u.x, u.y, u.z, u.w};
+  uint32_t ow[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 a = D::to_f2(gw[j]), b = D::to_f2(uw[j]);
+    const float sx = D::rd(__fdiv_rn(a.x, __fadd_rn(1.0f, expf(-a.x))));
+    const float sy = D::rd(__fdiv_rn(a.y, __fadd_rn(1.0f, expf(-a.y))));
+    ow[j] = D::pack2(__fmul_rn(sx, b.x), __fmul_rn(sy, b.y));
+  }
+  return make_uint4(ow[0], ow[1], ow[2], ow[3]);
+}
 // mbarrier wait without bookkeeping instructions in the retry path (try_wait suspends in hardware)
 __device__ __forceinline__ void mbar_arrive_u32(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
@@ -488,7 +505,12 @@ k3_skinny(const SkinnyArgs a) {
           const int bl = c / per_blk;
           const int rem = c - bl * per_blk;
           const int kblk = (kblk0 + bl) % kblocks;
-          vq[u] = *reinterpret_cast<const uint4*>(xg + static_cast<int64_t>(rem >> 4) * a.K + kblk * SK_KB + (rem & 15) * 8);
+          if (a.x_gate_up) {
+            const T* gp = xg + static_cast<int64_t>(rem >> 4) * (2 * a.K) + kblk * SK_KB + (rem & 15) * 8;
+            vq[u] = silu_mul8<T>(*reinterpret_cast<const uint4*>(gp), *reinterpret_cast<const uint4*>(gp + a.K));
+          } else {
+            vq[u] = *reinterpret_cast<const uint4*>(xg + static_cast<int64_t>(rem >> 4) * a.K + kblk * SK_KB + (rem & 15) * 8);
+          }
         }
       }
 #pragma unroll
@@ -1133,7 +1155,7 @@ size_t skinny_workspace_bytes(int64_t M, int64_t N, int64_t K) {
 
 int gemm_skinny(const void* x, const void* packed, const void* meta, const void* bias, void* y,
                 int64_t M, int64_t N, int64_t K, int group, int n_bits, int disable_zp, int dtype,
-                void* workspace, size_t workspace_bytes, int exact_weights, int pdl, cudaStream_t st) {
+                void* workspace, size_t workspace_bytes, int exact_weights, int pdl, int x_gate_up, cudaStream_t st) {
   Q100_REQUIRE(M >= 1 && M <= 32, Q100_EINVAL, "skinny GEMM handles 1 <= M <= 32 (got %lld)", (long long)M);
   Q100_REQUIRE(K % SK_KB == 0, Q100_EUNSUPPORTED, "K=%lld must be a multiple of 128", (long long)K);
   Q100_REQUIRE(N % 8 == 0, Q100_EUNSUPPORTED, "N=%lld must be a multiple of 8", (long long)N);
@@ -1164,6 +1186,7 @@ int gemm_skinny(const void* x, const void* packed, const void* meta, const void*
   a.m_rows = static_cast<int>(M);
   a.nsub = g >= SK_KB ? 1 : SK_KB / g;
   a.pdl = pdl;
+  a.x_gate_up = x_gate_up;
   static int launch_seq = 0;
   a.seq = launch_seq++;
   if (dtype == Q100_F16) return launch_skinny_bits<__half>(n_bits, a, st);

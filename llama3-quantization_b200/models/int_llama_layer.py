@@ -432,7 +432,7 @@ class QuantLlamaDecoderLayer(nn.Module):
         gu = mlp._gate_up((mlp.gate_proj, mlp.up_proj), n2, split=False)
         if gu is None:
             return None
-        d = mlp.down_proj(_ops.silu_mul(gu))
+        d = mlp.down_proj.forward_gate_up(gu)              # SiLU * up inside the down_proj GEMM's x staging
         if getattr(mlp, "tp_world", 1) > 1:
             d = _tp.reduce_output(d, _tp.ROW, mlp.tp_group)
         return d, h1

@@ -26,6 +26,7 @@ GEMM_FORCE_MMA_SYNC = 0x10
 GEMM_FORCE_STREAM_TC = 0x20
 GEMM_FORCE_TC_SMEM = 0x40
 GEMM_NO_IMMA = 0x80
+GEMM_X_GATE_UP = 0x100
 
 _vp, _i, _i64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
 

@@ -254,11 +254,12 @@ def gemm_wna16(x: torch.Tensor, w: PackedWeight, bias: Optional[torch.Tensor] = 
     if x.dtype != w.dtype:
         raise TypeError(f"q100.gemm_wna16: x is {x.dtype} but the packed weight was built for {w.dtype}")
     shp = x.shape
-    if shp[-1] != w.K:
-        raise ValueError(f"q100.gemm_wna16: x has K={shp[-1]}, weight has K={w.K}")
-    x2 = x.contiguous().view(-1, w.K)
-    M = x2.shape[0]
     flags |= _DEFAULT_GEMM_FLAGS
+    kx = 2 * w.K if flags & _lib.GEMM_X_GATE_UP else w.K      # gate | up in, act_fn(gate) * up staged by the kernel
+    if shp[-1] != kx:
+        raise ValueError(f"q100.gemm_wna16: x has K={shp[-1]}, expected {kx}")
+    x2 = x.contiguous().view(-1, kx)
+    M = x2.shape[0]
     y = torch.empty((M, w.N), dtype=x.dtype, device=x.device)
     if M == 0:
         return y.view(*shp[:-1], w.N)

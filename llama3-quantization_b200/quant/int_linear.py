@@ -20,6 +20,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from q100 import ops as _ops
+from q100._lib import GEMM_X_GATE_UP as _GEMM_X_GATE_UP
 from quant.quantizer import UniformAffineQuantizer
 
 
@@ -131,6 +132,18 @@ class QuantLinear(nn.Module):
         self.weight_quantizer._packed_of = (self.weight.data_ptr(), self.weight._version,
                                             tuple(self.weight.shape), self.weight.dtype)
         return True
+
+    def forward_gate_up(self, gate_up: torch.Tensor):
+        """``self(act_fn(gate) * up)`` for ``gate_up = gate | up`` (SiLU): at decode shapes the packed GEMM applies the
+        element-wise step while it stages x (Q100_GEMM_X_GATE_UP), otherwise K6 + the normal forward."""
+        rows = gate_up.numel() // gate_up.shape[-1]
+        if (rows <= 8 and not self.use_temporary_parameter and not self.use_weight_quant
+                and not (self.use_act_quant and not self.disable_input_quant) and not torch.is_grad_enabled()):
+            packed = self.weight_quantizer.packed_for(self.weight)
+            if packed is not None and gate_up.dtype == packed.dtype and gate_up.shape[-1] == 2 * packed.K \
+                    and packed.group % 128 == 0 and self._fused_ok(gate_up, packed):
+                return _ops.gemm_wna16(gate_up, packed, self.bias, flags=_GEMM_X_GATE_UP)
+        return self.forward(_ops.silu_mul(gate_up))
 
     def forward(self, input: torch.Tensor):
         packed = None

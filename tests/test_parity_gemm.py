@@ -174,3 +174,22 @@ def test_golden_linear_through_module(case):
     assert err <= tol, (err, tol)
     # reference side effects: scale / round_zero_point live on the quantizer
     assert ql.weight_quantizer.scale.shape == (w.shape[0] * (w.shape[1] // (int(rec["group"]) or w.shape[1])), 1)
+
+
+@pytest.mark.parametrize("dtype", ["f16", "bf16"])
+@pytest.mark.parametrize("n_bits", [4, 2, 3])
+@pytest.mark.parametrize("M", [1, 2, 5, 8])
+def test_gate_up_staging_equals_separate_silu_mul(dtype, n_bits, M):
+    """Q100_GEMM_X_GATE_UP: down_proj with act_fn(gate) * up applied while x is staged == K6 followed by the same
+    GEMM, bit for bit (same kernel, same x bits)."""
+    N, K = 256, 1024
+    gen = torch.Generator().manual_seed(31 + M + n_bits)
+    w = (torch.randn(N, K, generator=gen) * 0.02).to(TDT[dtype]).cuda()
+    gu = (torch.randn(M, 2 * K, generator=gen) * 2.0).to(TDT[dtype]).cuda()
+    pw, _ = q100.pack_weight(w, n_bits, 128)
+    y_ref = q100.gemm_wna16(q100.ops.silu_mul(gu), pw, None, flags=_lib.GEMM_FORCE_SKINNY)
+    y = q100.gemm_wna16(gu, pw, None, flags=_lib.GEMM_FORCE_SKINNY | _lib.GEMM_X_GATE_UP)
+    torch.cuda.synchronize()
+    assert torch.equal(y.view(torch.int16), y_ref.view(torch.int16))
+    with pytest.raises(q100.Q100Error):
+        q100.gemm_wna16(torch.zeros(64, 2 * K, dtype=TDT[dtype], device="cuda"), pw, None, flags=_lib.GEMM_X_GATE_UP)
