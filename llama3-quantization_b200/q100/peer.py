@@ -46,6 +46,11 @@ class OneShotAllReduce:
                 torch.cuda.current_stream(self.device).cuda_stream))
         return y
 
+    def check(self) -> None:
+        """Raise if any call so far gave up waiting for a peer (the kernel sets err_flag instead of hanging)."""
+        if int(self.err.item()) != 0:
+            raise RuntimeError("q100.peer: a one-shot all-reduce timed out waiting for a peer; its results are invalid")
+
     def fits(self, y: torch.Tensor) -> bool:
         return (y.is_cuda and y.dtype in _DT and y.is_contiguous() and y.numel() % 8 == 0
                 and 0 < y.numel() <= self.slot_elems and y.data_ptr() % 16 == 0)
@@ -79,5 +84,8 @@ def get(group=None) -> Optional[OneShotAllReduce]:
 
 
 def shutdown() -> None:
-    """Drop the peer buffers of every group (call before dist.destroy_process_group)."""
+    """Drop the peer buffers of every group (call before dist.destroy_process_group).  Raises if a call timed out."""
+    objs = [o for o in _STATE.values() if o is not None]
     _STATE.clear()
+    for o in objs:
+        o.check()

@@ -47,6 +47,10 @@ def main():
             from q100 import peer
             peer.enable(None, dev)          # K7: decode-size all-reduces over peer memory (falls back to NCCL by itself)
     out = run(a, dev, rank, world)
+    if world > 1:
+        from q100 import peer as _peer
+        if _peer.get(None) is not None:
+            _peer.get(None).check()
     if rank == 0:
         print(json.dumps(out), flush=True)
     if world > 1:
