@@ -570,8 +570,7 @@ def run_ours(args):
         fblocks.clear()
         torch.cuda.empty_cache()
         import bench_model
-        model_res = bench_model.run(bench_model.default_args(ppl_samples=1 if world == 1 else 0,
-                                                             ppl_ref=world == 1), dev, rank, world)
+        model_res = bench_model.run(bench_model.default_args(ppl_samples=1, ppl_ref=True), dev, rank, world)
 
     if world > 1:
         from q100 import peer as _peer

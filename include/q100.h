@@ -35,7 +35,7 @@ extern "C" {
 #pragma GCC visibility push(default)   /* the library itself is built with -fvisibility=hidden */
 #endif
 
-#define Q100_ABI_VERSION 1
+#define Q100_ABI_VERSION 2
 
 enum q100_dtype { Q100_F16 = 0, Q100_BF16 = 1, Q100_F32 = 2 };
 
@@ -140,6 +140,23 @@ int q100_quantize_backward(const void* x, const void* grad_out, int dtype, int64
 int q100_fakequant_rows(const void* x, int dtype, int64_t rows, int64_t cols, int n_bits,
                         void* out, void* scales_out, void* zeros_out, int flags, void* stream);
 
+/*
+ * K2 with the row statistics supplied from outside -- what per_token_dynamic_calibration
+ * (quant/quantizer.py:140-141, amin / amax over the last dim) needs when that dim is sharded over
+ * tensor-parallel ranks (inputs of the row-parallel o_proj / down_proj with abits < 16, and per-channel
+ * weights of those layers): every rank takes the min / max of its slice with q100_rows_minmax, the
+ * [rows, 2] pairs are MIN / MAX all-reduced by the caller, and q100_quantize_rows_stats quantises the
+ * local slice with the global statistics -- bit-identical to slicing the single-GPU result.
+ *   minmax      [rows, 2] (min, max) in `dtype`
+ *   other arguments as q100_quantize_groupwise with group = 0 (one group per row)
+ */
+int q100_rows_minmax(const void* x, int dtype, int64_t rows, int64_t cols, void* minmax_out, void* stream);
+int q100_quantize_rows_stats(const void* x, int dtype, int64_t rows, int64_t cols, int n_bits,
+                             int symmetric, int disable_zp, const void* minmax,
+                             const void* lwc_up, const void* lwc_low,
+                             void* dequant_out, void* packed_out, void* scales_out, void* zeros_out,
+                             void* meta_out, int flags, void* stream);
+
 /* Total uint32 words of a packed [rows, cols] code matrix (q100 v2 tile-major layout: tiles of
  * 128 rows x 64 k, ordered [n_tile][k_tile]; see DESIGN.md "Packed layout"); -1 if unsupported. */
 int64_t q100_packed_words(int64_t rows, int64_t cols, int n_bits);
@@ -195,11 +212,14 @@ int q100_add_rmsnorm(const void* x, const void* residual, const void* weight, fl
  *   (int_llama_layer.py:117, 125) and rounded once; rotary(k) with every op rounded to dtype and v are
  *   written to k_cache / v_cache [batch, kv_heads, max_len, head_dim] at `position`
  *   (the static-cache form of int_llama_layer.py:130-133).
+ *   rope_len = rows of cos_cache / sin_cache.  A position outside [0, min(max_len, rope_len)) writes
+ *   nothing and sets *err_flag (device uint32, nullable) to 1 -- the reference's torch.cat cache cannot
+ *   overflow, a static one can.
  */
 int q100_rope_kv_decode(const void* qkv, const void* cos_cache, const void* sin_cache,
                         const void* position, void* q_out, void* k_cache, void* v_cache,
                         int batch, int heads, int kv_heads, int head_dim, int64_t max_len,
-                        int dtype, void* stream);
+                        int64_t rope_len, void* err_flag, int dtype, void* stream);
 /*
  * q100_silu_mul: out[rows, inter] = silu(gate) * up for gate_up [rows, 2*inter] (gate columns first), the
  *   epilogue of the fused gate|up GEMM: act_fn(gate_proj(x)) * up_proj(x), int_llama_layer.py:45.

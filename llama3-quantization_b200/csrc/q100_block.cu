@@ -90,10 +90,15 @@ __global__ void __launch_bounds__(256) k4_add_rmsnorm(const T* __restrict__ x, c
 template <typename T>
 __global__ void k5_rope_kv(const T* __restrict__ qkv, const T* __restrict__ cosb, const T* __restrict__ sinb,
                            const int64_t* __restrict__ pos_p, T* __restrict__ q_out, T* __restrict__ k_cache,
-                           T* __restrict__ v_cache, int H, int KVH, int D, int64_t max_len) {
+                           T* __restrict__ v_cache, int H, int KVH, int D, int64_t max_len, int64_t rope_len,
+                           uint32_t* __restrict__ err_flag) {
   using Dt = DT<T>;
   const int head = blockIdx.x, b = blockIdx.y, i = threadIdx.x, half = D >> 1;
   const int64_t pos = *pos_p;
+  if (pos < 0 || pos >= max_len || pos >= rope_len) {      // past the cache / the rotary table: touch nothing
+    if (err_flag != nullptr && head == 0 && b == 0 && i == 0) *err_flag = 1u;
+    return;
+  }
   const T* src = qkv + static_cast<int64_t>(b) * (H + 2 * KVH) * D + static_cast<int64_t>(head) * D;
   const float x1 = Dt::to_f(src[i]), x2 = Dt::to_f(src[i + half]);
   if (head >= H + KVH) {                                   // value head: plain copy into the cache
@@ -181,13 +186,14 @@ extern "C" int q100_add_rmsnorm(const void* x, const void* residual, const void*
 extern "C" int q100_rope_kv_decode(const void* qkv, const void* cos_cache, const void* sin_cache,
                                    const void* position, void* q_out, void* k_cache, void* v_cache,
                                    int batch, int heads, int kv_heads, int head_dim, int64_t max_len,
-                                   int dtype, void* stream) {
+                                   int64_t rope_len, void* err_flag, int dtype, void* stream) {
   Q100_REQUIRE(qkv && cos_cache && sin_cache && position && q_out && k_cache && v_cache, Q100_EINVAL,
                "NULL pointer argument");
   Q100_REQUIRE(dtype == Q100_F16 || dtype == Q100_BF16, Q100_EUNSUPPORTED, "fp16 / bf16 only (got dtype %d)", dtype);
   Q100_REQUIRE(batch >= 0 && heads > 0 && kv_heads > 0 && head_dim >= 2 && head_dim % 2 == 0 && head_dim <= 2048 &&
-               max_len > 0, Q100_EINVAL, "bad shape");
+               max_len > 0 && rope_len > 0, Q100_EINVAL, "bad shape");
   if (batch == 0) return Q100_OK;
+  uint32_t* ef = reinterpret_cast<uint32_t*>(err_flag);
   int rc = ensure_device();
   if (rc != Q100_OK) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -197,13 +203,14 @@ extern "C" int q100_rope_kv_decode(const void* qkv, const void* cos_cache, const
     k5_rope_kv<__half><<<grid, head_dim / 2, 0, st>>>(
         reinterpret_cast<const __half*>(qkv), reinterpret_cast<const __half*>(cos_cache),
         reinterpret_cast<const __half*>(sin_cache), pos, reinterpret_cast<__half*>(q_out),
-        reinterpret_cast<__half*>(k_cache), reinterpret_cast<__half*>(v_cache), heads, kv_heads, head_dim, max_len);
+        reinterpret_cast<__half*>(k_cache), reinterpret_cast<__half*>(v_cache), heads, kv_heads, head_dim, max_len,
+        rope_len, ef);
   else
     k5_rope_kv<__nv_bfloat16><<<grid, head_dim / 2, 0, st>>>(
         reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(cos_cache),
         reinterpret_cast<const __nv_bfloat16*>(sin_cache), pos, reinterpret_cast<__nv_bfloat16*>(q_out),
         reinterpret_cast<__nv_bfloat16*>(k_cache), reinterpret_cast<__nv_bfloat16*>(v_cache), heads, kv_heads,
-        head_dim, max_len);
+        head_dim, max_len, rope_len, ef);
   return check_cuda(cudaGetLastError(), "k5_rope_kv launch");
 }
 

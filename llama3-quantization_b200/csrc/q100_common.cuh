@@ -17,6 +17,8 @@ void set_error(const char* fmt, ...);
 int check_cuda(cudaError_t e, const char* what);
 int ensure_device();   // Q100_OK iff current device is sm_100; caches the answer
 int sm_count();
+int current_device();   // index of the calling thread's current device in [0, 64), 0 on error
+constexpr int kMaxDevices = 64;   // per-device caches (function attributes are a per-device property)
 
 #define Q100_CUDA(call)                                            \
   do {                                                             \

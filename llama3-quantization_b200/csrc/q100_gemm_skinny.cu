@@ -1073,14 +1073,15 @@ static int launch_skinny(SkinnyArgs a, cudaStream_t st) {
   a.stages = stages;
   const int smem = stages * stage_pitch + slab_bytes(a.m_rows, chunk, xpitch) + 128;
   static std::mutex mu;           // one per instantiation
-  static int max_set = 0;
-  static std::unordered_map<int, int> occ_cache;
+  static int max_set[kMaxDevices] = {};            // the attribute is a per-device property
+  static std::unordered_map<int, int> occ_cache;   // all devices are sm_100: occupancy is the same on each
   int occ = 0;
   {
     std::lock_guard<std::mutex> lk(mu);
-    if (smem > max_set) {
+    const int dev = current_device();
+    if (smem > max_set[dev]) {
       Q100_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      max_set = smem;
+      max_set[dev] = smem;
     }
     auto itc = occ_cache.find(smem);
     if (itc == occ_cache.end()) {

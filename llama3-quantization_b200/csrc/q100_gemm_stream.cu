@@ -505,12 +505,13 @@ static int launch_stream(const CUtensorMap& tx, StreamArgs a, cudaStream_t st) {
   a.stages = stages;
   const int smem = stages * pitch + 1024;
   static std::mutex mu;
-  static bool attr_done = false;
+  static bool attr_done[kMaxDevices] = {};       // the attribute is a per-device property
   {
     std::lock_guard<std::mutex> lk(mu);
-    if (!attr_done) {
+    const int dev = current_device();
+    if (!attr_done[dev]) {
       Q100_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      attr_done = true;
+      attr_done[dev] = true;
     }
   }
   int grid = sm_count() * ST_OCC;

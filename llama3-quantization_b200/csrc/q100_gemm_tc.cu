@@ -19,6 +19,8 @@
 //               tile's main loop through the second accumulator stage.
 // The DENSE instantiation (B tile loaded by TMA from a 16-bit weight) validates the
 // TMA / descriptor / TMEM plumbing independently of the dequant stage.
+#include <mutex>
+
 #include "q100_common.cuh"
 #include "q100_ptx.cuh"
 
@@ -359,10 +361,15 @@ template <typename T, int NBITS, bool DENSE>
 static int launch_tc(const CUtensorMap& tx, const CUtensorMap& tw, TcArgs a, cudaStream_t st) {
   using SM = TcSmem<NBITS, DENSE>;
   auto kern = k3_tc<T, NBITS, DENSE>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    Q100_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
-    attr_done = true;
+  static std::mutex mu;                          // one per instantiation
+  static bool attr_done[kMaxDevices] = {};       // the attribute is a per-device property
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    const int dev = current_device();
+    if (!attr_done[dev]) {
+      Q100_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
+      attr_done[dev] = true;
+    }
   }
   a.m_tiles = (a.M + TC_BM - 1) / TC_BM;
   a.n_tiles = a.N / TC_BN;

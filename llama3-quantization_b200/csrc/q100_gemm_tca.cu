@@ -25,6 +25,8 @@
 //   warps 8-11  epilogue: tcgen05.ld (lane = weight row, column = token) -> (+bias) -> bf16/fp16 -> global.
 #include <cstdlib>
 
+#include <mutex>
+
 #include "q100_common.cuh"
 #include "q100_ptx.cuh"
 
@@ -466,10 +468,16 @@ template <typename T, int NBITS, int NT, int CL>
 static int launch_tca(const void* x, TcaArgs a, cudaStream_t st) {
   using SM = TcaSmem<NBITS, NT>;
   auto kern = k3_tca<T, NBITS, NT, CL>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    Q100_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
-    attr_done = true;
+  static std::mutex mu;                          // one per instantiation
+  static bool attr_done[kMaxDevices] = {};       // the attribute is a per-device property
+  static int max_clusters[kMaxDevices] = {};
+  const int dev = current_device();
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (!attr_done[dev]) {
+      Q100_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::kTotal));
+      attr_done[dev] = true;
+    }
   }
   CUtensorMap tx;
   int rc = make_tmap_2d(&tx, x, 2, a.K, a.M, static_cast<uint64_t>(a.K) * 2, TA_BK, NT / CL, 128);
@@ -492,13 +500,13 @@ static int launch_tca(const void* x, TcaArgs a, cudaStream_t st) {
   if (CL > 1) {
     // persistent kernel: never launch more clusters than can be resident at once (GPC packing: clusters of
     // four do not tile all 148 SMs)
-    static int max_clusters = 0;
-    if (max_clusters == 0) {
+    std::lock_guard<std::mutex> lk(mu);
+    if (max_clusters[dev] == 0) {
       cfg.gridDim = dim3(sm_count() / CL * CL);
-      Q100_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
-      if (max_clusters < 1) max_clusters = 1;
+      Q100_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters[dev], kern, &cfg));
+      if (max_clusters[dev] < 1) max_clusters[dev] = 1;
     }
-    if (clusters > max_clusters) clusters = max_clusters;
+    if (clusters > max_clusters[dev]) clusters = max_clusters[dev];
     cfg.gridDim = dim3(clusters * CL);
   }
   return check_cuda(cudaLaunchKernelEx(&cfg, kern, tx, a), "k3_tca launch");

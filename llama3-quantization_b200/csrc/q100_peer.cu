@@ -35,7 +35,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
 }
 
 template <typename T>
-__global__ void __launch_bounds__(256) k7_allreduce(const T* __restrict__ x, T* __restrict__ y, int64_t n,
+__global__ void __launch_bounds__(256) k7_allreduce(const T* x, T* y /* may alias x */, int64_t n,
                                                     T* const* __restrict__ bufs, uint32_t* const* __restrict__ flags,
                                                     uint32_t* __restrict__ epoch_p, int64_t slot_elems, int rank,
                                                     int world, uint32_t* __restrict__ err) {

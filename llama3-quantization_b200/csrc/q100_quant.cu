@@ -687,6 +687,19 @@ __global__ void __launch_bounds__(1024) k2_rows(const QuantArgs a) {
       mx = max_nan(mx, __shfl_xor_sync(0xffffffffu, mx, d));
     }
     __syncthreads();                                   // s_mn/s_mx reusable next row
+    if (a.minmax_out != nullptr) {                     // statistics pass (q100_rows_minmax)
+      if (tid == 0) {
+        T* o = reinterpret_cast<T*>(a.minmax_out) + 2 * row;
+        o[0] = DT<T>::from_f(mn);
+        o[1] = DT<T>::from_f(mx);
+      }
+      continue;
+    }
+    if (a.ext_minmax != nullptr) {                     // statistics of the full (sharded) row, from the caller
+      const T* e = reinterpret_cast<const T*>(a.ext_minmax) + 2 * row;
+      mn = DT<T>::to_f(e[0]);
+      mx = DT<T>::to_f(e[1]);
+    }
     const GroupQ<T> q = group_params<T>(mn, mx, a, row);
     // rows whose |x / scale| and |zp| fit the exact-integer window take k1_fast's element pass (CTA-uniform)
     if constexpr (MATH == MATH_PACKED && DT<T>::kCode != Q100_F32) {
@@ -1002,6 +1015,82 @@ extern "C" int q100_quantize_groupwise(const void* x, int dtype, int64_t rows, i
     case Q100_BF16: return quantize_dispatch<__nv_bfloat16>(a, pack, flags, st);
     default:        return quantize_dispatch<float>(a, pack, flags, st);
   }
+}
+
+namespace {
+int rows_entry(const void* x, int dtype, int64_t rows, int64_t cols, int n_bits, int symmetric, int disable_zp,
+               const void* ext_minmax, void* minmax_out, const void* lwc_up, const void* lwc_low,
+               void* dequant_out, void* packed_out, void* scales_out, void* zeros_out, void* meta_out,
+               int flags, void* stream) {
+  Q100_REQUIRE(dtype >= 0 && dtype <= 2, Q100_EINVAL, "bad dtype %d", dtype);
+  Q100_REQUIRE(rows >= 0 && cols >= 0, Q100_EINVAL, "negative shape");
+  Q100_REQUIRE(n_bits >= 2 && n_bits <= 8, Q100_EUNSUPPORTED, "n_bits=%d: 2..8", n_bits);
+  Q100_REQUIRE((lwc_up == nullptr) == (lwc_low == nullptr), Q100_EINVAL, "lwc_up and lwc_low must be given together");
+  if (rows == 0 || cols == 0) return Q100_OK;
+  Q100_REQUIRE(x != nullptr, Q100_EINVAL, "x is NULL");
+  const int esz = (dtype == Q100_F32) ? 4 : 2;
+  Q100_REQUIRE((cols * esz) % 16 == 0, Q100_EUNSUPPORTED, "row of %lld elements is not a multiple of 16 bytes",
+               static_cast<long long>(cols));
+  Q100_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(dequant_out) & 15) == 0,
+               Q100_EINVAL, "x / dequant_out must be 16-byte aligned");
+  const bool pack = packed_out != nullptr;
+  if (pack) {
+    Q100_REQUIRE(n_bits == 2 || n_bits == 3 || n_bits == 4 || n_bits == 8, Q100_EUNSUPPORTED,
+                 "packed output supports n_bits in {2,3,4,8}, got %d", n_bits);
+    Q100_REQUIRE(cols % 64 == 0, Q100_EUNSUPPORTED, "packed output needs cols %% 64 == 0");
+  }
+  Q100_REQUIRE(meta_out == nullptr || dtype != Q100_F32, Q100_EUNSUPPORTED, "meta side band is fp16/bf16 only");
+  int rc = ensure_device();
+  if (rc != Q100_OK) return rc;
+  QuantArgs a{};
+  a.x = x; a.deq = dequant_out; a.packed = reinterpret_cast<uint32_t*>(packed_out);
+  a.scales = scales_out; a.zeros = zeros_out; a.meta = meta_out;
+  a.lwc_up = lwc_up; a.lwc_low = lwc_low;
+  a.ext_minmax = ext_minmax; a.minmax_out = minmax_out;
+  a.rows = rows; a.cols = cols; a.group = static_cast<int>(cols);
+  a.groups_per_row = 1;
+  a.n_groups = rows;
+  Q100_REQUIRE(a.n_groups < (1ll << 31), Q100_EUNSUPPORTED, "too many rows");
+  a.n_bits = n_bits; a.symmetric = symmetric ? 1 : 0; a.has_zp = disable_zp ? 0 : 1;
+  if (disable_zp) { a.qmin = -static_cast<float>(1 << (n_bits - 1)); a.qmax = static_cast<float>((1 << (n_bits - 1)) - 1); }
+  else { a.qmin = 0.0f; a.qmax = static_cast<float>((1 << n_bits) - 1); }
+  a.denom = symmetric ? static_cast<float>((1 << (n_bits - 1)) - 1) : static_cast<float>((1 << n_bits) - 1);
+  a.rcp_denom = 1.0f / a.denom;
+  a.k_tiles = static_cast<int>(cols / 64);
+  a.tile_words = pack ? tile_words_of(n_bits) : 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const bool k16 = dtype != Q100_F32;
+  const int math = !k16 ? MATH_SCALAR_IEEE : (flags & Q100_FLAG_IEEE_DIV) ? MATH_SCALAR_IEEE
+                        : (flags & Q100_FLAG_SCALAR_MATH) ? MATH_SCALAR : MATH_PACKED;
+  switch (dtype) {
+    case Q100_F16:
+      if (math == MATH_SCALAR_IEEE) return launch_k2<__half, MATH_SCALAR_IEEE>(a, pack, st);
+      if (math == MATH_SCALAR) return launch_k2<__half, MATH_SCALAR>(a, pack, st);
+      return launch_k2<__half, MATH_PACKED>(a, pack, st);
+    case Q100_BF16:
+      if (math == MATH_SCALAR_IEEE) return launch_k2<__nv_bfloat16, MATH_SCALAR_IEEE>(a, pack, st);
+      if (math == MATH_SCALAR) return launch_k2<__nv_bfloat16, MATH_SCALAR>(a, pack, st);
+      return launch_k2<__nv_bfloat16, MATH_PACKED>(a, pack, st);
+    default:
+      return launch_k2<float, MATH_SCALAR_IEEE>(a, pack, st);
+  }
+}
+}  // namespace
+
+extern "C" int q100_rows_minmax(const void* x, int dtype, int64_t rows, int64_t cols, void* minmax_out, void* stream) {
+  Q100_REQUIRE(minmax_out != nullptr || rows == 0, Q100_EINVAL, "minmax_out is NULL");
+  return rows_entry(x, dtype, rows, cols, 8, 0, 0, nullptr, minmax_out, nullptr, nullptr, nullptr, nullptr, nullptr,
+                    nullptr, nullptr, 0, stream);
+}
+
+extern "C" int q100_quantize_rows_stats(const void* x, int dtype, int64_t rows, int64_t cols, int n_bits,
+                                        int symmetric, int disable_zp, const void* minmax,
+                                        const void* lwc_up, const void* lwc_low,
+                                        void* dequant_out, void* packed_out, void* scales_out, void* zeros_out,
+                                        void* meta_out, int flags, void* stream) {
+  Q100_REQUIRE(minmax != nullptr || rows == 0, Q100_EINVAL, "minmax is NULL");
+  return rows_entry(x, dtype, rows, cols, n_bits, symmetric, disable_zp, minmax, nullptr, lwc_up, lwc_low,
+                    dequant_out, packed_out, scales_out, zeros_out, meta_out, flags, stream);
 }
 
 extern "C" int q100_fakequant_rows(const void* x, int dtype, int64_t rows, int64_t cols, int n_bits,

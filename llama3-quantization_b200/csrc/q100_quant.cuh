@@ -16,6 +16,8 @@ struct QuantArgs {
   void* meta;
   const void* lwc_up;
   const void* lwc_low;
+  const void* ext_minmax;   // K2 only: [rows, 2] (min, max) supplied by the caller instead of the row reduction
+  void* minmax_out;         // K2 only: write the row's (min, max) here and do nothing else
   int64_t rows, cols, n_groups;
   int group;            // elements per group
   int groups_per_row;

@@ -399,7 +399,7 @@ class QuantLlamaDecoderLayer(nn.Module):
 
     # ------------------------------------------------------------------ fused decode step (extension)
     @torch.no_grad()
-    def decode_step_fused(self, x, residual, kv: "StaticKV", position, attention_mask):
+    def decode_step_fused(self, x, residual, kv: "StaticKV", position, attention_mask, err_flag=None):
         """One new token per sequence through this block in 4 GEMM launches + 4 small kernels + the
         attention core, on a static KV cache (CUDA-graph friendly).  Same arithmetic as ``forward`` with
         ``past_key_value=kv`` (tests/test_block.py compares the two); what moves is where the residual add
@@ -422,7 +422,7 @@ class QuantLlamaDecoderLayer(nn.Module):
         if rc is None or rc[0].dtype != x.dtype or rc[0].shape[0] < kv.k.shape[-2] or rc[0].device != x.device:
             cos, sin = attn.rotary_emb(kv.v, seq_len=kv.k.shape[-2])
             rc = attn._rope16 = (cos.to(x.dtype).contiguous(), sin.to(x.dtype).contiguous())
-        q = _ops.rope_kv_decode(qkv, rc[0], rc[1], position, kv.k, kv.v, nh, nkv)
+        q = _ops.rope_kv_decode(qkv, rc[0], rc[1], position, kv.k, kv.v, nh, nkv, err_flag)
         att = F.scaled_dot_product_attention(q, kv.k, kv.v, attn_mask=attention_mask, enable_gqa=nh != nkv)
         o = attn.o_proj(att.reshape(bsz, 1, nh * attn.head_dim))
         if attn.tp_world > 1:

@@ -38,12 +38,14 @@ SIGNATURES = {
     "q100_quantize_groupwise": (_i, [_vp, _i, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "q100_quantize_backward": (_i, [_vp, _vp, _i, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "q100_fakequant_rows": (_i, [_vp, _i, _i64, _i64, _i, _vp, _vp, _vp, _i, _vp]),
+    "q100_rows_minmax": (_i, [_vp, _i, _i64, _i64, _vp, _vp]),
+    "q100_quantize_rows_stats": (_i, [_vp, _i, _i64, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "q100_packed_words": (_i64, [_i64, _i64, _i]),
     "q100_dequantize": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _i, _i, _i, _vp, _vp]),
     "q100_gemm_wna16": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _sz, _i, _vp]),
     "q100_gemm_workspace_bytes": (_sz, [_i64, _i64, _i64, _i, _i]),
     "q100_add_rmsnorm": (_i, [_vp, _vp, _vp, C.c_float, _vp, _vp, _i64, _i64, _i, _vp]),
-    "q100_rope_kv_decode": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i64, _i, _vp]),
+    "q100_rope_kv_decode": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i64, _i64, _vp, _i, _vp]),
     "q100_silu_mul": (_i, [_vp, _vp, _i64, _i64, _i, _vp]),
     "q100_allreduce_oneshot": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp]),
     "q100_selftest_div": (_i, [_i, _vp, _vp]),

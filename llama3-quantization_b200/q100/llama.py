@@ -110,6 +110,16 @@ def build_block(cfg: LlamaCfg, weights: dict, args, rank=0, world=1, tp_group=No
     layer = QuantLlamaDecoderLayer(cfg, ori, args)
     layer.self_attn.tp_world, layer.self_attn.tp_group = world, tp_group
     layer.mlp.tp_world, layer.mlp.tp_group = world, tp_group
+    if world > 1:
+        # row-parallel layers see a K-slice: per-token activation statistics (abits < 16) and per-channel weight
+        # statistics (group_size=None) span all ranks -> one [rows, 2] MIN/MAX all-reduce inside the quantizer
+        import torch.distributed as dist
+        sg = tp_group if tp_group is not None else dist.group.WORLD
+        for m in (layer.self_attn.o_proj, layer.mlp.down_proj):
+            if m.act_quantizer is not None:
+                m.act_quantizer.stat_group = sg
+            if not m.weight_quantizer.group_size:
+                m.weight_quantizer.stat_group = sg
     if quantize and args.weight_quant_params["n_bits"] < 16:
         layer.smooth_and_quant_inplace()
         if drop_dense:
@@ -230,6 +240,10 @@ class GraphDecoder:
         self._neg = torch.finfo(dt).min
         self.graph = None
         self.use_graph = use_graph
+        # the static cache cannot grow: count the steps on the host and refuse to run past max_len (K5 also checks
+        # the device-side position and raises this flag instead of writing outside the cache)
+        self.err = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._host_pos = 0
 
     def _step(self):
         m = self.model
@@ -238,7 +252,7 @@ class GraphDecoder:
         mask = mask.expand(self.bsz, 1, 1, self.max_len)
         res = None                  # residual stream, kept apart from the last MLP output on the fused route
         for layer, kv in zip(m.layers, self.caches):
-            out = layer.decode_step_fused(x, res, kv, self.pos, mask) if self.fused else None
+            out = layer.decode_step_fused(x, res, kv, self.pos, mask, self.err) if self.fused else None
             if out is not None:
                 x, res = out
             else:
@@ -257,7 +271,10 @@ class GraphDecoder:
     @torch.no_grad()
     def prime(self, start_pos: int = 0):
         """Warm up (builds rotary caches, fused packs, workspaces) and capture."""
+        if not 0 <= start_pos or start_pos + 2 >= self.max_len:
+            raise ValueError(f"GraphDecoder.prime: start_pos={start_pos} leaves no room in a cache of {self.max_len}")
         self.pos.fill_(start_pos)
+        self._host_pos = start_pos
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -271,13 +288,18 @@ class GraphDecoder:
                 with torch.cuda.graph(g):
                     self._step_pdl()
                 self.graph = g
-            except Exception:                      # e.g. a collective that cannot be captured on this setup
+            except Exception as ex:                # e.g. a collective that cannot be captured on this setup
+                import warnings
+                warnings.warn(f"q100 GraphDecoder: CUDA-graph capture failed, decoding eagerly ({ex!r})")
                 self.graph = None
                 torch.cuda.synchronize()
         self.pos.fill_(start_pos)
 
     @torch.no_grad()
     def step(self, tokens: Optional[torch.Tensor] = None):
+        if self._host_pos >= self.max_len:
+            raise RuntimeError(f"GraphDecoder: KV cache of {self.max_len} positions is full")
+        self._host_pos += 1
         if tokens is not None:
             self.tok.copy_(tokens)
         if self.graph is not None:
@@ -285,6 +307,11 @@ class GraphDecoder:
         else:
             self._step_pdl()
         return self.next_tok
+
+    def check(self):
+        """Raise if a kernel saw a position outside the cache (synchronises)."""
+        if int(self.err.item()) != 0:
+            raise RuntimeError("GraphDecoder: a decode step ran past the KV cache / rotary table")
 
     def _step_pdl(self):
         # the weights are static during decode, so every GEMM may start streaming them while its

@@ -178,6 +178,56 @@ def fakequant_rows(x: torch.Tensor, n_bits: int, flags: int = 0) -> QuantResult:
     return res
 
 
+def rows_minmax(x: torch.Tensor) -> torch.Tensor:
+    """[rows, 2] (min, max) over the last dim of ``x`` (any leading shape), in x's dtype -- the statistics pass of K2.
+    With the feature dim sharded over tensor-parallel ranks the pairs are MIN / MAX all-reduced and handed to
+    :func:`quantize_rows_stats` (q100/tp.py ``allreduce_minmax``)."""
+    _require_cuda(x)
+    x2 = x.contiguous().view(-1, x.shape[-1])
+    out = torch.empty((x2.shape[0], 2), dtype=x.dtype, device=x.device)
+    with _on(x.device):
+        check(lib.q100_rows_minmax(x2.data_ptr(), _dtype_code(x2), x2.shape[0], x2.shape[1], out.data_ptr(), _stream(x2)))
+    return out
+
+
+def quantize_rows_stats(x: torch.Tensor, minmax: torch.Tensor, n_bits: int, symmetric: bool = False,
+                        disable_zero_point: bool = False, lwc_up: Optional[torch.Tensor] = None,
+                        lwc_low: Optional[torch.Tensor] = None, want_dequant: bool = True,
+                        want_packed: bool = False, want_meta: bool = False, flags: int = 0) -> QuantResult:
+    """One group per row of the 2-D ``x``, quantised with externally supplied row statistics ``minmax`` [rows, 2]
+    (UniformAffineQuantizer.forward when the row is sharded over ranks: quantizer.py:140-159 on the global
+    amin / amax)."""
+    _require_cuda(x, minmax, lwc_up, lwc_low)
+    if x.dim() != 2:
+        raise ValueError("q100.quantize_rows_stats expects a 2-D tensor")
+    x = x.contiguous()
+    rows, cols = x.shape
+    if minmax.shape != (rows, 2) or minmax.dtype != x.dtype:
+        raise ValueError("minmax must be [rows, 2] in x's dtype")
+    minmax = minmax.contiguous()
+    dev, dt = x.device, x.dtype
+    res = QuantResult()
+    if want_dequant:
+        res.dequant = torch.empty_like(x)
+    if want_packed:
+        shp = packed_shape(rows, cols, n_bits)
+        res.packed = (torch.zeros if rows % TILE_ROWS else torch.empty)(shp, dtype=torch.int32, device=dev)
+    res.scales = torch.empty((rows, 1), dtype=dt, device=dev)
+    if not disable_zero_point:
+        res.zeros = torch.empty((rows, 1), dtype=dt, device=dev)
+    if want_meta:
+        res.meta = torch.zeros((1, rows, 2), dtype=dt, device=dev)
+    if lwc_up is not None:
+        lwc_up = lwc_up.to(dt).contiguous()
+        lwc_low = lwc_low.to(dt).contiguous()
+    with _on(dev):
+        check(lib.q100_quantize_rows_stats(
+            x.data_ptr(), _dtype_code(x), rows, cols, n_bits, int(bool(symmetric)), int(bool(disable_zero_point)),
+            minmax.data_ptr(), _ptr(lwc_up), _ptr(lwc_low), _ptr(res.dequant), _ptr(res.packed), _ptr(res.scales),
+            _ptr(res.zeros), _ptr(res.meta), flags, _stream(x)))
+    return res
+
+
 def dequantize(packed: torch.Tensor, scales: Optional[torch.Tensor], zeros: Optional[torch.Tensor],
                rows: int, cols: int, group: int, n_bits: int, dtype: torch.dtype,
                disable_zero_point: bool = False) -> torch.Tensor:
@@ -293,9 +343,11 @@ def add_rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float, residual: Opt
 
 
 def rope_kv_decode(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, position: torch.Tensor,
-                   k_cache: torch.Tensor, v_cache: torch.Tensor, heads: int, kv_heads: int) -> torch.Tensor:
+                   k_cache: torch.Tensor, v_cache: torch.Tensor, heads: int, kv_heads: int,
+                   err_flag: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Rotary on q/k of one new token per sequence + append of k, v to the static cache (K5).
-    Returns q [batch, heads, 1, head_dim]."""
+    Returns q [batch, heads, 1, head_dim].  A position outside the cache / the rotary table writes nothing
+    and sets ``err_flag`` (int32 [1] on the device) to 1."""
     _require_cuda(qkv, cos, sin, position, k_cache, v_cache)
     bsz = k_cache.shape[0]
     hd, max_len = k_cache.shape[-1], k_cache.shape[-2]
@@ -308,7 +360,7 @@ def rope_kv_decode(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, posi
     with _on(qkv.device):
         check(lib.q100_rope_kv_decode(qkv.data_ptr(), cos.data_ptr(), sin.data_ptr(), position.data_ptr(),
                                       q.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), bsz, heads, kv_heads,
-                                      hd, max_len, _DT[qkv.dtype], _stream(qkv)))
+                                      hd, max_len, cos.shape[0], _ptr(err_flag), _DT[qkv.dtype], _stream(qkv)))
     return q
 
 

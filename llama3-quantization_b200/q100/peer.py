@@ -26,9 +26,19 @@ class OneShotAllReduce:
         self.rank = dist.get_rank(self.group)
         self.device = device
         self.slot_elems = int(slot_elems)
-        self.buf = symm.empty(2 * self.world * self.slot_elems, dtype=torch.float16, device=device)
-        self.flags = symm.empty(2 * self.world * FLAG_WORDS, dtype=torch.int32, device=device)
-        self.flags.zero_()
+        # 1) everything that can fail locally, 2) agree on it with ONE collective, 3) only then the collectives of
+        # the setup itself (rendezvous, barrier) -- a rank that raised in (1) must not leave its peers in a barrier
+        err = None
+        try:
+            self.buf = symm.empty(2 * self.world * self.slot_elems, dtype=torch.float16, device=device)
+            self.flags = symm.empty(2 * self.world * FLAG_WORDS, dtype=torch.int32, device=device)
+            self.flags.zero_()
+        except Exception as e:                                     # noqa: BLE001
+            err = e
+        ok = torch.tensor([0.0 if err is not None else 1.0], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if ok.item() == 0:
+            raise RuntimeError(f"symmetric-memory allocation failed on some rank ({err!r})")
         self.h_buf = symm.rendezvous(self.buf, self.group)
         self.h_flags = symm.rendezvous(self.flags, self.group)
         self.epoch = torch.zeros(FLAG_WORDS, dtype=torch.int32, device=device)
@@ -39,6 +49,8 @@ class OneShotAllReduce:
     def __call__(self, y: torch.Tensor) -> torch.Tensor:
         """In-place all-reduce(sum) of a contiguous fp16 / bf16 tensor of at most slot_elems elements."""
         n = y.numel()
+        if y.data_ptr() % 16:
+            raise ValueError("q100.peer: tensor must be 16-byte aligned")    # never a per-rank path choice (fits())
         with torch.cuda.device(self.device):
             check(lib.q100_allreduce_oneshot(
                 y.data_ptr(), y.data_ptr(), n, _DT[y.dtype], self.h_buf.buffer_ptrs_dev, self.h_flags.buffer_ptrs_dev,
@@ -52,8 +64,9 @@ class OneShotAllReduce:
             raise RuntimeError("q100.peer: a one-shot all-reduce timed out waiting for a peer; its results are invalid")
 
     def fits(self, y: torch.Tensor) -> bool:
+        # only properties that are identical on every rank may decide the path (NCCL vs peer): shape, dtype, layout
         return (y.is_cuda and y.dtype in _DT and y.is_contiguous() and y.numel() % 8 == 0
-                and 0 < y.numel() <= self.slot_elems and y.data_ptr() % 16 == 0)
+                and 0 < y.numel() <= self.slot_elems)
 
 
 def enable(group=None, device: Optional[torch.device] = None, slot_elems: int = 16 * 8192) -> Optional[OneShotAllReduce]:
@@ -65,15 +78,11 @@ def enable(group=None, device: Optional[torch.device] = None, slot_elems: int = 
     obj = None
     if dist.is_initialized() and dist.get_world_size(group) > 1 and torch.cuda.is_available():
         dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
-        ok = torch.ones(1, device=dev)
         try:
-            obj = OneShotAllReduce(group, dev, slot_elems)
+            obj = OneShotAllReduce(group, dev, slot_elems)         # agrees across ranks before its own collectives
         except Exception as e:                                     # noqa: BLE001 -- any setup failure => NCCL
             import warnings
             warnings.warn(f"q100.peer: symmetric memory unavailable, small all-reduces stay on NCCL ({e!r})")
-            ok.zero_()
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)   # all ranks or none
-        if ok.item() == 0:
             obj = None
     _STATE[key] = obj
     return obj

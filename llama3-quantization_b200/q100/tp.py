@@ -54,7 +54,10 @@ def shard_bounds(N: int, K: int, mode: str, rank: int, world: int, group: int = 
     if mode == ROW:
         g = K if group in (0, None) else group
         if g == K and world > 1:
-            raise ValueError("per-channel (one group per row) weights cannot be row-sharded bit-exactly")
+            # per-channel (one group per output row): the row's min / max spans all ranks, so
+            # the caller quantises its slice with all-reduced statistics (UniformAffineQuantizer.stat_group ->
+            # allreduce_minmax below); the cut only has to respect the packed layout's 128-k blocks
+            g = 128
         if K % (world * g) != 0:
             raise ValueError(f"K={K} cannot be split over {world} ranks in multiples of the group {g}")
         per = K // world
@@ -97,6 +100,21 @@ def gather_columns(y: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -
     parts = [torch.empty_like(y) for _ in range(dist.get_world_size(group))]
     dist.all_gather(parts, y.contiguous(), group=group)
     return torch.cat(parts, dim=-1)
+
+
+def allreduce_minmax(mm: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """[rows, 2] (min, max) pairs of a row whose elements are spread over the ranks of ``group`` -> the pairs of the
+    whole row, on every rank, with ONE collective: MAX over (-min, max) (negation is exact).  This is the extra
+    all-reduce SURVEY 8e asks for when abits < 16 (inputs of o_proj / down_proj) and for per-channel weights of
+    row-parallel layers; with it scales and zero-points are bit-identical to the single-GPU run
+    (quantizer.py:140-159 sees the same amin / amax)."""
+    if not (dist.is_initialized() and dist.get_world_size(group) > 1):
+        return mm
+    t = torch.stack((-mm[:, 0], mm[:, 1]), dim=1).contiguous()
+    work = t.float() if (not t.is_cuda and t.dtype != torch.float32) else t     # gloo has no 16-bit MAX on some builds
+    dist.all_reduce(work, op=dist.ReduceOp.MAX, group=group)
+    t = work.to(mm.dtype)
+    return torch.stack((-t[:, 0], t[:, 1]), dim=1).contiguous()
 
 
 def rowwise_minmax_allreduce(x_local: torch.Tensor, group: Optional[dist.ProcessGroup] = None):

@@ -179,6 +179,10 @@ class UniformAffineQuantizer(nn.Module):
         self.keep_packed = False
         self._packed = None
         self._packed_of = None
+        # tensor parallelism (extension; q100/tp.py): the process group over whose ranks the quantised row (the
+        # last dim, group_size=None) is sharded.  forward() then takes the row min / max over all ranks
+        # (one [rows, 2] all-reduce) so that scale / zero-point equal the single-GPU ones bit for bit.
+        self.stat_group = None
 
     def change_n_bits(self, n_bits):
         self.n_bits = n_bits
@@ -195,10 +199,15 @@ class UniformAffineQuantizer(nn.Module):
         self._run(x, want_dequant=False)
 
     def fake_quant(self, x, scale, round_zero_point):
-        """Reference quantizer.py:94-115.  ``scale`` / ``round_zero_point`` are recomputed by the
-        fused kernel from ``x`` itself; they equal the arguments whenever those came from
-        ``per_token_dynamic_calibration(x)``, which is the only way the reference calls it."""
-        return self._run(x, want_dequant=True)
+        """Reference quantizer.py:94-115.  When ``scale`` / ``round_zero_point`` are the tensors the last
+        ``per_token_dynamic_calibration(x)`` left on the module (the only way the reference calls it,
+        quantizer.py:128-129) this is the fused kernel pass; any other scale / zero-point is honoured through the
+        reference's own op sequence on the GPU."""
+        if scale is self.scale and round_zero_point is self.round_zero_point and self.n_bits <= 8:
+            return self._run(x, want_dequant=True)
+        if not x.is_cuda:
+            raise RuntimeError("q100 UniformAffineQuantizer: CUDA tensor required -- there is no CPU fallback")
+        return self._fake_quant_eager(x, scale, round_zero_point)
 
     def forward(self, x: torch.Tensor):
         if self.n_bits >= 16 or not self.enable:
@@ -225,7 +234,10 @@ class UniformAffineQuantizer(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("q100 UniformAffineQuantizer: CUDA tensor required -- there is no CPU fallback")
         if self.n_bits > 8:
-            raise NotImplementedError(f"q100: n_bits={self.n_bits} (9..15) is not implemented")
+            # 9..15 bits: accepted by the reference (quantizer.py:36) but used by no configuration (wbits 2/3/4/8,
+            # abits 4/8/16) and not representable by the packed layout; kept on the reference's own op sequence
+            # (eager torch ops on the GPU), not on a kernel.
+            return self._run_eager(x, want_dequant)
         orig_shape = x.shape
         x, up, low = self._lwc_multipliers(x)
         if self.group_size:
@@ -243,7 +255,29 @@ class UniformAffineQuantizer(nn.Module):
 
         need_grad = torch.is_grad_enabled() and (
             x2d.requires_grad or (up is not None and (up.requires_grad or low.requires_grad)))
-        if need_grad:
+        sharded_row = False
+        if self.stat_group is not None and not self.group_size:
+            import torch.distributed as dist
+            sharded_row = dist.is_initialized() and dist.get_world_size(self.stat_group) > 1
+        if sharded_row:
+            if need_grad:
+                raise NotImplementedError("q100: calibration (autograd) through a tensor-parallel row statistic")
+            from q100 import tp as _tp
+            x2c = x2d.contiguous()
+            mm = _tp.allreduce_minmax(_ops.rows_minmax(x2c), self.stat_group)
+            keep = self.keep_packed and x2d.dim() == 2 and want_dequant and self.n_bits in (2, 3, 4, 8) \
+                and x2d.dtype in (torch.float16, torch.bfloat16) and x2d.shape[1] % 128 == 0
+            res = _ops.quantize_rows_stats(
+                x2c, mm, self.n_bits, bool(self.symmetric), bool(self.disable_zero_point),
+                None if up is None else up.detach(), None if low is None else low.detach(),
+                want_dequant=want_dequant, want_packed=keep, want_meta=keep)
+            deq, scale, zp = res.dequant, res.scales, res.zeros
+            self._packed = self._packed_of = None
+            if keep:
+                self._packed = _ops.PackedWeight(res.packed, res.meta, res.scales, res.zeros, self.n_bits,
+                                                 x2d.shape[1], x2d.shape[0], x2d.shape[1],
+                                                 bool(self.disable_zero_point))
+        elif need_grad:
             deq, scale, zp = _FakeQuantFn.apply(x2d.contiguous(), up, low, group, self.n_bits,
                                                 bool(self.symmetric), bool(self.disable_zero_point),
                                                 self.qmin, self.qmax)
@@ -274,6 +308,59 @@ class UniformAffineQuantizer(nn.Module):
         if self._packed is not None:
             self._packed_of = (out.data_ptr(), out._version, tuple(out.shape), out.dtype)
         return out
+
+    def _run_eager(self, x: torch.Tensor, want_dequant: bool):
+        """The reference's op sequence (quantizer.py:94-159) with torch ops, for the bit widths no kernel covers
+        (9..15).  Differentiable like the reference."""
+        xr = x
+        if self.group_size:
+            if self.deficiency == 0:
+                xr = x.reshape(-1, self.group_size)
+            else:
+                pad = torch.zeros((x.shape[0], self.deficiency), dtype=x.dtype, device=x.device)
+                xr = torch.cat((x, pad), dim=1).reshape(-1, self.group_size)
+        xmin, xmax = xr.amin([-1], keepdim=True), xr.amax([-1], keepdim=True)
+        if self.lwc:
+            xmax = self.sigmoid(self.upbound_factor) * xmax
+            xmin = self.sigmoid(self.lowbound_factor) * xmin
+        if self.symmetric:
+            abs_max = torch.max(xmax.abs(), xmin.abs())
+            scale = abs_max / (2 ** (self.n_bits - 1) - 1)
+            self.scale = scale.clamp(min=CLIPMIN, max=1e4)
+            zero_point = (2 ** (self.n_bits - 1) - 1) * torch.ones_like(self.scale)
+        else:
+            scale = (xmax - xmin) / (2 ** self.n_bits - 1)
+            self.scale = scale.clamp(min=CLIPMIN, max=1e4)
+            zero_point = -xmin / self.scale
+        self.round_zero_point = None if self.disable_zero_point else zero_point.clamp(min=-1e4, max=1e4).round()
+        self._packed = self._packed_of = None
+        if not want_dequant:
+            return None
+        return self._fake_quant_eager(x, self.scale, self.round_zero_point)
+
+    def _fake_quant_eager(self, x, scale, round_zero_point):
+        """quantizer.py:94-115 with torch ops on the caller's scale / zero-point."""
+        if self.deficiency > 0:
+            pad = torch.zeros((x.shape[0], self.deficiency), dtype=x.dtype, device=x.device)
+            x = torch.cat((x, pad), dim=1)
+        dim1 = dim2 = None
+        if self.group_size:
+            assert len(x.shape) == 2, "only support linear layer now"
+            dim1, dim2 = x.shape
+            x = x.reshape(-1, self.group_size)
+        x_int = round_ste(x / scale)
+        if round_zero_point is not None:
+            x_int = x_int.add(round_zero_point)
+        x_int = x_int.clamp(self.qmin, self.qmax)
+        x_dequant = x_int
+        if round_zero_point is not None:
+            x_dequant = x_dequant.sub(round_zero_point)
+        x_dequant = x_dequant.mul(scale)
+        if self.group_size:
+            x_dequant = x_dequant.reshape(dim1, dim2)
+        if self.deficiency > 0:
+            x_dequant = x_dequant[:, :-self.deficiency]
+        return x_dequant
 
     def packed_for(self, w: torch.Tensor):
         """PackedWeight twin of ``w`` if ``w`` is exactly the tensor the last forward returned."""

@@ -112,8 +112,10 @@ def qrange(n_bits: int, disable_zero_point: bool):
 
 # --------------------------------------------------------------------------- calibration
 def calibrate(xg: np.ndarray, dtype: str, n_bits: int, symmetric: bool = False,
-              disable_zero_point: bool = False, lwc_up=None, lwc_low=None):
+              disable_zero_point: bool = False, lwc_up=None, lwc_low=None, ext_minmax=None):
     """Per-row min/max -> (scale, round_zero_point).  quant/quantizer.py:140-159.
+    ``ext_minmax`` [groups, 2]: amin / amax of the WHOLE row when ``xg`` is only a tensor-parallel slice of it
+    (the reference has no sharding; this states what its quantizer.py:140-141 sees on the unsharded row).
 
     ``xg`` is ``[groups, g]`` fp32 holding ``dtype``-representable values.
     ``lwc_up`` / ``lwc_low`` are the *post-sigmoid* multipliers ``[groups, 1]``
@@ -123,6 +125,9 @@ def calibrate(xg: np.ndarray, dtype: str, n_bits: int, symmetric: bool = False,
     with np.errstate(invalid="ignore", over="ignore", divide="ignore"):
         xmin = np.min(xg, axis=-1, keepdims=True)          # amin/amax propagate NaN like torch
         xmax = np.max(xg, axis=-1, keepdims=True)
+        if ext_minmax is not None:
+            em = np.asarray(ext_minmax, np.float32).reshape(-1, 2)
+            xmin, xmax = em[:, :1].copy(), em[:, 1:].copy()
         if lwc_up is not None:
             xmax = rnd(np.asarray(lwc_up, np.float32).reshape(-1, 1) * xmax, dtype)
             xmin = rnd(np.asarray(lwc_low, np.float32).reshape(-1, 1) * xmin, dtype)
@@ -166,7 +171,7 @@ def fake_quant(xg: np.ndarray, scale: np.ndarray, rzp, dtype: str, n_bits: int,
 
 def quantize_groupwise(w: np.ndarray, dtype: str, group: int, n_bits: int,
                        symmetric: bool = False, disable_zero_point: bool = False,
-                       lwc_up=None, lwc_low=None):
+                       lwc_up=None, lwc_low=None, ext_minmax=None):
     """UniformAffineQuantizer.forward on a 2-D tensor (quant/quantizer.py:118-130).
 
     ``group == 0`` means one group per row (``group_size=None``).  ``w`` is fp32
@@ -180,7 +185,7 @@ def quantize_groupwise(w: np.ndarray, dtype: str, group: int, n_bits: int,
     g = cols if group in (0, None) else group
     assert cols % g == 0
     xg = w.reshape(-1, g)
-    scale, rzp = calibrate(xg, dtype, n_bits, symmetric, disable_zero_point, lwc_up, lwc_low)
+    scale, rzp = calibrate(xg, dtype, n_bits, symmetric, disable_zero_point, lwc_up, lwc_low, ext_minmax)
     deq, codes = fake_quant(xg, scale, rzp, dtype, n_bits, disable_zero_point)
     return {
         "dequant": deq.reshape(rows, cols),

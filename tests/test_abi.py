@@ -28,7 +28,7 @@ def test_header_symbols_exported():
 
 
 def test_abi_version():
-    assert _lib.lib.q100_abi_version() == 1
+    assert _lib.lib.q100_abi_version() == 2
 
 
 def test_packed_shape():

@@ -60,6 +60,43 @@ def test_rope_kv_decode_bit_exact(dtype, bsz, heads, kvh, hd):
     assert kc[:, :, :pos].abs().max().item() == 0 and kc[:, :, pos + 1:].abs().max().item() == 0
 
 
+@pytest.mark.parametrize("pos", [-1, 40, 41, 10 ** 6, 30])
+def test_rope_kv_decode_position_outside_cache(pos):
+    """A static cache can overflow (the reference's torch.cat cache cannot): K5 must write nothing and raise the flag
+    when the device-side position is outside the cache or the rotary table (here: table 32 rows, cache 40 slots)."""
+    from q100 import ops
+    dev = torch.device("cuda:0")
+    bsz, heads, kvh, hd, max_len, rope_len = 2, 4, 2, 64, 40, 32
+    qkv = torch.randn(bsz, 1, (heads + 2 * kvh) * hd, device=dev).half()
+    cos, sin = LP.rotary_cache(hd, rope_len, 500000.0, dev, torch.float16)
+    guard = torch.full((bsz * kvh * max_len * hd + 4096,), 7.0, dtype=torch.float16, device=dev)
+    kc = guard[2048:2048 + bsz * kvh * max_len * hd].view(bsz, kvh, max_len, hd)
+    vc = torch.full_like(kc, 7.0)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    ops.rope_kv_decode(qkv, cos.contiguous(), sin.contiguous(), torch.tensor([[pos]], device=dev), kc, vc, heads, kvh, err)
+    torch.cuda.synchronize()
+    assert int(err.item()) == 1
+    assert bool((guard == 7.0).all()) and bool((vc == 7.0).all())
+
+
+def test_graph_decoder_refuses_to_run_past_the_cache():
+    from q100 import llama as QL
+    import dataclasses
+    cfg = dataclasses.replace(QL.LLAMA3_8B, hidden_size=256, intermediate_size=512, num_attention_heads=4,
+                              num_key_value_heads=2, num_hidden_layers=1, vocab_size=1000)
+    m = QL.QuantLlamaModel.random_init(cfg, QL.quant_args(4, 128, 16), torch.device("cuda:0"), torch.float16,
+                                       fast_attention=True)
+    dec = QL.GraphDecoder(m, 1, 8, use_graph=False)
+    dec.prime(4)
+    for _ in range(4):
+        dec.step()
+    dec.check()
+    with pytest.raises(RuntimeError):
+        dec.step()
+    with pytest.raises(ValueError):
+        dec.prime(7)
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("rows,inter", [(1, 14336), (16, 14336), (3, 512), (2, 1000)])
 def test_silu_mul(dtype, rows, inter):

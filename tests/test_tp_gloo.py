@@ -55,6 +55,19 @@ def _worker(rank, world, port, results):
         # --- per-token activation stats across a K-sharded activation (abits < 16)
         mn, mx = tp.rowwise_minmax_allreduce(torch.from_numpy(xl))
         assert np.array_equal(mn.numpy()[:, 0], x.min(axis=1)) and np.array_equal(mx.numpy()[:, 0], x.max(axis=1))
+        # ... the one-collective form the product uses (quantizer.stat_group): [rows, 2] pairs, MAX over (-min, max);
+        # quantising the local slice with the global pair reproduces the slice of the unsharded result bit for bit
+        xl16 = torch.from_numpy(xl).half()
+        mm = torch.stack((xl16.amin(-1), xl16.amax(-1)), dim=1)
+        mmg = tp.allreduce_minmax(mm)
+        xf = torch.from_numpy(x).half()
+        assert torch.equal(mmg[:, 0], xf.amin(-1)) and torch.equal(mmg[:, 1], xf.amax(-1))
+        for bits in (8, 4):
+            whole = O.quantize_groupwise(x, "f16", 0, bits)
+            part = O.quantize_groupwise(xl, "f16", 0, bits, ext_minmax=mmg.float().numpy())
+            k0 = rank * (K // world)
+            assert np.array_equal(part["dequant"], whole["dequant"][:, k0:k0 + K // world])
+            assert np.array_equal(part["scales"], whole["scales"]) and np.array_equal(part["zeros"], whole["zeros"])
         results[rank] = "ok"
     finally:
         dist.destroy_process_group()
@@ -88,8 +101,9 @@ def test_shard_bounds():
                 cover_n += n if mode == tp.COLUMN else 0
                 cover_k += k if mode == tp.ROW else 0
             assert cover_n == (N if mode == tp.COLUMN else 0) and cover_k == (K if mode == tp.ROW else 0)
-    with pytest.raises(ValueError):
-        tp.shard_bounds(4096, 4096, tp.ROW, 0, 2, 0)           # per-channel cannot be K-split bit-exactly
+    # per-channel weights: K is cut on the packed layout's 128-k blocks; the caller supplies all-reduced row statistics
+    sh = tp.shard_bounds(4096, 4096, tp.ROW, 1, 2, 0)
+    assert (sh.k0, sh.k1) == (2048, 4096)
     with pytest.raises(ValueError):
         tp.shard_bounds(4096, 4096 + 128, tp.ROW, 0, 8, 128)
     with pytest.raises(ValueError):

@@ -85,7 +85,7 @@ def run(a, dev, rank=0, world=1):
             l.self_attn.fast_attention = False        # reference attention formulation for the parity number
         ppl, nll = model.perplexity(testenc, a.seqlen)
         out["ppl"] = {"ppl": ppl, "mean_nll": nll, "tokens": a.ppl_samples * a.seqlen}
-        if a.ppl_ref and world == 1:
+        if a.ppl_ref and rank == 0:      # the single-GPU torch port on the full weights (rank 0; the others wait below)
             import llama_port as LP
             bc = LP.BlockCfg(cfg.hidden_size, cfg.intermediate_size, cfg.num_attention_heads,
                              cfg.num_key_value_heads, cfg.rms_norm_eps, cfg.rope_theta, a.wbits, a.group, a.abits)
@@ -106,6 +106,8 @@ def run(a, dev, rank=0, world=1):
                                "delta_ppl_at_wikitext2_scale(6.1)": 6.1 * (ppl - ppl_r) / ppl_r})
             del blocks
             torch.cuda.empty_cache()
+        if world > 1:
+            dist.barrier()
         for l in model.layers:
             l.self_attn.fast_attention = True
     # ---- prefill tokens/s ----

@@ -1,4 +1,4 @@
-"""torchrun --nproc-per-node N tools/test_peer_allreduce.py -- K7 (one-shot all-reduce over peer memory) against an
+"""torchrun --nproc-per-node N tools/peer_allreduce_check.py -- K7 (one-shot all-reduce over peer memory) against an
 fp32 reference built from an all-gather, eager and inside a CUDA graph, plus latency next to NCCL."""
 import os, sys
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "llama3-quantization_b200"))
