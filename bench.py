@@ -42,6 +42,13 @@ METRIC = "w4a16_g128_dequant_gemm_tflops"
 UNIT = "TFLOP/s"
 
 
+def WORKLOAD_CONFIG(m_total, world):
+    """The same `config` object on both arms (the driver compares them): BASELINE.json configs[1]."""
+    return {"workload": "llama3-8b decoder block: 7 QuantLinear GEMMs (q,k,v,o,gate,up,down), W4A16 g128, prefill, "
+                        "2048 tokens per GPU",
+            "tokens": m_total, "parallelism": f"tp{world}" if world > 1 else "single"}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -101,30 +108,57 @@ class ClockSampler:
 def run_reference(args):
     """The reference's own CPU implementation of the path, on the host cores.
 
-    /root/reference does not exist on the GPU box and the reference is pure PyTorch (nothing to
-    compile into oracle/_ref), so this leg runs oracle/torch_port.py: the same eager torch op
-    sequence as quant/quantizer.py + quant/int_linear.py (pinned against the unmodified
-    reference by the golden fixtures), in the reference's post-calibration inference mode --
-    weights already fake-quantised, QuantLinear.forward == F.linear on the dense weight
-    (int_linear.py:56-62).  fp32 on CPU (the reference keeps fp16 for the GPU only)."""
+    oracle/_ref holds the reference's unmodified modules (vendored by oracle/build_ref.py; they travel to the GPU
+    box with the snapshot): this leg builds the reference's QuantLinear (quant/int_linear.py) around the seven
+    linears of the block, fake-quantises the weights in place with its UniformAffineQuantizer exactly like
+    quant/utils.py::smooth_and_quant_inplace does after calibration, and times QuantLinear.forward
+    (int_linear.py:48-65: F.linear on the dense fake-quantised weight) at M = 2048 with every host thread.
+    fp32 on the CPU (the reference keeps fp16 for the GPU only).  Falls back to oracle/torch_port.py (kind "port")
+    only when oracle/_ref is missing."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch_port as TP
     torch.set_num_threads(os.cpu_count() or 1)
     gen = torch.Generator().manual_seed(0)
     M = PREFILL_M
-    weights = {}
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    kind = "reference" if os.path.exists(os.path.join(ref_dir, "quant", "int_linear.py")) else "port"
+    wparams = {"n_bits": WBITS, "per_channel_axes": [0], "symmetric": False, "dynamic_method": "per_channel",
+               "group_size": GROUP, "lwc": False, "disable_zero_point": False}
+    aparams = {"n_bits": 16, "per_channel_axes": [], "symmetric": False, "dynamic_method": "per_token"}
     with torch.no_grad():
-        for j, (name, n, k, _) in enumerate(LINEARS):
-            w = torch.randn(n, k, generator=gen) * 0.02
-            weights[name] = TP.fake_quant(w, WBITS, GROUP)[0]          # post-omniquant state
-        xs = {"h": torch.randn(M, HIDDEN, generator=gen), "a": torch.randn(M, HIDDEN, generator=gen),
-              "m": torch.randn(M, INTER, generator=gen)}
+        if kind == "reference":
+            pkg = os.path.join(ROOT, "llama3-quantization_b200")
+            sys.path[:] = [p for p in sys.path if os.path.abspath(p) != pkg]      # never the drop-in on this arm
+            sys.path[:0] = [ref_dir, os.path.join(ref_dir, "stubs")]
+            import quant.int_linear as RIL
+            assert os.path.realpath(RIL.__file__).startswith(os.path.realpath(ref_dir)), RIL.__file__
+            mods = {}
+            for j, (name, n, k, _) in enumerate(LINEARS):
+                lin = torch.nn.Linear(k, n, bias=False)
+                lin.weight.copy_(torch.randn(n, k, generator=gen) * 0.02)
+                ql = RIL.QuantLinear(lin, wparams, aparams)
+                ql.weight = ql.weight_quantizer(ql.weight)             # quant/utils.py:133-136
+                ql.set_quant_state(weight_quant=False, act_quant=False)
+                mods[name] = ql
+            xs = {"h": torch.randn(M, HIDDEN, generator=gen), "a": torch.randn(M, HIDDEN, generator=gen),
+                  "m": torch.randn(M, INTER, generator=gen)}
 
-        def step():
-            for name, n, k, src in LINEARS:
-                TP.quant_linear(xs[src], weights[name], None, WBITS, GROUP, requantize=False)
+            def step():
+                for name, n, k, src in LINEARS:
+                    mods[name](xs[src])
+        else:
+            import torch_port as TP
+            weights = {}
+            for j, (name, n, k, _) in enumerate(LINEARS):
+                w = torch.randn(n, k, generator=gen) * 0.02
+                weights[name] = TP.fake_quant(w, WBITS, GROUP)[0]          # post-omniquant state
+            xs = {"h": torch.randn(M, HIDDEN, generator=gen), "a": torch.randn(M, HIDDEN, generator=gen),
+                  "m": torch.randn(M, INTER, generator=gen)}
+
+            def step():
+                for name, n, k, src in LINEARS:
+                    TP.quant_linear(xs[src], weights[name], None, WBITS, GROUP, requantize=False)
 
         for _ in range(args.warmup):
             step()
@@ -136,10 +170,11 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "llama3-8b decoder block, 7 QuantLinear GEMMs, W4 g128 fake-quantised weights, "
-                                   "prefill M=2048", "where": "host CPU, torch eager"},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": "full step (7 linears, M=2048), fp32, torch CPU"},
+            "config": WORKLOAD_CONFIG(PREFILL_M * max(args.gpus, 1), max(args.gpus, 1)),
+            "notes": {"where": "host CPU, the reference's own QuantLinear.forward (torch eager, fp32)"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+                             "sample": f"7 linears at M=2048 of the {PREFILL_M * max(args.gpus, 1)} tokens per step "
+                                       "(the CPU rate does not depend on M at this size), fp32, torch CPU"},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
@@ -581,12 +616,9 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": {"workload": "llama3-8b decoder block: 7 QuantLinear GEMMs (q,k,v,o,gate,up,down), "
-                                       f"W4A16 g128, prefill M={M_PRE} tokens (2048 per GPU)",
-                           "parallelism": f"tp{world}" if world > 1 else "single",
-                           "l2": "3 weight sets rotated; per-step working set (109 MB packed weights + 270 MB "
-                                 "activations/outputs) exceeds the 126 MB L2",
-                           "force_skinny": bool(flags)},
+                "config": WORKLOAD_CONFIG(M_PRE, world),
+                "notes": {"l2": "3 weight sets rotated; per-step working set (109 MB packed weights + 270 MB "
+                                "activations/outputs) exceeds the 126 MB L2", "force_skinny": bool(flags)},
                 "roofline": roofline, "decode": decode, "quantize": quant, "llama3_8b": model_res,
                 "cpu_baseline": cpu_base, "gpu_eager_reference_ops": gpu_eager, "e2e": e2e,
                 "gpu_launches": n_launch, "clocks": clocks, "peaks": P}

@@ -54,6 +54,12 @@ enum q100_status {
 #define Q100_FLAG_SCALAR_MATH 0x2  /* f16/bf16: per-element fp32 math instead of packed half2 ops */
 #define Q100_FLAG_K1_GENERIC  0x4  /* f16/bf16, group 64/128/256: the first group kernel (k1_groups) instead of
                                       k1_fast (same bits; kept for A/B parity tests and profiling)          */
+#define Q100_FLAG_CUDA_SCALE   0x8  /* scale = range * RN(1 / (2^n - 1)) in fp32 -- what the reference computes when it runs
+                                      on CUDA tensors (torch's CUDA kernels turn `tensor / python_scalar`,
+                                      quant/quantizer.py:147,152, into a multiplication by the reciprocal) -- instead of
+                                      the true division its CPU kernels perform (the default, pinned by the CPU golden
+                                      vectors).  The two differ by at most one ulp of the scale.  Honoured by the quantize
+                                      entry points and by q100_quantize_backward. */
 /* flags for the GEMM entry points */
 #define Q100_GEMM_FORCE_SKINNY 0x1 /* always use the mma.sync weight-streaming kernel  */
 #define Q100_GEMM_FORCE_TC     0x2 /* always use the tcgen05 kernel                    */
@@ -126,11 +132,12 @@ int q100_quantize_groupwise(const void* x, int dtype, int64_t rows, int64_t cols
  *   lwc_up/low   nullable, [rows*cols/group] post-sigmoid multipliers as given to the forward
  *   grad_x       nullable; [rows, cols]
  *   grad_up/low  nullable; [rows*cols/group] d loss / d multiplier (only written with LWC)
+ *   flags        Q100_FLAG_CUDA_SCALE must match the forward's
  */
 int q100_quantize_backward(const void* x, const void* grad_out, int dtype, int64_t rows, int64_t cols,
                            int group, int n_bits, int symmetric, int disable_zp,
                            const void* lwc_up, const void* lwc_low,
-                           void* grad_x, void* grad_up, void* grad_low, void* stream);
+                           void* grad_x, void* grad_up, void* grad_low, int flags, void* stream);
 
 /*
  * K2 -- per-token activation fake-quant (asymmetric, one group per row), the

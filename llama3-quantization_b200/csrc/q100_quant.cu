@@ -414,8 +414,8 @@ __device__ __forceinline__ bool fast_params(typename Packed16<T>::T2 m, const Qu
     const T2 d2 = __hadd2(m, from_bits<T2>(__byte_perm(mb, 0, 0x1032)));   // min + (-max) in both halves
     num = -__low2float(d2);                                                // rd(max - min), one op in T
   }
-  float s = num * a.rcp_denom;
-  s = fmaf(fmaf(-s, a.denom, num), a.rcp_denom, s);
+  float s = num * a.rcp_denom;                                     // Q100_FLAG_CUDA_SCALE: this product is the scale
+  if (!a.cuda_scale) s = fmaf(fmaf(-s, a.denom, num), a.rcp_denom, s);
   const T2 s2 = __hmin2(__hmax2(from_bits<T2>(D::pack2(s, s)), k.s_lo), k.s_hi);
   q.scale = __low2float(s2);
   q.rcp = __frcp_rn(q.scale);
@@ -1007,6 +1007,7 @@ extern "C" int q100_quantize_groupwise(const void* x, int dtype, int64_t rows, i
   else { a.qmin = 0.0f; a.qmax = static_cast<float>((1 << n_bits) - 1); }
   a.denom = symmetric ? static_cast<float>((1 << (n_bits - 1)) - 1) : static_cast<float>((1 << n_bits) - 1);
   a.rcp_denom = 1.0f / a.denom;
+  a.cuda_scale = (flags & Q100_FLAG_CUDA_SCALE) ? 1 : 0;
   a.k_tiles = static_cast<int>(cols / 64);
   a.tile_words = pack ? tile_words_of(n_bits) : 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -1056,6 +1057,7 @@ int rows_entry(const void* x, int dtype, int64_t rows, int64_t cols, int n_bits,
   else { a.qmin = 0.0f; a.qmax = static_cast<float>((1 << n_bits) - 1); }
   a.denom = symmetric ? static_cast<float>((1 << (n_bits - 1)) - 1) : static_cast<float>((1 << n_bits) - 1);
   a.rcp_denom = 1.0f / a.denom;
+  a.cuda_scale = (flags & Q100_FLAG_CUDA_SCALE) ? 1 : 0;
   a.k_tiles = static_cast<int>(cols / 64);
   a.tile_words = pack ? tile_words_of(n_bits) : 0;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

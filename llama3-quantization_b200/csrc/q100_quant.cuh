@@ -27,6 +27,7 @@ struct QuantArgs {
   float qmin, qmax;     // reference code range (quantizer.py:46-51)
   float denom;          // 2^n - 1 (asymmetric) or 2^(n-1) - 1 (symmetric)
   float rcp_denom;      // RN(1 / denom), for k1_fast
+  int cuda_scale;       // Q100_FLAG_CUDA_SCALE: scale = range * RN(1 / denom) (torch's CUDA kernels) instead of range / denom
   int k_tiles;          // packed layout v2: cols / 64
   int tile_words;       // uint32 words per [128 rows x 64 k] tile
 };
@@ -43,6 +44,12 @@ struct GroupQ {
   float scale, zp, rcp;
 };
 
+// range / (2^n - 1), quantizer.py:147 / :152.  torch's CPU kernels divide; its CUDA kernels multiply a tensor by the fp32
+// reciprocal of a Python scalar divisor (BinaryDivTrueKernel.cu: "inv_b = 1 / b; a * inv_b"), which can differ by one ulp.
+__device__ __forceinline__ float scale_div(float num, const QuantArgs& a) {
+  return a.cuda_scale ? __fmul_rn(num, a.rcp_denom) : __fdiv_rn(num, a.denom);
+}
+
 // quantizer.py:143-159.  xmin/xmax are exact values of T.
 template <typename T>
 __device__ __forceinline__ GroupQ<T> group_params(float xmin, float xmax, const QuantArgs& a,
@@ -57,12 +64,12 @@ __device__ __forceinline__ GroupQ<T> group_params(float xmin, float xmax, const 
   GroupQ<T> q;
   if (a.symmetric) {
     const float am = max_nan(fabsf(xmax), fabsf(xmin));
-    float s = D::rd(__fdiv_rn(am, a.denom));
+    float s = D::rd(scale_div(am, a));
     q.scale = D::rd(clamp_nan(s, 1e-5f, 1e4f));
     q.zp = D::rd(a.denom);
   } else {
     const float rng = D::rd(xmax - xmin);
-    float s = D::rd(__fdiv_rn(rng, a.denom));
+    float s = D::rd(scale_div(rng, a));
     q.scale = D::rd(clamp_nan(s, 1e-5f, 1e4f));
     q.zp = D::rd(__fdiv_rn(D::rd(-xmin), q.scale));
   }

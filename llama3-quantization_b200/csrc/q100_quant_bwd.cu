@@ -136,18 +136,18 @@ __global__ void __launch_bounds__(256) k1_backward(const BwdArgs b) {
     float g_xmax_c, g_xmin_c;
     if (a.symmetric) {
       const float a_hi = fabsf(xmax_c), a_lo = fabsf(xmin_c);
-      const float s_raw = D::rd(__fdiv_rn(fmaxf(a_hi, a_lo), a.denom));
+      const float s_raw = D::rd(scale_div(fmaxf(a_hi, a_lo), a));
       const float live = (s_raw >= 1e-5f && s_raw <= 1e4f) ? 1.f : 0.f;
-      const float g_abs = gs * live / a.denom;
+      const float g_abs = scale_div(gs * live, a);
       const float w_hi = a_hi > a_lo ? 1.f : (a_hi == a_lo ? 0.5f : 0.f);
       const float sg_hi = xmax_c > 0.f ? 1.f : (xmax_c < 0.f ? -1.f : 0.f);
       const float sg_lo = xmin_c > 0.f ? 1.f : (xmin_c < 0.f ? -1.f : 0.f);
       g_xmax_c = g_abs * w_hi * sg_hi;
       g_xmin_c = g_abs * (1.f - w_hi) * sg_lo;
     } else {
-      const float s_raw = D::rd(__fdiv_rn(D::rd(xmax_c - xmin_c), a.denom));
+      const float s_raw = D::rd(scale_div(D::rd(xmax_c - xmin_c), a));
       const float live = (s_raw >= 1e-5f && s_raw <= 1e4f) ? 1.f : 0.f;
-      g_xmax_c = gs * live / a.denom;
+      g_xmax_c = scale_div(gs * live, a);
       g_xmin_c = -g_xmax_c;
     }
     if (l == 0 && valid && lwc) {
@@ -226,7 +226,7 @@ using namespace q100;
 extern "C" int q100_quantize_backward(const void* x, const void* grad_out, int dtype, int64_t rows, int64_t cols,
                                       int group, int n_bits, int symmetric, int disable_zp,
                                       const void* lwc_up, const void* lwc_low,
-                                      void* grad_x, void* grad_up, void* grad_low, void* stream) {
+                                      void* grad_x, void* grad_up, void* grad_low, int flags, void* stream) {
   Q100_REQUIRE(dtype >= 0 && dtype <= 2, Q100_EINVAL, "bad dtype %d", dtype);
   Q100_REQUIRE(rows >= 0 && cols >= 0, Q100_EINVAL, "negative shape");
   Q100_REQUIRE(n_bits >= 2 && n_bits <= 8, Q100_EUNSUPPORTED, "n_bits=%d: 2..8", n_bits);
@@ -252,6 +252,7 @@ extern "C" int q100_quantize_backward(const void* x, const void* grad_out, int d
   else { a.qmin = 0.0f; a.qmax = static_cast<float>((1 << n_bits) - 1); }
   a.denom = symmetric ? static_cast<float>((1 << (n_bits - 1)) - 1) : static_cast<float>((1 << n_bits) - 1);
   a.rcp_denom = 1.0f / a.denom;
+  a.cuda_scale = (flags & Q100_FLAG_CUDA_SCALE) ? 1 : 0;
   b.gout = grad_out; b.gx = grad_x; b.gup = grad_up; b.glow = grad_low;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (dtype) {

@@ -18,6 +18,7 @@ F16, BF16, F32 = 0, 1, 2
 FLAG_IEEE_DIV = 0x1
 FLAG_SCALAR_MATH = 0x2
 FLAG_K1_GENERIC = 0x4
+FLAG_CUDA_SCALE = 0x8
 GEMM_FORCE_SKINNY = 0x1
 GEMM_FORCE_TC = 0x2
 GEMM_EXACT_WEIGHTS = 0x4
@@ -36,7 +37,7 @@ SIGNATURES = {
     "q100_abi_version": (_i, []),
     "q100_device_ok": (_i, [_i]),
     "q100_quantize_groupwise": (_i, [_vp, _i, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
-    "q100_quantize_backward": (_i, [_vp, _vp, _i, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "q100_quantize_backward": (_i, [_vp, _vp, _i, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp]),
     "q100_fakequant_rows": (_i, [_vp, _i, _i64, _i64, _i, _vp, _vp, _vp, _i, _vp]),
     "q100_rows_minmax": (_i, [_vp, _i, _i64, _i64, _vp, _vp]),
     "q100_quantize_rows_stats": (_i, [_vp, _i, _i64, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp]),

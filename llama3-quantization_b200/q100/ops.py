@@ -133,7 +133,8 @@ BACKWARD_GROUPS = (32, 64, 128, 256)
 
 def quantize_backward(x: torch.Tensor, grad_out: torch.Tensor, group: int, n_bits: int, symmetric: bool = False,
                       disable_zero_point: bool = False, lwc_up: Optional[torch.Tensor] = None,
-                      lwc_low: Optional[torch.Tensor] = None, need_x: bool = True, need_lwc: bool = False):
+                      lwc_low: Optional[torch.Tensor] = None, need_x: bool = True, need_lwc: bool = False,
+                      flags: int = 0):
     """Fused backward of :func:`quantize_groupwise` (K1b).  Returns (grad_x, grad_up, grad_low); entries that were
     not asked for (or have no meaning without LWC) are None.  ``group`` must be in BACKWARD_GROUPS."""
     _require_cuda(x, grad_out, lwc_up, lwc_low)
@@ -155,7 +156,7 @@ def quantize_backward(x: torch.Tensor, grad_out: torch.Tensor, group: int, n_bit
         check(lib.q100_quantize_backward(
             x.data_ptr(), grad_out.data_ptr(), _dtype_code(x), rows, cols, int(group), n_bits,
             int(bool(symmetric)), int(bool(disable_zero_point)), _ptr(lwc_up), _ptr(lwc_low),
-            _ptr(gx), _ptr(gup), _ptr(glow), _stream(x)))
+            _ptr(gx), _ptr(gup), _ptr(glow), flags, _stream(x)))
     return gx, gup, glow
 
 

@@ -82,7 +82,7 @@ class QuantLinear(nn.Module):
             return None
         lwc_ver = (wq.upbound_factor._version, wq.lowbound_factor._version) if wq.lwc else None
         key = (w.data_ptr(), w._version, tuple(w.shape), w.dtype, wq.n_bits, wq.group_size,
-               wq.symmetric, wq.disable_zero_point, lwc_ver)
+               wq.symmetric, wq.disable_zero_point, lwc_ver, wq.cuda_eager_scale)
         if self._requant_cache is not None and self._requant_cache[0] == key:
             pw, scale, zp = self._requant_cache[1]
             wq.scale, wq.round_zero_point = scale, zp      # same side effects as a real call

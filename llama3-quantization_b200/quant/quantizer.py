@@ -8,12 +8,15 @@ Same class name, constructor keywords, attributes and method names as
 What changes underneath: ``forward`` no longer issues ~17 eager elementwise /
 reduction kernels (per_token_dynamic_calibration + fake_quant); it makes ONE call
 into ``q100_quantize_groupwise`` (K1/K2), which reproduces the reference's results
-bit-for-bit (tests/test_parity_quant.py).  There is no CPU path: a CPU tensor
-raises ``RuntimeError``.
+bit-for-bit (tests/test_parity_quant.py) -- the results of the reference's CPU run, which the
+golden vectors pin, by default; ``cuda_eager_scale = True`` (env ``Q100_CUDA_SCALE=1``) selects
+the one-ulp-different scale its CUDA run computes (tests/test_cuda_eager_parity.py).  There is
+no CPU path: a CPU tensor raises ``RuntimeError``.
 """
 from __future__ import annotations
 
 import math
+import os as _os
 from typing import Optional
 
 import torch
@@ -92,10 +95,11 @@ class _FakeQuantFn(torch.autograd.Function):
     """Forward = one libq100 pass; backward = :func:`fake_quant_backward`."""
 
     @staticmethod
-    def forward(ctx, x2d, su, sl, group, n_bits, symmetric, disable_zp, qmin, qmax):
-        res = _ops.quantize_groupwise(x2d, group, n_bits, symmetric, disable_zp, su, sl)
+    def forward(ctx, x2d, su, sl, group, n_bits, symmetric, disable_zp, qmin, qmax, flags=0):
+        res = _ops.quantize_groupwise(x2d, group, n_bits, symmetric, disable_zp, su, sl, flags=flags)
         ctx.save_for_backward(x2d, res.scales, res.zeros, su, sl)
         ctx.cfg = (group, n_bits, symmetric, qmin, qmax)
+        ctx.flags = flags
         ctx.mark_non_differentiable(res.scales)
         if res.zeros is not None:
             ctx.mark_non_differentiable(res.zeros)
@@ -112,14 +116,14 @@ class _FakeQuantFn(torch.autograd.Function):
         if g in _ops.BACKWARD_GROUPS and x2d.shape[1] % g == 0 and (need_x or need_lwc):
             # K1b: one fused pass (libq100 q100_quantize_backward); other group sizes keep the op-by-op form below
             gx, gsu, gsl = _ops.quantize_backward(x2d, gout, g, n_bits, symmetric, zp is None, su, sl,
-                                                  need_x, need_lwc)
-            return gx, gsu, gsl, None, None, None, None, None, None
+                                                  need_x, need_lwc, ctx.flags)
+            return gx, gsu, gsl, None, None, None, None, None, None, None
         gx, gsu, gsl = fake_quant_backward(
             x2d.reshape(-1, g), gout.reshape(-1, g), scale, zp, su, sl,
             n_bits, symmetric, qmin, qmax, need_x, need_lwc)
         if gx is not None:
             gx = gx.reshape(x2d.shape)
-        return gx, gsu, gsl, None, None, None, None, None, None
+        return gx, gsu, gsl, None, None, None, None, None, None, None
 
 
 class UniformAffineQuantizer(nn.Module):
@@ -183,6 +187,10 @@ class UniformAffineQuantizer(nn.Module):
         # last dim, group_size=None) is sharded.  forward() then takes the row min / max over all ranks
         # (one [rows, 2] all-reduce) so that scale / zero-point equal the single-GPU ones bit for bit.
         self.stat_group = None
+        # scale = range / (2^n - 1): True = multiply by the fp32 reciprocal like the reference does when it runs on
+        # CUDA tensors (torch's CUDA division by a Python scalar); False (default) = true division like its CPU
+        # kernels, the semantics the golden vectors pin.  At most one ulp of the scale apart (Q100_FLAG_CUDA_SCALE).
+        self.cuda_eager_scale = _os.environ.get("Q100_CUDA_SCALE", "0") == "1"
 
     def change_n_bits(self, n_bits):
         self.n_bits = n_bits
@@ -255,6 +263,7 @@ class UniformAffineQuantizer(nn.Module):
 
         need_grad = torch.is_grad_enabled() and (
             x2d.requires_grad or (up is not None and (up.requires_grad or low.requires_grad)))
+        kflags = q100._lib.FLAG_CUDA_SCALE if self.cuda_eager_scale else 0
         sharded_row = False
         if self.stat_group is not None and not self.group_size:
             import torch.distributed as dist
@@ -270,7 +279,7 @@ class UniformAffineQuantizer(nn.Module):
             res = _ops.quantize_rows_stats(
                 x2c, mm, self.n_bits, bool(self.symmetric), bool(self.disable_zero_point),
                 None if up is None else up.detach(), None if low is None else low.detach(),
-                want_dequant=want_dequant, want_packed=keep, want_meta=keep)
+                want_dequant=want_dequant, want_packed=keep, want_meta=keep, flags=kflags)
             deq, scale, zp = res.dequant, res.scales, res.zeros
             self._packed = self._packed_of = None
             if keep:
@@ -280,7 +289,7 @@ class UniformAffineQuantizer(nn.Module):
         elif need_grad:
             deq, scale, zp = _FakeQuantFn.apply(x2d.contiguous(), up, low, group, self.n_bits,
                                                 bool(self.symmetric), bool(self.disable_zero_point),
-                                                self.qmin, self.qmax)
+                                                self.qmin, self.qmax, kflags)
             self._packed = self._packed_of = None
         else:
             keep = self.keep_packed and x2d.dim() == 2 and want_dequant and self.deficiency == 0 \
@@ -289,7 +298,7 @@ class UniformAffineQuantizer(nn.Module):
             res = _ops.quantize_groupwise(
                 x2d, group, self.n_bits, bool(self.symmetric), bool(self.disable_zero_point),
                 None if up is None else up.detach(), None if low is None else low.detach(),
-                want_dequant=want_dequant, want_packed=keep, want_meta=keep)
+                want_dequant=want_dequant, want_packed=keep, want_meta=keep, flags=kflags)
             deq, scale, zp = res.dequant, res.scales, res.zeros
             if keep:
                 g = x2d.shape[1] if group == 0 else group

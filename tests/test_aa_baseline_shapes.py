@@ -6,7 +6,12 @@ decode sizes, every forced kernel that applies.
 Reference contraction: a float64 matmul ON THE GPU of x with the fake-quantised weight the quantize kernel returned
 (the CPU float64 product of a 2048 x 28672 x 8192 case would take minutes); that weight is itself pinned against the
 numpy oracle bit for bit, here for the 8B shapes and in tests/test_parity_quant.py for everything small.  Tolerances
-are the ones stated in tests/test_parity_gemm.py.  The file sorts first so that it is collected before anything slow.
+are the ones stated in tests/test_parity_gemm.py with one addition for the long contractions that only appear here:
+the fp32-accumulator term is max(8, K / 1024) * 2^-24 * sum_k |x_k w_k| -- a K = 28672 chain (70B down_proj) makes
+1792 accumulator updates per output, and the tensor core's accumulator rounding error grows with that count (first
+measured here: 8 of 16.7 M outputs of 70b_down at M = 2048 fell outside the factor-8 bound used for K <= 8192;
+the worst-case bound of any fp32 summation is (K - 1) * 2^-24).
+The file sorts first so that it is collected before anything slow.
 """
 import zlib
 
@@ -62,7 +67,7 @@ def _check(y, x, w64, dtype, exact_weights):
     x64 = x.double()
     ref = x64 @ w64.T
     mag = x64.abs() @ w64.abs().T
-    tol = 2 * EPS_OUT[dtype] * ref.abs() + 8 * 2.0 ** -24 * mag + 1e-7
+    tol = 2 * EPS_OUT[dtype] * ref.abs() + max(8.0, x.shape[-1] / 1024.0) * 2.0 ** -24 * mag + 1e-7
     if not exact_weights:
         tol = tol + 8 * EPS_W[dtype] * torch.sqrt((x64 ** 2) @ (w64 ** 2).T)
     err = (y.double() - ref).abs()
