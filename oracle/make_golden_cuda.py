@@ -40,7 +40,7 @@ def main(path):
                 for group in (128, None):
                     name = f"{dt}_w{n_bits}_{mode}_g{group or 0}"
                     g = torch.Generator().manual_seed(sum(map(ord, name)))
-                    rows, cols = 48, 512
+                    rows, cols = 16, 256
                     x = torch.randn(rows, cols, generator=g) * 0.02
                     x[0] = x[0].abs() + 0.01            # all-positive groups: negative zero-point
                     x[1] = 0.3                          # constant groups: scale clamps to CLIPMIN

@@ -60,7 +60,7 @@ def test_rope_kv_decode_bit_exact(dtype, bsz, heads, kvh, hd):
     assert kc[:, :, :pos].abs().max().item() == 0 and kc[:, :, pos + 1:].abs().max().item() == 0
 
 
-@pytest.mark.parametrize("pos", [-1, 40, 41, 10 ** 6, 30])
+@pytest.mark.parametrize("pos", [-1, 40, 41, 10 ** 6, 35])
 def test_rope_kv_decode_position_outside_cache(pos):
     """A static cache can overflow (the reference's torch.cat cache cannot): K5 must write nothing and raise the flag
     when the device-side position is outside the cache or the rotary table (here: table 32 rows, cache 40 slots)."""
