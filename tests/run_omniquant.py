@@ -62,8 +62,8 @@ def main():
     import quant.quantizer as quantizer_mod
     import quant.omniquant as omniquant_mod
 
-    where = {"int_llama_layer": layer_mod.__file__, "quantizer": quantizer_mod.__file__,
-             "omniquant": omniquant_mod.__file__}
+    where = {"int_llama_layer": os.path.realpath(layer_mod.__file__), "quantizer": os.path.realpath(quantizer_mod.__file__),
+             "omniquant": os.path.realpath(omniquant_mod.__file__)}
     assert os.path.realpath(omniquant_mod.__file__).startswith(os.path.realpath(REF)), where
     if a.impl == "ref":
         assert os.path.realpath(quantizer_mod.__file__).startswith(os.path.realpath(REF)), where

@@ -94,7 +94,10 @@ torch.save({{"x": x.cpu(), "y": y.cpu(), "scale": q.scale.cpu(), "zp": q.round_z
     assert torch.equal(got.scales.cpu().view(-1), ref["scale"].view(-1)), "scale differs from the reference on CUDA"
     assert torch.equal(got.zeros.cpu().view(-1), ref["zp"].view(-1)), "zero-point differs from the reference on CUDA"
     assert np.array_equal(torch_to_bits(got.dequant), torch_to_bits(ref["y"])), "dequant differs from the reference on CUDA"
-    # and how far the default (CPU semantics) is from it: at most one ulp of the scale, a handful of codes
+    # and how far the default (CPU semantics: true division) is from it: never more than one ulp of the scale.  In fp32
+    # most groups ARE one ulp apart (measured on B200: 72 % at W4 -- x / 15 against x * RN(1 / 15)); after the rounding
+    # to 16 bits almost none are.
     d = ops.quantize_groupwise(x, 128, n_bits)
-    frac = float((d.scales.cpu().view(-1) != ref["scale"].view(-1)).float().mean())
-    assert frac < 0.5
+    a, b = d.scales.cpu().view(-1).float(), ref["scale"].view(-1).float()
+    ulp = torch.finfo(TDT[dt]).eps * b.abs()
+    assert bool(((a - b).abs() <= ulp).all())
