@@ -234,6 +234,85 @@ int q100_rope_kv_decode(const void* qkv, const void* cos_cache, const void* sin_
 int q100_silu_mul(const void* gate_up, void* out, int64_t rows, int64_t inter, int dtype, void* stream);
 
 /*
+ * K9 -- the decode chain: ONE persistent launch that runs a list of phases -- the dequant-GEMMs of one or many
+ * decoder blocks at decode shapes (1 <= M <= 16 tokens), with the steps between them folded in -- while the
+ * packed-weight stream keeps running across the phase boundaries.  Per block and token the reference issues
+ * ~45 eager launches for QuantLlamaDecoderLayer.forward (models/int_llama_layer.py:213-262: input_layernorm,
+ * q/k/v_proj, rotary + cache append, softmax(QK^T)V, o_proj, residual add, post_attention_layernorm, gate/up_proj,
+ * act_fn(gate) * up, down_proj, residual add); a chain expresses the same sequence as phases:
+ *
+ *   Q100_PH_GEMM     y = x . dequant(W)^T (+ bias)       quant/int_linear.py:62 on the packed weight
+ *       x_mode   Q100_X_PLAIN    x [M, K]
+ *                Q100_X_GATE_UP  x [M, 2K] = gate | up, the kernel stages act_fn(gate) * up   (int_llama_layer.py:45)
+ *                Q100_X_NORM     x = residual stream h [M, K], the kernel stages norm_weight * (h * rstd)
+ *                                (quant/omni_norm.py:52-63) with rstd from ssq_in: [ssq_in_parts][M] fp32 partial
+ *                                sums of h^2 left by the phase that produced h
+ *       epi_mode Q100_EPI_STORE  y = result
+ *                Q100_EPI_ADD_SSQ y = r(r(result) + residual[M, N]) (int_llama_layer.py:246, 251) and
+ *                                ssq_out[q100_chain_ssq_parts(N)][M] receives the partial sums of y^2
+ *   Q100_PH_ATTN     rotary on q / k of the new token of each sequence, k / v appended to the static cache at the
+ *                    DEVICE-side position, attention of the new token over positions 0..position in fp32 (the
+ *                    decode form of int_llama_layer.py:114-172), flash-decoding partials into att_partials
+ *   Q100_PH_COMBINE  merges the partials into att_out [batch, heads * head_dim] (what o_proj reads)
+ *
+ * Phases run in order; between two phases every CTA passes a grid barrier, so a phase may read what any earlier phase
+ * wrote.  All buffers are the caller's and must stay valid (and at the same addresses) as long as the chain is used.
+ * Same weights, same layouts (packed / meta) as q100_gemm_wna16; group %% 128 == 0; one n_bits / dtype per chain.
+ */
+enum q100_phase_type { Q100_PH_GEMM = 0, Q100_PH_ATTN = 1, Q100_PH_COMBINE = 2 };
+enum q100_x_mode { Q100_X_PLAIN = 0, Q100_X_GATE_UP = 1, Q100_X_NORM = 2 };
+enum q100_epi_mode { Q100_EPI_STORE = 0, Q100_EPI_ADD_SSQ = 1 };
+typedef struct q100_phase {
+  int type;
+  /* Q100_PH_GEMM */
+  const void* x;
+  const void* packed;
+  const void* meta;
+  const void* bias;            /* nullable */
+  void* y;
+  int64_t N, K;
+  int x_mode;
+  const void* norm_weight;     /* [K], X_NORM */
+  const void* ssq_in;          /* fp32 [ssq_in_parts][M], X_NORM */
+  int ssq_in_parts;
+  float eps;
+  int epi_mode;
+  const void* residual;        /* [M, N], EPI_ADD_SSQ */
+  void* ssq_out;               /* fp32 [q100_chain_ssq_parts(N)][M], EPI_ADD_SSQ */
+  /* Q100_PH_ATTN / Q100_PH_COMBINE */
+  const void* qkv;             /* [batch, (heads + 2 kv_heads) * head_dim] */
+  const void* cos_cache;       /* [rope_len, head_dim] */
+  const void* sin_cache;
+  const void* position;        /* device int64 */
+  void* k_cache;               /* [batch, kv_heads, max_len, head_dim] */
+  void* v_cache;
+  void* att_partials;          /* fp32 [q100_chain_attn_partial_floats(batch, heads, max_len)] */
+  void* att_out;               /* [batch, heads * head_dim] */
+  int batch, heads, kv_heads, head_dim;
+  int64_t max_len, rope_len;
+} q100_phase;
+
+size_t q100_chain_desc_bytes(int n_phases);
+int64_t q100_chain_ssq_parts(int64_t N);
+int64_t q100_chain_attn_partial_floats(int batch, int heads, int64_t max_len);
+/*
+ * q100_chain_build: validates the phases (HOST array), plans the stream-K split of every GEMM for the persistent
+ *   grid and writes the device-side descriptor into `desc` (>= q100_chain_desc_bytes(n_phases) bytes of device
+ *   memory, 16-byte aligned).  *workspace_needed receives the scratch size the chain needs; `workspace` must be
+ *   that large, zero-filled once (the kernel leaves it zeroed) and must be the one passed to q100_chain_run.
+ *   Synchronises the stream (one-time set-up; not for use inside a graph capture).
+ * q100_chain_run: one launch; safe to capture in a CUDA graph.  Same M / group / n_bits / dtype as at build time.
+ * q100_chain_error: reads the chain's error word (grid-barrier time-out, position outside the KV cache);
+ *   synchronises the stream.
+ */
+int q100_chain_build(const q100_phase* phases, int n_phases, int M, int group, int n_bits, int disable_zp,
+                     int dtype, void* desc, size_t desc_bytes, void* workspace, size_t workspace_bytes,
+                     size_t* workspace_needed, void* stream);
+int q100_chain_run(void* desc, int n_phases, int M, int group, int n_bits, int disable_zp, int dtype,
+                   void* workspace, void* stream);
+int q100_chain_error(const void* desc, void* stream);
+
+/*
  * K7 -- one-shot all-reduce(sum) of a small tensor over peer memory (NVLink): the collective after a
  * row-parallel linear (o_proj, down_proj) at decode shapes, where NCCL's all-reduce is latency-bound
  * (the reference has no counterpart -- it places layers, parallel_utils.py:89-163).

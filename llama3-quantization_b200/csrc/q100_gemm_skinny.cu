@@ -35,10 +35,15 @@
 // k = 32t + 4s + {0,1,2,3}.  The contraction is invariant under that permutation because
 // A and B fragments use the same one.
 #include <mutex>
+#include <type_traits>
 #include <unordered_map>
+#include <vector>
+#include <cstring>
+#include <cmath>
 
 #include "q100_common.cuh"
 #include "q100_ptx.cuh"
+#include "q100_chain.cuh"
 
 namespace q100 {
 
@@ -57,29 +62,6 @@ constexpr int SK_MAX_SPLIT = 4;    // contributors per tile the stream-K split a
 constexpr int SK_SPLIT_UNITS = 8;  // ... as long as that keeps a CTA at or below this many blocks
 constexpr int SK_XPITCH = 320;     // bytes per (m, 128-k) x row in smem: 256 + 64 pad (conflict-free LDS.128)
 
-struct SkinnyArgs {
-  const void* x;          // [M, K] T
-  const void* packed;     // tile-major packed codes (layout v2)
-  const void* meta;       // [K/group, N, 2] T
-  const void* bias;       // [N] T or null
-  void* y;                // [M, N] T
-  uint2* ws_partials;     // workspace: fp32 partial fragments as {value, flag} pairs (all zero between launches)
-  int M, N, K, group;
-  int kblocks;            // K / 128 = stream-K units per tile
-  int n_tiles;
-  int total_units;        // n_tiles * kblocks
-  int max_slots;
-  int has_zp;
-  float qmin;
-  int post;               // 1: magic-form operand + fp32 group scaling (group % 128 == 0)
-  int m_rows;             // rows of x kept in shared memory (= M)
-  int chunk;              // k blocks of x staged per round
-  int stages;             // ring depth
-  int nsub;               // (scale, zero) rows per block: 128 / group for group < 128, else 1
-  int pdl;                // launch with programmatic stream serialization
-  int seq;                // launch sequence number (timing builds)
-  int x_gate_up;          // x is [M, 2K] = gate | up: stage act_fn(gate) * up (K6's arithmetic)
-};
 
 // One [128 rows x 64 k] tile of codes; a block = two tiles.  In shared memory the second tile is placed
 // kPad bytes past a multiple of 128 so that the eight lanes of an LDS phase (two rows x four k-quarters)
@@ -302,6 +284,19 @@ __device__ __noinline__ uint4 silu_mul8(const uint4& g, const uint4& u) {   // o
   }
   return make_uint4(ow[0], ow[1], ow[2], ow[3]);
 }
+// weight * (h * rstd) for eight elements: both products in fp32, one rounding to T (k4_add_rmsnorm, q100_block.cu)
+template <typename T>
+__device__ __noinline__ uint4 norm8(const uint4& h, const uint4& w, float rstd) {
+  using D = DT<T>;
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, ww[4] = {w.x, w.y, w.z, w.w};
+  uint32_t ow[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = D::to_f2(hw[j]), g = D::to_f2(ww[j]);
+    ow[j] = D::pack2(__fmul_rn(g.x, __fmul_rn(f.x, rstd)), __fmul_rn(g.y, __fmul_rn(f.y, rstd)));
+  }
+  return make_uint4(ow[0], ow[1], ow[2], ow[3]);
+}
 // mbarrier wait without bookkeeping instructions in the retry path (try_wait suspends in hardware)
 __device__ __forceinline__ void mbar_arrive_u32(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
@@ -355,9 +350,16 @@ __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u6
 // (two LOP3 + one shift per eight codes instead of five ALU ops) against x in block fixed point -- three signed
 // 8-bit limbs per (token, 128-k block), one mma column each, MB = ceil(3 M / 8) column groups.  The integer
 // contraction is exact; x is rounded once to 2^-22 of its block maximum (below fp32 accumulation noise).
-template <typename T, int NBITS, int MB, int MODE>
-__global__ void __launch_bounds__(SK_THREADS, MB <= 1 ? SK_OCC : 2)
-k3_skinny(const SkinnyArgs a) {
+struct RingPos { uint32_t soff, boff; int sleft; uint32_t ph; };   // consumer position in the weight ring
+
+// The consumer warps' share of ONE dequant-GEMM: stage x, pull landed blocks out of the ring, contract, write y or
+// hand the fragment to the stream-K fix-up.  Inlined into k3_skinny; k3_chain calls it once per GEMM phase through
+// consumer_gemm_call (not inlined there: its register allocation stays what it is in k3_skinny, the chain's own state
+// is saved around the call instead of competing with the inner loop -- inlined, the loop spilled 26 values per block).
+template <typename T, int NBITS, int MB, int MODE, bool CHAIN>
+__device__ __forceinline__ void consumer_gemm(const SkinnyArgs& a, const int G, const uint32_t ring_u32, uint8_t* ring_ptr,
+                                              const uint32_t full_base, const uint32_t empty_base,
+                                              const float* s_rstd, RingPos& rp) {
   using T2 = typename DQ<T>::T2;
   constexpr bool POST = MODE == 1;
   constexpr bool IMMA = MODE == 2;
@@ -365,102 +367,16 @@ k3_skinny(const SkinnyArgs a) {
   constexpr bool kConvX = POST && DT<T>::kCode == Q100_BF16;    // bf16 activations -> scaled fp16 at staging
   constexpr bool LOHI = POST && UseLoHi<NBITS>::value;
   using DQM = DQ<__half>;                                        // magic constants of the POST path
-  constexpr int kTileB = WGeom<NBITS>::kTileBytes;
-  constexpr int kBlkB = 2 * kTileB;                   // one [128 rows x 128 k] block of codes in HBM
   constexpr int FRAG = SK_ROWS * MB * 8;              // floats per partial tile
-
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  __shared__ uint64_t full_bar[SK_MAX_STAGES], empty_bar[SK_MAX_STAGES];
-  const uint32_t ring_u32 = (smem_u32(smem_raw) + 127u) & ~127u;
-  uint8_t* ring_ptr = smem_raw + (ring_u32 - smem_u32(smem_raw));
   const int stage_pitch = (stage_bytes<NBITS>(a.nsub) + 127) & ~127;
   const int stages = a.stages;
-
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int G = gridDim.x, U = a.total_units;
   const int cta = blockIdx.x;
-#ifdef SK_TIMING
-  if (tid == 0 && cta < 512) g_sk_w[a.seq & 15][cta][0] = gtime();
-#endif
+  const int U = a.total_units;
   const int q_begin = static_cast<int>(static_cast<int64_t>(cta) * U / G);
   const int q_end = static_cast<int>(static_cast<int64_t>(cta + 1) * U / G);
   const int kblocks = a.kblocks;
-
-  if (tid == 0) {
-    for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], SK_CWARPS); }
-    fence_mbar_init();
-  }
-  __syncthreads();
-  pdl_launch_dependents();
-
-  if (warp == SK_CWARPS) {
-    // ===================== producer: codes + side band of blocks [q_begin, q_end) =====================
-    // (static data: no griddepcontrol.wait on this path).  One lane per bulk copy of a stage -- lane 0/1
-    // the two code tiles, lanes 2.. the (scale, zero) rows -- each with its own incrementally updated
-    // source pointer, so that issuing a stage costs the warp a couple of dozen instructions.
-    if (lane < 2 + a.nsub) {
-      const uint64_t pol = policy_evict_first();
-      const bool is_code = lane < 2;
-      const int sub = lane - 2;
-      const int esz2 = 2 * static_cast<int>(sizeof(T));
-      const int64_t mrow_pitch = static_cast<int64_t>(a.N) * esz2;
-      const int gdiv = a.group >= SK_KB ? min(a.group / SK_KB, kblocks) : 1;     // k blocks per side-band row
-      const int64_t mstep = a.group >= SK_KB ? mrow_pitch : a.nsub * mrow_pitch;    // advance every gdiv blocks
-      int tile = q_begin / kblocks, kblk = q_begin - tile * kblocks;
-      const uint8_t* mtile = reinterpret_cast<const uint8_t*>(a.meta) + static_cast<int64_t>(tile) * SK_ROWS * esz2;
-      const uint8_t* src;
-      uint32_t dst_off, bytes;
-      int gleft = gdiv - kblk % gdiv;                 // blocks until the side-band row changes
-      int mbytes = min(SK_ROWS, a.N - tile * SK_ROWS) * esz2;
-      if (is_code) {
-        src = reinterpret_cast<const uint8_t*>(a.packed) + static_cast<int64_t>(q_begin) * kBlkB + lane * kTileB;
-        dst_off = lane * WGeom<NBITS>::kTileStride;
-        bytes = kTileB;
-      } else {
-        const int kg = a.group >= SK_KB ? kblk / gdiv : kblk * a.nsub + sub;
-        src = mtile + kg * mrow_pitch;
-        dst_off = WGeom<NBITS>::kCodeBytes + sub * 512;
-        bytes = mbytes;
-      }
-      uint32_t tx = kBlkB + a.nsub * mbytes;
-      int kleft = kblocks - kblk;                     // blocks until the tile changes
-      uint32_t soff = 0, boff = 0;
-      int sleft = stages;
-      uint32_t ph = 1;                                // parity the producer waits on (slots start free)
-      const uint32_t ring_base = ring_u32 + dst_off;
-      const uint32_t full_u32 = smem_u32(&full_bar[0]), empty_u32 = smem_u32(&empty_bar[0]);
-#ifdef SK_TIMING
-      long long p_wait = 0; const long long p_t0 = clock64();
-#endif
-#pragma unroll 1
-      for (int q = q_begin; q < q_end; ++q) {
-        SK_T(pw0);
-        mbar_wait_tight_u32(empty_u32 + boff, ph);
-#ifdef SK_TIMING
-        p_wait += clock64() - pw0;
-#endif
-        if (lane == 0) mbar_expect_tx_u32(full_u32 + boff, tx);
-        bulk_load_1d_hint_u32(ring_base + soff, src, bytes, full_u32 + boff, pol);
-        soff += stage_pitch; boff += 8;
-        if (--sleft == 0) { sleft = stages; soff = 0; boff = 0; ph ^= 1; }
-        if (is_code) src += kBlkB;
-        else if (--gleft == 0) { gleft = gdiv; src += mstep; }
-        if (--kleft == 0) {                           // next tile
-          kleft = kblocks; ++tile;
-          mtile += SK_ROWS * esz2;
-          mbytes = min(SK_ROWS, a.N - tile * SK_ROWS) * esz2;
-          tx = kBlkB + a.nsub * mbytes;
-          if (!is_code) { src = mtile + (a.group >= SK_KB ? 0 : sub) * mrow_pitch; bytes = mbytes; gleft = gdiv; }
-        }
-      }
-#ifdef SK_TIMING
-      if (lane == 0) { g_sk_t[cta][6] = p_wait; g_sk_t[cta][7] = clock64() - p_t0; }
-#endif
-    }
-    return;
-  }
-
   // ===================== consumers =====================
   const uint32_t xs_u32 = ring_u32 + stages * stage_pitch;
   uint8_t* xs_ptr = ring_ptr + stages * stage_pitch;
@@ -481,7 +397,7 @@ k3_skinny(const SkinnyArgs a) {
   // %tid in every iteration, on the ALU pipe that the extraction needs)
   const uint32_t cbase = reg_const(ring_u32 + coff), chbase = reg_const(ring_u32 + coff_hi);
   const uint32_t mbase_l = reg_const(ring_u32 + moff);
-  const uint32_t full_u32 = reg_const(smem_u32(&full_bar[0])), empty_u32 = reg_const(smem_u32(&empty_bar[0]));
+  const uint32_t full_u32 = reg_const(full_base), empty_u32 = reg_const(empty_base);
 
   // x slab of local blocks [q0, q0 + n): rows m < M only.  The 16-byte chunk c = 4t + j of a block is
   // stored at offset 16t + 64j (conflict-free LDS.128 for the mma B fragments); LOHI additionally swaps
@@ -505,7 +421,19 @@ k3_skinny(const SkinnyArgs a) {
           const int bl = c / per_blk;
           const int rem = c - bl * per_blk;
           const int kblk = (kblk0 + bl) % kblocks;
-          if (a.x_gate_up) {
+          if constexpr (CHAIN) {
+            // x was written by other SMs earlier in this launch: read it through L2 (ld.global.cg), never L1
+            if (a.x_gate_up) {
+              const T* gp = xg + static_cast<int64_t>(rem >> 4) * (2 * a.K) + kblk * SK_KB + (rem & 15) * 8;
+              vq[u] = silu_mul8<T>(__ldcg(reinterpret_cast<const uint4*>(gp)), __ldcg(reinterpret_cast<const uint4*>(gp + a.K)));
+            } else {
+              const int kofs = kblk * SK_KB + (rem & 15) * 8;
+              vq[u] = __ldcg(reinterpret_cast<const uint4*>(xg + static_cast<int64_t>(rem >> 4) * a.K + kofs));
+              if (a.x_norm)       // weight * (h * rstd), both products in fp32, one rounding: K4 / omni_norm.py:52-63
+                vq[u] = norm8<T>(vq[u], *reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(a.norm_w) + kofs),
+                                 s_rstd[rem >> 4]);
+            }
+          } else if (a.x_gate_up) {
             const T* gp = xg + static_cast<int64_t>(rem >> 4) * (2 * a.K) + kblk * SK_KB + (rem & 15) * 8;
             vq[u] = silu_mul8<T>(*reinterpret_cast<const uint4*>(gp), *reinterpret_cast<const uint4*>(gp + a.K));
           } else {
@@ -830,6 +758,20 @@ k3_skinny(const SkinnyArgs a) {
   auto write_fragment = [&](const float (&v)[MB][4], int n0) {
     T* y = reinterpret_cast<T*>(a.y);
     const T* bias = reinterpret_cast<const T*>(a.bias);
+    // chain epilogue (epi_add): h = r(r(acc) + res) is what gets stored, and the warp's 16 rows contribute one
+    // partial sum of h^2 per token to the RMSNorm of the phase that reads h (fixed summation order: deterministic)
+    bool epi_add = false;
+    if constexpr (CHAIN) epi_add = a.epi_add != 0;
+    auto add_res = [&](float o, int m, int n) {
+      const float r = DT<T>::to_f(__ldcg(reinterpret_cast<const T*>(a.res) + static_cast<int64_t>(m) * a.N + n));
+      return DT<T>::rd(__fadd_rn(r, DT<T>::rd(o)));
+    };
+    auto put_ssq = [&](float sq, int m, int n0_) {            // sq: this lane's share for token m; lanes with equal t hold the rows
+      sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+      sq += __shfl_xor_sync(0xffffffffu, sq, 8);
+      sq += __shfl_xor_sync(0xffffffffu, sq, 16);
+      if (g == 0 && m < a.M) a.ssq_out[static_cast<int64_t>((n0_ >> 7) * SK_CWARPS + warp) * a.M + m] = sq;
+    };
     if constexpr (IMMA) {
       // token m = sum of columns 3m, 3m+1, 3m+2 (the limb weights are already in the coefficients); column c
       // lives in lane quarter (c & 7) >> 1, register (c & 1) (+2 for row r1) of column group c >> 3
@@ -844,6 +786,7 @@ k3_skinny(const SkinnyArgs a) {
       }
 #pragma unroll
       for (int m = 0; m < (MB * 8) / 3; ++m) {
+        float sq = 0.f;
         if ((m & 3) == t && m < a.M) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -851,15 +794,28 @@ k3_skinny(const SkinnyArgs a) {
             if (n < a.N) {
               float o = h ? s1[m] : s0[m];
               if (bias) o += DT<T>::to_f(bias[n]);
+              if constexpr (CHAIN) {
+                if (epi_add) { o = add_res(o, m, n); sq = fmaf(o, o, sq); }
+              }
               y[static_cast<int64_t>(m) * a.N + n] = DT<T>::from_f(o);
             }
+          }
+        }
+        if constexpr (CHAIN) {
+          if (epi_add) {                                     // token m lives in lane quarter m & 3: sum over the 8 row lanes
+            sq += __shfl_xor_sync(0xffffffffu, sq, 4);
+            sq += __shfl_xor_sync(0xffffffffu, sq, 8);
+            sq += __shfl_xor_sync(0xffffffffu, sq, 16);
+            if (g == 0 && (m & 3) == t && m < a.M)
+              a.ssq_out[static_cast<int64_t>((n0 >> 7) * SK_CWARPS + warp) * a.M + m] = sq;
           }
         }
       }
       return;
     }
 #pragma unroll
-    for (int mb = 0; mb < MB; ++mb)
+    for (int mb = 0; mb < MB; ++mb) {
+      float sq[2] = {0.f, 0.f};                               // tokens mb*8 + 2t, + 1
 #pragma unroll
       for (int r = 0; r < 4; ++r) {
         const int n = n0 + ((r & 2) ? r1 : r0);
@@ -867,9 +823,16 @@ k3_skinny(const SkinnyArgs a) {
         if (m < a.M && n < a.N) {
           float o = v[mb][r];
           if (bias) o += DT<T>::to_f(bias[n]);
+          if constexpr (CHAIN) {
+            if (epi_add) { o = add_res(o, m, n); sq[r & 1] = fmaf(o, o, sq[r & 1]); }
+          }
           y[static_cast<int64_t>(m) * a.N + n] = DT<T>::from_f(o);
         }
       }
+      if constexpr (CHAIN) {
+        if (epi_add) { put_ssq(sq[0], mb * 8 + 2 * t, n0); put_ssq(sq[1], mb * 8 + 2 * t + 1, n0); }
+      }
+    }
   };
 
   // end of a tile segment [seg_begin, q]: write y or hand the fragment to the stream-K fix-up.
@@ -953,17 +916,17 @@ k3_skinny(const SkinnyArgs a) {
     for (int mb = 0; mb < MB; ++mb) { acc[mb][0] = acc[mb][1] = acc[mb][2] = acc[mb][3] = 0.f; }
   };
 
-  pdl_wait();                                   // x, y and the workspace belong to the stream order
+  if constexpr (!CHAIN) pdl_wait();             // x, y and the workspace belong to the stream order
 #ifdef SK_TIMING
   const long long c_t0 = clock64(); long long c_stage = 0, c_wait = 0, c_fin = 0, c_comp = 0;
   if (tid == 0 && cta < 512) g_sk_w[a.seq & 15][cta][1] = gtime();
 #endif
 
+  uint32_t soff = rp.soff, boff = rp.boff;      // byte offsets of the current stage / its barriers
+  int sleft = rp.sleft;                         // stages until the ring wraps
+  uint32_t ph = rp.ph;
   int seg_begin = q_begin;                      // first block of the current tile segment
   int kb = q_begin % kblocks;                   // block index inside its tile
-  uint32_t soff = 0, boff = 0;                  // byte offsets of the current stage / its barriers
-  int sleft = stages;                           // stages until the ring wraps
-  uint32_t ph = 0;
   for (int qc = q_begin; qc < q_end; qc += a.chunk) {
     const int nblk = min(a.chunk, q_end - qc);
     SK_T(ts0);
@@ -1010,6 +973,7 @@ k3_skinny(const SkinnyArgs a) {
   if (tid == 0 && cta < 512) g_sk_w[a.seq & 15][cta][2] = pend_tile >= 0 ? gtime() : -gtime();
 #endif
   if (pend_tile >= 0) resolve_pending();
+  rp.soff = soff; rp.boff = boff; rp.sleft = sleft; rp.ph = ph;
 #ifdef SK_TIMING
   if (tid == 0 && cta < 512) g_sk_w[a.seq & 15][cta][3] = gtime();
   if (tid == 0) {
@@ -1017,6 +981,229 @@ k3_skinny(const SkinnyArgs a) {
     g_sk_t[cta][4] = c_fin; g_sk_t[cta][5] = q_end - q_begin;
   }
 #endif
+}
+
+template <typename T, int NBITS, int MB, int MODE>
+__device__ __noinline__ void consumer_gemm_call(const SkinnyArgs& a, const int G, const uint32_t ring_u32, uint8_t* ring_ptr,
+                                                const uint32_t full_base, const uint32_t empty_base,
+                                                const float* s_rstd, RingPos& rp) {
+  consumer_gemm<T, NBITS, MB, MODE, true>(a, G, ring_u32, ring_ptr, full_base, empty_base, s_rstd, rp);
+}
+
+
+// CHAIN: the kernel body run over a list of phases (q100_chain.cuh) instead of one GEMM; `a_in` then carries what
+// is common to all GEMM phases (M, group, ring geometry, workspace) and the per-phase arguments come from `ch`.
+template <typename T, int NBITS, int MB, int MODE, bool CHAIN>
+__device__ __forceinline__ void skinny_body(const SkinnyArgs& a_in, const ChainArgs& ch) {
+  using T2 = typename DQ<T>::T2;
+  constexpr bool POST = MODE == 1;
+  constexpr bool IMMA = MODE == 2;
+  constexpr bool kBf16 = MODE == 0 && DT<T>::kCode == Q100_BF16;  // MMA operand type (POST: always fp16)
+  constexpr bool kConvX = POST && DT<T>::kCode == Q100_BF16;    // bf16 activations -> scaled fp16 at staging
+  constexpr bool LOHI = POST && UseLoHi<NBITS>::value;
+  using DQM = DQ<__half>;                                        // magic constants of the POST path
+  constexpr int kTileB = WGeom<NBITS>::kTileBytes;
+  constexpr int kBlkB = 2 * kTileB;                   // one [128 rows x 128 k] block of codes in HBM
+  constexpr int FRAG = SK_ROWS * MB * 8;              // floats per partial tile
+
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  __shared__ uint64_t full_bar[SK_MAX_STAGES], empty_bar[SK_MAX_STAGES];
+  // chain mode: the current phase (copied from global memory by the consumers) and the per-token 1 / rms of x_norm
+  __shared__ typename std::conditional<CHAIN, ChainPhase, int>::type s_ph;
+  __shared__ float s_rstd[CHAIN ? 32 : 1];
+  const SkinnyArgs* ap = &a_in;
+  if constexpr (CHAIN) ap = &s_ph.g;
+  const SkinnyArgs& a = *ap;                          // per-phase arguments (== a_in without CHAIN)
+  const uint32_t ring_u32 = (smem_u32(smem_raw) + 127u) & ~127u;
+  uint8_t* ring_ptr = smem_raw + (ring_u32 - smem_u32(smem_raw));
+  const int stage_pitch = (stage_bytes<NBITS>(a_in.nsub) + 127) & ~127;
+  const int stages = a_in.stages;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  int G = gridDim.x, U = a_in.total_units;            // chain: set per phase (G = the phase's share of the grid)
+  const int cta = blockIdx.x;
+#ifdef SK_TIMING
+  if (tid == 0 && cta < 512) g_sk_w[a_in.seq & 15][cta][0] = gtime();
+#endif
+  int q_begin = static_cast<int>(static_cast<int64_t>(cta) * U / G);
+  int q_end = static_cast<int>(static_cast<int64_t>(cta + 1) * U / G);
+  int kblocks = a_in.kblocks;
+
+  if (tid == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], SK_CWARPS); }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  pdl_launch_dependents();
+
+  if (warp == SK_CWARPS) {
+    // ===================== producer: codes + side band of blocks [q_begin, q_end) =====================
+    // (static data: no griddepcontrol.wait on this path).  One lane per bulk copy of a stage -- lane 0/1
+    // the two code tiles, lanes 2.. the (scale, zero) rows -- each with its own incrementally updated
+    // source pointer, so that issuing a stage costs the warp a couple of dozen instructions.
+    if (lane < 2 + a_in.nsub) {
+      const uint64_t pol = policy_evict_first();
+      const bool is_code = lane < 2;
+      const int sub = lane - 2;
+      const int esz2 = 2 * static_cast<int>(sizeof(T));
+      uint32_t soff = 0, boff = 0;                    // ring position: carried across the phases of a chain
+      int sleft = stages;
+      uint32_t ph = 1;                                // parity the producer waits on (slots start free)
+      const uint32_t full_u32 = smem_u32(&full_bar[0]), empty_u32 = smem_u32(&empty_bar[0]);
+#ifdef SK_TIMING
+      long long p_wait = 0; const long long p_t0 = clock64();
+#endif
+      // codes + side band of blocks [qb, qe) of one GEMM (pa: its arguments, kblk_n = its K / 128)
+      auto produce = [&](const SkinnyArgs& pa, const int kblocks, const int q_begin, const int q_end) {
+      const int64_t mrow_pitch = static_cast<int64_t>(pa.N) * esz2;
+      const int gdiv = pa.group >= SK_KB ? min(pa.group / SK_KB, kblocks) : 1;     // k blocks per side-band row
+      const int64_t mstep = pa.group >= SK_KB ? mrow_pitch : pa.nsub * mrow_pitch;    // advance every gdiv blocks
+      int tile = q_begin / kblocks, kblk = q_begin - tile * kblocks;
+      const uint8_t* mtile = reinterpret_cast<const uint8_t*>(pa.meta) + static_cast<int64_t>(tile) * SK_ROWS * esz2;
+      const uint8_t* src;
+      uint32_t dst_off, bytes;
+      int gleft = gdiv - kblk % gdiv;                 // blocks until the side-band row changes
+      int mbytes = min(SK_ROWS, pa.N - tile * SK_ROWS) * esz2;
+      if (is_code) {
+        src = reinterpret_cast<const uint8_t*>(pa.packed) + static_cast<int64_t>(q_begin) * kBlkB + lane * kTileB;
+        dst_off = lane * WGeom<NBITS>::kTileStride;
+        bytes = kTileB;
+      } else {
+        const int kg = pa.group >= SK_KB ? kblk / gdiv : kblk * pa.nsub + sub;
+        src = mtile + kg * mrow_pitch;
+        dst_off = WGeom<NBITS>::kCodeBytes + sub * 512;
+        bytes = mbytes;
+      }
+      uint32_t tx = kBlkB + pa.nsub * mbytes;
+      int kleft = kblocks - kblk;                     // blocks until the tile changes
+      const uint32_t ring_base = ring_u32 + dst_off;
+#pragma unroll 1
+      for (int q = q_begin; q < q_end; ++q) {
+        SK_T(pw0);
+        mbar_wait_tight_u32(empty_u32 + boff, ph);
+#ifdef SK_TIMING
+        p_wait += clock64() - pw0;
+#endif
+        if (lane == 0) mbar_expect_tx_u32(full_u32 + boff, tx);
+        bulk_load_1d_hint_u32(ring_base + soff, src, bytes, full_u32 + boff, pol);
+        soff += stage_pitch; boff += 8;
+        if (--sleft == 0) { sleft = stages; soff = 0; boff = 0; ph ^= 1; }
+        if (is_code) src += kBlkB;
+        else if (--gleft == 0) { gleft = gdiv; src += mstep; }
+        if (--kleft == 0) {                           // next tile
+          kleft = kblocks; ++tile;
+          mtile += SK_ROWS * esz2;
+          mbytes = min(SK_ROWS, pa.N - tile * SK_ROWS) * esz2;
+          tx = kBlkB + pa.nsub * mbytes;
+          if (!is_code) { src = mtile + (pa.group >= SK_KB ? 0 : sub) * mrow_pitch; bytes = mbytes; gleft = gdiv; }
+        }
+      }
+      };
+      if constexpr (CHAIN) {
+        // the weights of every phase are static: the producer never waits at a phase boundary, it is only ever
+        // held back by the depth of the ring
+        for (int p = 0; p < ch.n_phases; ++p) {
+          const ChainPhase* php = ch.phases + p;
+          if (php->type != PH_GEMM) continue;
+          const int gp = php->grid_p;
+          if (cta >= gp) continue;
+          const int u = php->g.total_units;
+          produce(php->g, php->g.kblocks, static_cast<int>(static_cast<int64_t>(cta) * u / gp),
+                  static_cast<int>(static_cast<int64_t>(cta + 1) * u / gp));
+        }
+      } else {
+        produce(a_in, kblocks, q_begin, q_end);
+      }
+#ifdef SK_TIMING
+      if (lane == 0) { g_sk_t[cta][6] = p_wait; g_sk_t[cta][7] = clock64() - p_t0; }
+#endif
+    }
+    return;
+  }
+
+  RingPos rp{0u, 0u, stages, 0u};
+  if constexpr (CHAIN) {
+    pdl_wait();
+    // grid barrier between phases: every CTA of the (fully resident) grid arrives once per phase.  bar.sync orders the
+    // CTA's y / ssq stores before thread 0's gpu-scope fence + arrival; the acquire on the way out (+ reading x
+    // through L2) makes the other CTAs' stores visible.  A bounded spin: a protocol bug sets err instead of hanging.
+    auto grid_barrier = [&](int p) {
+      bar_sync_consumers();
+      if (tid == 0) {
+        __threadfence();
+        atomicAdd(ch.bars + p, 1u);
+        uint32_t spins = 0;
+        while (ld_acquire_gpu_u32(ch.bars + p) < gridDim.x) {
+          __nanosleep(40);
+          ++spins;
+          // give up after ~2 s, and at once if another barrier already did: the launch then ends quickly instead of
+          // serialising one time-out per phase
+          if (spins > (1u << 22) || ((spins & 1023u) == 0 && ld_acquire_gpu_u32(ch.err) != 0u)) { *ch.err = 1u; break; }
+        }
+        __threadfence();
+      }
+      bar_sync_consumers();
+    };
+    for (int p = 0; p < ch.n_phases; ++p) {
+      bar_sync_consumers();                                   // everyone is done with the previous phase's arguments
+      {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(ch.phases + p);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_ph);
+        for (int i = tid; i < static_cast<int>(sizeof(ChainPhase) / 4); i += SK_CTHREADS) dst[i] = __ldg(src + i);
+      }
+      bar_sync_consumers();
+      if (s_ph.type == PH_GEMM) {
+        G = s_ph.grid_p;
+        if (cta < G) {
+          if (a.x_norm) {
+            const int mrows = a.m_rows;
+            // 1 / rms of every token of the residual stream from the partial sums the producing phase left
+            for (int m = warp; m < mrows; m += SK_CWARPS) {
+              float tot = 0.f;
+              for (int i = lane; i < a.n_part_in; i += 32) tot += __ldcg(a.ssq_in + static_cast<int64_t>(i) * mrows + m);
+#pragma unroll
+              for (int d = 16; d > 0; d >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, d);
+              if (lane == 0) s_rstd[m] = rsqrtf(__fadd_rn(__fdiv_rn(tot, static_cast<float>(a.K)), a.eps));
+            }
+          }
+          // (the first bar_sync inside publishes s_rstd)
+          consumer_gemm_call<T, NBITS, MB, MODE>(a, G, ring_u32, ring_ptr, smem_u32(&full_bar[0]), smem_u32(&empty_bar[0]),
+                                                 s_rstd, rp);
+        }
+      } else if (s_ph.type == PH_ATTN) {
+        chain_attn<T>(s_ph.at, cta, static_cast<int>(gridDim.x), warp, lane);
+      } else {
+        chain_combine<T>(s_ph.at, cta, static_cast<int>(gridDim.x), warp, lane);
+      }
+      if (p + 1 < ch.n_phases) grid_barrier(p);
+    }
+    // the last CTA out leaves the arrival counters zeroed for the next launch
+    bar_sync_consumers();
+    if (tid == 0) {
+      const uint32_t old = atomicAdd(ch.bars + ch.n_phases, 1u);
+      if (old == gridDim.x - 1) {
+        for (int i = 0; i <= ch.n_phases; ++i) ch.bars[i] = 0u;
+        __threadfence();
+      }
+    }
+  } else {
+    consumer_gemm<T, NBITS, MB, MODE, false>(a_in, G, ring_u32, ring_ptr, smem_u32(&full_bar[0]), smem_u32(&empty_bar[0]),
+                                             s_rstd, rp);
+  }
+}
+
+template <typename T, int NBITS, int MB, int MODE>
+__global__ void __launch_bounds__(SK_THREADS, MB <= 1 ? SK_OCC : 2)
+k3_skinny(const SkinnyArgs a) {
+  skinny_body<T, NBITS, MB, MODE, false>(a, ChainArgs{});
+}
+
+// the chain form: same body, phases from device memory (q100_chain.cuh)
+template <typename T, int NBITS, int MB, int MODE>
+__global__ void __launch_bounds__(SK_THREADS, MB <= 1 ? SK_OCC : 2)
+k3_chain(const SkinnyArgs a, const ChainArgs ch) {
+  skinny_body<T, NBITS, MB, MODE, true>(a, ch);
 }
 
 // ---------------------------------------------------------------- host
@@ -1194,4 +1381,236 @@ int gemm_skinny(const void* x, const void* packed, const void* meta, const void*
   return launch_skinny_bits<__nv_bfloat16>(n_bits, a, st);
 }
 
+
+// ---------------------------------------------------------------- chain: host side
+constexpr size_t CH_HEADER_BYTES = 8192;          // arrival counters [CH_MAX_PHASES + 1], error flag; then ChainPhase[n]
+constexpr int CH_ERR_WORD = CH_MAX_PHASES + 4;
+constexpr int CH_CHUNK_CAP = 16;                  // k blocks of x staged per round (gate|up: 16 blocks per CTA at 444 CTAs)
+
+struct ChainGeom { int smem, stages, chunk, grid, mb, mode; };
+
+template <typename T, int NBITS, int MB, int MODE>
+static int chain_geometry_t(int m_rows, ChainGeom& g) {
+  auto kern = k3_chain<T, NBITS, MB, MODE>;
+  constexpr int xpitch = MODE == 2 ? SK_IPITCH : SK_XPITCH;
+  constexpr int occ_target = MB <= 1 ? SK_OCC : 2;
+  const int budget = (228 * 1024) / occ_target - 1024 - 512 - 128 - static_cast<int>(sizeof(ChainPhase)) - 256;
+  const int stage_pitch = (stage_bytes<NBITS>(1) + 127) & ~127;
+  const int row_b = m_rows * xpitch;
+  int min_stages = (2 * budget / 3) / stage_pitch;
+  if (min_stages > 6) min_stages = 6;
+  if (min_stages < 2) min_stages = 2;
+  int chunk = (budget - min_stages * stage_pitch - xpitch) / row_b;
+  if (chunk > CH_CHUNK_CAP) chunk = CH_CHUNK_CAP;
+  Q100_REQUIRE(chunk >= 1, Q100_EUNSUPPORTED, "k3_chain: M=%d rows of x do not fit in shared memory", m_rows);
+  int stages = (budget - slab_bytes(m_rows, chunk, xpitch)) / stage_pitch;
+  if (stages > SK_MAX_STAGES) stages = SK_MAX_STAGES;
+  const int smem = stages * stage_pitch + slab_bytes(m_rows, chunk, xpitch) + 128;
+  static std::mutex mu;
+  static int max_set[kMaxDevices] = {};
+  int occ = 0;
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    const int dev = current_device();
+    if (smem > max_set[dev]) {
+      Q100_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      max_set[dev] = smem;
+    }
+    Q100_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, SK_THREADS, smem));
+  }
+  Q100_REQUIRE(occ >= 1, Q100_ECUDA, "k3_chain does not fit on an SM (%d bytes smem)", smem);
+  g.smem = smem; g.stages = stages; g.chunk = chunk;
+  g.grid = sm_count() * (occ > occ_target ? occ_target : occ);   // every CTA resident: the grid barrier relies on it
+  g.mb = MB; g.mode = MODE;
+  return Q100_OK;
+}
+
+template <typename T, int NBITS, int MB, int MODE>
+static int chain_launch_t(const SkinnyArgs& a, const ChainArgs& ch, const ChainGeom& g, cudaStream_t st) {
+  auto kern = k3_chain<T, NBITS, MB, MODE>;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(g.grid);
+  cfg.blockDim = dim3(SK_THREADS);
+  cfg.dynamicSmemBytes = g.smem;
+  cfg.stream = st;
+  return check_cuda(cudaLaunchKernelEx(&cfg, kern, a, ch), "k3_chain launch");
+}
+
+// the one place that maps (dtype, bits, M) to an instantiation: op 0 = geometry, op 1 = launch
+template <typename T, int NBITS>
+static int chain_dispatch_bits(int op, int M, const SkinnyArgs* a, const ChainArgs* ch, ChainGeom& g, cudaStream_t st) {
+  const bool imma = (NBITS == 4 || NBITS == 2) && M <= 2;
+  if constexpr (NBITS == 4 || NBITS == 2) {
+    if (imma) return op == 0 ? chain_geometry_t<T, NBITS, 1, 2>(M, g) : chain_launch_t<T, NBITS, 1, 2>(*a, *ch, g, st);
+  }
+  if (M <= 8) return op == 0 ? chain_geometry_t<T, NBITS, 1, 1>(M, g) : chain_launch_t<T, NBITS, 1, 1>(*a, *ch, g, st);
+  return op == 0 ? chain_geometry_t<T, NBITS, 2, 1>(M, g) : chain_launch_t<T, NBITS, 2, 1>(*a, *ch, g, st);
+}
+static int chain_dispatch(int op, int dtype, int n_bits, int M, const SkinnyArgs* a, const ChainArgs* ch, ChainGeom& g,
+                          cudaStream_t st) {
+  if (dtype == Q100_F16) {
+    switch (n_bits) {
+      case 2: return chain_dispatch_bits<__half, 2>(op, M, a, ch, g, st);
+      case 3: return chain_dispatch_bits<__half, 3>(op, M, a, ch, g, st);
+      case 4: return chain_dispatch_bits<__half, 4>(op, M, a, ch, g, st);
+      default: return chain_dispatch_bits<__half, 8>(op, M, a, ch, g, st);
+    }
+  }
+  switch (n_bits) {
+    case 2: return chain_dispatch_bits<__nv_bfloat16, 2>(op, M, a, ch, g, st);
+    case 3: return chain_dispatch_bits<__nv_bfloat16, 3>(op, M, a, ch, g, st);
+    case 4: return chain_dispatch_bits<__nv_bfloat16, 4>(op, M, a, ch, g, st);
+    default: return chain_dispatch_bits<__nv_bfloat16, 8>(op, M, a, ch, g, st);
+  }
+}
+
+static void chain_common_args(SkinnyArgs& a, int M, int group, int n_bits, int disable_zp, const ChainGeom& g,
+                              void* workspace) {
+  a.ws_partials = reinterpret_cast<uint2*>(reinterpret_cast<uint8_t*>(workspace) + SK_COUNTER_BYTES);
+  a.M = M; a.group = group; a.m_rows = M;
+  a.has_zp = disable_zp ? 0 : 1;
+  a.qmin = disable_zp ? -static_cast<float>(1 << (n_bits - 1)) : 0.0f;
+  a.post = g.mode;
+  a.chunk = g.chunk; a.stages = g.stages; a.nsub = 1;
+  a.pdl = 0; a.seq = 0;
+}
+
+static int chain_attn_chunk(int64_t max_len) { return 64 * static_cast<int>((max_len + 2047) / 2048); }
+
 }  // namespace q100
+
+using namespace q100;
+
+extern "C" size_t q100_chain_desc_bytes(int n_phases) {
+  if (n_phases < 0) n_phases = 0;
+  return CH_HEADER_BYTES + static_cast<size_t>(n_phases) * sizeof(ChainPhase);
+}
+
+extern "C" int64_t q100_chain_ssq_parts(int64_t N) { return ((N + SK_ROWS - 1) / SK_ROWS) * SK_CWARPS; }
+
+extern "C" int64_t q100_chain_attn_partial_floats(int batch, int heads, int64_t max_len) {
+  if (batch <= 0 || heads <= 0 || max_len <= 0) return 0;
+  const int cp = chain_attn_chunk(max_len);
+  return static_cast<int64_t>(batch) * heads * ((max_len + cp - 1) / cp) * 8 * AT_PART_STRIDE;
+}
+
+extern "C" int q100_chain_build(const q100_phase* phases, int n_phases, int M, int group, int n_bits, int disable_zp,
+                                int dtype, void* desc, size_t desc_bytes, void* workspace, size_t workspace_bytes,
+                                size_t* workspace_needed, void* stream) {
+  Q100_REQUIRE(phases != nullptr && n_phases >= 1 && n_phases <= CH_MAX_PHASES, Q100_EINVAL,
+               "1 <= n_phases <= %d (got %d)", CH_MAX_PHASES, n_phases);
+  Q100_REQUIRE(dtype == Q100_F16 || dtype == Q100_BF16, Q100_EUNSUPPORTED, "fp16 / bf16 only (got dtype %d)", dtype);
+  Q100_REQUIRE(n_bits == 2 || n_bits == 3 || n_bits == 4 || n_bits == 8, Q100_EUNSUPPORTED, "n_bits in {2,3,4,8}");
+  Q100_REQUIRE(M >= 1 && M <= 16, Q100_EUNSUPPORTED, "chain handles 1 <= M <= 16 tokens (got %d)", M);
+  Q100_REQUIRE(group > 0 && group % SK_KB == 0, Q100_EUNSUPPORTED, "chain needs group %% 128 == 0 (got %d)", group);
+  Q100_REQUIRE(desc != nullptr && desc_bytes >= q100_chain_desc_bytes(n_phases), Q100_EINVAL,
+               "descriptor buffer too small: need %zu bytes", q100_chain_desc_bytes(n_phases));
+  Q100_REQUIRE((reinterpret_cast<uintptr_t>(desc) & 15) == 0, Q100_EINVAL, "descriptor buffer must be 16-byte aligned");
+  int rc = ensure_device();
+  if (rc != Q100_OK) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  ChainGeom geo{};
+  rc = chain_dispatch(0, dtype, n_bits, M, nullptr, nullptr, geo, st);
+  if (rc != Q100_OK) return rc;
+  std::vector<ChainPhase> host(n_phases);
+  size_t need = 0;
+  for (int i = 0; i < n_phases; ++i) {
+    const q100_phase& p = phases[i];
+    ChainPhase& c = host[i];
+    memset(&c, 0, sizeof(c));
+    c.type = p.type;
+    if (p.type == Q100_PH_GEMM) {
+      Q100_REQUIRE(p.x && p.packed && p.meta && p.y, Q100_EINVAL, "phase %d: NULL pointer argument", i);
+      Q100_REQUIRE(p.N > 0 && p.K > 0 && p.K % SK_KB == 0 && p.N % 8 == 0 && p.K % group == 0, Q100_EUNSUPPORTED,
+                   "phase %d: N=%lld (%% 8), K=%lld (%% 128, %% group)", i, (long long)p.N, (long long)p.K);
+      Q100_REQUIRE(p.x_mode == Q100_X_PLAIN || p.x_mode == Q100_X_GATE_UP || p.x_mode == Q100_X_NORM, Q100_EINVAL,
+                   "phase %d: bad x_mode %d", i, p.x_mode);
+      Q100_REQUIRE(p.epi_mode == Q100_EPI_STORE || p.epi_mode == Q100_EPI_ADD_SSQ, Q100_EINVAL, "phase %d: bad epi_mode", i);
+      if (p.x_mode == Q100_X_NORM)
+        Q100_REQUIRE(p.norm_weight && p.ssq_in && p.ssq_in_parts > 0, Q100_EINVAL, "phase %d: x_mode NORM needs norm_weight / ssq_in", i);
+      if (p.epi_mode == Q100_EPI_ADD_SSQ)
+        Q100_REQUIRE(p.residual && p.ssq_out && p.N % SK_ROWS == 0, Q100_EINVAL,
+                     "phase %d: epi_mode ADD_SSQ needs residual / ssq_out and N %% 128 == 0", i);
+      const SkinnyPlan pl = plan_skinny(p.N, p.K);
+      SkinnyArgs& a = c.g;
+      chain_common_args(a, M, group, n_bits, disable_zp, geo, workspace);
+      a.x = p.x; a.packed = p.packed; a.meta = p.meta; a.bias = p.bias; a.y = p.y;
+      a.N = static_cast<int>(p.N); a.K = static_cast<int>(p.K);
+      a.kblocks = static_cast<int>(p.K / SK_KB);
+      a.n_tiles = pl.n_tiles; a.total_units = pl.total_units;
+      int gp = pl.grid_cap < geo.grid ? pl.grid_cap : geo.grid;
+      // plan_skinny sizes its cap for SK_OCC CTAs per SM; with fewer resident CTAs keep the same units-per-CTA floor
+      if (gp > a.total_units) gp = a.total_units;
+      c.grid_p = gp;
+      a.max_slots = static_cast<int>((static_cast<int64_t>(a.kblocks) * gp + a.total_units - 1) / a.total_units) + 2;
+      a.x_gate_up = p.x_mode == Q100_X_GATE_UP;
+      a.x_norm = p.x_mode == Q100_X_NORM;
+      a.norm_w = p.norm_weight; a.ssq_in = reinterpret_cast<const float*>(p.ssq_in); a.n_part_in = p.ssq_in_parts;
+      a.eps = p.eps;
+      a.epi_add = p.epi_mode == Q100_EPI_ADD_SSQ;
+      a.res = p.residual; a.ssq_out = reinterpret_cast<float*>(p.ssq_out);
+      const size_t ws = static_cast<size_t>(a.n_tiles) * a.max_slots * SK_ROWS * geo.mb * 8 * sizeof(uint2) + SK_COUNTER_BYTES;
+      if (ws > need) need = ws;
+    } else if (p.type == Q100_PH_ATTN || p.type == Q100_PH_COMBINE) {
+      Q100_REQUIRE(p.qkv && p.cos_cache && p.sin_cache && p.position && p.k_cache && p.v_cache && p.att_partials && p.att_out,
+                   Q100_EINVAL, "phase %d: NULL pointer argument", i);
+      Q100_REQUIRE(p.head_dim == AT_D, Q100_EUNSUPPORTED, "phase %d: head_dim %d (the attention phase handles 128)", i, p.head_dim);
+      Q100_REQUIRE(p.batch == M && p.heads > 0 && p.kv_heads > 0 && p.heads % p.kv_heads == 0, Q100_EINVAL,
+                   "phase %d: batch must equal M, heads %% kv_heads == 0", i);
+      const int rep = p.heads / p.kv_heads;
+      Q100_REQUIRE(rep == 1 || rep == 2 || rep % 4 == 0, Q100_EUNSUPPORTED, "phase %d: heads / kv_heads = %d", i, rep);
+      Q100_REQUIRE(p.max_len > 0 && p.rope_len > 0, Q100_EINVAL, "phase %d: bad cache length", i);
+      AttnArgs& t = c.at;
+      t.qkv = p.qkv; t.cosb = p.cos_cache; t.sinb = p.sin_cache; t.pos = reinterpret_cast<const int64_t*>(p.position);
+      t.k_cache = p.k_cache; t.v_cache = p.v_cache; t.part = reinterpret_cast<float*>(p.att_partials); t.out = p.att_out;
+      t.B = p.batch; t.H = p.heads; t.KVH = p.kv_heads;
+      t.chunk_pos = chain_attn_chunk(p.max_len);
+      t.max_parts = static_cast<int>((p.max_len + t.chunk_pos - 1) / t.chunk_pos) * 8;
+      t.max_len = p.max_len; t.rope_len = p.rope_len;
+      t.scale = 1.0f / sqrtf(static_cast<float>(AT_D));
+      t.err = reinterpret_cast<uint32_t*>(desc) + CH_ERR_WORD;
+    } else {
+      Q100_REQUIRE(false, Q100_EINVAL, "phase %d: unknown type %d", i, p.type);
+    }
+  }
+  if (workspace_needed) *workspace_needed = need;
+  Q100_REQUIRE(workspace != nullptr && workspace_bytes >= need, Q100_EWORKSPACE,
+               "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+  Q100_CUDA(cudaMemsetAsync(desc, 0, CH_HEADER_BYTES, st));
+  Q100_CUDA(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(desc) + CH_HEADER_BYTES, host.data(),
+                            static_cast<size_t>(n_phases) * sizeof(ChainPhase), cudaMemcpyHostToDevice, st));
+  Q100_CUDA(cudaStreamSynchronize(st));                    // `host` goes out of scope
+  return Q100_OK;
+}
+
+extern "C" int q100_chain_run(void* desc, int n_phases, int M, int group, int n_bits, int disable_zp, int dtype,
+                              void* workspace, void* stream) {
+  Q100_REQUIRE(desc != nullptr && workspace != nullptr && n_phases >= 1 && n_phases <= CH_MAX_PHASES, Q100_EINVAL,
+               "bad chain arguments");
+  Q100_REQUIRE(M >= 1 && M <= 16 && group > 0 && group % SK_KB == 0, Q100_EUNSUPPORTED, "chain: 1 <= M <= 16, group %% 128 == 0");
+  int rc = ensure_device();
+  if (rc != Q100_OK) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  ChainGeom geo{};
+  rc = chain_dispatch(0, dtype, n_bits, M, nullptr, nullptr, geo, st);
+  if (rc != Q100_OK) return rc;
+  SkinnyArgs a{};
+  chain_common_args(a, M, group, n_bits, disable_zp, geo, workspace);
+  a.total_units = 1; a.kblocks = 1;
+  ChainArgs ch{};
+  ch.phases = reinterpret_cast<const ChainPhase*>(reinterpret_cast<uint8_t*>(desc) + CH_HEADER_BYTES);
+  ch.n_phases = n_phases;
+  ch.bars = reinterpret_cast<uint32_t*>(desc);
+  ch.err = reinterpret_cast<uint32_t*>(desc) + CH_ERR_WORD;
+  return chain_dispatch(1, dtype, n_bits, M, &a, &ch, geo, st);
+}
+
+extern "C" int q100_chain_error(const void* desc, void* stream) {
+  Q100_REQUIRE(desc != nullptr, Q100_EINVAL, "NULL descriptor");
+  uint32_t v = 0;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  Q100_CUDA(cudaMemcpyAsync(&v, reinterpret_cast<const uint32_t*>(desc) + CH_ERR_WORD, 4, cudaMemcpyDeviceToHost, st));
+  Q100_CUDA(cudaStreamSynchronize(st));
+  Q100_REQUIRE(v == 0, Q100_ECUDA, "a chain launch reported an error (grid barrier time-out or a position outside the KV cache)");
+  return Q100_OK;
+}

@@ -139,10 +139,9 @@ class _FusedLinears:
                                  torch.cat([p.scales for p in parts], dim=0), zeros,
                                  p0.n_bits, p0.group, sum(p.N for p in parts), p0.K, p0.disable_zero_point)
 
-    def __call__(self, mods, x: torch.Tensor, split: bool = True):
-        """Returns the outputs of ``mods`` on ``x`` (a tuple; the unsplit ``[..., sum N]`` tensor with
-        ``split=False``), or None when the modules cannot be fused (then the caller runs them one by one
-        exactly like the reference)."""
+    def packed(self, mods, x: torch.Tensor):
+        """(concatenated PackedWeight, per-module N list) for ``mods`` on an input like ``x``, or None when the
+        modules cannot be fused (then the caller runs them one by one exactly like the reference)."""
         if not x.is_cuda or x.dtype not in (torch.float16, torch.bfloat16):
             return None
         parts = []
@@ -163,6 +162,16 @@ class _FusedLinears:
         if key != self._key:
             self._pw = self._concat(parts)
             self._key = key
+        return self._pw, [p.N for p in parts]
+
+    def __call__(self, mods, x: torch.Tensor, split: bool = True):
+        """Returns the outputs of ``mods`` on ``x`` (a tuple; the unsplit ``[..., sum N]`` tensor with
+        ``split=False``), or None when the modules cannot be fused."""
+        got = self.packed(mods, x)
+        if got is None:
+            return None
+        pw, ns = got
+        m0 = mods[0]
         if m0.use_act_quant and not m0.disable_input_quant:
             xq = m0.act_quantizer(x)                  # same input, same per-token statistics for every consumer
             for m in mods[1:]:
@@ -172,8 +181,8 @@ class _FusedLinears:
                 if aq.n_bits < 16 and aq.enable:
                     aq.scale, aq.round_zero_point = a0.scale, a0.round_zero_point
             x = xq
-        y = _ops.gemm_wna16(x, self._pw)
-        return y.split([p.N for p in parts], dim=-1) if split else y
+        y = _ops.gemm_wna16(x, pw)
+        return y.split(ns, dim=-1) if split else y
 
 
 class QuantLlamaMLP(nn.Module):

@@ -31,6 +31,24 @@ GEMM_X_GATE_UP = 0x100
 
 _vp, _i, _i64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
 
+PH_GEMM, PH_ATTN, PH_COMBINE = 0, 1, 2
+X_PLAIN, X_GATE_UP, X_NORM = 0, 1, 2
+EPI_STORE, EPI_ADD_SSQ = 0, 1
+
+
+class Phase(C.Structure):
+    """struct q100_phase of include/q100.h (one phase of a decode chain)."""
+    _fields_ = [("type", _i),
+                ("x", _vp), ("packed", _vp), ("meta", _vp), ("bias", _vp), ("y", _vp),
+                ("N", _i64), ("K", _i64),
+                ("x_mode", _i), ("norm_weight", _vp), ("ssq_in", _vp), ("ssq_in_parts", _i), ("eps", C.c_float),
+                ("epi_mode", _i), ("residual", _vp), ("ssq_out", _vp),
+                ("qkv", _vp), ("cos_cache", _vp), ("sin_cache", _vp), ("position", _vp), ("k_cache", _vp),
+                ("v_cache", _vp), ("att_partials", _vp), ("att_out", _vp),
+                ("batch", _i), ("heads", _i), ("kv_heads", _i), ("head_dim", _i),
+                ("max_len", _i64), ("rope_len", _i64)]
+
+
 # name -> (restype, argtypes); must list every symbol include/q100.h declares
 SIGNATURES = {
     "q100_last_error": (C.c_char_p, []),
@@ -45,6 +63,12 @@ SIGNATURES = {
     "q100_dequantize": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _i, _i, _i, _vp, _vp]),
     "q100_gemm_wna16": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _sz, _i, _vp]),
     "q100_gemm_workspace_bytes": (_sz, [_i64, _i64, _i64, _i, _i]),
+    "q100_chain_desc_bytes": (_sz, [_i]),
+    "q100_chain_ssq_parts": (_i64, [_i64]),
+    "q100_chain_attn_partial_floats": (_i64, [_i, _i, _i64]),
+    "q100_chain_build": (_i, [C.POINTER(Phase), _i, _i, _i, _i, _i, _i, _vp, _sz, _vp, _sz, C.POINTER(_sz), _vp]),
+    "q100_chain_run": (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    "q100_chain_error": (_i, [_vp, _vp]),
     "q100_add_rmsnorm": (_i, [_vp, _vp, _vp, C.c_float, _vp, _vp, _i64, _i64, _i, _vp]),
     "q100_rope_kv_decode": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i64, _i64, _vp, _i, _vp]),
     "q100_silu_mul": (_i, [_vp, _vp, _i64, _i64, _i, _vp]),

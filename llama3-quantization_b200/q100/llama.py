@@ -221,9 +221,13 @@ class GraphDecoder:
     (llama.py:409-465); the arithmetic per token is the same, the launch overhead is not."""
 
     def __init__(self, model: QuantLlamaModel, bsz: int, max_len: int, use_graph: bool = True,
-                 fused: bool = True):
+                 fused: bool = True, chain: Optional[bool] = None):
+        """``chain``: run all blocks of a step as ONE persistent launch (q100/chain.py, K9).  None = use it when the
+        model qualifies (single GPU, bsz <= 16, weight-only quantisation with group % 128 == 0, head_dim 128)."""
         from models.int_llama_layer import StaticKV
         self.fused = fused
+        self.want_chain = chain
+        self.chain = None
         self.pdl = False          # measured: 2.31 ms/token without, 2.46 with (predecessors are not PDL-aware)
         self.model, self.bsz, self.max_len = model, bsz, max_len
         cfg = model.cfg
@@ -245,7 +249,82 @@ class GraphDecoder:
         self.err = torch.zeros(1, dtype=torch.int32, device=dev)
         self._host_pos = 0
 
+    # ------------------------------------------------------------------ the chain route (K9)
+    def _build_chain(self):
+        """Lay the decode step of every block out as phases of one persistent launch.  Returns None (and the
+        per-kernel route stays) when a block does not qualify."""
+        import os
+        from . import _lib, chain as _chain, ops as _ops
+        m, cfg = self.model, self.model.cfg
+        dev, dt = m.embed_tokens.device, m.embed_tokens.dtype
+        B, H, I = self.bsz, cfg.hidden_size, cfg.intermediate_size
+        hd = H // cfg.num_attention_heads
+        if os.environ.get("Q100_NO_CHAIN") or B > 16 or hd != 128 or dt not in (torch.float16, torch.bfloat16):
+            return None
+        packs = []
+        xh = torch.zeros(B, H, dtype=dt, device=dev)
+        xi = torch.zeros(B, I, dtype=dt, device=dev)
+        for layer in m.layers:
+            attn, mlp = layer.self_attn, layer.mlp
+            if attn.tp_world > 1 or attn.use_act_quant or mlp.act_fn is not F.silu \
+                    or layer.input_layernorm.use_temporary_parameter or layer.post_attention_layernorm.use_temporary_parameter:
+                return None
+            qkv = attn._qkv.packed((attn.q_proj, attn.k_proj, attn.v_proj), xh)
+            gu = mlp._gate_up.packed((mlp.gate_proj, mlp.up_proj), xh)
+            o = attn.o_proj.packed_operand(xh) if attn.o_proj.bias is None else None
+            d = mlp.down_proj.packed_operand(xi) if mlp.down_proj.bias is None else None
+            if qkv is None or gu is None or o is None or d is None:
+                return None
+            ws = (qkv[0], o, gu[0], d)
+            w0 = ws[0]
+            if any((w.n_bits, w.group, w.disable_zero_point, w.dtype) != (w0.n_bits, w0.group, w0.disable_zero_point, dt)
+                   for w in ws) or w0.group % 128 != 0 or H % 128 != 0:
+                return None
+            packs.append(ws)
+        w0 = packs[0][0]
+        ch = _chain.Chain(B, w0.group, w0.n_bits, w0.disable_zero_point, dt, dev)
+        nh, nkv = cfg.num_attention_heads, cfg.num_key_value_heads
+        parts = _chain.ssq_parts(H)
+        b = self._cb = {"h": torch.zeros(B, H, dtype=dt, device=dev), "n1": torch.zeros(B, H, dtype=dt, device=dev),
+                        "qkv": torch.zeros(B, (nh + 2 * nkv) * hd, dtype=dt, device=dev),
+                        "att": torch.zeros(B, nh * hd, dtype=dt, device=dev),
+                        "gu": torch.zeros(B, 2 * I, dtype=dt, device=dev),
+                        "ssq_a": torch.zeros(parts, B, dtype=torch.float32, device=dev),
+                        "ssq_b": torch.zeros(parts, B, dtype=torch.float32, device=dev)}
+        n_layers = len(m.layers)
+        for li, (layer, kv, (wqkv, wo, wgu, wd)) in enumerate(zip(m.layers, self.caches, packs)):
+            attn = layer.self_attn
+            cos, sin = attn.rotary_emb(kv.v, seq_len=self.max_len)
+            cos, sin = cos.to(dt).contiguous(), sin.to(dt).contiguous()
+            if li == 0:       # block 0 reads K4's output (no partial sums of squares exist for the embedding)
+                ch.gemm(b["n1"], wqkv, b["qkv"])
+            else:
+                ch.gemm(b["h"], wqkv, b["qkv"], x_mode=_lib.X_NORM, norm_weight=layer.input_layernorm.weight,
+                        ssq_in=b["ssq_a"], eps=layer.input_layernorm.variance_epsilon)
+            ch.attention(b["qkv"], cos, sin, self.pos, kv.k, kv.v, b["att"], nh, nkv)
+            ch.gemm(b["att"], wo, b["h"], epi_mode=_lib.EPI_ADD_SSQ, residual=b["h"], ssq_out=b["ssq_b"])
+            ch.gemm(b["h"], wgu, b["gu"], x_mode=_lib.X_NORM, norm_weight=layer.post_attention_layernorm.weight,
+                    ssq_in=b["ssq_b"], eps=layer.post_attention_layernorm.variance_epsilon)
+            ch.gemm(b["gu"], wd, b["h"], x_mode=_lib.X_GATE_UP, epi_mode=_lib.EPI_ADD_SSQ, residual=b["h"],
+                    ssq_out=b["ssq_a"])
+        return ch.build()
+
+    def _step_chain(self):
+        from . import ops as _ops
+        m, b = self.model, self._cb
+        torch.index_select(m.embed_tokens, 0, self.tok.view(-1), out=b["h"])
+        l0 = m.layers[0]
+        _ops.add_rmsnorm(b["h"], l0.input_layernorm.weight, l0.input_layernorm.variance_epsilon, out_norm=b["n1"])
+        self.chain.run()
+        x = _ops.add_rmsnorm(b["h"], m.norm_weight, m.cfg.rms_norm_eps)[1]
+        logits = F.linear(x.view(self.bsz, 1, -1), m.lm_head)
+        self.last_logits = logits
+        self.next_tok.copy_(logits.argmax(-1))
+        self.pos.add_(1)
+
     def _step(self):
+        if self.chain is not None:
+            return self._step_chain()
         m = self.model
         x = F.embedding(self.tok, m.embed_tokens)
         mask = torch.where(self._slots <= self.pos.view(1, 1, 1, 1), 0.0, self._neg).to(x.dtype)
@@ -265,6 +344,7 @@ class GraphDecoder:
         else:
             x = m._norm(x)
         logits = F.linear(x, m.lm_head)
+        self.last_logits = logits
         self.next_tok.copy_(logits.argmax(-1))
         self.pos.add_(1)
 
@@ -275,6 +355,10 @@ class GraphDecoder:
             raise ValueError(f"GraphDecoder.prime: start_pos={start_pos} leaves no room in a cache of {self.max_len}")
         self.pos.fill_(start_pos)
         self._host_pos = start_pos
+        if self.chain is None and self.fused and self.want_chain is not False:
+            self.chain = self._build_chain()
+            if self.chain is None and self.want_chain:
+                raise RuntimeError("GraphDecoder: this model / batch does not qualify for the chain route")
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
@@ -312,6 +396,8 @@ class GraphDecoder:
         """Raise if a kernel saw a position outside the cache (synchronises)."""
         if int(self.err.item()) != 0:
             raise RuntimeError("GraphDecoder: a decode step ran past the KV cache / rotary table")
+        if self.chain is not None:
+            self.chain.check()
 
     def _step_pdl(self):
         # the weights are static during decode, so every GEMM may start streaming them while its

@@ -325,17 +325,19 @@ def gemm_wna16(x: torch.Tensor, w: PackedWeight, bias: Optional[torch.Tensor] = 
     return y.view(*shp[:-1], w.N)
 
 
-def add_rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float, residual: Optional[torch.Tensor] = None):
-    """(h, n) with h = residual + x (or x) and n = OmniLlamaRMSNorm(h); one launch (K4)."""
+def add_rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float, residual: Optional[torch.Tensor] = None,
+                out_norm: Optional[torch.Tensor] = None, out_sum: Optional[torch.Tensor] = None):
+    """(h, n) with h = residual + x (or x) and n = OmniLlamaRMSNorm(h); one launch (K4).  ``out_norm`` / ``out_sum``:
+    preallocated destinations (fixed addresses for a CUDA graph / a decode chain)."""
     _require_cuda(x, weight, residual)
     x = x.contiguous()
     cols = x.shape[-1]
     rows = x.numel() // cols
-    norm = torch.empty_like(x)
+    norm = torch.empty_like(x) if out_norm is None else out_norm
     h = x
     if residual is not None:
         residual = residual.contiguous()
-        h = torch.empty_like(x)
+        h = torch.empty_like(x) if out_sum is None else out_sum
     with _on(x.device):
         check(lib.q100_add_rmsnorm(x.data_ptr(), _ptr(residual), weight.data_ptr(), float(eps),
                                    h.data_ptr() if residual is not None else None, norm.data_ptr(), rows, cols,
