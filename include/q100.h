@@ -247,20 +247,24 @@ int q100_silu_mul(const void* gate_up, void* out, int64_t rows, int64_t inter, i
  *                Q100_X_NORM     x = residual stream h [M, K], the kernel stages norm_weight * (h * rstd)
  *                                (quant/omni_norm.py:52-63) with rstd from ssq_in: [ssq_in_parts][M] fp32 partial
  *                                sums of h^2 left by the phase that produced h
+ *                Q100_X_ATTN     x = the attention output [M, heads * 128], merged by the kernel while it stages x from
+ *                                the flash-decoding partials a preceding Q100_PH_ATTN left in att_partials (fields
+ *                                att_partials / position / max_len / heads of this phase; `x` itself is not read):
+ *                                o_proj directly behind the attention, no Q100_PH_COMBINE in between
  *       epi_mode Q100_EPI_STORE  y = result
  *                Q100_EPI_ADD_SSQ y = r(r(result) + residual[M, N]) (int_llama_layer.py:246, 251) and
  *                                ssq_out[q100_chain_ssq_parts(N)][M] receives the partial sums of y^2
  *   Q100_PH_ATTN     rotary on q / k of the new token of each sequence, k / v appended to the static cache at the
  *                    DEVICE-side position, attention of the new token over positions 0..position in fp32 (the
  *                    decode form of int_llama_layer.py:114-172), flash-decoding partials into att_partials
- *   Q100_PH_COMBINE  merges the partials into att_out [batch, heads * head_dim] (what o_proj reads)
+ *   Q100_PH_COMBINE  merges the partials into att_out [batch, heads * head_dim] (for a consumer that is not a chain GEMM)
  *
  * Phases run in order; between two phases every CTA passes a grid barrier, so a phase may read what any earlier phase
  * wrote.  All buffers are the caller's and must stay valid (and at the same addresses) as long as the chain is used.
  * Same weights, same layouts (packed / meta) as q100_gemm_wna16; group %% 128 == 0; one n_bits / dtype per chain.
  */
 enum q100_phase_type { Q100_PH_GEMM = 0, Q100_PH_ATTN = 1, Q100_PH_COMBINE = 2 };
-enum q100_x_mode { Q100_X_PLAIN = 0, Q100_X_GATE_UP = 1, Q100_X_NORM = 2 };
+enum q100_x_mode { Q100_X_PLAIN = 0, Q100_X_GATE_UP = 1, Q100_X_NORM = 2, Q100_X_ATTN = 3 };
 enum q100_epi_mode { Q100_EPI_STORE = 0, Q100_EPI_ADD_SSQ = 1 };
 typedef struct q100_phase {
   int type;

@@ -40,6 +40,10 @@ struct SkinnyArgs {
   const float* ssq_in;    // [n_part_in][M] partial sums of h^2 written by the phase that produced h
   int n_part_in;
   float eps;
+  int x_attn;             // x[m, head * 128 ..] = the attention output of (sequence m, head): merged here from the
+  const float* att_part;  // flash-decoding partials [M * H][att_max_parts][AT_PART_STRIDE] the attention phase left,
+  const int64_t* att_pos; // for the chunks up to the device-side position (K must equal H * 128)
+  int att_max_parts, att_chunk_pos;
   int epi_add;            // y = r(r(acc) + res) (the residual adds of int_llama_layer.py:246, 251) and ...
   const void* res;        // [M, N] T
   float* ssq_out;         // ... [n_tiles * 8][M] partial sums of y^2 for the next RMSNorm
@@ -58,35 +62,46 @@ struct AttnArgs {
   const int64_t* pos;     // device scalar: position of the new token
   void* k_cache;          // [B, KVH, max_len, D] T
   void* v_cache;
-  float* part;            // [B * H][max_parts][AT_PART_STRIDE]: flash-decoding partials of 8 warps per position chunk
+  float* part;            // [B * H][max_parts][AT_PART_STRIDE]: one flash-decoding partial per position chunk
   void* out;              // [B, H * D] T (what o_proj reads)
   int B, H, KVH;
   int chunk_pos;          // positions per work item (multiple of 64)
-  int max_parts;          // ceil(max_len / chunk_pos) * 8
+  int max_parts;          // ceil(max_len / chunk_pos)
   int pad_;
   int64_t max_len, rope_len;
   float scale;            // 1 / sqrt(D)
   uint32_t* err;          // set to 1 when the position is outside the cache / rotary table
 };
 
-struct ChainPhase {
+struct alignas(16) ChainPhase {
   int type;               // PH_*
   int grid_p;             // GEMM: CTAs that take units of this phase (<= gridDim.x; small GEMMs are not cut too finely)
   SkinnyArgs g;
   AttnArgs at;
 };
+constexpr int CH_PHASE_BYTES = 512;     // shared-memory slot of a phase (copied in 16-byte pieces)
+static_assert(sizeof(ChainPhase) <= CH_PHASE_BYTES && sizeof(ChainPhase) % 16 == 0, "ChainPhase layout");
 
 struct ChainArgs {
   const ChainPhase* phases;   // device memory
   int n_phases;
   uint32_t* bars;             // [n_phases + 1] arrival counters, zero between launches (the last CTA out resets them)
   uint32_t* err;              // set to 1 if a grid barrier timed out (results are then invalid)
+  unsigned long long* trace;  // nullable; [n_phases][3] globaltimer stamps per barrier: first arrival, last arrival,
+                              // last release (Q100_CHAIN_TRACE=1; the kernel accumulates min / max with atomics)
+  const int64_t* const* pos_pp; // device slot holding the pointer to the device-side position all attention phases share
+  int trace_phase;            // Q100_CHAIN_TRACE_PHASE: every CTA also stamps its way through this phase (8 stamps / CTA)
 };
 
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t ld_acquire_gpu_u32(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_relaxed_gpu_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
 
@@ -107,15 +122,17 @@ __device__ __forceinline__ float warp_reduce_scatter32(float (&v)[32], int lane)
 
 __device__ __forceinline__ float neg_inf_f() { return __int_as_float(0xff800000); }
 
-// ---- PH_ATTN: work item = (sequence b, kv head, chunk of chunk_pos positions); the 8 consumer warps of a CTA split
-// the chunk, every warp handles the q heads of the GQA group four at a time with an online softmax over its positions
-// and writes one partial {m, l, o[128]} per q head.  Lane l owns dims 4l .. 4l+3 of every vector.
+// ---- PH_ATTN: work item = (sequence b, kv head, chunk of chunk_pos positions), one CTA per item.  The 8 consumer
+// warps split the chunk's positions; every warp handles the q heads of the GQA group four at a time with an online
+// softmax over its positions (lane l owns dims 4l .. 4l+3 of every vector), the warps' results are merged through
+// shared memory (`scratch`: 8 x 4 x AT_PART_STRIDE floats) and ONE partial {m, l, o[128]} per (q head, chunk) goes to
+// global memory.  The phase that consumes the attention output merges the chunks (x_attn staging, or PH_COMBINE).
 // Arithmetic: rotary as K5 (q in fp32 rounded once to T; k with every op rounded to T; v copied), scores and
 // softmax in fp32 from the T-rounded q / k / v (what scaled_dot_product_attention does on the same tensors).
 template <typename T>
-__device__ __noinline__ void chain_attn(const AttnArgs& at, int cta, int G, int warp, int lane) {
+__device__ __noinline__ void chain_attn(const AttnArgs& at, const int64_t p, float* scratch, int cta, int G, int warp,
+                                        int lane) {
   using D = DT<T>;
-  const int64_t p = __ldcg(at.pos);
   if (p < 0 || p >= at.max_len || p >= at.rope_len) {
     if (cta == 0 && warp == 0 && lane == 0 && at.err != nullptr) *at.err = 1u;
     return;
@@ -126,6 +143,7 @@ __device__ __noinline__ void chain_attn(const AttnArgs& at, int cta, int G, int 
   const int n_chunks = static_cast<int>((p + at.chunk_pos) / at.chunk_pos);
   const int ppw = at.chunk_pos >> 3;                      // positions per warp
   const int n_items = at.B * at.KVH * n_chunks;
+  if (cta >= n_items) return;
   const bool lo_half = lane < 16;                         // dims < 64: partner dims are +64, else -64
   const T* cs = reinterpret_cast<const T*>(at.cosb) + p * AT_D + 4 * lane;
   const T* sn = reinterpret_cast<const T*>(at.sinb) + p * AT_D + 4 * lane;
@@ -180,18 +198,23 @@ __device__ __noinline__ void chain_attn(const AttnArgs& at, int cta, int G, int 
       for (int r0 = 0; r0 < ppw; r0 += 8) {
         const int64_t pr = p0 + r0;
         if (pr > p) break;                                // warp-uniform: nothing left below the new token
+        // the round's K and V rows are requested together: one memory round trip per round instead of two
+        uint2 kw[8], vw[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          kw[j] = make_uint2(0u, 0u); vw[j] = make_uint2(0u, 0u);
+          if (pr + j <= p) {
+            kw[j] = *reinterpret_cast<const uint2*>(kc + (pr + j) * AT_D + 4 * lane);
+            vw[j] = *reinterpret_cast<const uint2*>(vc + (pr + j) * AT_D + 4 * lane);
+          }
+        }
         float s[32];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          float kf[4] = {0.f, 0.f, 0.f, 0.f};
-          if (pr + j <= p) {
-            const uint2 kw = *reinterpret_cast<const uint2*>(kc + (pr + j) * AT_D + 4 * lane);
-            const float2 k01 = D::to_f2(kw.x), k23 = D::to_f2(kw.y);
-            kf[0] = k01.x; kf[1] = k01.y; kf[2] = k23.x; kf[3] = k23.y;
-          }
+          const float2 k01 = D::to_f2(kw[j].x), k23 = D::to_f2(kw[j].y);
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            s[j * 4 + i] = fmaf(q[i][3], kf[3], fmaf(q[i][2], kf[2], fmaf(q[i][1], kf[1], q[i][0] * kf[0])));
+            s[j * 4 + i] = fmaf(q[i][3], k23.y, fmaf(q[i][2], k23.x, fmaf(q[i][1], k01.y, q[i][0] * k01.x)));
         }
         float sc = warp_reduce_scatter32(s, lane) * at.scale;    // score of (position pr + (lane >> 2), head lane & 3)
         if (pr + (lane >> 2) > p) sc = neg_inf_f();
@@ -215,28 +238,43 @@ __device__ __noinline__ void chain_attn(const AttnArgs& at, int cta, int G, int 
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          float vf[4] = {0.f, 0.f, 0.f, 0.f};
-          if (pr + j <= p) {
-            const uint2 vw = *reinterpret_cast<const uint2*>(vc + (pr + j) * AT_D + 4 * lane);
-            const float2 v01 = D::to_f2(vw.x), v23 = D::to_f2(vw.y);
-            vf[0] = v01.x; vf[1] = v01.y; vf[2] = v23.x; vf[3] = v23.y;
-          }
+          const float2 v01 = D::to_f2(vw[j].x), v23 = D::to_f2(vw[j].y);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float pj = __shfl_sync(0xffffffffu, e, j * 4 + i);
-            o[i][0] = fmaf(pj, vf[0], o[i][0]); o[i][1] = fmaf(pj, vf[1], o[i][1]);
-            o[i][2] = fmaf(pj, vf[2], o[i][2]); o[i][3] = fmaf(pj, vf[3], o[i][3]);
+            o[i][0] = fmaf(pj, v01.x, o[i][0]); o[i][1] = fmaf(pj, v01.y, o[i][1]);
+            o[i][2] = fmaf(pj, v23.x, o[i][2]); o[i][3] = fmaf(pj, v23.y, o[i][3]);
           }
         }
       }
-      const int part_i = c * 8 + warp;
+      // merge the 8 warps: every warp leaves {m, l, o} per head in shared memory, warp i < HG merges head i
+      asm volatile("bar.sync 1, 256;" ::: "memory");        // the previous pass's readers are done with `scratch`
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        if (i < HG) {
-          float* dst = at.part + ((static_cast<int64_t>(b) * at.H + h0 + i) * at.max_parts + part_i) * AT_PART_STRIDE;
-          *reinterpret_cast<float4*>(dst + 4 + 4 * lane) = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
-          if (lane == i) *reinterpret_cast<float2*>(dst) = make_float2(m_run, l_run);
+        float* dst = scratch + (warp * 4 + i) * AT_PART_STRIDE;
+        *reinterpret_cast<float4*>(dst + 4 + 4 * lane) = make_float4(o[i][0], o[i][1], o[i][2], o[i][3]);
+        if (lane == i) *reinterpret_cast<float2*>(dst) = make_float2(m_run, l_run);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (warp < HG) {
+        float M = neg_inf_f(), L = 0.f, acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+          const float* src = scratch + (w * 4 + warp) * AT_PART_STRIDE;
+          const float2 ml = *reinterpret_cast<const float2*>(src);
+          const float4 ov = *reinterpret_cast<const float4*>(src + 4 + 4 * lane);
+          if (ml.y > 0.f) {                                  // l == 0: a warp whose positions were all masked
+            const float Mn = fmaxf(M, ml.x);
+            const float c0 = expf(M - Mn), c1 = expf(ml.x - Mn);
+            L = fmaf(L, c0, ml.y * c1);
+            acc[0] = fmaf(acc[0], c0, ov.x * c1); acc[1] = fmaf(acc[1], c0, ov.y * c1);
+            acc[2] = fmaf(acc[2], c0, ov.z * c1); acc[3] = fmaf(acc[3], c0, ov.w * c1);
+            M = Mn;
+          }
         }
+        float* dst = at.part + ((static_cast<int64_t>(b) * at.H + h0 + warp) * at.max_parts + c) * AT_PART_STRIDE;
+        *reinterpret_cast<float4*>(dst + 4 + 4 * lane) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        if (lane == 0) *reinterpret_cast<float2*>(dst) = make_float2(M, L);
       }
     }
   }
@@ -244,11 +282,10 @@ __device__ __noinline__ void chain_attn(const AttnArgs& at, int cta, int G, int 
 
 // ---- PH_COMBINE: one warp per (sequence, q head): merge the partials of the chunks up to the new token
 template <typename T>
-__device__ __noinline__ void chain_combine(const AttnArgs& at, int cta, int G, int warp, int lane) {
+__device__ __noinline__ void chain_combine(const AttnArgs& at, const int64_t p, int cta, int G, int warp, int lane) {
   using D = DT<T>;
-  const int64_t p = __ldcg(at.pos);
   if (p < 0 || p >= at.max_len || p >= at.rope_len) return;
-  const int n_parts = static_cast<int>((p + at.chunk_pos) / at.chunk_pos) * 8;
+  const int n_parts = static_cast<int>((p + at.chunk_pos) / at.chunk_pos);
   const int n_items = at.B * at.H;
   for (int item = cta * 8 + warp; item < n_items; item += G * 8) {
     const float* base = at.part + static_cast<int64_t>(item) * at.max_parts * AT_PART_STRIDE;

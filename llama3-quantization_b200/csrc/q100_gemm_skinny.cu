@@ -39,6 +39,8 @@
 #include <unordered_map>
 #include <vector>
 #include <cstring>
+#include <cstdlib>
+#include <cstdio>
 #include <cmath>
 
 #include "q100_common.cuh"
@@ -271,7 +273,7 @@ __device__ __forceinline__ void imma_16832(int (&d)[4], const uint32_t (&a)[4], 
 // act_fn(gate) * up for eight elements: F.silu in fp32 stored as T, then the product rounded to T -- the arithmetic
 // of k6_silu_mul (q100_block.cu), i.e. of models/int_llama_layer.py:45 on 16-bit tensors
 template <typename T>
-__device__ __noinline__ uint4 silu_mul8(const uint4& g, const uint4& u) {   // out of line: keeps its temporaries out of the kernel's 72-register budget
+__device__ __forceinline__ uint4 silu_mul8_inl(const uint4& g, const uint4& u) {
   using D = DT<T>;
   const uint32_t gw[4] = {g.x, g.y, g.z, g.w}, uw[4] = {u.x, u.y, u.z, u.w};
   uint32_t ow[4];
@@ -284,9 +286,13 @@ __device__ __noinline__ uint4 silu_mul8(const uint4& g, const uint4& u) {   // o
   }
   return make_uint4(ow[0], ow[1], ow[2], ow[3]);
 }
+template <typename T>
+__device__ __noinline__ uint4 silu_mul8(const uint4& g, const uint4& u) {   // out of line: keeps its temporaries out of the kernel's 72-register budget
+  return silu_mul8_inl<T>(g, u);
+}
 // weight * (h * rstd) for eight elements: both products in fp32, one rounding to T (k4_add_rmsnorm, q100_block.cu)
 template <typename T>
-__device__ __noinline__ uint4 norm8(const uint4& h, const uint4& w, float rstd) {
+__device__ __forceinline__ uint4 norm8(const uint4& h, const uint4& w, float rstd) {
   using D = DT<T>;
   const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, ww[4] = {w.x, w.y, w.z, w.w};
   uint32_t ow[4];
@@ -296,6 +302,45 @@ __device__ __noinline__ uint4 norm8(const uint4& h, const uint4& w, float rstd) 
     ow[j] = D::pack2(__fmul_rn(g.x, __fmul_rn(f.x, rstd)), __fmul_rn(g.y, __fmul_rn(f.y, rstd)));
   }
   return make_uint4(ow[0], ow[1], ow[2], ow[3]);
+}
+// x_attn staging: elements 8 ch .. 8 ch + 7 of the attention output of (sequence m, head) -- the flash-decoding partials
+// of the position chunks up to the new token merged (fp32) and rounded once to T
+template <typename T>
+__device__ __forceinline__ uint4 attn_merge8(const SkinnyArgs& a, const int64_t p, int m, int head, int ch) {
+  using D = DT<T>;
+  int n_parts = (p < 0) ? 0 : static_cast<int>((p + a.att_chunk_pos) / a.att_chunk_pos);
+  if (n_parts > a.att_max_parts) n_parts = 0;               // position outside the cache: the attention phase raised err
+  const int H = a.K / AT_D;
+  const float* base = a.att_part + (static_cast<int64_t>(m) * H + head) * a.att_max_parts * AT_PART_STRIDE;
+  float M = neg_inf_f(), L = 0.f, acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int i0 = 0; i0 < n_parts; i0 += 4) {
+    float2 ml[4];
+    float4 oa[4], ob[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u < n_parts ? i0 + u : n_parts - 1;
+      const float* src = base + i * AT_PART_STRIDE;
+      ml[u] = __ldcg(reinterpret_cast<const float2*>(src));
+      oa[u] = __ldcg(reinterpret_cast<const float4*>(src + 4 + 8 * ch));
+      ob[u] = __ldcg(reinterpret_cast<const float4*>(src + 8 + 8 * ch));
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (i0 + u < n_parts && ml[u].y > 0.f) {
+        const float Mn = fmaxf(M, ml[u].x);
+        const float c0 = expf(M - Mn), c1 = expf(ml[u].x - Mn);
+        L = fmaf(L, c0, ml[u].y * c1);
+        acc[0] = fmaf(acc[0], c0, oa[u].x * c1); acc[1] = fmaf(acc[1], c0, oa[u].y * c1);
+        acc[2] = fmaf(acc[2], c0, oa[u].z * c1); acc[3] = fmaf(acc[3], c0, oa[u].w * c1);
+        acc[4] = fmaf(acc[4], c0, ob[u].x * c1); acc[5] = fmaf(acc[5], c0, ob[u].y * c1);
+        acc[6] = fmaf(acc[6], c0, ob[u].z * c1); acc[7] = fmaf(acc[7], c0, ob[u].w * c1);
+        M = Mn;
+      }
+    }
+  }
+  const float inv = L > 0.f ? 1.0f / L : 0.f;
+  return make_uint4(D::pack2(acc[0] * inv, acc[1] * inv), D::pack2(acc[2] * inv, acc[3] * inv),
+                    D::pack2(acc[4] * inv, acc[5] * inv), D::pack2(acc[6] * inv, acc[7] * inv));
 }
 // mbarrier wait without bookkeeping instructions in the retry path (try_wait suspends in hardware)
 __device__ __forceinline__ void mbar_arrive_u32(uint32_t bar) {
@@ -324,6 +369,16 @@ __device__ __forceinline__ void mbar_wait_tight_u32(uint32_t bar, uint32_t parit
 
 // 8-byte accesses of the stream-K fix-up slots: .volatile keeps them out of L1 and un-merged; an aligned
 // 8-byte access is single-copy atomic, so {value, flag} is observed whole or not at all
+#ifdef SK_LL_GPU_SCOPE
+__device__ __forceinline__ uint2 ld_volatile_u2(const uint2* p) {
+  uint2 v;
+  asm volatile("ld.relaxed.gpu.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_volatile_u2(uint2* p, uint2 v) {
+  asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1,%2};" :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+#else
 __device__ __forceinline__ uint2 ld_volatile_u2(const uint2* p) {
   uint2 v;
   asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
@@ -332,6 +387,7 @@ __device__ __forceinline__ uint2 ld_volatile_u2(const uint2* p) {
 __device__ __forceinline__ void st_volatile_u2(uint2* p, uint2 v) {
   asm volatile("st.volatile.global.v2.u32 [%0], {%1,%2};" :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
 }
+#endif
 
 #ifdef SK_TIMING
 // debug build: per-CTA cycle breakdown (consumer warp 0 / producer), read back by q100_debug_skinny_timing
@@ -351,15 +407,51 @@ __device__ __forceinline__ long long gtime() { long long t; asm volatile("mov.u6
 // 8-bit limbs per (token, 128-k block), one mma column each, MB = ceil(3 M / 8) column groups.  The integer
 // contraction is exact; x is rounded once to 2^-22 of its block maximum (below fp32 accumulation noise).
 struct RingPos { uint32_t soff, boff; int sleft; uint32_t ph; };   // consumer position in the weight ring
+__device__ __forceinline__ void chain_stamp(unsigned long long* row, int i) {
+  if (row != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    row[i] = t;
+  }
+}
+
+// chain mode: fixed places at the start of the dynamic shared memory, so that the GEMM share of a phase needs no
+// arguments at all (see consumer_gemm_call): the phase being executed, 1 / rms of each token (x_norm), the consumers'
+// ring position (uniform over the consumer threads; carried from one GEMM phase to the next) and the ring's mbarriers
+constexpr size_t CH_TRACE_OFF = 8192;                             // descriptor header: barrier stamps [phases][3]
+constexpr size_t CH_CTA_TRACE_OFF = 8192 + 24 * CH_MAX_PHASES;    // ... and [512 CTAs][8] stamps of the traced phase
+constexpr int CH_SM_PHASE = 0;
+constexpr int CH_SM_RSTD = 512;
+constexpr int CH_SM_RPOS = 640;
+constexpr int CH_SM_POS = 656;                       // int64: the device-side position, read once per launch
+constexpr int CH_SM_TRACE = 704;                     // development: global pointer to this CTA's stamp row, or null
+constexpr int CH_SM_FULL = 768;
+constexpr int CH_SM_EMPTY = 768 + 8 * SK_MAX_STAGES;
+constexpr int CH_SM_ATT = 1024;                      // attention phase: 8 warps x 4 heads x AT_PART_STRIDE floats
+constexpr int CH_SM_NEXT = 1024 + 8 * 4 * AT_PART_STRIDE * 4;     // the next phase's arguments, prefetched with cp.async
+constexpr int CH_SM_RING = CH_SM_NEXT + CH_PHASE_BYTES;
+static_assert(CH_SM_RING % 128 == 0, "ring must stay 128-byte aligned");
+constexpr size_t CH_POS_SLOT_OFF = 4128;                          // descriptor header: pointer to the position scalar
 
 // The consumer warps' share of ONE dequant-GEMM: stage x, pull landed blocks out of the ring, contract, write y or
-// hand the fragment to the stream-K fix-up.  Inlined into k3_skinny; k3_chain calls it once per GEMM phase through
-// consumer_gemm_call (not inlined there: its register allocation stays what it is in k3_skinny, the chain's own state
-// is saved around the call instead of competing with the inner loop -- inlined, the loop spilled 26 values per block).
+// hand the fragment to the stream-K fix-up.  Inlined into k3_skinny.  k3_chain runs it once per GEMM phase; with three
+// CTAs per SM (72 registers) it is a function of its own there (consumer_gemm_call) that finds everything it needs in
+// shared memory: inlined next to the phase loop and the attention code, ptxas kept the ring position and the per-lane
+// operand addresses in local memory inside the block loop (26 LDL/STL per block; the loop ran at half speed).
 template <typename T, int NBITS, int MB, int MODE, bool CHAIN>
-__device__ __forceinline__ void consumer_gemm(const SkinnyArgs& a, const int G, const uint32_t ring_u32, uint8_t* ring_ptr,
-                                              const uint32_t full_base, const uint32_t empty_base,
-                                              const float* s_rstd, RingPos& rp) {
+__device__ __forceinline__ void consumer_gemm(const SkinnyArgs& a_in, const uint32_t full_in, const uint32_t empty_in) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const SkinnyArgs* ap = &a_in;
+  if constexpr (CHAIN) ap = &reinterpret_cast<const ChainPhase*>(smem_raw + CH_SM_PHASE)->g;
+  const SkinnyArgs& a = *ap;
+  const int G = CHAIN ? reinterpret_cast<const ChainPhase*>(smem_raw + CH_SM_PHASE)->grid_p : static_cast<int>(gridDim.x);
+  const uint32_t ring_u32 = CHAIN ? smem_u32(smem_raw) + CH_SM_RING : ((smem_u32(smem_raw) + 127u) & ~127u);
+  uint8_t* ring_ptr = smem_raw + (ring_u32 - smem_u32(smem_raw));
+  const uint32_t full_base = CHAIN ? smem_u32(smem_raw) + CH_SM_FULL : full_in;
+  const uint32_t empty_base = CHAIN ? smem_u32(smem_raw) + CH_SM_EMPTY : empty_in;
+  const float* s_rstd = reinterpret_cast<const float*>(smem_raw + CH_SM_RSTD);
+  RingPos rp{0u, 0u, a.stages, 0u};
+  if constexpr (CHAIN) rp = *reinterpret_cast<const RingPos*>(smem_raw + CH_SM_RPOS);
   using T2 = typename DQ<T>::T2;
   constexpr bool POST = MODE == 1;
   constexpr bool IMMA = MODE == 2;
@@ -425,7 +517,10 @@ __device__ __forceinline__ void consumer_gemm(const SkinnyArgs& a, const int G, 
             // x was written by other SMs earlier in this launch: read it through L2 (ld.global.cg), never L1
             if (a.x_gate_up) {
               const T* gp = xg + static_cast<int64_t>(rem >> 4) * (2 * a.K) + kblk * SK_KB + (rem & 15) * 8;
-              vq[u] = silu_mul8<T>(__ldcg(reinterpret_cast<const uint4*>(gp)), __ldcg(reinterpret_cast<const uint4*>(gp + a.K)));
+              vq[u] = silu_mul8_inl<T>(__ldcg(reinterpret_cast<const uint4*>(gp)), __ldcg(reinterpret_cast<const uint4*>(gp + a.K)));
+            } else if (a.x_attn) {
+              vq[u] = attn_merge8<T>(a, *reinterpret_cast<const int64_t*>(smem_raw + CH_SM_POS), rem >> 4, kblk,
+                                     rem & 15);                                 // k block == head (head_dim 128)
             } else {
               const int kofs = kblk * SK_KB + (rem & 15) * 8;
               vq[u] = __ldcg(reinterpret_cast<const uint4*>(xg + static_cast<int64_t>(rem >> 4) * a.K + kofs));
@@ -862,25 +957,39 @@ __device__ __forceinline__ void consumer_gemm(const SkinnyArgs& a, const int G, 
 #pragma unroll
       for (int i = 0; i < MB * 4; ++i) dst[i] = ld_volatile_u2(wst + static_cast<int64_t>(sl) * FRAG + i * 32 + lane);
     };
-    // the loads of up to RB slots are put in flight together: the reducer pays about one L2 round trip per
-    // batch instead of one per contributor (profiles/r01k: the serial version kept the reducers 3-4 us past
-    // the median CTA); the sum still runs in slot order, so the result stays deterministic
+    // the loads of up to RB slots are in flight together, and when some of them have not landed yet ALL the missing
+    // ones of the batch are requested again together: the reducer pays about one L2 round trip per round, not one per
+    // late contributor (measured with per-CTA time stamps, profiles/r02_chain_cta_trace.txt: re-fetching one slot at
+    // a time kept the reducer of a 10-way split tile 8 us past the last contributor -- they all finish within a
+    // microsecond of each other, i.e. every slot was late once).  The sum still runs in slot order: deterministic.
     constexpr int RB = MB == 1 ? 6 : MB == 2 ? 3 : 2;
     for (int base = 0; base < pend_n; base += RB) {
       uint2 buf[RB][MB * 4];
+      uint32_t ready = 0;                                     // warp-uniform: slots of the batch that are complete
+      const int nb = min(RB, pend_n - base);
+      const uint32_t all = (1u << nb) - 1u;
+      for (;;) {
+        if constexpr (CHAIN) {                                // development: count the polling rounds of warp 0
+          unsigned long long* row = *reinterpret_cast<unsigned long long**>(smem_raw + CH_SM_TRACE);
+          if (tid == 0 && row != nullptr) row[7] = (base == 0 && ready == 0 ? 0ull : row[7]) + 1ull;
+        }
 #pragma unroll
-      for (int s = 0; s < RB; ++s)
-        if (base + s < pend_n) fetch(buf[s], base + s);
+        for (int s = 0; s < RB; ++s)
+          if (s < nb && !((ready >> s) & 1u)) fetch(buf[s], base + s);
 #pragma unroll
-      for (int s = 0; s < RB; ++s) {
-        if (base + s < pend_n) {
-          for (;;) {
+        for (int s = 0; s < RB; ++s) {
+          if (s < nb && !((ready >> s) & 1u)) {
             uint32_t ok = 1;
 #pragma unroll
             for (int i = 0; i < MB * 4; ++i) ok &= buf[s][i].y;
-            if (__all_sync(0xffffffffu, ok != 0)) break;
-            fetch(buf[s], base + s);
+            if (__all_sync(0xffffffffu, ok != 0)) ready |= 1u << s;
           }
+        }
+        if (ready == all) break;
+      }
+#pragma unroll
+      for (int s = 0; s < RB; ++s) {
+        if (s < nb) {
 #pragma unroll
           for (int i = 0; i < MB * 4; ++i) {
             v[i >> 2][i & 3] += __uint_as_float(buf[s][i].x);
@@ -888,6 +997,9 @@ __device__ __forceinline__ void consumer_gemm(const SkinnyArgs& a, const int G, 
           }
         }
       }
+    }
+    if constexpr (CHAIN) {
+      if (tid == 0) chain_stamp(*reinterpret_cast<unsigned long long**>(smem_raw + CH_SM_TRACE), 1);   // polls done
     }
     write_fragment(v, pend_tile * SK_ROWS);
     pend_tile = -1;
@@ -933,6 +1045,9 @@ __device__ __forceinline__ void consumer_gemm(const SkinnyArgs& a, const int G, 
     bar_sync_consumers();                       // everyone is done with the previous slab
     stage_x(qc, nblk);
     bar_sync_consumers();
+    if constexpr (CHAIN) {
+      if (tid == 0 && qc == q_begin) chain_stamp(*reinterpret_cast<unsigned long long**>(smem_raw + CH_SM_TRACE), 3);
+    }
 #ifdef SK_TIMING
     c_stage += clock64() - ts0;
 #endif
@@ -972,8 +1087,16 @@ __device__ __forceinline__ void consumer_gemm(const SkinnyArgs& a, const int G, 
 #ifdef SK_TIMING
   if (tid == 0 && cta < 512) g_sk_w[a.seq & 15][cta][2] = pend_tile >= 0 ? gtime() : -gtime();
 #endif
+  if constexpr (CHAIN) {
+    if (tid == 0) chain_stamp(*reinterpret_cast<unsigned long long**>(smem_raw + CH_SM_TRACE), 4);
+  }
   if (pend_tile >= 0) resolve_pending();
-  rp.soff = soff; rp.boff = boff; rp.sleft = sleft; rp.ph = ph;
+  if constexpr (CHAIN) {
+    if (tid == 0) {
+      *reinterpret_cast<RingPos*>(smem_raw + CH_SM_RPOS) = RingPos{soff, boff, sleft, ph};
+      chain_stamp(*reinterpret_cast<unsigned long long**>(smem_raw + CH_SM_TRACE), 5);
+    }
+  }
 #ifdef SK_TIMING
   if (tid == 0 && cta < 512) g_sk_w[a.seq & 15][cta][3] = gtime();
   if (tid == 0) {
@@ -984,16 +1107,13 @@ __device__ __forceinline__ void consumer_gemm(const SkinnyArgs& a, const int G, 
 }
 
 template <typename T, int NBITS, int MB, int MODE>
-__device__ __noinline__ void consumer_gemm_call(const SkinnyArgs& a, const int G, const uint32_t ring_u32, uint8_t* ring_ptr,
-                                                const uint32_t full_base, const uint32_t empty_base,
-                                                const float* s_rstd, RingPos& rp) {
-  consumer_gemm<T, NBITS, MB, MODE, true>(a, G, ring_u32, ring_ptr, full_base, empty_base, s_rstd, rp);
+__device__ __noinline__ void consumer_gemm_call() {
+  consumer_gemm<T, NBITS, MB, MODE, true>(SkinnyArgs{}, 0u, 0u);
 }
-
 
 // CHAIN: the kernel body run over a list of phases (q100_chain.cuh) instead of one GEMM; `a_in` then carries what
 // is common to all GEMM phases (M, group, ring geometry, workspace) and the per-phase arguments come from `ch`.
-template <typename T, int NBITS, int MB, int MODE, bool CHAIN>
+template <typename T, int NBITS, int MB, int MODE, bool CHAIN, bool INLINE_GEMM = true>
 __device__ __forceinline__ void skinny_body(const SkinnyArgs& a_in, const ChainArgs& ch) {
   using T2 = typename DQ<T>::T2;
   constexpr bool POST = MODE == 1;
@@ -1007,15 +1127,19 @@ __device__ __forceinline__ void skinny_body(const SkinnyArgs& a_in, const ChainA
   constexpr int FRAG = SK_ROWS * MB * 8;              // floats per partial tile
 
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  __shared__ uint64_t full_bar[SK_MAX_STAGES], empty_bar[SK_MAX_STAGES];
-  // chain mode: the current phase (copied from global memory by the consumers) and the per-token 1 / rms of x_norm
-  __shared__ typename std::conditional<CHAIN, ChainPhase, int>::type s_ph;
-  __shared__ float s_rstd[CHAIN ? 32 : 1];
+  __shared__ uint64_t full_bar_s[CHAIN ? 1 : SK_MAX_STAGES], empty_bar_s[CHAIN ? 1 : SK_MAX_STAGES];
+  uint64_t* full_bar = full_bar_s;
+  uint64_t* empty_bar = empty_bar_s;
+  if constexpr (CHAIN) {                              // chain mode: everything at fixed places of the dynamic region
+    full_bar = reinterpret_cast<uint64_t*>(smem_raw + CH_SM_FULL);
+    empty_bar = reinterpret_cast<uint64_t*>(smem_raw + CH_SM_EMPTY);
+  }
+  ChainPhase& s_ph = *reinterpret_cast<ChainPhase*>(smem_raw + CH_SM_PHASE);
+  float* s_rstd = reinterpret_cast<float*>(smem_raw + CH_SM_RSTD);
   const SkinnyArgs* ap = &a_in;
   if constexpr (CHAIN) ap = &s_ph.g;
   const SkinnyArgs& a = *ap;                          // per-phase arguments (== a_in without CHAIN)
-  const uint32_t ring_u32 = (smem_u32(smem_raw) + 127u) & ~127u;
-  uint8_t* ring_ptr = smem_raw + (ring_u32 - smem_u32(smem_raw));
+  const uint32_t ring_u32 = CHAIN ? smem_u32(smem_raw) + CH_SM_RING : ((smem_u32(smem_raw) + 127u) & ~127u);
   const int stage_pitch = (stage_bytes<NBITS>(a_in.nsub) + 127) & ~127;
   const int stages = a_in.stages;
 
@@ -1122,9 +1246,25 @@ __device__ __forceinline__ void skinny_body(const SkinnyArgs& a_in, const ChainA
     return;
   }
 
-  RingPos rp{0u, 0u, stages, 0u};
   if constexpr (CHAIN) {
     pdl_wait();
+    if (tid == 0) {
+      *reinterpret_cast<RingPos*>(smem_raw + CH_SM_RPOS) = RingPos{0u, 0u, stages, 0u};
+      // the position does not change during a launch: one read for all attention phases
+      const int64_t* pp = *ch.pos_pp;
+      *reinterpret_cast<int64_t*>(smem_raw + CH_SM_POS) = pp != nullptr ? __ldcg(pp) : -1;
+    }
+    // phase arguments: the first set straight from global memory, every later one prefetched with cp.async into a
+    // second slot while its predecessor runs (static data: never waits for anything)
+    auto prefetch_phase = [&](int p) {
+      if (tid < CH_PHASE_BYTES / 16) {
+        const uint32_t dst = smem_u32(smem_raw) + CH_SM_NEXT + tid * 16;
+        const void* src = reinterpret_cast<const uint8_t*>(ch.phases + p) + tid * 16;
+        if (tid * 16 < static_cast<int>(sizeof(ChainPhase)))
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
+      }
+    };
+    prefetch_phase(0);
     // grid barrier between phases: every CTA of the (fully resident) grid arrives once per phase.  bar.sync orders the
     // CTA's y / ssq stores before thread 0's gpu-scope fence + arrival; the acquire on the way out (+ reading x
     // through L2) makes the other CTAs' stores visible.  A bounded spin: a protocol bug sets err instead of hanging.
@@ -1132,27 +1272,56 @@ __device__ __forceinline__ void skinny_body(const SkinnyArgs& a_in, const ChainA
       bar_sync_consumers();
       if (tid == 0) {
         __threadfence();
+        if (ch.trace != nullptr) {
+          unsigned long long t0;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+          atomicMin(ch.trace + 3 * p, t0);
+          atomicMax(ch.trace + 3 * p + 1, t0);
+        }
         atomicAdd(ch.bars + p, 1u);
         uint32_t spins = 0;
-        while (ld_acquire_gpu_u32(ch.bars + p) < gridDim.x) {
-          __nanosleep(40);
+        // relaxed polls with a back-off (hundreds of CTAs wait here for the phases only a part of the grid works on),
+        // one fence on the way out
+        while (ld_relaxed_gpu_u32(ch.bars + p) < gridDim.x) {
+          __nanosleep(100);
           ++spins;
           // give up after ~2 s, and at once if another barrier already did: the launch then ends quickly instead of
           // serialising one time-out per phase
           if (spins > (1u << 22) || ((spins & 1023u) == 0 && ld_acquire_gpu_u32(ch.err) != 0u)) { *ch.err = 1u; break; }
         }
         __threadfence();
+        if (ch.trace != nullptr) {
+          unsigned long long t1;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+          atomicMax(ch.trace + 3 * p + 2, t1);
+        }
       }
       bar_sync_consumers();
     };
     for (int p = 0; p < ch.n_phases; ++p) {
       bar_sync_consumers();                                   // everyone is done with the previous phase's arguments
-      {
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(ch.phases + p);
-        uint32_t* dst = reinterpret_cast<uint32_t*>(&s_ph);
-        for (int i = tid; i < static_cast<int>(sizeof(ChainPhase) / 4); i += SK_CTHREADS) dst[i] = __ldg(src + i);
+      unsigned long long* tr_row = nullptr;
+      if (tid == 0) {
+        if (ch.trace != nullptr && cta == 0 && (p == 0 || p == ch.n_phases - 1)) {
+          // SM clock over the launch: cycles and nanoseconds at the first and the last phase (last trace row)
+          unsigned long long tns;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tns));
+          unsigned long long* r = ch.trace + 3 * (CH_MAX_PHASES - 2) + (p == 0 ? 0 : 2);
+          r[0] = static_cast<unsigned long long>(clock64());
+          r[1] = tns;
+        }
+        if (ch.trace != nullptr && p == ch.trace_phase && cta < 512)
+          tr_row = ch.trace + (CH_CTA_TRACE_OFF - CH_TRACE_OFF) / 8 + cta * 8;
+        *reinterpret_cast<unsigned long long**>(smem_raw + CH_SM_TRACE) = tr_row;
+        chain_stamp(tr_row, 0);
       }
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      bar_sync_consumers();                                   // the prefetched arguments of phase p have landed
+      if (tid < static_cast<int>(sizeof(ChainPhase) / 16))
+        reinterpret_cast<uint4*>(&s_ph)[tid] = reinterpret_cast<const uint4*>(smem_raw + CH_SM_NEXT)[tid];
       bar_sync_consumers();
+      if (p + 1 < ch.n_phases) prefetch_phase(p + 1);
+      if (tid == 0) chain_stamp(tr_row, 1);
       if (s_ph.type == PH_GEMM) {
         G = s_ph.grid_p;
         if (cta < G) {
@@ -1161,21 +1330,34 @@ __device__ __forceinline__ void skinny_body(const SkinnyArgs& a_in, const ChainA
             // 1 / rms of every token of the residual stream from the partial sums the producing phase left
             for (int m = warp; m < mrows; m += SK_CWARPS) {
               float tot = 0.f;
-              for (int i = lane; i < a.n_part_in; i += 32) tot += __ldcg(a.ssq_in + static_cast<int64_t>(i) * mrows + m);
+              for (int i0 = 0; i0 < a.n_part_in; i0 += 256) {     // eight independent loads per lane in flight
+                float pv[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                  const int i = i0 + u * 32 + lane;
+                  pv[u] = i < a.n_part_in ? __ldcg(a.ssq_in + static_cast<int64_t>(i) * mrows + m) : 0.f;
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) tot += pv[u];
+              }
 #pragma unroll
               for (int d = 16; d > 0; d >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, d);
               if (lane == 0) s_rstd[m] = rsqrtf(__fadd_rn(__fdiv_rn(tot, static_cast<float>(a.K)), a.eps));
             }
           }
           // (the first bar_sync inside publishes s_rstd)
-          consumer_gemm_call<T, NBITS, MB, MODE>(a, G, ring_u32, ring_ptr, smem_u32(&full_bar[0]), smem_u32(&empty_bar[0]),
-                                                 s_rstd, rp);
+          if (tid == 0) chain_stamp(tr_row, 2);
+          if constexpr (INLINE_GEMM) consumer_gemm<T, NBITS, MB, MODE, true>(a_in, 0u, 0u);
+          else consumer_gemm_call<T, NBITS, MB, MODE>();
         }
       } else if (s_ph.type == PH_ATTN) {
-        chain_attn<T>(s_ph.at, cta, static_cast<int>(gridDim.x), warp, lane);
+        chain_attn<T>(s_ph.at, *reinterpret_cast<const int64_t*>(smem_raw + CH_SM_POS),
+                      reinterpret_cast<float*>(smem_raw + CH_SM_ATT), cta, static_cast<int>(gridDim.x), warp, lane);
       } else {
-        chain_combine<T>(s_ph.at, cta, static_cast<int>(gridDim.x), warp, lane);
+        chain_combine<T>(s_ph.at, *reinterpret_cast<const int64_t*>(smem_raw + CH_SM_POS), cta,
+                         static_cast<int>(gridDim.x), warp, lane);
       }
+      if (tid == 0) chain_stamp(tr_row, 6);
       if (p + 1 < ch.n_phases) grid_barrier(p);
     }
     // the last CTA out leaves the arrival counters zeroed for the next launch
@@ -1188,8 +1370,7 @@ __device__ __forceinline__ void skinny_body(const SkinnyArgs& a_in, const ChainA
       }
     }
   } else {
-    consumer_gemm<T, NBITS, MB, MODE, false>(a_in, G, ring_u32, ring_ptr, smem_u32(&full_bar[0]), smem_u32(&empty_bar[0]),
-                                             s_rstd, rp);
+    consumer_gemm<T, NBITS, MB, MODE, false>(a_in, smem_u32(&full_bar[0]), smem_u32(&empty_bar[0]));
   }
 }
 
@@ -1200,10 +1381,15 @@ k3_skinny(const SkinnyArgs a) {
 }
 
 // the chain form: same body, phases from device memory (q100_chain.cuh)
-template <typename T, int NBITS, int MB, int MODE>
-__global__ void __launch_bounds__(SK_THREADS, MB <= 1 ? SK_OCC : 2)
+#ifndef CHAIN_LB
+#define CHAIN_LB(occ) (occ)
+#endif
+// OCC = resident CTAs per SM the instantiation is compiled for: 3 leaves 72 registers per thread (the GEMM share is then
+// a separate function, see consumer_gemm_call), 2 leaves 112 (everything inlined, no spills)
+template <typename T, int NBITS, int MB, int MODE, int OCC>
+__global__ void __launch_bounds__(SK_THREADS, CHAIN_LB(OCC))
 k3_chain(const SkinnyArgs a, const ChainArgs ch) {
-  skinny_body<T, NBITS, MB, MODE, true>(a, ch);
+  skinny_body<T, NBITS, MB, MODE, true, (OCC < 3)>(a, ch);
 }
 
 // ---------------------------------------------------------------- host
@@ -1383,18 +1569,24 @@ int gemm_skinny(const void* x, const void* packed, const void* meta, const void*
 
 
 // ---------------------------------------------------------------- chain: host side
-constexpr size_t CH_HEADER_BYTES = 8192;          // arrival counters [CH_MAX_PHASES + 1], error flag; then ChainPhase[n]
+constexpr size_t CH_HEADER_BYTES = 8192 + 24 * CH_MAX_PHASES + 512 * 64;   // arrival counters [CH_MAX_PHASES + 1], error flag (8 KB); trace stamps; then ChainPhase[n]
+
 constexpr int CH_ERR_WORD = CH_MAX_PHASES + 4;
 constexpr int CH_CHUNK_CAP = 16;                  // k blocks of x staged per round (gate|up: 16 blocks per CTA at 444 CTAs)
 
 struct ChainGeom { int smem, stages, chunk, grid, mb, mode; };
 
-template <typename T, int NBITS, int MB, int MODE>
+static int chain_occ_env() {
+  static const int v = []() { const char* e = getenv("Q100_CHAIN_OCC"); return e ? atoi(e) : 0; }();
+  return v;
+}
+
+template <typename T, int NBITS, int MB, int MODE, int OCC>
 static int chain_geometry_t(int m_rows, ChainGeom& g) {
-  auto kern = k3_chain<T, NBITS, MB, MODE>;
+  auto kern = k3_chain<T, NBITS, MB, MODE, OCC>;
   constexpr int xpitch = MODE == 2 ? SK_IPITCH : SK_XPITCH;
-  constexpr int occ_target = MB <= 1 ? SK_OCC : 2;
-  const int budget = (228 * 1024) / occ_target - 1024 - 512 - 128 - static_cast<int>(sizeof(ChainPhase)) - 256;
+  constexpr int occ_target = OCC;
+  const int budget = (228 * 1024) / occ_target - 1024 - 128 - CH_SM_RING - 256;
   const int stage_pitch = (stage_bytes<NBITS>(1) + 127) & ~127;
   const int row_b = m_rows * xpitch;
   int min_stages = (2 * budget / 3) / stage_pitch;
@@ -1405,7 +1597,7 @@ static int chain_geometry_t(int m_rows, ChainGeom& g) {
   Q100_REQUIRE(chunk >= 1, Q100_EUNSUPPORTED, "k3_chain: M=%d rows of x do not fit in shared memory", m_rows);
   int stages = (budget - slab_bytes(m_rows, chunk, xpitch)) / stage_pitch;
   if (stages > SK_MAX_STAGES) stages = SK_MAX_STAGES;
-  const int smem = stages * stage_pitch + slab_bytes(m_rows, chunk, xpitch) + 128;
+  const int smem = CH_SM_RING + stages * stage_pitch + slab_bytes(m_rows, chunk, xpitch) + 128;
   static std::mutex mu;
   static int max_set[kMaxDevices] = {};
   int occ = 0;
@@ -1425,9 +1617,9 @@ static int chain_geometry_t(int m_rows, ChainGeom& g) {
   return Q100_OK;
 }
 
-template <typename T, int NBITS, int MB, int MODE>
+template <typename T, int NBITS, int MB, int MODE, int OCC>
 static int chain_launch_t(const SkinnyArgs& a, const ChainArgs& ch, const ChainGeom& g, cudaStream_t st) {
-  auto kern = k3_chain<T, NBITS, MB, MODE>;
+  auto kern = k3_chain<T, NBITS, MB, MODE, OCC>;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(g.grid);
   cfg.blockDim = dim3(SK_THREADS);
@@ -1437,14 +1629,23 @@ static int chain_launch_t(const SkinnyArgs& a, const ChainArgs& ch, const ChainG
 }
 
 // the one place that maps (dtype, bits, M) to an instantiation: op 0 = geometry, op 1 = launch
+template <typename T, int NBITS, int MB, int MODE>
+static int chain_dispatch_occ(int op, int M, const SkinnyArgs* a, const ChainArgs* ch, ChainGeom& g, cudaStream_t st) {
+  const int want = chain_occ_env();
+  if (MB <= 1 && want == 3)
+    return op == 0 ? chain_geometry_t<T, NBITS, MB, MODE, (MB <= 1 ? 3 : 2)>(M, g)
+                   : chain_launch_t<T, NBITS, MB, MODE, (MB <= 1 ? 3 : 2)>(*a, *ch, g, st);
+  return op == 0 ? chain_geometry_t<T, NBITS, MB, MODE, 2>(M, g) : chain_launch_t<T, NBITS, MB, MODE, 2>(*a, *ch, g, st);
+}
+
 template <typename T, int NBITS>
 static int chain_dispatch_bits(int op, int M, const SkinnyArgs* a, const ChainArgs* ch, ChainGeom& g, cudaStream_t st) {
   const bool imma = (NBITS == 4 || NBITS == 2) && M <= 2;
   if constexpr (NBITS == 4 || NBITS == 2) {
-    if (imma) return op == 0 ? chain_geometry_t<T, NBITS, 1, 2>(M, g) : chain_launch_t<T, NBITS, 1, 2>(*a, *ch, g, st);
+    if (imma) return chain_dispatch_occ<T, NBITS, 1, 2>(op, M, a, ch, g, st);
   }
-  if (M <= 8) return op == 0 ? chain_geometry_t<T, NBITS, 1, 1>(M, g) : chain_launch_t<T, NBITS, 1, 1>(*a, *ch, g, st);
-  return op == 0 ? chain_geometry_t<T, NBITS, 2, 1>(M, g) : chain_launch_t<T, NBITS, 2, 1>(*a, *ch, g, st);
+  if (M <= 8) return chain_dispatch_occ<T, NBITS, 1, 1>(op, M, a, ch, g, st);
+  return chain_dispatch_occ<T, NBITS, 2, 1>(op, M, a, ch, g, st);
 }
 static int chain_dispatch(int op, int dtype, int n_bits, int M, const SkinnyArgs* a, const ChainArgs* ch, ChainGeom& g,
                           cudaStream_t st) {
@@ -1491,7 +1692,7 @@ extern "C" int64_t q100_chain_ssq_parts(int64_t N) { return ((N + SK_ROWS - 1) /
 extern "C" int64_t q100_chain_attn_partial_floats(int batch, int heads, int64_t max_len) {
   if (batch <= 0 || heads <= 0 || max_len <= 0) return 0;
   const int cp = chain_attn_chunk(max_len);
-  return static_cast<int64_t>(batch) * heads * ((max_len + cp - 1) / cp) * 8 * AT_PART_STRIDE;
+  return static_cast<int64_t>(batch) * heads * ((max_len + cp - 1) / cp) * AT_PART_STRIDE;
 }
 
 extern "C" int q100_chain_build(const q100_phase* phases, int n_phases, int M, int group, int n_bits, int disable_zp,
@@ -1514,6 +1715,14 @@ extern "C" int q100_chain_build(const q100_phase* phases, int n_phases, int M, i
   if (rc != Q100_OK) return rc;
   std::vector<ChainPhase> host(n_phases);
   size_t need = 0;
+  const void* pos_ptr = nullptr;                          // the device-side position: one per chain
+  for (int i = 0; i < n_phases; ++i) {
+    const bool uses = phases[i].type != Q100_PH_GEMM || phases[i].x_mode == Q100_X_ATTN;
+    if (!uses) continue;
+    if (pos_ptr == nullptr) pos_ptr = phases[i].position;
+    Q100_REQUIRE(phases[i].position == pos_ptr, Q100_EINVAL,
+                 "phase %d: every attention phase of a chain must share one position scalar", i);
+  }
   for (int i = 0; i < n_phases; ++i) {
     const q100_phase& p = phases[i];
     ChainPhase& c = host[i];
@@ -1523,8 +1732,11 @@ extern "C" int q100_chain_build(const q100_phase* phases, int n_phases, int M, i
       Q100_REQUIRE(p.x && p.packed && p.meta && p.y, Q100_EINVAL, "phase %d: NULL pointer argument", i);
       Q100_REQUIRE(p.N > 0 && p.K > 0 && p.K % SK_KB == 0 && p.N % 8 == 0 && p.K % group == 0, Q100_EUNSUPPORTED,
                    "phase %d: N=%lld (%% 8), K=%lld (%% 128, %% group)", i, (long long)p.N, (long long)p.K);
-      Q100_REQUIRE(p.x_mode == Q100_X_PLAIN || p.x_mode == Q100_X_GATE_UP || p.x_mode == Q100_X_NORM, Q100_EINVAL,
-                   "phase %d: bad x_mode %d", i, p.x_mode);
+      Q100_REQUIRE(p.x_mode == Q100_X_PLAIN || p.x_mode == Q100_X_GATE_UP || p.x_mode == Q100_X_NORM ||
+                   p.x_mode == Q100_X_ATTN, Q100_EINVAL, "phase %d: bad x_mode %d", i, p.x_mode);
+      if (p.x_mode == Q100_X_ATTN)
+        Q100_REQUIRE(p.att_partials && p.position && p.max_len > 0 && p.heads > 0 && p.K == static_cast<int64_t>(p.heads) * AT_D,
+                     Q100_EINVAL, "phase %d: x_mode ATTN needs att_partials / position / max_len and K == heads * 128", i);
       Q100_REQUIRE(p.epi_mode == Q100_EPI_STORE || p.epi_mode == Q100_EPI_ADD_SSQ, Q100_EINVAL, "phase %d: bad epi_mode", i);
       if (p.x_mode == Q100_X_NORM)
         Q100_REQUIRE(p.norm_weight && p.ssq_in && p.ssq_in_parts > 0, Q100_EINVAL, "phase %d: x_mode NORM needs norm_weight / ssq_in", i);
@@ -1545,6 +1757,13 @@ extern "C" int q100_chain_build(const q100_phase* phases, int n_phases, int M, i
       a.max_slots = static_cast<int>((static_cast<int64_t>(a.kblocks) * gp + a.total_units - 1) / a.total_units) + 2;
       a.x_gate_up = p.x_mode == Q100_X_GATE_UP;
       a.x_norm = p.x_mode == Q100_X_NORM;
+      a.x_attn = p.x_mode == Q100_X_ATTN;
+      if (a.x_attn) {
+        a.att_part = reinterpret_cast<const float*>(p.att_partials);
+        a.att_pos = reinterpret_cast<const int64_t*>(p.position);
+        a.att_chunk_pos = chain_attn_chunk(p.max_len);
+        a.att_max_parts = static_cast<int>((p.max_len + a.att_chunk_pos - 1) / a.att_chunk_pos);
+      }
       a.norm_w = p.norm_weight; a.ssq_in = reinterpret_cast<const float*>(p.ssq_in); a.n_part_in = p.ssq_in_parts;
       a.eps = p.eps;
       a.epi_add = p.epi_mode == Q100_EPI_ADD_SSQ;
@@ -1565,7 +1784,7 @@ extern "C" int q100_chain_build(const q100_phase* phases, int n_phases, int M, i
       t.k_cache = p.k_cache; t.v_cache = p.v_cache; t.part = reinterpret_cast<float*>(p.att_partials); t.out = p.att_out;
       t.B = p.batch; t.H = p.heads; t.KVH = p.kv_heads;
       t.chunk_pos = chain_attn_chunk(p.max_len);
-      t.max_parts = static_cast<int>((p.max_len + t.chunk_pos - 1) / t.chunk_pos) * 8;
+      t.max_parts = static_cast<int>((p.max_len + t.chunk_pos - 1) / t.chunk_pos);
       t.max_len = p.max_len; t.rope_len = p.rope_len;
       t.scale = 1.0f / sqrtf(static_cast<float>(AT_D));
       t.err = reinterpret_cast<uint32_t*>(desc) + CH_ERR_WORD;
@@ -1577,6 +1796,8 @@ extern "C" int q100_chain_build(const q100_phase* phases, int n_phases, int M, i
   Q100_REQUIRE(workspace != nullptr && workspace_bytes >= need, Q100_EWORKSPACE,
                "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
   Q100_CUDA(cudaMemsetAsync(desc, 0, CH_HEADER_BYTES, st));
+  Q100_CUDA(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(desc) + CH_POS_SLOT_OFF, &pos_ptr, sizeof(pos_ptr),
+                            cudaMemcpyHostToDevice, st));
   Q100_CUDA(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(desc) + CH_HEADER_BYTES, host.data(),
                             static_cast<size_t>(n_phases) * sizeof(ChainPhase), cudaMemcpyHostToDevice, st));
   Q100_CUDA(cudaStreamSynchronize(st));                    // `host` goes out of scope
@@ -1602,7 +1823,43 @@ extern "C" int q100_chain_run(void* desc, int n_phases, int M, int group, int n_
   ch.n_phases = n_phases;
   ch.bars = reinterpret_cast<uint32_t*>(desc);
   ch.err = reinterpret_cast<uint32_t*>(desc) + CH_ERR_WORD;
+  ch.pos_pp = reinterpret_cast<const int64_t* const*>(reinterpret_cast<uint8_t*>(desc) + CH_POS_SLOT_OFF);
+  static const bool want_trace = []() { const char* e = getenv("Q100_CHAIN_TRACE"); return e && e[0] == '1'; }();
+  ch.trace = want_trace ? reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(desc) + CH_TRACE_OFF) : nullptr;
+  static const int trace_phase = []() { const char* e = getenv("Q100_CHAIN_TRACE_PHASE"); return e ? atoi(e) : -1; }();
+  ch.trace_phase = trace_phase;
   return chain_dispatch(1, dtype, n_bits, M, &a, &ch, geo, st);
+}
+
+// development hook: the per-CTA stamps of the traced phase, [512][8] uint64
+extern "C" __attribute__((visibility("default"))) int q100_debug_chain_cta_trace(void* desc, unsigned long long* out, void* stream) {
+  Q100_REQUIRE(desc && out, Q100_EINVAL, "bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  Q100_CUDA(cudaMemcpyAsync(out, reinterpret_cast<uint8_t*>(desc) + CH_CTA_TRACE_OFF, 512 * 64, cudaMemcpyDeviceToHost, st));
+  Q100_CUDA(cudaStreamSynchronize(st));
+  return Q100_OK;
+}
+
+// development hook (not part of include/q100.h): barrier time stamps of the last traced launch, [n_phases][3] uint64;
+// re-arms the trace (first-arrival slots back to UINT64_MAX, the others to 0)
+extern "C" __attribute__((visibility("default"))) int q100_debug_chain_trace(void* desc, int n_phases, unsigned long long* out,
+                                                                             void* stream) {
+  Q100_REQUIRE(desc && out && n_phases >= 1 && n_phases <= CH_MAX_PHASES, Q100_EINVAL, "bad arguments");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t* tr = reinterpret_cast<uint8_t*>(desc) + CH_TRACE_OFF;
+  Q100_CUDA(cudaMemcpyAsync(out, tr, 24ull * n_phases, cudaMemcpyDeviceToHost, st));
+  Q100_CUDA(cudaStreamSynchronize(st));
+  {
+    unsigned long long c[4] = {0, 0, 0, 0};               // (cycles, ns) at the first and the last phase
+    Q100_CUDA(cudaMemcpy(c, tr + 24ull * (CH_MAX_PHASES - 2), sizeof(c), cudaMemcpyDeviceToHost));
+    if (c[3] > c[1]) fprintf(stderr, "[q100 chain trace] SM clock over the traced launch: %.0f MHz (%llu cycles in %llu ns)\n",
+                             1e3 * static_cast<double>(c[2] - c[0]) / static_cast<double>(c[3] - c[1]), c[2] - c[0], c[3] - c[1]);
+  }
+  std::vector<unsigned long long> init(3 * static_cast<size_t>(n_phases), 0ull);
+  for (int i = 0; i < n_phases; ++i) init[3 * i] = ~0ull;
+  Q100_CUDA(cudaMemcpyAsync(tr, init.data(), 24ull * n_phases, cudaMemcpyHostToDevice, st));
+  Q100_CUDA(cudaStreamSynchronize(st));
+  return Q100_OK;
 }
 
 extern "C" int q100_chain_error(const void* desc, void* stream) {

@@ -32,7 +32,7 @@ GEMM_X_GATE_UP = 0x100
 _vp, _i, _i64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
 
 PH_GEMM, PH_ATTN, PH_COMBINE = 0, 1, 2
-X_PLAIN, X_GATE_UP, X_NORM = 0, 1, 2
+X_PLAIN, X_GATE_UP, X_NORM, X_ATTN = 0, 1, 2, 3
 EPI_STORE, EPI_ADD_SSQ = 0, 1
 
 

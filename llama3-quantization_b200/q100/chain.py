@@ -42,8 +42,9 @@ class Chain:
         return t.data_ptr()
 
     def gemm(self, x, w, y, bias=None, x_mode=_lib.X_PLAIN, norm_weight=None, ssq_in=None, eps=0.0,
-             epi_mode=_lib.EPI_STORE, residual=None, ssq_out=None):
-        """y = x . dequant(w)^T; ``w`` is a q100.ops.PackedWeight."""
+             epi_mode=_lib.EPI_STORE, residual=None, ssq_out=None, attn=None):
+        """y = x . dequant(w)^T; ``w`` is a q100.ops.PackedWeight.  ``attn``: the dict :meth:`attention` returned, for
+        ``x_mode=X_ATTN`` (x merged from the attention partials while it is staged)."""
         if (w.n_bits, w.group, w.disable_zero_point, w.dtype) != (self.n_bits, self.group, self.disable_zp, self.dtype):
             raise ValueError("q100.chain: every weight of a chain must share bit width, group, zero-point mode and dtype")
         kx = 2 * w.K if x_mode == _lib.X_GATE_UP else w.K
@@ -58,6 +59,11 @@ class Chain:
             if ssq_in.dtype != torch.float32 or ssq_in.shape[1] != self.M:
                 raise ValueError("q100.chain: ssq_in must be fp32 [parts, M]")
             ph.norm_weight, ph.ssq_in, ph.ssq_in_parts = self._p(norm_weight.to(self.dtype)), self._p(ssq_in), ssq_in.shape[0]
+        if x_mode == _lib.X_ATTN:
+            if attn["heads"] * 128 != w.K:
+                raise ValueError("q100.chain: X_ATTN needs K == heads * 128")
+            ph.att_partials, ph.position = self._p(attn["partials"]), self._p(attn["position"])
+            ph.max_len, ph.heads = attn["max_len"], attn["heads"]
         if epi_mode == _lib.EPI_ADD_SSQ:
             if tuple(residual.shape) != (self.M, w.N) or tuple(ssq_out.shape) != (ssq_parts(w.N), self.M) \
                     or ssq_out.dtype != torch.float32:
@@ -66,12 +72,14 @@ class Chain:
         self.phases.append(ph)
         return ph
 
-    def attention(self, qkv, cos, sin, position, k_cache, v_cache, att_out, heads, kv_heads):
-        """Rotary + cache append + attention of the new token (two phases: partials, combine)."""
+    def attention(self, qkv, cos, sin, position, k_cache, v_cache, att_out, heads, kv_heads, combine=True):
+        """Rotary + cache append + attention of the new token.  ``combine=True`` adds the phase that merges the
+        position chunks into ``att_out``; with False the consumer is a GEMM phase with ``x_mode=X_ATTN`` that takes the
+        returned dict as ``attn``."""
         bsz, kvh, max_len, hd = k_cache.shape
         n = int(lib.q100_chain_attn_partial_floats(bsz, heads, max_len))
-        part = torch.empty(n, dtype=torch.float32, device=self.device)
-        for t in (_lib.PH_ATTN, _lib.PH_COMBINE):
+        part = torch.zeros(n, dtype=torch.float32, device=self.device)
+        for t in ((_lib.PH_ATTN, _lib.PH_COMBINE) if combine else (_lib.PH_ATTN,)):
             ph = Phase()
             ph.type = t
             ph.qkv, ph.cos_cache, ph.sin_cache, ph.position = self._p(qkv), self._p(cos), self._p(sin), self._p(position)
@@ -79,6 +87,7 @@ class Chain:
             ph.batch, ph.heads, ph.kv_heads, ph.head_dim = bsz, heads, kv_heads, hd
             ph.max_len, ph.rope_len = max_len, cos.shape[0]
             self.phases.append(ph)
+        return {"partials": part, "position": position, "max_len": max_len, "heads": heads}
 
     # ------------------------------------------------------------------ build / run
     def build(self):

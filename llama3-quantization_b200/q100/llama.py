@@ -222,8 +222,10 @@ class GraphDecoder:
 
     def __init__(self, model: QuantLlamaModel, bsz: int, max_len: int, use_graph: bool = True,
                  fused: bool = True, chain: Optional[bool] = None):
-        """``chain``: run all blocks of a step as ONE persistent launch (q100/chain.py, K9).  None = use it when the
-        model qualifies (single GPU, bsz <= 16, weight-only quantisation with group % 128 == 0, head_dim 128)."""
+        """``chain``: run all blocks of a step as ONE persistent launch (q100/chain.py, K9; the model must qualify:
+        single GPU, bsz <= 16, weight-only quantisation with group % 128 == 0, head_dim 128).  None = only when
+        Q100_CHAIN=1 is set: measured on B200 the chain is correct but not yet faster than the per-kernel route
+        (2.9 vs 2.1 ms per token for LLaMA3-8B at batch 1), so it stays opt-in."""
         from models.int_llama_layer import StaticKV
         self.fused = fused
         self.want_chain = chain
@@ -301,8 +303,9 @@ class GraphDecoder:
             else:
                 ch.gemm(b["h"], wqkv, b["qkv"], x_mode=_lib.X_NORM, norm_weight=layer.input_layernorm.weight,
                         ssq_in=b["ssq_a"], eps=layer.input_layernorm.variance_epsilon)
-            ch.attention(b["qkv"], cos, sin, self.pos, kv.k, kv.v, b["att"], nh, nkv)
-            ch.gemm(b["att"], wo, b["h"], epi_mode=_lib.EPI_ADD_SSQ, residual=b["h"], ssq_out=b["ssq_b"])
+            at = ch.attention(b["qkv"], cos, sin, self.pos, kv.k, kv.v, b["att"], nh, nkv, combine=False)
+            ch.gemm(b["att"], wo, b["h"], x_mode=_lib.X_ATTN, attn=at, epi_mode=_lib.EPI_ADD_SSQ, residual=b["h"],
+                    ssq_out=b["ssq_b"])
             ch.gemm(b["h"], wgu, b["gu"], x_mode=_lib.X_NORM, norm_weight=layer.post_attention_layernorm.weight,
                     ssq_in=b["ssq_b"], eps=layer.post_attention_layernorm.variance_epsilon)
             ch.gemm(b["gu"], wd, b["h"], x_mode=_lib.X_GATE_UP, epi_mode=_lib.EPI_ADD_SSQ, residual=b["h"],
@@ -355,7 +358,9 @@ class GraphDecoder:
             raise ValueError(f"GraphDecoder.prime: start_pos={start_pos} leaves no room in a cache of {self.max_len}")
         self.pos.fill_(start_pos)
         self._host_pos = start_pos
-        if self.chain is None and self.fused and self.want_chain is not False:
+        import os as _os
+        want = self.want_chain if self.want_chain is not None else _os.environ.get("Q100_CHAIN") == "1"
+        if self.chain is None and self.fused and want:
             self.chain = self._build_chain()
             if self.chain is None and self.want_chain:
                 raise RuntimeError("GraphDecoder: this model / batch does not qualify for the chain route")
