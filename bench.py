@@ -58,6 +58,15 @@ def peaks():
     return {"hbm": 6650.0, "tc_burst": 1590.0, "tc_sustained": 1400.0, "src": "fallback"}
 
 
+def ncu_traffic(key):
+    """dram bytes per launch of a kernel from the committed ncu --set full digest (profiles/ncu_traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return float(json.load(open(p))[key]["dram_bytes_per_launch"])
+    except Exception:                                               # noqa: BLE001
+        return None
+
+
 def step_flops(M=PREFILL_M):
     return sum(2.0 * M * n * k for _, n, k, _ in LINEARS)
 
@@ -304,10 +313,10 @@ def run_ours(args):
                 "achieved": ach, "peak": P["tc_burst"], "unit": "TFLOP/s", "frac": ach / P["tc_burst"],
                 "peak_src": P["src"] + " cuBLAS bf16 burst",
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel (single GPU, up_proj,
-                # M = 2048) from the committed ncu --set full capture, profiles/r01k_full_tca.md: 48.6 + 11.9 MB
-                # against 106.7 MB of algorithmic operand bytes (x 16.8, codes + side band 31.2, y 58.7 -- most of
-                # y is still in the 126 MB L2 when the kernel ends); null for shapes the capture does not cover
-                "traffic": 60.53e6 if (world == 1 and M_PRE == 2048) else None, "traffic_unit": "bytes per launch",
+                # M = 2048) from the committed ncu --set full capture (profiles/ncu_traffic.json names the capture and
+                # the command); null for shapes the capture does not cover
+                "traffic": ncu_traffic("k3_tca_up_proj_m2048") if (world == 1 and M_PRE == 2048) else None,
+                "traffic_unit": "bytes per launch", "traffic_src": "profiles/ncu_traffic.json",
                 "frac_of_sustained": ach / P["tc_sustained"]}
 
     # =============== decode shapes: packed-weight stream GB/s ===============
@@ -402,12 +411,17 @@ def run_ours(args):
         wq = [(torch.randn(INTER, HIDDEN, device=dev) * 0.02).to(torch.float16) for _ in range(3)]
         qi = [0]
 
+        # inputs AND outputs rotate through three buffers each (3 x 117 MB in, 3 x 117 / 29 MB out): the last three
+        # results stay alive, so the allocator cannot hand the same (L2-resident) block back and the write stream
+        # has to reach HBM like the read stream does
+        keep = [None, None, None]
+
         def q_fake():
-            q100.quantize_groupwise(wq[qi[0] % 3], GROUP, WBITS, want_dequant=True)
+            keep[qi[0] % 3] = q100.quantize_groupwise(wq[qi[0] % 3], GROUP, WBITS, want_dequant=True)
             qi[0] += 1
 
         def q_pack():
-            q100.quantize_groupwise(wq[qi[0] % 3], GROUP, WBITS, want_dequant=False, want_packed=True)
+            keep[qi[0] % 3] = q100.quantize_groupwise(wq[qi[0] % 3], GROUP, WBITS, want_dequant=False, want_packed=True)
             qi[0] += 1
 
         n_el = INTER * HIDDEN
@@ -417,7 +431,9 @@ def run_ours(args):
             torch.cuda.synchronize()
             msq = timed(fn, 30)
             gbs = n_el * bpe / (msq * 1e-3) / 1e9
-            quant[nm] = {"ms": msq, "GBps": gbs, "frac_hbm": gbs / P["hbm"], "bytes_per_element": bpe}
+            quant[nm] = {"ms": msq, "GBps": gbs, "frac_hbm": gbs / P["hbm"], "bytes_per_element": bpe,
+                         "outputs": "rotated over 3 live buffers"}
+            keep[:] = [None, None, None]
         del wq
         # K2: per-token activation fake-quant (the act_quantizer of the W8A8 / W4A4 configurations), prefill-size input
         xa = [torch.randn(M_PRE, HIDDEN, device=dev).to(torch.float16) for _ in range(3)]
@@ -477,10 +493,22 @@ def run_ours(args):
                              {"n_bits": 16, "per_channel_axes": [], "symmetric": False, "dynamic_method": "per_token"})
             ql.set_quant_state(True, False)
             mods.append((ql, src, mode))
-        hin = {k: (tp.shard_input(v, tp.ROW, rank, world) if (world > 1 and k != "h") else v).cpu().pin_memory()
-               for k, v in xs.items()}
-        hout = [torch.empty(M_PRE, ql.out_features, dtype=dt_t).pin_memory() for ql, _, _ in mods]
+        # host buffers hold what THIS rank is responsible for: its K-slice of the row-parallel inputs ("a", "m"), its
+        # 1/N of the token rows of the replicated input "h" (all-gathered over NVLink inside the step), its column
+        # shard of q/k/v/gate/up and its 1/N of the token rows of the all-reduced o / down outputs -- every byte of the
+        # step's inputs and outputs crosses PCIe exactly once over the whole job
+        rows_per = M_PRE // world
+        r0_, r1_ = rank * rows_per, (rank + 1) * rows_per
+
+        def host_in(k, v):
+            if world == 1:
+                return v
+            return v[r0_:r1_] if k == "h" else tp.shard_input(v, tp.ROW, rank, world)
+        hin = {k: host_in(k, v).contiguous().cpu().pin_memory() for k, v in xs.items()}
+        hout = [torch.empty((rows_per if (mode == tp.ROW and world > 1) else M_PRE), ql.out_features, dtype=dt_t).pin_memory()
+                for ql, _, mode in mods]
         din = {k: torch.empty(v.shape, dtype=dt_t, device=dev) for k, v in hin.items()}
+        h_full = torch.empty(M_PRE, HIDDEN, dtype=dt_t, device=dev) if world > 1 else None
 
         # copies ride their own streams: PCIe is full duplex and independent of the SMs, so the H2D of a later
         # input and the D2H of an earlier output overlap the GEMMs in between (still inside the timed step)
@@ -495,9 +523,18 @@ def run_ours(args):
                         din[k].copy_(hin[k], non_blocking=True)
                         ready[k] = s_in.record_event()
                 keep = []
+                gathered = False
                 for (ql, src, mode), ho in zip(mods, hout):
                     cur.wait_event(ready[src])
-                    y = tp.reduce_output(ql(din[src]), mode)
+                    xin = din[src]
+                    if src == "h" and world > 1:
+                        if not gathered:
+                            dist.all_gather_into_tensor(h_full, din["h"])
+                            gathered = True
+                        xin = h_full
+                    y = tp.reduce_output(ql(xin), mode)
+                    if mode == tp.ROW and world > 1:
+                        y = y[r0_:r1_]
                     done = cur.record_event()
                     with torch.cuda.stream(s_out):
                         s_out.wait_event(done)
@@ -522,8 +559,8 @@ def run_ours(args):
                "h2d_bytes_per_step": sum(v.numel() * 2 for v in hin.values()) * world,
                "d2h_bytes_per_step": sum(h.numel() * 2 for h in hout) * world,
                "api": "quant.int_linear.QuantLinear.forward (use_weight_quant=True), pinned host buffers, "
-                      "all ranks; bytes summed over ranks"}
-        del mods, hin, hout, din
+                      "all ranks; bytes summed over ranks (each rank moves its own 1/N of the replicated tensors)"}
+        del mods, hin, hout, din, h_full
 
     if rank == 0 and world == 1:
         # ---- CPU baseline on the host cores: bounded sample of the same workload (torch port)
@@ -598,14 +635,43 @@ def run_ours(args):
                      "decode_linear_fp16_weight_GBps": INTER * HIDDEN * 2 / (ms_dec * 1e-3) / 1e9}
         del wg, wd, wds, x2k, x1
 
+    # =============== strong scaling: the same block step at a FIXED total of 2048 tokens ===============
+    strong = None
+    if world > 1:
+        xs_s = make_inputs(PREFILL_M)
+        it_s = [0]
+
+        def strong_step():
+            block_step(blocks[it_s[0] % NB], xs_s)
+            it_s[0] += 1
+        for _ in range(3):
+            strong_step()
+        sync_all()
+        ms_s = timed(strong_step, args.steps)
+        sync_all()
+        ts_ = torch.tensor([ms_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(ts_, op=dist.ReduceOp.MAX)
+        ms_s = float(ts_.item())
+        strong = {"tokens": PREFILL_M, "ms_per_step": ms_s, "value": step_flops(PREFILL_M) / (ms_s * 1e-3) / 1e12,
+                  "unit": UNIT, "scaling": "strong"}
+        del xs_s
+
     # =============== whole model: random-init LLaMA3-8B W4A16 g128, tensor parallel ===========
-    model_res = None
+    model_res = model70_res = None
     if not os.environ.get("Q100_BENCH_SKIP_MODEL"):
         blocks.clear()
         fblocks.clear()
         torch.cuda.empty_cache()
         import bench_model
         model_res = bench_model.run(bench_model.default_args(ppl_samples=1, ppl_ref=True), dev, rank, world)
+        # SURVEY 8d config 5 (BASELINE.json configs[4]): LLaMA3-70B W4A16 g128, tensor parallel over all ranks (the
+        # packed model is 38 GB: it also fits one B200, so the row exists at every N).  Perplexity is compared on the
+        # first 4 blocks (the fp16 reference of all 80 does not fit next to the model).
+        model70_res = None
+        if not os.environ.get("Q100_BENCH_SKIP_70B"):
+            torch.cuda.empty_cache()
+            model70_res = bench_model.run(bench_model.default_args(model="70b", ppl_samples=1, ppl_ref=True, ppl_layers=4,
+                                                                   batches="1,16", decode_steps=24), dev, rank, world)
 
     if world > 1:
         from q100 import peer as _peer
@@ -619,7 +685,8 @@ def run_ours(args):
                 "config": WORKLOAD_CONFIG(M_PRE, world),
                 "notes": {"l2": "3 weight sets rotated; per-step working set (109 MB packed weights + 270 MB "
                                 "activations/outputs) exceeds the 126 MB L2", "force_skinny": bool(flags)},
-                "roofline": roofline, "decode": decode, "quantize": quant, "llama3_8b": model_res,
+                "roofline": roofline, "decode": decode, "quantize": quant, "strong_scaling": strong,
+                "llama3_8b": model_res, "llama3_70b": model70_res,
                 "cpu_baseline": cpu_base, "gpu_eager_reference_ops": gpu_eager, "e2e": e2e,
                 "gpu_launches": n_launch, "clocks": clocks, "peaks": P}
         print(json.dumps(line), flush=True)

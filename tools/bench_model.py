@@ -15,8 +15,9 @@ import torch.distributed as dist
 
 
 def default_args(**kw):
-    a = argparse.Namespace(layers=32, wbits=4, abits=16, group=128, dtype="f16", seqlen=2048, ppl_samples=1,
-                           ppl_ref=True, batches="1,4,16", decode_steps=48, ctx=256, no_graph=False)
+    a = argparse.Namespace(layers=None, wbits=4, abits=16, group=128, dtype="f16", seqlen=2048, ppl_samples=1,
+                           ppl_ref=True, batches="1,4,16", decode_steps=48, ctx=256, no_graph=False, model="8b",
+                           ppl_layers=None)
     for k, v in kw.items():
         setattr(a, k, v)
     return a
@@ -24,7 +25,11 @@ def default_args(**kw):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--layers", type=int, default=32)
+    ap.add_argument("--layers", type=int, default=None, help="blocks (default: all of the model)")
+    ap.add_argument("--model", default="8b", choices=["8b", "70b"])
+    ap.add_argument("--ppl-layers", type=int, default=None,
+                    help="blocks of the stack the perplexity comparison runs on (default: all; the fp16 reference "
+                         "of the full 70B does not fit next to the model)")
     ap.add_argument("--wbits", type=int, default=4)
     ap.add_argument("--abits", type=int, default=16)
     ap.add_argument("--group", type=int, default=128)
@@ -68,13 +73,16 @@ def main():
 def run(a, dev, rank=0, world=1):
     from q100 import llama as QL
     dt = {"f16": torch.float16, "bf16": torch.bfloat16}[a.dtype]
-    cfg = QL.LLAMA3_8B
+    cfg = {"8b": QL.LLAMA3_8B, "70b": QL.LLAMA3_70B}[getattr(a, "model", "8b")]
+    n_layers = a.layers if a.layers else cfg.num_hidden_layers
+    ppl_layers = getattr(a, "ppl_layers", None) or n_layers
     args = QL.quant_args(a.wbits, a.group, a.abits)
     t0 = time.time()
-    model = QL.QuantLlamaModel.random_init(cfg, args, dev, dt, seed=0, rank=rank, world=world, n_layers=a.layers,
+    model = QL.QuantLlamaModel.random_init(cfg, args, dev, dt, seed=0, rank=rank, world=world, n_layers=n_layers,
                                            fast_attention=True)
     torch.cuda.synchronize()
-    out = {"model": f"llama3-8b random-init, {a.layers} blocks, W{a.wbits}A{a.abits} g{a.group}, {a.dtype}",
+    out = {"model": f"llama3-{getattr(a, 'model', '8b')} random-init, {n_layers} blocks, W{a.wbits}A{a.abits} "
+                    f"g{a.group}, {a.dtype}",
            "tp": world, "build_s": round(time.time() - t0, 2),
            "hbm_GB_after_build": round(torch.cuda.memory_allocated() / 1e9, 2)}
     g = torch.Generator().manual_seed(1)
@@ -83,14 +91,18 @@ def run(a, dev, rank=0, world=1):
     if a.ppl_samples > 0:
         for l in model.layers:
             l.self_attn.fast_attention = False        # reference attention formulation for the parity number
+        all_layers = model.layers
+        if ppl_layers < n_layers:                     # the comparison stack: the first ppl_layers blocks
+            model.layers = torch.nn.ModuleList(list(all_layers)[:ppl_layers])
         ppl, nll = model.perplexity(testenc, a.seqlen)
-        out["ppl"] = {"ppl": ppl, "mean_nll": nll, "tokens": a.ppl_samples * a.seqlen}
+        model.layers = all_layers
+        out["ppl"] = {"ppl": ppl, "mean_nll": nll, "tokens": a.ppl_samples * a.seqlen, "blocks": ppl_layers}
         if a.ppl_ref and rank == 0:      # the single-GPU torch port on the full weights (rank 0; the others wait below)
             import llama_port as LP
             bc = LP.BlockCfg(cfg.hidden_size, cfg.intermediate_size, cfg.num_attention_heads,
                              cfg.num_key_value_heads, cfg.rms_norm_eps, cfg.rope_theta, a.wbits, a.group, a.abits)
             blocks = []
-            for li in range(a.layers):
+            for li in range(ppl_layers):
                 w = QL.random_block_weights(cfg, li, 0, dev, dt)
                 blocks.append(LP.fake_quant_weights(w, bc))
                 del w
