@@ -219,6 +219,10 @@ def run_ours(args):
             # K7: the small all-reduces of the decode steps go over peer memory instead of NCCL (falls back by itself)
             from q100 import peer
             peer.enable(None, dev)
+            # K7b: at prefill sizes the reduce-scatter is the row-parallel GEMM's epilogue (q100/peer.py ScatterReduce)
+            if not os.environ.get("Q100_NO_SCATTER"):
+                peer.enable_scatter(None, dev, PREFILL_M * world, HIDDEN, torch.bfloat16)
+                peer.enable_scatter(None, dev, PREFILL_M, 8192, torch.float16)       # the model rows (fp16, seq 2048)
     P = peaks()
     dt_t = torch.bfloat16
     flags = _lib.GEMM_FORCE_SKINNY if os.environ.get("Q100_BENCH_FORCE_SKINNY") else 0
@@ -260,15 +264,24 @@ def run_ours(args):
         return {k: v for k, v in full.items()}
 
     launches = [0]
+    scatter = None
+    if world > 1:
+        from q100 import peer as _peer0
+        scatter = _peer0.get_scatter(None, dt_t)
 
     def block_step(blk, xs):
         outs = []
         for name, n, k, src in LINEARS:
             pw, mode = blk[name]
             x = tp.shard_input(xs[src], mode, rank, world) if world > 1 else xs[src]
-            y = q100.gemm_wna16(x, pw, None, flags)
-            launches[0] += 1
-            tp.reduce_output(y, mode)
+            sc = scatter if (world > 1 and mode == tp.ROW) else None
+            if sc is not None and sc.fits(x.shape[0], pw):
+                y = sc(x, pw)                       # GEMM with the reduce-scatter as its epilogue + reduce / broadcast
+                launches[0] += 2
+            else:
+                y = q100.gemm_wna16(x, pw, None, flags)
+                launches[0] += 1
+                tp.reduce_output(y, mode)
             outs.append(y)
         return outs
 
@@ -684,7 +697,9 @@ def run_ours(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": WORKLOAD_CONFIG(M_PRE, world),
                 "notes": {"l2": "3 weight sets rotated; per-step working set (109 MB packed weights + 270 MB "
-                                "activations/outputs) exceeds the 126 MB L2", "force_skinny": bool(flags)},
+                                "activations/outputs) exceeds the 126 MB L2", "force_skinny": bool(flags),
+                          "row_parallel_reduce": ("fused: scatter epilogue + reduce/broadcast over peer memory (K7b)"
+                                                  if scatter is not None else "NCCL all-reduce") if world > 1 else None},
                 "roofline": roofline, "decode": decode, "quantize": quant, "strong_scaling": strong,
                 "llama3_8b": model_res, "llama3_70b": model70_res,
                 "cpu_baseline": cpu_base, "gpu_eager_reference_ops": gpu_eager, "e2e": e2e,

@@ -335,6 +335,27 @@ int q100_allreduce_oneshot(const void* x, void* y, int64_t n, int dtype, const v
                            void* err_flag, void* stream);
 
 /*
+ * Row-parallel all-reduce at prefill sizes as GEMM epilogue + one kernel, over peer memory (the
+ * reference has no counterpart).  The token rows are cut into `world` blocks; rank r owns block r.
+ *
+ * q100_gemm_wna16_scatter: the tcgen05 dequant-GEMM of q100_gemm_wna16 (M %% (world * 256) == 0, no bias) whose
+ *   epilogue stores each [128 x 256-token] tile over NVLink straight into slot `rank` of the OWNER's staging buffer
+ *   (peer_stage: DEVICE array [world] of pointers to every rank's [world][M / world][N] buffer, e.g. torch symmetric
+ *   memory) -- the reduce-scatter's transfer overlaps the GEMM's math tile by tile; nothing is written to a local y.
+ * q100_reduce_bcast: next in the stream on every rank.  Waits until every peer's GEMM has completed, sums the `world`
+ *   slots of the owned rows in rank order in fp32 (all ranks compute identical bits), stores the result into every
+ *   rank's y (peer_y: DEVICE array [world] of pointers to every rank's [M, N] buffer) and returns once every peer's
+ *   rows have arrived.  peer_flags: DEVICE array [world] of pointers to every rank's 4 * world * 128 uint32 flag
+ *   words, zeroed once; epoch: this rank's 128 uint32 counters, zeroed once.  Every rank must issue the same sequence
+ *   of calls.  err_flag is set to 1 after a 30 s wait for a peer.  Safe to capture in a CUDA graph.
+ */
+int q100_gemm_wna16_scatter(const void* x, const void* packed, const void* meta, int64_t M, int64_t N, int64_t K,
+                            int group, int n_bits, int disable_zp, int dtype, const void* peer_stage, int rank,
+                            int world, void* stream);
+int q100_reduce_bcast(const void* stage, const void* peer_y, const void* peer_flags, void* epoch, int64_t rows_per,
+                      int64_t N, int dtype, int rank, int world, void* err_flag, void* stream);
+
+/*
  * Development / verification hooks (used by tests only).
  * q100_selftest_div: exhaustively compares the fast 16-bit division sequence with
  * div.rn.f32 + round over all (x, scale) pairs of `dtype` with scale in [1e-5, 1e4];

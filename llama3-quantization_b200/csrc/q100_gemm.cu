@@ -29,7 +29,8 @@ int gemm_tc_dense(const void* x, const void* w, void* y, int64_t M, int64_t N, i
                   cudaStream_t st);
 int gemm_tca(const void* x, const void* packed, const void* meta, const void* bias, void* y,
              int64_t M, int64_t N, int64_t K, int group, int n_bits, int disable_zp, int dtype,
-             int cluster, cudaStream_t st);
+             int cluster, cudaStream_t st, void* const* peer_stage = nullptr, int rows_per = 0, int rank = 0,
+             int world = 1);
 bool gemm_tca_supported(int64_t M, int64_t N, int64_t K, int group, int n_bits);
 
 // ---------------------------------------------------------------- tensor maps
@@ -139,6 +140,24 @@ extern "C" int q100_gemm_wna16(const void* x, const void* packed, const void* me
     if (rc != Q100_OK) return rc;
   }
   return Q100_OK;
+}
+
+extern "C" int q100_gemm_wna16_scatter(const void* x, const void* packed, const void* meta, int64_t M, int64_t N,
+                                       int64_t K, int group, int n_bits, int disable_zp, int dtype,
+                                       const void* peer_stage, int rank, int world, void* stream) {
+  Q100_REQUIRE(x && packed && meta && peer_stage, Q100_EINVAL, "NULL pointer argument");
+  Q100_REQUIRE(dtype == Q100_F16 || dtype == Q100_BF16, Q100_EUNSUPPORTED, "fp16 / bf16 only (got dtype %d)", dtype);
+  Q100_REQUIRE(world >= 2 && world <= 16 && rank >= 0 && rank < world, Q100_EINVAL, "bad rank %d / world %d", rank, world);
+  Q100_REQUIRE(M > 0 && M % (static_cast<int64_t>(world) * 256) == 0, Q100_EUNSUPPORTED,
+               "scatter epilogue: M=%lld must be a multiple of world * 256 token rows", (long long)M);
+  Q100_REQUIRE(gemm_tca_supported(M, N, K, group, n_bits), Q100_EUNSUPPORTED, "tcgen05 path does not support this shape");
+  int rc = ensure_device();
+  if (rc != Q100_OK) return rc;
+  const int64_t row_tiles = (N + 127) / 128;
+  const int cluster = row_tiles % 4 == 0 ? 4 : row_tiles % 2 == 0 ? 2 : 1;
+  return gemm_tca(x, packed, meta, nullptr, nullptr, M, N, K, group, n_bits, disable_zp, dtype, cluster,
+                  reinterpret_cast<cudaStream_t>(stream), reinterpret_cast<void* const*>(peer_stage),
+                  static_cast<int>(M / world), rank, world);
 }
 
 #ifdef TA_TIMING

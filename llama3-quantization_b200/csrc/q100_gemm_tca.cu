@@ -52,6 +52,11 @@ struct TcaArgs {
   int has_zp;
   float qmin;
   int m_tiles, n_tiles;
+  // row-parallel tensor parallelism, reduce-scatter as the epilogue (q100_gemm_wna16_scatter): the token rows are
+  // cut into `world` blocks of rows_per; the tile of tokens [m0, m0 + NT) belongs to rank m0 / rows_per and is
+  // stored over NVLink into slot `rank` of THAT rank's staging buffer [world][rows_per][N] instead of into y
+  void* const* peer_stage;     // device array of `world` pointers (peer-mapped symmetric memory); null = plain y
+  int rows_per, rank, world;
 };
 
 template <int NBITS, int NT>
@@ -404,6 +409,14 @@ k3_tca(const __grid_constant__ CUtensorMap tm_x, const TcaArgs a) {
       // transposed through shared memory and leaves as 16-byte stores (8 rows of one token each) -- the
       // direct form, one 2-byte store per value, kept the tensor core idle for ~6 us per tile
       const int n_warp = nt * TA_ROWS + quad * 32;                      // first row of this warp
+      // destination of this token tile: y, or the owner rank's staging slot (rows_per % NT == 0: one owner per tile)
+      T* ydst = reinterpret_cast<T*>(a.y);
+      int m_shift = 0;                                                  // row index in the destination = m - m_shift
+      if (a.peer_stage != nullptr) {
+        const int owner = m0 / a.rows_per;
+        ydst = reinterpret_cast<T*>(a.peer_stage[owner]) + static_cast<int64_t>(a.rank) * a.rows_per * a.N;
+        m_shift = owner * a.rows_per;
+      }
       const uint32_t ebase = base_u32 + SM::kOffE + quad * (2 * 2048);
       const int tj = lane >> 2, rq = (lane & 3) * 8;                    // read side: token tj (+8i), rows rq..rq+7
 #pragma unroll 1
@@ -431,13 +444,14 @@ k3_tca(const __grid_constant__ CUtensorMap tm_x, const TcaArgs a) {
             asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
                          : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(eb + (tj + 8 * i) * 64 + rq * 2));
             if (m < a.M && n_warp + rq < a.N)
-              *reinterpret_cast<uint4*>(reinterpret_cast<T*>(a.y) + static_cast<int64_t>(m) * a.N + n_warp + rq) = v;
+              *reinterpret_cast<uint4*>(ydst + static_cast<int64_t>(m - m_shift) * a.N + n_warp + rq) = v;
           }
         }
         // the buffer is reused two chunks later: the __syncwarp of the next chunk orders these reads before
         // the writes after it
       }
     }
+    if (a.peer_stage != nullptr) __threadfence_system();   // the peer stores are performed before the grid completes
   }
   tc_fence_before();
   __syncthreads();
@@ -539,10 +553,11 @@ static int gemm_tca_t(const void* x, const TcaArgs& a, int n_bits, int cluster, 
 
 int gemm_tca(const void* x, const void* packed, const void* meta, const void* bias, void* y,
              int64_t M, int64_t N, int64_t K, int group, int n_bits, int disable_zp, int dtype,
-             int cluster, cudaStream_t st) {
+             int cluster, cudaStream_t st, void* const* peer_stage, int rows_per, int rank, int world) {
   Q100_REQUIRE(gemm_tca_supported(M, N, K, group, n_bits), Q100_EUNSUPPORTED, "tcgen05 (TMEM-A) path: unsupported shape");
   TcaArgs a{};
   a.packed = packed; a.meta = meta; a.bias = bias; a.y = y;
+  a.peer_stage = peer_stage; a.rows_per = rows_per; a.rank = rank; a.world = world;
   a.M = static_cast<int>(M); a.N = static_cast<int>(N); a.K = static_cast<int>(K);
   a.group = group == 0 ? static_cast<int>(K) : group;
   a.has_zp = disable_zp ? 0 : 1;

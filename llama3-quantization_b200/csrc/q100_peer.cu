@@ -90,9 +90,112 @@ __global__ void __launch_bounds__(256) k7_allreduce(const T* x, T* y /* may alia
   if (tid == 0) epoch_p[c] = e;
 }
 
+// ---------------------------------------------------------------- K7b: reduce + broadcast after a scatter-epilogue GEMM
+// The second half of the row-parallel all-reduce at prefill sizes.  q100_gemm_wna16_scatter has stored every rank's
+// partial of the token rows a rank owns into that rank's staging buffer stage[src rank][rows_per][N] while the GEMM
+// was still running; this kernel (next in the stream) waits until every peer's GEMM is complete, sums the `world`
+// slots of its rows in rank order in fp32 -- the same bits on every rank as an fp32 sum of the gathered partials --
+// and stores the result into EVERY rank's y (rows [rank * rows_per, ...)), then waits until every peer has done so.
+// Chunk-local protocol like K7: CTA c of every rank handshakes with CTA c of the others (a fixed CTA count keeps the
+// per-CTA epochs in lockstep, the epoch lives in device memory: graph-capturable).  Flags: [barrier 2][parity 2]
+// [rank][K7B_CTAS] words per rank.
+constexpr int K7B_CTAS = 128;
+
+template <typename T>
+__global__ void __launch_bounds__(256) k7b_reduce_bcast(const T* __restrict__ stage, T* const* __restrict__ ys,
+                                                        uint32_t* const* __restrict__ flags, uint32_t* __restrict__ epoch_p,
+                                                        int64_t slot_elems, int64_t n_own, int rank, int world,
+                                                        uint32_t* __restrict__ err) {
+  using D = DT<T>;
+  const int c = blockIdx.x, tid = threadIdx.x;
+  const uint32_t e = epoch_p[c] + 1;
+  const int par = static_cast<int>(e & 1u);
+  auto flag_of = [&](int barrier, int r) {
+    return ((static_cast<int64_t>(barrier) * 2 + par) * world + r) * K7B_CTAS + c;
+  };
+  auto handshake = [&](int barrier) {
+    __syncthreads();                                   // this CTA's stores (if any) precede the flag writers
+    if (tid < world) {
+      st_release_sys(flags[tid] + flag_of(barrier, rank), e);
+      const uint32_t* f = flags[rank] + flag_of(barrier, tid);
+      const unsigned long long t0 = gtimer();
+      while (ld_acquire_sys(f) != e) {
+        if (gtimer() - t0 > 30000000000ull) { atomicExch(err, 1u); break; }
+      }
+    }
+    __syncthreads();
+  };
+  // (A) every peer's GEMM -- the kernel before this one in its stream -- has completed: its partials are in `stage`
+  handshake(0);
+  const int64_t nvec = n_own >> 3;
+  const int64_t per = (nvec + gridDim.x - 1) / gridDim.x;
+  const int64_t v0 = c * per, v1 = min(nvec, v0 + per);
+  // four 16-byte vectors per thread and round, all `world` slots of each requested before the first sum: enough
+  // bytes in flight to keep HBM (the local slot reads) and NVLink (the stores) busy from 128 CTAs
+  constexpr int U = 4;
+  for (int64_t vb = v0 + tid; vb < v1; vb += static_cast<int64_t>(blockDim.x) * U) {
+    float acc[U][8];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[u][i] = 0.f;
+    for (int r = 0; r < world; ++r) {
+      uint4 q[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t v = vb + static_cast<int64_t>(u) * blockDim.x;
+        q[u] = v < v1 ? __ldcs(reinterpret_cast<const uint4*>(stage + r * slot_elems) + v) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float2 a = D::to_f2(q[u].x), b = D::to_f2(q[u].y), cc = D::to_f2(q[u].z), d = D::to_f2(q[u].w);
+        acc[u][0] += a.x; acc[u][1] += a.y; acc[u][2] += b.x; acc[u][3] += b.y;
+        acc[u][4] += cc.x; acc[u][5] += cc.y; acc[u][6] += d.x; acc[u][7] += d.y;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = vb + static_cast<int64_t>(u) * blockDim.x;
+      if (v < v1) {
+        const uint4 o = make_uint4(D::pack2(acc[u][0], acc[u][1]), D::pack2(acc[u][2], acc[u][3]),
+                                   D::pack2(acc[u][4], acc[u][5]), D::pack2(acc[u][6], acc[u][7]));
+        for (int k = 0; k < world; ++k) {                // own copy last: the NVLink stores leave first
+          const int p = (rank + 1 + k) % world;
+          reinterpret_cast<uint4*>(ys[p] + static_cast<int64_t>(rank) * n_own)[v] = o;
+        }
+      }
+    }
+  }
+  // (B) every peer has stored its rows into my y
+  handshake(1);
+  if (tid == 0) epoch_p[c] = e;
+}
+
 }  // namespace q100
 
 using namespace q100;
+
+extern "C" int q100_reduce_bcast(const void* stage, const void* peer_y, const void* peer_flags, void* epoch,
+                                 int64_t rows_per, int64_t N, int dtype, int rank, int world, void* err_flag,
+                                 void* stream) {
+  Q100_REQUIRE(stage && peer_y && peer_flags && epoch && err_flag, Q100_EINVAL, "NULL pointer argument");
+  Q100_REQUIRE(dtype == Q100_F16 || dtype == Q100_BF16, Q100_EUNSUPPORTED, "fp16 / bf16 only (got dtype %d)", dtype);
+  Q100_REQUIRE(world >= 2 && world <= 16 && rank >= 0 && rank < world, Q100_EINVAL, "bad rank %d / world %d", rank, world);
+  Q100_REQUIRE(rows_per > 0 && N > 0 && (rows_per * N) % 8 == 0, Q100_EINVAL, "rows_per * N must be a positive multiple of 8");
+  int rc = ensure_device();
+  if (rc != Q100_OK) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t n_own = rows_per * N;
+  if (dtype == Q100_F16)
+    k7b_reduce_bcast<__half><<<K7B_CTAS, 256, 0, st>>>(reinterpret_cast<const __half*>(stage),
+        reinterpret_cast<__half* const*>(peer_y), reinterpret_cast<uint32_t* const*>(peer_flags),
+        reinterpret_cast<uint32_t*>(epoch), n_own, n_own, rank, world, reinterpret_cast<uint32_t*>(err_flag));
+  else
+    k7b_reduce_bcast<__nv_bfloat16><<<K7B_CTAS, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(stage),
+        reinterpret_cast<__nv_bfloat16* const*>(peer_y), reinterpret_cast<uint32_t* const*>(peer_flags),
+        reinterpret_cast<uint32_t*>(epoch), n_own, n_own, rank, world, reinterpret_cast<uint32_t*>(err_flag));
+  return check_cuda(cudaGetLastError(), "k7b_reduce_bcast launch");
+}
 
 extern "C" int q100_allreduce_oneshot(const void* x, void* y, int64_t n, int dtype, const void* peer_bufs,
                                       const void* peer_flags, void* epoch, int64_t slot_elems, int rank, int world,

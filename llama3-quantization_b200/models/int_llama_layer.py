@@ -203,7 +203,9 @@ class QuantLlamaMLP(nn.Module):
         else:
             gate, up = self.gate_proj(x), self.up_proj(x)
         out = self.down_proj(self.act_fn(gate) * up)
-        return _tp.reduce_output(out, _tp.ROW, self.tp_group) if getattr(self, "tp_world", 1) > 1 else out
+        if getattr(self, "tp_world", 1) > 1 and not self.down_proj.reduced:
+            out = _tp.reduce_output(out, _tp.ROW, self.tp_group)
+        return out
 
 
 class QuantLlamaAttention(nn.Module):
@@ -330,7 +332,7 @@ class QuantLlamaAttention(nn.Module):
         attn_output = attn_output.transpose(1, 2)
         attn_output = attn_output.reshape(bsz, q_len, nh * self.head_dim)
         attn_output = self.o_proj(attn_output)
-        if self.tp_world > 1:
+        if self.tp_world > 1 and not self.o_proj.reduced:
             attn_output = _tp.reduce_output(attn_output, _tp.ROW, self.tp_group)
         if not output_attentions:
             attn_weights = None
@@ -434,7 +436,7 @@ class QuantLlamaDecoderLayer(nn.Module):
         q = _ops.rope_kv_decode(qkv, rc[0], rc[1], position, kv.k, kv.v, nh, nkv, err_flag)
         att = F.scaled_dot_product_attention(q, kv.k, kv.v, attn_mask=attention_mask, enable_gqa=nh != nkv)
         o = attn.o_proj(att.reshape(bsz, 1, nh * attn.head_dim))
-        if attn.tp_world > 1:
+        if attn.tp_world > 1 and not attn.o_proj.reduced:
             o = _tp.reduce_output(o, _tp.ROW, attn.tp_group)
         h1, n2 = _ops.add_rmsnorm(o, self.post_attention_layernorm.weight,
                                   self.post_attention_layernorm.variance_epsilon, h0)
@@ -442,7 +444,7 @@ class QuantLlamaDecoderLayer(nn.Module):
         if gu is None:
             return None
         d = mlp.down_proj.forward_gate_up(gu)              # SiLU * up inside the down_proj GEMM's x staging
-        if getattr(mlp, "tp_world", 1) > 1:
+        if getattr(mlp, "tp_world", 1) > 1 and not mlp.down_proj.reduced:
             d = _tp.reduce_output(d, _tp.ROW, mlp.tp_group)
         return d, h1
 

@@ -115,7 +115,9 @@ def build_block(cfg: LlamaCfg, weights: dict, args, rank=0, world=1, tp_group=No
         # statistics (group_size=None) span all ranks -> one [rows, 2] MIN/MAX all-reduce inside the quantizer
         import torch.distributed as dist
         sg = tp_group if tp_group is not None else dist.group.WORLD
+        from . import peer as _peer
         for m in (layer.self_attn.o_proj, layer.mlp.down_proj):
+            m.tp_scatter = _peer.get_scatter(tp_group, weights["o_proj"].dtype)     # None unless enable_scatter() ran
             if m.act_quantizer is not None:
                 m.act_quantizer.stat_group = sg
             if not m.weight_quantizer.group_size:

@@ -69,6 +69,97 @@ class OneShotAllReduce:
                 and 0 < y.numel() <= self.slot_elems)
 
 
+class ScatterReduce:
+    """Row-parallel all-reduce at prefill sizes fused with the GEMM (K7b, include/q100.h q100_gemm_wna16_scatter +
+    q100_reduce_bcast): the GEMM's epilogue stores every output tile over NVLink into the staging buffer of the rank
+    that owns those token rows (the reduce-scatter travels while the tensor cores work), one more kernel sums the
+    slots in fp32 and stores the result into every rank's y.  ``__call__(x, w)`` returns the COMPLETE ``[M, N]``
+    output (a view of one of two alternating symmetric buffers: consume it before the second next call).
+    Collective set-up: every rank constructs it at the same point with the same sizes."""
+
+    FLAG_WORDS = 4 * 128                  # [barrier 2][parity 2][rank][128 CTAs] -> times world
+
+    def __init__(self, group, device: torch.device, max_tokens: int, max_cols: int, dtype: torch.dtype):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.device, self.dtype = device, dtype
+        self.cap = int(max_tokens) * int(max_cols)
+        err = None
+        try:
+            self.stage = symm.empty(self.cap, dtype=dtype, device=device)
+            self.y = [symm.empty(self.cap, dtype=dtype, device=device) for _ in range(2)]
+            self.flags = symm.empty(self.FLAG_WORDS * self.world, dtype=torch.int32, device=device)
+            self.flags.zero_()
+        except Exception as e:                                     # noqa: BLE001
+            err = e
+        ok = torch.tensor([0.0 if err is not None else 1.0], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if ok.item() == 0:
+            raise RuntimeError(f"symmetric-memory allocation failed on some rank ({err!r})")
+        self.h_stage = symm.rendezvous(self.stage, self.group)
+        self.h_y = [symm.rendezvous(t, self.group) for t in self.y]
+        self.h_flags = symm.rendezvous(self.flags, self.group)
+        self.epoch = torch.zeros(128, dtype=torch.int32, device=device)
+        self.err = torch.zeros(1, dtype=torch.int32, device=device)
+        self.turn = 0
+        torch.cuda.synchronize(device)
+        dist.barrier(self.group)
+
+    def fits(self, M: int, w) -> bool:
+        """Only properties that are identical on every rank decide the path."""
+        return (M > 32 and M % (self.world * 256) == 0 and M * w.N <= self.cap and w.dtype == self.dtype
+                and w.K % 64 == 0 and w.N % 8 == 0 and w.group % 64 == 0)
+
+    def __call__(self, x: torch.Tensor, w) -> torch.Tensor:
+        shp = x.shape
+        x2 = x.contiguous().view(-1, w.K)
+        M = x2.shape[0]
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        k = self.turn
+        self.turn ^= 1
+        with torch.cuda.device(self.device):
+            check(lib.q100_gemm_wna16_scatter(x2.data_ptr(), w.packed.data_ptr(), w.meta.data_ptr(), M, w.N, w.K,
+                                              w.group, w.n_bits, int(w.disable_zero_point), _DT[x.dtype],
+                                              self.h_stage.buffer_ptrs_dev, self.rank, self.world, st))
+            check(lib.q100_reduce_bcast(self.stage.data_ptr(), self.h_y[k].buffer_ptrs_dev, self.h_flags.buffer_ptrs_dev,
+                                        self.epoch.data_ptr(), M // self.world, w.N, _DT[x.dtype], self.rank,
+                                        self.world, self.err.data_ptr(), st))
+        return self.y[k][:M * w.N].view(*shp[:-1], w.N)
+
+    def check(self) -> None:
+        if int(self.err.item()) != 0:
+            raise RuntimeError("q100.peer: a fused reduce timed out waiting for a peer; its results are invalid")
+
+
+_SCATTER: dict = {}
+
+
+def enable_scatter(group=None, device: Optional[torch.device] = None, max_tokens: int = 2048, max_cols: int = 8192,
+                   dtype: torch.dtype = torch.bfloat16) -> Optional[ScatterReduce]:
+    """Collective.  Sets up the fused row-parallel reduce for ``group``; None (NCCL stays) when symmetric memory is
+    not available."""
+    key = (group, dtype)
+    if key in _SCATTER:
+        return _SCATTER[key]
+    obj = None
+    if dist.is_initialized() and dist.get_world_size(group) > 1 and torch.cuda.is_available():
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        try:
+            obj = ScatterReduce(group, dev, max_tokens, max_cols, dtype)
+        except Exception as e:                                     # noqa: BLE001
+            import warnings
+            warnings.warn(f"q100.peer: fused row-parallel reduce unavailable, NCCL all-reduce stays ({e!r})")
+            obj = None
+    _SCATTER[key] = obj
+    return obj
+
+
+def get_scatter(group=None, dtype: torch.dtype = torch.bfloat16) -> Optional[ScatterReduce]:
+    return _SCATTER.get((group, dtype))
+
+
 def enable(group=None, device: Optional[torch.device] = None, slot_elems: int = 16 * 8192) -> Optional[OneShotAllReduce]:
     """Collective.  Sets up the peer buffers for ``group`` (default: world); returns None (and remembers it) when
     symmetric memory is not available, in which case reduce_output keeps using NCCL."""
@@ -94,7 +185,8 @@ def get(group=None) -> Optional[OneShotAllReduce]:
 
 def shutdown() -> None:
     """Drop the peer buffers of every group (call before dist.destroy_process_group).  Raises if a call timed out."""
-    objs = [o for o in _STATE.values() if o is not None]
+    objs = [o for o in _STATE.values() if o is not None] + [o for o in _SCATTER.values() if o is not None]
     _STATE.clear()
+    _SCATTER.clear()
     for o in objs:
         o.check()

@@ -62,6 +62,11 @@ class QuantLinear(nn.Module):
         # fused dequant-GEMM switch (extension; True keeps reference results within GEMM tolerance)
         self.use_fused_gemm = True
         self._requant_cache = None
+        # tensor parallelism (extension): a q100.peer.ScatterReduce makes forward() of a row-parallel layer return the
+        # ALL-REDUCED output at prefill sizes (reduce-scatter as the GEMM's epilogue); `reduced` tells the caller
+        # whether the last forward did, so that it skips its own all-reduce
+        self.tp_scatter = None
+        self.reduced = False
 
     # ------------------------------------------------------------------ fused path plumbing
     def _fused_ok(self, x: torch.Tensor, packed) -> bool:
@@ -137,6 +142,7 @@ class QuantLinear(nn.Module):
         """``self(act_fn(gate) * up)`` for ``gate_up = gate | up`` (SiLU): at decode shapes the packed GEMM applies the
         element-wise step while it stages x (Q100_GEMM_X_GATE_UP), otherwise K6 + the normal forward."""
         rows = gate_up.numel() // gate_up.shape[-1]
+        self.reduced = False
         if (rows <= 8 and not self.use_temporary_parameter and not self.use_weight_quant
                 and not (self.use_act_quant and not self.disable_input_quant) and not torch.is_grad_enabled()):
             packed = self.weight_quantizer.packed_for(self.weight)
@@ -148,6 +154,7 @@ class QuantLinear(nn.Module):
     def forward(self, input: torch.Tensor):
         packed = None
         weight = None
+        self.reduced = False
         if self.use_temporary_parameter:
             weight = self.temp_weight
             bias = self.temp_bias
@@ -174,6 +181,10 @@ class QuantLinear(nn.Module):
             if x.dtype != packed.dtype and torch.is_autocast_enabled():
                 x = x.to(packed.dtype)                     # what autocast does in front of F.linear
             if self._fused_ok(x, packed):
+                sc = self.tp_scatter
+                if sc is not None and bias is None and sc.fits(x.numel() // x.shape[-1], packed):
+                    self.reduced = True
+                    return sc(x, packed)
                 return _ops.gemm_wna16(x, packed, bias)
             if weight is None:
                 weight = self.weight_quantizer(self.weight)
