@@ -199,6 +199,27 @@ int q100_gemm_wna16(const void* x, const void* packed, const void* meta, const v
 size_t q100_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int n_bits, int flags);
 
 /*
+ * K3c -- W8A8 / W4A4 (SmoothQuant-style configurations, main.py:326-349): per-token activation quantisation FUSED into
+ * the GEMM as its prologue and an integer contraction on the tensor cores, at decode shapes (M <= 15).
+ * Replaces  act_quantizer(x)  +  F.linear(x_q, w_q)  of quant/int_linear.py:59-62.
+ *
+ *   row_minmax  [M, 2] (min, max) of every token row over the FULL K in `dtype` (q100_rows_minmax; MIN / MAX
+ *               all-reduced under tensor parallelism): the statistics of quantizer.py:140-141
+ *   a_bits      activation bits (2..8): codes in [0, 2^a_bits - 1], asymmetric, per token
+ * While it stages x the kernel computes scale / zero-point per token with the reference's per-op rounding and the
+ * codes q_x = clamp(round_ste(x / s_x) + z_x) -- bit-identical to the reference's -- and feeds them as unsigned bytes to
+ * mma.sync.m16n8k32.u8.u8 against the weight codes (W8: the packed bytes; W4: nibbles).  Per 128-k block and
+ * (row n, token m):  y += s_w s_x (sum q_w q_x - z_x sum q_w - z_w sum q_x + 128 z_w z_x), the integer sums exact,
+ * the scaling in fp32.  The reference multiplies the two fake-quantised 16-bit operands instead, i.e. it rounds
+ * (q - z) s to 16 bits on both sides first: the results agree within the stated GEMM tolerance (tests/test_w8a8.py),
+ * not bit for bit (hard part 6).
+ * Weights: W4 / W8, group a multiple of 128 (or 0 = per channel).  flags: Q100_FLAG_CUDA_SCALE, Q100_GEMM_PDL.
+ */
+int q100_gemm_wna8(const void* x, const void* row_minmax, const void* packed, const void* meta, const void* bias,
+                   void* y, int64_t M, int64_t N, int64_t K, int group, int n_bits, int a_bits, int disable_zp,
+                   int dtype, void* workspace, size_t workspace_bytes, int flags, void* stream);
+
+/*
  * K4-K6 -- the memory-bound steps between the quantised linears of a decoder block at decode shapes
  * (QuantLlamaDecoderLayer.forward, models/int_llama_layer.py:213-262): ~35 eager launches per block and
  * token in the reference, four here.  fp16 / bf16 only; each reproduces the reference's op order and

@@ -34,6 +34,10 @@ struct SkinnyArgs {
   int pdl;                // launch with programmatic stream serialization
   int seq;                // launch sequence number (timing builds)
   int x_gate_up;          // x is [M, 2K] = gate | up: stage act_fn(gate) * up (K6's arithmetic)
+  // ---- MODE 3 (q100_gemm_wna8): per-token activation quantisation as the GEMM's prologue, integer contraction
+  const void* x_minmax;   // [M, 2] T: (min, max) of every token row over the FULL K (q100_rows_minmax, all-reduced under TP)
+  float a_qmax, a_denom;  // 2^abits - 1 (codes are [0, a_qmax]; scale = range / a_denom)
+  int a_cuda_scale;       // Q100_FLAG_CUDA_SCALE for the activation scale
   // ---- chain mode only (k3_chain, q100_chain.cuh): what surrounds the GEMM inside a decoder block
   int x_norm;             // x is the residual stream h [M, K]: stage weight * (h * rstd) (K4's arithmetic, omni_norm.py:52-63)
   const void* norm_w;     // [K] T

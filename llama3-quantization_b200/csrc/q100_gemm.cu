@@ -13,7 +13,8 @@ namespace q100 {
 
 int gemm_skinny(const void* x, const void* packed, const void* meta, const void* bias, void* y,
                 int64_t M, int64_t N, int64_t K, int group, int n_bits, int disable_zp, int dtype,
-                void* workspace, size_t workspace_bytes, int exact_weights, int pdl, int x_gate_up, cudaStream_t st);
+                void* workspace, size_t workspace_bytes, int exact_weights, int pdl, int x_gate_up, cudaStream_t st,
+                const void* x_minmax = nullptr, int a_bits = 16, int a_cuda_scale = 0);
 size_t skinny_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int gemm_stream(const void* x, const void* packed, const void* meta, const void* bias, void* y,
                 int64_t M, int64_t N, int64_t K, int group, int n_bits, int disable_zp, int dtype,
@@ -140,6 +141,25 @@ extern "C" int q100_gemm_wna16(const void* x, const void* packed, const void* me
     if (rc != Q100_OK) return rc;
   }
   return Q100_OK;
+}
+
+extern "C" int q100_gemm_wna8(const void* x, const void* row_minmax, const void* packed, const void* meta,
+                              const void* bias, void* y, int64_t M, int64_t N, int64_t K, int group, int n_bits,
+                              int a_bits, int disable_zp, int dtype, void* workspace, size_t workspace_bytes,
+                              int flags, void* stream) {
+  Q100_REQUIRE(x && row_minmax && packed && meta && y, Q100_EINVAL, "NULL pointer argument");
+  Q100_REQUIRE(dtype == Q100_F16 || dtype == Q100_BF16, Q100_EUNSUPPORTED, "fp16 / bf16 only (got dtype %d)", dtype);
+  Q100_REQUIRE(n_bits == 4 || n_bits == 8, Q100_EUNSUPPORTED, "integer W x A path: W4 or W8 (got W%d)", n_bits);
+  Q100_REQUIRE(M >= 0 && N > 0 && K > 0 && K % 128 == 0 && N % 8 == 0, Q100_EINVAL, "bad shape M=%lld N=%lld K=%lld",
+               (long long)M, (long long)N, (long long)K);
+  Q100_REQUIRE(M <= 15, Q100_EUNSUPPORTED,
+               "q100_gemm_wna8 covers decode shapes (M <= 15); prefill runs q100_fakequant_rows + q100_gemm_wna16");
+  if (M == 0) return Q100_OK;
+  int rc = ensure_device();
+  if (rc != Q100_OK) return rc;
+  return gemm_skinny(x, packed, meta, bias, y, M, N, K, group, n_bits, disable_zp, dtype, workspace, workspace_bytes, 0,
+                     (flags & Q100_GEMM_PDL) ? 1 : 0, 0, reinterpret_cast<cudaStream_t>(stream), row_minmax, a_bits,
+                     (flags & Q100_FLAG_CUDA_SCALE) ? 1 : 0);
 }
 
 extern "C" int q100_gemm_wna16_scatter(const void* x, const void* packed, const void* meta, int64_t M, int64_t N,

@@ -46,6 +46,7 @@
 #include "q100_common.cuh"
 #include "q100_ptx.cuh"
 #include "q100_chain.cuh"
+#include "q100_quant.cuh"
 
 namespace q100 {
 
@@ -270,6 +271,12 @@ __device__ __forceinline__ void imma_16832(int (&d)[4], const uint32_t (&a)[4], 
                : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
+// D += A(16 x 32, unsigned bytes, row) * B(32 x 8, UNSIGNED bytes, col): weight codes x activation codes (MODE 3)
+__device__ __forceinline__ void imma_16832_uu(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 // act_fn(gate) * up for eight elements: F.silu in fp32 stored as T, then the product rounded to T -- the arithmetic
 // of k6_silu_mul (q100_block.cu), i.e. of models/int_llama_layer.py:45 on 16-bit tensors
 template <typename T>
@@ -455,6 +462,7 @@ __device__ __forceinline__ void consumer_gemm(const SkinnyArgs& a_in, const uint
   using T2 = typename DQ<T>::T2;
   constexpr bool POST = MODE == 1;
   constexpr bool IMMA = MODE == 2;
+  constexpr bool A8 = MODE == 3;                                 // activation codes x weight codes (q100_gemm_wna8)
   constexpr bool kBf16 = MODE == 0 && DT<T>::kCode == Q100_BF16;  // MMA operand type (POST: always fp16)
   constexpr bool kConvX = POST && DT<T>::kCode == Q100_BF16;    // bf16 activations -> scaled fp16 at staging
   constexpr bool LOHI = POST && UseLoHi<NBITS>::value;
@@ -473,8 +481,8 @@ __device__ __forceinline__ void consumer_gemm(const SkinnyArgs& a_in, const uint
   const uint32_t xs_u32 = ring_u32 + stages * stage_pitch;
   uint8_t* xs_ptr = ring_ptr + stages * stage_pitch;
   const int mrows = a.m_rows;
-  constexpr int kXPitch = IMMA ? SK_IPITCH : SK_XPITCH;
-  const int blk_pitch = mrows * kXPitch;              // bytes of x per staged k block
+  constexpr int kXPitch = IMMA ? SK_IPITCH : A8 ? SK_ICOL : SK_XPITCH;
+  const int blk_pitch = (A8 ? mrows + 1 : mrows) * kXPitch;   // bytes of x per staged k block (A8: + the all-ones column)
   const int g = lane >> 2, t = lane & 3;
   const int r0 = warp * 16 + g, r1 = r0 + 8;
   const bool has_zp = a.has_zp != 0;
@@ -497,7 +505,7 @@ __device__ __forceinline__ void consumer_gemm(const SkinnyArgs& a_in, const uint
   // (sum of the "plain" pairs, sum of the "x16" pairs) of row (bl, m) go to the row's padding.
   auto stage_x = [&](int q0, int n) {
     const T* xg = reinterpret_cast<const T*>(a.x);
-    const int per_blk = mrows * 16;
+    const int per_blk = (A8 ? mrows + 1 : mrows) * 16;
     const int total = n * per_blk;                         // 16-byte chunks
     const int kblk0 = q0 % kblocks;
     // XU > 1 (loads of several rounds in flight) and a cp.async variant (raw chunks global -> shared, transformed in
@@ -513,7 +521,10 @@ __device__ __forceinline__ void consumer_gemm(const SkinnyArgs& a_in, const uint
           const int bl = c / per_blk;
           const int rem = c - bl * per_blk;
           const int kblk = (kblk0 + bl) % kblocks;
-          if constexpr (CHAIN) {
+          if constexpr (A8) {
+            if ((rem >> 4) < mrows)
+              vq[u] = *reinterpret_cast<const uint4*>(xg + static_cast<int64_t>(rem >> 4) * a.K + kblk * SK_KB + (rem & 15) * 8);
+          } else if constexpr (CHAIN) {
             // x was written by other SMs earlier in this launch: read it through L2 (ld.global.cg), never L1
             if (a.x_gate_up) {
               const T* gp = xg + static_cast<int64_t>(rem >> 4) * (2 * a.K) + kblk * SK_KB + (rem & 15) * 8;
@@ -544,6 +555,46 @@ __device__ __forceinline__ void consumer_gemm(const SkinnyArgs& a_in, const uint
       const int rem = c - bl * per_blk;
       const int m = rem >> 4, ch = rem & 15;
       uint4 v = vq[u];
+      if constexpr (A8) {
+        // per-token activation quantisation (quantizer.py:140-159 on the row's min / max, then :103-106) right here:
+        // the codes are the reference's, bit for bit; they go to the tensor core as unsigned bytes in the byte order
+        // in which the weight codes come out of a packed word.  Column m = mrows is all ones: its product with the
+        // weight codes is sum_k q_w, the term the activation zero-point multiplies.
+        uint8_t* colp = xs_ptr + bl * blk_pitch + m * SK_ICOL;
+        const int boff = (ch >> 2) * 32 + (ch & 3) * 8;
+        if (m == mrows) {
+          *reinterpret_cast<uint2*>(colp + boff) = make_uint2(0x01010101u, 0x01010101u);
+          continue;
+        }
+        QuantArgs qa{};
+        qa.denom = a.a_denom; qa.rcp_denom = 1.0f / a.a_denom; qa.has_zp = 1; qa.cuda_scale = a.a_cuda_scale;
+        const T* mmp = reinterpret_cast<const T*>(a.x_minmax) + 2 * m;
+        const GroupQ<T> q = group_params<T>(DT<T>::to_f(mmp[0]), DT<T>::to_f(mmp[1]), qa, 0);
+        const float2 p0 = DT<T>::to_f2(v.x), p1 = DT<T>::to_f2(v.y), p2 = DT<T>::to_f2(v.z), p3 = DT<T>::to_f2(v.w);
+        const float f[8] = {p0.x, p0.y, p1.x, p1.y, p2.x, p2.y, p3.x, p3.y};
+        uint32_t cq[8];
+        float sx = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          using D = DT<T>;
+          const float vv = D::rd(__fdiv_rn(f[i], q.scale));
+          float xi = D::rd(D::rd(rintf(vv) - vv) + vv);
+          xi = D::rd(xi + q.zp);
+          const float c = clamp_nan(xi, 0.f, a.a_qmax);
+          cq[i] = static_cast<uint32_t>(__float2int_rn(c));
+          sx += static_cast<float>(cq[i]);
+        }
+        const uint32_t half_mask = (lane < 16) ? 0x0000ffffu : 0xffff0000u;   // the 16 chunks of one (block, m)
+#pragma unroll
+        for (int d = 1; d < 16; d <<= 1) sx += __shfl_xor_sync(half_mask, sx, d);
+        auto pk = [](uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3) { return b0 | (b1 << 8) | (b2 << 16) | (b3 << 24); };
+        if constexpr (NBITS == 4)
+          *reinterpret_cast<uint2*>(colp + boff) = make_uint2(pk(cq[0], cq[4], cq[1], cq[5]), pk(cq[2], cq[6], cq[3], cq[7]));
+        else
+          *reinterpret_cast<uint2*>(colp + boff) = make_uint2(pk(cq[0], cq[2], cq[1], cq[3]), pk(cq[4], cq[6], cq[5], cq[7]));
+        if (ch == 0) *reinterpret_cast<float4*>(colp + 128) = make_float4(sx, q.scale, q.zp, 0.f);
+        continue;
+      }
       if constexpr (IMMA) {
         // block fixed point: xi = rint(x * 2^(21 - e)) with e the exponent of the (token, block) maximum, so
         // |xi| < 2^22, split into balanced base-256 digits l0 + 256 l1 + 65536 l2 (each in [-128, 127]).
@@ -663,12 +714,13 @@ __device__ __forceinline__ void consumer_gemm(const SkinnyArgs& a_in, const uint
 
   // per-lane x addresses: column n = mb*8+g of the mma B operand is token m; columns >= M read the last
   // valid row instead (their results are never stored), so no zero fill and no branch is needed
-  uint32_t xrow[MB], srow[MB], srow1[IMMA ? MB : 1];
+  uint32_t xrow[MB], srow[MB], srow1[(IMMA || A8) ? MB : 1];
 #pragma unroll
   for (int mb = 0; mb < MB; ++mb) {
-    if constexpr (IMMA) {
-      // mma column n = mb*8 + g is (token, limb) = divmod(n, 3); this lane's output columns are n = mb*8 + 2t, +1
-      const int ncols = 3 * mrows;
+    if constexpr (IMMA || A8) {
+      // IMMA: mma column n = mb*8 + g is (token, limb) = divmod(n, 3); A8: column n is token n, column mrows the all-ones
+      // column.  This lane's output columns are n = mb*8 + 2t, +1
+      const int ncols = A8 ? mrows + 1 : 3 * mrows;
       xrow[mb] = xs_u32 + min(mb * 8 + g, ncols - 1) * SK_ICOL + t * 32;
       srow[mb] = xs_u32 + min(mb * 8 + 2 * t, ncols - 1) * SK_ICOL + 128;
       srow1[mb] = xs_u32 + min(mb * 8 + 2 * t + 1, ncols - 1) * SK_ICOL + 128;
@@ -690,7 +742,61 @@ __device__ __forceinline__ void consumer_gemm(const SkinnyArgs& a_in, const uint
   const uint32_t magic = reg_const(DQM::kMagic);
 
   auto compute_block = [&](const BlockRegs<NBITS>& b, uint32_t xoff) {
-    if constexpr (IMMA) {
+    if constexpr (A8) {
+      if constexpr (NBITS == 4 || NBITS == 8) {
+        int di[MB][4];
+#pragma unroll
+        for (int mb = 0; mb < MB; ++mb) { di[mb][0] = di[mb][1] = di[mb][2] = di[mb][3] = 0; }
+        uint4 xb[MB][2];
+#pragma unroll
+        for (int mb = 0; mb < MB; ++mb) { xb[mb][0] = lds128(xrow[mb] + xoff); xb[mb][1] = lds128(xrow[mb] + xoff + 16); }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t af[4];
+          if constexpr (NBITS == 4) {
+            const uint32_t w0 = b.c0.word(j), w1 = b.c1.word(j);
+            af[0] = w0 & 0x0f0f0f0fu;
+            af[1] = w1 & 0x0f0f0f0fu;
+            af[2] = shr4_fma(w0) & 0x0f0f0f0fu;
+            af[3] = shr4_fma(w1) & 0x0f0f0f0fu;
+          } else {                                          // W8: the packed words are the byte operands
+            af[0] = b.c0.wsel(2 * j); af[1] = b.c1.wsel(2 * j);
+            af[2] = b.c0.wsel(2 * j + 1); af[3] = b.c1.wsel(2 * j + 1);
+          }
+#pragma unroll
+          for (int mb = 0; mb < MB; ++mb) {
+            const uint4& q4 = xb[mb][j >> 1];
+            imma_16832_uu(di[mb], af, (j & 1) ? q4.z : q4.x, (j & 1) ? q4.w : q4.y);
+          }
+        }
+        // sum_k q_w of rows r0 / r1: the all-ones column mrows, held by lane quarter (mrows & 7) >> 1
+        const int cs = mrows;
+        int sw0i = (cs & 1) ? di[0][1] : di[0][0], sw1i = (cs & 1) ? di[0][3] : di[0][2];
+        if constexpr (MB > 1) {
+          if ((cs >> 3) == 1) { sw0i = (cs & 1) ? di[1][1] : di[1][0]; sw1i = (cs & 1) ? di[1][3] : di[1][2]; }
+        }
+        const int src = (lane & ~3) | ((cs & 7) >> 1);
+        const float sw0 = static_cast<float>(__shfl_sync(0xffffffffu, sw0i, src));
+        const float sw1 = static_cast<float>(__shfl_sync(0xffffffffu, sw1i, src));
+        const float2 sz0 = DT<T>::to_f2(b.m0), sz1 = DT<T>::to_f2(b.m1);     // (scale, zero) of rows r0, r1
+        const float zw0 = has_zp ? sz0.y : zp_fix, zw1 = has_zp ? sz1.y : zp_fix;
+#pragma unroll
+        for (int mb = 0; mb < MB; ++mb) {
+          const uint4 u0 = lds128(srow[mb] + xoff), u1 = lds128(srow1[mb] + xoff);   // (sum of codes, scale, zero-point)
+          const float sx0 = __uint_as_float(u0.x), ax0 = __uint_as_float(u0.y), zx0 = __uint_as_float(u0.z);
+          const float sx1 = __uint_as_float(u1.x), ax1 = __uint_as_float(u1.y), zx1 = __uint_as_float(u1.z);
+          // sum_k (q_w - z_w)(q_x - z_x) = D - z_x sum q_w - z_w sum q_x + 128 z_w z_x: integers, exact in fp32
+          const float v0 = fmaf(zw0, fmaf(128.f, zx0, -sx0), fmaf(-zx0, sw0, static_cast<float>(di[mb][0])));
+          const float v1 = fmaf(zw0, fmaf(128.f, zx1, -sx1), fmaf(-zx1, sw0, static_cast<float>(di[mb][1])));
+          const float v2 = fmaf(zw1, fmaf(128.f, zx0, -sx0), fmaf(-zx0, sw1, static_cast<float>(di[mb][2])));
+          const float v3 = fmaf(zw1, fmaf(128.f, zx1, -sx1), fmaf(-zx1, sw1, static_cast<float>(di[mb][3])));
+          acc[mb][0] = fmaf(sz0.x * ax0, v0, acc[mb][0]);
+          acc[mb][1] = fmaf(sz0.x * ax1, v1, acc[mb][1]);
+          acc[mb][2] = fmaf(sz1.x * ax0, v2, acc[mb][2]);
+          acc[mb][3] = fmaf(sz1.x * ax1, v3, acc[mb][3]);
+        }
+      }
+    } else if constexpr (IMMA) {
       int di[MB][4];
 #pragma unroll
       for (int mb = 0; mb < MB; ++mb) { di[mb][0] = di[mb][1] = di[mb][2] = di[mb][3] = 0; }
@@ -1422,8 +1528,10 @@ static SkinnyPlan plan_skinny(int64_t N, int64_t K) {
 template <typename T, int NBITS, int MB, int MODE>
 static int launch_skinny(SkinnyArgs a, cudaStream_t st) {
   auto kern = k3_skinny<T, NBITS, MB, MODE>;
-  constexpr int xpitch = MODE == 2 ? SK_IPITCH : SK_XPITCH;
+  constexpr int xpitch = MODE == 2 ? SK_IPITCH : MODE == 3 ? SK_ICOL : SK_XPITCH;
   constexpr int occ_target = MB <= 1 ? SK_OCC : 2;
+  const int m_rows_real = a.m_rows;
+  if (MODE == 3) a.m_rows += 1;                   // sizing only: the all-ones column rides with the tokens
   // per-CTA shared memory: ring + x slab within the budget that keeps occ_target CTAs resident
   const int budget = (228 * 1024) / occ_target - 1024 /* driver reserve */ - 512 /* static */ - 128 /* align */;
   const int stage_pitch = (stage_bytes<NBITS>(a.nsub) + 127) & ~127;
@@ -1445,6 +1553,7 @@ static int launch_skinny(SkinnyArgs a, cudaStream_t st) {
   a.chunk = chunk;
   a.stages = stages;
   const int smem = stages * stage_pitch + slab_bytes(a.m_rows, chunk, xpitch) + 128;
+  a.m_rows = m_rows_real;
   static std::mutex mu;           // one per instantiation
   static int max_set[kMaxDevices] = {};            // the attribute is a per-device property
   static std::unordered_map<int, int> occ_cache;   // all devices are sm_100: occupancy is the same on each
@@ -1492,6 +1601,10 @@ static int launch_skinny_post(const SkinnyArgs& a, cudaStream_t st) {
 
 template <typename T, int NBITS>
 static int launch_skinny_mb(const SkinnyArgs& a, cudaStream_t st) {
+  if constexpr (NBITS == 4 || NBITS == 8) {
+    // activation codes x weight codes on the integer tensor cores (q100_gemm_wna8); one mma column is the all-ones column
+    if (a.post == 3) return a.M <= 7 ? launch_skinny<T, NBITS, 1, 3>(a, st) : launch_skinny<T, NBITS, 2, 3>(a, st);
+  }
   if constexpr (NBITS == 4 || NBITS == 2) {
     // integer tensor-core path.  Measured (profiles/r01k): with one column group (M <= 2) it beats the fp16 form
     // (gate|up 16.6 vs 19.3 us); with two groups (M = 4) the extra MMAs, int->float conversions and limb staging
@@ -1529,7 +1642,8 @@ size_t skinny_workspace_bytes(int64_t M, int64_t N, int64_t K) {
 
 int gemm_skinny(const void* x, const void* packed, const void* meta, const void* bias, void* y,
                 int64_t M, int64_t N, int64_t K, int group, int n_bits, int disable_zp, int dtype,
-                void* workspace, size_t workspace_bytes, int exact_weights, int pdl, int x_gate_up, cudaStream_t st) {
+                void* workspace, size_t workspace_bytes, int exact_weights, int pdl, int x_gate_up, cudaStream_t st,
+                const void* x_minmax, int a_bits, int a_cuda_scale) {
   Q100_REQUIRE(M >= 1 && M <= 32, Q100_EINVAL, "skinny GEMM handles 1 <= M <= 32 (got %lld)", (long long)M);
   Q100_REQUIRE(K % SK_KB == 0, Q100_EUNSUPPORTED, "K=%lld must be a multiple of 128", (long long)K);
   Q100_REQUIRE(N % 8 == 0, Q100_EUNSUPPORTED, "N=%lld must be a multiple of 8", (long long)N);
@@ -1557,6 +1671,15 @@ int gemm_skinny(const void* x, const void* packed, const void* meta, const void*
   // the integer path applies
   a.post = (g % SK_KB == 0 && exact_weights != 1) ? 1 : 0;
   if (a.post && (n_bits == 4 || n_bits == 2) && M <= 2 && exact_weights == 0) a.post = 2;
+  if (x_minmax != nullptr) {
+    Q100_REQUIRE(a.post != 0 && (n_bits == 4 || n_bits == 8) && M <= 15 && a_bits >= 2 && a_bits <= 8 && !x_gate_up,
+                 Q100_EUNSUPPORTED, "integer W x A path: W4 / W8, group %% 128 == 0, M <= 15, abits 2..8");
+    a.post = 3;
+    a.x_minmax = x_minmax;
+    a.a_qmax = static_cast<float>((1 << a_bits) - 1);
+    a.a_denom = a.a_qmax;
+    a.a_cuda_scale = a_cuda_scale;
+  }
   a.m_rows = static_cast<int>(M);
   a.nsub = g >= SK_KB ? 1 : SK_KB / g;
   a.pdl = pdl;

@@ -173,6 +173,14 @@ class _FusedLinears:
         pw, ns = got
         m0 = mods[0]
         if m0.use_act_quant and not m0.disable_input_quant:
+            aq0 = m0.act_quantizer
+            same = all(m.act_quantizer.n_bits == aq0.n_bits and m.act_quantizer.enable == aq0.enable for m in mods)
+            if same and x.numel() // x.shape[-1] <= 15 and aq0.stat_group is None:
+                # decode shapes: activation quantisation as the prologue of the integer GEMM (K3c), one launch
+                saved = m0.bias
+                y = m0._fused_act_gemm(x, pw, None) if saved is None else None
+                if y is not None:
+                    return y.split(ns, dim=-1) if split else y
             xq = m0.act_quantizer(x)                  # same input, same per-token statistics for every consumer
             for m in mods[1:]:
                 aq, a0 = m.act_quantizer, m0.act_quantizer

@@ -62,6 +62,7 @@ SIGNATURES = {
     "q100_packed_words": (_i64, [_i64, _i64, _i]),
     "q100_dequantize": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _i, _i, _i, _vp, _vp]),
     "q100_gemm_wna16": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _sz, _i, _vp]),
+    "q100_gemm_wna8": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _i, _vp, _sz, _i, _vp]),
     "q100_gemm_workspace_bytes": (_sz, [_i64, _i64, _i64, _i, _i]),
     "q100_chain_desc_bytes": (_sz, [_i]),
     "q100_chain_ssq_parts": (_i64, [_i64]),

@@ -325,6 +325,31 @@ def gemm_wna16(x: torch.Tensor, w: PackedWeight, bias: Optional[torch.Tensor] = 
     return y.view(*shp[:-1], w.N)
 
 
+def gemm_wna8(x: torch.Tensor, w: PackedWeight, a_bits: int, minmax: Optional[torch.Tensor] = None,
+              bias: Optional[torch.Tensor] = None, flags: int = 0) -> torch.Tensor:
+    """y = fakequant_rows(x, a_bits) @ dequant(w)^T with the activation quantisation fused into the GEMM and the
+    contraction on the integer tensor cores (K3c, decode shapes: at most 15 rows).  ``minmax`` [rows, 2]: row
+    statistics over the full K (default: computed here with rows_minmax; pass the all-reduced ones under TP)."""
+    _require_cuda(x, w.packed, bias, minmax)
+    if x.dtype != w.dtype:
+        raise TypeError(f"q100.gemm_wna8: x is {x.dtype} but the packed weight was built for {w.dtype}")
+    shp = x.shape
+    x2 = x.contiguous().view(-1, w.K)
+    M = x2.shape[0]
+    if minmax is None:
+        minmax = rows_minmax(x2)
+    y = torch.empty((M, w.N), dtype=x.dtype, device=x.device)
+    if bias is not None:
+        bias = bias.to(x.dtype).contiguous()
+    need = _gemm_workspace_bytes(M, w.N, w.K, w.n_bits, 0)
+    ws = _workspace(x.device, need)
+    with _on(x.device):
+        check(lib.q100_gemm_wna8(x2.data_ptr(), minmax.data_ptr(), w.packed.data_ptr(), w.meta.data_ptr(), _ptr(bias),
+                                 y.data_ptr(), M, w.N, w.K, w.group, w.n_bits, int(a_bits), int(w.disable_zero_point),
+                                 _DT[x.dtype], ws.data_ptr(), ws.numel(), flags, _stream(x2)))
+    return y.view(*shp[:-1], w.N)
+
+
 def add_rmsnorm(x: torch.Tensor, weight: torch.Tensor, eps: float, residual: Optional[torch.Tensor] = None,
                 out_norm: Optional[torch.Tensor] = None, out_sum: Optional[torch.Tensor] = None):
     """(h, n) with h = residual + x (or x) and n = OmniLlamaRMSNorm(h); one launch (K4).  ``out_norm`` / ``out_sum``:

@@ -125,6 +125,25 @@ class QuantLinear(nn.Module):
             return None
         return packed
 
+    def _fused_act_gemm(self, x: torch.Tensor, packed, bias):
+        """W8A8 / W4A4 at decode shapes: the per-token activation quantisation runs as the prologue of the integer
+        dequant-GEMM (K3c, q100_gemm_wna8) instead of as a K2 launch in front of a 16-bit-activation GEMM.  None when the
+        case does not qualify (then forward() takes the reference's two steps)."""
+        aq = self.act_quantizer
+        if (packed is None or aq is None or not aq.enable or aq.n_bits > 8 or aq.symmetric or aq.group_size
+                or aq.disable_zero_point or aq.lwc or aq.metric == "fix0to1" or packed.n_bits not in (4, 8)
+                or packed.group % 128 != 0 or not self._fused_ok(x, packed) or x.numel() // x.shape[-1] > 15
+                or (torch.is_grad_enabled() and x.requires_grad)):
+            return None
+        mm = _ops.rows_minmax(x)
+        if aq.stat_group is not None:
+            import torch.distributed as dist
+            if dist.is_initialized() and dist.get_world_size(aq.stat_group) > 1:
+                from q100 import tp as _tp
+                mm = _tp.allreduce_minmax(mm, aq.stat_group)
+        from q100._lib import FLAG_CUDA_SCALE
+        return _ops.gemm_wna8(x, packed, aq.n_bits, mm, bias, FLAG_CUDA_SCALE if aq.cuda_eager_scale else 0)
+
     def release_dense_weight(self) -> bool:
         """Inference-only extension: free the dense fake-quantised ``weight`` buffer and keep only its
         packed twin (0.5 B/weight at W4 instead of 2.5).  ``weight`` becomes an empty tensor of the same
@@ -174,6 +193,9 @@ class QuantLinear(nn.Module):
                 packed = self.weight_quantizer.packed_for(weight)
 
         if self.use_act_quant and not self.disable_input_quant:
+            y = self._fused_act_gemm(input, packed, bias)
+            if y is not None:
+                return y
             input = self.act_quantizer(input)
 
         if packed is not None:
