@@ -671,6 +671,7 @@ def run_ours(args):
 
     # =============== whole model: random-init LLaMA3-8B W4A16 g128, tensor parallel ===========
     model_res = model70_res = None
+    cfg4_res = None
     if not os.environ.get("Q100_BENCH_SKIP_MODEL"):
         blocks.clear()
         fblocks.clear()
@@ -680,6 +681,16 @@ def run_ours(args):
         # SURVEY 8d config 5 (BASELINE.json configs[4]): LLaMA3-70B W4A16 g128, tensor parallel over all ranks (the
         # packed model is 38 GB: it also fits one B200, so the row exists at every N).  Perplexity is compared on the
         # first 4 blocks (the fp16 reference of all 80 does not fit next to the model).
+        # SURVEY 8d config 4 (BASELINE.json configs[3]): SmoothQuant-style W8A8 and W4A4 -- per-channel weights, per-token
+        # activations (K2 in front of the prefill GEMMs and inside QuantMatMul; K3c, the integer GEMM with the activation
+        # quantisation as its prologue, at decode shapes); under TP the row statistics are all-reduced
+        cfg4_res = {}
+        if not os.environ.get("Q100_BENCH_SKIP_CFG4"):
+            for tag, wb, ab in (("w8a8", 8, 8), ("w4a4", 4, 4)):
+                torch.cuda.empty_cache()
+                cfg4_res[tag] = bench_model.run(bench_model.default_args(wbits=wb, abits=ab, group=0, ppl_samples=1,
+                                                                         ppl_ref=True, batches="1,8", decode_steps=24),
+                                                dev, rank, world)
         model70_res = None
         if not os.environ.get("Q100_BENCH_SKIP_70B"):
             torch.cuda.empty_cache()
@@ -701,7 +712,7 @@ def run_ours(args):
                           "row_parallel_reduce": ("fused: scatter epilogue + reduce/broadcast over peer memory (K7b)"
                                                   if scatter is not None else "NCCL all-reduce") if world > 1 else None},
                 "roofline": roofline, "decode": decode, "quantize": quant, "strong_scaling": strong,
-                "llama3_8b": model_res, "llama3_70b": model70_res,
+                "llama3_8b": model_res, "llama3_8b_smoothquant_configs": cfg4_res, "llama3_70b": model70_res,
                 "cpu_baseline": cpu_base, "gpu_eager_reference_ops": gpu_eager, "e2e": e2e,
                 "gpu_launches": n_launch, "clocks": clocks, "peaks": P}
         print(json.dumps(line), flush=True)

@@ -31,7 +31,7 @@ int gemm_tc_dense(const void* x, const void* w, void* y, int64_t M, int64_t N, i
 int gemm_tca(const void* x, const void* packed, const void* meta, const void* bias, void* y,
              int64_t M, int64_t N, int64_t K, int group, int n_bits, int disable_zp, int dtype,
              int cluster, cudaStream_t st, void* const* peer_stage = nullptr, int rows_per = 0, int rank = 0,
-             int world = 1);
+             int world = 1, void* workspace = nullptr, size_t workspace_bytes = 0);
 bool gemm_tca_supported(int64_t M, int64_t N, int64_t K, int group, int n_bits);
 
 // ---------------------------------------------------------------- tensor maps
@@ -81,7 +81,15 @@ extern "C" size_t q100_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int
   const int64_t mm = M < 32 ? M : 32;
   const size_t a = skinny_workspace_bytes(mm, N, K);
   const size_t b = stream_workspace_bytes(mm < 16 ? mm : 16, N, K);
-  return a > b ? a : b;
+  size_t need = a > b ? a : b;
+  if (M > 32) {
+    // prefill (tcgen05) kernel, stream-K: fp32 partials of the tiles shared by neighbouring clusters, one
+    // [128 x 256] slots per SM, behind the first 4 MB (the decode kernels' share); optional -- without it the kernel
+    // schedules whole tiles
+    const size_t sk = (static_cast<size_t>(1) << 22) + 65536 + static_cast<size_t>(sm_count() + 8) * 2 * 128 * 256 * 4;
+    if (sk > need) need = sk;
+  }
+  return need;
 }
 
 extern "C" int q100_gemm_wna16(const void* x, const void* packed, const void* meta, const void* bias,
@@ -117,7 +125,8 @@ extern "C" int q100_gemm_wna16(const void* x, const void* packed, const void* me
       // measured on up_proj, M = 2048 (profiles/r01): 1193 / 1221 / 1236 TFLOP/s for clusters of 1 / 2 / 4
       const int64_t row_tiles = (N + 127) / 128;
       const int cluster = env_cluster > 0 ? env_cluster : (row_tiles % 4 == 0 ? 4 : row_tiles % 2 == 0 ? 2 : 1);
-      return gemm_tca(x, packed, meta, bias, y, M, N, K, group, n_bits, disable_zp, dtype, cluster, st);
+      return gemm_tca(x, packed, meta, bias, y, M, N, K, group, n_bits, disable_zp, dtype, cluster, st, nullptr, 0, 0, 1,
+                      workspace, workspace_bytes);
     }
     return gemm_tc(x, packed, meta, bias, y, M, N, K, group, n_bits, disable_zp, dtype, st);
   }

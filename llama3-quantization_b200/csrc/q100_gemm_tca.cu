@@ -57,7 +57,48 @@ struct TcaArgs {
   // stored over NVLink into slot `rank` of THAT rank's staging buffer [world][rows_per][N] instead of into y
   void* const* peer_stage;     // device array of `world` pointers (peer-mapped symmetric memory); null = plain y
   int rows_per, rank, world;
+  // stream-K for the tiles left over after the last full round (see SegIter): the clusters that share such a tile hand
+  // fp32 partials to the one that owns its last k blocks through `ws`
+  int stream_k;                // 0: whole tiles only
+  float* ws_part;              // [cluster][2][CL][NT columns][128 rows] fp32 partials (a range crosses <= 1 tile boundary)
+  uint32_t* ws_flag;           // [cluster][2][CL] arrival flags, zero between launches
 };
+
+// The (cluster tile, k range) segments of one cluster.  Whole tiles ct0, ct0 + C, ... in full rounds (the CTAs running
+// at the same time then work on neighbouring tiles and share x / weight tiles in L2); with stream_k the tiles left over
+// after the last full round (L = n_ct mod C of them) are cut along K instead: their L * num_kb k blocks are dealt out
+// evenly, cluster c takes the contiguous unit range [c UL / C, (c + 1) UL / C), split at the tile boundary it may
+// cross.  (Cutting ALL the work stream-K style was measured first: 967 instead of 1195 TFLOP/s on up_proj -- the
+// round-robin tile order matters more than the balance.)
+struct SegIter {
+  int ct, n_full_end, step, num_kb;      // full rounds: ct = ct0, ct0 + step, ... < n_full_end
+  int u, u_end, tile0;                   // leftover: units [u, u_end) of the tiles tile0, tile0 + 1, ...
+  __device__ __forceinline__ SegIter(const TcaArgs& a, int n_ct, int num_kb_, int ct0, int ct_step)
+      : ct(ct0), n_full_end(n_ct), step(ct_step), num_kb(num_kb_), u(0), u_end(0), tile0(n_ct) {
+    if (a.stream_k) {
+      const int rounds = n_ct / ct_step;
+      n_full_end = rounds * ct_step;
+      tile0 = n_full_end;
+      const long long UL = static_cast<long long>(n_ct - n_full_end) * num_kb_;
+      u = static_cast<int>(UL * ct0 / ct_step);
+      u_end = static_cast<int>(UL * (ct0 + 1) / ct_step);
+    }
+  }
+  __device__ __forceinline__ bool next(int& ct_out, int& kb0, int& kb1) {
+    if (ct < n_full_end) { ct_out = ct; kb0 = 0; kb1 = num_kb; ct += step; return true; }
+    if (u >= u_end) return false;
+    const int t = u / num_kb;
+    ct_out = tile0 + t;
+    kb0 = u - t * num_kb;
+    kb1 = min(num_kb, kb0 + (u_end - u));
+    u += kb1 - kb0;
+    return true;
+  }
+};
+// cluster that owns leftover unit u when C clusters split UL units as [floor(c UL / C), floor((c + 1) UL / C))
+__device__ __forceinline__ int sk_owner(int u, int C, long long UL) {
+  return static_cast<int>((static_cast<long long>(u + 1) * C + UL - 1) / UL) - 1;
+}
 
 template <int NBITS, int NT>
 struct TcaSmem {
@@ -117,6 +158,14 @@ __device__ __forceinline__ void ta_wait(uint32_t bar, uint32_t parity) {
       "bra LAB_WAIT;\n\t"
       "DONE:\n\t}\n"
       :: "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void ta_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
@@ -206,9 +255,11 @@ k3_tca(const __grid_constant__ CUtensorMap tm_x, const TcaArgs a) {
       tma_prefetch_desc(&tm_x);
       const uint64_t pol_x = policy_evict_last();
       uint32_t it = 0;
-      for (int ct = ct0; ct < n_ct; ct += ct_step) {
+      SegIter seg(a, n_ct, num_kb, ct0, ct_step);
+      int ct, kb0, kb1;
+      while (seg.next(ct, kb0, kb1)) {
         const int m0 = (ct % a.m_tiles) * NT;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const uint32_t s = it % SX;
           ta_wait(empty_x + 8 * s, ((it / SX) & 1) ^ 1);     // all CL CTAs have retired their MMAs on this stage
 #ifdef TA_EXP_NOX
@@ -231,11 +282,13 @@ k3_tca(const __grid_constant__ CUtensorMap tm_x, const TcaArgs a) {
       const uint64_t pol_w = policy_evict_first();
       uint8_t* pbase = smem_raw + (base_u32 - smem_u32(smem_raw)) + SM::kOffP;
       uint32_t it = 0;
-      for (int ct = ct0; ct < n_ct; ct += ct_step) {
+      SegIter seg(a, n_ct, num_kb, ct0, ct_step);
+      int ct, kb0, kb1;
+      while (seg.next(ct, kb0, kb1)) {
         const int nt = min((ct / a.m_tiles) * CL + rank, a.n_tiles - 1);   // ragged last group: redo the last tile
         const int n0 = nt * TA_ROWS;
         const int mbytes = min(TA_ROWS, a.N - n0) * 4;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const uint32_t s = it % TA_SP;
           ta_wait(empty_p + 8 * s, ((it / TA_SP) & 1) ^ 1);
           uint8_t* st = pbase + s * SM::kPStage;
@@ -255,14 +308,16 @@ k3_tca(const __grid_constant__ CUtensorMap tm_x, const TcaArgs a) {
 #ifdef TA_TIMING
     long long t_de = 0, t_af = 0, t_fx = 0, t_is = 0; const long long t_begin = clock64();
 #endif
-    for (int ct = ct0; ct < n_ct; ct += ct_step, ++tcount) {
+    SegIter seg(a, n_ct, num_kb, ct0, ct_step);
+    int ct, kb0, kb1;
+    for (; seg.next(ct, kb0, kb1); ++tcount) {
       TA_T(q0);
       ta_wait(d_empty, (tcount & 1) ^ 1);            // the epilogue has drained the accumulator
       tc_fence_after();
 #ifdef TA_TIMING
       t_de += clock64() - q0;
 #endif
-      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const uint32_t sx = it % SX, sa = it % TA_SA;
         TA_T(q1);
         ta_wait(a_full + 8 * sa, (it / TA_SA) & 1);
@@ -278,11 +333,11 @@ k3_tca(const __grid_constant__ CUtensorMap tm_x, const TcaArgs a) {
           const uint32_t at = tmem + TA_COL_A + sa * 32;
 #pragma unroll
           for (int k = 0; k < TA_BK / 16; ++k)
-            umma_f16_ts(tmem, at + 8 * k, bd + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_f16_ts(tmem, at + 8 * k, bd + 2 * k, idesc, (kb != kb0 || k != 0) ? 1u : 0u);   // a segment starts from zero
           umma_commit_u32(a_empty + 8 * sa);
           if (CL == 1) umma_commit_u32(empty_x + 8 * sx);
           else umma_commit_mc(empty_x + 8 * sx, kMask);      // frees the stage in every CTA of the cluster
-          if (kb == num_kb - 1) umma_commit_u32(d_full);
+          if (kb == kb1 - 1) umma_commit_u32(d_full);
         }
         __syncwarp();
 #ifdef TA_TIMING
@@ -308,8 +363,10 @@ k3_tca(const __grid_constant__ CUtensorMap tm_x, const TcaArgs a) {
     const uint32_t code_off_hi = ta_reg(base_u32 + SM::kOffP + 128 * 16 + row * 8);
     const uint32_t meta_off = ta_reg(base_u32 + SM::kOffP + SM::kP + row * 4);
     uint32_t it = 0;
-    for (int ct = ct0; ct < n_ct; ct += ct_step) {
-      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+    SegIter seg(a, n_ct, num_kb, ct0, ct_step);
+    int ct, kb0, kb1;
+    while (seg.next(ct, kb0, kb1)) {
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
         if (static_cast<int>(it & 1) != grp) continue;
         const uint32_t sp = it % TA_SP, sa = it % TA_SA;
         TA_T(d0);
@@ -398,10 +455,45 @@ k3_tca(const __grid_constant__ CUtensorMap tm_x, const TcaArgs a) {
     const T* bias = reinterpret_cast<const T*>(a.bias);
     const uint32_t lane_t = tmem + (static_cast<uint32_t>(quad * 32) << 16);
     uint32_t tcount = 0;
-    for (int ct = ct0; ct < n_ct; ct += ct_step, ++tcount) {
+    SegIter seg(a, n_ct, num_kb, ct0, ct_step);
+    int ct, kb0, kb1;
+    for (; seg.next(ct, kb0, kb1); ++tcount) {
       const int m0 = (ct % a.m_tiles) * NT;
       const int nt = (ct / a.m_tiles) * CL + rank;      // >= n_tiles in a ragged last group: nothing to store
       const int n = nt < a.n_tiles ? nt * TA_ROWS + quad * 32 + lane : a.N;
+      // stream-K (leftover tiles only): this cluster holds k blocks [kb0, kb1) of a tile that clusters c_first .. c_last
+      // share.  c_first (it owns the tile's first k block) is the finalizer: it adds the others' fp32 partials to its
+      // accumulator and writes y; the others leave their accumulator in their slot.  A cluster whose range crosses a
+      // tile boundary works on the END of one tile first (as a contributor) and on the START of the next one second
+      // (as its finalizer), so a finalizer only ever waits for segments that are FIRST in their cluster's range -- with
+      // the roles the other way round every cluster waited for its predecessor's second segment, a serial chain over
+      // all clusters (measured: 751 instead of 201 us on up_proj).
+      const bool split = (kb0 > 0 || kb1 < num_kb);
+      int c_first = 0, c_last = 0;
+      bool contributor = false;
+      const int C = ct_step, me = ct0;
+      const int n_full_end = (n_ct / C) * C;
+      const long long UL = static_cast<long long>(n_ct - n_full_end) * num_kb;
+      if (split) {
+        const int tl = ct - n_full_end;
+        c_first = sk_owner(tl * num_kb, C, UL);
+        c_last = sk_owner((tl + 1) * num_kb - 1, C, UL);
+        contributor = me != c_first;
+      }
+      auto slot_of = [&](int c) {                          // cluster c's slot for THIS tile: 0 = its range starts in it
+        const int first_tile = n_full_end + static_cast<int>((UL * c / C) / num_kb);
+        return (c * 2 + (ct == first_tile ? 0 : 1)) * CL + rank;
+      };
+      float* my_part = a.ws_part + static_cast<int64_t>(slot_of(me)) * (TA_ROWS * NT) + quad * 32 + lane;
+      if (split && !contributor && nt < a.n_tiles) {
+        if (quad == 0 && lane == 0) {
+          for (int c = c_first + 1; c <= c_last; ++c) {
+            uint32_t spins = 0;
+            while (ld_acquire_gpu(a.ws_flag + slot_of(c)) == 0u) { if (++spins > (1u << 26)) __trap(); }
+          }
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");   // the four epilogue warps
+      }
       ta_wait(d_full, tcount & 1);
       tc_fence_after();
       const float bv = (bias != nullptr && n < a.N) ? DT<T>::to_f(bias[n]) : 0.f;
@@ -429,6 +521,24 @@ k3_tca(const __grid_constant__ CUtensorMap tm_x, const TcaArgs a) {
           __syncwarp();
           if (lane == 0) ta_arrive(d_empty);
         }
+        if (contributor) {
+          // fp32 partial, [column][row]: a warp's store of one column is 128 contiguous bytes
+          if (nt < a.n_tiles) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) __stcg(my_part + (c0 + j) * TA_ROWS, __uint_as_float(r[j]));
+          }
+          continue;
+        }
+        if (split && nt < a.n_tiles) {
+          for (int c = c_first + 1; c <= c_last; ++c) {    // fixed order: deterministic
+            float* pc = a.ws_part + static_cast<int64_t>(slot_of(c)) * (TA_ROWS * NT) + quad * 32 + lane;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __ldcg(pc + (c0 + j) * TA_ROWS));
+            // the workspace is shared with the decode kernels' fix-up slots, which expect zeros: leave it clean
+#pragma unroll
+            for (int j = 0; j < 32; ++j) __stcg(pc + (c0 + j) * TA_ROWS, 0.f);
+          }
+        }
         const uint32_t eb = ebase + ((c0 >> 5) & 1) * 2048;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
@@ -449,6 +559,14 @@ k3_tca(const __grid_constant__ CUtensorMap tm_x, const TcaArgs a) {
         }
         // the buffer is reused two chunks later: the __syncwarp of the next chunk orders these reads before
         // the writes after it
+      }
+      if (nt < a.n_tiles && split) {
+        if (contributor) __threadfence();                  // this thread's partial stores are visible gpu-wide ...
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (quad == 0 && lane == 0) {
+          if (contributor) st_release_gpu(a.ws_flag + slot_of(me), 1u);      // ... before the flag
+          else for (int c = c_first + 1; c <= c_last; ++c) a.ws_flag[slot_of(c)] = 0u;   // consumed: clean for the next launch
+        }
       }
     }
     if (a.peer_stage != nullptr) __threadfence_system();   // the peer stores are performed before the grid completes
@@ -478,6 +596,8 @@ bool gemm_tca_supported(int64_t M, int64_t N, int64_t K, int group, int n_bits) 
          g % TA_BK == 0 && K % g == 0;
 }
 
+static thread_local size_t g_tca_ws_bytes = 0;     // size of the workspace behind TcaArgs::ws_flag for the current call
+
 template <typename T, int NBITS, int NT, int CL>
 static int launch_tca(const void* x, TcaArgs a, cudaStream_t st) {
   using SM = TcaSmem<NBITS, NT>;
@@ -501,6 +621,7 @@ static int launch_tca(const void* x, TcaArgs a, cudaStream_t st) {
   const int n_ct = a.m_tiles * ((a.n_tiles + CL - 1) / CL);
   int clusters = sm_count() / CL;
   if (clusters > n_ct) clusters = n_ct;
+  const bool want_sk = a.stream_k != 0;           // the caller has a workspace; decided below once the grid is known
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(clusters * CL);
   cfg.blockDim = dim3(TA_THREADS);
@@ -523,6 +644,19 @@ static int launch_tca(const void* x, TcaArgs a, cudaStream_t st) {
     if (clusters > max_clusters[dev]) clusters = max_clusters[dev];
     cfg.gridDim = dim3(clusters * CL);
   }
+  // stream-K for the leftover tiles when the tiles do not divide evenly over the clusters (896 tiles of up_proj at
+  // M = 2048 on 37 clusters of 4: 6.05 rounds that cost 7) and there is at least one full round
+  const int num_kb = a.K / TA_BK;
+  a.stream_k = 0;
+  if (want_sk && n_ct % clusters != 0 && n_ct > clusters && num_kb >= 8) {
+    const size_t flag_bytes = (static_cast<size_t>(clusters) * 2 * CL * 4 + 255) & ~static_cast<size_t>(255);
+    const size_t need = flag_bytes + static_cast<size_t>(clusters) * 2 * CL * TA_ROWS * NT * 4;
+    if (a.ws_flag != nullptr && a.ws_part == nullptr && need <= g_tca_ws_bytes) {
+      a.ws_part = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a.ws_flag) + flag_bytes);
+      a.stream_k = 1;
+    }
+  }
+  if (!a.stream_k) { a.ws_flag = nullptr; a.ws_part = nullptr; }
   return check_cuda(cudaLaunchKernelEx(&cfg, kern, tx, a), "k3_tca launch");
 }
 
@@ -553,9 +687,24 @@ static int gemm_tca_t(const void* x, const TcaArgs& a, int n_bits, int cluster, 
 
 int gemm_tca(const void* x, const void* packed, const void* meta, const void* bias, void* y,
              int64_t M, int64_t N, int64_t K, int group, int n_bits, int disable_zp, int dtype,
-             int cluster, cudaStream_t st, void* const* peer_stage, int rows_per, int rank, int world) {
+             int cluster, cudaStream_t st, void* const* peer_stage, int rows_per, int rank, int world,
+             void* workspace, size_t workspace_bytes) {
   Q100_REQUIRE(gemm_tca_supported(M, N, K, group, n_bits), Q100_EUNSUPPORTED, "tcgen05 (TMEM-A) path: unsupported shape");
   TcaArgs a{};
+  // Off unless Q100_TCA_STREAMK=1.  Measured on B200 at M = 2048 (tools/exp_streamk_tca.py, profiles/r02_streamk_tca.txt):
+  // cutting the leftover tiles along K balances the last round (6.05 instead of 7 tile times on up_proj) but the fp32
+  // partials (write, read, re-zero: ~70 MB) and the short segments' pipeline fill cost more than that: up_proj 213.6
+  // vs 201.3 us, q_proj 83.0 vs 67.5, 70B down_proj 771 vs 791 (the one shape that gains).
+  static const bool no_sk = []() { const char* e = getenv("Q100_TCA_STREAMK"); return !(e && e[0] == '1'); }();
+  // the stream-K slots live behind the decode kernels' share of the workspace (all zero between launches)
+  constexpr size_t kSkOff = 1 << 22;
+  if (workspace != nullptr && workspace_bytes > kSkOff && peer_stage == nullptr && !no_sk) {
+    a.stream_k = 1;
+    a.ws_flag = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(workspace) + kSkOff);
+    g_tca_ws_bytes = workspace_bytes - kSkOff;
+  } else {
+    g_tca_ws_bytes = 0;
+  }
   a.packed = packed; a.meta = meta; a.bias = bias; a.y = y;
   a.peer_stage = peer_stage; a.rows_per = rows_per; a.rank = rank; a.world = world;
   a.M = static_cast<int>(M); a.N = static_cast<int>(N); a.K = static_cast<int>(K);

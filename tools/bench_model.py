@@ -76,7 +76,7 @@ def run(a, dev, rank=0, world=1):
     cfg = {"8b": QL.LLAMA3_8B, "70b": QL.LLAMA3_70B}[getattr(a, "model", "8b")]
     n_layers = a.layers if a.layers else cfg.num_hidden_layers
     ppl_layers = getattr(a, "ppl_layers", None) or n_layers
-    args = QL.quant_args(a.wbits, a.group, a.abits)
+    args = QL.quant_args(a.wbits, a.group or None, a.abits)
     t0 = time.time()
     model = QL.QuantLlamaModel.random_init(cfg, args, dev, dt, seed=0, rank=rank, world=world, n_layers=n_layers,
                                            fast_attention=True)
@@ -100,7 +100,7 @@ def run(a, dev, rank=0, world=1):
         if a.ppl_ref and rank == 0:      # the single-GPU torch port on the full weights (rank 0; the others wait below)
             import llama_port as LP
             bc = LP.BlockCfg(cfg.hidden_size, cfg.intermediate_size, cfg.num_attention_heads,
-                             cfg.num_key_value_heads, cfg.rms_norm_eps, cfg.rope_theta, a.wbits, a.group, a.abits)
+                             cfg.num_key_value_heads, cfg.rms_norm_eps, cfg.rope_theta, a.wbits, a.group or None, a.abits)
             blocks = []
             for li in range(ppl_layers):
                 w = QL.random_block_weights(cfg, li, 0, dev, dt)
