@@ -55,6 +55,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     hdrs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     hdrs.append(os.path.join(ROOT, "include", "q100.h"))
     hdrs.append(os.path.abspath(__file__))
+    # the object directory does not travel to the GPU box (.gpurunignore): a library newer than every source is current
+    if not force and not _stale(OUT, [os.path.join(CSRC, s) for s in srcs] + hdrs):
+        return OUT
     jobs = []
     objs = []
     for s in srcs:
