@@ -249,6 +249,20 @@ int q100_rope_kv_decode(const void* qkv, const void* cos_cache, const void* sin_
                         int batch, int heads, int kv_heads, int head_dim, int64_t max_len,
                         int64_t rope_len, void* err_flag, int dtype, void* stream);
 /*
+ * q100_rope_qkv_prefill: the same step for q_len new tokens per sequence (prefill / calibration forward):
+ *   qkv [batch, q_len, (heads + 2*kv_heads) * head_dim]; position_ids int64 on the device, element
+ *   [b * pos_batch_stride + t] (stride 0 = one row shared by the batch, the reference's [1, q_len] form);
+ *   q_out [batch, heads, q_len, head_dim], k_out / v_out [batch, kv_heads, q_len, head_dim] -- the
+ *   transposed layouts of int_llama_layer.py:114-116 that the attention core and the tuple cache
+ *   (:130-135) consume, rotary applied to q (fp32, one rounding) and k (every op rounded) as above,
+ *   int_llama_layer.py:117-127.  head_dim % 16 == 0.  A position outside [0, rope_len) leaves that token's
+ *   outputs unwritten and sets *err_flag (nullable).
+ */
+int q100_rope_qkv_prefill(const void* qkv, const void* cos_cache, const void* sin_cache,
+                          const void* position_ids, int64_t pos_batch_stride, void* q_out, void* k_out,
+                          void* v_out, int batch, int64_t q_len, int heads, int kv_heads, int head_dim,
+                          int64_t rope_len, void* err_flag, int dtype, void* stream);
+/*
  * q100_silu_mul: out[rows, inter] = silu(gate) * up for gate_up [rows, 2*inter] (gate columns first), the
  *   epilogue of the fused gate|up GEMM: act_fn(gate_proj(x)) * up_proj(x), int_llama_layer.py:45.
  */

@@ -120,6 +120,78 @@ __global__ void k5_rope_kv(const T* __restrict__ qkv, const T* __restrict__ cosb
   }
 }
 
+// ---------------------------------------------------------------- K5p: rotary + head-major q / k / v (prefill)
+// One CTA per token; thread = (head, 8 consecutive pair indices): 16-byte loads of the two halves of a head from the
+// fused q|k|v row, 16-byte stores into q_out [B, H, T, D], k_out / v_out [B, KVH, T, D] (what the attention core and
+// the tuple cache read).  Same arithmetic as K5: q in fp32 with one rounding, k with every op rounded to T, v copied.
+template <typename T>
+__global__ void __launch_bounds__(256) k5p_rope_qkv(const T* __restrict__ qkv, const T* __restrict__ cosb,
+                                                    const T* __restrict__ sinb, const int64_t* __restrict__ pos_ids,
+                                                    int64_t pos_bstride, T* __restrict__ q_out, T* __restrict__ k_out,
+                                                    T* __restrict__ v_out, int Tq, int H, int KVH, int D,
+                                                    int64_t rope_len, uint32_t* __restrict__ err_flag) {
+  using Dt = DT<T>;
+  const int t = blockIdx.x, b = blockIdx.y;
+  const int half = D >> 1, cph = half >> 3;                 // 16-byte chunks per half head
+  const int heads = H + 2 * KVH;
+  const int64_t pos = pos_ids[b * pos_bstride + t];
+  if (pos < 0 || pos >= rope_len) {
+    if (err_flag != nullptr && threadIdx.x == 0) *err_flag = 1u;
+    return;
+  }
+  const T* row = qkv + (static_cast<int64_t>(b) * Tq + t) * heads * D;
+  const T* cr = cosb + pos * D;
+  const T* sr = sinb + pos * D;
+  for (int w = threadIdx.x; w < heads * cph; w += blockDim.x) {
+    const int head = w / cph, c = w - head * cph;
+    const T* src = row + static_cast<int64_t>(head) * D + c * 8;
+    const uint4 a = *reinterpret_cast<const uint4*>(src);
+    const uint4 bb = *reinterpret_cast<const uint4*>(src + half);
+    T* dst;
+    if (head < H) dst = q_out + ((static_cast<int64_t>(b) * H + head) * Tq + t) * D + c * 8;
+    else if (head < H + KVH) dst = k_out + ((static_cast<int64_t>(b) * KVH + (head - H)) * Tq + t) * D + c * 8;
+    else dst = v_out + ((static_cast<int64_t>(b) * KVH + (head - H - KVH)) * Tq + t) * D + c * 8;
+    if (head >= H + KVH) {
+      *reinterpret_cast<uint4*>(dst) = a;
+      *reinterpret_cast<uint4*>(dst + half) = bb;
+      continue;
+    }
+    const uint4 c1v = *reinterpret_cast<const uint4*>(cr + c * 8), c2v = *reinterpret_cast<const uint4*>(cr + half + c * 8);
+    const uint4 s1v = *reinterpret_cast<const uint4*>(sr + c * 8), s2v = *reinterpret_cast<const uint4*>(sr + half + c * 8);
+    const uint32_t* aw = reinterpret_cast<const uint32_t*>(&a);
+    const uint32_t* bw = reinterpret_cast<const uint32_t*>(&bb);
+    const uint32_t* c1w = reinterpret_cast<const uint32_t*>(&c1v);
+    const uint32_t* c2w = reinterpret_cast<const uint32_t*>(&c2v);
+    const uint32_t* s1w = reinterpret_cast<const uint32_t*>(&s1v);
+    const uint32_t* s2w = reinterpret_cast<const uint32_t*>(&s2v);
+    uint4 o1, o2;
+    uint32_t* o1w = reinterpret_cast<uint32_t*>(&o1);
+    uint32_t* o2w = reinterpret_cast<uint32_t*>(&o2);
+    const bool is_q = head < H;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 x1 = Dt::to_f2(aw[j]), x2 = Dt::to_f2(bw[j]);
+      const float2 c1 = Dt::to_f2(c1w[j]), c2 = Dt::to_f2(c2w[j]), s1 = Dt::to_f2(s1w[j]), s2 = Dt::to_f2(s2w[j]);
+      float lo_x, lo_y, hi_x, hi_y;
+      if (is_q) {
+        lo_x = __fadd_rn(__fmul_rn(x1.x, c1.x), __fmul_rn(-x2.x, s1.x));
+        lo_y = __fadd_rn(__fmul_rn(x1.y, c1.y), __fmul_rn(-x2.y, s1.y));
+        hi_x = __fadd_rn(__fmul_rn(x2.x, c2.x), __fmul_rn(x1.x, s2.x));
+        hi_y = __fadd_rn(__fmul_rn(x2.y, c2.y), __fmul_rn(x1.y, s2.y));
+      } else {
+        lo_x = __fadd_rn(Dt::rd(__fmul_rn(x1.x, c1.x)), Dt::rd(__fmul_rn(-x2.x, s1.x)));
+        lo_y = __fadd_rn(Dt::rd(__fmul_rn(x1.y, c1.y)), Dt::rd(__fmul_rn(-x2.y, s1.y)));
+        hi_x = __fadd_rn(Dt::rd(__fmul_rn(x2.x, c2.x)), Dt::rd(__fmul_rn(x1.x, s2.x)));
+        hi_y = __fadd_rn(Dt::rd(__fmul_rn(x2.y, c2.y)), Dt::rd(__fmul_rn(x1.y, s2.y)));
+      }
+      o1w[j] = Dt::pack2(lo_x, lo_y);
+      o2w[j] = Dt::pack2(hi_x, hi_y);
+    }
+    *reinterpret_cast<uint4*>(dst) = o1;
+    *reinterpret_cast<uint4*>(dst + half) = o2;
+  }
+}
+
 // ---------------------------------------------------------------- K6: silu(gate) * up
 // gate_up [M, 2I] (gate columns first), out [M, I]; 8 elements per thread.
 template <typename T>
@@ -212,6 +284,39 @@ extern "C" int q100_rope_kv_decode(const void* qkv, const void* cos_cache, const
         reinterpret_cast<__nv_bfloat16*>(k_cache), reinterpret_cast<__nv_bfloat16*>(v_cache), heads, kv_heads,
         head_dim, max_len, rope_len, ef);
   return check_cuda(cudaGetLastError(), "k5_rope_kv launch");
+}
+
+extern "C" int q100_rope_qkv_prefill(const void* qkv, const void* cos_cache, const void* sin_cache,
+                                     const void* position_ids, int64_t pos_batch_stride, void* q_out, void* k_out,
+                                     void* v_out, int batch, int64_t q_len, int heads, int kv_heads, int head_dim,
+                                     int64_t rope_len, void* err_flag, int dtype, void* stream) {
+  Q100_REQUIRE(qkv && cos_cache && sin_cache && position_ids && q_out && k_out && v_out, Q100_EINVAL,
+               "NULL pointer argument");
+  Q100_REQUIRE(dtype == Q100_F16 || dtype == Q100_BF16, Q100_EUNSUPPORTED, "fp16 / bf16 only (got dtype %d)", dtype);
+  Q100_REQUIRE(batch >= 0 && batch < 65536 && q_len >= 0 && q_len < (1ll << 31) && heads > 0 && kv_heads > 0 &&
+               rope_len > 0 && pos_batch_stride >= 0, Q100_EINVAL, "bad shape");
+  Q100_REQUIRE(head_dim >= 16 && head_dim % 16 == 0 && head_dim <= 1024, Q100_EUNSUPPORTED,
+               "head_dim=%d: a multiple of 16 (16-byte accesses of both halves of a head)", head_dim);
+  if (batch == 0 || q_len == 0) return Q100_OK;
+  int rc = ensure_device();
+  if (rc != Q100_OK) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const dim3 grid(static_cast<unsigned>(q_len), static_cast<unsigned>(batch));
+  const int64_t* pos = reinterpret_cast<const int64_t*>(position_ids);
+  uint32_t* ef = reinterpret_cast<uint32_t*>(err_flag);
+  if (dtype == Q100_F16)
+    k5p_rope_qkv<__half><<<grid, 256, 0, st>>>(
+        reinterpret_cast<const __half*>(qkv), reinterpret_cast<const __half*>(cos_cache),
+        reinterpret_cast<const __half*>(sin_cache), pos, pos_batch_stride, reinterpret_cast<__half*>(q_out),
+        reinterpret_cast<__half*>(k_out), reinterpret_cast<__half*>(v_out), static_cast<int>(q_len), heads, kv_heads,
+        head_dim, rope_len, ef);
+  else
+    k5p_rope_qkv<__nv_bfloat16><<<grid, 256, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(cos_cache),
+        reinterpret_cast<const __nv_bfloat16*>(sin_cache), pos, pos_batch_stride,
+        reinterpret_cast<__nv_bfloat16*>(q_out), reinterpret_cast<__nv_bfloat16*>(k_out),
+        reinterpret_cast<__nv_bfloat16*>(v_out), static_cast<int>(q_len), heads, kv_heads, head_dim, rope_len, ef);
+  return check_cuda(cudaGetLastError(), "k5p_rope_qkv launch");
 }
 
 extern "C" int q100_silu_mul(const void* gate_up, void* out, int64_t rows, int64_t inter, int dtype, void* stream) {

@@ -205,12 +205,20 @@ class QuantLlamaMLP(nn.Module):
         self.tp_group = None
 
     def forward(self, x):
-        fused = self._gate_up((self.gate_proj, self.up_proj), x)
-        if fused is not None:
-            gate, up = fused
-        else:
-            gate, up = self.gate_proj(x), self.up_proj(x)
-        out = self.down_proj(self.act_fn(gate) * up)
+        out = None
+        if self.act_fn is F.silu and not torch.is_grad_enabled():
+            # inference: gate | up stays one tensor and act_fn(gate) * up is K6 (or the down_proj GEMM's x staging at
+            # decode shapes) instead of two strided element-wise passes
+            gu = self._gate_up((self.gate_proj, self.up_proj), x, split=False)
+            if gu is not None:
+                out = self.down_proj.forward_gate_up(gu)
+        if out is None:
+            fused = self._gate_up((self.gate_proj, self.up_proj), x)
+            if fused is not None:
+                gate, up = fused
+            else:
+                gate, up = self.gate_proj(x), self.up_proj(x)
+            out = self.down_proj(self.act_fn(gate) * up)
         if getattr(self, "tp_world", 1) > 1 and not self.down_proj.reduced:
             out = _tp.reduce_output(out, _tp.ROW, self.tp_group)
         return out
@@ -269,25 +277,43 @@ class QuantLlamaAttention(nn.Module):
         nh = self.num_heads // self.tp_world
         nkv = max(self.num_key_value_heads // self.tp_world, 1)
 
-        fused = self._qkv((self.q_proj, self.k_proj, self.v_proj), hidden_states)
-        if fused is not None:
-            q, k, v = fused
-        else:
-            q, k, v = self.q_proj(hidden_states), self.k_proj(hidden_states), self.v_proj(hidden_states)
-        query_states = q.view(bsz, q_len, nh, self.head_dim).transpose(1, 2).type(torch.float32)
-        key_states = k.view(bsz, q_len, nkv, self.head_dim).transpose(1, 2)
-        value_states = v.view(bsz, q_len, nkv, self.head_dim).transpose(1, 2)
-
         static_kv = past_key_value if isinstance(past_key_value, StaticKV) else None
-        kv_seq_len = key_states.shape[-2]
+        kv_seq_len = q_len
         if static_kv is not None:
             kv_seq_len = static_kv.k.shape[-2]
         elif past_key_value is not None:
             kv_seq_len += past_key_value[0].shape[-2]
-        cos, sin = self.rotary_emb(value_states, seq_len=kv_seq_len)
         if position_ids is None:
             position_ids = torch.arange(kv_seq_len - q_len, kv_seq_len, device=hidden_states.device).unsqueeze(0)
-        query_states, key_states = apply_rotary_pos_emb(query_states, key_states, cos, sin, position_ids)
+
+        hd = self.head_dim
+        qkv = None
+        if (hidden_states.is_cuda and hidden_states.dtype in (torch.float16, torch.bfloat16) and hd % 16 == 0
+                and not torch.is_grad_enabled() and not torch.is_autocast_enabled() and position_ids.dim() == 2):
+            qkv = self._qkv((self.q_proj, self.k_proj, self.v_proj), hidden_states, split=False)
+        if qkv is not None and qkv.shape[-1] == (nh + 2 * nkv) * hd:
+            # inference outside autocast: rotary + the three head-major transposes as one launch (K5p); q is rotated
+            # in fp32 and rounded once -- what the fp32 cast of int_llama_layer.py:117 followed by the cast back below
+            # computes -- k with every op rounded to the 16-bit type
+            rc = getattr(self, "_rope16", None)
+            if rc is None or rc[0].dtype != qkv.dtype or rc[0].shape[0] < kv_seq_len or rc[0].device != qkv.device:
+                cos, sin = self.rotary_emb(qkv, seq_len=kv_seq_len)
+                rc = self._rope16 = (cos.to(qkv.dtype).contiguous(), sin.to(qkv.dtype).contiguous())
+            query_states, key_states, value_states = _ops.rope_qkv_prefill(qkv, rc[0], rc[1], position_ids, nh, nkv)
+        else:
+            if qkv is not None:
+                q, k, v = qkv.split([nh * hd, nkv * hd, nkv * hd], dim=-1)
+            else:
+                fused = self._qkv((self.q_proj, self.k_proj, self.v_proj), hidden_states)
+                if fused is not None:
+                    q, k, v = fused
+                else:
+                    q, k, v = self.q_proj(hidden_states), self.k_proj(hidden_states), self.v_proj(hidden_states)
+            query_states = q.view(bsz, q_len, nh, self.head_dim).transpose(1, 2).type(torch.float32)
+            key_states = k.view(bsz, q_len, nkv, self.head_dim).transpose(1, 2)
+            value_states = v.view(bsz, q_len, nkv, self.head_dim).transpose(1, 2)
+            cos, sin = self.rotary_emb(value_states, seq_len=kv_seq_len)
+            query_states, key_states = apply_rotary_pos_emb(query_states, key_states, cos, sin, position_ids)
 
         if static_kv is not None:
             key_states, value_states = static_kv.update(key_states, value_states, position_ids)
@@ -402,10 +428,8 @@ class QuantLlamaDecoderLayer(nn.Module):
             output_attentions=output_attentions,
             use_cache=use_cache,
         )
-        hidden_states = residual + hidden_states
-
-        residual = hidden_states
-        hidden_states = self.post_attention_layernorm(hidden_states)
+        # residual add + post-attention norm (one launch, K4, for 16-bit CUDA inference; the two eager steps otherwise)
+        residual, hidden_states = self.post_attention_layernorm.add_norm(hidden_states, residual)
         hidden_states = self.mlp(hidden_states)
         hidden_states = residual + hidden_states
 

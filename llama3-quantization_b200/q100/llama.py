@@ -163,6 +163,10 @@ class QuantLlamaModel(nn.Module):
 
     # ------------------------------------------------------------------ forward
     def _norm(self, x):
+        if x.is_cuda and x.dtype in (torch.float16, torch.bfloat16) and self.norm_weight.dtype == x.dtype \
+                and x.shape[-1] % 8 == 0 and x.shape[-1] <= 8192:
+            from . import ops as _ops
+            return _ops.add_rmsnorm(x, self.norm_weight, self.cfg.rms_norm_eps)[1]      # K4
         dt = x.dtype
         var = x.to(torch.float32).pow(2).mean(-1, keepdim=True)
         return (self.norm_weight * (x * torch.rsqrt(var + self.cfg.rms_norm_eps))).to(dt)

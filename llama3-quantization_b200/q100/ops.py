@@ -392,6 +392,33 @@ def rope_kv_decode(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, posi
     return q
 
 
+def rope_qkv_prefill(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, position_ids: torch.Tensor,
+                     heads: int, kv_heads: int, err_flag: Optional[torch.Tensor] = None):
+    """Rotary on q / k of ``q_len`` new tokens per sequence and the head-major layouts the attention core reads (K5p).
+    ``qkv`` [batch, q_len, (heads + 2 kv_heads) * head_dim] (the fused projection); ``position_ids`` int64 [1, q_len]
+    or [batch, q_len].  Returns q [batch, heads, q_len, hd], k, v [batch, kv_heads, q_len, hd]."""
+    _require_cuda(qkv, cos, sin, position_ids)
+    bsz, q_len, width = qkv.shape
+    hd = width // (heads + 2 * kv_heads)
+    qkv = qkv.contiguous()
+    if hd * (heads + 2 * kv_heads) != width or position_ids.dtype != torch.int64:
+        raise ValueError("q100.rope_qkv_prefill: qkv must be [batch, q_len, (heads + 2 kv_heads) * head_dim], positions int64")
+    if cos.dtype != qkv.dtype or cos.shape[-1] != hd or not cos.is_contiguous() or not sin.is_contiguous():
+        raise ValueError("q100.rope_qkv_prefill: cos/sin cache must be contiguous [pos, head_dim] in the model dtype")
+    pos = position_ids.reshape(-1, q_len).contiguous()
+    if pos.shape[0] not in (1, bsz):
+        raise ValueError("q100.rope_qkv_prefill: position_ids must be [1, q_len] or [batch, q_len]")
+    q = torch.empty((bsz, heads, q_len, hd), dtype=qkv.dtype, device=qkv.device)
+    k = torch.empty((bsz, kv_heads, q_len, hd), dtype=qkv.dtype, device=qkv.device)
+    v = torch.empty_like(k)
+    with _on(qkv.device):
+        check(lib.q100_rope_qkv_prefill(qkv.data_ptr(), cos.data_ptr(), sin.data_ptr(), pos.data_ptr(),
+                                        0 if pos.shape[0] == 1 else q_len, q.data_ptr(), k.data_ptr(), v.data_ptr(),
+                                        bsz, q_len, heads, kv_heads, hd, cos.shape[0], _ptr(err_flag),
+                                        _DT[qkv.dtype], _stream(qkv)))
+    return q, k, v
+
+
 def silu_mul(gate_up: torch.Tensor) -> torch.Tensor:
     """silu(gate) * up on the fused gate|up GEMM output [..., 2I] -> [..., I] (K6)."""
     _require_cuda(gate_up)

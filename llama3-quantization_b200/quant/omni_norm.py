@@ -3,8 +3,9 @@
 Module surface kept (buffer ``weight``, ``bias``, ``variance_epsilon`` / ``eps``, ``use_temporary_parameter``
 with ``temp_weight`` / ``temp_bias``, ``set_quant_state``) because ``models/transformation.py`` and
 ``quant/utils.py`` of the reference poke these attributes.  The normalisation is tiny and memory-bound and
-stays a handful of torch elementwise ops in the reference's order (fp32 variance, scale in the promoted
-dtype, affine, cast back); fusing it with the activation fake-quant is SURVEY.md section 8 row f4.
+is a handful of torch elementwise ops in the reference's order (fp32 variance, scale in the promoted dtype, affine,
+cast back) wherever autograd or fp32 is involved; 16-bit CUDA inference rows run K4 (q100_add_rmsnorm: one launch,
+optionally with the residual add in front) -- same per-op rounding.
 """
 import torch
 import torch.nn as nn
@@ -29,7 +30,29 @@ class OmniLlamaRMSNorm(_TemporaryAffine):
         self.bias = None
         self.variance_epsilon = eps
 
+    def _k4_ok(self, x):
+        """K4 (q100_add_rmsnorm) computes this module bit for bit up to the order of the fp32 sum of squares: 16-bit
+        CUDA rows of at most 8192 columns, no bias, nothing to differentiate."""
+        weight, bias = self._affine()
+        return (bias is None and x.is_cuda and x.dtype in (torch.float16, torch.bfloat16) and weight.dtype == x.dtype
+                and weight.device == x.device and x.shape[-1] % 8 == 0 and x.shape[-1] <= 8192 and x.numel() > 0
+                and weight.numel() == x.shape[-1]
+                and not (torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad)))
+
+    def add_norm(self, x, residual):
+        """(residual + x, self(residual + x)): the residual add of int_llama_layer.py:246 / :251 and the norm that
+        follows it as one launch (K4) where that applies."""
+        if self._k4_ok(x) and residual.dtype == x.dtype and residual.shape == x.shape and residual.is_cuda \
+                and not (torch.is_grad_enabled() and residual.requires_grad):
+            from q100 import ops as _ops
+            return _ops.add_rmsnorm(x, self._affine()[0], self.variance_epsilon, residual)
+        h = residual + x
+        return h, self.forward(h)
+
     def forward(self, hidden_states):
+        if self._k4_ok(hidden_states):
+            from q100 import ops as _ops
+            return _ops.add_rmsnorm(hidden_states, self._affine()[0], self.variance_epsilon)[1]
         in_dtype = hidden_states.dtype
         mean_sq = hidden_states.to(torch.float32).pow(2).mean(-1, keepdim=True)
         normed = hidden_states * torch.rsqrt(mean_sq + self.variance_epsilon)

@@ -166,3 +166,71 @@ def test_graph_decoder_fused_matches_module_path():
     # eager-fused and graph-fused run the very same kernels and must agree exactly
     assert torch.equal(outs[1], outs[2])
     assert (outs[0] == outs[1]).float().mean().item() >= 0.5
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("bsz,q_len,heads,kvh,hd,per_batch_pos", [
+    (1, 2048, 32, 8, 128, False), (2, 37, 32, 8, 128, True), (3, 5, 4, 2, 64, False), (1, 1, 8, 8, 128, False),
+    (2, 300, 8, 1, 128, False), (1, 64, 6, 2, 48, False)])
+def test_rope_qkv_prefill_bit_exact(dtype, bsz, q_len, heads, kvh, hd, per_batch_pos):
+    """K5p against the reference formulation (int_llama_layer.py:114-127: view / transpose, q in fp32, rotary on
+    q and k) + the cast back to the model dtype our layer applies outside autocast: bit-exact, all three outputs."""
+    from q100 import ops
+    dev = torch.device("cuda:0")
+    past = 11
+    g = torch.Generator(device=dev).manual_seed(bsz * 7 + q_len)
+    qkv = torch.randn(bsz, q_len, (heads + 2 * kvh) * hd, generator=g, device=dev).to(dtype)
+    cos, sin = LP.rotary_cache(hd, past + q_len + 3, 500000.0, dev, dtype)
+    pos = torch.arange(past, past + q_len, device=dev).unsqueeze(0)
+    if per_batch_pos:
+        pos = torch.stack([pos[0] - b for b in range(bsz)])
+    q, k, v = ops.rope_qkv_prefill(qkv, cos.contiguous(), sin.contiguous(), pos, heads, kvh)
+    qs, ks, vs = qkv.split([heads * hd, kvh * hd, kvh * hd], dim=-1)
+    q_ref = qs.view(bsz, q_len, heads, hd).transpose(1, 2).type(torch.float32)
+    k_ref = ks.view(bsz, q_len, kvh, hd).transpose(1, 2)
+    v_ref = vs.view(bsz, q_len, kvh, hd).transpose(1, 2)
+    q_ref, k_ref = LP.apply_rotary_pos_emb(q_ref, k_ref, cos, sin, pos)
+    assert q.is_contiguous() and k.is_contiguous() and v.is_contiguous()
+    assert torch.equal(q, q_ref.to(dtype))
+    assert torch.equal(k, k_ref) and torch.equal(v, v_ref)
+
+
+def test_rope_qkv_prefill_position_outside_table():
+    from q100 import ops
+    dev = torch.device("cuda:0")
+    qkv = torch.randn(1, 4, (4 + 4) * 64, device=dev).half()
+    cos, sin = LP.rotary_cache(64, 8, 500000.0, dev, torch.float16)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    ops.rope_qkv_prefill(qkv, cos.contiguous(), sin.contiguous(), torch.tensor([[5, 6, 7, 8]], device=dev), 4, 2, err)
+    torch.cuda.synchronize()
+    assert int(err.item()) == 1
+    with pytest.raises(ValueError):
+        ops.rope_qkv_prefill(qkv, cos.contiguous(), sin.contiguous(), torch.zeros(3, 4, dtype=torch.int64, device=dev), 4, 2)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("use_cache", [False, True])
+def test_block_prefill_kernels_match_eager_formulation(dtype, use_cache, monkeypatch):
+    """QuantLlamaDecoderLayer.forward at prefill sizes: the K4 / K5p / K6 route (inference, no autocast) against the
+    same layer with those kernels switched off (the reference's eager op sequence on the same packed GEMMs)."""
+    from q100 import llama as QL
+    from quant import omni_norm
+    import models.int_llama_layer as ILL
+    dev = torch.device("cuda:0")
+    cfg = QL.LlamaCfg(512, 1024, 8, 2, 1, 64)
+    layer = QL.build_block(cfg, QL.random_block_weights(cfg, 0, 3, dev, dtype), QL.quant_args(4, 128))
+    g = torch.Generator(device=dev).manual_seed(1)
+    x = torch.randn(2, 96, 512, generator=g, device=dev).to(dtype)
+    mask = QL.QuantLlamaModel.causal_mask(2, 96, 96, dtype, dev)
+    pos = torch.arange(96, device=dev).unsqueeze(0)
+    with torch.no_grad():
+        out = layer(x, attention_mask=mask, position_ids=pos, use_cache=use_cache)
+        with torch.enable_grad():            # grad mode switches every fused glue kernel off (nothing requires grad)
+            monkeypatch.setattr(omni_norm.OmniLlamaRMSNorm, "_k4_ok", lambda self, t: False)
+            ref = layer(x, attention_mask=mask, position_ids=pos, use_cache=use_cache)
+    assert torch.allclose(out[0].float(), ref[0].float(), rtol=4 * _ulp(dtype), atol=4 * _ulp(dtype) * ref[0].float().abs().max().item())
+    if use_cache:
+        (k, v), (k_ref, v_ref) = out[-1], ref[-1]
+        # the norm in front differs by the order of its fp32 sum (<= 1 ulp of n1), so k / v agree to GEMM round-off
+        assert torch.allclose(v.float(), v_ref.float(), rtol=0, atol=8 * _ulp(dtype) * v_ref.float().abs().max().item())
+        assert torch.allclose(k.float(), k_ref.float(), rtol=0, atol=8 * _ulp(dtype) * k_ref.float().abs().max().item())
