@@ -78,6 +78,9 @@ enum q100_status {
                                       applies act_fn(gate) * up (SiLU, the arithmetic of q100_silu_mul, i.e. of
                                       models/int_llama_layer.py:45) while it stages x: down_proj without the
                                       separate element-wise launch.  Q100_EUNSUPPORTED for M > 32.      */
+#define Q100_GEMM_NO_ROWS      0x200 /* decode shapes, W4 g128, M <= 8: the stream-K kernel (K3a, tiles shared between CTAs and
+                                      fixed up through the workspace) instead of the row-owner kernel (K3r: every CTA
+                                      streams whole rows, no fix-up), which is the default where it applies      */
 #define Q100_GEMM_PDL          0x8 /* launch with programmatic stream serialization: the kernel starts
                                       streaming its (static) weights while the previous kernel of the
                                       stream drains, and waits (griddepcontrol.wait) before it touches

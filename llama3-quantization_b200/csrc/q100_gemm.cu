@@ -14,7 +14,7 @@ namespace q100 {
 int gemm_skinny(const void* x, const void* packed, const void* meta, const void* bias, void* y,
                 int64_t M, int64_t N, int64_t K, int group, int n_bits, int disable_zp, int dtype,
                 void* workspace, size_t workspace_bytes, int exact_weights, int pdl, int x_gate_up, cudaStream_t st,
-                const void* x_minmax = nullptr, int a_bits = 16, int a_cuda_scale = 0);
+                const void* x_minmax = nullptr, int a_bits = 16, int a_cuda_scale = 0, int no_rows = 0);
 size_t skinny_workspace_bytes(int64_t M, int64_t N, int64_t K);
 int gemm_stream(const void* x, const void* packed, const void* meta, const void* bias, void* y,
                 int64_t M, int64_t N, int64_t K, int group, int n_bits, int disable_zp, int dtype,
@@ -146,7 +146,8 @@ extern "C" int q100_gemm_wna16(const void* x, const void* packed, const void* me
                      reinterpret_cast<uint8_t*>(y) + m0 * N * esz, mc, N, K, group, n_bits, disable_zp,
                      dtype, workspace, workspace_bytes,
                      (flags & Q100_GEMM_EXACT_WEIGHTS) ? 1 : (flags & Q100_GEMM_NO_IMMA) ? 2 : 0,
-                     (flags & Q100_GEMM_PDL) ? 1 : 0, gate_up ? 1 : 0, st);
+                     (flags & Q100_GEMM_PDL) ? 1 : 0, gate_up ? 1 : 0, st, nullptr, 16, 0,
+                     (flags & Q100_GEMM_NO_ROWS) ? 1 : 0);
     if (rc != Q100_OK) return rc;
   }
   return Q100_OK;

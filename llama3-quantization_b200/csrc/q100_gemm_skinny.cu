@@ -1633,6 +1633,10 @@ int skinny_timing(long long* out, int n) {
 }
 #endif
 
+bool gemm_rows_supported(int64_t M, int64_t N, int64_t K, int group, int n_bits, int mode);
+int gemm_rows(const void* x, const void* packed, const void* meta, const void* bias, void* y, int64_t M, int64_t N,
+              int64_t K, int disable_zp, int dtype, int mode, int pdl, int x_gate_up, cudaStream_t st);
+
 size_t skinny_workspace_bytes(int64_t M, int64_t N, int64_t K) {
   const SkinnyPlan p = plan_skinny(N, K);
   const int mb = M <= 8 ? 1 : M <= 16 ? 2 : 4;
@@ -1643,7 +1647,7 @@ size_t skinny_workspace_bytes(int64_t M, int64_t N, int64_t K) {
 int gemm_skinny(const void* x, const void* packed, const void* meta, const void* bias, void* y,
                 int64_t M, int64_t N, int64_t K, int group, int n_bits, int disable_zp, int dtype,
                 void* workspace, size_t workspace_bytes, int exact_weights, int pdl, int x_gate_up, cudaStream_t st,
-                const void* x_minmax, int a_bits, int a_cuda_scale) {
+                const void* x_minmax, int a_bits, int a_cuda_scale, int no_rows) {
   Q100_REQUIRE(M >= 1 && M <= 32, Q100_EINVAL, "skinny GEMM handles 1 <= M <= 32 (got %lld)", (long long)M);
   Q100_REQUIRE(K % SK_KB == 0, Q100_EUNSUPPORTED, "K=%lld must be a multiple of 128", (long long)K);
   Q100_REQUIRE(N % 8 == 0, Q100_EUNSUPPORTED, "N=%lld must be a multiple of 8", (long long)N);
@@ -1680,6 +1684,9 @@ int gemm_skinny(const void* x, const void* packed, const void* meta, const void*
     a.a_denom = a.a_qmax;
     a.a_cuda_scale = a_cuda_scale;
   }
+  // K3r (q100_gemm_rows.cu): every CTA owns whole rows, no fix-up between CTAs -- the default where it applies
+  if (!no_rows && (a.post == 1 || a.post == 2) && gemm_rows_supported(M, N, K, g, n_bits, a.post))
+    return gemm_rows(x, packed, meta, bias, y, M, N, K, disable_zp, dtype, a.post, pdl, x_gate_up, st);
   a.m_rows = static_cast<int>(M);
   a.nsub = g >= SK_KB ? 1 : SK_KB / g;
   a.pdl = pdl;

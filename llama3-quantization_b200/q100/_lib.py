@@ -28,6 +28,7 @@ GEMM_FORCE_STREAM_TC = 0x20
 GEMM_FORCE_TC_SMEM = 0x40
 GEMM_NO_IMMA = 0x80
 GEMM_X_GATE_UP = 0x100
+GEMM_NO_ROWS = 0x200
 
 _vp, _i, _i64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
 
