@@ -26,6 +26,7 @@
 //     bias is added and y is written with coalesced stores.
 // x is staged in shared memory by the CTA (all of K at once when it fits, else in chunks inside every pass).
 #include <mutex>
+#include <type_traits>
 #include <cstdlib>
 #include <cstdio>
 
@@ -36,9 +37,8 @@ namespace q100 {
 
 namespace {
 
-constexpr int RW_WARPS = 8;
+constexpr int RW_WARPS = 16;
 constexpr int RW_THREADS = RW_WARPS * 32;
-constexpr int RW_PR = 32;                         // rows per pass
 constexpr int RW_TROW = 32;                       // bytes per row of a 64-k tile at W4
 constexpr int RW_TILE_BYTES = 128 * RW_TROW;      // one [128 x 64] tile in HBM
 constexpr int RW_XPITCH = 320;                    // fp16 form: bytes per (token, 128-k block) of x: 256 + 64 (sums)
@@ -52,11 +52,11 @@ struct RowsArgs {
   const void* bias;       // [N] T or null
   void* y;                // [M, N] T
   int M, N, K;
-  int kblocks;            // K / 128
-  int chunk;              // k blocks of x staged at a time (a multiple of 8; >= kblocks: everything, once)
+  int kblocks;            // K / 128 (a multiple of 8)
   int has_zp;
   float qmin;
   int x_gate_up;
+  int pair;               // two blocks per step (development switch)
 };
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
@@ -74,13 +74,14 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
-// 16 / 4 bytes global -> shared, asynchronous; src_bytes = 0 writes zeros without reading
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes, uint64_t policy) {
-  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2, %3;"
-               :: "r"(dst), "l"(src), "r"(src_bytes), "l"(policy) : "memory");
+// 16 / 4 bytes global -> shared, asynchronous
+// (no L2 cache hint: with the policy operand ptxas 12.9 put the descriptor of the LDGSTS inside the main loop into an
+// odd uniform register pair, desc[UR1], and the launch died with "illegal instruction" as soon as that path ran)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
 }
-__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, uint32_t src_bytes) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(dst), "l"(src), "r"(src_bytes) : "memory");
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
@@ -127,154 +128,171 @@ __device__ __forceinline__ uint4 silu_mul8(const uint4& g, const uint4& u) {
   return make_uint4(ow[0], ow[1], ow[2], ow[3]);
 }
 
-struct BlockRegs { uint4 c0, c1; uint32_t m0, m1; };   // codes of rows g / g + 8 (32 k each) and their (scale, zero)
+// ---------------------------------------------------------------- the kernel
+// Shared memory: red[2][16 warps][4][32] fp32 | misc (token maxima, coefficients) | the warps' rings [16][D][RW_SLOT] |
+// stab[kblocks][8] fp32 (zero-point sums per limb column) | x limbs [kblocks][3 M][RW_ICOL]
+constexpr int RW_RED_BYTES = 2 * RW_WARPS * 4 * 32 * 4;
+constexpr int RW_MISC_BYTES = 1024;
+constexpr int RW_XR = 8;                          // 16-byte chunks of x a thread holds between the two staging phases
 
-// MODE 1: fp16 magic-form operand (M <= 8);  MODE 2: integer operand, three limbs per token (M <= 2)
-// D: blocks a warp keeps in flight;  OCC: CTAs per SM the instantiation is compiled for
-template <typename T, int MODE, int D, int OCC>
-__global__ void __launch_bounds__(RW_THREADS, OCC) k3_rows(const RowsArgs a) {
-  constexpr bool IMMA = MODE == 2;
-  constexpr bool kConvX = !IMMA && DT<T>::kCode == Q100_BF16;    // bf16 activations -> scaled fp16 at staging
-  constexpr int RED_FLOATS = RW_WARPS * 4 * 32;                  // one parity of the cross-warp reduction buffer
+template <typename T, int D, bool HAS_ZP>
+__global__ void __launch_bounds__(RW_THREADS, 1) k3_rows(const RowsArgs a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  float* red = reinterpret_cast<float*>(smem_raw);
-  const uint32_t wring = smem_u32(smem_raw) + 2 * RED_FLOATS * 4 + (threadIdx.x >> 5) * (D * RW_SLOT);   // this warp's ring
-  uint8_t* xs_ptr = smem_raw + 2 * RED_FLOATS * 4 + RW_WARPS * D * RW_SLOT;
-  const uint32_t xs_u32 = smem_u32(xs_ptr);
-
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
+  float* red = reinterpret_cast<float*>(smem_raw);
+  uint32_t* tokmax = reinterpret_cast<uint32_t*>(smem_raw + RW_RED_BYTES);               // [16 warps][2]
+  float* coef = reinterpret_cast<float*>(smem_raw + RW_RED_BYTES + 256);                 // [2 tokens][4]
+  const uint32_t wring = smem_u32(smem_raw) + RW_RED_BYTES + RW_MISC_BYTES + warp * (D * RW_SLOT) + lane * 16;
+  uint8_t* stab_ptr = smem_raw + RW_RED_BYTES + RW_MISC_BYTES + RW_WARPS * D * RW_SLOT;
+  const int kblocks = a.kblocks;
+  uint8_t* xs_ptr = stab_ptr + kblocks * 32;
+  const int mrows = a.M;
+  const int blk_pitch = 3 * mrows * RW_ICOL;      // bytes of x limbs per k block
+
   const int G = gridDim.x, cta = blockIdx.x;
   const int Q = a.N >> 2;
   const int q0 = static_cast<int>(static_cast<int64_t>(cta) * Q / G);
   const int q1 = static_cast<int>(static_cast<int64_t>(cta + 1) * Q / G);
   const int R0 = 4 * q0, nr = 4 * (q1 - q0);
-  const int np = (nr + RW_PR - 1) / RW_PR;
-  const int kblocks = a.kblocks;
   pdl_launch_dependents();
   if (nr == 0) return;
 
-  // ---- this warp's sequence of blocks: pass p (rows R0 + 32 p ...), j-th k group of the warp inside the pass
-  const int last_pr = nr - (np - 1) * RW_PR;
-  const bool last_two = last_pr > 16;
-  const int bpp2 = (kblocks + 3) >> 2, bpp1 = (kblocks + 7) >> 3;      // blocks per pass and warp (two slabs / one slab)
-  const int ktiles = kblocks * 2;
+  // ---- geometry of this CTA: its ns = ceil(nr / 16) slabs of 16 rows are walked in passes of S = 4 slabs, then what
+  // is left as 2 + 1, 2 or 1; in a pass of S slabs the 16 warps split the work by (slab, k group mod KW), KW = 16 / S
+  const int ns = (nr + 15) >> 4;
+  const int n4 = ns >> 2, rem = ns & 3;
+  const int np = n4 + (rem == 3 ? 2 : rem ? 1 : 0);
+  auto pass_geo = [&](int p, int& sh_, int& slab0_) {   // log2 S and first slab of pass p
+    if (p < n4) { sh_ = 2; slab0_ = 4 * p; }
+    else if (rem == 3) { sh_ = p == n4 ? 1 : 0; slab0_ = 4 * n4 + (p == n4 ? 0 : 2); }
+    else { sh_ = rem == 2 ? 1 : 0; slab0_ = 4 * n4; }
+  };
   const uint8_t* packed = reinterpret_cast<const uint8_t*>(a.packed);
   const uint8_t* meta = reinterpret_cast<const uint8_t*>(a.meta);
-  const int64_t mrow_pitch = static_cast<int64_t>(a.N) * 4;           // bytes between the side-band rows of two groups
+  const int64_t ktile_row = static_cast<int64_t>(kblocks) * 2 * RW_TILE_BYTES;   // bytes of one 128-row tile row
 
-  // the block the load iterator points at
-  int lp = 0, lj = 0;                             // pass, index inside the pass
-  const uint8_t* pc0 = nullptr;                   // codes of row g of the slab: this lane's 16 bytes of k group kb
-  const uint8_t* pc1 = nullptr;                   // ... of row g + 8
-  const uint8_t* pm0 = nullptr;                   // (scale, zero) of row g, group kb
-  bool v0 = false, v1 = false;                    // the rows exist (inside this CTA's range)
-  int lstride = 4, lbpp = bpp2, lkb = 0;
+  // ---- the load iterator: rows past the CTA's range are clamped to its last row (same sectors, results unused)
+  const uint8_t* pc0; const uint8_t* pc1; const uint8_t* pm0; const uint8_t* pm1;
+  int64_t cstep = 0, mstep = 0;                   // to this warp's next k group
+  int lj = 0, lp = 0, lbpp = 0;
   auto setup_pass = [&](int p) {
-    const bool two = (p < np - 1) || last_two;
-    const int slab = two ? (warp & 1) : 0;
-    lkb = two ? (warp >> 1) : warp;
-    lstride = two ? 4 : 8;
-    lbpp = two ? bpp2 : bpp1;
-    const int rel = p * RW_PR + slab * 16 + g;    // row inside the CTA's range
-    v0 = rel < nr; v1 = rel + 8 < nr;
-    const int r0 = R0 + rel, r1 = r0 + 8;
-    const int lo = (t >> 1) * RW_TILE_BYTES + (t & 1) * 16;
-    pc0 = packed + (static_cast<int64_t>(r0 >> 7) * ktiles + 2 * lkb) * RW_TILE_BYTES + (r0 & 127) * RW_TROW + lo;
-    pc1 = packed + (static_cast<int64_t>(r1 >> 7) * ktiles + 2 * lkb) * RW_TILE_BYTES + (r1 & 127) * RW_TROW + lo;
-    pm0 = meta + lkb * mrow_pitch + static_cast<int64_t>(r0) * 4;
+    int sh_, slab0_;
+    pass_geo(p, sh_, slab0_);
+    const int kw = RW_WARPS >> sh_, kq = warp >> sh_;
+    const int rel = (slab0_ + (warp & ((1 << sh_) - 1))) * 16 + g;
+    const int r0 = R0 + min(rel, nr - 1), r1 = R0 + min(rel + 8, nr - 1);
+    const int lo = (t >> 1) * RW_TILE_BYTES + (t & 1) * 16 + kq * 2 * RW_TILE_BYTES;
+    pc0 = packed + (r0 >> 7) * ktile_row + (r0 & 127) * RW_TROW + lo;
+    pc1 = packed + (r1 >> 7) * ktile_row + (r1 & 127) * RW_TROW + lo;
+    pm0 = meta + (static_cast<int64_t>(kq) * a.N + r0) * 4;
+    pm1 = meta + (static_cast<int64_t>(kq) * a.N + r1) * 4;
+    cstep = static_cast<int64_t>(kw) * 2 * RW_TILE_BYTES;
+    mstep = static_cast<int64_t>(kw) * a.N * 4;
+    lbpp = kblocks >> (4 - sh_);
   };
-  const uint64_t pol = policy_evict_first();
-  uint32_t islot = 0;                             // ring slot the next request lands in
-  auto issue_next = [&]() {                       // request the block under the load iterator (one cp.async group), advance it
+  auto issue = [&](uint32_t slot_addr) {          // one cp.async group: the block under the iterator (or nothing)
     if (lp < np) {
-      const bool kv = lkb < kblocks;
-      const uint32_t dst = wring + islot * RW_SLOT + lane * 16;
-      const uint32_t dm = wring + islot * RW_SLOT + 1024 + lane * 4;
-      const bool a0 = kv && v0, a1 = kv && v1;
-      cp_async16(dst, a0 ? pc0 : packed, a0 ? 16u : 0u, pol);
-      cp_async16(dst + 512, a1 ? pc1 : packed, a1 ? 16u : 0u, pol);
-      cp_async4(dm, a0 ? pm0 : meta, a0 ? 4u : 0u);
-      cp_async4(dm + 128, a1 ? pm0 + 32 : meta, a1 ? 4u : 0u);
-      lkb += lstride;
-      pc0 += lstride * 2 * RW_TILE_BYTES;
-      pc1 += lstride * 2 * RW_TILE_BYTES;
-      pm0 += lstride * mrow_pitch;
+      cp_async16(slot_addr, pc0);
+      cp_async16(slot_addr + 512, pc1);
+      cp_async4(slot_addr + 1024 - lane * 12, pm0);
+      cp_async4(slot_addr + 1152 - lane * 12, pm1);
+      pc0 += cstep; pc1 += cstep; pm0 += mstep; pm1 += mstep;
       if (++lj == lbpp) { lj = 0; ++lp; if (lp < np) setup_pass(lp); }
     }
     cp_async_commit();
-    if (++islot == D) islot = 0;
   };
-
   setup_pass(0);
 #pragma unroll 1
-  for (int d = 0; d < D - 1; ++d) issue_next();   // static data: in flight before the previous kernel has finished
+  for (int d = 0; d < D - 2; ++d) issue(wring + d * RW_SLOT);   // static data: in flight before the previous kernel ends
 
-  // ===================== x =====================
-  const int mrows = a.M;
-  constexpr int kXPitch = IMMA ? 3 * RW_ICOL : RW_XPITCH;
-  const int blk_pitch = mrows * kXPitch;          // bytes of x per staged k block
-  const bool has_zp = a.has_zp != 0;
-  const float zp_fix = -a.qmin;
-
-  // x of blocks [kb0, kb0 + n): rows m < M.  Layouts as in K3a (q100_gemm_skinny.cu: stage_x).
-  auto stage_x = [&](int kb0, int n) {
+  // ===================== x: block fixed point with ONE exponent per token =====================
+  // xi = rint(x 2^(21 - e)), e = exponent of the token's largest magnitude, as three balanced base-256 digits, one mma
+  // column each.  The elements that meet the HIGH nibbles of the packed words (e2, e3, e6, e7 of every 8) are scaled
+  // by another 1/16: the weight operand for them is (w & 0xf0f0f0f0) = 16 q, no shift.  stab holds, per k block and
+  // column, sum_lo l + 16 sum_hi l: the factor of the weight zero-point.
+  pdl_wait();                                     // x and y belong to the stream order
+  {
     const T* xg = reinterpret_cast<const T*>(a.x);
-    const int per_blk = mrows * 16;
-    const int total_c = n * per_blk;                       // 16-byte chunks
-    constexpr int XU = 4;                                  // loads of four rounds in flight (one L2 round trip, not four)
-    for (int cb = tid; cb < total_c; cb += RW_THREADS * XU) {
-      uint4 vq[XU], vu[XU];
+    const int cpt = a.K >> 3;                     // 16-byte chunks per token
+    const int total_c = mrows * cpt;
+    uint4 vq[RW_XR], vu[RW_XR];
 #pragma unroll
-      for (int u = 0; u < XU; ++u) {
-        const int c = cb + u * RW_THREADS;
-        if (c < total_c) {
-          const int bl = c / per_blk;
-          const int rem = c - bl * per_blk;
-          const int kofs = (kb0 + bl) * 128 + (rem & 15) * 8;
-          if (a.x_gate_up) {
-            const T* gp = xg + static_cast<int64_t>(rem >> 4) * (2 * a.K) + kofs;
-            vq[u] = *reinterpret_cast<const uint4*>(gp);
-            vu[u] = *reinterpret_cast<const uint4*>(gp + a.K);
-          } else {
-            vq[u] = *reinterpret_cast<const uint4*>(xg + static_cast<int64_t>(rem >> 4) * a.K + kofs);
-          }
+    for (int u = 0; u < RW_XR; ++u) {
+      const int c = tid + u * RW_THREADS;
+      if (c < total_c) {
+        const int m = c >= cpt ? 1 : 0;
+        const int kofs = (c - m * cpt) * 8;
+        if (a.x_gate_up) {
+          const T* gp = xg + static_cast<int64_t>(m) * (2 * a.K) + kofs;
+          vq[u] = *reinterpret_cast<const uint4*>(gp);
+          vu[u] = *reinterpret_cast<const uint4*>(gp + a.K);
+        } else {
+          vq[u] = *reinterpret_cast<const uint4*>(xg + static_cast<int64_t>(m) * a.K + kofs);
         }
       }
+    }
+    for (int i = tid; i < kblocks * 8; i += RW_THREADS) reinterpret_cast<float*>(stab_ptr)[i] = 0.f;
+    uint32_t mx0 = 0, mx1 = 0;                    // max |x| as bits per token: finite < inf < NaN
 #pragma unroll
-      for (int u = 0; u < XU; ++u) {
-      const int c = cb + u * RW_THREADS;
-      if (c >= total_c) break;                             // uniform per half-warp: total_c is a multiple of 16
-      const int bl = c / per_blk;
-      const int rem = c - bl * per_blk;
-      const int m = rem >> 4, ch = rem & 15;
-      uint4 v = a.x_gate_up ? silu_mul8<T>(vq[u], vu[u]) : vq[u];
-      const uint32_t half_mask = (lane < 16) ? 0x0000ffffu : 0xffff0000u;   // the 16 chunks of one (block, m)
-      if constexpr (IMMA) {
-        // block fixed point: xi = rint(x * 2^(21 - e)), e = exponent of the (token, block) maximum, |xi| < 2^22,
-        // split into balanced base-256 digits.  Bytes are stored in the order (e0, e4, e1, e5 | e2, e6, e3, e7) in
-        // which the weight nibbles come out of a packed word.
-        const float2 p0 = DT<T>::to_f2(v.x), p1 = DT<T>::to_f2(v.y), p2 = DT<T>::to_f2(v.z), p3 = DT<T>::to_f2(v.w);
-        const float f[8] = {p0.x, p0.y, p1.x, p1.y, p2.x, p2.y, p3.x, p3.y};
-        uint32_t ab = 0;                                   // max |x| as bits: finite < inf < NaN
+    for (int u = 0; u < RW_XR; ++u) {
+      const int c = tid + u * RW_THREADS;
+      if (c < total_c) {
+        if (a.x_gate_up) vq[u] = silu_mul8<T>(vq[u], vu[u]);
+        const float2 p0 = DT<T>::to_f2(vq[u].x), p1 = DT<T>::to_f2(vq[u].y), p2 = DT<T>::to_f2(vq[u].z), p3 = DT<T>::to_f2(vq[u].w);
+        uint32_t ab = max(max(__float_as_uint(p0.x) & 0x7fffffffu, __float_as_uint(p0.y) & 0x7fffffffu),
+                          max(__float_as_uint(p1.x) & 0x7fffffffu, __float_as_uint(p1.y) & 0x7fffffffu));
+        ab = max(ab, max(max(__float_as_uint(p2.x) & 0x7fffffffu, __float_as_uint(p2.y) & 0x7fffffffu),
+                         max(__float_as_uint(p3.x) & 0x7fffffffu, __float_as_uint(p3.y) & 0x7fffffffu)));
+        if (c >= cpt) mx1 = max(mx1, ab); else mx0 = max(mx0, ab);
+      }
+    }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) ab = max(ab, __float_as_uint(f[i]) & 0x7fffffffu);
+    for (int d = 16; d > 0; d >>= 1) {
+      mx0 = max(mx0, __shfl_xor_sync(0xffffffffu, mx0, d));
+      mx1 = max(mx1, __shfl_xor_sync(0xffffffffu, mx1, d));
+    }
+    if (lane == 0) { tokmax[warp * 2] = mx0; tokmax[warp * 2 + 1] = mx1; }
+    __syncthreads();
+    mx0 = 0; mx1 = 0;
 #pragma unroll
-        for (int d = 1; d < 16; d <<= 1) ab = max(ab, __shfl_xor_sync(half_mask, ab, d));
-        const int e = static_cast<int>(ab >> 23);
-        const int fe = min(max(275 - e, 1), 250);          // scale = 2^(fe - 127) = 2^(21 - (e - 127))
-        const float scale = __uint_as_float(static_cast<uint32_t>(fe) << 23);
+    for (int w = 0; w < RW_WARPS; ++w) { mx0 = max(mx0, tokmax[w * 2]); mx1 = max(mx1, tokmax[w * 2 + 1]); }
+    const int e0 = static_cast<int>(mx0 >> 23), e1 = static_cast<int>(mx1 >> 23);
+    const int fe0 = min(max(275 - e0, 5), 250), fe1 = min(max(275 - e1, 5), 250);   // scale = 2^(fe - 127)
+    if (tid < 2) {
+      const int fe = tid ? fe1 : fe0;
+      const bool bad = (tid ? e1 : e0) == 255;    // inf / NaN anywhere poisons the token's result
+      const uint32_t cexp = static_cast<uint32_t>(254 - fe);
+      coef[tid * 4 + 0] = bad ? nan_f() : __uint_as_float(cexp << 23);
+      coef[tid * 4 + 1] = bad ? nan_f() : __uint_as_float((cexp + 8) << 23);
+      coef[tid * 4 + 2] = bad ? nan_f() : __uint_as_float((cexp + 16) << 23);
+    }
+    const uint32_t half_mask = (lane < 16) ? 0x0000ffffu : 0xffff0000u;   // the 16 chunks of one (token, block)
+#pragma unroll
+    for (int u = 0; u < RW_XR; ++u) {
+      const int c = tid + u * RW_THREADS;
+      if (c < total_c) {                          // uniform per half-warp: total_c is a multiple of 16
+        const int m = c >= cpt ? 1 : 0;
+        const int kc = c - m * cpt;               // chunk inside the token
+        const int bl = kc >> 4, ch = kc & 15;
+        const int fe = m ? fe1 : fe0;
+        const float sc_lo = __uint_as_float(static_cast<uint32_t>(fe) << 23);
+        const float sc_hi = __uint_as_float(static_cast<uint32_t>(fe - 4) << 23);
+        const float2 p0 = DT<T>::to_f2(vq[u].x), p1 = DT<T>::to_f2(vq[u].y), p2 = DT<T>::to_f2(vq[u].z), p3 = DT<T>::to_f2(vq[u].w);
+        const float f[8] = {p0.x * sc_lo, p0.y * sc_lo, p1.x * sc_hi, p1.y * sc_hi,
+                            p2.x * sc_lo, p2.y * sc_lo, p3.x * sc_hi, p3.y * sc_hi};
         int l0[8], l1[8], l2[8];
-        int s0 = 0, s1 = 0, s2 = 0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int xi = __float2int_rn(f[i] * scale);
+          const int xi = __float2int_rn(f[i]);
           l0[i] = (xi << 24) >> 24;
           const int x1 = (xi - l0[i]) >> 8;
           l1[i] = (x1 << 24) >> 24;
           l2[i] = (x1 - l1[i]) >> 8;
-          s0 += l0[i]; s1 += l1[i]; s2 += l2[i];
         }
+        int s0 = (l0[0] + l0[1] + l0[4] + l0[5]) + 16 * (l0[2] + l0[3] + l0[6] + l0[7]);
+        int s1 = (l1[0] + l1[1] + l1[4] + l1[5]) + 16 * (l1[2] + l1[3] + l1[6] + l1[7]);
+        int s2 = (l2[0] + l2[1] + l2[4] + l2[5]) + 16 * (l2[2] + l2[3] + l2[6] + l2[7]);
 #pragma unroll
         for (int d = 1; d < 16; d <<= 1) {
           s0 += __shfl_xor_sync(half_mask, s0, d);
@@ -285,288 +303,156 @@ __global__ void __launch_bounds__(RW_THREADS, OCC) k3_rows(const RowsArgs a) {
           return (static_cast<uint32_t>(b0) & 0xffu) | ((static_cast<uint32_t>(b1) & 0xffu) << 8) |
                  ((static_cast<uint32_t>(b2) & 0xffu) << 16) | (static_cast<uint32_t>(b3) << 24);
         };
-        uint8_t* colp = xs_ptr + bl * blk_pitch + (3 * m) * RW_ICOL;
-        const int boff = (ch >> 2) * 32 + (ch & 3) * 8;
-        *reinterpret_cast<uint2*>(colp + boff) = make_uint2(pk(l0[0], l0[4], l0[1], l0[5]), pk(l0[2], l0[6], l0[3], l0[7]));
-        *reinterpret_cast<uint2*>(colp + RW_ICOL + boff) = make_uint2(pk(l1[0], l1[4], l1[1], l1[5]), pk(l1[2], l1[6], l1[3], l1[7]));
-        *reinterpret_cast<uint2*>(colp + 2 * RW_ICOL + boff) = make_uint2(pk(l2[0], l2[4], l2[1], l2[5]), pk(l2[2], l2[6], l2[3], l2[7]));
+        // bytes in the order in which the nibbles come out of a packed word: (e0, e4, e1, e5 | e2, e6, e3, e7)
+        uint8_t* colp = xs_ptr + bl * blk_pitch + (3 * m) * RW_ICOL + (ch >> 2) * 32 + (ch & 3) * 8;
+        *reinterpret_cast<uint2*>(colp) = make_uint2(pk(l0[0], l0[4], l0[1], l0[5]), pk(l0[2], l0[6], l0[3], l0[7]));
+        *reinterpret_cast<uint2*>(colp + RW_ICOL) = make_uint2(pk(l1[0], l1[4], l1[1], l1[5]), pk(l1[2], l1[6], l1[3], l1[7]));
+        *reinterpret_cast<uint2*>(colp + 2 * RW_ICOL) = make_uint2(pk(l2[0], l2[4], l2[1], l2[5]), pk(l2[2], l2[6], l2[3], l2[7]));
         if (ch == 0) {
-          // column coefficient 256^l / scale; inf / NaN anywhere in the block poisons the token's result
-          const uint32_t cexp = static_cast<uint32_t>(254 - fe);
-          const bool bad = e == 255;
-          const float c0 = bad ? nan_f() : __uint_as_float(cexp << 23);
-          const float c1 = bad ? nan_f() : __uint_as_float((cexp + 8) << 23);
-          const float c2 = bad ? nan_f() : __uint_as_float((cexp + 16) << 23);
-          *reinterpret_cast<float2*>(colp + 128) = make_float2(static_cast<float>(s0), c0);
-          *reinterpret_cast<float2*>(colp + RW_ICOL + 128) = make_float2(static_cast<float>(s1), c1);
-          *reinterpret_cast<float2*>(colp + 2 * RW_ICOL + 128) = make_float2(static_cast<float>(s2), c2);
+          float* sp = reinterpret_cast<float*>(stab_ptr) + bl * 8 + 3 * m;
+          sp[0] = static_cast<float>(s0); sp[1] = static_cast<float>(s1); sp[2] = static_cast<float>(s2);
         }
-      } else {
-        float2 f0 = DT<T>::to_f2(v.x), f1 = DT<T>::to_f2(v.y), f2 = DT<T>::to_f2(v.z), f3 = DT<T>::to_f2(v.w);
-        float inv = 1.0f;
-        if constexpr (kConvX) {
-          // bf16 -> fp16 without loss: scale the (token, block) slice by the power of two that puts its largest
-          // magnitude in [2^14, 2^15); the inverse power goes into the fp32 group step
-          float am = fmaxf(fmaxf(fmaxf(fabsf(f0.x), fabsf(f0.y)), fmaxf(fabsf(f1.x), fabsf(f1.y))),
-                           fmaxf(fmaxf(fabsf(f2.x), fabsf(f2.y)), fmaxf(fabsf(f3.x), fabsf(f3.y))));
-#pragma unroll
-          for (int d = 1; d < 16; d <<= 1) am = fmaxf(am, __shfl_xor_sync(half_mask, am, d));
-          const int e = static_cast<int>((__float_as_uint(am) >> 23) & 0xffu);
-          int fe = 268 - e;
-          fe = (e == 0 || e == 255) ? 127 : min(max(fe, 1), 253);
-          const float f = __uint_as_float(static_cast<uint32_t>(fe) << 23);
-          inv = __uint_as_float(static_cast<uint32_t>(254 - fe) << 23);
-          f0.x *= f; f0.y *= f; f1.x *= f; f1.y *= f; f2.x *= f; f2.y *= f; f3.x *= f; f3.y *= f;
-          v.x = DT<__half>::pack2(f0.x, f0.y); v.y = DT<__half>::pack2(f1.x, f1.y);
-          v.z = DT<__half>::pack2(f2.x, f2.y); v.w = DT<__half>::pack2(f3.x, f3.y);
-          if (e != 0 && e != 255) {      // sums of what the tensor core will see (exact conversions)
-            f0 = DT<__half>::to_f2(v.x); f1 = DT<__half>::to_f2(v.y); f2 = DT<__half>::to_f2(v.z); f3 = DT<__half>::to_f2(v.w);
-          }
-        }
-        // sums of the "plain" pairs (value 1024 + q) and of the "x16" pairs (value 1024 + 16 q)
-        float s_a = (f0.x + f0.y) + (f2.x + f2.y), s_b = (f1.x + f1.y) + (f3.x + f3.y);
-#pragma unroll
-        for (int d = 1; d < 16; d <<= 1) {
-          s_a += __shfl_xor_sync(half_mask, s_a, d);
-          s_b += __shfl_xor_sync(half_mask, s_b, d);
-        }
-        if (ch == 0)
-          *reinterpret_cast<float4*>(xs_ptr + bl * blk_pitch + m * RW_XPITCH + 256 + ((m >> 1) & 3) * 16) =
-              make_float4(s_a, s_b, inv, 0.f);
-        { const uint32_t yy = v.y; v.y = v.z; v.z = yy; }   // one LDS.128 yields (k0,k1 | k4,k5 | k2,k3 | k6,k7)
-        *reinterpret_cast<uint4*>(xs_ptr + bl * blk_pitch + m * RW_XPITCH + (ch >> 2) * 16 + (ch & 3) * 64) = v;
-      }
       }
     }
-  };
-
-  // per-lane x addresses: mma column n = g is token g (integer form: (token, limb) = divmod(g, 3)); columns past the
-  // last valid one re-read it (their results are never stored)
-  uint32_t xrow, srow, srow1;
-  if constexpr (IMMA) {
-    const int ncols = 3 * mrows;
-    xrow = xs_u32 + min(g, ncols - 1) * RW_ICOL + t * 32;
-    srow = xs_u32 + min(2 * t, ncols - 1) * RW_ICOL + 128;
-    srow1 = xs_u32 + min(2 * t + 1, ncols - 1) * RW_ICOL + 128;
-  } else {
-    xrow = xs_u32 + min(g, mrows - 1) * RW_XPITCH + t * 16;
-    const int m0 = min(2 * t, mrows - 1), m1 = min(2 * t + 1, mrows - 1);
-    srow = xs_u32 + m0 * RW_XPITCH + 256 + ((m0 >> 1) & 3) * 16;
-    srow1 = xs_u32 + m1 * RW_XPITCH + 256 + ((m1 >> 1) & 3) * 16;
+    __syncthreads();
   }
 
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  const uint32_t magic = reg_const(0x64006400u);
-  constexpr float kMagicF = 1024.0f;
-
-  auto compute_block = [&](const BlockRegs& b, uint32_t xoff) {
-    const uint32_t w0[4] = {b.c0.x, b.c0.y, b.c0.z, b.c0.w}, w1[4] = {b.c1.x, b.c1.y, b.c1.z, b.c1.w};
-    const float2 sz0 = DT<T>::to_f2(b.m0), sz1 = DT<T>::to_f2(b.m1);     // (scale, zero) of rows g, g + 8
-    if constexpr (IMMA) {
-      int di[4] = {0, 0, 0, 0};
-      const uint4 xb0 = lds128(xrow + xoff), xb1 = lds128(xrow + xoff + 16);
+  // ===================== the stream =====================
+  const int ncols = 3 * mrows;
+  const float nz_fix = a.qmin;
+  // ring bookkeeping: D - 2 blocks are outstanding between steps, the two slots behind the read position are free;
+  // a step reads NB slots and refills NB slots that were read at least one step ago
+  const uint8_t* wring_g = smem_raw + (wring - smem_u32(smem_raw));       // generic address of this lane's ring
+  uint32_t coff = 0, roff = (D - 2) * RW_SLOT;    // byte offsets of the read position / the refill position
+  auto next_off = [&](uint32_t o) { o += RW_SLOT; return o == D * RW_SLOT ? 0u : o; };
+  auto step = [&](auto nb_tag, uint32_t xo, uint32_t so, uint32_t xstep, uint32_t sstep, float (&acc)[2][4]) {
+    constexpr int NB = decltype(nb_tag)::value;
+    cp_async_wait<D - 2 - NB>();                  // this lane's share of the NB oldest blocks has landed (it reads only that)
+    uint4 c0[NB], c1[NB], xb0[NB], xb1[NB];
+    uint32_t m0[NB], m1[NB];
+    float2 sv[NB];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+    for (int b = 0; b < NB; ++b) {
+      const uint8_t* sp = wring_g + coff;
+      c0[b] = *reinterpret_cast<const uint4*>(sp);
+      c1[b] = *reinterpret_cast<const uint4*>(sp + 512);
+      m0[b] = *reinterpret_cast<const uint32_t*>(sp + 1024 - lane * 12);
+      m1[b] = *reinterpret_cast<const uint32_t*>(sp + 1152 - lane * 12);
+      coff = next_off(coff);
+      xb0[b] = *reinterpret_cast<const uint4*>(smem_raw + xo + b * xstep);
+      xb1[b] = *reinterpret_cast<const uint4*>(smem_raw + xo + b * xstep + 16);
+      sv[b] = *reinterpret_cast<const float2*>(smem_raw + so + b * sstep);      // zero-point sums of columns 2t, 2t + 1
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) { issue(wring + roff); roff = next_off(roff); }
+    int di[NB][4];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) { di[b][0] = di[b][1] = di[b][2] = di[b][3] = 0; }
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        const uint32_t w0 = w == 0 ? c0[b].x : w == 1 ? c0[b].y : w == 2 ? c0[b].z : c0[b].w;
+        const uint32_t w1 = w == 0 ? c1[b].x : w == 1 ? c1[b].y : w == 2 ? c1[b].z : c1[b].w;
+        const uint4& xq = (w >> 1) ? xb1[b] : xb0[b];
         uint32_t af[4];
-        af[0] = w0[j] & 0x0f0f0f0fu;                       // (e0, e4, e1, e5) of row g
-        af[1] = w1[j] & 0x0f0f0f0fu;                       //                  of row g + 8
-        af[2] = shr4_fma(w0[j]) & 0x0f0f0f0fu;             // (e2, e6, e3, e7)
-        af[3] = shr4_fma(w1[j]) & 0x0f0f0f0fu;
-        const uint4& q4 = (j >> 1) ? xb1 : xb0;
-        imma_16832(di, af, (j & 1) ? q4.z : q4.x, (j & 1) ? q4.w : q4.y);
+        af[0] = w0 & 0x0f0f0f0fu; af[1] = w1 & 0x0f0f0f0fu; af[2] = w0 & 0xf0f0f0f0u; af[3] = w1 & 0xf0f0f0f0u;
+        imma_16832(di[b], af, (w & 1) ? xq.z : xq.x, (w & 1) ? xq.w : xq.y);
       }
-      const float nz0 = has_zp ? -sz0.y : -zp_fix, nz1 = has_zp ? -sz1.y : -zp_fix;
-      const float2 u0 = lds64f(srow + xoff), u1 = lds64f(srow1 + xoff);   // (sum of limbs, coefficient)
-      const float r0 = fmaf(nz0, u0.x, static_cast<float>(di[0]));
-      const float r1 = fmaf(nz0, u1.x, static_cast<float>(di[1]));
-      const float r2 = fmaf(nz1, u0.x, static_cast<float>(di[2]));
-      const float r3 = fmaf(nz1, u1.x, static_cast<float>(di[3]));
-      acc[0] = fmaf(sz0.x * u0.y, r0, acc[0]);
-      acc[1] = fmaf(sz0.x * u1.y, r1, acc[1]);
-      acc[2] = fmaf(sz1.x * u0.y, r2, acc[2]);
-      acc[3] = fmaf(sz1.x * u1.y, r3, acc[3]);
-    } else {
-      float ag[4], agh[4];
+    }
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint4 xb = lds128(xrow + xoff + i * 64);
-        const uint32_t s0 = shr8_fma(w0[i]), s1 = shr8_fma(w1[i]);
-        uint32_t al[4], ah[4];
-        al[0] = lop_and_or<0x000f000fu>(w0[i], magic);
-        al[1] = lop_and_or<0x000f000fu>(w1[i], magic);
-        al[2] = lop_and_or<0x000f000fu>(s0, magic);
-        al[3] = lop_and_or<0x000f000fu>(s1, magic);
-        ah[0] = lop_and_or<0x00f000f0u>(w0[i], magic);
-        ah[1] = lop_and_or<0x00f000f0u>(w1[i], magic);
-        ah[2] = lop_and_or<0x00f000f0u>(s0, magic);
-        ah[3] = lop_and_or<0x00f000f0u>(s1, magic);
-        const uint32_t bl2[2] = {xb.x, xb.y}, bh2[2] = {xb.z, xb.w};
-        if (i == 0) { mma_16816_zero(ag, al, bl2, false); mma_16816_zero(agh, ah, bh2, false); }
-        else { mma_16816(ag, al, bl2, false); mma_16816(agh, ah, bh2, false); }
-      }
-      const float z0 = has_zp ? sz0.y : zp_fix, z1 = has_zp ? sz1.y : zp_fix;
-      const float off0 = -(kMagicF + z0), off1 = -(kMagicF + z1);
-      const float offh0 = -(kMagicF * 0.0625f + z0), offh1 = -(kMagicF * 0.0625f + z1);
-      // (S_plain, S_x16, 2^-e, -) of tokens m = 2t and 2t + 1
-      const uint4 u0 = lds128(srow + xoff), u1 = lds128(srow1 + xoff);
-      const float sa0 = __uint_as_float(u0.x), sb0 = __uint_as_float(u0.y);
-      const float sa1 = __uint_as_float(u1.x), sb1 = __uint_as_float(u1.y);
-      float r0 = fmaf(agh[0], 0.0625f, ag[0]), r1 = fmaf(agh[1], 0.0625f, ag[1]);
-      float r2 = fmaf(agh[2], 0.0625f, ag[2]), r3 = fmaf(agh[3], 0.0625f, ag[3]);
-      r0 = fmaf(offh0, sb0, r0); r1 = fmaf(offh0, sb1, r1);
-      r2 = fmaf(offh1, sb0, r2); r3 = fmaf(offh1, sb1, r3);
-      float w00 = sz0.x, w01 = sz0.x, w10 = sz1.x, w11 = sz1.x;
-      if constexpr (kConvX) {
-        const float i0 = __uint_as_float(u0.z), i1 = __uint_as_float(u1.z);
-        w00 *= i0; w01 *= i1; w10 *= i0; w11 *= i1;
-      }
-      acc[0] = fmaf(w00, fmaf(off0, sa0, r0), acc[0]);
-      acc[1] = fmaf(w01, fmaf(off0, sa1, r1), acc[1]);
-      acc[2] = fmaf(w10, fmaf(off1, sa0, r2), acc[2]);
-      acc[3] = fmaf(w11, fmaf(off1, sa1, r3), acc[3]);
+    for (int b = 0; b < NB; ++b) {
+      const float2 sz0 = DT<T>::to_f2(m0[b]), sz1 = DT<T>::to_f2(m1[b]);     // (scale, zero) of rows g, g + 8
+      const float nz0 = HAS_ZP ? -sz0.y : nz_fix, nz1 = HAS_ZP ? -sz1.y : nz_fix;
+      acc[b][0] = fmaf(sz0.x, fmaf(nz0, sv[b].x, static_cast<float>(di[b][0])), acc[b][0]);
+      acc[b][1] = fmaf(sz0.x, fmaf(nz0, sv[b].y, static_cast<float>(di[b][1])), acc[b][1]);
+      acc[b][2] = fmaf(sz1.x, fmaf(nz1, sv[b].x, static_cast<float>(di[b][2])), acc[b][2]);
+      acc[b][3] = fmaf(sz1.x, fmaf(nz1, sv[b].y, static_cast<float>(di[b][3])), acc[b][3]);
     }
   };
-
-  // end of pass p: the warps' fragments meet in shared memory, fixed summation order
-  int pass_parity = 0;
-  auto finish_pass = [&](int p) {
-    float* rp = red + pass_parity * RED_FLOATS;
-    pass_parity ^= 1;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      rp[(warp * 4 + r) * 32 + lane] = acc[r];
-      acc[r] = 0.f;
-    }
-    __syncthreads();
-    const int pr = min(RW_PR, nr - p * RW_PR);
-    const bool two = pr > 16;
-    T* y = reinterpret_cast<T*>(a.y);
-    const T* bias = reinterpret_cast<const T*>(a.bias);
-    const int nw = two ? 4 : 8;                   // warps that share a slab
-    for (int o = tid; o < RW_PR * mrows; o += RW_THREADS) {
-      const int rr32 = o & 31, m = o >> 5;
-      if (rr32 < pr) {
-        const int sl = rr32 >> 4, rr = rr32 & 15;
-        float sum = 0.f;
-        for (int j = 0; j < nw; ++j) {
-          const int w = two ? sl + 2 * j : j;
-          if constexpr (IMMA) {
-#pragma unroll
-            for (int l = 0; l < 3; ++l) {
-              const int c = 3 * m + l;
-              sum += rp[(w * 4 + ((c & 1) | ((rr >> 3) << 1))) * 32 + (rr & 7) * 4 + ((c & 7) >> 1)];
-            }
-          } else {
-            sum += rp[(w * 4 + ((m & 1) | ((rr >> 3) << 1))) * 32 + (rr & 7) * 4 + ((m & 7) >> 1)];
-          }
-        }
-        const int n = R0 + p * RW_PR + rr32;
-        if (bias) sum += DT<T>::to_f(bias[n]);
-        y[static_cast<int64_t>(m) * a.N + n] = DT<T>::from_f(sum);
-      }
-    }
-  };
-
-  pdl_wait();                                     // x and y belong to the stream order
-
-  const int chunk = a.chunk;
-  const bool x_once = chunk >= kblocks;
-  if (x_once) {
-    stage_x(0, kblocks);
-    __syncthreads();
-  }
-  // the compute side walks the same sequence as the load iterator, D - 1 blocks behind
-  uint32_t cslot = 0;
+  int parity = 0;
 #pragma unroll 1
   for (int p = 0; p < np; ++p) {
-    const bool two = (p < np - 1) || last_two;
-    int ckb = two ? (warp >> 1) : warp;
-    const int cstride = two ? 4 : 8;
-    const int cbpp = two ? bpp2 : bpp1;
-    int ckc = 0;                                  // first block of the staged chunk
-    if (!x_once) {
-      __syncthreads();                            // everyone is done with the previous slab
-      stage_x(0, min(chunk, kblocks));
-      __syncthreads();
+    int sh, slab0;
+    pass_geo(p, sh, slab0);
+    const int S = 1 << sh, KW = RW_WARPS >> sh, kq = warp >> sh;
+    const int bpp = kblocks >> (4 - sh);          // blocks per warp in this pass
+    // mma column g is (token, limb) = divmod(g, 3); columns past the last one re-read it (never stored)
+    uint32_t xo = static_cast<uint32_t>(xs_ptr - smem_raw) + min(g, ncols - 1) * RW_ICOL + t * 32 + kq * blk_pitch;
+    uint32_t so = static_cast<uint32_t>(stab_ptr - smem_raw) + t * 8 + kq * 32;
+    const uint32_t xstep = KW * blk_pitch, sstep = KW * 32;
+    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    int j = 0;
+#pragma unroll 1
+    for (; a.pair && j + 2 <= bpp; j += 2) {      // two blocks per step: independent chains the scheduler interleaves
+      step(std::integral_constant<int, 2>{}, xo, so, xstep, sstep, acc);
+      xo += 2 * xstep; so += 2 * sstep;
     }
 #pragma unroll 1
-    for (int j = 0; j < cbpp; ++j) {
-      if (!x_once) {
-        // the chunk that holds the j-th blocks of every warp: a chunk is a multiple of 8 blocks, and the warps' k
-        // groups of one j lie inside one aligned run of 4 or 8
-        const int lead = (j * cstride / chunk) * chunk;
-        if (lead != ckc) {
-          ckc = lead;
-          __syncthreads();
-          stage_x(ckc, min(chunk, kblocks - ckc));
-          __syncthreads();
-        }
-      }
-      cp_async_wait<D - 2>();                     // this lane's share of the oldest block has landed (it reads only that)
-      BlockRegs cur;
-      const uint32_t sb = wring + cslot * RW_SLOT + lane * 16;
-      cur.c0 = lds128(sb);
-      cur.c1 = lds128(sb + 512);
-      cur.m0 = lds32(wring + cslot * RW_SLOT + 1024 + lane * 4);
-      cur.m1 = lds32(wring + cslot * RW_SLOT + 1152 + lane * 4);
-      if (++cslot == D) cslot = 0;
-      issue_next();                               // into the slot that was read one step ago
-      if (ckb < kblocks) compute_block(cur, static_cast<uint32_t>((ckb - ckc) * blk_pitch));
-      ckb += cstride;
+    for (; j < bpp; ++j) {
+      step(std::integral_constant<int, 1>{}, xo, so, xstep, sstep, acc);
+      xo += xstep; so += sstep;
     }
-    finish_pass(p);
+    // ---- end of the pass: the warps' fragments meet in shared memory, fixed summation order
+    float* rp = red + parity * (RW_WARPS * 4 * 32);
+    parity ^= 1;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) rp[(warp * 4 + r) * 32 + lane] = acc[0][r] + acc[1][r];
+    __syncthreads();
+    const int PRW = 16 * S;
+    if (tid < PRW * mrows) {
+      const int rr = tid & (PRW - 1), m = tid >> (4 + sh);
+      const int rel = slab0 * 16 + rr;
+      if (rel < nr) {
+        const int sl = rr >> 4, r16 = rr & 15;
+        float sum = 0.f;
+        for (int kw = 0; kw < KW; ++kw) {
+          const float* wp = rp + ((sl + S * kw) * 4 + ((r16 >> 3) << 1)) * 32 + (r16 & 7) * 4;
+#pragma unroll
+          for (int l = 0; l < 3; ++l) {
+            const int c = 3 * m + l;
+            sum = fmaf(coef[m * 4 + l], wp[(c & 1) * 32 + ((c & 7) >> 1)], sum);
+          }
+        }
+        const int n = R0 + rel;
+        if (a.bias) sum += DT<T>::to_f(reinterpret_cast<const T*>(a.bias)[n]);
+        reinterpret_cast<T*>(a.y)[static_cast<int64_t>(m) * a.N + n] = DT<T>::from_f(sum);
+      }
+    }
   }
 }
 
-struct RowsPlan { int occ, depth, chunk, smem; };
+struct RowsPlan { int depth, smem; };
 
-// shared-memory plan: two CTAs per SM (one on request); all of x next to the warps' rings when that leaves a ring of
-// >= 6 blocks per warp, else x in chunks
-bool plan_rows(int M, int K, int mode, RowsPlan& p) {
+bool plan_rows(int M, int K, RowsPlan& p) {
   const int kblocks = K / 128;
-  const int blk_pitch = M * (mode == 2 ? 3 * RW_ICOL : RW_XPITCH);
-  const int fixed = 2 * RW_WARPS * 4 * 32 * 4 + 256;
-  const int x_all = kblocks * blk_pitch;
-  static const int env_occ = []() { const char* e = getenv("Q100_ROWS_OCC"); return e ? atoi(e) : 0; }();
+  const int fixed = RW_RED_BYTES + RW_MISC_BYTES + kblocks * 32 + kblocks * 3 * M * RW_ICOL + 128;
   static const int env_depth = []() { const char* e = getenv("Q100_ROWS_DEPTH"); return e ? atoi(e) : 0; }();
-  const int occ = env_occ == 1 ? 1 : 2;
-  const int budget = occ == 1 ? 232448 : (233472 - 2 * 1024) / 2;
-  const int depths[3] = {8, 6, 4};
-  for (int di = 0; di < 3; ++di) {
+  const int depths[4] = {8, 6, 5, 4};              // >= 4: a step of two blocks waits for all but D - 4 groups
+  for (int di = 0; di < 4; ++di) {
     const int depth = depths[di];
-    if (env_depth > 0 && depth != env_depth) continue;
-    const int ring = RW_WARPS * depth * RW_SLOT;
-    if (fixed + ring + x_all <= budget) {
-      p = RowsPlan{occ, depth, ((kblocks + 7) / 8) * 8, fixed + ring + x_all};
-      return true;
-    }
-    if (depth == 6 || env_depth > 0) {            // chunked x with a ring of 6 rather than everything with a ring of 4
-      const int chunk = ((budget - fixed - ring) / blk_pitch) / 8 * 8;
-      if (chunk >= 16) {
-        p = RowsPlan{occ, depth, chunk, fixed + ring + chunk * blk_pitch};
-        return true;
-      }
-    }
+    if (env_depth > 0 && depth > env_depth) continue;
+    const int smem = fixed + RW_WARPS * depth * RW_SLOT;
+    if (smem <= 232448 - 1024) { p = RowsPlan{depth, smem}; return true; }
   }
   return false;
 }
 
-template <typename T, int MODE, int D, int OCC>
-int launch_rows_t(RowsArgs a, const RowsPlan& p, int pdl, cudaStream_t st) {
-  auto kern = k3_rows<T, MODE, D, OCC>;
+template <typename T, int D>
+int launch_rows_t(const RowsArgs& a, const RowsPlan& p, int pdl, cudaStream_t st) {
+  auto kern = a.has_zp ? k3_rows<T, D, true> : k3_rows<T, D, false>;
   static std::mutex mu;
-  static int max_set[kMaxDevices] = {};
+  static int max_set[2][kMaxDevices] = {};
   {
     std::lock_guard<std::mutex> lk(mu);
     const int dev = current_device();
-    if (p.smem > max_set[dev]) {
+    if (p.smem > max_set[a.has_zp ? 1 : 0][dev]) {
       Q100_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, p.smem));
-      max_set[dev] = p.smem;
+      max_set[a.has_zp ? 1 : 0][dev] = p.smem;
     }
   }
-  a.chunk = p.chunk;
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(sm_count() * p.occ);
+  cfg.gridDim = dim3(sm_count());
   cfg.blockDim = dim3(RW_THREADS);
   cfg.dynamicSmemBytes = p.smem;
   cfg.stream = st;
@@ -578,32 +464,34 @@ int launch_rows_t(RowsArgs a, const RowsPlan& p, int pdl, cudaStream_t st) {
   return check_cuda(cudaLaunchKernelEx(&cfg, kern, a), "k3_rows launch");
 }
 
-template <typename T, int MODE>
+template <typename T>
 int launch_rows(const RowsArgs& a, const RowsPlan& p, int pdl, cudaStream_t st) {
-  if (p.occ == 1) return p.depth == 8 ? launch_rows_t<T, MODE, 8, 1>(a, p, pdl, st)
-                       : p.depth == 6 ? launch_rows_t<T, MODE, 6, 1>(a, p, pdl, st) : launch_rows_t<T, MODE, 4, 1>(a, p, pdl, st);
-  return p.depth == 8 ? launch_rows_t<T, MODE, 8, 2>(a, p, pdl, st)
-       : p.depth == 6 ? launch_rows_t<T, MODE, 6, 2>(a, p, pdl, st) : launch_rows_t<T, MODE, 4, 2>(a, p, pdl, st);
+  switch (p.depth) {
+    case 8: return launch_rows_t<T, 8>(a, p, pdl, st);
+    case 6: return launch_rows_t<T, 6>(a, p, pdl, st);
+    case 5: return launch_rows_t<T, 5>(a, p, pdl, st);
+    default: return launch_rows_t<T, 4>(a, p, pdl, st);
+  }
 }
 
 }  // namespace
 
-// mode: 1 = fp16 magic form (M <= 8), 2 = integer form (M <= 2)
+// mode: 2 = integer form (M <= 2); the fp16 form (mode 1, M <= 8) stays on K3a
 bool gemm_rows_supported(int64_t M, int64_t N, int64_t K, int group, int n_bits, int mode) {
   static const bool off = []() { const char* e = getenv("Q100_GEMM_ROWS"); return e && atoi(e) == 0; }();
   if (off) return false;
-  if (n_bits != 4 || group != 128 || K % 128 != 0 || N % 8 != 0 || M < 1) return false;
-  if (mode == 2 ? M > 2 : M > 8) return false;
-  if (mode != 1 && mode != 2) return false;
+  if (mode != 2 || n_bits != 4 || group != 128 || K % 2048 != 0 || N % 8 != 0 || M < 1 || M > 2) return false;
+  if (M * K > RW_XR * RW_THREADS * 8) return false;     // x is held in registers between the two staging phases
   if (N > (1 << 24) || K > (1 << 20)) return false;
   RowsPlan p;
-  return plan_rows(static_cast<int>(M), static_cast<int>(K), mode, p);
+  return plan_rows(static_cast<int>(M), static_cast<int>(K), p);
 }
 
 int gemm_rows(const void* x, const void* packed, const void* meta, const void* bias, void* y, int64_t M, int64_t N,
               int64_t K, int disable_zp, int dtype, int mode, int pdl, int x_gate_up, cudaStream_t st) {
+  (void)mode;
   RowsPlan p;
-  Q100_REQUIRE(plan_rows(static_cast<int>(M), static_cast<int>(K), mode, p), Q100_EUNSUPPORTED,
+  Q100_REQUIRE(plan_rows(static_cast<int>(M), static_cast<int>(K), p), Q100_EUNSUPPORTED,
                "k3_rows: no shared-memory plan for M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
   RowsArgs a{};
   a.x = x; a.packed = packed; a.meta = meta; a.bias = bias; a.y = y;
@@ -612,8 +500,10 @@ int gemm_rows(const void* x, const void* packed, const void* meta, const void* b
   a.has_zp = disable_zp ? 0 : 1;
   a.qmin = disable_zp ? -8.0f : 0.0f;
   a.x_gate_up = x_gate_up;
-  if (dtype == Q100_F16) return mode == 2 ? launch_rows<__half, 2>(a, p, pdl, st) : launch_rows<__half, 1>(a, p, pdl, st);
-  return mode == 2 ? launch_rows<__nv_bfloat16, 2>(a, p, pdl, st) : launch_rows<__nv_bfloat16, 1>(a, p, pdl, st);
+  static const int env_pair = []() { const char* e = getenv("Q100_ROWS_PAIR"); return e ? atoi(e) : 1; }();
+  a.pair = env_pair;
+  if (dtype == Q100_F16) return launch_rows<__half>(a, p, pdl, st);
+  return launch_rows<__nv_bfloat16>(a, p, pdl, st);
 }
 
 }  // namespace q100
