@@ -37,8 +37,6 @@ namespace q100 {
 
 namespace {
 
-constexpr int RW_WARPS = 16;
-constexpr int RW_THREADS = RW_WARPS * 32;
 constexpr int RW_TROW = 32;                       // bytes per row of a 64-k tile at W4
 constexpr int RW_TILE_BYTES = 128 * RW_TROW;      // one [128 x 64] tile in HBM
 constexpr int RW_XPITCH = 320;                    // fp16 form: bytes per (token, 128-k block) of x: 256 + 64 (sums)
@@ -56,7 +54,6 @@ struct RowsArgs {
   int has_zp;
   float qmin;
   int x_gate_up;
-  int pair;               // two blocks per step (development switch)
 };
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
@@ -80,8 +77,8 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory");
 }
-__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"(dst), "l"(src) : "memory");
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
@@ -129,188 +126,174 @@ __device__ __forceinline__ uint4 silu_mul8(const uint4& g, const uint4& u) {
 }
 
 // ---------------------------------------------------------------- the kernel
-// Shared memory: red[2][16 warps][4][32] fp32 | misc (token maxima, coefficients) | the warps' rings [16][D][RW_SLOT] |
-// stab[kblocks][8] fp32 (zero-point sums per limb column) | x limbs [kblocks][3 M][RW_ICOL]
-constexpr int RW_RED_BYTES = 2 * RW_WARPS * 4 * 32 * 4;
+// Shared memory: red[2][32 warps][4][32] fp32 | (1 KB spare) | the warps' rings [32][D][RW_SLOT] |
+// stab[kblocks][8][2] fp32 (zero-point sum, weight per limb column) | x limbs [kblocks][4 M][RW_ICOL]
 constexpr int RW_MISC_BYTES = 1024;
-constexpr int RW_XR = 8;                          // 16-byte chunks of x a thread holds between the two staging phases
+constexpr int RW_XU = 2;                          // loads of x in flight per thread while it is staged
 
-template <typename T, int D, bool HAS_ZP>
-__global__ void __launch_bounds__(RW_THREADS, 1) k3_rows(const RowsArgs a) {
+// mma row i of a slab is slab row 2 i (i < 8) or 2 (i - 8) + 1: the two rows a lane feeds (mma rows g, g + 8) are the
+// ADJACENT rows 2 g, 2 g + 1 -- one code pointer (the rows are 32 bytes apart inside a tile) and one 8-byte side-band read
+// LOGW: log2 of the warps per CTA -- 5: one CTA per SM; 4: two (the next launch's CTAs are co-resident with this one's tail)
+template <typename T, int D, bool HAS_ZP, int LOGW>
+__global__ void __launch_bounds__(32 << LOGW, LOGW == 5 ? 1 : 2) k3_rows(const RowsArgs a) {
+  constexpr int RW_WARPS = 1 << LOGW, RW_THREADS = 32 << LOGW;
+  constexpr int RW_RED_BYTES = 2 * RW_WARPS * 4 * 32 * 4;
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   float* red = reinterpret_cast<float*>(smem_raw);
-  uint32_t* tokmax = reinterpret_cast<uint32_t*>(smem_raw + RW_RED_BYTES);               // [16 warps][2]
-  float* coef = reinterpret_cast<float*>(smem_raw + RW_RED_BYTES + 256);                 // [2 tokens][4]
   const uint32_t wring = smem_u32(smem_raw) + RW_RED_BYTES + RW_MISC_BYTES + warp * (D * RW_SLOT) + lane * 16;
   uint8_t* stab_ptr = smem_raw + RW_RED_BYTES + RW_MISC_BYTES + RW_WARPS * D * RW_SLOT;
   const int kblocks = a.kblocks;
-  uint8_t* xs_ptr = stab_ptr + kblocks * 32;
+  uint8_t* xs_ptr = stab_ptr + kblocks * 64;
   const int mrows = a.M;
-  const int blk_pitch = 3 * mrows * RW_ICOL;      // bytes of x limbs per k block
+  const int blk_pitch = 4 * mrows * RW_ICOL;      // bytes of x limbs per k block
 
   const int G = gridDim.x, cta = blockIdx.x;
   const int Q = a.N >> 2;
-  const int q0 = static_cast<int>(static_cast<int64_t>(cta) * Q / G);
-  const int q1 = static_cast<int>(static_cast<int64_t>(cta + 1) * Q / G);
-  const int R0 = 4 * q0, nr = 4 * (q1 - q0);
+  const int R0 = 4 * static_cast<int>(static_cast<uint32_t>(cta) * static_cast<uint32_t>(Q) / static_cast<uint32_t>(G));
+  const int nr = 4 * static_cast<int>(static_cast<uint32_t>(cta + 1) * static_cast<uint32_t>(Q) / static_cast<uint32_t>(G)) - R0;
   pdl_launch_dependents();
   if (nr == 0) return;
 
-  // ---- geometry of this CTA: its ns = ceil(nr / 16) slabs of 16 rows are walked in passes of S = 4 slabs, then what
-  // is left as 2 + 1, 2 or 1; in a pass of S slabs the 16 warps split the work by (slab, k group mod KW), KW = 16 / S
+  // ---- geometry of this CTA: its ns = ceil(nr / 16) slabs of 16 rows are walked in passes of S = W / 4 slabs and one
+  // last pass of W / 4, W / 8 or W / 16; in a pass of S slabs the W warps split the work by (slab, k group mod KW),
+  // KW = W / S
+  constexpr int SHM = LOGW - 2;                   // log2 of the slabs of a full pass
   const int ns = (nr + 15) >> 4;
-  const int n4 = ns >> 2, rem = ns & 3;
-  const int np = n4 + (rem == 3 ? 2 : rem ? 1 : 0);
-  auto pass_geo = [&](int p, int& sh_, int& slab0_) {   // log2 S and first slab of pass p
-    if (p < n4) { sh_ = 2; slab0_ = 4 * p; }
-    else if (rem == 3) { sh_ = p == n4 ? 1 : 0; slab0_ = 4 * n4 + (p == n4 ? 0 : 2); }
-    else { sh_ = rem == 2 ? 1 : 0; slab0_ = 4 * n4; }
-  };
+  const int n8 = ns >> SHM, rem = ns & ((1 << SHM) - 1);
+  const int np = n8 + (rem ? 1 : 0);
+  const int sh_last = rem > (1 << (SHM - 1)) ? SHM : rem > (1 << (SHM - 2)) ? SHM - 1 : SHM - 2;
   const uint8_t* packed = reinterpret_cast<const uint8_t*>(a.packed);
   const uint8_t* meta = reinterpret_cast<const uint8_t*>(a.meta);
   const int64_t ktile_row = static_cast<int64_t>(kblocks) * 2 * RW_TILE_BYTES;   // bytes of one 128-row tile row
 
-  // ---- the load iterator: rows past the CTA's range are clamped to its last row (same sectors, results unused)
-  const uint8_t* pc0; const uint8_t* pc1; const uint8_t* pm0; const uint8_t* pm1;
-  int64_t cstep = 0, mstep = 0;                   // to this warp's next k group
+  // ---- the load iterator: row pairs past the CTA's range are clamped to its last pair (same sectors, results unused)
+  const uint8_t* pc0 = packed;                    // this lane's 16 bytes of row 2g of the slab, current k group
+  const uint8_t* pm0 = meta;                      // (scale, zero) of rows 2g, 2g + 1
+  int cstep = 0;                                  // bytes to this warp's next k group (< 2^31)
+  int64_t mstep = 0;
   int lj = 0, lp = 0, lbpp = 0;
   auto setup_pass = [&](int p) {
-    int sh_, slab0_;
-    pass_geo(p, sh_, slab0_);
+    const int sh_ = p < n8 ? SHM : sh_last;
     const int kw = RW_WARPS >> sh_, kq = warp >> sh_;
-    const int rel = (slab0_ + (warp & ((1 << sh_) - 1))) * 16 + g;
-    const int r0 = R0 + min(rel, nr - 1), r1 = R0 + min(rel + 8, nr - 1);
-    const int lo = (t >> 1) * RW_TILE_BYTES + (t & 1) * 16 + kq * 2 * RW_TILE_BYTES;
-    pc0 = packed + (r0 >> 7) * ktile_row + (r0 & 127) * RW_TROW + lo;
-    pc1 = packed + (r1 >> 7) * ktile_row + (r1 & 127) * RW_TROW + lo;
+    const int rel = (((p << SHM) + (warp & ((1 << sh_) - 1))) << 4) + 2 * g;
+    const int r0 = R0 + min(rel, nr - 2);
+    pc0 = packed + (r0 >> 7) * ktile_row + (r0 & 127) * RW_TROW + (t >> 1) * RW_TILE_BYTES + (t & 1) * 16 +
+          kq * 2 * RW_TILE_BYTES;
     pm0 = meta + (static_cast<int64_t>(kq) * a.N + r0) * 4;
-    pm1 = meta + (static_cast<int64_t>(kq) * a.N + r1) * 4;
-    cstep = static_cast<int64_t>(kw) * 2 * RW_TILE_BYTES;
+    cstep = kw * 2 * RW_TILE_BYTES;
     mstep = static_cast<int64_t>(kw) * a.N * 4;
-    lbpp = kblocks >> (4 - sh_);
+    lbpp = kblocks >> (LOGW - sh_);
   };
   auto issue = [&](uint32_t slot_addr) {          // one cp.async group: the block under the iterator (or nothing)
     if (lp < np) {
       cp_async16(slot_addr, pc0);
-      cp_async16(slot_addr + 512, pc1);
-      cp_async4(slot_addr + 1024 - lane * 12, pm0);
-      cp_async4(slot_addr + 1152 - lane * 12, pm1);
-      pc0 += cstep; pc1 += cstep; pm0 += mstep; pm1 += mstep;
-      if (++lj == lbpp) { lj = 0; ++lp; if (lp < np) setup_pass(lp); }
+      cp_async16(slot_addr + 512, pc0 + RW_TROW);
+      cp_async8(slot_addr + 1024 - lane * 8, pm0);
+      pc0 += cstep; pm0 += mstep;
+      if (__builtin_expect(++lj == lbpp, 0)) { lj = 0; ++lp; if (lp < np) setup_pass(lp); }
     }
     cp_async_commit();
   };
   setup_pass(0);
 #pragma unroll 1
-  for (int d = 0; d < D - 2; ++d) issue(wring + d * RW_SLOT);   // static data: in flight before the previous kernel ends
+  for (int d = 0; d < D - 1; ++d) issue(wring + d * RW_SLOT);   // static data: in flight before the previous kernel ends
 
-  // ===================== x: block fixed point with ONE exponent per token =====================
-  // xi = rint(x 2^(21 - e)), e = exponent of the token's largest magnitude, as three balanced base-256 digits, one mma
-  // column each.  The elements that meet the HIGH nibbles of the packed words (e2, e3, e6, e7 of every 8) are scaled
-  // by another 1/16: the weight operand for them is (w & 0xf0f0f0f0) = 16 q, no shift.  stab holds, per k block and
-  // column, sum_lo l + 16 sum_hi l: the factor of the weight zero-point.
+  // ===================== x: block fixed point, four limbs =====================
+  // Per (token, 128-k block): xi = rint(x 2^(25 - e)), e = exponent of the block's largest magnitude, as four balanced
+  // base-256 digits, one mma column each.  The elements that meet the HIGH nibbles of the packed words (e2, e3, e6, e7
+  // of every 8) are scaled by another 1/16 -- rint(x 2^(21 - e)), the precision K3a gives every element -- because the
+  // weight operand for them is (w & 0xf0f0f0f0) = 16 q: no shift in the inner loop.  stab holds, per k block and
+  // column, (sum_lo l + 16 sum_hi l, 256^l 2^(e - 25)): the factor of the weight zero-point and the column's weight.
   pdl_wait();                                     // x and y belong to the stream order
   {
     const T* xg = reinterpret_cast<const T*>(a.x);
     const int cpt = a.K >> 3;                     // 16-byte chunks per token
     const int total_c = mrows * cpt;
-    uint4 vq[RW_XR], vu[RW_XR];
+    for (int i = tid; i < kblocks * 16; i += RW_THREADS)   // columns past 4 M: zero sums and weights
+      if ((i & 15) >= 8 * mrows) reinterpret_cast<float*>(stab_ptr)[i] = 0.f;
+    const uint32_t half_mask = (lane < 16) ? 0x0000ffffu : 0xffff0000u;   // the 16 chunks of one (token, block)
+#pragma unroll 1
+    for (int cb = tid; cb < total_c; cb += RW_XU * RW_THREADS) {
+      uint4 vq[RW_XU], vu[RW_XU];
 #pragma unroll
-    for (int u = 0; u < RW_XR; ++u) {
-      const int c = tid + u * RW_THREADS;
-      if (c < total_c) {
-        const int m = c >= cpt ? 1 : 0;
-        const int kofs = (c - m * cpt) * 8;
-        if (a.x_gate_up) {
-          const T* gp = xg + static_cast<int64_t>(m) * (2 * a.K) + kofs;
-          vq[u] = *reinterpret_cast<const uint4*>(gp);
-          vu[u] = *reinterpret_cast<const uint4*>(gp + a.K);
-        } else {
-          vq[u] = *reinterpret_cast<const uint4*>(xg + static_cast<int64_t>(m) * a.K + kofs);
+      for (int u = 0; u < RW_XU; ++u) {           // the loads of a batch in flight together: one L2 round trip
+        const int c = cb + u * RW_THREADS;
+        if (c < total_c) {
+          const int m = c >= cpt ? 1 : 0;
+          const int kofs = (c - m * cpt) * 8;
+          if (a.x_gate_up) {
+            const T* gp = xg + static_cast<int64_t>(m) * (2 * a.K) + kofs;
+            vq[u] = *reinterpret_cast<const uint4*>(gp);
+            vu[u] = *reinterpret_cast<const uint4*>(gp + a.K);
+          } else {
+            vq[u] = *reinterpret_cast<const uint4*>(xg + static_cast<int64_t>(m) * a.K + kofs);
+          }
         }
       }
-    }
-    for (int i = tid; i < kblocks * 8; i += RW_THREADS) reinterpret_cast<float*>(stab_ptr)[i] = 0.f;
-    uint32_t mx0 = 0, mx1 = 0;                    // max |x| as bits per token: finite < inf < NaN
 #pragma unroll
-    for (int u = 0; u < RW_XR; ++u) {
-      const int c = tid + u * RW_THREADS;
-      if (c < total_c) {
-        if (a.x_gate_up) vq[u] = silu_mul8<T>(vq[u], vu[u]);
-        const float2 p0 = DT<T>::to_f2(vq[u].x), p1 = DT<T>::to_f2(vq[u].y), p2 = DT<T>::to_f2(vq[u].z), p3 = DT<T>::to_f2(vq[u].w);
+      for (int u = 0; u < RW_XU; ++u) {
+        const int c = cb + u * RW_THREADS;
+        if (c >= total_c) break;                  // uniform per half-warp: total_c is a multiple of 16
+        const uint4 v = a.x_gate_up ? silu_mul8<T>(vq[u], vu[u]) : vq[u];
+        const int m = c >= cpt ? 1 : 0;
+        const int kc = c - m * cpt;               // chunk inside the token
+        const int bl = kc >> 4, ch = kc & 15;
+        const float2 p0 = DT<T>::to_f2(v.x), p1 = DT<T>::to_f2(v.y), p2 = DT<T>::to_f2(v.z), p3 = DT<T>::to_f2(v.w);
         uint32_t ab = max(max(__float_as_uint(p0.x) & 0x7fffffffu, __float_as_uint(p0.y) & 0x7fffffffu),
                           max(__float_as_uint(p1.x) & 0x7fffffffu, __float_as_uint(p1.y) & 0x7fffffffu));
         ab = max(ab, max(max(__float_as_uint(p2.x) & 0x7fffffffu, __float_as_uint(p2.y) & 0x7fffffffu),
                          max(__float_as_uint(p3.x) & 0x7fffffffu, __float_as_uint(p3.y) & 0x7fffffffu)));
-        if (c >= cpt) mx1 = max(mx1, ab); else mx0 = max(mx0, ab);
-      }
-    }
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      mx0 = max(mx0, __shfl_xor_sync(0xffffffffu, mx0, d));
-      mx1 = max(mx1, __shfl_xor_sync(0xffffffffu, mx1, d));
-    }
-    if (lane == 0) { tokmax[warp * 2] = mx0; tokmax[warp * 2 + 1] = mx1; }
-    __syncthreads();
-    mx0 = 0; mx1 = 0;
-#pragma unroll
-    for (int w = 0; w < RW_WARPS; ++w) { mx0 = max(mx0, tokmax[w * 2]); mx1 = max(mx1, tokmax[w * 2 + 1]); }
-    const int e0 = static_cast<int>(mx0 >> 23), e1 = static_cast<int>(mx1 >> 23);
-    const int fe0 = min(max(275 - e0, 5), 250), fe1 = min(max(275 - e1, 5), 250);   // scale = 2^(fe - 127)
-    if (tid < 2) {
-      const int fe = tid ? fe1 : fe0;
-      const bool bad = (tid ? e1 : e0) == 255;    // inf / NaN anywhere poisons the token's result
-      const uint32_t cexp = static_cast<uint32_t>(254 - fe);
-      coef[tid * 4 + 0] = bad ? nan_f() : __uint_as_float(cexp << 23);
-      coef[tid * 4 + 1] = bad ? nan_f() : __uint_as_float((cexp + 8) << 23);
-      coef[tid * 4 + 2] = bad ? nan_f() : __uint_as_float((cexp + 16) << 23);
-    }
-    const uint32_t half_mask = (lane < 16) ? 0x0000ffffu : 0xffff0000u;   // the 16 chunks of one (token, block)
-#pragma unroll
-    for (int u = 0; u < RW_XR; ++u) {
-      const int c = tid + u * RW_THREADS;
-      if (c < total_c) {                          // uniform per half-warp: total_c is a multiple of 16
-        const int m = c >= cpt ? 1 : 0;
-        const int kc = c - m * cpt;               // chunk inside the token
-        const int bl = kc >> 4, ch = kc & 15;
-        const int fe = m ? fe1 : fe0;
+        for (int d = 1; d < 16; d <<= 1) ab = max(ab, __shfl_xor_sync(half_mask, ab, d));   // finite < inf < NaN
+        const int e = static_cast<int>(ab >> 23);
+        const int fe = min(max(279 - e, 5), 250);            // scale = 2^(fe - 127) = 2^(25 - (e - 127))
         const float sc_lo = __uint_as_float(static_cast<uint32_t>(fe) << 23);
         const float sc_hi = __uint_as_float(static_cast<uint32_t>(fe - 4) << 23);
-        const float2 p0 = DT<T>::to_f2(vq[u].x), p1 = DT<T>::to_f2(vq[u].y), p2 = DT<T>::to_f2(vq[u].z), p3 = DT<T>::to_f2(vq[u].w);
         const float f[8] = {p0.x * sc_lo, p0.y * sc_lo, p1.x * sc_hi, p1.y * sc_hi,
                             p2.x * sc_lo, p2.y * sc_lo, p3.x * sc_hi, p3.y * sc_hi};
-        int l0[8], l1[8], l2[8];
+        int l0[8], l1[8], l2[8], l3[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int xi = __float2int_rn(f[i]);
           l0[i] = (xi << 24) >> 24;
           const int x1 = (xi - l0[i]) >> 8;
           l1[i] = (x1 << 24) >> 24;
-          l2[i] = (x1 - l1[i]) >> 8;
+          const int x2 = (x1 - l1[i]) >> 8;
+          l2[i] = (x2 << 24) >> 24;
+          l3[i] = (x2 - l2[i]) >> 8;
         }
         int s0 = (l0[0] + l0[1] + l0[4] + l0[5]) + 16 * (l0[2] + l0[3] + l0[6] + l0[7]);
         int s1 = (l1[0] + l1[1] + l1[4] + l1[5]) + 16 * (l1[2] + l1[3] + l1[6] + l1[7]);
         int s2 = (l2[0] + l2[1] + l2[4] + l2[5]) + 16 * (l2[2] + l2[3] + l2[6] + l2[7]);
+        int s3 = (l3[0] + l3[1] + l3[4] + l3[5]) + 16 * (l3[2] + l3[3] + l3[6] + l3[7]);
 #pragma unroll
         for (int d = 1; d < 16; d <<= 1) {
           s0 += __shfl_xor_sync(half_mask, s0, d);
           s1 += __shfl_xor_sync(half_mask, s1, d);
           s2 += __shfl_xor_sync(half_mask, s2, d);
+          s3 += __shfl_xor_sync(half_mask, s3, d);
         }
         auto pk = [](int b0, int b1, int b2, int b3) {
           return (static_cast<uint32_t>(b0) & 0xffu) | ((static_cast<uint32_t>(b1) & 0xffu) << 8) |
                  ((static_cast<uint32_t>(b2) & 0xffu) << 16) | (static_cast<uint32_t>(b3) << 24);
         };
         // bytes in the order in which the nibbles come out of a packed word: (e0, e4, e1, e5 | e2, e6, e3, e7)
-        uint8_t* colp = xs_ptr + bl * blk_pitch + (3 * m) * RW_ICOL + (ch >> 2) * 32 + (ch & 3) * 8;
+        uint8_t* colp = xs_ptr + bl * blk_pitch + (4 * m) * RW_ICOL + (ch >> 2) * 32 + (ch & 3) * 8;
         *reinterpret_cast<uint2*>(colp) = make_uint2(pk(l0[0], l0[4], l0[1], l0[5]), pk(l0[2], l0[6], l0[3], l0[7]));
         *reinterpret_cast<uint2*>(colp + RW_ICOL) = make_uint2(pk(l1[0], l1[4], l1[1], l1[5]), pk(l1[2], l1[6], l1[3], l1[7]));
         *reinterpret_cast<uint2*>(colp + 2 * RW_ICOL) = make_uint2(pk(l2[0], l2[4], l2[1], l2[5]), pk(l2[2], l2[6], l2[3], l2[7]));
+        *reinterpret_cast<uint2*>(colp + 3 * RW_ICOL) = make_uint2(pk(l3[0], l3[4], l3[1], l3[5]), pk(l3[2], l3[6], l3[3], l3[7]));
         if (ch == 0) {
-          float* sp = reinterpret_cast<float*>(stab_ptr) + bl * 8 + 3 * m;
-          sp[0] = static_cast<float>(s0); sp[1] = static_cast<float>(s1); sp[2] = static_cast<float>(s2);
+          // column weight 256^l / scale; inf / NaN anywhere in the block poisons the token's result
+          const uint32_t cexp = static_cast<uint32_t>(254 - fe);
+          const bool bad = e == 255;
+          float4* sp = reinterpret_cast<float4*>(stab_ptr + bl * 64 + m * 32);
+          sp[0] = make_float4(static_cast<float>(s0), bad ? nan_f() : __uint_as_float(cexp << 23),
+                              static_cast<float>(s1), bad ? nan_f() : __uint_as_float((cexp + 8) << 23));
+          sp[1] = make_float4(static_cast<float>(s2), bad ? nan_f() : __uint_as_float((cexp + 16) << 23),
+                              static_cast<float>(s3), bad ? nan_f() : __uint_as_float((cexp + 24) << 23));
         }
       }
     }
@@ -318,100 +301,75 @@ __global__ void __launch_bounds__(RW_THREADS, 1) k3_rows(const RowsArgs a) {
   }
 
   // ===================== the stream =====================
-  const int ncols = 3 * mrows;
+  const int ncols = 4 * mrows;
   const float nz_fix = a.qmin;
-  // ring bookkeeping: D - 2 blocks are outstanding between steps, the two slots behind the read position are free;
-  // a step reads NB slots and refills NB slots that were read at least one step ago
+  // ring bookkeeping: D - 1 blocks are outstanding between steps; a step reads the oldest block and refills the slot
+  // that was read one step ago
   const uint8_t* wring_g = smem_raw + (wring - smem_u32(smem_raw));       // generic address of this lane's ring
-  uint32_t coff = 0, roff = (D - 2) * RW_SLOT;    // byte offsets of the read position / the refill position
-  auto next_off = [&](uint32_t o) { o += RW_SLOT; return o == D * RW_SLOT ? 0u : o; };
-  auto step = [&](auto nb_tag, uint32_t xo, uint32_t so, uint32_t xstep, uint32_t sstep, float (&acc)[2][4]) {
-    constexpr int NB = decltype(nb_tag)::value;
-    cp_async_wait<D - 2 - NB>();                  // this lane's share of the NB oldest blocks has landed (it reads only that)
-    uint4 c0[NB], c1[NB], xb0[NB], xb1[NB];
-    uint32_t m0[NB], m1[NB];
-    float2 sv[NB];
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-      const uint8_t* sp = wring_g + coff;
-      c0[b] = *reinterpret_cast<const uint4*>(sp);
-      c1[b] = *reinterpret_cast<const uint4*>(sp + 512);
-      m0[b] = *reinterpret_cast<const uint32_t*>(sp + 1024 - lane * 12);
-      m1[b] = *reinterpret_cast<const uint32_t*>(sp + 1152 - lane * 12);
-      coff = next_off(coff);
-      xb0[b] = *reinterpret_cast<const uint4*>(smem_raw + xo + b * xstep);
-      xb1[b] = *reinterpret_cast<const uint4*>(smem_raw + xo + b * xstep + 16);
-      sv[b] = *reinterpret_cast<const float2*>(smem_raw + so + b * sstep);      // zero-point sums of columns 2t, 2t + 1
-    }
-#pragma unroll
-    for (int b = 0; b < NB; ++b) { issue(wring + roff); roff = next_off(roff); }
-    int di[NB][4];
-#pragma unroll
-    for (int b = 0; b < NB; ++b) { di[b][0] = di[b][1] = di[b][2] = di[b][3] = 0; }
-#pragma unroll
-    for (int w = 0; w < 4; ++w) {
-#pragma unroll
-      for (int b = 0; b < NB; ++b) {
-        const uint32_t w0 = w == 0 ? c0[b].x : w == 1 ? c0[b].y : w == 2 ? c0[b].z : c0[b].w;
-        const uint32_t w1 = w == 0 ? c1[b].x : w == 1 ? c1[b].y : w == 2 ? c1[b].z : c1[b].w;
-        const uint4& xq = (w >> 1) ? xb1[b] : xb0[b];
-        uint32_t af[4];
-        af[0] = w0 & 0x0f0f0f0fu; af[1] = w1 & 0x0f0f0f0fu; af[2] = w0 & 0xf0f0f0f0u; af[3] = w1 & 0xf0f0f0f0u;
-        imma_16832(di[b], af, (w & 1) ? xq.z : xq.x, (w & 1) ? xq.w : xq.y);
-      }
-    }
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-      const float2 sz0 = DT<T>::to_f2(m0[b]), sz1 = DT<T>::to_f2(m1[b]);     // (scale, zero) of rows g, g + 8
-      const float nz0 = HAS_ZP ? -sz0.y : nz_fix, nz1 = HAS_ZP ? -sz1.y : nz_fix;
-      acc[b][0] = fmaf(sz0.x, fmaf(nz0, sv[b].x, static_cast<float>(di[b][0])), acc[b][0]);
-      acc[b][1] = fmaf(sz0.x, fmaf(nz0, sv[b].y, static_cast<float>(di[b][1])), acc[b][1]);
-      acc[b][2] = fmaf(sz1.x, fmaf(nz1, sv[b].x, static_cast<float>(di[b][2])), acc[b][2]);
-      acc[b][3] = fmaf(sz1.x, fmaf(nz1, sv[b].y, static_cast<float>(di[b][3])), acc[b][3]);
-    }
-  };
+  uint32_t coff = 0, roff = (D - 1) * RW_SLOT;    // byte offsets of the read position / the refill position
   int parity = 0;
 #pragma unroll 1
   for (int p = 0; p < np; ++p) {
-    int sh, slab0;
-    pass_geo(p, sh, slab0);
+    const int sh = p < n8 ? SHM : sh_last;
     const int S = 1 << sh, KW = RW_WARPS >> sh, kq = warp >> sh;
-    const int bpp = kblocks >> (4 - sh);          // blocks per warp in this pass
-    // mma column g is (token, limb) = divmod(g, 3); columns past the last one re-read it (never stored)
+    const int bpp = kblocks >> (LOGW - sh);       // blocks per warp in this pass
+    // mma column g is (token, limb) = divmod(g, 4); columns past the last one re-read it (never stored)
     uint32_t xo = static_cast<uint32_t>(xs_ptr - smem_raw) + min(g, ncols - 1) * RW_ICOL + t * 32 + kq * blk_pitch;
-    uint32_t so = static_cast<uint32_t>(stab_ptr - smem_raw) + t * 8 + kq * 32;
-    const uint32_t xstep = KW * blk_pitch, sstep = KW * 32;
-    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-    int j = 0;
+    uint32_t so = static_cast<uint32_t>(stab_ptr - smem_raw) + t * 16 + kq * 64;
+    const uint32_t xstep = KW * blk_pitch, sstep = KW * 64;
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
 #pragma unroll 1
-    for (; a.pair && j + 2 <= bpp; j += 2) {      // two blocks per step: independent chains the scheduler interleaves
-      step(std::integral_constant<int, 2>{}, xo, so, xstep, sstep, acc);
-      xo += 2 * xstep; so += 2 * sstep;
-    }
-#pragma unroll 1
-    for (; j < bpp; ++j) {
-      step(std::integral_constant<int, 1>{}, xo, so, xstep, sstep, acc);
+    for (int j = 0; j < bpp; ++j) {
+      cp_async_wait<D - 2>();                     // this lane's share of the oldest block has landed (it reads only that)
+      const uint8_t* sp = wring_g + coff;
+      const uint4 c0 = *reinterpret_cast<const uint4*>(sp);
+      const uint4 c1 = *reinterpret_cast<const uint4*>(sp + 512);
+      const uint2 mm = *reinterpret_cast<const uint2*>(sp + 1024 - lane * 8);
+      const uint4 xb0 = *reinterpret_cast<const uint4*>(smem_raw + xo);
+      const uint4 xb1 = *reinterpret_cast<const uint4*>(smem_raw + xo + 16);
+      const float4 sv = *reinterpret_cast<const float4*>(smem_raw + so);      // (zero-point sum, weight) of columns 2t, 2t + 1
+      issue(wring + roff);
+      roff = coff;
+      coff += RW_SLOT;
+      if (coff == D * RW_SLOT) coff = 0;
+      int di[4] = {0, 0, 0, 0};
+      uint32_t af[4];
+      af[0] = c0.x & 0x0f0f0f0fu; af[1] = c1.x & 0x0f0f0f0fu; af[2] = c0.x & 0xf0f0f0f0u; af[3] = c1.x & 0xf0f0f0f0u;
+      imma_16832(di, af, xb0.x, xb0.y);
+      af[0] = c0.y & 0x0f0f0f0fu; af[1] = c1.y & 0x0f0f0f0fu; af[2] = c0.y & 0xf0f0f0f0u; af[3] = c1.y & 0xf0f0f0f0u;
+      imma_16832(di, af, xb0.z, xb0.w);
+      af[0] = c0.z & 0x0f0f0f0fu; af[1] = c1.z & 0x0f0f0f0fu; af[2] = c0.z & 0xf0f0f0f0u; af[3] = c1.z & 0xf0f0f0f0u;
+      imma_16832(di, af, xb1.x, xb1.y);
+      af[0] = c0.w & 0x0f0f0f0fu; af[1] = c1.w & 0x0f0f0f0fu; af[2] = c0.w & 0xf0f0f0f0u; af[3] = c1.w & 0xf0f0f0f0u;
+      imma_16832(di, af, xb1.z, xb1.w);
+      const float2 sz0 = DT<T>::to_f2(mm.x), sz1 = DT<T>::to_f2(mm.y);     // (scale, zero) of rows 2g, 2g + 1
+      const float nz0 = HAS_ZP ? -sz0.y : nz_fix, nz1 = HAS_ZP ? -sz1.y : nz_fix;
+      acc0 = fmaf(sz0.x * sv.y, fmaf(nz0, sv.x, static_cast<float>(di[0])), acc0);
+      acc1 = fmaf(sz0.x * sv.w, fmaf(nz0, sv.z, static_cast<float>(di[1])), acc1);
+      acc2 = fmaf(sz1.x * sv.y, fmaf(nz1, sv.x, static_cast<float>(di[2])), acc2);
+      acc3 = fmaf(sz1.x * sv.w, fmaf(nz1, sv.z, static_cast<float>(di[3])), acc3);
       xo += xstep; so += sstep;
     }
     // ---- end of the pass: the warps' fragments meet in shared memory, fixed summation order
     float* rp = red + parity * (RW_WARPS * 4 * 32);
     parity ^= 1;
-#pragma unroll
-    for (int r = 0; r < 4; ++r) rp[(warp * 4 + r) * 32 + lane] = acc[0][r] + acc[1][r];
+    rp[(warp * 4 + 0) * 32 + lane] = acc0; rp[(warp * 4 + 1) * 32 + lane] = acc1;
+    rp[(warp * 4 + 2) * 32 + lane] = acc2; rp[(warp * 4 + 3) * 32 + lane] = acc3;
     __syncthreads();
     const int PRW = 16 * S;
     if (tid < PRW * mrows) {
       const int rr = tid & (PRW - 1), m = tid >> (4 + sh);
-      const int rel = slab0 * 16 + rr;
+      const int rel = (p << (SHM + 4)) + rr;
       if (rel < nr) {
         const int sl = rr >> 4, r16 = rr & 15;
         float sum = 0.f;
         for (int kw = 0; kw < KW; ++kw) {
-          const float* wp = rp + ((sl + S * kw) * 4 + ((r16 >> 3) << 1)) * 32 + (r16 & 7) * 4;
+          // slab row r16 = mma row (r16 >> 1) + 8 (r16 & 1): lane quarter-group g = r16 >> 1, registers 2 (r16 & 1), + 1
+          const float* wp = rp + ((sl + S * kw) * 4 + ((r16 & 1) << 1)) * 32 + (r16 >> 1) * 4;
 #pragma unroll
-          for (int l = 0; l < 3; ++l) {
-            const int c = 3 * m + l;
-            sum = fmaf(coef[m * 4 + l], wp[(c & 1) * 32 + ((c & 7) >> 1)], sum);
+          for (int l = 0; l < 4; ++l) {           // the four limb columns of token m: 4 m + l
+            const int c = 4 * m + l;
+            sum += wp[(c & 1) * 32 + ((c & 7) >> 1)];
           }
         }
         const int n = R0 + rel;
@@ -422,25 +380,34 @@ __global__ void __launch_bounds__(RW_THREADS, 1) k3_rows(const RowsArgs a) {
   }
 }
 
-struct RowsPlan { int depth, smem; };
+struct RowsPlan { int logw, depth, smem; };
 
+// two CTAs of 16 warps per SM when everything fits twice (the next launch's CTAs then start -- and request their first
+// blocks -- while this launch is still running), else one CTA of 32 warps
 bool plan_rows(int M, int K, RowsPlan& p) {
   const int kblocks = K / 128;
-  const int fixed = RW_RED_BYTES + RW_MISC_BYTES + kblocks * 32 + kblocks * 3 * M * RW_ICOL + 128;
+  const int fixed0 = RW_MISC_BYTES + kblocks * 64 + kblocks * 4 * M * RW_ICOL + 128;
   static const int env_depth = []() { const char* e = getenv("Q100_ROWS_DEPTH"); return e ? atoi(e) : 0; }();
-  const int depths[4] = {8, 6, 5, 4};              // >= 4: a step of two blocks waits for all but D - 4 groups
-  for (int di = 0; di < 4; ++di) {
-    const int depth = depths[di];
-    if (env_depth > 0 && depth > env_depth) continue;
-    const int smem = fixed + RW_WARPS * depth * RW_SLOT;
-    if (smem <= 232448 - 1024) { p = RowsPlan{depth, smem}; return true; }
+  static const int env_logw = []() { const char* e = getenv("Q100_ROWS_LOGW"); return e ? atoi(e) : 0; }();
+  for (int logw = 4; logw <= 5; ++logw) {
+    if (env_logw && logw != env_logw) continue;
+    const int budget = logw == 4 ? (233472 - 2 * 1024) / 2 : 232448 - 1024;
+    const int fixed = fixed0 + 2 * (1 << logw) * 4 * 32 * 4;
+    const int depths[3] = {5, 4, 3};
+    for (int di = 0; di < 3; ++di) {
+      const int depth = depths[di];
+      if (env_depth > 0 && depth > env_depth) continue;
+      if (logw == 4 && depth < 4) continue;
+      const int smem = fixed + (1 << logw) * depth * RW_SLOT;
+      if (smem <= budget) { p = RowsPlan{logw, depth, smem}; return true; }
+    }
   }
   return false;
 }
 
-template <typename T, int D>
+template <typename T, int D, int LOGW>
 int launch_rows_t(const RowsArgs& a, const RowsPlan& p, int pdl, cudaStream_t st) {
-  auto kern = a.has_zp ? k3_rows<T, D, true> : k3_rows<T, D, false>;
+  auto kern = a.has_zp ? k3_rows<T, D, true, LOGW> : k3_rows<T, D, false, LOGW>;
   static std::mutex mu;
   static int max_set[2][kMaxDevices] = {};
   {
@@ -452,8 +419,8 @@ int launch_rows_t(const RowsArgs& a, const RowsPlan& p, int pdl, cudaStream_t st
     }
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(sm_count());
-  cfg.blockDim = dim3(RW_THREADS);
+  cfg.gridDim = dim3(sm_count() * (LOGW == 4 ? 2 : 1));
+  cfg.blockDim = dim3(32 << LOGW);
   cfg.dynamicSmemBytes = p.smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -466,11 +433,11 @@ int launch_rows_t(const RowsArgs& a, const RowsPlan& p, int pdl, cudaStream_t st
 
 template <typename T>
 int launch_rows(const RowsArgs& a, const RowsPlan& p, int pdl, cudaStream_t st) {
+  if (p.logw == 4) return p.depth == 5 ? launch_rows_t<T, 5, 4>(a, p, pdl, st) : launch_rows_t<T, 4, 4>(a, p, pdl, st);
   switch (p.depth) {
-    case 8: return launch_rows_t<T, 8>(a, p, pdl, st);
-    case 6: return launch_rows_t<T, 6>(a, p, pdl, st);
-    case 5: return launch_rows_t<T, 5>(a, p, pdl, st);
-    default: return launch_rows_t<T, 4>(a, p, pdl, st);
+    case 5: return launch_rows_t<T, 5, 5>(a, p, pdl, st);
+    case 4: return launch_rows_t<T, 4, 5>(a, p, pdl, st);
+    default: return launch_rows_t<T, 3, 5>(a, p, pdl, st);
   }
 }
 
@@ -481,7 +448,6 @@ bool gemm_rows_supported(int64_t M, int64_t N, int64_t K, int group, int n_bits,
   static const bool off = []() { const char* e = getenv("Q100_GEMM_ROWS"); return e && atoi(e) == 0; }();
   if (off) return false;
   if (mode != 2 || n_bits != 4 || group != 128 || K % 2048 != 0 || N % 8 != 0 || M < 1 || M > 2) return false;
-  if (M * K > RW_XR * RW_THREADS * 8) return false;     // x is held in registers between the two staging phases
   if (N > (1 << 24) || K > (1 << 20)) return false;
   RowsPlan p;
   return plan_rows(static_cast<int>(M), static_cast<int>(K), p);
@@ -500,8 +466,6 @@ int gemm_rows(const void* x, const void* packed, const void* meta, const void* b
   a.has_zp = disable_zp ? 0 : 1;
   a.qmin = disable_zp ? -8.0f : 0.0f;
   a.x_gate_up = x_gate_up;
-  static const int env_pair = []() { const char* e = getenv("Q100_ROWS_PAIR"); return e ? atoi(e) : 1; }();
-  a.pair = env_pair;
   if (dtype == Q100_F16) return launch_rows<__half>(a, p, pdl, st);
   return launch_rows<__nv_bfloat16>(a, p, pdl, st);
 }

@@ -91,6 +91,8 @@ def test_decode_shapes(name, n_bits, M):
         paths["stream_tc"] = _lib.GEMM_FORCE_STREAM_TC
         if M <= 2:
             paths["mma_sync_f16"] = _lib.GEMM_FORCE_MMA_SYNC | _lib.GEMM_NO_IMMA
+            if n_bits == 4:                       # default at these shapes: the row-owner kernel K3r; keep K3a covered
+                paths["mma_sync_streamk"] = _lib.GEMM_FORCE_MMA_SYNC | _lib.GEMM_NO_ROWS
     for pname, fl in paths.items():
         y = q100.gemm_wna16(x, pw, None, flags=fl)
         torch.cuda.synchronize()

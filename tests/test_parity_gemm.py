@@ -30,7 +30,10 @@ EPS_W = {"f16": 2.0 ** -12, "bf16": 2.0 ** -9}
 # the mma.sync kernel itself has two operand forms for W4 at M <= 8: unsigned-byte codes x signed-byte limbs of x
 # on the integer tensor-core path (default) and the fp16 magic form (GEMM_NO_IMMA)
 PATHS = {"stream_tc": _lib.GEMM_FORCE_STREAM_TC, "mma_sync": _lib.GEMM_FORCE_MMA_SYNC,
-         "mma_sync_f16": _lib.GEMM_FORCE_MMA_SYNC | _lib.GEMM_NO_IMMA}
+         "mma_sync_f16": _lib.GEMM_FORCE_MMA_SYNC | _lib.GEMM_NO_IMMA,
+         # W4 g128, M <= 2, K % 2048 == 0 run the row-owner kernel K3r by default (tests/test_rows.py); this path keeps
+         # the stream-K kernel K3a covered on those shapes
+         "mma_sync_streamk": _lib.GEMM_FORCE_MMA_SYNC | _lib.GEMM_NO_ROWS}
 
 
 def _check(y, x, wdeq, bias, dtype, exact_weights=True):
@@ -67,6 +70,8 @@ def test_skinny_vs_oracle(dtype, n_bits, M, path):
         pytest.skip("same kernel as mma_sync for this case")
     if path == "mma_sync_f16" and (n_bits not in (2, 4) or M > 2):
         pytest.skip("same kernel as mma_sync for this case")
+    if path == "mma_sync_streamk":
+        pytest.skip("same kernel as mma_sync for this case (K = 1024)")
     N, K = 384, 1024
     x, w, pw, r = _make(N, K, M, dtype, n_bits, 128, 1000 + M + n_bits)
     # the packed twin is consistent with the oracle (bit-exact)
@@ -88,6 +93,8 @@ def test_skinny_vs_oracle(dtype, n_bits, M, path):
                                        (256, 1024, 0), (6144, 4096, 128)])
 def test_skinny_shapes(dtype, N, K, group, path):
     if path == "stream_tc" and group in (32, 64):
+        pytest.skip("same kernel as mma_sync for this case")
+    if path == "mma_sync_streamk" and (group != 128 or K % 2048):
         pytest.skip("same kernel as mma_sync for this case")
     for M, bias in ((1, False), (3, True), (16, True)):
         x, w, pw, r = _make(N, K, M, dtype, 4, group or None, N + K + M)
