@@ -202,6 +202,25 @@ int q100_gemm_wna16(const void* x, const void* packed, const void* meta, const v
 size_t q100_gemm_workspace_bytes(int64_t M, int64_t N, int64_t K, int n_bits, int flags);
 
 /*
+ * K3r with the glue of a decoder block folded in (decode shapes; batch <= 2): the launches of
+ *   input_layernorm / post_attention_layernorm   (models/int_llama_layer.py:228, 249; quant/omni_norm.py:52-63)
+ *   hidden_states = residual + hidden_states     (models/int_llama_layer.py:246, 251)
+ * disappear into the GEMMs on either side of them:
+ *   norm_weight != NULL  x is the residual stream h [M, K]; the kernel stages weight * (h * rsqrt(mean(h^2) + eps))
+ *                        -- K4's arithmetic (q100_add_rmsnorm), up to the order of the fp32 sum of squares -- instead
+ *                        of x.  Excludes Q100_GEMM_X_GATE_UP.
+ *   residual != NULL     y = r(residual + r(x W^T + bias)), every rounding to `dtype` as on 16-bit tensors; residual
+ *                        [M, N] may be the same buffer as y.
+ * flags: Q100_GEMM_X_GATE_UP, Q100_GEMM_PDL.  Needs no workspace.  Only for the cases the row-owner kernel takes
+ * (q100_gemm_block_fusable(...) != 0: W4, group 128, M <= 2, K %% 2048 == 0, N %% 8 == 0); Q100_EUNSUPPORTED otherwise
+ * -- the caller then runs q100_add_rmsnorm + q100_gemm_wna16.
+ */
+int q100_gemm_wna16_block(const void* x, const void* packed, const void* meta, const void* bias, void* y,
+                          int64_t M, int64_t N, int64_t K, int group, int n_bits, int disable_zp, int dtype,
+                          const void* norm_weight, float eps, const void* residual, int flags, void* stream);
+int q100_gemm_block_fusable(int64_t M, int64_t N, int64_t K, int group, int n_bits);
+
+/*
  * K3c -- W8A8 / W4A4 (SmoothQuant-style configurations, main.py:326-349): per-token activation quantisation FUSED into
  * the GEMM as its prologue and an integer contraction on the tensor cores, at decode shapes (M <= 15).
  * Replaces  act_quantizer(x)  +  F.linear(x_q, w_q)  of quant/int_linear.py:59-62.

@@ -11,9 +11,32 @@
 // core.  Each kernel reproduces the reference's op sequence and per-op rounding (fp32 where torch promotes,
 // one rounding to the 16-bit storage type where torch stores); only the order of the fp32 sum inside the
 // variance differs from torch's reduction.  All are HBM/L2-latency bound and tiny: one CTA per row / head.
+#include <cstdlib>
+
 #include "q100_common.cuh"
+#include "q100_ptx.cuh"
 
 namespace q100 {
+
+// The small kernels of a decoder block are launched with programmatic stream serialization (Q100_BLOCK_PDL=0 turns it
+// off): each one lets its successor start at once (griddepcontrol.launch_dependents) and waits for its predecessors
+// (griddepcontrol.wait) before it touches memory -- a decode GEMM that follows K4 / K5 then fetches its first weight
+// blocks while the small kernel runs.  Without a PDL-aware predecessor both instructions are no-ops.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args) {
+  static const bool on = []() { const char* e = getenv("Q100_BLOCK_PDL"); return !(e && atoi(e) == 0); }();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = on ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 // ---------------------------------------------------------------- K4: (residual add +) RMSNorm
 // rows x cols, one CTA of 256 threads per row, the row lives in registers (cols <= 8192).
@@ -22,6 +45,8 @@ __global__ void __launch_bounds__(256) k4_add_rmsnorm(const T* __restrict__ x, c
                                                       const T* __restrict__ w, float eps, T* __restrict__ sum_out,
                                                       T* __restrict__ norm_out, int cols) {
   using D = DT<T>;
+  pdl_launch_dependents();
+  pdl_wait();
   const int64_t row = blockIdx.x;
   const int nvec = cols >> 3;
   const uint4* xr = reinterpret_cast<const uint4*>(x + row * cols);
@@ -93,6 +118,8 @@ __global__ void k5_rope_kv(const T* __restrict__ qkv, const T* __restrict__ cosb
                            T* __restrict__ v_cache, int H, int KVH, int D, int64_t max_len, int64_t rope_len,
                            uint32_t* __restrict__ err_flag) {
   using Dt = DT<T>;
+  pdl_launch_dependents();
+  pdl_wait();
   const int head = blockIdx.x, b = blockIdx.y, i = threadIdx.x, half = D >> 1;
   const int64_t pos = *pos_p;
   if (pos < 0 || pos >= max_len || pos >= rope_len) {      // past the cache / the rotary table: touch nothing
@@ -197,6 +224,8 @@ __global__ void __launch_bounds__(256) k5p_rope_qkv(const T* __restrict__ qkv, c
 template <typename T>
 __global__ void __launch_bounds__(256) k6_silu_mul(const T* __restrict__ gu, T* __restrict__ out, int64_t M, int I) {
   using D = DT<T>;
+  pdl_launch_dependents();
+  pdl_wait();
   const int vec_per_row = I >> 3;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= M * vec_per_row) return;
@@ -228,10 +257,11 @@ static int launch_add_rmsnorm(const void* x, const void* res, const void* w, flo
   T* sp = reinterpret_cast<T*>(sum_out);
   T* np_ = reinterpret_cast<T*>(norm_out);
   const unsigned grid = static_cast<unsigned>(rows);
-  if (nvec <= 256) k4_add_rmsnorm<T, 1><<<grid, 256, 0, st>>>(xp, rp, wp, eps, sp, np_, cols);
-  else if (nvec <= 512) k4_add_rmsnorm<T, 2><<<grid, 256, 0, st>>>(xp, rp, wp, eps, sp, np_, cols);
-  else k4_add_rmsnorm<T, 4><<<grid, 256, 0, st>>>(xp, rp, wp, eps, sp, np_, cols);
-  return check_cuda(cudaGetLastError(), "k4_add_rmsnorm launch");
+  cudaError_t e;
+  if (nvec <= 256) e = launch_pdl(k4_add_rmsnorm<T, 1>, dim3(grid), dim3(256), st, xp, rp, wp, eps, sp, np_, cols);
+  else if (nvec <= 512) e = launch_pdl(k4_add_rmsnorm<T, 2>, dim3(grid), dim3(256), st, xp, rp, wp, eps, sp, np_, cols);
+  else e = launch_pdl(k4_add_rmsnorm<T, 4>, dim3(grid), dim3(256), st, xp, rp, wp, eps, sp, np_, cols);
+  return check_cuda(e, "k4_add_rmsnorm launch");
 }
 
 }  // namespace q100
@@ -271,19 +301,20 @@ extern "C" int q100_rope_kv_decode(const void* qkv, const void* cos_cache, const
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const dim3 grid(heads + 2 * kv_heads, batch);
   const int64_t* pos = reinterpret_cast<const int64_t*>(position);
+  cudaError_t e;
   if (dtype == Q100_F16)
-    k5_rope_kv<__half><<<grid, head_dim / 2, 0, st>>>(
+    e = launch_pdl(k5_rope_kv<__half>, grid, dim3(head_dim / 2), st,
         reinterpret_cast<const __half*>(qkv), reinterpret_cast<const __half*>(cos_cache),
         reinterpret_cast<const __half*>(sin_cache), pos, reinterpret_cast<__half*>(q_out),
         reinterpret_cast<__half*>(k_cache), reinterpret_cast<__half*>(v_cache), heads, kv_heads, head_dim, max_len,
         rope_len, ef);
   else
-    k5_rope_kv<__nv_bfloat16><<<grid, head_dim / 2, 0, st>>>(
+    e = launch_pdl(k5_rope_kv<__nv_bfloat16>, grid, dim3(head_dim / 2), st,
         reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<const __nv_bfloat16*>(cos_cache),
         reinterpret_cast<const __nv_bfloat16*>(sin_cache), pos, reinterpret_cast<__nv_bfloat16*>(q_out),
         reinterpret_cast<__nv_bfloat16*>(k_cache), reinterpret_cast<__nv_bfloat16*>(v_cache), heads, kv_heads,
         head_dim, max_len, rope_len, ef);
-  return check_cuda(cudaGetLastError(), "k5_rope_kv launch");
+  return check_cuda(e, "k5_rope_kv launch");
 }
 
 extern "C" int q100_rope_qkv_prefill(const void* qkv, const void* cos_cache, const void* sin_cache,

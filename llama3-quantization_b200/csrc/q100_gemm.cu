@@ -153,6 +153,33 @@ extern "C" int q100_gemm_wna16(const void* x, const void* packed, const void* me
   return Q100_OK;
 }
 
+namespace q100 {
+bool gemm_rows_supported(int64_t M, int64_t N, int64_t K, int group, int n_bits, int mode);
+int gemm_rows(const void* x, const void* packed, const void* meta, const void* bias, void* y, int64_t M, int64_t N,
+              int64_t K, int disable_zp, int dtype, int mode, int pdl, int x_gate_up, cudaStream_t st,
+              const void* norm_w, float eps, const void* res);
+}
+
+extern "C" int q100_gemm_block_fusable(int64_t M, int64_t N, int64_t K, int group, int n_bits) {
+  return (M > 0 && N > 0 && K > 0 && q100::gemm_rows_supported(M, N, K, group == 0 ? static_cast<int>(K) : group, n_bits, 2)) ? 1 : 0;
+}
+
+extern "C" int q100_gemm_wna16_block(const void* x, const void* packed, const void* meta, const void* bias, void* y,
+                                     int64_t M, int64_t N, int64_t K, int group, int n_bits, int disable_zp, int dtype,
+                                     const void* norm_weight, float eps, const void* residual, int flags, void* stream) {
+  Q100_REQUIRE(x && packed && meta && y, Q100_EINVAL, "NULL pointer argument");
+  Q100_REQUIRE(dtype == Q100_F16 || dtype == Q100_BF16, Q100_EUNSUPPORTED, "fp16 / bf16 only (got dtype %d)", dtype);
+  const bool gate_up = (flags & Q100_GEMM_X_GATE_UP) != 0;
+  Q100_REQUIRE(!(gate_up && norm_weight), Q100_EINVAL, "Q100_GEMM_X_GATE_UP and norm_weight exclude each other");
+  Q100_REQUIRE(q100_gemm_block_fusable(M, N, K, group, n_bits), Q100_EUNSUPPORTED,
+               "q100_gemm_wna16_block: M=%lld N=%lld K=%lld group=%d W%d is not a row-owner (K3r) case: see "
+               "q100_gemm_block_fusable", (long long)M, (long long)N, (long long)K, group, n_bits);
+  int rc = ensure_device();
+  if (rc != Q100_OK) return rc;
+  return gemm_rows(x, packed, meta, bias, y, M, N, K, disable_zp, dtype, 2, (flags & Q100_GEMM_PDL) ? 1 : 0,
+                   gate_up ? 1 : 0, reinterpret_cast<cudaStream_t>(stream), norm_weight, eps, residual);
+}
+
 extern "C" int q100_gemm_wna8(const void* x, const void* row_minmax, const void* packed, const void* meta,
                               const void* bias, void* y, int64_t M, int64_t N, int64_t K, int group, int n_bits,
                               int a_bits, int disable_zp, int dtype, void* workspace, size_t workspace_bytes,

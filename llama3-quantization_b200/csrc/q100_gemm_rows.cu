@@ -54,6 +54,11 @@ struct RowsArgs {
   int has_zp;
   float qmin;
   int x_gate_up;
+  // block glue folded into the GEMM (q100_gemm_wna16_block): x = OmniLlamaRMSNorm(x) while it is staged (K4's
+  // arithmetic, quant/omni_norm.py:52-63), y = res + y in the epilogue (models/int_llama_layer.py:246, 251)
+  const void* norm_w;     // [K] T or null
+  float eps;
+  const void* res;        // [M, N] T or null
 };
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
@@ -121,6 +126,20 @@ __device__ __forceinline__ uint4 silu_mul8(const uint4& g, const uint4& u) {
     const float sx = D::rd(__fdiv_rn(a.x, __fadd_rn(1.0f, expf(-a.x))));
     const float sy = D::rd(__fdiv_rn(a.y, __fadd_rn(1.0f, expf(-a.y))));
     ow[j] = D::pack2(__fmul_rn(sx, b.x), __fmul_rn(sy, b.y));
+  }
+  return make_uint4(ow[0], ow[1], ow[2], ow[3]);
+}
+
+// weight * (h * rstd) for eight elements: both products in fp32, one rounding to T (k4_add_rmsnorm, q100_block.cu)
+template <typename T>
+__device__ __forceinline__ uint4 norm8(const uint4& h, const uint4& w, float rstd) {
+  using D = DT<T>;
+  const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, ww[4] = {w.x, w.y, w.z, w.w};
+  uint32_t ow[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = D::to_f2(hw[j]), g = D::to_f2(ww[j]);
+    ow[j] = D::pack2(__fmul_rn(g.x, __fmul_rn(f.x, rstd)), __fmul_rn(g.y, __fmul_rn(f.y, rstd)));
   }
   return make_uint4(ow[0], ow[1], ow[2], ow[3]);
 }
@@ -214,86 +233,134 @@ __global__ void __launch_bounds__(32 << LOGW, LOGW == 5 ? 1 : 2) k3_rows(const R
     for (int i = tid; i < kblocks * 16; i += RW_THREADS)   // columns past 4 M: zero sums and weights
       if ((i & 15) >= 8 * mrows) reinterpret_cast<float*>(stab_ptr)[i] = 0.f;
     const uint32_t half_mask = (lane < 16) ? 0x0000ffffu : 0xffff0000u;   // the 16 chunks of one (token, block)
-#pragma unroll 1
-    for (int cb = tid; cb < total_c; cb += RW_XU * RW_THREADS) {
-      uint4 vq[RW_XU], vu[RW_XU];
+    // one chunk: block maximum -> exponent -> four limbs per element -> shared memory
+    auto convert = [&](const uint4& v, int c) {
+      const int m = c >= cpt ? 1 : 0;
+      const int kc = c - m * cpt;                 // chunk inside the token
+      const int bl = kc >> 4, ch = kc & 15;
+      const float2 p0 = DT<T>::to_f2(v.x), p1 = DT<T>::to_f2(v.y), p2 = DT<T>::to_f2(v.z), p3 = DT<T>::to_f2(v.w);
+      uint32_t ab = max(max(__float_as_uint(p0.x) & 0x7fffffffu, __float_as_uint(p0.y) & 0x7fffffffu),
+                        max(__float_as_uint(p1.x) & 0x7fffffffu, __float_as_uint(p1.y) & 0x7fffffffu));
+      ab = max(ab, max(max(__float_as_uint(p2.x) & 0x7fffffffu, __float_as_uint(p2.y) & 0x7fffffffu),
+                       max(__float_as_uint(p3.x) & 0x7fffffffu, __float_as_uint(p3.y) & 0x7fffffffu)));
 #pragma unroll
-      for (int u = 0; u < RW_XU; ++u) {           // the loads of a batch in flight together: one L2 round trip
-        const int c = cb + u * RW_THREADS;
+      for (int d = 1; d < 16; d <<= 1) ab = max(ab, __shfl_xor_sync(half_mask, ab, d));   // finite < inf < NaN
+      const int e = static_cast<int>(ab >> 23);
+      const int fe = min(max(279 - e, 5), 250);            // scale = 2^(fe - 127) = 2^(25 - (e - 127))
+      const float sc_lo = __uint_as_float(static_cast<uint32_t>(fe) << 23);
+      const float sc_hi = __uint_as_float(static_cast<uint32_t>(fe - 4) << 23);
+      const float f[8] = {p0.x * sc_lo, p0.y * sc_lo, p1.x * sc_hi, p1.y * sc_hi,
+                          p2.x * sc_lo, p2.y * sc_lo, p3.x * sc_hi, p3.y * sc_hi};
+      int l0[8], l1[8], l2[8], l3[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int xi = __float2int_rn(f[i]);
+        l0[i] = (xi << 24) >> 24;
+        const int x1 = (xi - l0[i]) >> 8;
+        l1[i] = (x1 << 24) >> 24;
+        const int x2 = (x1 - l1[i]) >> 8;
+        l2[i] = (x2 << 24) >> 24;
+        l3[i] = (x2 - l2[i]) >> 8;
+      }
+      int s0 = (l0[0] + l0[1] + l0[4] + l0[5]) + 16 * (l0[2] + l0[3] + l0[6] + l0[7]);
+      int s1 = (l1[0] + l1[1] + l1[4] + l1[5]) + 16 * (l1[2] + l1[3] + l1[6] + l1[7]);
+      int s2 = (l2[0] + l2[1] + l2[4] + l2[5]) + 16 * (l2[2] + l2[3] + l2[6] + l2[7]);
+      int s3 = (l3[0] + l3[1] + l3[4] + l3[5]) + 16 * (l3[2] + l3[3] + l3[6] + l3[7]);
+#pragma unroll
+      for (int d = 1; d < 16; d <<= 1) {
+        s0 += __shfl_xor_sync(half_mask, s0, d);
+        s1 += __shfl_xor_sync(half_mask, s1, d);
+        s2 += __shfl_xor_sync(half_mask, s2, d);
+        s3 += __shfl_xor_sync(half_mask, s3, d);
+      }
+      auto pk = [](int b0, int b1, int b2, int b3) {
+        return (static_cast<uint32_t>(b0) & 0xffu) | ((static_cast<uint32_t>(b1) & 0xffu) << 8) |
+               ((static_cast<uint32_t>(b2) & 0xffu) << 16) | (static_cast<uint32_t>(b3) << 24);
+      };
+      // bytes in the order in which the nibbles come out of a packed word: (e0, e4, e1, e5 | e2, e6, e3, e7)
+      uint8_t* colp = xs_ptr + bl * blk_pitch + (4 * m) * RW_ICOL + (ch >> 2) * 32 + (ch & 3) * 8;
+      *reinterpret_cast<uint2*>(colp) = make_uint2(pk(l0[0], l0[4], l0[1], l0[5]), pk(l0[2], l0[6], l0[3], l0[7]));
+      *reinterpret_cast<uint2*>(colp + RW_ICOL) = make_uint2(pk(l1[0], l1[4], l1[1], l1[5]), pk(l1[2], l1[6], l1[3], l1[7]));
+      *reinterpret_cast<uint2*>(colp + 2 * RW_ICOL) = make_uint2(pk(l2[0], l2[4], l2[1], l2[5]), pk(l2[2], l2[6], l2[3], l2[7]));
+      *reinterpret_cast<uint2*>(colp + 3 * RW_ICOL) = make_uint2(pk(l3[0], l3[4], l3[1], l3[5]), pk(l3[2], l3[6], l3[3], l3[7]));
+      if (ch == 0) {
+        // column weight 256^l / scale; inf / NaN anywhere in the block poisons the token's result
+        const uint32_t cexp = static_cast<uint32_t>(254 - fe);
+        const bool bad = e == 255;
+        float4* sp = reinterpret_cast<float4*>(stab_ptr + bl * 64 + m * 32);
+        sp[0] = make_float4(static_cast<float>(s0), bad ? nan_f() : __uint_as_float(cexp << 23),
+                            static_cast<float>(s1), bad ? nan_f() : __uint_as_float((cexp + 8) << 23));
+        sp[1] = make_float4(static_cast<float>(s2), bad ? nan_f() : __uint_as_float((cexp + 16) << 23),
+                            static_cast<float>(s3), bad ? nan_f() : __uint_as_float((cexp + 24) << 23));
+      }
+    };
+    if (a.norm_w != nullptr) {
+      // x_norm (host: at most two chunks per thread): the chunks stay in registers between the sum of squares and the
+      // normalisation -- one sweep, one L2 round trip
+      uint4 vq[2], vw[2];
+      float ss0 = 0.f, ss1 = 0.f;
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int c = tid + u * RW_THREADS;
+        const int m = c >= cpt ? 1 : 0;
         if (c < total_c) {
-          const int m = c >= cpt ? 1 : 0;
-          const int kofs = (c - m * cpt) * 8;
-          if (a.x_gate_up) {
-            const T* gp = xg + static_cast<int64_t>(m) * (2 * a.K) + kofs;
-            vq[u] = *reinterpret_cast<const uint4*>(gp);
-            vu[u] = *reinterpret_cast<const uint4*>(gp + a.K);
-          } else {
-            vq[u] = *reinterpret_cast<const uint4*>(xg + static_cast<int64_t>(m) * a.K + kofs);
-          }
+          vq[u] = *reinterpret_cast<const uint4*>(xg + static_cast<int64_t>(m) * a.K + (c - m * cpt) * 8);
+          vw[u] = *reinterpret_cast<const uint4*>(reinterpret_cast<const T*>(a.norm_w) + (c - m * cpt) * 8);
+        } else {
+          vq[u] = make_uint4(0u, 0u, 0u, 0u);
         }
       }
 #pragma unroll
-      for (int u = 0; u < RW_XU; ++u) {
-        const int c = cb + u * RW_THREADS;
-        if (c >= total_c) break;                  // uniform per half-warp: total_c is a multiple of 16
-        const uint4 v = a.x_gate_up ? silu_mul8<T>(vq[u], vu[u]) : vq[u];
-        const int m = c >= cpt ? 1 : 0;
-        const int kc = c - m * cpt;               // chunk inside the token
-        const int bl = kc >> 4, ch = kc & 15;
-        const float2 p0 = DT<T>::to_f2(v.x), p1 = DT<T>::to_f2(v.y), p2 = DT<T>::to_f2(v.z), p3 = DT<T>::to_f2(v.w);
-        uint32_t ab = max(max(__float_as_uint(p0.x) & 0x7fffffffu, __float_as_uint(p0.y) & 0x7fffffffu),
-                          max(__float_as_uint(p1.x) & 0x7fffffffu, __float_as_uint(p1.y) & 0x7fffffffu));
-        ab = max(ab, max(max(__float_as_uint(p2.x) & 0x7fffffffu, __float_as_uint(p2.y) & 0x7fffffffu),
-                         max(__float_as_uint(p3.x) & 0x7fffffffu, __float_as_uint(p3.y) & 0x7fffffffu)));
+      for (int u = 0; u < 2; ++u) {
+        const int c = tid + u * RW_THREADS;
+        const uint32_t w[4] = {vq[u].x, vq[u].y, vq[u].z, vq[u].w};
+        float ss = 0.f;
 #pragma unroll
-        for (int d = 1; d < 16; d <<= 1) ab = max(ab, __shfl_xor_sync(half_mask, ab, d));   // finite < inf < NaN
-        const int e = static_cast<int>(ab >> 23);
-        const int fe = min(max(279 - e, 5), 250);            // scale = 2^(fe - 127) = 2^(25 - (e - 127))
-        const float sc_lo = __uint_as_float(static_cast<uint32_t>(fe) << 23);
-        const float sc_hi = __uint_as_float(static_cast<uint32_t>(fe - 4) << 23);
-        const float f[8] = {p0.x * sc_lo, p0.y * sc_lo, p1.x * sc_hi, p1.y * sc_hi,
-                            p2.x * sc_lo, p2.y * sc_lo, p3.x * sc_hi, p3.y * sc_hi};
-        int l0[8], l1[8], l2[8], l3[8];
+        for (int i = 0; i < 4; ++i) { const float2 f = DT<T>::to_f2(w[i]); ss = fmaf(f.x, f.x, ss); ss = fmaf(f.y, f.y, ss); }
+        if (c >= cpt) ss1 += ss; else ss0 += ss;
+      }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int xi = __float2int_rn(f[i]);
-          l0[i] = (xi << 24) >> 24;
-          const int x1 = (xi - l0[i]) >> 8;
-          l1[i] = (x1 << 24) >> 24;
-          const int x2 = (x1 - l1[i]) >> 8;
-          l2[i] = (x2 << 24) >> 24;
-          l3[i] = (x2 - l2[i]) >> 8;
+      for (int d = 16; d > 0; d >>= 1) {
+        ss0 += __shfl_xor_sync(0xffffffffu, ss0, d);
+        ss1 += __shfl_xor_sync(0xffffffffu, ss1, d);
+      }
+      float* ssq = reinterpret_cast<float*>(smem_raw + RW_RED_BYTES);          // [warps][2] in the spare kilobyte
+      if (lane == 0) { ssq[warp * 2] = ss0; ssq[warp * 2 + 1] = ss1; }
+      __syncthreads();
+      ss0 = 0.f; ss1 = 0.f;
+#pragma unroll
+      for (int w = 0; w < RW_WARPS; ++w) { ss0 += ssq[w * 2]; ss1 += ssq[w * 2 + 1]; }     // fixed order: every thread the same bits
+      const float rstd0 = rsqrtf(__fadd_rn(__fdiv_rn(ss0, static_cast<float>(a.K)), a.eps));
+      const float rstd1 = rsqrtf(__fadd_rn(__fdiv_rn(ss1, static_cast<float>(a.K)), a.eps));
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int c = tid + u * RW_THREADS;
+        if (c < total_c) convert(norm8<T>(vq[u], vw[u], c >= cpt ? rstd1 : rstd0), c);   // uniform per half-warp
+      }
+    } else {
+#pragma unroll 1
+      for (int cb = tid; cb < total_c; cb += RW_XU * RW_THREADS) {
+        uint4 vq[RW_XU], vu[RW_XU];
+#pragma unroll
+        for (int u = 0; u < RW_XU; ++u) {         // the loads of a batch in flight together: one L2 round trip
+          const int c = cb + u * RW_THREADS;
+          if (c < total_c) {
+            const int m = c >= cpt ? 1 : 0;
+            const int kofs = (c - m * cpt) * 8;
+            if (a.x_gate_up) {
+              const T* gp = xg + static_cast<int64_t>(m) * (2 * a.K) + kofs;
+              vq[u] = *reinterpret_cast<const uint4*>(gp);
+              vu[u] = *reinterpret_cast<const uint4*>(gp + a.K);
+            } else {
+              vq[u] = *reinterpret_cast<const uint4*>(xg + static_cast<int64_t>(m) * a.K + kofs);
+            }
+          }
         }
-        int s0 = (l0[0] + l0[1] + l0[4] + l0[5]) + 16 * (l0[2] + l0[3] + l0[6] + l0[7]);
-        int s1 = (l1[0] + l1[1] + l1[4] + l1[5]) + 16 * (l1[2] + l1[3] + l1[6] + l1[7]);
-        int s2 = (l2[0] + l2[1] + l2[4] + l2[5]) + 16 * (l2[2] + l2[3] + l2[6] + l2[7]);
-        int s3 = (l3[0] + l3[1] + l3[4] + l3[5]) + 16 * (l3[2] + l3[3] + l3[6] + l3[7]);
 #pragma unroll
-        for (int d = 1; d < 16; d <<= 1) {
-          s0 += __shfl_xor_sync(half_mask, s0, d);
-          s1 += __shfl_xor_sync(half_mask, s1, d);
-          s2 += __shfl_xor_sync(half_mask, s2, d);
-          s3 += __shfl_xor_sync(half_mask, s3, d);
-        }
-        auto pk = [](int b0, int b1, int b2, int b3) {
-          return (static_cast<uint32_t>(b0) & 0xffu) | ((static_cast<uint32_t>(b1) & 0xffu) << 8) |
-                 ((static_cast<uint32_t>(b2) & 0xffu) << 16) | (static_cast<uint32_t>(b3) << 24);
-        };
-        // bytes in the order in which the nibbles come out of a packed word: (e0, e4, e1, e5 | e2, e6, e3, e7)
-        uint8_t* colp = xs_ptr + bl * blk_pitch + (4 * m) * RW_ICOL + (ch >> 2) * 32 + (ch & 3) * 8;
-        *reinterpret_cast<uint2*>(colp) = make_uint2(pk(l0[0], l0[4], l0[1], l0[5]), pk(l0[2], l0[6], l0[3], l0[7]));
-        *reinterpret_cast<uint2*>(colp + RW_ICOL) = make_uint2(pk(l1[0], l1[4], l1[1], l1[5]), pk(l1[2], l1[6], l1[3], l1[7]));
-        *reinterpret_cast<uint2*>(colp + 2 * RW_ICOL) = make_uint2(pk(l2[0], l2[4], l2[1], l2[5]), pk(l2[2], l2[6], l2[3], l2[7]));
-        *reinterpret_cast<uint2*>(colp + 3 * RW_ICOL) = make_uint2(pk(l3[0], l3[4], l3[1], l3[5]), pk(l3[2], l3[6], l3[3], l3[7]));
-        if (ch == 0) {
-          // column weight 256^l / scale; inf / NaN anywhere in the block poisons the token's result
-          const uint32_t cexp = static_cast<uint32_t>(254 - fe);
-          const bool bad = e == 255;
-          float4* sp = reinterpret_cast<float4*>(stab_ptr + bl * 64 + m * 32);
-          sp[0] = make_float4(static_cast<float>(s0), bad ? nan_f() : __uint_as_float(cexp << 23),
-                              static_cast<float>(s1), bad ? nan_f() : __uint_as_float((cexp + 8) << 23));
-          sp[1] = make_float4(static_cast<float>(s2), bad ? nan_f() : __uint_as_float((cexp + 16) << 23),
-                              static_cast<float>(s3), bad ? nan_f() : __uint_as_float((cexp + 24) << 23));
+        for (int u = 0; u < RW_XU; ++u) {
+          const int c = cb + u * RW_THREADS;
+          if (c >= total_c) break;                // uniform per half-warp: total_c is a multiple of 16
+          convert(a.x_gate_up ? silu_mul8<T>(vq[u], vu[u]) : vq[u], c);
         }
       }
     }
@@ -318,6 +385,14 @@ __global__ void __launch_bounds__(32 << LOGW, LOGW == 5 ? 1 : 2) k3_rows(const R
     uint32_t so = static_cast<uint32_t>(stab_ptr - smem_raw) + t * 16 + kq * 64;
     const uint32_t xstep = KW * blk_pitch, sstep = KW * 64;
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+    // this thread's element of the residual (it finishes output (row tid mod 16 S, token tid / 16 S) of the pass):
+    // requested now, needed after the pass
+    float resv = 0.f;
+    if (a.res != nullptr && tid < (16 << sh) * mrows) {
+      const int rel_o = (p << (SHM + 4)) + (tid & ((16 << sh) - 1));
+      if (rel_o < nr)
+        resv = DT<T>::to_f(reinterpret_cast<const T*>(a.res)[static_cast<int64_t>(tid >> (4 + sh)) * a.N + R0 + rel_o]);
+    }
 #pragma unroll 1
     for (int j = 0; j < bpp; ++j) {
       cp_async_wait<D - 2>();                     // this lane's share of the oldest block has landed (it reads only that)
@@ -374,6 +449,7 @@ __global__ void __launch_bounds__(32 << LOGW, LOGW == 5 ? 1 : 2) k3_rows(const R
         }
         const int n = R0 + rel;
         if (a.bias) sum += DT<T>::to_f(reinterpret_cast<const T*>(a.bias)[n]);
+        if (a.res != nullptr) sum = __fadd_rn(resv, DT<T>::rd(sum));   // residual + r(y), rounded to T: K4's add on two 16-bit tensors
         reinterpret_cast<T*>(a.y)[static_cast<int64_t>(m) * a.N + n] = DT<T>::from_f(sum);
       }
     }
@@ -454,11 +530,15 @@ bool gemm_rows_supported(int64_t M, int64_t N, int64_t K, int group, int n_bits,
 }
 
 int gemm_rows(const void* x, const void* packed, const void* meta, const void* bias, void* y, int64_t M, int64_t N,
-              int64_t K, int disable_zp, int dtype, int mode, int pdl, int x_gate_up, cudaStream_t st) {
+              int64_t K, int disable_zp, int dtype, int mode, int pdl, int x_gate_up, cudaStream_t st,
+              const void* norm_w, float eps, const void* res) {
   (void)mode;
   RowsPlan p;
   Q100_REQUIRE(plan_rows(static_cast<int>(M), static_cast<int>(K), p), Q100_EUNSUPPORTED,
                "k3_rows: no shared-memory plan for M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
+  Q100_REQUIRE(norm_w == nullptr || M * K / 8 <= 2 * (32 << p.logw), Q100_EUNSUPPORTED,
+               "k3_rows: RMSNorm in the x staging holds x in registers: M * K <= %d (got M=%lld K=%lld)",
+               16 * (32 << p.logw), (long long)M, (long long)K);
   RowsArgs a{};
   a.x = x; a.packed = packed; a.meta = meta; a.bias = bias; a.y = y;
   a.M = static_cast<int>(M); a.N = static_cast<int>(N); a.K = static_cast<int>(K);
@@ -466,6 +546,7 @@ int gemm_rows(const void* x, const void* packed, const void* meta, const void* b
   a.has_zp = disable_zp ? 0 : 1;
   a.qmin = disable_zp ? -8.0f : 0.0f;
   a.x_gate_up = x_gate_up;
+  a.norm_w = norm_w; a.eps = eps; a.res = res;
   if (dtype == Q100_F16) return launch_rows<__half>(a, p, pdl, st);
   return launch_rows<__nv_bfloat16>(a, p, pdl, st);
 }

@@ -1635,7 +1635,8 @@ int skinny_timing(long long* out, int n) {
 
 bool gemm_rows_supported(int64_t M, int64_t N, int64_t K, int group, int n_bits, int mode);
 int gemm_rows(const void* x, const void* packed, const void* meta, const void* bias, void* y, int64_t M, int64_t N,
-              int64_t K, int disable_zp, int dtype, int mode, int pdl, int x_gate_up, cudaStream_t st);
+              int64_t K, int disable_zp, int dtype, int mode, int pdl, int x_gate_up, cudaStream_t st,
+              const void* norm_w = nullptr, float eps = 0.f, const void* res = nullptr);
 
 size_t skinny_workspace_bytes(int64_t M, int64_t N, int64_t K) {
   const SkinnyPlan p = plan_skinny(N, K);

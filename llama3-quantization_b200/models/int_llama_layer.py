@@ -123,6 +123,9 @@ class StaticKV:
 
 
 # ------------------------------------------------------------------------------------ fused launches
+from q100._lib import GEMM_X_GATE_UP as _GEMM_X_GATE_UP
+
+
 class _FusedLinears:
     """Several QuantLinears that consume the same input, run as one dequant-GEMM on the concatenation
     (along N) of their packed weights.  The concatenation is cached on the identity of the parts."""
@@ -457,6 +460,9 @@ class QuantLlamaDecoderLayer(nn.Module):
         bsz = x.shape[0]
         nh = attn.num_heads // attn.tp_world
         nkv = max(attn.num_key_value_heads // attn.tp_world, 1)
+        folded = self._decode_step_folded(x, residual, kv, position, attention_mask, err_flag, nh, nkv)
+        if folded is not None:
+            return folded
         h0, n1 = _ops.add_rmsnorm(x, self.input_layernorm.weight, self.input_layernorm.variance_epsilon, residual)
         qkv = attn._qkv((attn.q_proj, attn.k_proj, attn.v_proj), n1, split=False)
         if qkv is None:
@@ -479,6 +485,43 @@ class QuantLlamaDecoderLayer(nn.Module):
         if getattr(mlp, "tp_world", 1) > 1 and not mlp.down_proj.reduced:
             d = _tp.reduce_output(d, _tp.ROW, mlp.tp_group)
         return d, h1
+
+    def _decode_step_folded(self, x, residual, kv, position, attention_mask, err_flag, nh, nkv):
+        """The decode step in 4 GEMM launches + K5 + the attention core: both RMSNorms run inside the x staging of the
+        GEMM that consumes them and both residual adds inside the epilogue of the GEMM that produces the summand
+        (q100_gemm_wna16_block: the row-owner kernel K3r, batch <= 2, W4 g128, one GPU).  Takes and returns the
+        residual stream: ``x`` is this block's input hidden state (``residual`` None), the result is (h_out, None).
+        None when the block does not qualify -- the caller then runs the K4 route."""
+        import os
+        attn, mlp = self.self_attn, self.mlp
+        bsz = x.shape[0]
+        if residual is not None or bsz > 2 or x.numel() > 16384 or attn.tp_world > 1 or getattr(mlp, "tp_world", 1) > 1 \
+                or os.environ.get("Q100_NO_FOLD") or torch.is_grad_enabled():
+            return None
+        h = x.reshape(bsz, -1)
+        got_qkv = attn._qkv.packed((attn.q_proj, attn.k_proj, attn.v_proj), h)
+        got_gu = mlp._gate_up.packed((mlp.gate_proj, mlp.up_proj), h)
+        if got_qkv is None or got_gu is None or attn.q_proj.use_act_quant or mlp.gate_proj.use_act_quant:
+            return None
+        wqkv, wgu = got_qkv[0], got_gu[0]
+        wo = attn.o_proj.packed_operand(h)
+        wd = mlp.down_proj.packed_operand(h)
+        if wo is None or wd is None or attn.o_proj.use_act_quant or mlp.down_proj.use_act_quant \
+                or not all(_ops.gemm_block_fusable(bsz, w) and w.dtype == h.dtype for w in (wqkv, wo, wgu, wd)):
+            return None
+        rc = getattr(attn, "_rope16", None)
+        if rc is None or rc[0].dtype != x.dtype or rc[0].shape[0] < kv.k.shape[-2] or rc[0].device != x.device:
+            cos, sin = attn.rotary_emb(kv.v, seq_len=kv.k.shape[-2])
+            rc = attn._rope16 = (cos.to(x.dtype).contiguous(), sin.to(x.dtype).contiguous())
+        ln1, ln2 = self.input_layernorm, self.post_attention_layernorm
+        qkv = _ops.gemm_wna16_block(h, wqkv, norm_weight=ln1.weight, eps=ln1.variance_epsilon)
+        q = _ops.rope_kv_decode(qkv, rc[0], rc[1], position, kv.k, kv.v, nh, nkv, err_flag)
+        att = F.scaled_dot_product_attention(q, kv.k, kv.v, attn_mask=attention_mask, enable_gqa=nh != nkv)
+        h1 = _ops.gemm_wna16_block(att.reshape(bsz, nh * attn.head_dim), wo, attn.o_proj.bias, residual=h)
+        gu = _ops.gemm_wna16_block(h1, wgu, norm_weight=ln2.weight, eps=ln2.variance_epsilon)
+        h2 = _ops.gemm_wna16_block(gu, wd, mlp.down_proj.bias, flags=_GEMM_X_GATE_UP, residual=h1)
+        attn.o_proj.reduced = mlp.down_proj.reduced = False
+        return h2.view(x.shape), None
 
     # ------------------------------------------------------------------ quantisation state
     def _quant_linears(self):

@@ -65,6 +65,8 @@ SIGNATURES = {
     "q100_gemm_wna16": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _sz, _i, _vp]),
     "q100_gemm_wna8": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _i, _vp, _sz, _i, _vp]),
     "q100_gemm_workspace_bytes": (_sz, [_i64, _i64, _i64, _i, _i]),
+    "q100_gemm_wna16_block": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _vp, C.c_float, _vp, _i, _vp]),
+    "q100_gemm_block_fusable": (_i, [_i64, _i64, _i64, _i, _i]),
     "q100_chain_desc_bytes": (_sz, [_i]),
     "q100_chain_ssq_parts": (_i64, [_i64]),
     "q100_chain_attn_partial_floats": (_i64, [_i, _i, _i64]),

@@ -236,7 +236,10 @@ class GraphDecoder:
         self.fused = fused
         self.want_chain = chain
         self.chain = None
-        self.pdl = False          # measured: 2.31 ms/token without, 2.46 with (predecessors are not PDL-aware)
+        # programmatic dependent launch for the decode GEMMs: since K4 / K5 release their successor at once, the GEMM
+        # behind them fetches its first weight blocks while they run (Q100_DECODE_PDL=0: off)
+        import os as _os
+        self.pdl = _os.environ.get("Q100_DECODE_PDL", "1") != "0"
         self.model, self.bsz, self.max_len = model, bsz, max_len
         cfg = model.cfg
         dev, dt = model.embed_tokens.device, model.embed_tokens.dtype

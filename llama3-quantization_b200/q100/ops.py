@@ -325,6 +325,45 @@ def gemm_wna16(x: torch.Tensor, w: PackedWeight, bias: Optional[torch.Tensor] = 
     return y.view(*shp[:-1], w.N)
 
 
+def gemm_block_fusable(rows: int, w: PackedWeight) -> bool:
+    """True when ``gemm_wna16_block`` takes ``rows`` x this weight (the row-owner decode kernel K3r applies)."""
+    return bool(lib.q100_gemm_block_fusable(rows, w.N, w.K, w.group, w.n_bits))
+
+
+def gemm_wna16_block(x: torch.Tensor, w: PackedWeight, bias: Optional[torch.Tensor] = None, flags: int = 0,
+                     norm_weight: Optional[torch.Tensor] = None, eps: float = 0.0,
+                     residual: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Decode GEMM with the glue of a decoder block folded in (q100_gemm_wna16_block): ``norm_weight`` -- x is the
+    residual stream and OmniLlamaRMSNorm(x) is what gets multiplied; ``residual`` -- returns residual + x W^T.
+    Raises Q100Error(EUNSUPPORTED) unless ``gemm_block_fusable``."""
+    _require_cuda(x, w.packed, bias, norm_weight, residual)
+    if x.dtype != w.dtype:
+        raise TypeError(f"q100.gemm_wna16_block: x is {x.dtype} but the packed weight was built for {w.dtype}")
+    flags |= _DEFAULT_GEMM_FLAGS & _lib.GEMM_PDL
+    kx = 2 * w.K if flags & _lib.GEMM_X_GATE_UP else w.K
+    if x.shape[-1] != kx:
+        raise ValueError(f"q100.gemm_wna16_block: x has K={x.shape[-1]}, expected {kx}")
+    shp = x.shape
+    x2 = x.contiguous().view(-1, kx)
+    M = x2.shape[0]
+    y = torch.empty((M, w.N), dtype=x.dtype, device=x.device) if out is None else out
+    if bias is not None:
+        bias = bias.to(x.dtype).contiguous()
+    if norm_weight is not None:
+        norm_weight = norm_weight.to(x.dtype).contiguous()
+        if norm_weight.numel() != w.K:
+            raise ValueError("q100.gemm_wna16_block: norm_weight must have K elements")
+    if residual is not None:
+        residual = residual.contiguous()
+        if residual.numel() != M * w.N or residual.dtype != x.dtype:
+            raise ValueError("q100.gemm_wna16_block: residual must be [rows, N] in the dtype of x")
+    with _on(x.device):
+        check(lib.q100_gemm_wna16_block(x2.data_ptr(), w.packed.data_ptr(), w.meta.data_ptr(), _ptr(bias), y.data_ptr(),
+                                        M, w.N, w.K, w.group, w.n_bits, int(w.disable_zero_point), _DT[x.dtype],
+                                        _ptr(norm_weight), float(eps), _ptr(residual), flags, _stream(x2)))
+    return y.view(*shp[:-1], w.N)
+
+
 def gemm_wna8(x: torch.Tensor, w: PackedWeight, a_bits: int, minmax: Optional[torch.Tensor] = None,
               bias: Optional[torch.Tensor] = None, flags: int = 0) -> torch.Tensor:
     """y = fakequant_rows(x, a_bits) @ dequant(w)^T with the activation quantisation fused into the GEMM and the

@@ -104,3 +104,71 @@ def test_rows_outliers_and_specials(dtype):
     x3 = torch.zeros_like(x)
     y3 = q100.gemm_wna16(x3, pw, None)
     assert float(y3.float().abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("dtype", ["f16", "bf16"])
+@pytest.mark.parametrize("M", [1, 2])
+def test_block_glue_folded_into_the_gemm(dtype, M):
+    """q100_gemm_wna16_block: RMSNorm in the x staging == K4 + GEMM up to the order of the fp32 sum of squares (at most
+    one 16-bit ulp on a few staged elements); residual add in the epilogue == the add on the two 16-bit tensors, bit
+    for bit; both together; in place."""
+    N, K = 4096, 4096
+    gen = torch.Generator().manual_seed(17 + M)
+    w = (torch.randn(N, K, generator=gen) * 0.02).to(TDT[dtype]).cuda()
+    h = (torch.randn(M, K, generator=gen) * 1.5).to(TDT[dtype]).cuda()
+    nw = (1.0 + 0.1 * torch.randn(K, generator=gen)).to(TDT[dtype]).cuda()
+    res = torch.randn(M, N, generator=gen).to(TDT[dtype]).cuda()
+    pw, _ = q100.pack_weight(w, 4, 128)
+    assert q100.ops.gemm_block_fusable(M, pw)
+    eps_out = 2.0 ** -8 if dtype == "bf16" else 2.0 ** -11
+    n_ref = q100.ops.add_rmsnorm(h, nw, 1e-5)[1]
+    y_ref = q100.gemm_wna16(n_ref, pw, None)
+    y = q100.ops.gemm_wna16_block(h, pw, norm_weight=nw, eps=1e-5)
+    torch.cuda.synchronize()
+    assert (y.float() - y_ref.float()).abs().max().item() <= 4 * eps_out * y_ref.float().abs().max().item()
+    # residual in the epilogue: same kernel, same accumulator bits, then the 16-bit add
+    y2_ref = res + q100.gemm_wna16(n_ref, pw, None)
+    y2 = q100.ops.gemm_wna16_block(n_ref, pw, residual=res)
+    torch.cuda.synchronize()
+    assert torch.equal(y2.view(torch.int16), y2_ref.view(torch.int16))
+    # both, in place on the residual buffer, with a bias
+    b = (torch.randn(N, generator=gen) * 0.1).to(TDT[dtype]).cuda()
+    y3_ref = res + q100.gemm_wna16(n_ref, pw, b)
+    buf = res.clone()
+    y3 = q100.ops.gemm_wna16_block(h, pw, b, norm_weight=nw, eps=1e-5, residual=buf, out=buf)
+    torch.cuda.synchronize()
+    assert y3.data_ptr() == buf.data_ptr()
+    assert (y3.float() - y3_ref.float()).abs().max().item() <= 4 * eps_out * max(y3_ref.float().abs().max().item(), 1.0)
+    # not a K3r case: refused, not silently different
+    pw3, _ = q100.pack_weight(w, 3, 128)
+    assert not q100.ops.gemm_block_fusable(M, pw3)
+    with pytest.raises(q100.Q100Error):
+        q100.ops.gemm_wna16_block(h, pw3, norm_weight=nw, eps=1e-5)
+
+
+def test_decoder_folded_route_matches_the_k4_route(monkeypatch):
+    """GraphDecoder at batch 1 / 2: the folded route (4 GEMM launches with the norms and residual adds inside) against the
+    K4 route on the same model: same greedy tokens, logits within 16-bit round-off."""
+    from q100 import llama as QL
+    dev = torch.device("cuda", 0)
+    cfg = QL.LLAMA3_8B
+    model = QL.QuantLlamaModel.random_init(cfg, QL.quant_args(4, 128, 16), dev, torch.float16, seed=0, n_layers=2,
+                                           fast_attention=True)
+    for B in (1, 2):
+        outs = {}
+        for fold in (True, False):
+            if fold:
+                monkeypatch.delenv("Q100_NO_FOLD", raising=False)
+            else:
+                monkeypatch.setenv("Q100_NO_FOLD", "1")
+            dec = QL.GraphDecoder(model, B, 64)
+            dec.prime(8)
+            tok = torch.arange(B, device=dev).view(B, 1) + 11
+            toks, logits = [], []
+            for i in range(4):
+                toks.append(dec.step(tok if i == 0 else None).clone())
+                logits.append(dec.last_logits.float().clone())
+            dec.check()
+            outs[fold] = (toks, logits)
+        for la, lb in zip(outs[True][1], outs[False][1]):
+            assert (la - lb).abs().max().item() <= 0.02 * max(lb.abs().max().item(), 1.0)
