@@ -14,9 +14,9 @@ torch.cuda.synchronize(); fn(buf, 148)          # reset
 q100.gemm_wna16(x, pw, None, _lib.GEMM_FORCE_TC); torch.cuda.synchronize()
 assert fn(buf, 148) == 0
 t = np.array(buf[:], dtype=np.int64).reshape(148, 8)
-names = ["mma_warp_total", "wait d_empty", "wait a_full", "wait full_x", "issue+commit", "k-blocks", "dq warp0: waiting", "dq warp0: working"]
+names = ["mma_warp_total", "wait d_empty", "wait a_full", "wait full_x", "issue+commit", "k-blocks", "dq warp0: wait full_p", "dq warp0: wait a_empty"]
 for j, nm in enumerate(names):
     c = t[:, j]; print(f"{nm:22s} mean {c.mean():10.0f}  p50 {np.median(c):10.0f}  max {c.max():10.0f}")
 kb = t[:, 5].mean()
 print(f"per k-block (MMA warp): total {t[:,0].mean()/kb:.0f}  a_full {t[:,2].mean()/kb:.0f}  full_x {t[:,3].mean()/kb:.0f}  issue {t[:,4].mean()/kb:.0f}  d_empty/tile {t[:,1].mean()/(kb/64):.0f}")
-print(f"dequant warp 0 per own k-block: waiting {t[:,6].mean()/(kb/2):.0f}  working {t[:,7].mean()/(kb/2):.0f}")
+print(f"dequant warp 0 per own k-block: wait full_p {t[:,6].mean()/(kb/2):.0f}  wait a_empty {t[:,7].mean()/(kb/2):.0f}")
