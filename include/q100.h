@@ -242,6 +242,29 @@ int q100_gemm_wna8(const void* x, const void* row_minmax, const void* packed, co
                    int dtype, void* workspace, size_t workspace_bytes, int flags, void* stream);
 
 /*
+ * K3d -- W8A8 at prefill sizes (SmoothQuant configuration of main.py:326-349: per-channel 8-bit weights, per-token 8-bit
+ * activations) as ONE integer GEMM on the 5th-generation tensor cores (tcgen05.mma kind::i8, int32 accumulators in
+ * tensor memory).  Replaces  act_quantizer(x)  +  F.linear(x_q, w_q)  of quant/int_linear.py:59-62 for M > 15 rows.
+ *
+ *   x_packed, w_packed  the 8-bit codes of the activations [M, K] and of the weight [N, K] in the q100 packed
+ *                       layout (q100_quantize_groupwise / q100_quantize_rows_stats with group = 0, n_bits = 8,
+ *                       `packed` output): both operands are read by TMA exactly as the quantize kernels wrote them
+ *   x_meta, w_meta      [M][2] / [N][2] (scale, zero-point) in `dtype`: the `meta` output of the same calls
+ *   x_sums, w_sums      [M] / [N] int32: sum over k of each row's codes (q100_code_rowsums; the weight's once per model)
+ *   y[m, n] = s_x[m] s_w[n] (sum_k q_x q_w - z_x[m] w_sums[n] - z_w[n] (x_sums[m] - K z_x[m])) (+ bias[n]),
+ * the integer part exact (64-bit), one fp32 product and one rounding to `dtype` per output.  The reference multiplies
+ * the two fake-quantised 16-bit operands instead, i.e. it rounds (q - z) s to 16 bits on both sides first: same
+ * statement as K3c -- within the stated GEMM tolerance (tests/test_w8a8.py), not bit for bit.
+ * K % 128 == 0, K <= 32768 (int32 accumulator), N % 8 == 0.  Under tensor parallelism the sums are over the local K.
+ *
+ * q100_code_rowsums: sums_out[r] = sum_k code[r, k] for a packed 8-bit [rows, cols] matrix (cols % 64 == 0).
+ */
+int q100_gemm_w8a8(const void* x_packed, const void* x_meta, const void* x_sums, const void* w_packed,
+                   const void* w_meta, const void* w_sums, const void* bias, void* y, int64_t M, int64_t N,
+                   int64_t K, int dtype, void* stream);
+int q100_code_rowsums(const void* packed, int64_t rows, int64_t cols, void* sums_out, void* stream);
+
+/*
  * K4-K6 -- the memory-bound steps between the quantised linears of a decoder block at decode shapes
  * (QuantLlamaDecoderLayer.forward, models/int_llama_layer.py:213-262): ~35 eager launches per block and
  * token in the reference, four here.  fp16 / bf16 only; each reproduces the reference's op order and

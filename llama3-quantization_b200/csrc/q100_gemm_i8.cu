@@ -6,8 +6,8 @@
 // activations) as ONE integer GEMM: quant/int_linear.py:59-62 runs act_quantizer(x) and F.linear on the two
 // fake-quantised 16-bit tensors; here both operands stay 8-bit codes,
 //   y[m, n] = s_x[m] s_w[n] ( sum_k q_x q_w  -  z_x[m] sum_k q_w[n, k]  -  z_w[n] sum_k q_x[m, k]  +  K z_x[m] z_w[n] ),
-// the contraction exact in int32 on the tensor cores, the zero-point correction exact in (wrapping) 32-bit integer
-// arithmetic in the epilogue, one fp32 product per output.  (The reference rounds (q - z) s to 16 bits on both sides
+// the contraction exact in int32 on the tensor cores, the zero-point correction exact in 64-bit integer arithmetic in
+// the epilogue, one fp32 product per output.  (The reference rounds (q - z) s to 16 bits on both sides
 // before its GEMM: the difference is that rounding, SURVEY.md section 7 hard part 6; same statement as K3c.)
 //
 // Both operands are q100 v2 packed code matrices (q100_quantize_groupwise with group = 0, n_bits = 8): tile-major
@@ -21,8 +21,10 @@
 //   warp 1      allocates tensor memory (2 x 256 int32 columns: two accumulator stages); one elected thread issues
 //               4 x tcgen05.mma.kind::i8 (M = 128, N = 256, K = 32) per stage, tcgen05.commit frees the stage /
 //               publishes the accumulator;
-//   warps 4-7   epilogue: tcgen05.ld (lane = weight row, column = token) -> integer correction -> scale -> (+ bias) ->
-//               16 bit -> transposed through shared memory -> 16-byte stores; overlaps the next tile's MMAs.
+//   warps 4-11  epilogue (two warps per TMEM lane quarter, 128 token columns each): tcgen05.ld (lane = weight row,
+//               column = token) -> integer correction -> scale -> (+ bias) -> 16 bit -> transposed through shared
+//               memory -> 16-byte stores; overlaps the next tile's MMAs (with four warps the epilogue of a
+//               K = 4096 tile took longer than the tile's MMAs).
 #include <cstdlib>
 #include <mutex>
 
@@ -38,8 +40,8 @@ constexpr int I8_NT = 256;            // tokens per tile (UMMA N)
 constexpr int I8_TILE = 128 * 64;     // bytes of one packed [128 x 64] tile
 constexpr int I8_STAGE = 6 * I8_TILE; // two weight tiles, 2 x 2 activation tiles
 constexpr int I8_STAGES = 4;
-constexpr int I8_THREADS = 8 * 32;
-constexpr int I8_EPI = 4 * 2 * 2048;  // 4 warps x 2 buffers x [32 tokens x 32 rows] 16-bit
+constexpr int I8_THREADS = 12 * 32;
+constexpr int I8_EPI = 8 * 2048;      // 8 warps x [32 tokens x 32 rows] 16-bit
 constexpr int I8_COLP = 2 * I8_NT * 16;   // per accumulator stage: (s_x, z_x, sum q_x, K z_x) per token
 constexpr int I8_SMEM = I8_STAGES * I8_STAGE + I8_EPI + I8_COLP + 1024;
 static_assert(I8_SMEM <= 227 * 1024, "shared memory budget");
@@ -97,7 +99,10 @@ __device__ __forceinline__ void i8_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
 }
 
-template <typename T>
+// CL = cluster size: the CL CTAs of a cluster work on CL consecutive weight-row tiles of the SAME 256-token tile; each
+// loads 1/CL of the stage's activation tiles and multicasts it to all of them (the L2 -> SM traffic of one CTA per
+// stage drops from 48 KB to 16 + 32/CL KB: at the integer rate the single-CTA version asks L2 for more than it delivers).
+template <typename T, int CL>
 __global__ void __launch_bounds__(I8_THREADS, 1)
 k3_i8(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_x, const I8Args a) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -107,18 +112,23 @@ k3_i8(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensor
   __shared__ uint32_t tmem_base_s;
   const uint32_t full = smem_u32(&bars[0]), empty = full + 8 * I8_STAGES, d_full = empty + 8 * I8_STAGES, d_empty = d_full + 16;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n_ct = a.m_tiles * a.n_tiles;
+  const int rank = CL > 1 ? static_cast<int>(cluster_ctarank()) : 0;
+  const int n_groups = (a.n_tiles + CL - 1) / CL;
+  const int n_ct = a.m_tiles * n_groups;
+  const int ct0 = blockIdx.x / CL, ct_step = gridDim.x / CL;
   const int num_ks = a.K / 128;
+  constexpr uint16_t kMask = static_cast<uint16_t>((1u << CL) - 1u);
 
   if (tid == 0) {
-    for (int s = 0; s < I8_STAGES; ++s) { mbar_init(&bars[s], 1); mbar_init(&bars[I8_STAGES + s], 1); }
-    for (int d = 0; d < 2; ++d) { mbar_init(&bars[2 * I8_STAGES + d], 1); mbar_init(&bars[2 * I8_STAGES + 2 + d], 4); }
+    for (int s = 0; s < I8_STAGES; ++s) { mbar_init(&bars[s], 1); mbar_init(&bars[I8_STAGES + s], CL); }
+    for (int d = 0; d < 2; ++d) { mbar_init(&bars[2 * I8_STAGES + d], 1); mbar_init(&bars[2 * I8_STAGES + 2 + d], 8); }
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(&tmem_base_s, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (CL > 1) cluster_sync_all();                    // every CTA's barriers exist before any remote arrive
   const uint32_t tmem = tmem_base_s;
 
   if (warp == 0) {
@@ -128,20 +138,30 @@ k3_i8(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensor
       tma_prefetch_desc(&tm_x);
       const uint64_t pol_w = policy_evict_first(), pol_x = policy_evict_last();
       uint32_t it = 0;
-      for (int ct = blockIdx.x; ct < n_ct; ct += gridDim.x) {
-        const int mt = ct % a.m_tiles, nt = ct / a.m_tiles;
+      for (int ct = ct0; ct < n_ct; ct += ct_step) {
+        const int mt = ct % a.m_tiles;
+        const int nt = min((ct / a.m_tiles) * CL + rank, a.n_tiles - 1);                // ragged last group: redo the last tile
         const int xt0 = min(2 * mt, a.mt128 - 1), xt1 = min(2 * mt + 1, a.mt128 - 1);   // a missing second half: redo the first
         for (int ks = 0; ks < num_ks; ++ks, ++it) {
           const uint32_t s = it % I8_STAGES;
-          i8_wait(empty + 8 * s, ((it / I8_STAGES) & 1) ^ 1);
-          mbar_expect_tx(&bars[s], I8_STAGE);
+          i8_wait(empty + 8 * s, ((it / I8_STAGES) & 1) ^ 1);   // all CL CTAs have retired their MMAs on this stage
+          mbar_expect_tx(&bars[s], I8_STAGE);                   // own weight tiles + the whole activation part
           uint8_t* st = base_ptr + s * I8_STAGE;
+          const uint32_t st32 = base_u32 + s * I8_STAGE;
 #pragma unroll
           for (int kk = 0; kk < 2; ++kk) {
             const int kt = 2 * ks + kk;
             tma_load_2d_hint(st + kk * I8_TILE, &tm_w, &bars[s], 0, (nt * a.kt + kt) * 128, pol_w);
-            tma_load_2d_hint(st + (2 + 2 * kk) * I8_TILE, &tm_x, &bars[s], 0, (xt0 * a.kt + kt) * 128, pol_x);
-            tma_load_2d_hint(st + (3 + 2 * kk) * I8_TILE, &tm_x, &bars[s], 0, (xt1 * a.kt + kt) * 128, pol_x);
+            if (CL == 1) {
+              tma_load_2d_hint(st + (2 + 2 * kk) * I8_TILE, &tm_x, &bars[s], 0, (xt0 * a.kt + kt) * 128, pol_x);
+              tma_load_2d_hint(st + (3 + 2 * kk) * I8_TILE, &tm_x, &bars[s], 0, (xt1 * a.kt + kt) * 128, pol_x);
+            } else if (CL == 2) {                               // rank = token half, both k tiles
+              tma_load_2d_mc(st32 + (2 + 2 * kk + rank) * I8_TILE, &tm_x, full + 8 * s, 0,
+                             ((rank ? xt1 : xt0) * a.kt + kt) * 128, kMask, pol_x);
+            } else if (kk == (rank >> 1)) {                     // CL == 4: rank = (k tile, token half)
+              tma_load_2d_mc(st32 + (2 + 2 * kk + (rank & 1)) * I8_TILE, &tm_x, full + 8 * s, 0,
+                             (((rank & 1) ? xt1 : xt0) * a.kt + kt) * 128, kMask, pol_x);
+            }
           }
         }
       }
@@ -150,7 +170,7 @@ k3_i8(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensor
     // ===================== MMA issuer =====================
     constexpr uint32_t idesc = umma_idesc_u8(I8_ROWS, I8_NT);
     uint32_t it = 0, tcount = 0;
-    for (int ct = blockIdx.x; ct < n_ct; ct += gridDim.x, ++tcount) {
+    for (int ct = ct0; ct < n_ct; ct += ct_step, ++tcount) {
       const uint32_t ds = tcount & 1;
       i8_wait(d_empty + 8 * ds, ((tcount >> 1) & 1) ^ 1);     // the epilogue has drained this accumulator stage
       tc_fence_after();
@@ -168,22 +188,24 @@ k3_i8(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensor
             for (int h = 0; h < 2; ++h)                                                // K = 32 bytes per instruction
               umma_i8_ss(tmem + ds * I8_NT, ad + 2 * h, bd + 2 * h, idesc, (ks != 0 || kk != 0 || h != 0) ? 1u : 0u);
           }
-          umma_commit_u32(empty + 8 * s);
+          if (CL == 1) umma_commit_u32(empty + 8 * s);
+          else umma_commit_mc(empty + 8 * s, kMask);           // frees the stage in every CTA of the cluster
           if (ks == num_ks - 1) umma_commit_u32(d_full + 8 * ds);
         }
         __syncwarp();
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue warps (4..7): lane = weight row, columns = tokens =====================
-    const int quad = warp & 3;
-    const int et = tid - 128;                                           // 0..127 among the epilogue threads
+    // ===================== epilogue warps (4..11): lane = weight row, columns = tokens =====================
+    // two warps per TMEM lane quarter, each takes 128 of the tile's 256 token columns
+    const int quad = warp & 3, half = (warp - 4) >> 2;
+    const int et = tid - 128;                                           // 0..255 among the epilogue threads
     const T* bias = reinterpret_cast<const T*>(a.bias);
     const uint32_t lane_t = tmem + (static_cast<uint32_t>(quad * 32) << 16);
     uint32_t tcount = 0;
-    for (int ct = blockIdx.x; ct < n_ct; ct += gridDim.x, ++tcount) {
+    for (int ct = ct0; ct < n_ct; ct += ct_step, ++tcount) {
       const uint32_t ds = tcount & 1;
-      const int mt = ct % a.m_tiles, nt = ct / a.m_tiles;
+      const int mt = ct % a.m_tiles, nt = (ct / a.m_tiles) * CL + rank;   // >= n_tiles in a ragged last group: nothing to store
       const int m0 = mt * I8_NT;
       const int n = nt * I8_ROWS + quad * 32 + lane;
       const bool n_ok = n < a.N;
@@ -196,45 +218,60 @@ k3_i8(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensor
         sw = m.x; zw = __float2int_rn(m.y); Sw = a.w_sum[n];
         if (bias != nullptr) bv = DT<T>::to_f(bias[n]);
       }
-      // the tile's tokens: (s_x, z_x, sum q_x, K z_x) per column
+      const bool w_wide = static_cast<uint32_t>(zw) > 255u;
+      // the tile's tokens: (s_x, z_x, sum q_x - K z_x, zero-point outside [0, 255]) per column
       uint4* colp = reinterpret_cast<uint4*>(base_ptr + I8_STAGES * I8_STAGE + I8_EPI + ds * (I8_NT * 16));
-      for (int c = et; c < I8_NT; c += 128) {
-        const int m = m0 + c;
+      {
+        const int m = m0 + et;
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
         if (m < a.M) {
           const float2 xm = DT<T>::to_f2(reinterpret_cast<const uint32_t*>(a.x_meta)[m]);
           const int zx = __float2int_rn(xm.y);
-          v = make_uint4(__float_as_uint(xm.x), static_cast<uint32_t>(zx), static_cast<uint32_t>(a.x_sum[m]),
-                         static_cast<uint32_t>(a.K) * static_cast<uint32_t>(zx));
+          // c1 = sum q_x - K z_x fits 32 bits (|z_x| <= 1e4 by the reference's clamp, K <= 32768)
+          v = make_uint4(__float_as_uint(xm.x), static_cast<uint32_t>(zx),
+                         static_cast<uint32_t>(a.x_sum[m] - a.K * zx), static_cast<uint32_t>(zx) > 255u ? 1u : 0u);
         }
-        colp[c] = v;
+        colp[et] = v;
       }
-      asm volatile("bar.sync 2, 128;" ::: "memory");                    // the four epilogue warps
+      asm volatile("bar.sync 2, 256;" ::: "memory");                    // the eight epilogue warps
       i8_wait(d_full + 8 * ds, (tcount >> 1) & 1);
       tc_fence_after();
       T* ydst = reinterpret_cast<T*>(a.y);
       const int n_warp = nt * I8_ROWS + quad * 32;                      // first row of this warp
-      const uint32_t ebase = base_u32 + I8_STAGES * I8_STAGE + quad * (2 * 2048);
+      const uint32_t eb = base_u32 + I8_STAGES * I8_STAGE + (warp - 4) * 2048;
       const int tj = lane >> 2, rq = (lane & 3) * 8;                    // read side: token tj (+8i), rows rq..rq+7
-      const int c_end = min(I8_NT, a.M - m0);
+      const int c_lo = half * (I8_NT / 2), c_hi = min(c_lo + I8_NT / 2, a.M - m0);
+      if (c_lo >= c_hi) {                            // no token of this half exists: only hand the accumulator back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) i8_arrive(d_empty + 8 * ds);
+      }
 #pragma unroll 1
-      for (int c0 = 0; c0 < c_end; c0 += 32) {
+      for (int c0 = c_lo; c0 < c_hi; c0 += 32) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(lane_t + ds * I8_NT + c0, r);
         tmem_ld_wait();
-        if (c0 + 32 >= c_end) {                      // last chunk read: the accumulator may be overwritten
+        if (c0 + 32 >= c_hi) {                       // last chunk read: the accumulator may be overwritten
           tc_fence_before();
           __syncwarp();
           if (lane == 0) i8_arrive(d_empty + 8 * ds);
         }
-        const uint32_t eb = ebase + ((c0 >> 5) & 1) * 2048;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const uint4 cp = colp[c0 + j];                                // broadcast read
-          // sum (q_x - z_x)(q_w - z_w) = D - z_x Sw - z_w Sx + K z_x z_w: exact in wrapping 32-bit arithmetic
-          const uint32_t t = r[j] - cp.y * static_cast<uint32_t>(Sw) - static_cast<uint32_t>(zw) * cp.z +
-                             cp.w * static_cast<uint32_t>(zw);
-          const float f = fmaf(static_cast<float>(static_cast<int32_t>(t)), __uint_as_float(cp.x) * sw, bv);
+          // sum (q_x - z_x)(q_w - z_w) = D - z_x Sw - z_w (Sx - K z_x).  Zero-points in [0, 255] (a row with both signs):
+          // every term and the result fit 32 bits; otherwise (a row of one sign, zero-point up to the reference's
+          // clamp at 1e4) the same expression in 64-bit integers
+          float ti;
+          if (!(w_wide || cp.w)) {
+            ti = static_cast<float>(static_cast<int32_t>(r[j]) - static_cast<int32_t>(cp.y) * Sw -
+                                    zw * static_cast<int32_t>(cp.z));
+          } else {
+            ti = __ll2float_rn(static_cast<long long>(static_cast<int32_t>(r[j])) -
+                               static_cast<long long>(static_cast<int32_t>(cp.y)) * Sw -
+                               static_cast<long long>(zw) * static_cast<int32_t>(cp.z));
+          }
+          const float f = fmaf(ti, __uint_as_float(cp.x) * sw, bv);
           const T v = DT<T>::from_f(f);
           asm volatile("st.shared.u16 [%0], %1;" :: "r"(eb + j * 64 + lane * 2), "h"(*reinterpret_cast<const uint16_t*>(&v)) : "memory");
         }
@@ -248,14 +285,14 @@ k3_i8(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensor
           if (m < a.M && n_warp + rq < a.N)
             *reinterpret_cast<uint4*>(ydst + static_cast<int64_t>(m) * a.N + n_warp + rq) = v;
         }
-        // the buffer is reused two chunks later: the __syncwarp of the next chunk orders these reads before the
-        // writes after it
+        __syncwarp();                                                   // the buffer is rewritten by the next chunk
       }
-      asm volatile("bar.sync 2, 128;" ::: "memory");                    // colp[ds] is rewritten two tiles later; keep the warps together
+      asm volatile("bar.sync 2, 256;" ::: "memory");                    // colp[ds] is rewritten two tiles later; keep the warps together
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();                    // nobody leaves while a peer may still multicast into it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
@@ -280,24 +317,55 @@ __global__ void __launch_bounds__(128) k_code_rowsums(const uint8_t* __restrict_
   if (r < rows) atomicAdd(out + r, static_cast<int32_t>(acc));
 }
 
-template <typename T>
+template <typename T, int CL>
 int launch_i8(const CUtensorMap& tw, const CUtensorMap& tx, const I8Args& a, cudaStream_t st) {
-  auto kern = k3_i8<T>;
-  static std::mutex mu;
-  static bool attr_done[kMaxDevices] = {};
+  auto kern = k3_i8<T, CL>;
+  static std::mutex mu;                          // one per instantiation
+  static bool attr_done[kMaxDevices] = {};       // the attribute is a per-device property
+  static int max_clusters[kMaxDevices] = {};
+  const int dev = current_device();
   {
     std::lock_guard<std::mutex> lk(mu);
-    const int dev = current_device();
     if (!attr_done[dev]) {
       Q100_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, I8_SMEM));
       attr_done[dev] = true;
     }
   }
-  int grid = sm_count();
-  const int n_ct = a.m_tiles * a.n_tiles;
-  if (grid > n_ct) grid = n_ct;
-  kern<<<grid, I8_THREADS, I8_SMEM, st>>>(tw, tx, a);
-  return check_cuda(cudaGetLastError(), "k3_i8 launch");
+  const int n_ct = a.m_tiles * ((a.n_tiles + CL - 1) / CL);
+  int clusters = sm_count() / CL;
+  if (clusters > n_ct) clusters = n_ct;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(clusters * CL);
+  cfg.blockDim = dim3(I8_THREADS);
+  cfg.dynamicSmemBytes = I8_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = CL > 1 ? 1 : 0;
+  if (CL > 1) {
+    // persistent kernel: never more clusters than can be resident at once
+    std::lock_guard<std::mutex> lk(mu);
+    if (max_clusters[dev] == 0) {
+      cfg.gridDim = dim3(sm_count() / CL * CL);
+      Q100_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters[dev], kern, &cfg));
+      if (max_clusters[dev] < 1) max_clusters[dev] = 1;
+    }
+    if (clusters > max_clusters[dev]) clusters = max_clusters[dev];
+    cfg.gridDim = dim3(clusters * CL);
+  }
+  return check_cuda(cudaLaunchKernelEx(&cfg, kern, tw, tx, a), "k3_i8 launch");
+}
+
+template <typename T>
+int launch_i8_cl(const CUtensorMap& tw, const CUtensorMap& tx, const I8Args& a, cudaStream_t st) {
+  static const int env_cl = []() { const char* e = getenv("Q100_I8_CLUSTER"); return e ? atoi(e) : 0; }();   // experiments
+  int cl = env_cl ? env_cl : 2;
+  if (a.n_tiles < cl) cl = 1;
+  if (cl == 4) return launch_i8<T, 4>(tw, tx, a, st);
+  if (cl == 2) return launch_i8<T, 2>(tw, tx, a, st);
+  return launch_i8<T, 1>(tw, tx, a, st);
 }
 
 }  // namespace
@@ -354,6 +422,6 @@ extern "C" int q100_gemm_w8a8(const void* x_packed, const void* x_meta, const vo
   rc = make_tmap_2d(&tx, x_packed, 1, 64, x_rows, 64, 64, 128, 64);
   if (rc != Q100_OK) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (dtype == Q100_F16) return launch_i8<__half>(tw, tx, a, st);
-  return launch_i8<__nv_bfloat16>(tw, tx, a, st);
+  if (dtype == Q100_F16) return launch_i8_cl<__half>(tw, tx, a, st);
+  return launch_i8_cl<__nv_bfloat16>(tw, tx, a, st);
 }

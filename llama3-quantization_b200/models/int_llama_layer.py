@@ -178,8 +178,9 @@ class _FusedLinears:
         if m0.use_act_quant and not m0.disable_input_quant:
             aq0 = m0.act_quantizer
             same = all(m.act_quantizer.n_bits == aq0.n_bits and m.act_quantizer.enable == aq0.enable for m in mods)
-            if same and x.numel() // x.shape[-1] <= 15 and aq0.stat_group is None:
-                # decode shapes: activation quantisation as the prologue of the integer GEMM (K3c), one launch
+            if same and (x.numel() // x.shape[-1] <= 15 or aq0.n_bits == 8) and aq0.stat_group is None:
+                # decode shapes: activation quantisation as the prologue of the integer GEMM (K3c), one launch;
+                # W8A8 per-channel at prefill sizes: codes x codes on the integer tensor cores (K3d)
                 saved = m0.bias
                 y = m0._fused_act_gemm(x, pw, None) if saved is None else None
                 if y is not None:

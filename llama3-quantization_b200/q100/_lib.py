@@ -64,6 +64,8 @@ SIGNATURES = {
     "q100_dequantize": (_i, [_vp, _vp, _vp, _i, _i64, _i64, _i, _i, _i, _vp, _vp]),
     "q100_gemm_wna16": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _sz, _i, _vp]),
     "q100_gemm_wna8": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _i, _vp, _sz, _i, _vp]),
+    "q100_gemm_w8a8": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i, _vp]),
+    "q100_code_rowsums": (_i, [_vp, _i64, _i64, _vp, _vp]),
     "q100_gemm_workspace_bytes": (_sz, [_i64, _i64, _i64, _i, _i]),
     "q100_gemm_wna16_block": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _vp, C.c_float, _vp, _i, _vp]),
     "q100_gemm_block_fusable": (_i, [_i64, _i64, _i64, _i, _i]),

@@ -254,6 +254,7 @@ class PackedWeight:
     N: int
     K: int
     disable_zero_point: bool = False
+    code_sums: Optional[torch.Tensor] = None   # int32 [N]: sum over k of the row's 8-bit codes (K3d, filled on first use)
 
     @property
     def dtype(self) -> torch.dtype:
@@ -386,6 +387,57 @@ def gemm_wna8(x: torch.Tensor, w: PackedWeight, a_bits: int, minmax: Optional[to
         check(lib.q100_gemm_wna8(x2.data_ptr(), minmax.data_ptr(), w.packed.data_ptr(), w.meta.data_ptr(), _ptr(bias),
                                  y.data_ptr(), M, w.N, w.K, w.group, w.n_bits, int(a_bits), int(w.disable_zero_point),
                                  _DT[x.dtype], ws.data_ptr(), ws.numel(), flags, _stream(x2)))
+    return y.view(*shp[:-1], w.N)
+
+
+def code_rowsums(packed: torch.Tensor, rows: int, cols: int) -> torch.Tensor:
+    """int32 [rows]: the sum over k of every row's codes of a packed 8-bit [rows, cols] matrix (the zero-point
+    correction terms of K3d)."""
+    _require_cuda(packed)
+    out = torch.empty((rows,), dtype=torch.int32, device=packed.device)
+    with _on(packed.device):
+        check(lib.q100_code_rowsums(packed.data_ptr(), rows, cols, out.data_ptr(), _stream(packed)))
+    return out
+
+
+def gemm_w8a8_supported(rows: int, w: PackedWeight) -> bool:
+    """True when :func:`gemm_w8a8` takes ``rows`` x this weight: 8-bit per-channel codes with zero-points."""
+    return (w.n_bits == 8 and w.group == w.K and not w.disable_zero_point and w.K % 128 == 0 and w.K <= 32768
+            and w.N % 8 == 0 and rows > 0)
+
+
+def gemm_w8a8(x: torch.Tensor, w: PackedWeight, minmax: Optional[torch.Tensor] = None,
+              bias: Optional[torch.Tensor] = None, flags: int = 0) -> torch.Tensor:
+    """y = fakequant_rows(x, 8) @ dequant(w)^T for a per-channel 8-bit weight at prefill sizes (K3d): the activations are
+    quantised and packed once (K2 in pack mode; with ``minmax`` [rows, 2] the externally supplied -- all-reduced -- row
+    statistics are used), then codes x codes on the integer tensor cores (tcgen05.mma kind::i8) with the zero-point
+    terms applied in the epilogue.  ``flags``: FLAG_CUDA_SCALE for the activation quantiser."""
+    _require_cuda(x, w.packed, bias, minmax)
+    if x.dtype != w.dtype:
+        raise TypeError(f"q100.gemm_w8a8: x is {x.dtype} but the packed weight was built for {w.dtype}")
+    if x.shape[-1] != w.K:
+        raise ValueError(f"q100.gemm_w8a8: x has K={x.shape[-1]}, expected {w.K}")
+    if not gemm_w8a8_supported(1, w):
+        raise ValueError("q100.gemm_w8a8: per-channel 8-bit weights with zero-points, K % 128 == 0, N % 8 == 0")
+    shp = x.shape
+    x2 = x.contiguous().view(-1, w.K)
+    M = x2.shape[0]
+    y = torch.empty((M, w.N), dtype=x.dtype, device=x.device)
+    if M == 0:
+        return y.view(*shp[:-1], w.N)
+    if minmax is None:
+        r = quantize_groupwise(x2, 0, 8, want_dequant=False, want_packed=True, want_meta=True, flags=flags)
+    else:
+        r = quantize_rows_stats(x2, minmax, 8, want_dequant=False, want_packed=True, want_meta=True, flags=flags)
+    xs = code_rowsums(r.packed, M, w.K)
+    if w.code_sums is None:
+        w.code_sums = code_rowsums(w.packed, w.N, w.K)
+    if bias is not None:
+        bias = bias.to(x.dtype).contiguous()
+    with _on(x.device):
+        check(lib.q100_gemm_w8a8(r.packed.data_ptr(), r.meta.data_ptr(), xs.data_ptr(), w.packed.data_ptr(),
+                                 w.meta.data_ptr(), w.code_sums.data_ptr(), _ptr(bias), y.data_ptr(), M, w.N, w.K,
+                                 _DT[x.dtype], _stream(x2)))
     return y.view(*shp[:-1], w.N)
 
 

@@ -127,22 +127,36 @@ class QuantLinear(nn.Module):
 
     def _fused_act_gemm(self, x: torch.Tensor, packed, bias):
         """W8A8 / W4A4 at decode shapes: the per-token activation quantisation runs as the prologue of the integer
-        dequant-GEMM (K3c, q100_gemm_wna8) instead of as a K2 launch in front of a 16-bit-activation GEMM.  None when the
-        case does not qualify (then forward() takes the reference's two steps)."""
+        dequant-GEMM (K3c, q100_gemm_wna8) instead of as a K2 launch in front of a 16-bit-activation GEMM.  W8A8 with
+        per-channel weights at more than 15 rows: K2 in pack mode + the integer GEMM K3d (q100_gemm_w8a8).  None when
+        the case does not qualify (then forward() takes the reference's two steps)."""
         aq = self.act_quantizer
+        rows = x.numel() // x.shape[-1] if x.dim() else 0
         if (packed is None or aq is None or not aq.enable or aq.n_bits > 8 or aq.symmetric or aq.group_size
                 or aq.disable_zero_point or aq.lwc or aq.metric == "fix0to1" or packed.n_bits not in (4, 8)
-                or packed.group % 128 != 0 or not self._fused_ok(x, packed) or x.numel() // x.shape[-1] > 15
+                or packed.group % 128 != 0 or not self._fused_ok(x, packed)
                 or (torch.is_grad_enabled() and x.requires_grad)):
             return None
-        mm = _ops.rows_minmax(x)
+        # more than 15 rows: K3d (codes x codes on tcgen05 kind::i8) for the W8A8 per-channel configuration; everything
+        # else keeps the reference's two steps at these sizes
+        prefill = rows > 15
+        if prefill and not (aq.n_bits == 8 and _ops.gemm_w8a8_supported(rows, packed)):
+            return None
+        from q100._lib import FLAG_CUDA_SCALE
+        fl = FLAG_CUDA_SCALE if aq.cuda_eager_scale else 0
+        mm = None
+        tp_stats = False
         if aq.stat_group is not None:
             import torch.distributed as dist
-            if dist.is_initialized() and dist.get_world_size(aq.stat_group) > 1:
+            tp_stats = dist.is_initialized() and dist.get_world_size(aq.stat_group) > 1
+        if tp_stats or not prefill:
+            mm = _ops.rows_minmax(x)
+            if tp_stats:
                 from q100 import tp as _tp
                 mm = _tp.allreduce_minmax(mm, aq.stat_group)
-        from q100._lib import FLAG_CUDA_SCALE
-        return _ops.gemm_wna8(x, packed, aq.n_bits, mm, bias, FLAG_CUDA_SCALE if aq.cuda_eager_scale else 0)
+        if prefill:
+            return _ops.gemm_w8a8(x, packed, mm, bias, fl)
+        return _ops.gemm_wna8(x, packed, aq.n_bits, mm, bias, fl)
 
     def release_dense_weight(self) -> bool:
         """Inference-only extension: free the dense fake-quantised ``weight`` buffer and keep only its

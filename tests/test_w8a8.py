@@ -81,3 +81,86 @@ def test_quantlinear_takes_the_fused_path_at_decode_shapes():
         y_ref = ql(x)                                     # act fake-quant + F.linear on the dense fake-quantised weight
     assert y_fused.shape == y_ref.shape
     assert float((y_fused.float() - y_ref.float()).abs().max()) <= 2e-2 * float(y_ref.float().abs().max())
+
+
+# ------------------------------------------------------------------------------------------------ K3d (prefill sizes)
+@pytest.mark.parametrize("dtype", ["f16", "bf16"])
+@pytest.mark.parametrize("M,N,K", [(16, 512, 1024), (100, 520, 1024), (257, 6144, 4096), (2048, 4096, 4096),
+                                   (2048, 14336, 4096), (2048, 4096, 14336), (4100, 1024, 8192)])
+def test_gemm_w8a8_prefill(dtype, M, N, K):
+    """K3d, q100_gemm_w8a8: 8-bit codes x 8-bit codes on tcgen05 kind::i8 (per-channel weights, per-token activations).
+    Same two references as K3c above; the token rows include one-signed rows (zero-points outside [0, 255])."""
+    if dtype == "bf16" and M * N * K > 2048 * 4096 * 4096:
+        pytest.skip("largest shapes: fp16 only")
+    dt = TDT[dtype]
+    g = torch.Generator(device="cuda").manual_seed(N + K + M)
+    w = (torch.randn(N, K, generator=g, device="cuda") * 0.02).to(dt)
+    x = (torch.randn(M, K, generator=g, device="cuda") * (1 + torch.rand(M, 1, generator=g, device="cuda") * 3)).to(dt)
+    x[:, ::97] *= 6.0
+    x[3] = x[3].abs() + 2.0                               # zero-point < 0
+    x[5] = -x[5].abs() - 8.0                              # zero-point > 255
+    w[7] = w[7].abs() + 0.02
+    bias = (torch.randn(N, generator=g, device="cuda") * 0.1).to(dt) if N == 520 else None
+    pw, rw = q100.pack_weight(w, 8, None, want_dequant=True)
+    xq = ops.fakequant_rows(x, 8)
+    y = ops.gemm_w8a8(x, pw, bias=bias)
+    torch.cuda.synchronize()
+    qw = interop.unpack_codes(pw.packed, N, K, 8).double()
+    assert torch.equal(ops.code_rowsums(pw.packed, N, K).long(), qw.sum(1).long())
+    sw, zw = pw.scales.double().view(N, 1), pw.zeros.double().view(N, 1)
+    sx, zx = xq.scales.double().view(M, 1), xq.zeros.double().view(M, 1)
+    rq = ops.quantize_groupwise(x, 0, 8, want_dequant=True, want_packed=True)
+    assert torch.equal(rq.dequant.view(torch.int16), xq.dequant.view(torch.int16))
+    qx = interop.unpack_codes(rq.packed, M, K, 8).double()
+    wd, xd = (qw - zw) * sw, (qx - zx) * sx
+    exact = xd @ wd.T
+    mag = xd.abs() @ wd.abs().T
+    if bias is not None:
+        exact = exact + bias.double()
+        mag = mag + bias.double().abs()
+    err = (y.double() - exact).abs()
+    # the integer part is exact; what is left is one fp32 product of the scales, one fma and the rounding to 16 bits
+    tol = 1.01 * EPS_OUT[dtype] * exact.abs() + 4 * 2.0 ** -24 * mag + 1e-7
+    assert bool((err <= tol).all()), f"vs exact integer product: max err {float(err.max()):.3e}, {int((err > tol).sum())} outside"
+    ref = xq.dequant.double() @ rw.dequant.double().T
+    if bias is not None:
+        ref = ref + bias.double()
+    tol2 = 2 * EPS_OUT[dtype] * ref.abs() + 16 * EPS_OP[dtype] * torch.sqrt((xd ** 2) @ (wd ** 2).T) + 16 * 2.0 ** -24 * mag + 1e-6
+    err2 = (y.double() - ref).abs()
+    assert bool((err2 <= tol2).all()), f"vs fake-quant F.linear: max err {float(err2.max()):.3e}, {int((err2 > tol2).sum())} outside"
+
+
+def test_gemm_w8a8_external_stats_match_single_pass():
+    """Row statistics supplied from outside (the tensor-parallel route: MIN / MAX all-reduced) give the same bits."""
+    g = torch.Generator(device="cuda").manual_seed(5)
+    w = (torch.randn(1024, 2048, generator=g, device="cuda") * 0.02).half()
+    x = torch.randn(300, 2048, generator=g, device="cuda").half()
+    pw, _ = q100.pack_weight(w, 8, None)
+    y0 = ops.gemm_w8a8(x, pw)
+    y1 = ops.gemm_w8a8(x, pw, minmax=ops.rows_minmax(x))
+    assert torch.equal(y0, y1)
+
+
+def test_quantlinear_takes_k3d_at_prefill_shapes():
+    """QuantLinear.forward with W8A8 per-channel and more than 15 rows runs K3d; agrees with the reference's two steps."""
+    from quant.int_linear import QuantLinear
+    lin = torch.nn.Linear(1024, 512, bias=True, device="cuda", dtype=torch.float16)
+    ql = QuantLinear(lin, {"n_bits": 8, "per_channel_axes": [0], "symmetric": False, "dynamic_method": "per_channel",
+                           "group_size": None, "lwc": False, "disable_zero_point": False},
+                     {"n_bits": 8, "per_channel_axes": [], "symmetric": False, "dynamic_method": "per_token"})
+    calls = []
+    orig = ops.gemm_w8a8
+    with torch.no_grad():
+        ql.weight = ql.weight_quantizer(ql.weight)
+        ql.set_quant_state(False, True)
+        x = torch.randn(3, 50, 1024, device="cuda").half()
+        try:
+            ops.gemm_w8a8 = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
+            y_fused = ql(x)
+        finally:
+            ops.gemm_w8a8 = orig
+        ql.use_fused_gemm = False
+        y_ref = ql(x)
+    assert calls, "K3d was not taken"
+    assert y_fused.shape == y_ref.shape
+    assert float((y_fused.float() - y_ref.float()).abs().max()) <= 2e-2 * float(y_ref.float().abs().max())
