@@ -672,12 +672,55 @@ def run_ours(args):
     # =============== whole model: random-init LLaMA3-8B W4A16 g128, tensor parallel ===========
     model_res = model70_res = None
     cfg4_res = None
+    extra = {"llama3_8b": None, "llama3_8b_smoothquant_configs": None, "llama3_70b": None}
+
+    def make_line(note=None):
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": WORKLOAD_CONFIG(M_PRE, world),
+                "notes": {"l2": "3 weight sets rotated; per-step working set (109 MB packed weights + 270 MB "
+                                "activations/outputs) exceeds the 126 MB L2", "force_skinny": bool(flags),
+                          "row_parallel_reduce": ("fused: scatter epilogue + reduce/broadcast over peer memory (K7b)"
+                                                  if scatter is not None else "NCCL all-reduce") if world > 1 else None},
+                "roofline": roofline, "decode": decode, "quantize": quant, "strong_scaling": strong,
+                "llama3_8b": extra["llama3_8b"], "llama3_8b_smoothquant_configs": extra["llama3_8b_smoothquant_configs"],
+                "llama3_70b": extra["llama3_70b"],
+                "cpu_baseline": cpu_base, "gpu_eager_reference_ops": gpu_eager, "e2e": e2e,
+                "gpu_launches": n_launch, "clocks": clocks, "peaks": P}
+        if note:
+            line["notes"]["model_rows"] = note
+        return line
+
+    # the whole-model rows are extras of the line: if one of them gets stuck (a lost rank, a collective that never
+    # completes) the contract line still goes out with the rows that finished, and every rank leaves
+    import threading
+    budget_s = float(os.environ.get("Q100_BENCH_MODEL_BUDGET_S", "900"))
+    done_flag = threading.Event()
+
+    def _deadline():
+        if done_flag.is_set():
+            return
+        if rank == 0:
+            print(json.dumps(make_line(f"cut off after {budget_s:.0f} s: unfinished rows are null")), flush=True)
+        os._exit(0)
+    wd = threading.Timer(budget_s if rank == 0 else budget_s + 10.0, _deadline)
+    wd.daemon = True
+    wd.start()
     if not os.environ.get("Q100_BENCH_SKIP_MODEL"):
         blocks.clear()
         fblocks.clear()
         torch.cuda.empty_cache()
         import bench_model
-        model_res = bench_model.run(bench_model.default_args(ppl_samples=1, ppl_ref=True), dev, rank, world)
+        def row(**kw):
+            try:
+                return bench_model.run(bench_model.default_args(**kw), dev, rank, world)
+            except Exception as ex:                                   # noqa: BLE001 -- the row is reported as failed, the line survives
+                import traceback
+                traceback.print_exc(file=sys.stderr)
+                return {"error": f"{type(ex).__name__}: {ex}"[:400]}
+        model_res = row(ppl_samples=1, ppl_ref=True)
+        extra["llama3_8b"] = model_res
         # SURVEY 8d config 5 (BASELINE.json configs[4]): LLaMA3-70B W4A16 g128, tensor parallel over all ranks (the
         # packed model is 38 GB: it also fits one B200, so the row exists at every N).  Perplexity is compared on the
         # first 4 blocks (the fp16 reference of all 80 does not fit next to the model).
@@ -688,33 +731,24 @@ def run_ours(args):
         if not os.environ.get("Q100_BENCH_SKIP_CFG4"):
             for tag, wb, ab in (("w8a8", 8, 8), ("w4a4", 4, 4)):
                 torch.cuda.empty_cache()
-                cfg4_res[tag] = bench_model.run(bench_model.default_args(wbits=wb, abits=ab, group=0, ppl_samples=1,
-                                                                         ppl_ref=True, batches="1,8", decode_steps=24),
-                                                dev, rank, world)
+                cfg4_res[tag] = row(wbits=wb, abits=ab, group=0, ppl_samples=1, ppl_ref=True, batches="1,8", decode_steps=24)
+                extra["llama3_8b_smoothquant_configs"] = dict(cfg4_res)
+        extra["llama3_8b_smoothquant_configs"] = cfg4_res
         model70_res = None
         if not os.environ.get("Q100_BENCH_SKIP_70B"):
             torch.cuda.empty_cache()
-            model70_res = bench_model.run(bench_model.default_args(model="70b", ppl_samples=1, ppl_ref=True, ppl_layers=4,
-                                                                   batches="1,16", decode_steps=24), dev, rank, world)
+            model70_res = row(model="70b", ppl_samples=1, ppl_ref=True, ppl_layers=4, batches="1,16", decode_steps=24)
+            extra["llama3_70b"] = model70_res
 
     if world > 1:
         from q100 import peer as _peer
         _one = _peer.get(None)
         if _one is not None:
             _one.check()                                            # a timed-out peer all-reduce voids the decode numbers
+    done_flag.set()
+    wd.cancel()
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-                "config": WORKLOAD_CONFIG(M_PRE, world),
-                "notes": {"l2": "3 weight sets rotated; per-step working set (109 MB packed weights + 270 MB "
-                                "activations/outputs) exceeds the 126 MB L2", "force_skinny": bool(flags),
-                          "row_parallel_reduce": ("fused: scatter epilogue + reduce/broadcast over peer memory (K7b)"
-                                                  if scatter is not None else "NCCL all-reduce") if world > 1 else None},
-                "roofline": roofline, "decode": decode, "quantize": quant, "strong_scaling": strong,
-                "llama3_8b": model_res, "llama3_8b_smoothquant_configs": cfg4_res, "llama3_70b": model70_res,
-                "cpu_baseline": cpu_base, "gpu_eager_reference_ops": gpu_eager, "e2e": e2e,
-                "gpu_launches": n_launch, "clocks": clocks, "peaks": P}
+        line = make_line()
         print(json.dumps(line), flush=True)
     if world > 1:
         _teardown_distributed()

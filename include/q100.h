@@ -294,6 +294,23 @@ int q100_rope_kv_decode(const void* qkv, const void* cos_cache, const void* sin_
                         int batch, int heads, int kv_heads, int head_dim, int64_t max_len,
                         int64_t rope_len, void* err_flag, int dtype, void* stream);
 /*
+ * K8 -- q100_attn_decode: the whole attention core of a decode step in one launch (decode
+ *   form): rotary on q / k of the new token, cache append (as q100_rope_kv_decode above), then
+ *   softmax(q k^T / sqrt(head_dim)) v over the cache positions 0..position of each sequence -- the static-cache form
+ *   of int_llama_layer.py:114-172 with the causal mask (every slot up to the new token visible, none behind it) --
+ *   with scores / softmax / P.V in fp32 from the 16-bit q, k, v (what scaled_dot_product_attention computes from the
+ *   same tensors, up to the order of the fp32 sums).  out [batch, heads * head_dim] is the row o_proj reads
+ *   (int_llama_layer.py:170-172).  Flash-decoding: the positions are split over CTAs, the last CTA of a
+ *   (sequence, kv head) merges the partials; `workspace` (q100_attn_decode_workspace_bytes; zero-filled once by the
+ *   caller, left zeroed) holds the arrival counters and the partials and may be shared by all blocks of a model on
+ *   one stream.  head_dim == 128, heads / kv_heads in {1, 2, 3, 4, 8}.  Position errors as q100_rope_kv_decode.
+ */
+size_t q100_attn_decode_workspace_bytes(int batch, int heads, int kv_heads, int64_t max_len);
+int q100_attn_decode(const void* qkv, const void* cos_cache, const void* sin_cache, const void* position,
+                     void* k_cache, void* v_cache, void* out, void* workspace, size_t workspace_bytes,
+                     int batch, int heads, int kv_heads, int head_dim, int64_t max_len, int64_t rope_len,
+                     void* err_flag, int dtype, void* stream);
+/*
  * q100_rope_qkv_prefill: the same step for q_len new tokens per sequence (prefill / calibration forward):
  *   qkv [batch, q_len, (heads + 2*kv_heads) * head_dim]; position_ids int64 on the device, element
  *   [b * pos_batch_stride + t] (stride 0 = one row shared by the batch, the reference's [1, q_len] form);

@@ -446,7 +446,20 @@ class QuantLlamaDecoderLayer(nn.Module):
 
     # ------------------------------------------------------------------ fused decode step (extension)
     @torch.no_grad()
-    def decode_step_fused(self, x, residual, kv: "StaticKV", position, attention_mask, err_flag=None):
+    def _decode_attention(self, qkv, rc, position, kv, nh, nkv, attention_mask, err_flag, causal_cache):
+        """rotary + cache append + single-token attention on the fused q|k|v row: ONE launch (K8, q100_attn_decode) when
+        the caller states that ``attention_mask`` is the plain static-cache mask (``causal_cache``: every slot up to the
+        position visible), else K5 + scaled_dot_product_attention with the mask.  Returns [bsz, nh * head_dim]."""
+        import os
+        hd = self.self_attn.head_dim
+        if causal_cache and _ops.attn_decode_supported(nh, nkv, hd) and not os.environ.get("Q100_NO_K8"):
+            return _ops.attn_decode(qkv, rc[0], rc[1], position, kv.k, kv.v, nh, nkv, err_flag)
+        q = _ops.rope_kv_decode(qkv, rc[0], rc[1], position, kv.k, kv.v, nh, nkv, err_flag)
+        att = F.scaled_dot_product_attention(q, kv.k, kv.v, attn_mask=attention_mask, enable_gqa=nh != nkv)
+        return att.reshape(q.shape[0], nh * hd)
+
+    def decode_step_fused(self, x, residual, kv: "StaticKV", position, attention_mask, err_flag=None,
+                          causal_cache: bool = False):
         """One new token per sequence through this block in 4 GEMM launches + 4 small kernels + the
         attention core, on a static KV cache (CUDA-graph friendly).  Same arithmetic as ``forward`` with
         ``past_key_value=kv`` (tests/test_block.py compares the two); what moves is where the residual add
@@ -461,7 +474,7 @@ class QuantLlamaDecoderLayer(nn.Module):
         bsz = x.shape[0]
         nh = attn.num_heads // attn.tp_world
         nkv = max(attn.num_key_value_heads // attn.tp_world, 1)
-        folded = self._decode_step_folded(x, residual, kv, position, attention_mask, err_flag, nh, nkv)
+        folded = self._decode_step_folded(x, residual, kv, position, attention_mask, err_flag, nh, nkv, causal_cache)
         if folded is not None:
             return folded
         h0, n1 = _ops.add_rmsnorm(x, self.input_layernorm.weight, self.input_layernorm.variance_epsilon, residual)
@@ -472,8 +485,7 @@ class QuantLlamaDecoderLayer(nn.Module):
         if rc is None or rc[0].dtype != x.dtype or rc[0].shape[0] < kv.k.shape[-2] or rc[0].device != x.device:
             cos, sin = attn.rotary_emb(kv.v, seq_len=kv.k.shape[-2])
             rc = attn._rope16 = (cos.to(x.dtype).contiguous(), sin.to(x.dtype).contiguous())
-        q = _ops.rope_kv_decode(qkv, rc[0], rc[1], position, kv.k, kv.v, nh, nkv, err_flag)
-        att = F.scaled_dot_product_attention(q, kv.k, kv.v, attn_mask=attention_mask, enable_gqa=nh != nkv)
+        att = self._decode_attention(qkv, rc, position, kv, nh, nkv, attention_mask, err_flag, causal_cache)
         o = attn.o_proj(att.reshape(bsz, 1, nh * attn.head_dim))
         if attn.tp_world > 1 and not attn.o_proj.reduced:
             o = _tp.reduce_output(o, _tp.ROW, attn.tp_group)
@@ -487,7 +499,7 @@ class QuantLlamaDecoderLayer(nn.Module):
             d = _tp.reduce_output(d, _tp.ROW, mlp.tp_group)
         return d, h1
 
-    def _decode_step_folded(self, x, residual, kv, position, attention_mask, err_flag, nh, nkv):
+    def _decode_step_folded(self, x, residual, kv, position, attention_mask, err_flag, nh, nkv, causal_cache=False):
         """The decode step in 4 GEMM launches + K5 + the attention core: both RMSNorms run inside the x staging of the
         GEMM that consumes them and both residual adds inside the epilogue of the GEMM that produces the summand
         (q100_gemm_wna16_block: the row-owner kernel K3r, batch <= 2, W4 g128, one GPU).  Takes and returns the
@@ -516,9 +528,8 @@ class QuantLlamaDecoderLayer(nn.Module):
             rc = attn._rope16 = (cos.to(x.dtype).contiguous(), sin.to(x.dtype).contiguous())
         ln1, ln2 = self.input_layernorm, self.post_attention_layernorm
         qkv = _ops.gemm_wna16_block(h, wqkv, norm_weight=ln1.weight, eps=ln1.variance_epsilon)
-        q = _ops.rope_kv_decode(qkv, rc[0], rc[1], position, kv.k, kv.v, nh, nkv, err_flag)
-        att = F.scaled_dot_product_attention(q, kv.k, kv.v, attn_mask=attention_mask, enable_gqa=nh != nkv)
-        h1 = _ops.gemm_wna16_block(att.reshape(bsz, nh * attn.head_dim), wo, attn.o_proj.bias, residual=h)
+        att = self._decode_attention(qkv, rc, position, kv, nh, nkv, attention_mask, err_flag, causal_cache)
+        h1 = _ops.gemm_wna16_block(att, wo, attn.o_proj.bias, residual=h)
         gu = _ops.gemm_wna16_block(h1, wgu, norm_weight=ln2.weight, eps=ln2.variance_epsilon)
         h2 = _ops.gemm_wna16_block(gu, wd, mlp.down_proj.bias, flags=_GEMM_X_GATE_UP, residual=h1)
         attn.o_proj.reduced = mlp.down_proj.reduced = False

@@ -77,6 +77,8 @@ SIGNATURES = {
     "q100_chain_error": (_i, [_vp, _vp]),
     "q100_add_rmsnorm": (_i, [_vp, _vp, _vp, C.c_float, _vp, _vp, _i64, _i64, _i, _vp]),
     "q100_rope_kv_decode": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i64, _i64, _vp, _i, _vp]),
+    "q100_attn_decode_workspace_bytes": (_sz, [_i, _i, _i, _i64]),
+    "q100_attn_decode": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i64, _i64, _vp, _i, _vp]),
     "q100_rope_qkv_prefill": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _i64, _vp, _i, _vp]),
     "q100_silu_mul": (_i, [_vp, _vp, _i64, _i64, _i, _vp]),
     "q100_allreduce_oneshot": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp]),

@@ -343,7 +343,8 @@ class GraphDecoder:
         mask = mask.expand(self.bsz, 1, 1, self.max_len)
         res = None                  # residual stream, kept apart from the last MLP output on the fused route
         for layer, kv in zip(m.layers, self.caches):
-            out = layer.decode_step_fused(x, res, kv, self.pos, mask, self.err) if self.fused else None
+            # `mask` IS the plain static-cache mask: the block may run its attention core as K8 (one launch)
+            out = layer.decode_step_fused(x, res, kv, self.pos, mask, self.err, causal_cache=True) if self.fused else None
             if out is not None:
                 x, res = out
             else:

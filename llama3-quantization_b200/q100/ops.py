@@ -483,6 +483,46 @@ def rope_kv_decode(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, posi
     return q
 
 
+_ATTN_WS: dict = {}
+
+
+def attn_decode(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, position: torch.Tensor,
+                k_cache: torch.Tensor, v_cache: torch.Tensor, heads: int, kv_heads: int,
+                err_flag: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """The attention core of a decode step in one launch (K8): rotary on q / k of one new token per sequence, append of
+    k, v to the static cache at ``position`` and softmax(q k^T / sqrt(d)) v over the slots 0..position.  Returns
+    [batch, heads * head_dim] (what o_proj reads).  ``position``: int64 scalar on the device, shared by the batch."""
+    _require_cuda(qkv, cos, sin, position, k_cache, v_cache)
+    bsz, hd, max_len = k_cache.shape[0], k_cache.shape[-1], k_cache.shape[-2]
+    qkv = qkv.contiguous()
+    if qkv.numel() != bsz * (heads + 2 * kv_heads) * hd or position.dtype != torch.int64:
+        raise ValueError("q100.attn_decode: qkv must be [batch, (heads + 2 kv_heads) * head_dim], position int64")
+    if cos.dtype != qkv.dtype or cos.shape[-1] != hd or not cos.is_contiguous() or not sin.is_contiguous():
+        raise ValueError("q100.attn_decode: cos/sin cache must be contiguous [pos, head_dim] in the model dtype")
+    if not (k_cache.is_contiguous() and v_cache.is_contiguous()) or k_cache.dtype != qkv.dtype:
+        raise ValueError("q100.attn_decode: contiguous [batch, kv_heads, max_len, head_dim] caches in the model dtype")
+    dev = qkv.device
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream, bsz, heads, kv_heads, max_len)
+    ws = _ATTN_WS.get(key)
+    if ws is None:
+        ws = torch.zeros(int(lib.q100_attn_decode_workspace_bytes(bsz, heads, kv_heads, max_len)), dtype=torch.uint8,
+                         device=dev)
+        _ATTN_WS[key] = ws
+    if out is None:
+        out = torch.empty((bsz, heads * hd), dtype=qkv.dtype, device=dev)
+    with _on(dev):
+        check(lib.q100_attn_decode(qkv.data_ptr(), cos.data_ptr(), sin.data_ptr(), position.data_ptr(),
+                                   k_cache.data_ptr(), v_cache.data_ptr(), out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                   bsz, heads, kv_heads, hd, max_len, cos.shape[0], _ptr(err_flag), _DT[qkv.dtype],
+                                   _stream(qkv)))
+    return out
+
+
+def attn_decode_supported(heads: int, kv_heads: int, head_dim: int) -> bool:
+    rep = heads // max(kv_heads, 1)
+    return head_dim == 128 and kv_heads > 0 and heads % kv_heads == 0 and rep in (1, 2, 3, 4, 8)
+
+
 def rope_qkv_prefill(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, position_ids: torch.Tensor,
                      heads: int, kv_heads: int, err_flag: Optional[torch.Tensor] = None):
     """Rotary on q / k of ``q_len`` new tokens per sequence and the head-major layouts the attention core reads (K5p).

@@ -234,3 +234,66 @@ def test_block_prefill_kernels_match_eager_formulation(dtype, use_cache, monkeyp
         # the norm in front differs by the order of its fp32 sum (<= 1 ulp of n1), so k / v agree to GEMM round-off
         assert torch.allclose(v.float(), v_ref.float(), rtol=0, atol=8 * _ulp(dtype) * v_ref.float().abs().max().item())
         assert torch.allclose(k.float(), k_ref.float(), rtol=0, atol=8 * _ulp(dtype) * k_ref.float().abs().max().item())
+
+
+# ------------------------------------------------------------------------------------------------ K8 (decode attention)
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("bsz,heads,kvh", [(1, 32, 8), (2, 32, 8), (16, 32, 8), (1, 64, 8), (3, 4, 1), (2, 8, 8), (1, 6, 2)])
+@pytest.mark.parametrize("max_len,pos", [(512, 0), (512, 5), (512, 63), (512, 64), (512, 256), (512, 511),
+                                         (4096, 1000), (4096, 4095)])
+def test_attn_decode_matches_k5_plus_reference_attention(dtype, bsz, heads, kvh, max_len, pos):
+    """K8 = K5 (bit-exact cache append) + softmax(q k^T / sqrt(d)) v over slots 0..pos in fp32 from the 16-bit q, k, v
+    (int_llama_layer.py:136-163 on the static cache); the output agrees within the rounding of the 16-bit result."""
+    from q100 import ops
+    if bsz == 16 and max_len == 4096 and dtype == torch.bfloat16:
+        pytest.skip("covered by fp16")
+    dev = torch.device("cuda:0")
+    hd = 128
+    g = torch.Generator(device=dev).manual_seed(bsz * 131 + heads + pos)
+    qkv = torch.randn(bsz, (heads + 2 * kvh) * hd, generator=g, device=dev).to(dtype)
+    cos, sin = LP.rotary_cache(hd, max_len, 500000.0, dev, dtype)
+    cos, sin = cos.contiguous(), sin.contiguous()
+    kc = torch.randn(bsz, kvh, max_len, hd, generator=g, device=dev).to(dtype)
+    vc = torch.randn(bsz, kvh, max_len, hd, generator=g, device=dev).to(dtype)
+    kc[:, :, pos + 1:] = 1000.0                          # slots behind the new token must not be read
+    vc[:, :, pos + 1:] = 1000.0
+    kc2, vc2 = kc.clone(), vc.clone()
+    p = torch.tensor([[pos]], device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    out = ops.attn_decode(qkv, cos, sin, p, kc, vc, heads, kvh, err)
+    q = ops.rope_kv_decode(qkv, cos, sin, p, kc2, vc2, heads, kvh)
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0
+    assert torch.equal(kc, kc2) and torch.equal(vc, vc2)
+    rep = heads // kvh
+    k = kc2[:, :, :pos + 1].float().repeat_interleave(rep, dim=1)
+    v = vc2[:, :, :pos + 1].float().repeat_interleave(rep, dim=1)
+    s = (q.float() @ k.transpose(-1, -2)) / math.sqrt(hd)
+    ref = (torch.softmax(s, dim=-1) @ v).reshape(bsz, heads * hd)
+    assert out.shape == ref.shape
+    tol = _ulp(dtype) * ref.abs() + 2e-5 * v.abs().amax()
+    bad = (out.float() - ref).abs() > tol
+    assert not bool(bad.any()), f"{int(bad.sum())} outside, max err {(out.float() - ref).abs().max().item():.3e}"
+    # a second call on the same workspace (the counters must have been left zeroed)
+    out2 = ops.attn_decode(qkv, cos, sin, p, kc, vc, heads, kvh, err)
+    assert torch.equal(out, out2)
+
+
+@pytest.mark.parametrize("pos", [-1, 512, 10 ** 6, 300])
+def test_attn_decode_position_outside_cache(pos):
+    from q100 import ops
+    dev = torch.device("cuda:0")
+    bsz, heads, kvh, hd, max_len, rope_len = 2, 8, 2, 128, 512, 256
+    qkv = torch.randn(bsz, (heads + 2 * kvh) * hd, device=dev).half()
+    cos, sin = LP.rotary_cache(hd, rope_len, 500000.0, dev, torch.float16)
+    kc = torch.full((bsz, kvh, max_len, hd), 7.0, dtype=torch.float16, device=dev)
+    vc = torch.full_like(kc, 7.0)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    ops.attn_decode(qkv, cos.contiguous(), sin.contiguous(), torch.tensor([[pos]], device=dev), kc, vc, heads, kvh, err)
+    torch.cuda.synchronize()
+    assert int(err.item()) == 1
+    assert bool((kc == 7.0).all()) and bool((vc == 7.0).all())
+    # the next good call works (no counter was left behind)
+    err.zero_()
+    out = ops.attn_decode(qkv, cos.contiguous(), sin.contiguous(), torch.tensor([[3]], device=dev), kc, vc, heads, kvh, err)
+    assert int(err.item()) == 0 and bool(torch.isfinite(out).all())
