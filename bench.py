@@ -681,7 +681,9 @@ def run_ours(args):
                 "config": WORKLOAD_CONFIG(M_PRE, world),
                 "notes": {"l2": "3 weight sets rotated; per-step working set (109 MB packed weights + 270 MB "
                                 "activations/outputs) exceeds the 126 MB L2", "force_skinny": bool(flags),
-                          "row_parallel_reduce": ("fused: scatter epilogue + reduce/broadcast over peer memory (K7b)"
+                          "row_parallel_reduce": (("through the switch: multimem.ld_reduce + multimem.st on the GEMM output "
+                                                   "(K7c)" if type(scatter).__name__ == "MulticastReduce" else
+                                                   "fused: scatter epilogue + reduce/broadcast over peer memory (K7b)")
                                                   if scatter is not None else "NCCL all-reduce") if world > 1 else None},
                 "roofline": roofline, "decode": decode, "quantize": quant, "strong_scaling": strong,
                 "llama3_8b": extra["llama3_8b"], "llama3_8b_smoothquant_configs": extra["llama3_8b_smoothquant_configs"],

@@ -451,6 +451,16 @@ int q100_gemm_wna16_scatter(const void* x, const void* packed, const void* meta,
                             int world, void* stream);
 int q100_reduce_bcast(const void* stage, const void* peer_y, const void* peer_flags, void* epoch, int64_t rows_per,
                       int64_t N, int dtype, int rank, int world, void* err_flag, void* stream);
+/*
+ * K7c -- q100_allreduce_multimem: in-place all-reduce(sum) of a [world * rows_per, N] tensor that every rank holds in
+ * a symmetric buffer with a MULTICAST mapping (NVSwitch): rank r reduces its rows through the switch
+ * (multimem.ld_reduce, fp32 accumulation) and writes them into every rank's copy (multimem.st).  `mc_buf` is the
+ * multicast address of the buffer (torch symmetric memory: handle.multicast_ptr), `peer_flags` / `epoch` / `err_flag`
+ * as q100_reduce_bcast.  No counterpart in the reference (parallel_utils.py only places layers); the all-reduce
+ * after the row-parallel o_proj / down_proj of a tensor-parallel block at prefill sizes.
+ */
+int q100_allreduce_multimem(void* mc_buf, const void* peer_flags, void* epoch, int64_t rows_per, int64_t N,
+                            int dtype, int rank, int world, void* err_flag, void* stream);
 
 /*
  * Development / verification hooks (used by tests only).

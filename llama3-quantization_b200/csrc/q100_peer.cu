@@ -171,9 +171,118 @@ __global__ void __launch_bounds__(256) k7b_reduce_bcast(const T* __restrict__ st
   if (tid == 0) epoch_p[c] = e;
 }
 
+// ---------------------------------------------------------------- K7c: all-reduce through the switch (NVLS multicast)
+// The row-parallel all-reduce at prefill sizes when the symmetric buffer has a MULTICAST mapping (NVSwitch, NVLink 5):
+// every rank's GEMM wrote its partial [M, N] into its own copy of the buffer; rank r then owns the token rows
+// [r * rows_per, (r + 1) * rows_per):
+//   multimem.ld_reduce   one 16-byte load on the multicast address -- the SWITCH fetches the `world` copies, adds them
+//                        (fp32 accumulation) and returns the sum: 1/world of the tensor comes in per GPU instead of
+//                        (world - 1)/world;
+//   multimem.st          one 16-byte store on the multicast address -- the switch writes it into every rank's copy.
+// In place: an element is read and then rewritten by exactly one rank (its owner), nobody else touches it between the
+// two handshakes.  Per GPU and direction the links carry about one tensor size (K7b: the scatter and the broadcast
+// each carry (world - 1)/world of it out of every GPU, and the reduce re-reads `world` slots from HBM).  The sum is
+// formed in the switch: every rank receives the same bits, but the order of the fp32 additions is the switch's, not
+// rank order (tools/peer_scatter_check.py states the tolerance: one rounding of the 16-bit result).
+template <typename T> struct MultimemOps;
+template <> struct MultimemOps<__half> {
+  static __device__ __forceinline__ uint4 ld_reduce(const void* mc) {
+    uint4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.f16x2 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(mc) : "memory");
+    return v;
+  }
+  static __device__ __forceinline__ void st(void* mc, const uint4& v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f16x2 [%0], {%1, %2, %3, %4};"
+                 :: "l"(mc), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  }
+};
+template <> struct MultimemOps<__nv_bfloat16> {
+  static __device__ __forceinline__ uint4 ld_reduce(const void* mc) {
+    uint4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(mc) : "memory");
+    return v;
+  }
+  static __device__ __forceinline__ void st(void* mc, const uint4& v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.bf16x2 [%0], {%1, %2, %3, %4};"
+                 :: "l"(mc), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(512) k7c_multimem_allreduce(T* __restrict__ mc, uint32_t* const* __restrict__ flags,
+                                                              uint32_t* __restrict__ epoch_p, int64_t n_own, int rank,
+                                                              int world, uint32_t* __restrict__ err) {
+  const int c = blockIdx.x, tid = threadIdx.x;
+  const uint32_t e = epoch_p[c] + 1;
+  const int par = static_cast<int>(e & 1u);
+  auto flag_of = [&](int barrier, int r) {
+    return ((static_cast<int64_t>(barrier) * 2 + par) * world + r) * K7B_CTAS + c;
+  };
+  auto handshake = [&](int barrier) {
+    __syncthreads();
+    if (tid < world) {
+      st_release_sys(flags[tid] + flag_of(barrier, rank), e);
+      const uint32_t* f = flags[rank] + flag_of(barrier, tid);
+      const unsigned long long t0 = gtimer();
+      while (ld_acquire_sys(f) != e) {
+        if (gtimer() - t0 > 30000000000ull) { atomicExch(err, 1u); break; }
+      }
+    }
+    __syncthreads();
+  };
+  // (A) every peer's GEMM -- the kernel before this one in its stream -- has completed: its partial is in its copy
+  handshake(0);
+  const int64_t nvec = n_own >> 3;
+  const int64_t per = (nvec + gridDim.x - 1) / gridDim.x;
+  const int64_t v0 = c * per, v1 = min(nvec, v0 + per);
+  uint4* base = reinterpret_cast<uint4*>(mc + static_cast<int64_t>(rank) * n_own);
+  constexpr int U = 8;                                  // 16-byte requests in flight per thread
+  for (int64_t vb = v0 + tid; vb < v1; vb += static_cast<int64_t>(blockDim.x) * U) {
+    uint4 q[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = vb + static_cast<int64_t>(u) * blockDim.x;
+      if (v < v1) q[u] = MultimemOps<T>::ld_reduce(base + v);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t v = vb + static_cast<int64_t>(u) * blockDim.x;
+      if (v < v1) MultimemOps<T>::st(base + v, q[u]);
+    }
+  }
+  __threadfence_system();                               // the multicast stores are ordered before this CTA's flags
+  // (B) every peer has stored its rows into my copy
+  handshake(1);
+  if (tid == 0) epoch_p[c] = e;
+}
+
 }  // namespace q100
 
 using namespace q100;
+
+extern "C" int q100_allreduce_multimem(void* mc_buf, const void* peer_flags, void* epoch, int64_t rows_per, int64_t N,
+                                       int dtype, int rank, int world, void* err_flag, void* stream) {
+  Q100_REQUIRE(mc_buf && peer_flags && epoch && err_flag, Q100_EINVAL, "NULL pointer argument");
+  Q100_REQUIRE(dtype == Q100_F16 || dtype == Q100_BF16, Q100_EUNSUPPORTED, "fp16 / bf16 only (got dtype %d)", dtype);
+  Q100_REQUIRE(world >= 2 && world <= 16 && rank >= 0 && rank < world, Q100_EINVAL, "bad rank %d / world %d", rank, world);
+  Q100_REQUIRE(rows_per > 0 && N > 0 && (rows_per * N) % 8 == 0, Q100_EINVAL, "rows_per * N must be a positive multiple of 8");
+  Q100_REQUIRE((reinterpret_cast<uintptr_t>(mc_buf) & 15) == 0, Q100_EINVAL, "the multicast address must be 16-byte aligned");
+  int rc = ensure_device();
+  if (rc != Q100_OK) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int64_t n_own = rows_per * N;
+  if (dtype == Q100_F16)
+    k7c_multimem_allreduce<__half><<<K7B_CTAS, 512, 0, st>>>(reinterpret_cast<__half*>(mc_buf),
+        reinterpret_cast<uint32_t* const*>(peer_flags), reinterpret_cast<uint32_t*>(epoch), n_own, rank, world,
+        reinterpret_cast<uint32_t*>(err_flag));
+  else
+    k7c_multimem_allreduce<__nv_bfloat16><<<K7B_CTAS, 512, 0, st>>>(reinterpret_cast<__nv_bfloat16*>(mc_buf),
+        reinterpret_cast<uint32_t* const*>(peer_flags), reinterpret_cast<uint32_t*>(epoch), n_own, rank, world,
+        reinterpret_cast<uint32_t*>(err_flag));
+  return check_cuda(cudaGetLastError(), "k7c_multimem_allreduce launch");
+}
 
 extern "C" int q100_reduce_bcast(const void* stage, const void* peer_y, const void* peer_flags, void* epoch,
                                  int64_t rows_per, int64_t N, int dtype, int rank, int world, void* err_flag,

@@ -300,8 +300,9 @@ def _workspace(dev: torch.device, nbytes: int) -> torch.Tensor:
 
 
 def gemm_wna16(x: torch.Tensor, w: PackedWeight, bias: Optional[torch.Tensor] = None,
-               flags: int = 0) -> torch.Tensor:
-    """y = x @ dequant(w)^T (+ bias) straight from packed codes (K3)."""
+               flags: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """y = x @ dequant(w)^T (+ bias) straight from packed codes (K3).  ``out``: a preallocated contiguous
+    [rows, N] destination (e.g. a symmetric-memory buffer a collective reads next)."""
     _require_cuda(x, w.packed, bias)
     if x.dtype != w.dtype:
         raise TypeError(f"q100.gemm_wna16: x is {x.dtype} but the packed weight was built for {w.dtype}")
@@ -312,7 +313,12 @@ def gemm_wna16(x: torch.Tensor, w: PackedWeight, bias: Optional[torch.Tensor] = 
         raise ValueError(f"q100.gemm_wna16: x has K={shp[-1]}, expected {kx}")
     x2 = x.contiguous().view(-1, kx)
     M = x2.shape[0]
-    y = torch.empty((M, w.N), dtype=x.dtype, device=x.device)
+    if out is None:
+        y = torch.empty((M, w.N), dtype=x.dtype, device=x.device)
+    else:
+        if out.numel() != M * w.N or out.dtype != x.dtype or not out.is_contiguous():
+            raise ValueError("q100.gemm_wna16: out must be a contiguous [rows, N] tensor in the dtype of x")
+        y = out
     if M == 0:
         return y.view(*shp[:-1], w.N)
     if bias is not None:

@@ -133,6 +133,76 @@ class ScatterReduce:
             raise RuntimeError("q100.peer: a fused reduce timed out waiting for a peer; its results are invalid")
 
 
+class MulticastReduce:
+    """Row-parallel all-reduce at prefill sizes through the switch (K7c, q100_allreduce_multimem): the GEMM writes its
+    partial ``[M, N]`` into one of two alternating symmetric buffers that have a multicast mapping, then ONE kernel
+    reduces this rank's token rows with ``multimem.ld_reduce`` (the switch adds the ``world`` copies) and broadcasts
+    them with ``multimem.st``, in place.  Same interface as :class:`ScatterReduce`; chosen by :func:`enable_scatter`
+    when every rank reports a multicast address (NVSwitch).  Collective set-up."""
+
+    FLAG_WORDS = 4 * 128
+
+    def __init__(self, group, device: torch.device, max_tokens: int, max_cols: int, dtype: torch.dtype):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.device, self.dtype = device, dtype
+        self.cap = int(max_tokens) * int(max_cols)
+        err = None
+        try:
+            self.y = [symm.empty(self.cap, dtype=dtype, device=device) for _ in range(2)]
+            self.flags = symm.empty(self.FLAG_WORDS * self.world, dtype=torch.int32, device=device)
+            self.flags.zero_()
+        except Exception as e:                                     # noqa: BLE001
+            err = e
+        ok = torch.tensor([0.0 if err is not None else 1.0], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if ok.item() == 0:
+            raise RuntimeError(f"symmetric-memory allocation failed on some rank ({err!r})")
+        self.h_y = [symm.rendezvous(t, self.group) for t in self.y]
+        self.h_flags = symm.rendezvous(self.flags, self.group)
+        self.mc = [int(getattr(h, "multicast_ptr", 0) or 0) for h in self.h_y]
+        have = torch.tensor([1.0 if all(self.mc) else 0.0], device=device)
+        dist.all_reduce(have, op=dist.ReduceOp.MIN, group=self.group)
+        if have.item() == 0:
+            raise RuntimeError("no multicast mapping for the symmetric buffers (not an NVSwitch fabric?)")
+        self.epoch = torch.zeros(128, dtype=torch.int32, device=device)
+        self.err = torch.zeros(1, dtype=torch.int32, device=device)
+        self.turn = 0
+        torch.cuda.synchronize(device)
+        dist.barrier(self.group)
+
+    def fits(self, M: int, w) -> bool:
+        """Only properties that are identical on every rank decide the path."""
+        return (M > 32 and M % self.world == 0 and (M // self.world) * w.N % 8 == 0 and M * w.N <= self.cap
+                and w.dtype == self.dtype and w.K % 128 == 0 and w.N % 8 == 0)
+
+    def reduce_(self, k: int, M: int, N: int) -> None:
+        """In-place all-reduce of the first M * N elements of buffer k (every rank has written its partial there)."""
+        st = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            check(lib.q100_allreduce_multimem(self.mc[k], self.h_flags.buffer_ptrs_dev, self.epoch.data_ptr(),
+                                              M // self.world, N, _DT[self.dtype], self.rank, self.world,
+                                              self.err.data_ptr(), st))
+
+    def __call__(self, x: torch.Tensor, w) -> torch.Tensor:
+        from . import ops as _ops
+        shp = x.shape
+        x2 = x.contiguous().view(-1, w.K)
+        M = x2.shape[0]
+        k = self.turn
+        self.turn ^= 1
+        y = self.y[k][:M * w.N].view(M, w.N)
+        _ops.gemm_wna16(x2, w, out=y)
+        self.reduce_(k, M, w.N)
+        return y.view(*shp[:-1], w.N)
+
+    def check(self) -> None:
+        if int(self.err.item()) != 0:
+            raise RuntimeError("q100.peer: a multicast all-reduce timed out waiting for a peer; its results are invalid")
+
+
 _SCATTER: dict = {}
 
 
@@ -146,8 +216,21 @@ def enable_scatter(group=None, device: Optional[torch.device] = None, max_tokens
     obj = None
     if dist.is_initialized() and dist.get_world_size(group) > 1 and torch.cuda.is_available():
         dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        import os
         try:
-            obj = ScatterReduce(group, dev, max_tokens, max_cols, dtype)
+            # K7c (through the switch, multimem) is opt-in: measured on 8 x B200 it ties K7b on o_proj and loses on
+            # down_proj (the scatter of K7b travels under the GEMM; multimem moved 134 MB in 346 us = 0.44 TB/s per
+            # direction, plain peer stores reach 0.68), and its sum is not the rank-order fp32 sum
+            if os.environ.get("Q100_MULTIMEM") == "1" and not os.environ.get("Q100_NO_MULTIMEM"):
+                try:
+                    obj = MulticastReduce(group, dev, max_tokens, max_cols, dtype)
+                except Exception as e:                             # noqa: BLE001 -- agreed across ranks inside
+                    obj = None
+                    if os.environ.get("Q100_PEER_VERBOSE"):
+                        import warnings
+                        warnings.warn(f"q100.peer: multicast all-reduce unavailable ({e!r}); using the scatter epilogue")
+            if obj is None:
+                obj = ScatterReduce(group, dev, max_tokens, max_cols, dtype)
         except Exception as e:                                     # noqa: BLE001
             import warnings
             warnings.warn(f"q100.peer: fused row-parallel reduce unavailable, NCCL all-reduce stays ({e!r})")

@@ -1,1 +1,3 @@
-timeout 900 python tools/bench_model.py --wbits 8 --abits 8 --group 0 --ppl-ref --ppl-samples 2 --batches 1 > gpurun_out/r4a_w8a8_k3d.json 2> gpurun_out/r4a_err.log; tail -3 gpurun_out/r4a_err.log; cat gpurun_out/r4a_w8a8_k3d.json
+timeout 300 python tools/trace_decode.py --layers 8 --batch 1 --out gpurun_out/tr_b1.json 2>&1 | tail -22
+timeout 300 python tools/trace_decode.py --layers 8 --batch 16 --out gpurun_out/tr_b16.json 2>&1 | tail -16
+rm -f gpurun_out/tr_b1.json gpurun_out/tr_b16.json

@@ -1,0 +1,3 @@
+export Q100_PEER_VERBOSE=1
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 tools/peer_scatter_check.py > gpurun_out/mc.log 2>&1
+grep -v "^\*\*\*\|OMP_NUM\|^$" gpurun_out/mc.log | grep -A8 "rank0.*Traceback\|world\|OK" | head -30

@@ -1,4 +1,5 @@
-timeout 840 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/r4b_bench_n8.json 2> gpurun_out/r4b_bench_n8.err
-echo rc=$?
-tail -c 1500 gpurun_out/r4b_bench_n8.err
-wc -c gpurun_out/r4b_bench_n8.json
+export Q100_PEER_VERBOSE=1
+timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541 tools/peer_scatter_check.py > gpurun_out/mc8.log 2>&1
+grep -v "^\*\*\*\|OMP_NUM\|^$" gpurun_out/mc8.log | grep -A8 "rank0.*Traceback\|world\|OK" | head -30
+Q100_NO_MULTIMEM=1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29542 tools/peer_scatter_check.py > gpurun_out/sc8.log 2>&1
+grep -v "^\*\*\*\|OMP_NUM\|^$" gpurun_out/sc8.log | grep -A8 "rank0.*Traceback\|world\|OK" | head -30
