@@ -329,6 +329,15 @@ int q100_rope_qkv_prefill(const void* qkv, const void* cos_cache, const void* si
  *   epilogue of the fused gate|up GEMM: act_fn(gate_proj(x)) * up_proj(x), int_llama_layer.py:45.
  */
 int q100_silu_mul(const void* gate_up, void* out, int64_t rows, int64_t inter, int dtype, void* stream);
+/*
+ * K10 -- q100_argmax_rows: out_index[r] (int64) = argmax over the last dim of x [rows, cols] -- the greedy token choice
+ *   after lm_head in the reference's generation loop (llama.py:409-465).  Ties go to the lowest index, NaN counts as
+ *   the maximum (torch.argmax's rule).  64 CTAs per row + the last one merges; `workspace`
+ *   (q100_argmax_workspace_bytes, zero-filled once by the caller, left zeroed) holds counters and partials.
+ */
+size_t q100_argmax_workspace_bytes(int64_t rows);
+int q100_argmax_rows(const void* x, int64_t rows, int64_t cols, int dtype, void* out_index, void* workspace,
+                     size_t workspace_bytes, void* stream);
 
 /*
  * K9 -- the decode chain: ONE persistent launch that runs a list of phases -- the dequant-GEMMs of one or many

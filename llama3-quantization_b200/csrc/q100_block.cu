@@ -370,3 +370,122 @@ extern "C" int q100_silu_mul(const void* gate_up, void* out, int64_t rows, int64
                                                      static_cast<int>(inter));
   return check_cuda(cudaGetLastError(), "k6_silu_mul launch");
 }
+
+// ---------------------------------------------------------------- K10: argmax over the vocabulary (greedy decode step)
+// next_token = logits.argmax(-1) of the reference's generation loop (llama.py:409-465 measures forward + token
+// choice per step).  torch's reduction runs one CTA per row: 42 us for a [1, 128256] fp16 row inside the decode graph.
+// Here AM_CTAS CTAs per row each scan a slice with 16-byte loads, leave (value, index) in global memory, and the last
+// one to arrive (a counter per row, left at zero) reduces the partials.  Ties: the lowest index; NaN counts as the
+// maximum (torch's rule), the first NaN wins.
+namespace q100 {
+constexpr int AM_CTAS = 64;
+
+__device__ __forceinline__ bool am_better(float v, int i, float bv, int bi) {
+  const bool vn = v != v, bn = bv != bv;
+  if (vn || bn) return vn && (!bn || i < bi);
+  return v > bv || (v == bv && i < bi);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k10_argmax(const T* __restrict__ x, int64_t cols, float2* __restrict__ part,
+                                                  uint32_t* __restrict__ counters, int64_t* __restrict__ out) {
+  using D = DT<T>;
+  __shared__ float s_v[8];
+  __shared__ int s_i[8];
+  __shared__ int s_last;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int row = blockIdx.y, c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const T* xr = x + static_cast<int64_t>(row) * cols;
+  const int64_t nvec = cols >> 3;
+  float bv = __int_as_float(0xff800000);
+  int bi = 0x7fffffff;
+  for (int64_t v = static_cast<int64_t>(c) * 256 + tid; v < nvec; v += static_cast<int64_t>(AM_CTAS) * 256) {
+    const uint4 q = __ldcs(reinterpret_cast<const uint4*>(xr) + v);
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = D::to_f2(w[j]);
+      const int i0 = static_cast<int>(v * 8) + 2 * j;
+      if (am_better(f.x, i0, bv, bi)) { bv = f.x; bi = i0; }
+      if (am_better(f.y, i0 + 1, bv, bi)) { bv = f.y; bi = i0 + 1; }
+    }
+  }
+  if (c == 0) {                                        // the tail when cols % 8 != 0
+    for (int64_t i = (nvec << 3) + tid; i < cols; i += 256) {
+      const float f = D::to_f(xr[i]);
+      if (am_better(f, static_cast<int>(i), bv, bi)) { bv = f; bi = static_cast<int>(i); }
+    }
+  }
+  auto warp_red = [&]() {
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, d);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, d);
+      if (am_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+  };
+  warp_red();
+  if (lane == 0) { s_v[warp] = bv; s_i[warp] = bi; }
+  __syncthreads();
+  if (warp == 0) {
+    bv = lane < 8 ? s_v[lane] : __int_as_float(0xff800000);
+    bi = lane < 8 ? s_i[lane] : 0x7fffffff;
+    warp_red();
+    if (lane == 0) {
+      part[row * AM_CTAS + c] = make_float2(bv, __int_as_float(bi));
+      __threadfence();
+      const uint32_t old = atomicAdd(counters + row, 1u);
+      const int last = old == AM_CTAS - 1;
+      if (last) counters[row] = 0u;
+      __threadfence();
+      s_last = last;
+    }
+    __syncwarp();
+    if (s_last) {
+      bv = __int_as_float(0xff800000);
+      bi = 0x7fffffff;
+      for (int k = lane; k < AM_CTAS; k += 32) {
+        const float2 p = __ldcg(part + row * AM_CTAS + k);
+        const int pi = __float_as_int(p.y);
+        if (am_better(p.x, pi, bv, bi)) { bv = p.x; bi = pi; }
+      }
+      warp_red();
+      if (lane == 0) out[row] = bi;
+    }
+  }
+}
+}  // namespace q100
+
+extern "C" size_t q100_argmax_workspace_bytes(int64_t rows) {
+  if (rows <= 0) return 0;
+  return ((static_cast<size_t>(rows) * 4 + 255) & ~static_cast<size_t>(255)) + static_cast<size_t>(rows) * AM_CTAS * 8;
+}
+
+extern "C" int q100_argmax_rows(const void* x, int64_t rows, int64_t cols, int dtype, void* out_index,
+                                void* workspace, size_t workspace_bytes, void* stream) {
+  Q100_REQUIRE(x && out_index && workspace, Q100_EINVAL, "NULL pointer argument");
+  Q100_REQUIRE(dtype == Q100_F16 || dtype == Q100_BF16, Q100_EUNSUPPORTED, "fp16 / bf16 only (got dtype %d)", dtype);
+  Q100_REQUIRE(rows >= 0 && rows < 65536 && cols > 0 && cols < (1ll << 31), Q100_EINVAL, "bad shape rows=%lld cols=%lld",
+               (long long)rows, (long long)cols);
+  Q100_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (cols % 8 == 0 || rows == 1), Q100_EUNSUPPORTED,
+               "rows must start on 16-byte boundaries (cols %% 8 == 0)");
+  if (rows == 0) return Q100_OK;
+  Q100_REQUIRE(workspace_bytes >= q100_argmax_workspace_bytes(rows), Q100_EWORKSPACE, "workspace too small: %zu bytes",
+               workspace_bytes);
+  int rc = ensure_device();
+  if (rc != Q100_OK) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint32_t* counters = reinterpret_cast<uint32_t*>(workspace);
+  float2* part = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(workspace) +
+                                           ((static_cast<size_t>(rows) * 4 + 255) & ~static_cast<size_t>(255)));
+  const dim3 grid(AM_CTAS, static_cast<unsigned>(rows));
+  cudaError_t e;
+  if (dtype == Q100_F16)
+    e = launch_pdl(k10_argmax<__half>, grid, dim3(256), st, reinterpret_cast<const __half*>(x), cols, part, counters,
+                   reinterpret_cast<int64_t*>(out_index));
+  else
+    e = launch_pdl(k10_argmax<__nv_bfloat16>, grid, dim3(256), st, reinterpret_cast<const __nv_bfloat16*>(x), cols, part,
+                   counters, reinterpret_cast<int64_t*>(out_index));
+  return check_cuda(e, "k10_argmax launch");
+}

@@ -452,9 +452,7 @@ class QuantLlamaDecoderLayer(nn.Module):
         position visible), else K5 + scaled_dot_product_attention with the mask.  Returns [bsz, nh * head_dim]."""
         import os
         hd = self.self_attn.head_dim
-        # measured (8B, one B200, ctx 256): 2.05 vs 2.08 ms per token at batch 1, but slower than K5 + the library kernel
-        # from batch 4 on (one 153-register CTA per SM and item: several waves) -- K8 is taken for batch <= 2
-        k8_max = int(os.environ.get("Q100_K8_MAX_BATCH", "2"))
+        k8_max = int(os.environ.get("Q100_K8_MAX_BATCH", "64"))
         if causal_cache and qkv.shape[0] <= k8_max and _ops.attn_decode_supported(nh, nkv, hd) \
                 and not os.environ.get("Q100_NO_K8"):
             return _ops.attn_decode(qkv, rc[0], rc[1], position, kv.k, kv.v, nh, nkv, err_flag)

@@ -81,6 +81,8 @@ SIGNATURES = {
     "q100_attn_decode": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i64, _i64, _vp, _i, _vp]),
     "q100_rope_qkv_prefill": (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _vp, _vp, _i, _i64, _i, _i, _i, _i64, _vp, _i, _vp]),
     "q100_silu_mul": (_i, [_vp, _vp, _i64, _i64, _i, _vp]),
+    "q100_argmax_workspace_bytes": (_sz, [_i64]),
+    "q100_argmax_rows": (_i, [_vp, _i64, _i64, _i, _vp, _vp, _sz, _vp]),
     "q100_allreduce_oneshot": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp, _i64, _i, _i, _vp, _vp]),
     "q100_gemm_wna16_scatter": (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "q100_reduce_bcast": (_i, [_vp, _vp, _vp, _vp, _i64, _i64, _i, _i, _i, _vp, _vp]),

@@ -331,7 +331,11 @@ class GraphDecoder:
         x = _ops.add_rmsnorm(b["h"], m.norm_weight, m.cfg.rms_norm_eps)[1]
         logits = F.linear(x.view(self.bsz, 1, -1), m.lm_head)
         self.last_logits = logits
-        self.next_tok.copy_(logits.argmax(-1))
+        if logits.dtype in (torch.float16, torch.bfloat16) and logits.shape[-1] % 8 == 0:
+            from . import ops as _ops
+            _ops.argmax_rows(logits, out=self.next_tok)              # K10: 64 CTAs per row instead of torch's one
+        else:
+            self.next_tok.copy_(logits.argmax(-1))
         self.pos.add_(1)
 
     def _step(self):
@@ -358,7 +362,11 @@ class GraphDecoder:
             x = m._norm(x)
         logits = F.linear(x, m.lm_head)
         self.last_logits = logits
-        self.next_tok.copy_(logits.argmax(-1))
+        if logits.dtype in (torch.float16, torch.bfloat16) and logits.shape[-1] % 8 == 0:
+            from . import ops as _ops
+            _ops.argmax_rows(logits, out=self.next_tok)              # K10: 64 CTAs per row instead of torch's one
+        else:
+            self.next_tok.copy_(logits.argmax(-1))
         self.pos.add_(1)
 
     @torch.no_grad()

@@ -569,6 +569,30 @@ def silu_mul(gate_up: torch.Tensor) -> torch.Tensor:
     return out
 
 
+_ARGMAX_WS: dict = {}
+
+
+def argmax_rows(x: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """int64 argmax over the last dim of a 16-bit tensor (K10; the greedy token choice of a decode step).  Ties go to
+    the lowest index, NaN counts as the maximum.  Returns shape x.shape[:-1]."""
+    _require_cuda(x)
+    x2 = x.contiguous().view(-1, x.shape[-1])
+    rows, cols = x2.shape
+    dev = x.device
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream, rows)
+    ws = _ARGMAX_WS.get(key)
+    if ws is None:
+        ws = torch.zeros(int(lib.q100_argmax_workspace_bytes(rows)), dtype=torch.uint8, device=dev)
+        _ARGMAX_WS[key] = ws
+    res = torch.empty(rows, dtype=torch.int64, device=dev) if out is None else out
+    if res.numel() != rows or res.dtype != torch.int64 or not res.is_contiguous():
+        raise ValueError("q100.argmax_rows: out must be a contiguous int64 tensor with one entry per row")
+    with _on(dev):
+        check(lib.q100_argmax_rows(x2.data_ptr(), rows, cols, _dtype_code(x2), res.data_ptr(), ws.data_ptr(), ws.numel(),
+                                   _stream(x2)))
+    return res.view(x.shape[:-1]) if out is None else out
+
+
 def selftest_div(dtype: torch.dtype, device="cuda") -> int:
     """Exhaustive check of the fast 16-bit division; returns the mismatch count."""
     out = torch.zeros(1, dtype=torch.int64, device=device)

@@ -1,3 +1,4 @@
-timeout 300 python tools/trace_decode.py --layers 8 --batch 1 --out gpurun_out/tr_b1.json 2>&1 | tail -22
-timeout 300 python tools/trace_decode.py --layers 8 --batch 16 --out gpurun_out/tr_b16.json 2>&1 | tail -16
-rm -f gpurun_out/tr_b1.json gpurun_out/tr_b16.json
+py='import json,sys; d=json.loads(sys.stdin.read()); print({k:round(v["median_ms_per_token"],3) for k,v in d["decode"].items()})'
+echo "== default"; timeout 300 python tools/bench_model.py --wbits 4 --ppl-samples 0 --batches 1,2,4,8,16 2>/dev/null | python -c "$py"
+echo "== Q100_DECODE_PDL=0"; Q100_DECODE_PDL=0 timeout 300 python tools/bench_model.py --wbits 4 --ppl-samples 0 --batches 4,8,16 2>/dev/null | python -c "$py"
+echo "== Q100_BLOCK_PDL=0"; Q100_BLOCK_PDL=0 timeout 300 python tools/bench_model.py --wbits 4 --ppl-samples 0 --batches 4,8,16 2>/dev/null | python -c "$py"
