@@ -298,12 +298,13 @@ int q100_rope_kv_decode(const void* qkv, const void* cos_cache, const void* sin_
  *   form): rotary on q / k of the new token, cache append (as q100_rope_kv_decode above), then
  *   softmax(q k^T / sqrt(head_dim)) v over the cache positions 0..position of each sequence -- the static-cache form
  *   of int_llama_layer.py:114-172 with the causal mask (every slot up to the new token visible, none behind it) --
- *   with scores / softmax / P.V in fp32 from the 16-bit q, k, v (what scaled_dot_product_attention computes from the
- *   same tensors, up to the order of the fp32 sums).  out [batch, heads * head_dim] is the row o_proj reads
+ *   with scores, softmax and accumulation in fp32 from the 16-bit q, k, v on mma.sync tiles, the probabilities rounded
+ *   to `dtype` for the second product like the reference's (int_llama_layer.py:152-153; what
+ *   scaled_dot_product_attention computes from the same tensors, up to the order of the fp32 sums).  out [batch, heads * head_dim] is the row o_proj reads
  *   (int_llama_layer.py:170-172).  Flash-decoding: the positions are split over CTAs, the last CTA of a
  *   (sequence, kv head) merges the partials; `workspace` (q100_attn_decode_workspace_bytes; zero-filled once by the
  *   caller, left zeroed) holds the arrival counters and the partials and may be shared by all blocks of a model on
- *   one stream.  head_dim == 128, heads / kv_heads in {1, 2, 3, 4, 8}.  Position errors as q100_rope_kv_decode.
+ *   one stream.  head_dim == 128, heads / kv_heads <= 8.  Position errors as q100_rope_kv_decode.
  */
 size_t q100_attn_decode_workspace_bytes(int batch, int heads, int kv_heads, int64_t max_len);
 int q100_attn_decode(const void* qkv, const void* cos_cache, const void* sin_cache, const void* position,

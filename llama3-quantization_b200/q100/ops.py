@@ -526,7 +526,7 @@ def attn_decode(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, positio
 
 def attn_decode_supported(heads: int, kv_heads: int, head_dim: int) -> bool:
     rep = heads // max(kv_heads, 1)
-    return head_dim == 128 and kv_heads > 0 and heads % kv_heads == 0 and rep in (1, 2, 3, 4, 8)
+    return head_dim == 128 and kv_heads > 0 and heads % kv_heads == 0 and 1 <= rep <= 8
 
 
 def rope_qkv_prefill(qkv: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, position_ids: torch.Tensor,
