@@ -41,6 +41,7 @@ constexpr int TA_EPI_WARP0 = 8;
 constexpr int TA_TMAX_WARP = 12, TA_MMA_WARP = 13, TA_TMAP_WARP = 14;
 constexpr int TA_THREADS = 15 * 32;
 constexpr uint32_t TA_TMEM_COLS = 512;
+constexpr uint32_t TA_COL_A = 256;    // A ring starts after the (up to) 256 accumulator columns
 
 struct TcaArgs {
   const void* packed;
@@ -58,9 +59,6 @@ struct TcaArgs {
   int rows_per, rank, world;
   // stream-K for the tiles left over after the last full round (see SegIter): the clusters that share such a tile hand
   // fp32 partials to the one that owns its last k blocks through `ws`
-  int mixed;                   // 1: M %% NT != 0 and the narrow last token tile of every row group is scheduled apart
-                               //    (SegIter): all full-width tiles round-robin first, then the narrow ones dealt to
-                               //    the clusters that got one full-width tile less
   int stream_k;                // 0: whole tiles only
   float* ws_part;              // [cluster][2][CL][NT columns][128 rows] fp32 partials (a range crosses <= 1 tile boundary)
   uint32_t* ws_flag;           // [cluster][2][CL] arrival flags, zero between launches
@@ -75,20 +73,8 @@ struct TcaArgs {
 struct SegIter {
   int ct, n_full_end, step, num_kb;      // full rounds: ct = ct0, ct0 + step, ... < n_full_end
   int u, u_end, tile0;                   // leftover: units [u, u_end) of the tiles tile0, tile0 + 1, ...
-  // mixed mode: b / s walk the full-width / narrow tiles of this cluster (indices in their own spaces)
-  int mixed, m_tiles, b, n_big, s, s_step, n_small;
   __device__ __forceinline__ SegIter(const TcaArgs& a, int n_ct, int num_kb_, int ct0, int ct_step)
-      : ct(ct0), n_full_end(n_ct), step(ct_step), num_kb(num_kb_), u(0), u_end(0), tile0(n_ct), mixed(a.mixed),
-        m_tiles(a.m_tiles), b(ct0), n_big(0), s(0), s_step(1), n_small(0) {
-    if (mixed) {
-      n_small = n_ct / m_tiles;                      // one narrow tile per row group
-      n_big = n_ct - n_small;
-      const int r = n_big % ct_step;                 // clusters < r hold one more full-width tile
-      const int first = r, cnt = r ? ct_step - r : ct_step;
-      s_step = cnt;
-      s = (r == 0 || ct0 >= first) ? (r ? ct0 - first : ct0) : n_small;   // not eligible: no narrow tiles
-      return;
-    }
+      : ct(ct0), n_full_end(n_ct), step(ct_step), num_kb(num_kb_), u(0), u_end(0), tile0(n_ct) {
     if (a.stream_k) {
       const int rounds = n_ct / ct_step;
       n_full_end = rounds * ct_step;
@@ -99,12 +85,6 @@ struct SegIter {
     }
   }
   __device__ __forceinline__ bool next(int& ct_out, int& kb0, int& kb1) {
-    if (mixed) {
-      kb0 = 0; kb1 = num_kb;
-      if (b < n_big) { ct_out = (b / (m_tiles - 1)) * m_tiles + b % (m_tiles - 1); b += step; return true; }
-      if (s < n_small) { ct_out = s * m_tiles + (m_tiles - 1); s += s_step; return true; }
-      return false;
-    }
     if (ct < n_full_end) { ct_out = ct; kb0 = 0; kb1 = num_kb; ct += step; return true; }
     if (u >= u_end) return false;
     const int t = u / num_kb;
@@ -179,20 +159,6 @@ __device__ __forceinline__ void ta_wait(uint32_t bar, uint32_t parity) {
       "DONE:\n\t}\n"
       :: "r"(bar), "r"(parity) : "memory");
 }
-// two barriers at once: the two try_wait instructions are independent, so their latencies (~90 cycles each even when the
-// phase has completed) overlap instead of adding up
-__device__ __forceinline__ void ta_wait2(uint32_t bar_a, uint32_t par_a, uint32_t bar_b, uint32_t par_b) {
-  asm volatile(
-      "{\n\t.reg .pred PA, PB;\n\t"
-      "LAB_WAIT2:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 PA, [%0], %1;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 PB, [%2], %3;\n\t"
-      "and.pred PA, PA, PB;\n\t"
-      "@PA bra DONE2;\n\t"
-      "bra LAB_WAIT2;\n\t"
-      "DONE2:\n\t}\n"
-      :: "r"(bar_a), "r"(par_a), "r"(bar_b), "r"(par_b) : "memory");
-}
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -250,18 +216,14 @@ k3_tca(const __grid_constant__ CUtensorMap tm_x, const TcaArgs a) {
   constexpr bool kBf16 = DT<T>::kCode == Q100_BF16;
   constexpr int SX = SM::kSX;
   constexpr int NW = SM::kP / TA_ROWS / 4;             // code words per row per k block (W4: 8)
-  // accumulator stages: two when they fit next to the A ring (NT <= 192) -- the epilogue of a tile then overlaps the
-  // MMAs of the next one; the A ring starts behind them
-  constexpr int ND = (2 * NT + TA_SA * 32 <= static_cast<int>(TA_TMEM_COLS)) ? 2 : 1;
-  constexpr uint32_t TA_COL_A = ND * NT;
 
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const uint32_t base_u32 = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  __shared__ uint64_t bars[SX + SX + TA_SP + TA_SP + TA_SA + TA_SA + 4];
+  __shared__ uint64_t bars[SX + SX + TA_SP + TA_SP + TA_SA + TA_SA + 2];
   __shared__ uint32_t tmem_base_s;
   const uint32_t b0 = smem_u32(&bars[0]);
   const uint32_t full_x = b0, empty_x = full_x + 8 * SX, full_p = empty_x + 8 * SX, empty_p = full_p + 8 * TA_SP;
-  const uint32_t a_full = empty_p + 8 * TA_SP, a_empty = a_full + 8 * TA_SA, d_full = a_empty + 8 * TA_SA, d_empty = d_full + 16;
+  const uint32_t a_full = empty_p + 8 * TA_SP, a_empty = a_full + 8 * TA_SA, d_full = a_empty + 8 * TA_SA, d_empty = d_full + 8;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int num_kb = a.K / TA_BK;
@@ -276,10 +238,8 @@ k3_tca(const __grid_constant__ CUtensorMap tm_x, const TcaArgs a) {
     for (int s = 0; s < SX; ++s) { mbar_init(&bars[s], 1); mbar_init(&bars[SX + s], CL); }
     for (int s = 0; s < TA_SP; ++s) { mbar_init(&bars[2 * SX + s], 1); mbar_init(&bars[2 * SX + TA_SP + s], 4); }
     for (int s = 0; s < TA_SA; ++s) { mbar_init(&bars[2 * SX + 2 * TA_SP + s], 4); mbar_init(&bars[2 * SX + 2 * TA_SP + TA_SA + s], 1); }
-    for (int d = 0; d < 2; ++d) {
-      mbar_init(&bars[2 * SX + 2 * TA_SP + 2 * TA_SA + d], 1);        // d_full
-      mbar_init(&bars[2 * SX + 2 * TA_SP + 2 * TA_SA + 2 + d], 4);    // d_empty
-    }
+    mbar_init(&bars[2 * SX + 2 * TA_SP + 2 * TA_SA], 1);        // d_full
+    mbar_init(&bars[2 * SX + 2 * TA_SP + 2 * TA_SA + 1], 4);    // d_empty
     fence_mbar_init();
   }
   if (warp == TA_MMA_WARP) tmem_alloc(&tmem_base_s, TA_TMEM_COLS);
@@ -343,6 +303,7 @@ k3_tca(const __grid_constant__ CUtensorMap tm_x, const TcaArgs a) {
     }
   } else if (warp == TA_MMA_WARP) {
     // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = umma_idesc_f16(kBf16 ? 1 : 0, TA_ROWS, NT);
     uint32_t it = 0, tcount = 0;
 #ifdef TA_TIMING
     long long t_de = 0, t_af = 0, t_fx = 0, t_is = 0; const long long t_begin = clock64();
@@ -351,11 +312,7 @@ k3_tca(const __grid_constant__ CUtensorMap tm_x, const TcaArgs a) {
     int ct, kb0, kb1;
     for (; seg.next(ct, kb0, kb1); ++tcount) {
       TA_T(q0);
-      const uint32_t ds = tcount % ND;
-      // a narrow last token tile: only the columns that exist (a multiple of 16)
-      const int cols = min(NT, ((a.M - (ct % a.m_tiles) * NT) + 15) & ~15);
-      const uint32_t idesc = umma_idesc_f16(kBf16 ? 1 : 0, TA_ROWS, cols);
-      ta_wait(d_empty + 8 * ds, ((tcount / ND) & 1) ^ 1);   // the epilogue has drained this accumulator stage
+      ta_wait(d_empty, (tcount & 1) ^ 1);            // the epilogue has drained the accumulator
       tc_fence_after();
 #ifdef TA_TIMING
       t_de += clock64() - q0;
@@ -363,13 +320,9 @@ k3_tca(const __grid_constant__ CUtensorMap tm_x, const TcaArgs a) {
       for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const uint32_t sx = it % SX, sa = it % TA_SA;
         TA_T(q1);
-#ifdef TA_TIMING
         ta_wait(a_full + 8 * sa, (it / TA_SA) & 1);
         TA_T(q2);
         ta_wait(full_x + 8 * sx, (it / SX) & 1);
-#else
-        ta_wait2(a_full + 8 * sa, (it / TA_SA) & 1, full_x + 8 * sx, (it / SX) & 1);
-#endif
         TA_T(q3);
 #ifdef TA_TIMING
         t_af += q2 - q1; t_fx += q3 - q2;
@@ -380,11 +333,11 @@ k3_tca(const __grid_constant__ CUtensorMap tm_x, const TcaArgs a) {
           const uint32_t at = tmem + TA_COL_A + sa * 32;
 #pragma unroll
           for (int k = 0; k < TA_BK / 16; ++k)
-            umma_f16_ts(tmem + ds * NT, at + 8 * k, bd + 2 * k, idesc, (kb != kb0 || k != 0) ? 1u : 0u);   // a segment starts from zero
+            umma_f16_ts(tmem, at + 8 * k, bd + 2 * k, idesc, (kb != kb0 || k != 0) ? 1u : 0u);   // a segment starts from zero
           umma_commit_u32(a_empty + 8 * sa);
           if (CL == 1) umma_commit_u32(empty_x + 8 * sx);
           else umma_commit_mc(empty_x + 8 * sx, kMask);      // frees the stage in every CTA of the cluster
-          if (kb == kb1 - 1) umma_commit_u32(d_full + 8 * ds);
+          if (kb == kb1 - 1) umma_commit_u32(d_full);
         }
         __syncwarp();
 #ifdef TA_TIMING
@@ -490,8 +443,8 @@ k3_tca(const __grid_constant__ CUtensorMap tm_x, const TcaArgs a) {
         if (lane == 0) ta_arrive(a_full + 8 * sa);
 #ifdef TA_TIMING
         if (tid == 0 && blockIdx.x < 256) {
-          g_ta_t[blockIdx.x][6] += (d1 - d0);                   // waiting for the packed codes (full_p)
-          g_ta_t[blockIdx.x][7] += (d3 - d2);                   // waiting for the A stage (a_empty)
+          g_ta_t[blockIdx.x][6] += (d1 - d0) + (d3 - d2);       // waiting (full_p + a_empty)
+          g_ta_t[blockIdx.x][7] += (d2 - d1) + (clock64() - d3); // working (loads + math, store + publish)
         }
 #endif
       }
@@ -541,8 +494,7 @@ k3_tca(const __grid_constant__ CUtensorMap tm_x, const TcaArgs a) {
         }
         asm volatile("bar.sync 2, 128;" ::: "memory");   // the four epilogue warps
       }
-      const uint32_t ds = tcount % ND;
-      ta_wait(d_full + 8 * ds, (tcount / ND) & 1);
+      ta_wait(d_full, tcount & 1);
       tc_fence_after();
       const float bv = (bias != nullptr && n < a.N) ? DT<T>::to_f(bias[n]) : 0.f;
       // y is [tokens, rows]: the accumulator has a row per lane, so a chunk of [32 tokens x 32 rows] is
@@ -559,16 +511,15 @@ k3_tca(const __grid_constant__ CUtensorMap tm_x, const TcaArgs a) {
       }
       const uint32_t ebase = base_u32 + SM::kOffE + quad * (2 * 2048);
       const int tj = lane >> 2, rq = (lane & 3) * 8;                    // read side: token tj (+8i), rows rq..rq+7
-      const int c_end = min(NT, a.M - m0);                               // columns of this tile that exist
 #pragma unroll 1
-      for (int c0 = 0; c0 < c_end; c0 += 32) {
+      for (int c0 = 0; c0 < NT; c0 += 32) {
         uint32_t r[32];
-        tmem_ld_32x32b_x32(lane_t + ds * NT + c0, r);
+        tmem_ld_32x32b_x32(lane_t + c0, r);
         tmem_ld_wait();
-        if (c0 + 32 >= c_end) {                      // last chunk read: the accumulator may be overwritten
+        if (c0 + 32 >= NT) {                         // last chunk read: the accumulator may be overwritten
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) ta_arrive(d_empty + 8 * ds);
+          if (lane == 0) ta_arrive(d_empty);
         }
         if (contributor) {
           // fp32 partial, [column][row]: a warp's store of one column is 128 contiguous bytes
@@ -667,8 +618,6 @@ static int launch_tca(const void* x, TcaArgs a, cudaStream_t st) {
   if (rc != Q100_OK) return rc;
   a.m_tiles = (a.M + NT - 1) / NT;
   a.n_tiles = (a.N + TA_ROWS - 1) / TA_ROWS;
-  a.mixed = (a.M % NT != 0 && a.m_tiles >= 2) ? 1 : 0;
-  if (a.mixed) a.stream_k = 0;
   const int n_ct = a.m_tiles * ((a.n_tiles + CL - 1) / CL);
   int clusters = sm_count() / CL;
   if (clusters > n_ct) clusters = n_ct;
@@ -720,16 +669,6 @@ static int gemm_tca_nt(const void* x, const TcaArgs& a, int cluster, cudaStream_
   if (a.M <= 128 || env_nt == 128) {
     if (cluster >= 2 && n_tiles >= 2) return launch_tca<T, NBITS, 128, 2>(x, a, st);
     return launch_tca<T, NBITS, 128, 1>(x, a, st);
-  }
-  if constexpr (NBITS == 4) {
-    // 192-token tiles: two accumulator stages fit in tensor memory (2 x 192 + the A ring = 512 columns), so a tile's
-    // epilogue overlaps the next tile's MMAs, and 2048 tokens = 10 x 192 + 128 leaves narrow tiles that fill the last
-    // round (see SegIter, mixed mode)
-    if (env_nt == 192 && a.peer_stage == nullptr) {
-      if (cluster >= 4 && n_tiles >= 4) return launch_tca<T, NBITS, 192, 4>(x, a, st);
-      if (cluster >= 2 && n_tiles >= 2) return launch_tca<T, NBITS, 192, 2>(x, a, st);
-      return launch_tca<T, NBITS, 192, 1>(x, a, st);
-    }
   }
   if (cluster >= 4 && n_tiles >= 4) return launch_tca<T, NBITS, 256, 4>(x, a, st);
   if (cluster >= 2 && n_tiles >= 2) return launch_tca<T, NBITS, 256, 2>(x, a, st);

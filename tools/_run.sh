@@ -1,3 +1,1 @@
-py='import json,sys; d=json.loads(sys.stdin.read()); print({k:round(v["median_ms_per_token"],3) for k,v in d["decode"].items()})'
-echo "== K4 policy (late at 3-8 rows)"; timeout 300 python tools/bench_model.py --wbits 4 --ppl-samples 0 --batches 3,4,8 2>/dev/null | python -c "$py"
-echo "== Q100_K4_EARLY=1"; Q100_K4_EARLY=1 timeout 300 python tools/bench_model.py --wbits 4 --ppl-samples 0 --batches 3,4,8 2>/dev/null | python -c "$py"
+for l in "" _tca_650c23b _tca_3e478c0; do echo "== lib$l"; Q100_LIB=$PWD/llama3-quantization_b200/q100/libq100$l.so timeout 200 python tools/exp_tc_shapes.py 2>&1 | tail -5; done
