@@ -462,7 +462,29 @@ def run_ours(args):
         bpe = 4.0 + 4.0 / HIDDEN
         gbs = M_PRE * HIDDEN * bpe / (msq * 1e-3) / 1e9
         quant["act_fake_quant_f16_a8"] = {"ms": msq, "GBps": gbs, "frac_hbm": gbs / P["hbm"], "bytes_per_element": bpe,
-                                          "shape": [M_PRE, HIDDEN]}
+                                          "shape": [M_PRE, HIDDEN],
+                                          "note": "through the Python API: host-bound at this size (allocations + ctypes)"}
+        # the same 12 calls captured in a CUDA graph: the kernel without the per-call host work
+        try:
+            sg = torch.cuda.Stream()
+            sg.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(sg):
+                q_act()
+            torch.cuda.current_stream().wait_stream(sg)
+            torch.cuda.synchronize()
+            gq = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gq):
+                for _ in range(12):
+                    q_act()
+            gq.replay()
+            torch.cuda.synchronize()
+            msg_ = timed(gq.replay, 5) / 12
+            gbs_g = M_PRE * HIDDEN * bpe / (msg_ * 1e-3) / 1e9
+            quant["act_fake_quant_f16_a8_graph"] = {"ms": msg_, "GBps": gbs_g, "frac_hbm": gbs_g / P["hbm"],
+                                                    "bytes_per_element": bpe, "shape": [M_PRE, HIDDEN]}
+            del gq
+        except Exception as ex:                                     # noqa: BLE001
+            quant["act_fake_quant_f16_a8_graph"] = {"error": str(ex)[:200]}
         del xa
         # K1b: fused backward of the quantizer (calibration loop), fp32 like the reference's training dtype, LWC on
         from q100 import ops as _qops
