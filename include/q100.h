@@ -471,6 +471,20 @@ int q100_reduce_bcast(const void* stage, const void* peer_y, const void* peer_fl
  */
 int q100_allreduce_multimem(void* mc_buf, const void* peer_flags, void* epoch, int64_t rows_per, int64_t N,
                             int dtype, int rank, int world, void* err_flag, void* stream);
+/*
+ * K7n -- q100_allreduce_add_rmsnorm: the all-reduce after a row-parallel linear of a tensor-parallel DECODE step fused
+ * with the residual add + RMSNorm that consumes it (q100_allreduce_oneshot + q100_add_rmsnorm in one launch):
+ *   y = sum over ranks of x (fp32 in rank order, one rounding to dtype -- the bits q100_allreduce_oneshot produces),
+ *   h = residual + y (rounded; h = y when residual == NULL), norm_out = weight * (h * rsqrt(mean(h^2) + eps)),
+ * i.e. int_llama_layer.py:246 / 251 + quant/omni_norm.py:52-63 on the all-reduced output.  sum_out (nullable) receives h.
+ * One CTA per token row pushes its partial row to every rank over peer memory and waits for the others' rows.
+ * peer_bufs: device array of `world` pointers to staging buffers of 2 * world * 64 * cols elements; peer_flags: `world`
+ * pointers to 2 * world * 64 zero-initialised words; epoch: 64 zero-initialised words (advanced by the kernel, so the
+ * launch is graph-capturable).  rows <= 64, cols % 8 == 0, cols <= 8192, the same `cols` in every call on one buffer set.
+ */
+int q100_allreduce_add_rmsnorm(const void* x, const void* residual, const void* weight, float eps, void* sum_out,
+                               void* norm_out, int64_t rows, int64_t cols, int dtype, const void* peer_bufs,
+                               const void* peer_flags, void* epoch, int rank, int world, void* err_flag, void* stream);
 
 /*
  * Development / verification hooks (used by tests only).

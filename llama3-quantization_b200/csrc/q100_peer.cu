@@ -171,6 +171,131 @@ __global__ void __launch_bounds__(256) k7b_reduce_bcast(const T* __restrict__ st
   if (tid == 0) epoch_p[c] = e;
 }
 
+// ---------------------------------------------------------------- K7n: all-reduce + residual add + RMSNorm, one launch
+// A tensor-parallel decode step ran  GEMM -> K7 (all-reduce) -> K4 (residual add + RMSNorm)  after o_proj and down_proj:
+// two launches of pure latency per row-parallel linear.  Here K4's CTA (one per token row) does K7's exchange itself:
+//   push   its partial row into slot [parity][rank][row] of EVERY rank's staging buffer, then the call's epoch into flag
+//          [parity][rank][row] of every rank;
+//   wait   for the `world` flags of its row;
+//   sum    the `world` slots in rank order in fp32, ONE rounding to T -- the bits K7 produces;
+//   then K4's arithmetic on that row: h = r(residual + y), norm = weight * (h * rsqrt(mean(h^2) + eps)).
+// Per-row epochs in device memory (graph-capturable), two parity sets for slot reuse as in K7, 30 s time-out.
+constexpr int K7N_MAX_ROWS = 64;
+
+template <typename T, int VMAX>
+__global__ void __launch_bounds__(256) k7n_allreduce_add_rmsnorm(const T* __restrict__ x, const T* __restrict__ res,
+                                                                 const T* __restrict__ w, float eps,
+                                                                 T* __restrict__ sum_out, T* __restrict__ norm_out,
+                                                                 T* const* __restrict__ bufs,
+                                                                 uint32_t* const* __restrict__ flags,
+                                                                 uint32_t* __restrict__ epoch_p, int cols, int rank,
+                                                                 int world, uint32_t* __restrict__ err) {
+  using D = DT<T>;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int row = blockIdx.x, tid = threadIdx.x;
+  const int nvec = cols >> 3;
+  const uint32_t e = epoch_p[row] + 1;
+  const int par = static_cast<int>(e & 1u);
+  const int64_t slot = static_cast<int64_t>(K7N_MAX_ROWS) * cols;           // elements per (parity, rank) slot
+  // ---- push my partial row, peers first
+  uint4 mine[VMAX];
+#pragma unroll
+  for (int k = 0; k < VMAX; ++k) {
+    const int v = tid + k * 256;
+    if (v < nvec) mine[k] = reinterpret_cast<const uint4*>(x + static_cast<int64_t>(row) * cols)[v];
+  }
+  for (int k = 1; k <= world; ++k) {
+    const int p = (rank + k) % world;
+    uint4* dst = reinterpret_cast<uint4*>(bufs[p] + (static_cast<int64_t>(par) * world + rank) * slot +
+                                          static_cast<int64_t>(row) * cols);
+#pragma unroll
+    for (int kk = 0; kk < VMAX; ++kk) {
+      const int v = tid + kk * 256;
+      if (v < nvec) dst[v] = mine[kk];
+    }
+  }
+  __syncthreads();
+  if (tid < world) {
+    st_release_sys(flags[tid] + (static_cast<int64_t>(par) * world + rank) * K7N_MAX_ROWS + row, e);
+    const uint32_t* f = flags[rank] + (static_cast<int64_t>(par) * world + tid) * K7N_MAX_ROWS + row;
+    const unsigned long long t0 = gtimer();
+    while (ld_acquire_sys(f) != e) {
+      if (gtimer() - t0 > 30000000000ull) { atomicExch(err, 1u); break; }     // 30 s: a peer is gone; do not hang
+    }
+  }
+  __syncthreads();
+  // ---- sum in rank order (fp32, one rounding), residual add (rounded to T), sum of squares
+  const T* base = bufs[rank] + static_cast<int64_t>(par) * world * slot + static_cast<int64_t>(row) * cols;
+  const uint4* rr = res ? reinterpret_cast<const uint4*>(res + static_cast<int64_t>(row) * cols) : nullptr;
+  uint4 h[VMAX];
+  float ss = 0.f;
+#pragma unroll
+  for (int k = 0; k < VMAX; ++k) {
+    const int v = tid + k * 256;
+    if (v < nvec) {
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      for (int r = 0; r < world; ++r) {
+        const uint4 q = __ldcg(reinterpret_cast<const uint4*>(base + r * slot) + v);
+        const float2 a = D::to_f2(q.x), b = D::to_f2(q.y), cc = D::to_f2(q.z), d = D::to_f2(q.w);
+        acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+        acc[4] += cc.x; acc[5] += cc.y; acc[6] += d.x; acc[7] += d.y;
+      }
+      uint4 a = make_uint4(D::pack2(acc[0], acc[1]), D::pack2(acc[2], acc[3]), D::pack2(acc[4], acc[5]),
+                           D::pack2(acc[6], acc[7]));
+      if (rr) {
+        const uint4 b = rr[v];
+        uint32_t* aw = reinterpret_cast<uint32_t*>(&a);
+        const uint32_t* bw = reinterpret_cast<const uint32_t*>(&b);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {                       // residual + hidden_states, rounded to T (K4)
+          const float2 fa = D::to_f2(aw[j]), fb = D::to_f2(bw[j]);
+          aw[j] = D::pack2(__fadd_rn(fb.x, fa.x), __fadd_rn(fb.y, fa.y));
+        }
+      }
+      if (sum_out) reinterpret_cast<uint4*>(sum_out + static_cast<int64_t>(row) * cols)[v] = a;
+      h[k] = a;
+      const uint32_t* aw = reinterpret_cast<const uint32_t*>(&a);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = D::to_f2(aw[j]);
+        ss = fmaf(f.x, f.x, ss);
+        ss = fmaf(f.y, f.y, ss);
+      }
+    }
+  }
+  __shared__ float red[8];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, d);
+  if ((tid & 31) == 0) red[tid >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += red[i];
+  const float inv = rsqrtf(__fadd_rn(__fdiv_rn(tot, static_cast<float>(cols)), eps));
+  const uint4* wr = reinterpret_cast<const uint4*>(w);
+#pragma unroll
+  for (int k = 0; k < VMAX; ++k) {
+    const int v = tid + k * 256;
+    if (v < nvec) {
+      const uint4 wv = wr[v];
+      const uint32_t* hw = reinterpret_cast<const uint32_t*>(&h[k]);
+      const uint32_t* ww = reinterpret_cast<const uint32_t*>(&wv);
+      uint4 o;
+      uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {                         // weight * (h * rsqrt(var + eps)), both products in fp32 (K4)
+        const float2 f = D::to_f2(hw[j]), g = D::to_f2(ww[j]);
+        ow[j] = D::pack2(__fmul_rn(g.x, __fmul_rn(f.x, inv)), __fmul_rn(g.y, __fmul_rn(f.y, inv)));
+      }
+      reinterpret_cast<uint4*>(norm_out + static_cast<int64_t>(row) * cols)[v] = o;
+    }
+  }
+  if (tid == 0) epoch_p[row] = e;
+}
+
 // ---------------------------------------------------------------- K7c: all-reduce through the switch (NVLS multicast)
 // The row-parallel all-reduce at prefill sizes when the symmetric buffer has a MULTICAST mapping (NVSwitch, NVLink 5):
 // every rank's GEMM wrote its partial [M, N] into its own copy of the buffer; rank r then owns the token rows
@@ -332,4 +457,45 @@ extern "C" int q100_allreduce_oneshot(const void* x, void* y, int64_t n, int dty
         reinterpret_cast<uint32_t* const*>(peer_flags), reinterpret_cast<uint32_t*>(epoch), slot_elems, rank, world,
         reinterpret_cast<uint32_t*>(err_flag));
   return check_cuda(cudaGetLastError(), "k7_allreduce launch");
+}
+
+extern "C" int q100_allreduce_add_rmsnorm(const void* x, const void* residual, const void* weight, float eps,
+                                          void* sum_out, void* norm_out, int64_t rows, int64_t cols, int dtype,
+                                          const void* peer_bufs, const void* peer_flags, void* epoch, int rank,
+                                          int world, void* err_flag, void* stream) {
+  Q100_REQUIRE(x && weight && norm_out && peer_bufs && peer_flags && epoch && err_flag, Q100_EINVAL, "NULL pointer argument");
+  Q100_REQUIRE(dtype == Q100_F16 || dtype == Q100_BF16, Q100_EUNSUPPORTED, "fp16 / bf16 only (got dtype %d)", dtype);
+  Q100_REQUIRE(world >= 2 && world <= 16 && rank >= 0 && rank < world, Q100_EINVAL, "bad rank %d / world %d", rank, world);
+  Q100_REQUIRE(rows > 0 && rows <= K7N_MAX_ROWS && cols > 0 && cols % 8 == 0 && cols <= 8192, Q100_EUNSUPPORTED,
+               "rows in [1, %d], cols %% 8 == 0, cols <= 8192 (got %lld x %lld)", K7N_MAX_ROWS, (long long)rows, (long long)cols);
+  int rc = ensure_device();
+  if (rc != Q100_OK) return rc;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(rows));
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = reinterpret_cast<cudaStream_t>(stream);
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const int nvec = static_cast<int>(cols / 8);
+  const int c = static_cast<int>(cols);
+  uint32_t* ef = reinterpret_cast<uint32_t*>(err_flag);
+  uint32_t* ep = reinterpret_cast<uint32_t*>(epoch);
+  uint32_t* const* fl = reinterpret_cast<uint32_t* const*>(peer_flags);
+  cudaError_t e;
+#define Q100_K7N(TT, V)                                                                                              \
+  e = cudaLaunchKernelEx(&cfg, k7n_allreduce_add_rmsnorm<TT, V>, reinterpret_cast<const TT*>(x),                     \
+                         reinterpret_cast<const TT*>(residual), reinterpret_cast<const TT*>(weight), eps,            \
+                         reinterpret_cast<TT*>(sum_out), reinterpret_cast<TT*>(norm_out),                            \
+                         reinterpret_cast<TT* const*>(peer_bufs), fl, ep, c, rank, world, ef)
+  if (dtype == Q100_F16) {
+    if (nvec <= 256) Q100_K7N(__half, 1); else if (nvec <= 512) Q100_K7N(__half, 2); else Q100_K7N(__half, 4);
+  } else {
+    if (nvec <= 256) Q100_K7N(__nv_bfloat16, 1); else if (nvec <= 512) Q100_K7N(__nv_bfloat16, 2); else Q100_K7N(__nv_bfloat16, 4);
+  }
+#undef Q100_K7N
+  return check_cuda(e, "k7n_allreduce_add_rmsnorm launch");
 }

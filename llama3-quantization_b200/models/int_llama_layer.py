@@ -461,7 +461,7 @@ class QuantLlamaDecoderLayer(nn.Module):
         return att.reshape(q.shape[0], nh * hd)
 
     def decode_step_fused(self, x, residual, kv: "StaticKV", position, attention_mask, err_flag=None,
-                          causal_cache: bool = False):
+                          causal_cache: bool = False, x_partial: bool = False):
         """One new token per sequence through this block in 4 GEMM launches + 4 small kernels + the
         attention core, on a static KV cache (CUDA-graph friendly).  Same arithmetic as ``forward`` with
         ``past_key_value=kv`` (tests/test_block.py compares the two); what moves is where the residual add
@@ -479,7 +479,22 @@ class QuantLlamaDecoderLayer(nn.Module):
         folded = self._decode_step_folded(x, residual, kv, position, attention_mask, err_flag, nh, nkv, causal_cache)
         if folded is not None:
             return folded
-        h0, n1 = _ops.add_rmsnorm(x, self.input_layernorm.weight, self.input_layernorm.variance_epsilon, residual)
+        # tensor parallel: the all-reduce after a row-parallel linear runs inside the norm kernel that consumes it (K7n,
+        # q100.peer.ReduceNorm) -- ``x_partial``: the previous block left its down_proj output un-reduced for this one
+        self.last_output_partial = False
+        rn = None
+        if attn.tp_world > 1 and getattr(mlp, "tp_world", 1) == attn.tp_world and not torch.is_grad_enabled():
+            from q100 import peer as _peer
+            rn = _peer.get_reduce_norm(attn.tp_group, x.shape[-1])
+            if rn is not None and not rn.fits(x):
+                rn = None
+        if x_partial and (rn is None or residual is None):
+            return None
+        ln1 = self.input_layernorm
+        if x_partial:
+            h0, n1 = rn(x, ln1.weight, ln1.variance_epsilon, residual)
+        else:
+            h0, n1 = _ops.add_rmsnorm(x, ln1.weight, ln1.variance_epsilon, residual)
         qkv = attn._qkv((attn.q_proj, attn.k_proj, attn.v_proj), n1, split=False)
         if qkv is None:
             return None
@@ -489,15 +504,21 @@ class QuantLlamaDecoderLayer(nn.Module):
             rc = attn._rope16 = (cos.to(x.dtype).contiguous(), sin.to(x.dtype).contiguous())
         att = self._decode_attention(qkv, rc, position, kv, nh, nkv, attention_mask, err_flag, causal_cache)
         o = attn.o_proj(att.reshape(bsz, 1, nh * attn.head_dim))
-        if attn.tp_world > 1 and not attn.o_proj.reduced:
-            o = _tp.reduce_output(o, _tp.ROW, attn.tp_group)
-        h1, n2 = _ops.add_rmsnorm(o, self.post_attention_layernorm.weight,
-                                  self.post_attention_layernorm.variance_epsilon, h0)
+        ln2 = self.post_attention_layernorm
+        if rn is not None and not attn.o_proj.reduced:
+            h1, n2 = rn(o.contiguous(), ln2.weight, ln2.variance_epsilon, h0)
+        else:
+            if attn.tp_world > 1 and not attn.o_proj.reduced:
+                o = _tp.reduce_output(o, _tp.ROW, attn.tp_group)
+            h1, n2 = _ops.add_rmsnorm(o, ln2.weight, ln2.variance_epsilon, h0)
         gu = mlp._gate_up((mlp.gate_proj, mlp.up_proj), n2, split=False)
         if gu is None:
             return None
         d = mlp.down_proj.forward_gate_up(gu)              # SiLU * up inside the down_proj GEMM's x staging
         if getattr(mlp, "tp_world", 1) > 1 and not mlp.down_proj.reduced:
+            if rn is not None:
+                self.last_output_partial = True            # the consumer's norm kernel reduces it (x_partial=True)
+                return d.contiguous(), h1
             d = _tp.reduce_output(d, _tp.ROW, mlp.tp_group)
         return d, h1
 

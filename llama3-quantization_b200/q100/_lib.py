@@ -87,6 +87,7 @@ SIGNATURES = {
     "q100_gemm_wna16_scatter": (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     "q100_reduce_bcast": (_i, [_vp, _vp, _vp, _vp, _i64, _i64, _i, _i, _i, _vp, _vp]),
     "q100_allreduce_multimem": (_i, [_vp, _vp, _vp, _i64, _i64, _i, _i, _i, _vp, _vp]),
+    "q100_allreduce_add_rmsnorm": (_i, [_vp, _vp, _vp, C.c_float, _vp, _vp, _i64, _i64, _i, _vp, _vp, _vp, _i, _i, _vp, _vp]),
     "q100_selftest_div": (_i, [_i, _vp, _vp]),
     "q100_debug_gemm_dense_tc": (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _i, _vp]),
 }

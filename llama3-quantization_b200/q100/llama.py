@@ -259,6 +259,16 @@ class GraphDecoder:
         # the device-side position and raises this flag instead of writing outside the cache)
         self.err = torch.zeros(1, dtype=torch.int32, device=dev)
         self._host_pos = 0
+        # tensor parallel: K7n (all-reduce inside the norm kernel) when the peer buffers of K7 are up -- collective
+        # set-up, every rank builds its GraphDecoder at the same point
+        self._reduce_norm = None
+        import os as _os2
+        tpw = max((getattr(l.self_attn, "tp_world", 1) for l in model.layers), default=1)
+        if tpw > 1 and not _os2.environ.get("Q100_NO_REDUCE_NORM"):
+            from . import peer as _peer
+            grp = model.layers[0].self_attn.tp_group
+            if _peer.get(grp) is not None:
+                self._reduce_norm = _peer.enable_reduce_norm(grp, dev, cfg.hidden_size)
 
     # ------------------------------------------------------------------ the chain route (K9)
     def _build_chain(self):
@@ -346,18 +356,30 @@ class GraphDecoder:
         mask = torch.where(self._slots <= self.pos.view(1, 1, 1, 1), 0.0, self._neg).to(x.dtype)
         mask = mask.expand(self.bsz, 1, 1, self.max_len)
         res = None                  # residual stream, kept apart from the last MLP output on the fused route
+        partial = False             # tensor parallel: x is this rank's un-reduced down_proj output (K7n reduces it)
         for layer, kv in zip(m.layers, self.caches):
             # `mask` IS the plain static-cache mask: the block may run its attention core as K8 (one launch)
-            out = layer.decode_step_fused(x, res, kv, self.pos, mask, self.err, causal_cache=True) if self.fused else None
+            out = layer.decode_step_fused(x, res, kv, self.pos, mask, self.err, causal_cache=True,
+                                          x_partial=partial) if self.fused else None
+            if out is None and partial:
+                x, partial = self._reduce_partial(x, layer), False
+                out = layer.decode_step_fused(x, res, kv, self.pos, mask, self.err, causal_cache=True)
             if out is not None:
                 x, res = out
+                partial = bool(getattr(layer, "last_output_partial", False))
             else:
                 if res is not None:
                     x, res = x + res, None
                 x = layer(x, attention_mask=mask, position_ids=self.pos, past_key_value=kv, use_cache=False)[0]
         if res is not None:
             from . import ops as _ops
-            x = _ops.add_rmsnorm(x, m.norm_weight, m.cfg.rms_norm_eps, res)[1]
+            rn = self._reduce_norm if partial else None
+            if rn is not None and rn.fits(x):
+                x = rn(x, m.norm_weight, m.cfg.rms_norm_eps, res)[1]
+            else:
+                if partial:
+                    x = self._reduce_partial(x, m.layers[-1])
+                x = _ops.add_rmsnorm(x, m.norm_weight, m.cfg.rms_norm_eps, res)[1]
         else:
             x = m._norm(x)
         logits = F.linear(x, m.lm_head)
@@ -368,6 +390,11 @@ class GraphDecoder:
         else:
             self.next_tok.copy_(logits.argmax(-1))
         self.pos.add_(1)
+
+    @staticmethod
+    def _reduce_partial(x, layer):
+        from . import tp as _tp
+        return _tp.reduce_output(x, _tp.ROW, layer.mlp.tp_group)
 
     @torch.no_grad()
     def prime(self, start_pos: int = 0):

@@ -203,6 +203,88 @@ class MulticastReduce:
             raise RuntimeError("q100.peer: a multicast all-reduce timed out waiting for a peer; its results are invalid")
 
 
+class ReduceNorm:
+    """All-reduce + residual add + RMSNorm in one launch for the row-parallel outputs of a tensor-parallel decode step
+    (K7n, q100_allreduce_add_rmsnorm): K4's CTA per token row does K7's exchange itself.  ``cols`` (the hidden size)
+    is fixed per instance; at most 64 rows per call.  Collective set-up, outside CUDA-graph capture."""
+
+    MAX_ROWS = 64
+
+    def __init__(self, group, device: torch.device, cols: int):
+        import torch.distributed._symmetric_memory as symm
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.device, self.cols = device, int(cols)
+        err = None
+        try:
+            self.buf = symm.empty(2 * self.world * self.MAX_ROWS * self.cols, dtype=torch.float16, device=device)
+            self.flags = symm.empty(2 * self.world * self.MAX_ROWS, dtype=torch.int32, device=device)
+            self.flags.zero_()
+        except Exception as e:                                     # noqa: BLE001
+            err = e
+        ok = torch.tensor([0.0 if err is not None else 1.0], device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if ok.item() == 0:
+            raise RuntimeError(f"symmetric-memory allocation failed on some rank ({err!r})")
+        self.h_buf = symm.rendezvous(self.buf, self.group)
+        self.h_flags = symm.rendezvous(self.flags, self.group)
+        self.epoch = torch.zeros(self.MAX_ROWS, dtype=torch.int32, device=device)
+        self.err = torch.zeros(1, dtype=torch.int32, device=device)
+        torch.cuda.synchronize(device)
+        dist.barrier(self.group)
+
+    def fits(self, x: torch.Tensor) -> bool:
+        """Only properties that are identical on every rank decide the path."""
+        return (x.is_cuda and x.dtype in _DT and x.is_contiguous() and x.shape[-1] == self.cols
+                and 0 < x.numel() // self.cols <= self.MAX_ROWS)
+
+    def __call__(self, x: torch.Tensor, weight: torch.Tensor, eps: float, residual: Optional[torch.Tensor] = None):
+        """(h, norm): h = residual + all_reduce(x) (or the all-reduced x), norm = OmniLlamaRMSNorm(h)."""
+        rows = x.numel() // self.cols
+        h = torch.empty_like(x)
+        norm = torch.empty_like(x)
+        if residual is not None:
+            residual = residual.contiguous()
+        with torch.cuda.device(self.device):
+            check(lib.q100_allreduce_add_rmsnorm(
+                x.data_ptr(), None if residual is None else residual.data_ptr(), weight.data_ptr(), float(eps),
+                h.data_ptr(), norm.data_ptr(), rows, self.cols, _DT[x.dtype], self.h_buf.buffer_ptrs_dev,
+                self.h_flags.buffer_ptrs_dev, self.epoch.data_ptr(), self.rank, self.world, self.err.data_ptr(),
+                torch.cuda.current_stream(self.device).cuda_stream))
+        return h, norm
+
+    def check(self) -> None:
+        if int(self.err.item()) != 0:
+            raise RuntimeError("q100.peer: a fused all-reduce + norm timed out waiting for a peer; its results are invalid")
+
+
+_REDUCE_NORM: dict = {}
+
+
+def enable_reduce_norm(group=None, device: Optional[torch.device] = None, cols: int = 4096) -> Optional[ReduceNorm]:
+    """Collective.  Sets up K7n for ``group`` and hidden size ``cols``; None when symmetric memory is not available (the
+    caller keeps K7 / NCCL + K4)."""
+    key = (group, int(cols))
+    if key in _REDUCE_NORM:
+        return _REDUCE_NORM[key]
+    obj = None
+    if dist.is_initialized() and dist.get_world_size(group) > 1 and torch.cuda.is_available():
+        dev = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        try:
+            obj = ReduceNorm(group, dev, cols)
+        except Exception as e:                                     # noqa: BLE001
+            import warnings
+            warnings.warn(f"q100.peer: fused all-reduce + norm unavailable ({e!r})")
+            obj = None
+    _REDUCE_NORM[key] = obj
+    return obj
+
+
+def get_reduce_norm(group=None, cols: int = 4096) -> Optional[ReduceNorm]:
+    return _REDUCE_NORM.get((group, int(cols)))
+
+
 _SCATTER: dict = {}
 
 
@@ -268,8 +350,10 @@ def get(group=None) -> Optional[OneShotAllReduce]:
 
 def shutdown() -> None:
     """Drop the peer buffers of every group (call before dist.destroy_process_group).  Raises if a call timed out."""
-    objs = [o for o in _STATE.values() if o is not None] + [o for o in _SCATTER.values() if o is not None]
+    objs = [o for o in _STATE.values() if o is not None] + [o for o in _SCATTER.values() if o is not None] \
+        + [o for o in _REDUCE_NORM.values() if o is not None]
     _STATE.clear()
     _SCATTER.clear()
+    _REDUCE_NORM.clear()
     for o in objs:
         o.check()

@@ -128,3 +128,36 @@ def test_markstein_scale_division_exhaustive():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "check_markstein.py")], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+def _fake_packed(n_bits, group, N, K, disable_zp=False):
+    from q100 import ops
+    e = torch.empty(0)
+    return ops.PackedWeight(e, torch.empty(0, dtype=torch.float16), e, None if disable_zp else e, n_bits, group, N, K,
+                            disable_zp)
+
+
+def test_k3d_route_conditions():
+    """q100_gemm_w8a8 (K3d) takes per-channel 8-bit weights with zero-points only (include/q100.h); everything else keeps
+    the reference's two steps at prefill sizes."""
+    from q100 import ops
+    assert ops.gemm_w8a8_supported(2048, _fake_packed(8, 4096, 4096, 4096))
+    assert not ops.gemm_w8a8_supported(2048, _fake_packed(8, 128, 4096, 4096))        # group-wise
+    assert not ops.gemm_w8a8_supported(2048, _fake_packed(4, 4096, 4096, 4096))       # W4: nibble operands
+    assert not ops.gemm_w8a8_supported(2048, _fake_packed(8, 4096, 4096, 4096, True)) # no zero-point
+    assert not ops.gemm_w8a8_supported(2048, _fake_packed(8, 4160, 4096, 4160))       # K % 128
+    assert not ops.gemm_w8a8_supported(2048, _fake_packed(8, 65536, 4096, 65536))     # int32 accumulator bound
+    assert not ops.gemm_w8a8_supported(0, _fake_packed(8, 4096, 4096, 4096))
+    with pytest.raises(RuntimeError):
+        ops.gemm_w8a8(torch.zeros(16, 4096, dtype=torch.float16), _fake_packed(8, 4096, 4096, 4096))   # no CPU path
+
+
+def test_k8_route_conditions():
+    from q100 import ops
+    assert ops.attn_decode_supported(32, 8, 128) and ops.attn_decode_supported(64, 8, 128)
+    assert ops.attn_decode_supported(4, 1, 128) and ops.attn_decode_supported(8, 8, 128)
+    assert not ops.attn_decode_supported(32, 8, 64)          # head_dim
+    assert not ops.attn_decode_supported(32, 2, 128)         # 16 query heads per kv head
+    assert not ops.attn_decode_supported(30, 8, 128)
+    with pytest.raises(RuntimeError):
+        ops.argmax_rows(torch.zeros(2, 16, dtype=torch.float16))                       # no CPU path

@@ -1,5 +1,6 @@
-export Q100_PEER_VERBOSE=1
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29541 tools/peer_scatter_check.py > gpurun_out/mc8.log 2>&1
-grep -v "^\*\*\*\|OMP_NUM\|^$" gpurun_out/mc8.log | grep -A8 "rank0.*Traceback\|world\|OK" | head -30
-Q100_NO_MULTIMEM=1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29542 tools/peer_scatter_check.py > gpurun_out/sc8.log 2>&1
-grep -v "^\*\*\*\|OMP_NUM\|^$" gpurun_out/sc8.log | grep -A8 "rank0.*Traceback\|world\|OK" | head -30
+for n in 4 8; do
+timeout 700 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 2953$n bench.py --gpus $n --steps 10 --warmup 3 > gpurun_out/r4g_bench_n$n.json 2> gpurun_out/r4g_bench_n$n.err
+echo "n=$n rc=$?"
+grep -v "^\*\*\*\|OMP_NUM\|^$" gpurun_out/r4g_bench_n$n.err | tail -5
+wc -c gpurun_out/r4g_bench_n$n.json
+done
