@@ -182,37 +182,33 @@ __global__ void __launch_bounds__(256) k7b_reduce_bcast(const T* __restrict__ st
 // Per-row epochs in device memory (graph-capturable), two parity sets for slot reuse as in K7, 30 s time-out.
 constexpr int K7N_MAX_ROWS = 64;
 
-template <typename T, int VMAX>
-__global__ void __launch_bounds__(256) k7n_allreduce_add_rmsnorm(const T* __restrict__ x, const T* __restrict__ res,
-                                                                 const T* __restrict__ w, float eps,
-                                                                 T* __restrict__ sum_out, T* __restrict__ norm_out,
-                                                                 T* const* __restrict__ bufs,
-                                                                 uint32_t* const* __restrict__ flags,
-                                                                 uint32_t* __restrict__ epoch_p, int cols, int rank,
-                                                                 int world, uint32_t* __restrict__ err) {
+// One thread per 16-byte vector of the row (cols / 8 <= 1024 threads): a thread's `world` slot reads are independent
+// loads in flight together (with 256 threads and four vectors per thread the rank loop was a chain of dependent round
+// trips: 17 us per call at 8 ranks x 8192 columns).
+template <typename T>
+__global__ void __launch_bounds__(1024) k7n_allreduce_add_rmsnorm(const T* __restrict__ x, const T* __restrict__ res,
+                                                                  const T* __restrict__ w, float eps,
+                                                                  T* __restrict__ sum_out, T* __restrict__ norm_out,
+                                                                  T* const* __restrict__ bufs,
+                                                                  uint32_t* const* __restrict__ flags,
+                                                                  uint32_t* __restrict__ epoch_p, int cols, int rank,
+                                                                  int world, uint32_t* __restrict__ err) {
   using D = DT<T>;
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const int row = blockIdx.x, tid = threadIdx.x;
   const int nvec = cols >> 3;
+  const bool act = tid < nvec;
   const uint32_t e = epoch_p[row] + 1;
   const int par = static_cast<int>(e & 1u);
   const int64_t slot = static_cast<int64_t>(K7N_MAX_ROWS) * cols;           // elements per (parity, rank) slot
+  const int64_t roff = static_cast<int64_t>(row) * cols;
   // ---- push my partial row, peers first
-  uint4 mine[VMAX];
-#pragma unroll
-  for (int k = 0; k < VMAX; ++k) {
-    const int v = tid + k * 256;
-    if (v < nvec) mine[k] = reinterpret_cast<const uint4*>(x + static_cast<int64_t>(row) * cols)[v];
-  }
-  for (int k = 1; k <= world; ++k) {
-    const int p = (rank + k) % world;
-    uint4* dst = reinterpret_cast<uint4*>(bufs[p] + (static_cast<int64_t>(par) * world + rank) * slot +
-                                          static_cast<int64_t>(row) * cols);
-#pragma unroll
-    for (int kk = 0; kk < VMAX; ++kk) {
-      const int v = tid + kk * 256;
-      if (v < nvec) dst[v] = mine[kk];
+  if (act) {
+    const uint4 mine = reinterpret_cast<const uint4*>(x + roff)[tid];
+    for (int k = 1; k <= world; ++k) {
+      const int p = (rank + k) % world;
+      reinterpret_cast<uint4*>(bufs[p] + (static_cast<int64_t>(par) * world + rank) * slot + roff)[tid] = mine;
     }
   }
   __syncthreads();
@@ -226,72 +222,83 @@ __global__ void __launch_bounds__(256) k7n_allreduce_add_rmsnorm(const T* __rest
   }
   __syncthreads();
   // ---- sum in rank order (fp32, one rounding), residual add (rounded to T), sum of squares
-  const T* base = bufs[rank] + static_cast<int64_t>(par) * world * slot + static_cast<int64_t>(row) * cols;
-  const uint4* rr = res ? reinterpret_cast<const uint4*>(res + static_cast<int64_t>(row) * cols) : nullptr;
-  uint4 h[VMAX];
-  float ss = 0.f;
+  uint4 h = make_uint4(0u, 0u, 0u, 0u);
+  if (act) {
+    const T* base = bufs[rank] + static_cast<int64_t>(par) * world * slot + roff;
+    uint4 rv = make_uint4(0u, 0u, 0u, 0u);
+    if (res) rv = reinterpret_cast<const uint4*>(res + roff)[tid];
+    float acc[8];
 #pragma unroll
-  for (int k = 0; k < VMAX; ++k) {
-    const int v = tid + k * 256;
-    if (v < nvec) {
-      float acc[8];
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int r0 = 0; r0 < world; r0 += 8) {                // eight independent loads in flight, summed in rank order
+      uint4 q[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-      for (int r = 0; r < world; ++r) {
-        const uint4 q = __ldcg(reinterpret_cast<const uint4*>(base + r * slot) + v);
-        const float2 a = D::to_f2(q.x), b = D::to_f2(q.y), cc = D::to_f2(q.z), d = D::to_f2(q.w);
-        acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
-        acc[4] += cc.x; acc[5] += cc.y; acc[6] += d.x; acc[7] += d.y;
-      }
-      uint4 a = make_uint4(D::pack2(acc[0], acc[1]), D::pack2(acc[2], acc[3]), D::pack2(acc[4], acc[5]),
-                           D::pack2(acc[6], acc[7]));
-      if (rr) {
-        const uint4 b = rr[v];
-        uint32_t* aw = reinterpret_cast<uint32_t*>(&a);
-        const uint32_t* bw = reinterpret_cast<const uint32_t*>(&b);
+      for (int r = 0; r < 8; ++r)
+        if (r0 + r < world) q[r] = __ldcg(reinterpret_cast<const uint4*>(base + (r0 + r) * slot) + tid);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {                       // residual + hidden_states, rounded to T (K4)
-          const float2 fa = D::to_f2(aw[j]), fb = D::to_f2(bw[j]);
-          aw[j] = D::pack2(__fadd_rn(fb.x, fa.x), __fadd_rn(fb.y, fa.y));
+      for (int r = 0; r < 8; ++r) {
+        if (r0 + r < world) {
+          const float2 a = D::to_f2(q[r].x), b = D::to_f2(q[r].y), cc = D::to_f2(q[r].z), d = D::to_f2(q[r].w);
+          acc[0] += a.x; acc[1] += a.y; acc[2] += b.x; acc[3] += b.y;
+          acc[4] += cc.x; acc[5] += cc.y; acc[6] += d.x; acc[7] += d.y;
         }
       }
-      if (sum_out) reinterpret_cast<uint4*>(sum_out + static_cast<int64_t>(row) * cols)[v] = a;
-      h[k] = a;
-      const uint32_t* aw = reinterpret_cast<const uint32_t*>(&a);
+    }
+    h = make_uint4(D::pack2(acc[0], acc[1]), D::pack2(acc[2], acc[3]), D::pack2(acc[4], acc[5]), D::pack2(acc[6], acc[7]));
+    if (res) {
+      uint32_t* aw = reinterpret_cast<uint32_t*>(&h);
+      const uint32_t* bw = reinterpret_cast<const uint32_t*>(&rv);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = D::to_f2(aw[j]);
-        ss = fmaf(f.x, f.x, ss);
-        ss = fmaf(f.y, f.y, ss);
+      for (int j = 0; j < 4; ++j) {                       // residual + hidden_states, rounded to T (K4)
+        const float2 fa = D::to_f2(aw[j]), fb = D::to_f2(bw[j]);
+        aw[j] = D::pack2(__fadd_rn(fb.x, fa.x), __fadd_rn(fb.y, fa.y));
       }
     }
+    if (sum_out) reinterpret_cast<uint4*>(sum_out + roff)[tid] = h;
   }
+  // the sum of squares in K4's order (bit-identical rstd): K4's thread t runs ONE fmaf chain over the vectors
+  // t, t + 256, t + 512, t + 768; here those vectors belong to four threads, so they meet in shared memory
+  __shared__ uint4 hs[1024];
   __shared__ float red[8];
+  hs[tid] = h;
+  __syncthreads();
+  if (tid < 256) {
+    float ss = 0.f;
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, d);
-  if ((tid & 31) == 0) red[tid >> 5] = ss;
+    for (int k = 0; k < 4; ++k) {
+      const int t = tid + 256 * k;
+      if (t < nvec) {
+        const uint4 a = hs[t];
+        const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = D::to_f2(aw[j]);
+          ss = fmaf(f.x, f.x, ss);
+          ss = fmaf(f.y, f.y, ss);
+        }
+      }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, d);
+    if ((tid & 31) == 0) red[tid >> 5] = ss;
+  }
   __syncthreads();
   float tot = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) tot += red[i];
   const float inv = rsqrtf(__fadd_rn(__fdiv_rn(tot, static_cast<float>(cols)), eps));
-  const uint4* wr = reinterpret_cast<const uint4*>(w);
+  if (act) {
+    const uint4 wv = reinterpret_cast<const uint4*>(w)[tid];
+    const uint32_t* hw = reinterpret_cast<const uint32_t*>(&h);
+    const uint32_t* ww = reinterpret_cast<const uint32_t*>(&wv);
+    uint4 o;
+    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
-  for (int k = 0; k < VMAX; ++k) {
-    const int v = tid + k * 256;
-    if (v < nvec) {
-      const uint4 wv = wr[v];
-      const uint32_t* hw = reinterpret_cast<const uint32_t*>(&h[k]);
-      const uint32_t* ww = reinterpret_cast<const uint32_t*>(&wv);
-      uint4 o;
-      uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {                         // weight * (h * rsqrt(var + eps)), both products in fp32 (K4)
-        const float2 f = D::to_f2(hw[j]), g = D::to_f2(ww[j]);
-        ow[j] = D::pack2(__fmul_rn(g.x, __fmul_rn(f.x, inv)), __fmul_rn(g.y, __fmul_rn(f.y, inv)));
-      }
-      reinterpret_cast<uint4*>(norm_out + static_cast<int64_t>(row) * cols)[v] = o;
+    for (int j = 0; j < 4; ++j) {                         // weight * (h * rsqrt(var + eps)), both products in fp32 (K4)
+      const float2 f = D::to_f2(hw[j]), g = D::to_f2(ww[j]);
+      ow[j] = D::pack2(__fmul_rn(g.x, __fmul_rn(f.x, inv)), __fmul_rn(g.y, __fmul_rn(f.y, inv)));
     }
+    reinterpret_cast<uint4*>(norm_out + roff)[tid] = o;
   }
   if (tid == 0) epoch_p[row] = e;
 }
@@ -482,20 +489,20 @@ extern "C" int q100_allreduce_add_rmsnorm(const void* x, const void* residual, c
   cfg.numAttrs = 1;
   const int nvec = static_cast<int>(cols / 8);
   const int c = static_cast<int>(cols);
+  cfg.blockDim = dim3(static_cast<unsigned>(((nvec + 255) / 256) * 256));      // one thread per 16-byte vector, whole K4 "columns"
   uint32_t* ef = reinterpret_cast<uint32_t*>(err_flag);
   uint32_t* ep = reinterpret_cast<uint32_t*>(epoch);
   uint32_t* const* fl = reinterpret_cast<uint32_t* const*>(peer_flags);
   cudaError_t e;
-#define Q100_K7N(TT, V)                                                                                              \
-  e = cudaLaunchKernelEx(&cfg, k7n_allreduce_add_rmsnorm<TT, V>, reinterpret_cast<const TT*>(x),                     \
-                         reinterpret_cast<const TT*>(residual), reinterpret_cast<const TT*>(weight), eps,            \
-                         reinterpret_cast<TT*>(sum_out), reinterpret_cast<TT*>(norm_out),                            \
-                         reinterpret_cast<TT* const*>(peer_bufs), fl, ep, c, rank, world, ef)
-  if (dtype == Q100_F16) {
-    if (nvec <= 256) Q100_K7N(__half, 1); else if (nvec <= 512) Q100_K7N(__half, 2); else Q100_K7N(__half, 4);
-  } else {
-    if (nvec <= 256) Q100_K7N(__nv_bfloat16, 1); else if (nvec <= 512) Q100_K7N(__nv_bfloat16, 2); else Q100_K7N(__nv_bfloat16, 4);
-  }
-#undef Q100_K7N
+  if (dtype == Q100_F16)
+    e = cudaLaunchKernelEx(&cfg, k7n_allreduce_add_rmsnorm<__half>, reinterpret_cast<const __half*>(x),
+                           reinterpret_cast<const __half*>(residual), reinterpret_cast<const __half*>(weight), eps,
+                           reinterpret_cast<__half*>(sum_out), reinterpret_cast<__half*>(norm_out),
+                           reinterpret_cast<__half* const*>(peer_bufs), fl, ep, c, rank, world, ef);
+  else
+    e = cudaLaunchKernelEx(&cfg, k7n_allreduce_add_rmsnorm<__nv_bfloat16>, reinterpret_cast<const __nv_bfloat16*>(x),
+                           reinterpret_cast<const __nv_bfloat16*>(residual), reinterpret_cast<const __nv_bfloat16*>(weight),
+                           eps, reinterpret_cast<__nv_bfloat16*>(sum_out), reinterpret_cast<__nv_bfloat16*>(norm_out),
+                           reinterpret_cast<__nv_bfloat16* const*>(peer_bufs), fl, ep, c, rank, world, ef);
   return check_cuda(e, "k7n_allreduce_add_rmsnorm launch");
 }
