@@ -743,7 +743,7 @@ def run_ours(args):
                 import traceback
                 traceback.print_exc(file=sys.stderr)
                 return {"error": f"{type(ex).__name__}: {ex}"[:400]}
-        model_res = row(ppl_samples=1, ppl_ref=True)
+        model_res = row(ppl_samples=1, ppl_ref=True, quant_head=not os.environ.get("Q100_BENCH_SKIP_QUANT_HEAD"))
         extra["llama3_8b"] = model_res
         # SURVEY 8d config 5 (BASELINE.json configs[4]): LLaMA3-70B W4A16 g128, tensor parallel over all ranks (the
         # packed model is 38 GB: it also fits one B200, so the row exists at every N).  Perplexity is compared on the

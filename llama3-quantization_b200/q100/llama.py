@@ -11,7 +11,8 @@ kept: an 8B model is 4.3 GB of W4 codes, a 70B shard at TP=8 is 4.5 GB per GPU.
 
 Tensor parallel layout per block (q100/tp.py): q/k/v/gate/up column shards (heads split across ranks),
 o/down row shards, one all-reduce after o_proj and after down_proj.  Embedding, norms and lm_head are
-replicated (lm_head is unquantised fp16/bf16 in the reference as well).
+replicated (lm_head is unquantised fp16/bf16 in the reference as well; ``QuantLlamaModel.quantize_head`` is the
+opt-in that puts it on packed codes too).
 """
 from __future__ import annotations
 
@@ -140,6 +141,36 @@ class QuantLlamaModel(nn.Module):
         self.register_buffer("embed_tokens", embed)
         self.register_buffer("norm_weight", norm_w)
         self.register_buffer("lm_head", lm_head)
+        self.head_linear = None          # set by quantize_head(): lm_head as a QuantLinear on packed codes
+
+    # ------------------------------------------------------------------ lm_head
+    @torch.no_grad()
+    def quantize_head(self, wbits: int = 4, group_size: Optional[int] = 128, keep_dense: bool = False):
+        """Opt-in extension: the reference leaves ``lm_head`` in 16 bits (1.05 GB of an 8B model's 5.4 GB decode
+        stream at W4).  This wraps it in the drop-in ``QuantLinear`` with the reference's weight-quantizer
+        parameters (main.py:317-325), quantises it in place the way ``smooth_and_quant_inplace`` treats a block's
+        linears (int_llama_layer.py:307-324: ``weight <- weight_quantizer(weight)``) and keeps the packed twin, so
+        the logits come from the same fused dequant-GEMM as every other linear.  ``lm_head`` becomes the
+        fake-quantised dense weight (``keep_dense``) or is dropped."""
+        from quant.int_linear import QuantLinear
+        if self.lm_head is None or self.lm_head.numel() == 0:
+            raise RuntimeError("quantize_head: the model has no dense lm_head to quantise")
+        wq = quant_args(wbits, group_size).weight_quant_params
+        m = QuantLinear(_linear(self.lm_head), wq, {}, disable_input_quant=True)
+        m.weight = m.weight_quantizer(m.weight)
+        m.set_quant_state(weight_quant=False, act_quant=False)
+        if m.weight_quantizer.packed_for(m.weight) is None:
+            raise RuntimeError("quantize_head: no packed form for this lm_head (needs CUDA, 16-bit, K % 128 == 0)")
+        self.lm_head = m.weight if keep_dense else torch.empty(0, dtype=m.weight.dtype, device=m.weight.device)
+        if not keep_dense:
+            m.release_dense_weight()
+        self.head_linear = m
+        return m
+
+    def head(self, x: torch.Tensor) -> torch.Tensor:
+        if self.head_linear is not None:
+            return self.head_linear(x)
+        return F.linear(x, self.lm_head)
 
     # ------------------------------------------------------------------ construction
     @classmethod
@@ -202,7 +233,7 @@ class QuantLlamaModel(nn.Module):
 
     @torch.no_grad()
     def logits(self, tokens):
-        return F.linear(self.forward(tokens), self.lm_head)
+        return self.head(self.forward(tokens))
 
     @torch.no_grad()
     def perplexity(self, testenc: torch.Tensor, seqlen: int):
@@ -339,7 +370,7 @@ class GraphDecoder:
         _ops.add_rmsnorm(b["h"], l0.input_layernorm.weight, l0.input_layernorm.variance_epsilon, out_norm=b["n1"])
         self.chain.run()
         x = _ops.add_rmsnorm(b["h"], m.norm_weight, m.cfg.rms_norm_eps)[1]
-        logits = F.linear(x.view(self.bsz, 1, -1), m.lm_head)
+        logits = m.head(x.view(self.bsz, 1, -1))
         self.last_logits = logits
         if logits.dtype in (torch.float16, torch.bfloat16) and logits.shape[-1] % 8 == 0:
             from . import ops as _ops
@@ -382,7 +413,7 @@ class GraphDecoder:
                 x = _ops.add_rmsnorm(x, m.norm_weight, m.cfg.rms_norm_eps, res)[1]
         else:
             x = m._norm(x)
-        logits = F.linear(x, m.lm_head)
+        logits = m.head(x)
         self.last_logits = logits
         if logits.dtype in (torch.float16, torch.bfloat16) and logits.shape[-1] % 8 == 0:
             from . import ops as _ops

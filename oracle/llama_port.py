@@ -105,15 +105,19 @@ def _aq(x, cfg: BlockCfg, act_quant: bool):
 
 def block_forward(x, w: Dict[str, torch.Tensor], cfg: BlockCfg, attention_mask=None, position_ids=None,
                   past_key_value: Optional[Tuple[torch.Tensor, torch.Tensor]] = None, use_cache=False,
-                  act_quant=False):
-    """QuantLlamaDecoderLayer.forward on (already fake-quantised) dense weights ``w``."""
+                  act_quant=False, linear=None):
+    """QuantLlamaDecoderLayer.forward on (already fake-quantised) dense weights ``w``.  ``linear`` replaces
+    ``F.linear`` (the reference's ``fwd_func``, int_linear.py:26): ``linear_fp32_once`` below is the same product with
+    another, equally valid, accumulation -- used to measure how far the REFERENCE's own perplexity moves with the GEMM's
+    rounding (the yardstick for abits < 16, where one flipped activation code is a discrete step)."""
+    lin = linear if linear is not None else F.linear
     bsz, q_len, _ = x.shape
     residual = x
     h = rms_norm(x, w["input_layernorm"], cfg.eps)
     hq = _aq(h, cfg, act_quant)
-    q = F.linear(hq, w["q_proj"]).view(bsz, q_len, cfg.heads, cfg.head_dim).transpose(1, 2).type(torch.float32)
-    k = F.linear(hq, w["k_proj"]).view(bsz, q_len, cfg.kv_heads, cfg.head_dim).transpose(1, 2)
-    v = F.linear(hq, w["v_proj"]).view(bsz, q_len, cfg.kv_heads, cfg.head_dim).transpose(1, 2)
+    q = lin(hq, w["q_proj"]).view(bsz, q_len, cfg.heads, cfg.head_dim).transpose(1, 2).type(torch.float32)
+    k = lin(hq, w["k_proj"]).view(bsz, q_len, cfg.kv_heads, cfg.head_dim).transpose(1, 2)
+    v = lin(hq, w["v_proj"]).view(bsz, q_len, cfg.kv_heads, cfg.head_dim).transpose(1, 2)
     kv_len = k.shape[-2] + (past_key_value[0].shape[-2] if past_key_value is not None else 0)
     cos, sin = rotary_cache(cfg.head_dim, kv_len, cfg.rope_theta, x.device, v.dtype)
     if position_ids is None:
@@ -136,13 +140,13 @@ def block_forward(x, w: Dict[str, torch.Tensor], cfg: BlockCfg, attention_mask=N
     att = F.softmax(att, dim=-1, dtype=torch.float32).to(q.dtype)
     v2 = _aq(v2, cfg, act_quant)
     o = torch.matmul(att, v2).transpose(1, 2).reshape(bsz, q_len, cfg.hidden)
-    o = F.linear(_aq(o, cfg, act_quant), w["o_proj"])
+    o = lin(_aq(o, cfg, act_quant), w["o_proj"])
     x = residual + o
     residual = x
     h = rms_norm(x, w["post_attention_layernorm"], cfg.eps)
     hq = _aq(h, cfg, act_quant)
-    m = F.silu(F.linear(hq, w["gate_proj"])) * F.linear(hq, w["up_proj"])
-    x = residual + F.linear(_aq(m, cfg, act_quant), w["down_proj"])
+    m = F.silu(lin(hq, w["gate_proj"])) * lin(hq, w["up_proj"])
+    x = residual + lin(_aq(m, cfg, act_quant), w["down_proj"])
     return x, present
 
 
@@ -160,14 +164,22 @@ def random_block_weights(cfg: BlockCfg, seed: int, dtype=torch.float32, device="
 
 
 # ------------------------------------------------------------------------------------ whole model
-def model_forward(tokens, embed, blocks, final_norm, cfg: BlockCfg, act_quant=False):
+def linear_fp32_once(x, w, b=None):
+    """x @ w.T accumulated in fp32 by an fp32 GEMM (no tensor-core split of the K loop) and rounded once."""
+    y = torch.matmul(x.to(torch.float32), w.to(torch.float32).t())
+    if b is not None:
+        y = y + b.to(torch.float32)
+    return y.to(x.dtype)
+
+
+def model_forward(tokens, embed, blocks, final_norm, cfg: BlockCfg, act_quant=False, linear=None):
     """LlamaModel.forward without cache: embedding -> blocks (causal mask) -> final RMSNorm."""
     bsz, q_len = tokens.shape
     x = F.embedding(tokens, embed)
     mask = causal_mask(bsz, q_len, q_len, x.dtype, x.device)
     pos = torch.arange(q_len, device=x.device).unsqueeze(0)
     for w in blocks:
-        x, _ = block_forward(x, w, cfg, attention_mask=mask, position_ids=pos, act_quant=act_quant)
+        x, _ = block_forward(x, w, cfg, attention_mask=mask, position_ids=pos, act_quant=act_quant, linear=linear)
     return rms_norm(x, final_norm, cfg.eps)
 
 

@@ -20,6 +20,7 @@ import pytest
 import torch
 
 import llama_port as LP
+import torch_port as TP
 from conftest import load_golden
 
 GOLD = load_golden("block")
@@ -234,3 +235,73 @@ def test_model_perplexity_delta(wbits, group):
     ppl_ref, nll_ref = LP.perplexity(testenc, seqlen, logits_fn)
     assert abs(nll - nll_ref) <= 1.6e-3, (nll, nll_ref)
     assert abs(ppl - ppl_ref) / ppl_ref <= 1.6e-3, (ppl, ppl_ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("wbits,group,keep", [(4, 128, False), (4, 128, True), (8, 128, False), (2, 64, False)])
+def test_model_quantized_head(wbits, group, keep):
+    """SURVEY section 8 row f4 (opt-in extension): ``QuantLlamaModel.quantize_head`` puts lm_head through the drop-in
+    QuantLinear.  The packed head dequantises to the reference op sequence's fake-quantised weight bit for bit, the
+    logits agree with F.linear on that weight within the GEMM tolerance of tests/test_parity_gemm.py (prefill rows
+    and a single decode row), perplexity meets the 1.6e-3 bar against the port with the same head, and a graph
+    decode step picks the token the dense computation picks."""
+    from q100 import llama as QL, ops as Q
+    dev = torch.device("cuda:0")
+    cfg = QL.LlamaCfg(512, 1024, 8, 2, 2, 2048)
+    model = QL.QuantLlamaModel.random_init(cfg, QL.quant_args(4, 128), dev, torch.float16, seed=5)
+    dense = model.lm_head.clone()
+    head_fq = TP.fake_quant(dense.cpu(), wbits, group)[0].to(dev)       # CPU: the division semantics the oracle pins
+    m = model.quantize_head(wbits, group, keep_dense=keep)
+    assert model.head_linear is m and (model.lm_head.numel() == dense.numel()) == keep
+    pw = m.weight_quantizer.packed_for(m.weight)
+    assert pw is not None
+    assert torch.equal(Q.dequantize(pw.packed, pw.scales, pw.zeros, pw.N, pw.K, pw.group, pw.n_bits, torch.float16),
+                       head_fq)
+    if keep:
+        assert torch.equal(model.lm_head, head_fq)
+
+    g = torch.Generator().manual_seed(2)
+    for rows in (1, 4, 300):
+        x = (torch.randn(1, rows, cfg.hidden_size, generator=g) * 0.5).to(dev, torch.float16)
+        got = model.head(x).double()
+        ref = x.double() @ head_fq.double().t()
+        mag = x.double().abs() @ head_fq.double().abs().t()
+        # tests/test_parity_gemm.py, default decode kernel form (covers the exact-weight prefill kernel as well)
+        tol = 2 * 2.0 ** -11 * ref.abs() + 8 * 2.0 ** -12 * ((x.double() ** 2) @ (head_fq.double() ** 2).t()).sqrt() \
+            + 8 * 2.0 ** -24 * mag + 1e-7
+        assert bool(((got - ref).abs() <= tol).all()), float((got - ref).abs().max())
+
+    seqlen = 256
+    testenc = torch.randint(0, cfg.vocab_size, (1, 2 * seqlen), generator=g)
+    ppl, nll = model.perplexity(testenc, seqlen)
+    bc = LP.BlockCfg(cfg.hidden_size, cfg.intermediate_size, cfg.num_attention_heads, cfg.num_key_value_heads,
+                     cfg.rms_norm_eps, cfg.rope_theta, 4, 128)
+    blocks = [LP.fake_quant_weights(QL.random_block_weights(cfg, li, 5, dev, torch.float16), bc)
+              for li in range(cfg.num_hidden_layers)]
+
+    def logits_fn(batch):
+        with torch.no_grad():
+            h = LP.model_forward(batch.to(dev), model.embed_tokens, blocks, model.norm_weight, bc)
+            return torch.nn.functional.linear(h, head_fq).float()
+    ppl_ref, nll_ref = LP.perplexity(testenc, seqlen, logits_fn)
+    assert abs(nll - nll_ref) <= 1.6e-3, (nll, nll_ref)
+
+    dec = QL.GraphDecoder(model, 2, 64)
+    dec.prime(3)
+    tok = torch.randint(0, cfg.vocab_size, (2, 1), generator=g).to(dev)
+    dec.step(tok)
+    torch.cuda.synchronize()
+    lg = dec.last_logits.view(2, -1).float()
+    assert lg.shape[-1] == cfg.vocab_size and bool(torch.isfinite(lg).all())
+    assert torch.equal(dec.next_tok.view(-1), lg.argmax(-1))
+
+
+@pytest.mark.gpu
+def test_quantize_head_refuses_twice():
+    from q100 import llama as QL
+    dev = torch.device("cuda:0")
+    model = QL.QuantLlamaModel.random_init(QL.LlamaCfg(256, 512, 4, 2, 1, 1024), QL.quant_args(4, 128), dev,
+                                           torch.float16, seed=1)
+    model.quantize_head(4, 128)
+    with pytest.raises(RuntimeError):
+        model.quantize_head(4, 128)

@@ -125,3 +125,22 @@ def test_rounding_helpers():
     # round_ste: -0 -> +0, inf -> nan
     r = O.round_ste(np.array([-0.2, np.inf, 2.5, 3.5], np.float32), "f32")
     assert not np.signbit(r[0]) and np.isnan(r[1]) and r[2] == 2.0 and r[3] == 4.0
+
+
+def test_port_linear_hook_is_the_same_product():
+    """``llama_port.block_forward(linear=...)``: the hook bench_model.py uses to measure how far the REFERENCE's own
+    perplexity moves when its linears accumulate differently (the yardstick for abits < 16).  In fp32 the two forms
+    are the same product up to accumulation order."""
+    import llama_port as LP
+    cfg = LP.BlockCfg(128, 256, 4, 2, w_bits=4, group=64, a_bits=8)
+    w = LP.fake_quant_weights(LP.random_block_weights(cfg, 7), cfg)
+    x = torch.randn(1, 9, 128, generator=torch.Generator().manual_seed(0))
+    calls = []
+
+    def counting(x_, w_, b_=None):
+        calls.append(tuple(w_.shape))
+        return LP.linear_fp32_once(x_, w_, b_)
+    a = LP.block_forward(x, w, cfg, act_quant=True)[0]
+    b = LP.block_forward(x, w, cfg, act_quant=True, linear=counting)[0]
+    assert len(calls) == 7
+    assert torch.allclose(a, b, rtol=1e-4, atol=1e-5)
