@@ -159,6 +159,9 @@ __global__ void __launch_bounds__(256) k1_backward(const BwdArgs b) {
     if (gxo != nullptr) {
       const float pmax = (g_xmax_c * su) / static_cast<float>(nmax);
       const float pmin = (g_xmin_c * sl) / static_cast<float>(nmin);
+      // a NaN anywhere in the group makes amin / amax and with them the scale NaN: autograd through the reference op
+      // sequence (0 / NaN in the division's backward, a 0 / 0 share of the extrema) then yields NaN for every element
+      const bool nan_group = (mn != mn) || (mx != mx);
 #pragma unroll
       for (int k = 0; k < V; ++k) {
         float xf[E], gf[E], o[E];
@@ -169,7 +172,7 @@ __global__ void __launch_bounds__(256) k1_backward(const BwdArgs b) {
           float r = ((inside_bits >> (k * E + i)) & 1u) ? gf[i] : 0.f;
           if (xf[i] == mx) r += pmax;
           if (xf[i] == mn) r += pmin;
-          o[i] = r;
+          o[i] = nan_group ? __int_as_float(0x7fc00000) : r;
         }
         if (valid) stg_stream(gxo + g * (L * V) + k * L + l, Vec16<T>::pack(o));
       }

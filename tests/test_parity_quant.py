@@ -255,6 +255,7 @@ def test_backward_kernel_vs_op_by_op(dtype, n_bits, group):
     x = (torch.randn(rows, cols, generator=gen) * 0.05).to(TDT[dtype]).cuda()
     x[3, :group] = 0.25                                     # constant group: every element is both min and max
     x[4, 5] = x[4, 6] = x[4, :group].max()                  # tied maxima
+    x[6, group + 3] = float("nan")                          # NaN group: every gradient of the group is NaN
     go = torch.randn(rows, cols, generator=gen).to(TDT[dtype]).cuda()
     ng = rows * cols // group
     su = (torch.rand(ng, 1, generator=gen) * 0.4 + 0.6).to(TDT[dtype]).cuda()
@@ -276,6 +277,8 @@ def test_backward_kernel_vs_op_by_op(dtype, n_bits, group):
                 assert g_ is None, name + " " + tag
                 continue
             g64, w64 = g_.double(), w_.double()
+            assert torch.equal(g64.isnan(), w64.isnan()), f"{name} {tag}: NaN pattern differs"
+            g64, w64 = g64.nan_to_num(0.0), w64.nan_to_num(0.0)
             err = (g64 - w64).abs()
             # 16-bit: torch rounds every product of the group sum to the storage type before adding, the kernel keeps
             # fp32 -- the reference's own noise scales with the largest term, not with the (cancelling) sum
