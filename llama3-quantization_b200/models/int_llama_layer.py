@@ -17,9 +17,11 @@ B200-specific sits underneath:
 * under tensor parallelism (``tp_world > 1``) q/k/v/gate/up hold column shards, o/down row shards, and
   the one collective is the all-reduce after o_proj and down_proj (q100/tp.py).
 
-The attention core between the two ``QuantMatMul``s is the reference's eager formulation (fp32 softmax);
-with ``fast_attention = True`` and no activation quantisation it is ``scaled_dot_product_attention``
-(a library kernel; the attention core is SURVEY section 8 row f3, not part of this path).
+The attention core between the two ``QuantMatMul``s is the reference's eager formulation (fp32 softmax), with one
+exact re-ordering: K and V pass their per-(head, token) quantisers BEFORE ``repeat_kv`` (a quarter of the rows, the
+same bits).  With ``fast_attention = True`` the core is ``scaled_dot_product_attention`` on the (fake-quantised, when
+activation quantisation is on) Q / K / V with ``enable_gqa`` -- no ``[B, heads, T, T]`` tensor, no expanded K / V (a
+library kernel; the prefill attention core is SURVEY section 8 row f3, the single-token form is K8).
 
 The rotary embedding follows transformers 4.37 (the version the reference pins): ``rotary_emb(x, seq_len)``
 returns the ``[seq_len, head_dim]`` cos/sin cache which ``apply_rotary_pos_emb`` indexes by position.  If
@@ -333,16 +335,20 @@ class QuantLlamaAttention(nn.Module):
             query_states = query_states.to(key_states.dtype)
         n_rep = nh // nkv
 
-        if self.fast_attention and not self.use_act_quant and not output_attentions:
+        # K / V are quantised per (head, token) row over head_dim, and repeat_kv only copies whole heads: quantising the
+        # nkv heads BEFORE the GQA expansion gives bit for bit the rows the reference gets from quantising the expanded
+        # tensor (int_llama_layer.py:136-141), on a quarter of the rows
+        if self.sdpa_route() and not output_attentions:
+            query_states = self.qkt_matmul.quant_x1(query_states)
+            key_states = self.qkt_matmul.quant_x2(key_states)
+            value_states = self.pv_matmul.quant_x2(value_states)
             attn_output = F.scaled_dot_product_attention(
                 query_states, key_states, value_states, attn_mask=attention_mask,
                 is_causal=attention_mask is None and q_len > 1, enable_gqa=n_rep > 1)
             attn_weights = None
         else:
-            key_states = repeat_kv(key_states, n_rep)
-            value_states = repeat_kv(value_states, n_rep)
+            key_states = repeat_kv(self.qkt_matmul.quant_x2(key_states), n_rep)
             query_states = self.qkt_matmul.quant_x1(query_states)
-            key_states = self.qkt_matmul.quant_x2(key_states)
             attn_weights = self.qkt_matmul(query_states, key_states.transpose(2, 3)) / math.sqrt(self.head_dim)
             if attn_weights.size() != (bsz, nh, q_len, kv_seq_len):
                 raise ValueError(
@@ -359,7 +365,7 @@ class QuantLlamaAttention(nn.Module):
             # upcast attention to fp32
             attn_weights = nn.functional.softmax(attn_weights, dim=-1, dtype=torch.float32).to(query_states.dtype)
             attn_weights = self.pv_matmul.quant_x1(attn_weights)
-            value_states = self.pv_matmul.quant_x2(value_states)
+            value_states = repeat_kv(self.pv_matmul.quant_x2(value_states), n_rep)
             attn_output = self.pv_matmul(attn_weights, value_states)
 
         if attn_output.size() != (bsz, nh, q_len, self.head_dim):
@@ -375,6 +381,14 @@ class QuantLlamaAttention(nn.Module):
         if not output_attentions:
             attn_weights = None
         return attn_output, attn_weights, past_key_value
+
+    def sdpa_route(self) -> bool:
+        """``fast_attention`` (extension) sends the attention core through ``scaled_dot_product_attention`` -- on the
+        fake-quantised Q / K / V when activation quantisation is on -- unless the softmax output has a quantiser of its
+        own to pass (the reference's ``p_quant_params`` are 16 bits: identity)."""
+        pv = self.pv_matmul
+        pq = pv.x1_quantizer
+        return bool(self.fast_attention) and (not pv.use_act_quant or pq.n_bits >= 16 or not pq.enable)
 
     def set_quant_state(self, weight_quant: bool = False, act_quant: bool = False):
         # setting weight quantization here does not affect actual forward pass

@@ -216,7 +216,7 @@ class QuantLlamaModel(nn.Module):
         bsz, q_len = tokens.shape
         past_len = 0 if past is None else past[0][0].shape[-2]
         x = F.embedding(tokens, self.embed_tokens)
-        fast = all(l.self_attn.fast_attention and not l.self_attn.use_act_quant for l in self.layers)
+        fast = all(l.self_attn.sdpa_route() for l in self.layers)
         mask = None
         if not (fast and (q_len == 1 or past_len == 0)):
             mask = self.causal_mask(bsz, q_len, past_len + q_len, x.dtype, x.device)

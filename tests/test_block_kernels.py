@@ -327,3 +327,111 @@ def test_argmax_rows(dtype, rows, cols):
     assert all(int(v) == 0 for v in out[1:, 0])
     x[0, 0, cols - 1] = float("nan")
     assert int(ops.argmax_rows(x)[0, 0]) == cols - 1 == int(torch.argmax(x[0, 0]))
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("abits", [8, 4])
+def test_kv_quantised_before_repeat_kv_is_exact(dtype, abits):
+    """QuantMatMul.quant_x2 works per (head, token) row over head_dim and repeat_kv copies whole heads, so the block
+    quantises the kv heads before the GQA expansion: the same bits as the reference's order
+    (int_llama_layer.py:134-141: repeat_kv first), a quarter of the rows."""
+    from models.int_llama_layer import repeat_kv
+    from quant.int_matmul import QuantMatMul
+    dev = torch.device("cuda:0")
+    act = {"n_bits": abits, "per_channel_axes": [], "symmetric": False, "dynamic_method": "per_token"}
+    mm = QuantMatMul(act, act, matmul_func=torch.matmul).to(dev)
+    mm.set_quant_state(False, True)
+    g = torch.Generator(device=dev).manual_seed(abits)
+    k = (torch.randn(2, 2, 37, 128, generator=g, device=dev) * 1.7).to(dtype)
+    k[0, 1, 5] = 0                                       # a constant row (scale at its lower clamp)
+    a = repeat_kv(mm.quant_x2(k), 4)
+    b = mm.quant_x2(repeat_kv(k, 4))
+    assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("wbits,abits,group", [(8, 8, None), (4, 4, None), (4, 8, 128)])
+def test_fast_attention_with_act_quant_matches_reference_formulation(wbits, abits, group):
+    """``fast_attention`` with activation quantisation on: SDPA on the fake-quantised Q / K / V (kv heads, no
+    expansion) against the reference formulation of the same block -- prefill with a causal mask, then one decode
+    step on a static cache.  The same fake-quantised tensors enter softmax(QK^T)V on both sides; what differs is the
+    library kernel's online softmax against the fp32 softmax rounded to 16 bits.
+    (i) attention module with o_proj's input quantiser off (nothing discrete behind the core): a few 16-bit ulps of
+    the largest output; (ii) the whole block with every quantiser on: a 1-ulp difference may flip codes of o_proj's
+    and the MLP's per-token quantisers (one A4 step is 1/15 of a row's range), so the bound is on the relative
+    Frobenius distance -- 1e-2 (A8) / 6e-2 (A4); a wrong mask or head mapping gives O(1)."""
+    from q100 import llama as QL
+    from models.int_llama_layer import StaticKV
+    dev, dtype = torch.device("cuda:0"), torch.float16
+    cfg = QL.LlamaCfg(512, 1024, 8, 2, 1, 64)
+    args = QL.quant_args(wbits, group, abits)
+    layer = QL.build_block(cfg, QL.random_block_weights(cfg, 0, 11, dev, dtype), args)
+    attn = layer.self_attn
+    assert attn.use_act_quant and attn.qkt_matmul.use_act_quant
+    g = torch.Generator(device=dev).manual_seed(3)
+    T = 48
+    x = torch.randn(2, T, 512, generator=g, device=dev).to(dtype)
+    pos = torch.arange(T, device=dev).unsqueeze(0)
+    mask = QL.QuantLlamaModel.causal_mask(2, T, T, dtype, dev)
+    fro_tol = 1e-2 if abits == 8 else 6e-2
+
+    def rel_max(a, b):
+        return (a.float() - b.float()).abs().max().item() / b.float().abs().max().item()
+
+    def rel_fro(a, b):
+        return ((a.float() - b.float()).norm() / b.float().norm()).item()
+
+    def both(fn):
+        out = []
+        for fast in (False, True):
+            attn.fast_attention = fast
+            assert attn.sdpa_route() == fast
+            with torch.no_grad():
+                out.append(fn())
+        return out
+
+    # (i) the core alone
+    attn.o_proj.use_act_quant = False
+    h = layer.input_layernorm(x)
+    ref, got = both(lambda: attn(h, attention_mask=mask, position_ids=pos)[0])
+    attn.fast_attention = True
+    with torch.no_grad():
+        got_causal = attn(h, attention_mask=None, position_ids=pos)[0]        # what QuantLlamaModel.forward passes
+    assert rel_max(got, ref) <= 8 * _ulp(dtype), rel_max(got, ref)
+    assert rel_max(got_causal, ref) <= 8 * _ulp(dtype), rel_max(got_causal, ref)
+    attn.o_proj.use_act_quant = True
+
+    # (ii) the whole block, every quantiser on
+    ref, got = both(lambda: layer(x, attention_mask=mask, position_ids=pos)[0])
+    assert rel_fro(got, ref) <= fro_tol, rel_fro(got, ref)
+
+    # decode step on a static cache: the cache rows are quantised on the kv heads, unwritten slots are masked
+    bsz, max_len, ctx = 2, 32, 9
+    kvs = []
+    k0 = torch.randn(bsz, 2, ctx, 64, generator=g, device=dev).to(dtype)
+    v0 = torch.randn(bsz, 2, ctx, 64, generator=g, device=dev).to(dtype)
+    for _ in range(4):
+        kv = StaticKV(bsz, 2, max_len, 64, dtype, dev)
+        kv.k[:, :, :ctx] = k0
+        kv.v[:, :, :ctx] = v0
+        kvs.append(kv)
+    x1 = torch.randn(bsz, 1, 512, generator=g, device=dev).to(dtype)
+    p1 = torch.tensor([[ctx]], device=dev)
+    slots = torch.arange(max_len, device=dev).view(1, 1, 1, max_len)
+    m1 = torch.where(slots <= ctx, 0.0, torch.finfo(dtype).min).to(dtype).expand(bsz, 1, 1, max_len)
+    attn.o_proj.use_act_quant = False
+    h1 = layer.input_layernorm(x1)
+    it = iter(kvs)
+    ref1, got1 = both(lambda: attn(h1, attention_mask=m1, position_ids=p1, past_key_value=next(it))[0])
+    assert rel_max(got1, ref1) <= 8 * _ulp(dtype), rel_max(got1, ref1)
+    attn.o_proj.use_act_quant = True
+    ref2, got2 = both(lambda: layer(x1, attention_mask=m1, position_ids=p1, past_key_value=next(it), use_cache=False)[0])
+    assert rel_fro(got2, ref2) <= fro_tol, rel_fro(got2, ref2)
+    for kv in kvs[1:]:
+        assert torch.equal(kv.k, kvs[0].k) and torch.equal(kv.v, kvs[0].v)
+
+    # a softmax-output quantiser of its own keeps the reference formulation
+    attn.fast_attention = True
+    attn.pv_matmul.x1_quantizer.change_n_bits(8)
+    assert not attn.sdpa_route()
+    attn.pv_matmul.x1_quantizer.change_n_bits(16)
+    assert attn.sdpa_route()
