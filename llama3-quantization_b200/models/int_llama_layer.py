@@ -465,13 +465,22 @@ class QuantLlamaDecoderLayer(nn.Module):
         the caller states that ``attention_mask`` is the plain static-cache mask (``causal_cache``: every slot up to the
         position visible), else K5 + scaled_dot_product_attention with the mask.  Returns [bsz, nh * head_dim]."""
         import os
-        hd = self.self_attn.head_dim
+        attn = self.self_attn
+        hd = attn.head_dim
+        act_q = attn.qkt_matmul.use_act_quant or attn.pv_matmul.use_act_quant
         k8_max = int(os.environ.get("Q100_K8_MAX_BATCH", "64"))
-        if causal_cache and qkv.shape[0] <= k8_max and _ops.attn_decode_supported(nh, nkv, hd) \
+        if not act_q and causal_cache and qkv.shape[0] <= k8_max and _ops.attn_decode_supported(nh, nkv, hd) \
                 and not os.environ.get("Q100_NO_K8"):
             return _ops.attn_decode(qkv, rc[0], rc[1], position, kv.k, kv.v, nh, nkv, err_flag)
         q = _ops.rope_kv_decode(qkv, rc[0], rc[1], position, kv.k, kv.v, nh, nkv, err_flag)
-        att = F.scaled_dot_product_attention(q, kv.k, kv.v, attn_mask=attention_mask, enable_gqa=nh != nkv)
+        k, v = kv.k, kv.v
+        if act_q:
+            # W8A8 / W4A4: the cache holds what the reference's cache holds (unquantised K / V); Q and the kv heads pass
+            # their per-(head, token) quantisers on the way into the product, as in forward() (identity when off)
+            q = attn.qkt_matmul.quant_x1(q)
+            k = attn.qkt_matmul.quant_x2(k)
+            v = attn.pv_matmul.quant_x2(v)
+        att = F.scaled_dot_product_attention(q, k, v, attn_mask=attention_mask, enable_gqa=nh != nkv)
         return att.reshape(q.shape[0], nh * hd)
 
     def decode_step_fused(self, x, residual, kv: "StaticKV", position, attention_mask, err_flag=None,
@@ -481,12 +490,18 @@ class QuantLlamaDecoderLayer(nn.Module):
         ``past_key_value=kv`` (tests/test_block.py compares the two); what moves is where the residual add
         happens: this block receives the previous block's MLP output ``x`` and residual stream ``residual``
         separately, adds them inside its first norm kernel (K4), and returns its own (mlp_out, residual)
-        pair.  Returns None when the block cannot take this route (activation quantisation on, dense
-        weights, non-SiLU activation, fp32): the caller then uses ``forward``."""
+        pair.  With activation quantisation on (W8A8 / W4A4) the GEMMs are K3c launches (the per-token quantisation
+        as their prologue) and the attention core is SDPA on the fake-quantised Q / K / V.  Returns None when the
+        block cannot take this route (a quantiser of its own on the softmax output, dense weights, non-SiLU
+        activation, fp32): the caller then uses ``forward``."""
         attn, mlp = self.self_attn, self.mlp
-        if x.dtype not in (torch.float16, torch.bfloat16) or attn.use_act_quant or mlp.act_fn is not F.silu \
+        if x.dtype not in (torch.float16, torch.bfloat16) or mlp.act_fn is not F.silu \
                 or self.input_layernorm.use_temporary_parameter or self.post_attention_layernorm.use_temporary_parameter:
             return None
+        if attn.use_act_quant or attn.qkt_matmul.use_act_quant or attn.pv_matmul.use_act_quant:
+            pq = attn.pv_matmul.x1_quantizer
+            if (attn.pv_matmul.use_act_quant and pq.n_bits < 16 and pq.enable) or torch.is_grad_enabled():
+                return None
         bsz = x.shape[0]
         nh = attn.num_heads // attn.tp_world
         nkv = max(attn.num_key_value_heads // attn.tp_world, 1)

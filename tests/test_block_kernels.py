@@ -435,3 +435,54 @@ def test_fast_attention_with_act_quant_matches_reference_formulation(wbits, abit
     assert not attn.sdpa_route()
     attn.pv_matmul.x1_quantizer.change_n_bits(16)
     assert attn.sdpa_route()
+
+
+@pytest.mark.parametrize("wbits,abits,group,bsz", [(8, 8, None, 1), (8, 8, None, 3), (4, 4, None, 2), (4, 8, 128, 16)])
+def test_block_fused_decode_step_with_act_quant(wbits, abits, group, bsz):
+    """decode_step_fused with activation quantisation on (W8A8 / W4A4: K3c GEMMs, SDPA on the fake-quantised Q / K / V)
+    against forward() in the reference formulation on the same static cache.  The cache rows are bit-identical (same
+    GEMM, rotary bit-exact); the block output differs by the attention core's rounding pushed through per-token
+    quantisers (tolerance of test_fast_attention_with_act_quant_matches_reference_formulation)."""
+    from q100 import llama as QL
+    from models.int_llama_layer import StaticKV
+    dev, dtype = torch.device("cuda:0"), torch.float16
+    cfg = QL.LlamaCfg(512, 1024, 8, 2, 1, 64)
+    layer = QL.build_block(cfg, QL.random_block_weights(cfg, 0, 13, dev, dtype), QL.quant_args(wbits, group, abits))
+    assert layer.self_attn.use_act_quant
+    max_len, ctx = 32, 9
+    g = torch.Generator(device=dev).manual_seed(bsz)
+    k0 = torch.randn(bsz, 2, ctx, 64, generator=g, device=dev).to(dtype)
+    v0 = torch.randn(bsz, 2, ctx, 64, generator=g, device=dev).to(dtype)
+    kvs = []
+    for _ in range(3):
+        kv = StaticKV(bsz, 2, max_len, 64, dtype, dev)
+        kv.k[:, :, :ctx] = k0
+        kv.v[:, :, :ctx] = v0
+        kvs.append(kv)
+    x = torch.randn(bsz, 1, 512, generator=g, device=dev).to(dtype)
+    res = torch.randn(bsz, 1, 512, generator=g, device=dev).to(dtype)
+    pos = torch.tensor([[ctx]], device=dev)
+    slots = torch.arange(max_len, device=dev).view(1, 1, 1, max_len)
+    mask = torch.where(slots <= ctx, 0.0, torch.finfo(dtype).min).to(dtype).expand(bsz, 1, 1, max_len)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    with torch.no_grad():
+        layer.self_attn.fast_attention = False
+        ref = layer(res + x, attention_mask=mask, position_ids=pos, past_key_value=kvs[0], use_cache=False)[0]
+        layer.self_attn.fast_attention = True
+        mod = layer(res + x, attention_mask=mask, position_ids=pos, past_key_value=kvs[1], use_cache=False)[0]
+        out = layer.decode_step_fused(x, res, kvs[2], pos, mask, err, causal_cache=True)
+    assert out is not None, "the fused decode step must take W8A8 / W4A4 blocks"
+    d, h1 = out
+    got = (h1 + d).view_as(ref)
+    assert int(err.item()) == 0
+    for kv in kvs[1:]:
+        assert torch.equal(kv.k, kvs[0].k) and torch.equal(kv.v, kvs[0].v)
+    tol = 1e-2 if abits == 8 else 6e-2
+    for name, t in (("forward + SDPA", mod), ("decode_step_fused", got)):
+        e = ((t.float() - ref.float()).norm() / ref.float().norm()).item()
+        assert e <= tol, (name, e)
+
+    # a quantiser of its own on the softmax output: the fused route declines, forward() keeps the reference formulation
+    layer.self_attn.pv_matmul.x1_quantizer.change_n_bits(8)
+    with torch.no_grad():
+        assert layer.decode_step_fused(x, res, kvs[2], pos, mask, err, causal_cache=True) is None
