@@ -498,10 +498,11 @@ class QuantLlamaDecoderLayer(nn.Module):
         if x.dtype not in (torch.float16, torch.bfloat16) or mlp.act_fn is not F.silu \
                 or self.input_layernorm.use_temporary_parameter or self.post_attention_layernorm.use_temporary_parameter:
             return None
-        if attn.use_act_quant or attn.qkt_matmul.use_act_quant or attn.pv_matmul.use_act_quant:
-            pq = attn.pv_matmul.x1_quantizer
-            if (attn.pv_matmul.use_act_quant and pq.n_bits < 16 and pq.enable) or torch.is_grad_enabled():
-                return None
+        # (the quantisation state lives on the QuantLinear / QuantMatMul modules: like the reference's, this layer's
+        # set_quant_state does not touch the attention module's own ``use_act_quant`` attribute)
+        pq = attn.pv_matmul.x1_quantizer
+        if attn.pv_matmul.use_act_quant and pq.n_bits < 16 and pq.enable:
+            return None
         bsz = x.shape[0]
         nh = attn.num_heads // attn.tp_world
         nkv = max(attn.num_key_value_heads // attn.tp_world, 1)
@@ -588,6 +589,16 @@ class QuantLlamaDecoderLayer(nn.Module):
         return h2.view(x.shape), None
 
     # ------------------------------------------------------------------ quantisation state
+    def act_quant_active(self) -> bool:
+        """True when any linear or attention matmul of the block fake-quantises its input (the state set_quant_state
+        leaves on the QuantLinear / QuantMatMul modules -- the attention module's own flag is not part of it)."""
+        for m in self.modules():
+            if isinstance(m, QuantLinear) and m.use_act_quant and not m.disable_input_quant:
+                return True
+            if isinstance(m, QuantMatMul) and m.use_act_quant:
+                return True
+        return False
+
     def _quant_linears(self):
         return [m for _, m in self.named_modules() if isinstance(m, QuantLinear)]
 

@@ -318,7 +318,7 @@ class GraphDecoder:
         xi = torch.zeros(B, I, dtype=dt, device=dev)
         for layer in m.layers:
             attn, mlp = layer.self_attn, layer.mlp
-            if attn.tp_world > 1 or attn.use_act_quant or mlp.act_fn is not F.silu \
+            if attn.tp_world > 1 or layer.act_quant_active() or mlp.act_fn is not F.silu \
                     or layer.input_layernorm.use_temporary_parameter or layer.post_attention_layernorm.use_temporary_parameter:
                 return None
             qkv = attn._qkv.packed((attn.q_proj, attn.k_proj, attn.v_proj), xh)

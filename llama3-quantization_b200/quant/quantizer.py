@@ -64,16 +64,18 @@ def fake_quant_backward(xg: torch.Tensor, gout: torch.Tensor, scale: torch.Tenso
         denom = 2 ** (n_bits - 1) - 1
         a_hi, a_lo = xmax_c.abs(), xmin_c.abs()
         s_raw = torch.max(a_hi, a_lo) / denom
-        live = ((s_raw >= CLIPMIN) & (s_raw <= 1e4)).to(xg.dtype)
-        g_abs = g_scale * live / denom
+        live = (s_raw >= CLIPMIN) & (s_raw <= 1e4)
+        # clamp's backward selects (where), it does not multiply: an overflowed 16-bit group sum (inf) behind a clamped
+        # scale must give 0, not inf * 0
+        g_abs = torch.where(live, g_scale, torch.zeros_like(g_scale)) / denom
         w_hi = (a_hi > a_lo).to(xg.dtype) + 0.5 * (a_hi == a_lo).to(xg.dtype)
         g_xmax_c = g_abs * w_hi * torch.sign(xmax_c)
         g_xmin_c = g_abs * (1.0 - w_hi) * torch.sign(xmin_c)
     else:
         denom = 2 ** n_bits - 1
         s_raw = (xmax_c - xmin_c) / denom
-        live = ((s_raw >= CLIPMIN) & (s_raw <= 1e4)).to(xg.dtype)
-        g_xmax_c = g_scale * live / denom
+        live = (s_raw >= CLIPMIN) & (s_raw <= 1e4)
+        g_xmax_c = torch.where(live, g_scale, torch.zeros_like(g_scale)) / denom       # see above
         g_xmin_c = -g_xmax_c
     grad_su = grad_sl = None
     if su is not None:

@@ -355,7 +355,7 @@ def test_fast_attention_with_act_quant_matches_reference_formulation(wbits, abit
     expansion) against the reference formulation of the same block -- prefill with a causal mask, then one decode
     step on a static cache.  The same fake-quantised tensors enter softmax(QK^T)V on both sides; what differs is the
     library kernel's online softmax against the fp32 softmax rounded to 16 bits.
-    (i) attention module with o_proj's input quantiser off (nothing discrete behind the core): a few 16-bit ulps of
+    (i) attention module with o_proj's input quantiser off (nothing discrete behind the core): <= 16 16-bit ulps of
     the largest output; (ii) the whole block with every quantiser on: a 1-ulp difference may flip codes of o_proj's
     and the MLP's per-token quantisers (one A4 step is 1/15 of a row's range), so the bound is on the relative
     Frobenius distance -- 1e-2 (A8) / 6e-2 (A4); a wrong mask or head mapping gives O(1)."""
@@ -366,7 +366,7 @@ def test_fast_attention_with_act_quant_matches_reference_formulation(wbits, abit
     args = QL.quant_args(wbits, group, abits)
     layer = QL.build_block(cfg, QL.random_block_weights(cfg, 0, 11, dev, dtype), args)
     attn = layer.self_attn
-    assert attn.use_act_quant and attn.qkt_matmul.use_act_quant
+    assert layer.act_quant_active() and attn.qkt_matmul.use_act_quant and attn.pv_matmul.use_act_quant
     g = torch.Generator(device=dev).manual_seed(3)
     T = 48
     x = torch.randn(2, T, 512, generator=g, device=dev).to(dtype)
@@ -391,13 +391,14 @@ def test_fast_attention_with_act_quant_matches_reference_formulation(wbits, abit
 
     # (i) the core alone
     attn.o_proj.use_act_quant = False
-    h = layer.input_layernorm(x)
+    with torch.no_grad():
+        h = layer.input_layernorm(x)
     ref, got = both(lambda: attn(h, attention_mask=mask, position_ids=pos)[0])
     attn.fast_attention = True
     with torch.no_grad():
         got_causal = attn(h, attention_mask=None, position_ids=pos)[0]        # what QuantLlamaModel.forward passes
-    assert rel_max(got, ref) <= 8 * _ulp(dtype), rel_max(got, ref)
-    assert rel_max(got_causal, ref) <= 8 * _ulp(dtype), rel_max(got_causal, ref)
+    assert rel_max(got, ref) <= 16 * _ulp(dtype), rel_max(got, ref)
+    assert rel_max(got_causal, ref) <= 16 * _ulp(dtype), rel_max(got_causal, ref)
     attn.o_proj.use_act_quant = True
 
     # (ii) the whole block, every quantiser on
@@ -419,10 +420,11 @@ def test_fast_attention_with_act_quant_matches_reference_formulation(wbits, abit
     slots = torch.arange(max_len, device=dev).view(1, 1, 1, max_len)
     m1 = torch.where(slots <= ctx, 0.0, torch.finfo(dtype).min).to(dtype).expand(bsz, 1, 1, max_len)
     attn.o_proj.use_act_quant = False
-    h1 = layer.input_layernorm(x1)
+    with torch.no_grad():
+        h1 = layer.input_layernorm(x1)
     it = iter(kvs)
     ref1, got1 = both(lambda: attn(h1, attention_mask=m1, position_ids=p1, past_key_value=next(it))[0])
-    assert rel_max(got1, ref1) <= 8 * _ulp(dtype), rel_max(got1, ref1)
+    assert rel_max(got1, ref1) <= 16 * _ulp(dtype), rel_max(got1, ref1)
     attn.o_proj.use_act_quant = True
     ref2, got2 = both(lambda: layer(x1, attention_mask=m1, position_ids=p1, past_key_value=next(it), use_cache=False)[0])
     assert rel_fro(got2, ref2) <= fro_tol, rel_fro(got2, ref2)
@@ -448,7 +450,7 @@ def test_block_fused_decode_step_with_act_quant(wbits, abits, group, bsz):
     dev, dtype = torch.device("cuda:0"), torch.float16
     cfg = QL.LlamaCfg(512, 1024, 8, 2, 1, 64)
     layer = QL.build_block(cfg, QL.random_block_weights(cfg, 0, 13, dev, dtype), QL.quant_args(wbits, group, abits))
-    assert layer.self_attn.use_act_quant
+    assert layer.act_quant_active() and layer.self_attn.pv_matmul.use_act_quant
     max_len, ctx = 32, 9
     g = torch.Generator(device=dev).manual_seed(bsz)
     k0 = torch.randn(bsz, 2, ctx, 64, generator=g, device=dev).to(dtype)

@@ -268,6 +268,9 @@ def test_backward_kernel_vs_op_by_op(dtype, n_bits, group):
         qmin, qmax = O.qrange(n_bits, nozp)
         want = fake_quant_backward(x.reshape(-1, group), go.reshape(-1, group), r.scales, r.zeros, up, low,
                                    n_bits, sym, qmin, qmax, True, lwc)
+        f32 = lambda t: None if t is None else t.float()                                    # noqa: E731
+        want32 = fake_quant_backward(x.float().reshape(-1, group), go.float().reshape(-1, group), f32(r.scales),
+                                     f32(r.zeros), f32(up), f32(low), n_bits, sym, qmin, qmax, True, lwc)
         got = q100.ops.quantize_backward(x, go, group, n_bits, sym, nozp, up, low, True, lwc)
         torch.cuda.synchronize()
         tag = f"sym={sym} nozp={nozp} lwc={lwc}"
@@ -277,8 +280,16 @@ def test_backward_kernel_vs_op_by_op(dtype, n_bits, group):
                 assert g_ is None, name + " " + tag
                 continue
             g64, w64 = g_.double(), w_.double()
-            assert torch.equal(g64.isnan(), w64.isnan()), f"{name} {tag}: NaN pattern differs"
-            g64, w64 = g64.nan_to_num(0.0), w64.nan_to_num(0.0)
+            # NaN: a NaN in a group makes every gradient of that group NaN (autograd through the reference op sequence
+            # does the same).  The 16-bit op-by-op form can ALSO lose a finite group to overflow (a clamped constant
+            # group sums gout * 1e4 past 65504: inf - inf between the max and the min share); the kernel accumulates
+            # in fp32 and keeps those -- the pattern it must reproduce is the one of the form evaluated in fp32.
+            n32 = {"grad_x": 0, "grad_up": 1, "grad_low": 2}[name]
+            nan_ref = want32[n32].reshape(w64.shape).isnan()
+            assert torch.equal(g64.isnan(), nan_ref), f"{name} {tag}: NaN pattern differs"
+            assert bool((w64.isnan() | ~nan_ref).all()), f"{name} {tag}: the 16-bit form is finite where fp32 is NaN"
+            skip = w64.isnan()
+            g64, w64 = torch.where(skip, 0.0, g64), torch.where(skip, 0.0, w64)
             err = (g64 - w64).abs()
             # 16-bit: torch rounds every product of the group sum to the storage type before adding, the kernel keeps
             # fp32 -- the reference's own noise scales with the largest term, not with the (cancelling) sum
