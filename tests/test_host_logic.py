@@ -161,3 +161,59 @@ def test_k8_route_conditions():
     assert not ops.attn_decode_supported(30, 8, 128)
     with pytest.raises(RuntimeError):
         ops.argmax_rows(torch.zeros(2, 16, dtype=torch.float16))                       # no CPU path
+
+
+@pytest.mark.parametrize("group,bits", [(128, 4), (256, 4), (64, 2)])
+def test_backward_form_nan_and_clamped_groups_fp16(group, bits):
+    """The op-by-op backward form against torch autograd through the reference op sequence in fp16, on the two cases a
+    plain tolerance check cannot see: (i) a group containing a NaN -- every gradient of the group is NaN on both sides;
+    (ii) a constant group (scale at its lower clamp, codes clamped): the 16-bit group sum of gout * (c - zp) overflows
+    to inf, and because clamp's backward SELECTS (where) instead of multiplying, autograd returns 0 there, not
+    inf * 0 = NaN.  K1b (fp32 inside) agrees with both: tests/test_parity_quant.py::test_backward_kernel_vs_op_by_op.
+    (W2 / W4 only: at 8 bits fp16 autograd through the reference sequence is NaN for EVERY group -- d(x/s)/ds = -(x/s)/s
+    exceeds 65504 -- which is why the reference calibrates in fp32 / under AMP.)"""
+    gen = torch.Generator().manual_seed(77 + bits + group)
+    rows, cols = 8, 1024
+    x = (torch.randn(rows, cols, generator=gen) * 0.05).half()
+    x[3, :group] = 0.25
+    x[6, group + 3] = float("nan")
+    go = torch.randn(rows, cols, generator=gen).half()
+    xr = x.clone().requires_grad_(True)
+    out, scale, zp = TP.fake_quant(xr, bits, group)
+    out.backward(go)
+    ref = xr.grad.reshape(-1, group)
+    gx, _, _ = fake_quant_backward(x.reshape(-1, group), go.reshape(-1, group), scale.detach(), zp.detach(), None, None,
+                                   bits, False, 0, 2 ** bits - 1, True, False)
+    per_row = cols // group
+    nan_group, const_group = 6 * per_row + 1, 3 * per_row
+    want_nan = torch.zeros_like(ref, dtype=torch.bool)
+    want_nan[nan_group] = True
+    assert torch.equal(ref.isnan(), want_nan)
+    assert torch.equal(gx.isnan(), want_nan)
+    assert float(ref[const_group].abs().max()) == 0.0 and float(gx[const_group].abs().max()) == 0.0
+    ok = ~want_nan
+    assert float((gx[ok].float() - ref[ok].float()).abs().max()) <= 4e-3 * float(ref[ok].float().abs().max())
+
+
+def test_act_quant_state_lives_on_the_quant_modules():
+    """Like the reference's (int_llama_layer.py:269-277), the decoder layer's set_quant_state walks the QuantLinear /
+    QuantMatMul modules and leaves the attention module's own ``use_act_quant`` attribute alone; every route decision of
+    the drop-in (SDPA route, fused decode step, chain) therefore reads the state from those modules."""
+    from q100 import llama as QL
+    cfg = QL.LlamaCfg(128, 256, 4, 2, 1, 64)
+    w = QL.random_block_weights(cfg, 0, 1, "cpu", torch.float32)
+    layer = QL.build_block(cfg, w, QL.quant_args(16, None, 8), quantize=False)
+    attn = layer.self_attn
+    assert attn.use_act_quant is False                      # not touched by the layer's set_quant_state
+    assert attn.qkt_matmul.use_act_quant and attn.pv_matmul.use_act_quant and attn.q_proj.use_act_quant
+    assert layer.act_quant_active()
+    assert not attn.sdpa_route()                            # fast_attention is off by default
+    attn.fast_attention = True
+    assert attn.sdpa_route()                                # p_quant_params are 16 bits: identity
+    attn.pv_matmul.x1_quantizer.change_n_bits(8)
+    assert not attn.sdpa_route()                            # a real quantiser on the softmax output: reference formulation
+    attn.pv_matmul.x1_quantizer.change_n_bits(16)
+    layer.set_quant_state(False, False)
+    assert not layer.act_quant_active() and attn.sdpa_route()
+    attn.set_quant_state(False, True)                       # the attention module's own call sets both
+    assert attn.use_act_quant and layer.act_quant_active()

@@ -127,14 +127,19 @@ def run(a, dev, rank=0, world=1):
         model.layers = all_layers
         out["ppl"] = {"ppl": ppl, "mean_nll": nll, "tokens": a.ppl_samples * a.seqlen, "blocks": ppl_layers}
         if a.ppl_ref and rank == 0:      # the single-GPU torch port on the full weights (rank 0; the others wait below)
-            ppl_r, nll_r, nll_o = _port_ppl(a, cfg, model, testenc, dev, dt, ppl_layers, model.lm_head,
-                                            order_noise=True)
-            out["ppl"].update({"ref_ppl": ppl_r, "ref_mean_nll": nll_r, "delta_mean_nll": nll - nll_r,
-                               "delta_ppl_rel": (ppl - ppl_r) / ppl_r,
-                               "delta_ppl_at_wikitext2_scale(6.1)": 6.1 * (ppl - ppl_r) / ppl_r,
-                               # the yardstick for abits < 16: the reference against ITSELF with every F.linear
-                               # accumulated by an fp32 GEMM and rounded once (oracle/llama_port.linear_fp32_once)
-                               "ref_vs_ref_fp32_gemm_delta_mean_nll": nll_r - nll_o})
+            try:                         # rank 0 only: a failure here must still reach the barrier the others wait at
+                ppl_r, nll_r, nll_o = _port_ppl(a, cfg, model, testenc, dev, dt, ppl_layers, model.lm_head,
+                                                order_noise=True)
+                out["ppl"].update({"ref_ppl": ppl_r, "ref_mean_nll": nll_r, "delta_mean_nll": nll - nll_r,
+                                   "delta_ppl_rel": (ppl - ppl_r) / ppl_r,
+                                   "delta_ppl_at_wikitext2_scale(6.1)": 6.1 * (ppl - ppl_r) / ppl_r,
+                                   # the yardstick for abits < 16: the reference against ITSELF with every F.linear
+                                   # accumulated by an fp32 GEMM and rounded once (oracle/llama_port.linear_fp32_once)
+                                   "ref_vs_ref_fp32_gemm_delta_mean_nll": nll_r - nll_o})
+            except Exception as ex:                                   # noqa: BLE001
+                import traceback
+                traceback.print_exc(file=sys.stderr)
+                out["ppl"]["ref_error"] = f"{type(ex).__name__}: {ex}"[:400]
         if world > 1:
             dist.barrier()
         for l in model.layers:
@@ -208,11 +213,16 @@ def _quant_head_rows(a, cfg, model, testenc, dev, dt, ppl_layers, n_layers, rank
             l.self_attn.fast_attention = True
         res["ppl"] = {"ppl": ppl, "mean_nll": nll}
         if a.ppl_ref and rank == 0:       # the port with the head fake-quantised by the reference's op sequence
-            import torch_port as TPo
-            head_fq = TPo.fake_quant(dense_head, a.wbits, hg)[0]
-            ppl_r, nll_r, _ = _port_ppl(a, cfg, model, testenc, dev, dt, ppl_layers, head_fq)
-            res["ppl"].update({"ref_ppl": ppl_r, "ref_mean_nll": nll_r, "delta_mean_nll": nll - nll_r})
-            del head_fq
+            try:                          # rank 0 only: see above
+                import torch_port as TPo
+                head_fq = TPo.fake_quant(dense_head, a.wbits, hg)[0]
+                ppl_r, nll_r, _ = _port_ppl(a, cfg, model, testenc, dev, dt, ppl_layers, head_fq)
+                res["ppl"].update({"ref_ppl": ppl_r, "ref_mean_nll": nll_r, "delta_mean_nll": nll - nll_r})
+                del head_fq
+            except Exception as ex:                                   # noqa: BLE001
+                import traceback
+                traceback.print_exc(file=sys.stderr)
+                res["ppl"]["ref_error"] = f"{type(ex).__name__}: {ex}"[:400]
         if world > 1:
             dist.barrier()
     del dense_head
