@@ -217,3 +217,36 @@ def test_act_quant_state_lives_on_the_quant_modules():
     assert not layer.act_quant_active() and attn.sdpa_route()
     attn.set_quant_state(False, True)                       # the attention module's own call sets both
     assert attn.use_act_quant and layer.act_quant_active()
+
+
+def test_product_never_touches_the_oracle_and_has_no_cpu_path():
+    """The oracle is test infrastructure: nothing under llama3-quantization_b200/ may import, name or execute it (only
+    tests/, __graft_entry__.smoke() and bench.py's checker / reference legs do), and a quantised call on CPU tensors
+    raises instead of falling back."""
+    import os
+    import re
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "llama3-quantization_b200")
+    pat = re.compile(r"\b(q100_oracle|torch_port|llama_port|make_golden|oracle)\b")
+    hits = []
+    for dp, _, fns in os.walk(root):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                path = os.path.join(dp, fn)
+                for i, line in enumerate(open(path, errors="ignore"), 1):
+                    if pat.search(line):
+                        hits.append(f"{os.path.relpath(path, root)}:{i}: {line.strip()}")
+    assert not hits, "\n".join(hits)
+
+    import q100
+    q = UniformAffineQuantizer(n_bits=4, per_channel_axes=[0], symmetric=False, dynamic_method="per_channel",
+                               group_size=128, shape=(8, 256))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        q(torch.randn(8, 256))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        q100.quantize_groupwise(torch.randn(8, 256), 128, 4)
+    lin = QuantLinear(nn.Linear(256, 8, bias=False), {"n_bits": 4, "per_channel_axes": [0], "symmetric": False,
+                                                      "dynamic_method": "per_channel", "group_size": 128},
+                      {"n_bits": 8, "per_channel_axes": [], "symmetric": False, "dynamic_method": "per_token"})
+    lin.set_quant_state(True, False)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        lin(torch.randn(2, 256))
